@@ -1,0 +1,147 @@
+"""PDBbind-shaped synthetic complexes (geometry option B).
+
+Produces exactly the tensors `EfficientMCAttModel.forward` takes (reference signature at
+FABind/fabind/models/att_model.py:170), laid out as the reference dataloader lays them out
+(FABind/fabind/utils/utils.py:328-365): per complex the nodes are
+``[glb_c | ligand atoms | glb_p | pocket residues]``; segment 0 = compound side, 1 = protein side;
+``mask`` marks the nodes that move between refinement iterations (compound side + glb_p);
+coordinates are divided by ``coordinate_scale`` (5 A).
+
+Residues sit on a jittered 5.2 A cubic lattice with a cavity at the origin, the ligand is a random
+walk of 1.5 A bonds inside the cavity; bonds = atom pairs closer than 1.7 A (both directions),
+LAS (local-atomic-structure) pairs = atom pairs closer than 2.7 A.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+
+@dataclass
+class ComplexBatch:
+    X: torch.Tensor            # [N, 1, 3] float32, normalised coordinates
+    H: torch.Tensor            # [N, embed] float32 node features
+    batch_id: torch.Tensor     # [N] int64, sorted
+    segment_id: torch.Tensor   # [N] bool (False compound side / True protein side)
+    mask: torch.Tensor         # [N] bool, nodes updated between iterations
+    is_global: torch.Tensor    # [N] bool
+    compound_edge_index: torch.Tensor  # [2, E_bond] int64, global node ids
+    LAS_edge_index: torch.Tensor       # [2, E_las] int64
+    X_LAS: torch.Tensor        # [N, 1, 3] float32 reference conformer (normalised), zero off-ligand
+    n_c: list                  # ligand atoms per complex
+    n_p: list                  # pocket residues per complex
+
+    def to(self, device):
+        kw = {}
+        for k, v in self.__dict__.items():
+            kw[k] = v.to(device) if torch.is_tensor(v) else v
+        return ComplexBatch(**kw)
+
+    def clone(self):
+        kw = {}
+        for k, v in self.__dict__.items():
+            kw[k] = v.clone() if torch.is_tensor(v) else list(v)
+        return ComplexBatch(**kw)
+
+    def forward_args(self):
+        """Positional/keyword arguments in the reference order (att_model.py:170)."""
+        return dict(X=self.X, H=self.H, batch_id=self.batch_id, segment_id=self.segment_id,
+                    mask=self.mask, is_global=self.is_global,
+                    compound_edge_index=self.compound_edge_index,
+                    LAS_edge_index=self.LAS_edge_index,
+                    batched_complex_coord_LAS=self.X_LAS, LAS_mask=None)
+
+
+def _one_complex(rng, n_c, n_p, spacing=5.2, jitter=1.0, cavity=6.0):
+    # residues: jittered lattice, cavity around the origin, keep the n_p closest
+    half = 2
+    while (2 * half + 1) ** 3 < 4 * n_p + 64:
+        half += 1
+    g = np.arange(-half, half + 1, dtype=np.float64) * spacing
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    pts = pts + rng.uniform(-jitter, jitter, size=pts.shape)
+    d = np.linalg.norm(pts, axis=1)
+    pts = pts[d > cavity]
+    d = d[d > cavity]
+    order = np.argsort(d, kind="stable")[:n_p]
+    order.sort()
+    prot = pts[order]
+    # ligand: random walk with 1.5 A steps kept inside the cavity
+    lig = np.zeros((n_c, 3))
+    for i in range(1, n_c):
+        for _ in range(64):
+            step = rng.normal(size=3)
+            step *= 1.5 / np.linalg.norm(step)
+            # branch off a random earlier atom now and then so the graph is not a pure chain
+            base = lig[i - 1] if rng.uniform() < 0.8 else lig[rng.integers(0, i)]
+            cand = base + step
+            if np.linalg.norm(cand) < cavity - 1.0 and (
+                    i < 2 or np.min(np.linalg.norm(lig[:i] - cand, axis=1)) > 1.1):
+                break
+        lig[i] = cand
+    dm = np.linalg.norm(lig[:, None] - lig[None], axis=-1)
+    np.fill_diagonal(dm, 1e9)
+    bonds = np.argwhere(dm < 1.7)
+    las = np.argwhere(dm < 2.7)
+    lig_ref = lig + rng.normal(scale=0.3, size=lig.shape)
+    return prot, lig, bonds, las, lig_ref
+
+
+def make_batch(n_complexes=1, n_c=30, n_p=200, embed=512, seed=0, coordinate_scale=5.0,
+               n_c_range=None, n_p_range=None, feature_std=0.1):
+    """Seeded batch; `n_c_range`/`n_p_range` = (lo, hi) inclusive draw ragged sizes."""
+    rng = np.random.default_rng(seed)
+    Xs, XL, Hs, bid, seg, msk, glb, bonds_all, las_all = [], [], [], [], [], [], [], [], []
+    ncs, nps = [], []
+    off = 0
+    for b in range(n_complexes):
+        nc = int(rng.integers(n_c_range[0], n_c_range[1] + 1)) if n_c_range else n_c
+        np_ = int(rng.integers(n_p_range[0], n_p_range[1] + 1)) if n_p_range else n_p
+        prot, lig, bonds, las, lig_ref = _one_complex(rng, nc, np_)
+        n = nc + np_ + 2
+        x = np.concatenate([np.zeros((1, 3)), lig, np.zeros((1, 3)), prot], 0)
+        xl = np.concatenate([np.zeros((1, 3)), lig_ref, np.zeros((1, 3)), np.zeros_like(prot)], 0)
+        Xs.append(x)
+        XL.append(xl)
+        Hs.append(rng.normal(scale=feature_std, size=(n, embed)))
+        bid.append(np.full(n, b))
+        s = np.zeros(n, dtype=bool)
+        s[nc + 1:] = True
+        seg.append(s)
+        m = np.zeros(n, dtype=bool)
+        m[:nc + 2] = True
+        msk.append(m)
+        g = np.zeros(n, dtype=bool)
+        g[0] = True
+        g[nc + 1] = True
+        glb.append(g)
+        bonds_all.append(bonds.T + 1 + off)
+        las_all.append(las.T + 1 + off)
+        ncs.append(nc)
+        nps.append(np_)
+        off += n
+    f32 = lambda a: torch.from_numpy(np.concatenate(a, 0)).float()
+    X = (f32(Xs) / coordinate_scale).unsqueeze(1).contiguous()
+    XLt = (f32(XL) / coordinate_scale).unsqueeze(1).contiguous()
+    cat_i = lambda a: torch.from_numpy(np.concatenate(a, 1).astype(np.int64)).contiguous()
+    return ComplexBatch(
+        X=X, H=f32(Hs).contiguous(),
+        batch_id=torch.from_numpy(np.concatenate(bid).astype(np.int64)),
+        segment_id=torch.from_numpy(np.concatenate(seg)),
+        mask=torch.from_numpy(np.concatenate(msk)),
+        is_global=torch.from_numpy(np.concatenate(glb)),
+        compound_edge_index=cat_i(bonds_all), LAS_edge_index=cat_i(las_all), X_LAS=XLt,
+        n_c=ncs, n_p=nps)
+
+
+def randomize_coord_heads(module, std=0.5, seed=1234):
+    """The reference initialises every coordinate head with xavier gain 0.001 (egnn.py:52,164), so
+    with seeded random weights coordinates barely move.  Parity tests overwrite those heads with
+    O(0.1) values so that clamps, the LAS step and the moving inter-edge set are exercised
+    (SURVEY.md section 8c)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith("coord_mlp.2.weight") or name.endswith("coord_mlp.linear2.weight"):
+                p.copy_(torch.randn(p.shape, generator=g) * std / (p.shape[1] ** 0.5) * 4.0)
+    return module

@@ -1,0 +1,93 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (dev container only).
+
+    python scripts/make_golden.py
+
+Each fixture stores the recipe (synthetic-batch arguments, deterministic-weight seed, key shapes)
+and the reference's outputs; inputs and weights are regenerated from the recipe by the tests
+(`fabind_b200.synthetic.make_batch`, `oracle.det_weights.det_state_dict`), so fixtures stay small.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims                      # noqa: E402
+from oracle.det_weights import det_state_dict     # noqa: E402
+from fabind_b200.synthetic import make_batch      # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (hidden, n_layers, n_iter, make_batch kwargs, weight seed, far_ligand)
+    "v1_h64_l2_it3_ragged": (64, 2, 3, dict(n_complexes=3, seed=1, n_c_range=(8, 30), n_p_range=(40, 90)), 11, False),
+    "v1_h128_l1_it1_cfg1": (128, 1, 1, dict(n_complexes=1, seed=0, n_c=30, n_p=200), 12, False),
+    "v1_h32_l1_it2_noedge": (32, 1, 2, dict(n_complexes=2, seed=3, n_c=6, n_p=30), 13, True),
+    "v1_h32_l1_it2_fallback": (32, 1, 2, dict(n_complexes=1, seed=4, n_c=5, n_p=24), 14, True),
+}
+
+
+def build_reference(mods, hidden, n_layers, n_iter, wseed):
+    args = ref_shims.published_args()
+    scale = args.coordinate_scale
+    m = mods.att_model.EfficientMCAttModel(
+        args, hidden, hidden, 1, n_edge_feats=0, n_layers=n_layers, n_iter=n_iter,
+        inter_cutoff=args.inter_cutoff, intra_cutoff=args.intra_cutoff,
+        normalize_coord=lambda x: x / scale, unnormalize_coord=lambda x: x * scale).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+    return m, shapes
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    mods = ref_shims.load_reference("v1")
+    for name, (hidden, L, IT, bkw, wseed, far) in CASES.items():
+        m, shapes = build_reference(mods, hidden, L, IT, wseed)
+        b = make_batch(embed=hidden, **bkw)
+        if far:  # push the first complex's ligand 100 A away: no inter edge -> fallback (att_model.py:85)
+            nc = b.n_c[0]
+            b.X[1:nc + 1] += 20.0
+        traces = []
+        hooks = []
+        gnn = m.gnn
+        last = {"it": -1}
+
+        def pre_hook(mod, inp):
+            last["it"] += 1
+        hooks.append(gnn.register_forward_pre_hook(pre_hook))
+        for i in range(L):
+            for kind in ("gcl", "att"):
+                def hk(mod, inp, out, tag=f"{kind}_{i}"):
+                    if last["it"] == IT - 1:
+                        traces.append((tag, out[0].detach().clone(), out[1].detach().clone()))
+                hooks.append(getattr(gnn, f"{kind}_{i}").register_forward_hook(hk))
+        edges = []
+        orig = m.extract_edges.forward
+
+        def rec(X, bid, seg, glb):
+            r = orig(X, bid, seg, glb)
+            edges.append((r[0].to(torch.int32).clone(), r[1].to(torch.int32).clone()))
+            return r
+        m.extract_edges.forward = rec
+        with torch.no_grad():
+            bb = b.clone()
+            X, H = m(**bb.forward_args())
+        for h in hooks:
+            h.remove()
+        torch.save({
+            "recipe": dict(hidden=hidden, n_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed,
+                           far_ligand=far, flavour="v1"),
+            "shapes": shapes,
+            "X": X.clone(), "H": H.clone(),
+            "edges": edges,
+            "trace_last_iter": traces,
+            "torch": torch.__version__,
+        }, os.path.join(OUT, name + ".pt"))
+        print(name, "X", tuple(X.shape), "moved", float((X - b.X).abs().max()),
+              "E_int", [int(e[1].shape[1]) for e in edges])
+
+
+if __name__ == "__main__":
+    main()
