@@ -1,0 +1,94 @@
+"""ctypes binding of libfabind_b200.so (C ABI declared in include/fabind_b200.h).
+
+The product path has NO fallback: if the shared library is missing or does not export the ABI this
+module raises, and every op raises on a negative return code.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfabind_b200.so")
+ABI_VERSION = 1
+
+ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "CUDA launch error", -4: "unsupported configuration"}
+
+
+class ModelParams(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("B", C.c_int32), ("Nc_tot", C.c_int32), ("P_total", C.c_int32),
+        ("hidden", C.c_int32), ("n_layers", C.c_int32), ("n_iter", C.c_int32), ("n_bond", C.c_int32),
+        ("n_las", C.c_int32), ("E_ctx", C.c_int32), ("cap_int", C.c_int32), ("bf16_mode", C.c_int32),
+        ("fb_atom", C.c_int32), ("fb_res", C.c_int32),
+        ("intra_cutoff", C.c_float), ("inter_cutoff", C.c_float), ("coord_clamp", C.c_float),
+        ("las_clamp", C.c_float), ("las_step", C.c_float),
+        ("X_in", C.c_void_p), ("H_in", C.c_void_p), ("X_las", C.c_void_p), ("bonds", C.c_void_p), ("las", C.c_void_p),
+        ("perm", C.c_void_p), ("inv", C.c_void_p), ("node_cplx", C.c_void_p), ("node_flags", C.c_void_p),
+        ("c_off", C.c_void_p), ("p_off", C.c_void_p), ("pair_base", C.c_void_p),
+        ("w32", C.c_void_p), ("w16", C.c_void_p),
+        ("ws_graph", C.c_void_p), ("ws_graph_bytes", C.c_size_t),
+        ("ws_main", C.c_void_p), ("ws_main_bytes", C.c_size_t),
+        ("X_out", C.c_void_p), ("H_out", C.c_void_p), ("stats", C.c_void_p),
+        ("trace_h", C.c_void_p), ("trace_x", C.c_void_p),
+    ]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int32), ("K1", C.c_int32),
+        ("A2", C.c_void_p), ("lda2", C.c_int32), ("K2", C.c_int32),
+        ("W", C.c_void_p), ("bias", C.c_void_p), ("act", C.c_int32),
+        ("res", C.c_void_p), ("ldres", C.c_int32),
+        ("C", C.c_void_p), ("ldc", C.c_int32),
+        ("Cb", C.c_void_p), ("ldcb", C.c_int32),
+        ("dotv", C.c_void_p), ("dot_out", C.c_void_p), ("dot_stride", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("m_dev", C.c_void_p),
+        ("bf16_mode", C.c_int32), ("force_simt", C.c_int32),
+    ]
+
+
+EXPORTS = {
+    "fb_abi_version": (C.c_int32, []),
+    "fb_weight_slot_count": (C.c_int32, [C.c_int32, C.c_int32]),
+    "fb_weight_slot_info": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32,
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fb_weight_arena_elems": (C.c_int64, [C.c_int32, C.c_int32]),
+    "fb_graph_workspace_bytes": (C.c_int64, [C.POINTER(ModelParams)]),
+    "fb_model_workspace_bytes": (C.c_int64, [C.POINTER(ModelParams)]),
+    "fb_graph_static": (C.c_int32, [C.POINTER(ModelParams), C.c_void_p]),
+    "fb_graph_ctx_count_ptr": (C.c_void_p, [C.POINTER(ModelParams)]),
+    "fb_model_forward": (C.c_int32, [C.POINTER(ModelParams), C.c_void_p]),
+    "fb_edges_ref_count": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p]),
+    "fb_edges_ref_fill": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                      C.c_float, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "fb_gemm": (C.c_int32, [C.POINTER(GemmParams), C.c_void_p]),
+    "fb_gemm_dot_tiles": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m fabind_b200.build` (nvcc, sm_100a). "
+            "fabind_b200 has no CPU or PyTorch fallback.")
+    l = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(l, name)   # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if l.fb_abi_version() != ABI_VERSION:
+        raise RuntimeError("libfabind_b200.so ABI version mismatch; rebuild")
+    _lib = l
+    return l
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"fabind_b200: {what} failed: {ERRORS.get(rc, rc)}")

@@ -1,0 +1,80 @@
+// Shared device helpers for the fabind_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define FB_OK 0
+#define FB_ERR_BAD_ARG (-1)
+#define FB_ERR_WORKSPACE (-2)
+#define FB_ERR_CUDA (-3)
+#define FB_ERR_UNSUPPORTED (-4)
+
+#define FB_ACT_NONE 0
+#define FB_ACT_SILU 1
+#define FB_ACT_RELU 2
+
+#define FB_CHECK_LAUNCH()                                   \
+  do {                                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return FB_ERR_CUDA;             \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+namespace fb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// SiLU as torch computes it: x / (1 + exp(-x))  (full-precision expf, no fast-math)
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == FB_ACT_SILU) return silu(x);
+  if (ACT == FB_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+__device__ __forceinline__ float apply_act_rt(float x, int act) {
+  if (act == FB_ACT_SILU) return silu(x);
+  if (act == FB_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+// element load/store with conversion (T = float or bf16)
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4-wide vector access on 4-aligned element offsets
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb2 = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb2.x, fb2.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+}  // namespace fb

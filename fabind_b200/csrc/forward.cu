@@ -1,0 +1,449 @@
+// Host-side orchestration of the docking stack: weight-arena layout, scratch planning and the launch
+// sequence of EfficientMCAttModel.forward.  No allocation, no synchronisation: everything is enqueued
+// on the caller's stream.
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fabind_b200.h"
+#include "gemm.h"
+#include "layers.h"
+
+namespace fb {
+
+constexpr int HD = 128;  // RowAttentionBlock: 4 heads x 32 channels (cross_att.py:98)
+
+// ------------------------------------------------------------------------------------------------
+// weight arena layout
+// ------------------------------------------------------------------------------------------------
+struct Slot { std::string name; int64_t rows, cols, off; };
+
+struct GclW { int64_t e1_rc, e1_rad, e1_b, e2_w, e2_b, c1_w, c1_b, c2_w, n1_w, n1_b, n2_w, n2_b; };
+struct AttW {
+  int64_t ca_c_w, ca_c_b, ca_p_w, ca_p_b, ca_p2_w, o_p_w, o_p_b, o_c_w, o_c_b;
+  int64_t tp1_w, tp1_b, tp2_w, tp2_b, tc1_w, tc1_b, tc2_w, tc2_b;
+  int64_t i32_p_w, i32_p_b, i32_c_w, i32_c_b, i32_o_w, i32_o_b;
+  int64_t pt1_w, pt1_b, pt2v, pt_c;
+  int64_t qk_w, qk_b, k_r, v_w, v_b, v_r, ac1_w, ac1_b, ac2_w, ac_u;
+};
+struct ModelW {
+  int64_t in_w, in_b, out_w, out_b, il_p_w, il_p_b, il_c_w, il_c_b, il_o_w, il_o_b, pb_w, pb_b;
+  std::vector<GclW> gcl;  // n_layers + 1 (last = out_layer)
+  std::vector<AttW> att;
+  int64_t total = 0;
+  std::vector<Slot> slots;
+};
+
+static void build_weights(int H, int L, ModelW& w) {
+  int64_t off = 0;
+  auto add = [&](const std::string& name, int64_t rows, int64_t cols) {
+    const int64_t o = off;
+    w.slots.push_back({name, rows, cols, o});
+    off += (rows * cols + 63) / 64 * 64;  // 256-byte aligned slots
+    return o;
+  };
+  w.in_w = add("in_w", H, H); w.in_b = add("in_b", 1, H);
+  w.out_w = add("out_w", H, H); w.out_b = add("out_b", 1, H);
+  w.il_p_w = add("il_p_w", H, H); w.il_p_b = add("il_p_b", 1, H);
+  w.il_c_w = add("il_c_w", H, H); w.il_c_b = add("il_c_b", 1, H);
+  w.il_o_w = add("il_o_w", H, H); w.il_o_b = add("il_o_b", 1, H);
+  w.pb_w = add("pb_w", 16 * L, H); w.pb_b = add("pb_b", 1, 16 * L);
+  for (int i = 0; i <= L; ++i) {
+    const std::string p = i < L ? "gcl" + std::to_string(i) + "." : std::string("out.");
+    GclW g;
+    g.e1_rc = add(p + "e1_rc", 2 * H, H); g.e1_rad = add(p + "e1_rad", 1, H); g.e1_b = add(p + "e1_b", 1, H);
+    g.e2_w = add(p + "e2_w", H, H); g.e2_b = add(p + "e2_b", 1, H);
+    g.c1_w = add(p + "c1_w", H, H); g.c1_b = add(p + "c1_b", 1, H); g.c2_w = add(p + "c2_w", 1, H);
+    g.n1_w = add(p + "n1_w", H, 2 * H); g.n1_b = add(p + "n1_b", 1, H);
+    g.n2_w = add(p + "n2_w", H, H); g.n2_b = add(p + "n2_b", 1, H);
+    w.gcl.push_back(g);
+  }
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "att" + std::to_string(i) + ".";
+    AttW a;
+    a.ca_c_w = add(p + "ca_c_w", 4 * HD, H); a.ca_c_b = add(p + "ca_c_b", 1, 4 * HD);
+    a.ca_p_w = add(p + "ca_p_w", 2 * HD, H); a.ca_p_b = add(p + "ca_p_b", 1, 2 * HD);
+    a.ca_p2_w = add(p + "ca_p2_w", 2 * HD, H);
+    a.o_p_w = add(p + "o_p_w", H, HD); a.o_p_b = add(p + "o_p_b", 1, H);
+    a.o_c_w = add(p + "o_c_w", H, HD); a.o_c_b = add(p + "o_c_b", 1, H);
+    a.tp1_w = add(p + "tp1_w", 2 * H, H); a.tp1_b = add(p + "tp1_b", 1, 2 * H);
+    a.tp2_w = add(p + "tp2_w", H, 2 * H); a.tp2_b = add(p + "tp2_b", 1, H);
+    a.tc1_w = add(p + "tc1_w", 2 * H, H); a.tc1_b = add(p + "tc1_b", 1, 2 * H);
+    a.tc2_w = add(p + "tc2_w", H, 2 * H); a.tc2_b = add(p + "tc2_b", 1, H);
+    a.i32_p_w = add(p + "i32_p_w", 32, H); a.i32_p_b = add(p + "i32_p_b", 1, 32);
+    a.i32_c_w = add(p + "i32_c_w", 32, H); a.i32_c_b = add(p + "i32_c_b", 1, 32);
+    a.i32_o_w = add(p + "i32_o_w", H, 32); a.i32_o_b = add(p + "i32_o_b", 1, H);
+    a.pt1_w = add(p + "pt1_w", 2 * H, H); a.pt1_b = add(p + "pt1_b", 1, 2 * H);
+    a.pt2v = add(p + "pt2v", 1, 2 * H); a.pt_c = add(p + "pt_c", 1, 1);
+    a.qk_w = add(p + "qk_w", 2 * H, H); a.qk_b = add(p + "qk_b", 1, 2 * H); a.k_r = add(p + "k_r", 1, H);
+    a.v_w = add(p + "v_w", H, H); a.v_b = add(p + "v_b", 1, H); a.v_r = add(p + "v_r", 1, H);
+    a.ac1_w = add(p + "ac1_w", H, H); a.ac1_b = add(p + "ac1_b", 1, H);
+    a.ac2_w = add(p + "ac2_w", 1, H); a.ac_u = add(p + "ac_u", 1, H);
+    w.att.push_back(a);
+  }
+  w.total = off;
+}
+
+static const ModelW& weights_for(int H, int L) {
+  static std::vector<std::pair<std::pair<int, int>, ModelW*>> cache;
+  for (auto& kv : cache)
+    if (kv.first.first == H && kv.first.second == L) return *kv.second;
+  ModelW* w = new ModelW();
+  build_weights(H, L, *w);
+  cache.push_back({{H, L}, w});
+  return *w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scratch arena (dry run = size query)
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  char* base; size_t cap; size_t off = 0; size_t peak = 0; bool dry; bool ok = true;
+  Arena(void* b, size_t c, bool d) : base((char*)b), cap(c), dry(d) {}
+  void* take(size_t bytes) {
+    const size_t a = (off + 255) / 256 * 256;
+    off = a + bytes;
+    if (off > peak) peak = off;
+    if (dry) return (void*)(uintptr_t)(a + 256);  // non-null fake
+    if (off > cap) { ok = false; return nullptr; }
+    return base + a;
+  }
+  template <typename T> T* get(size_t n) { return (T*)take(n * sizeof(T)); }
+};
+
+struct GraphBufs { GraphDev g; };
+
+static void plan_graph(const fb_model_params& p, Arena& a, GraphDev& g) {
+  g.N = p.N; g.B = p.B; g.Nc_tot = p.Nc_tot; g.n_bond = p.n_bond; g.n_las = p.n_las;
+  g.fb_atom = p.fb_atom; g.fb_res = p.fb_res;
+  g.perm = p.perm; g.inv = p.inv; g.node_cplx = p.node_cplx; g.node_flags = p.node_flags;
+  g.c_off = p.c_off; g.p_off = p.p_off; g.pair_base = p.pair_base;
+  g.bond_row = a.get<int>(p.n_bond + 1); g.bond_col = a.get<int>(p.n_bond + 1);
+  g.las_src = a.get<int>(p.n_las + 1); g.las_dst = a.get<int>(p.n_las + 1);
+  g.las_deg = a.get<int>(p.N); g.las_rowptr = a.get<int>(p.N + 1); g.las_csr_src = a.get<int>(p.n_las + 1);
+  g.ctx_deg = a.get<int>(p.N); g.ctx_rowptr = a.get<int>(p.N + 1);
+  g.int_deg = a.get<int>(p.N); g.int_rowptr = a.get<int>(p.N + 1);
+  g.int_fallback = a.get<int>(1);
+  g.xtmp = a.get<float>(3 * (size_t)p.N);
+}
+
+struct Bufs {
+  // edges
+  int *ctx_row, *ctx_col, *int_row, *int_col, *int_pair;
+  // coordinates
+  float *x_state, *xa, *xb, *xl;
+  // node features
+  float *Hin32, *h, *pc, *Pn, *CAc, *CAp, *CAp2, *pc32, *QK, *V32, *VC, *Hfin;
+  void *HinT, *hT, *agg, *T1, *O, *TH, *VT;
+  // pair
+  void *P0, *A0, *Zin; float *PBraw, *PB, *pb_dense, *dotU;
+  // edge
+  float *radc, *normc, *radi, *normi, *dotE; void *A1, *M;
+};
+
+static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
+  const size_t N = p.N, H = p.hidden, E = p.E_ctx > 0 ? p.E_ctx : 1, P = p.P_total, L = p.n_layers;
+  const size_t capI = p.cap_int > 0 ? p.cap_int : 2, capU = capI / 2 + 1;
+  const size_t TS = p.bf16_mode ? 2 : 4;
+  const size_t Nc = p.Nc_tot, Np = N - Nc;
+  const bool bf = p.bf16_mode;
+  const size_t tilesH = gemm_dot_tiles((int)H, (int)H, bf), tiles2H = gemm_dot_tiles((int)(2 * H), (int)H, bf);
+  b.ctx_row = a.get<int>(E); b.ctx_col = a.get<int>(E);
+  b.int_row = a.get<int>(capI); b.int_col = a.get<int>(capI); b.int_pair = a.get<int>(capI);
+  b.x_state = a.get<float>(3 * N); b.xa = a.get<float>(3 * N); b.xb = a.get<float>(3 * N); b.xl = a.get<float>(3 * N);
+  b.Hin32 = a.get<float>(N * H);
+  b.HinT = bf ? a.take(N * H * TS) : (void*)b.Hin32;
+  b.h = a.get<float>(N * H);
+  b.hT = bf ? a.take(N * H * TS) : (void*)b.h;
+  b.Hfin = a.get<float>(N * H);
+  b.pc = a.get<float>(N * H);
+  b.P0 = a.take(P * H * TS);
+  b.PB = a.get<float>(P * L * 8);
+  b.pb_dense = a.get<float>(P);
+  // per-sub-layer temporaries
+  b.Pn = a.get<float>(N * 2 * H);
+  b.radc = a.get<float>(E); b.normc = a.get<float>(p.B);
+  b.A1 = a.take(E * H * TS); b.M = a.take(E * H * TS);
+  b.dotE = a.get<float>(tilesH * E);
+  b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
+  b.CAc = a.get<float>((Nc + 1) * 4 * HD); b.CAp = a.get<float>((Np + 1) * 2 * HD); b.CAp2 = a.get<float>((Np + 1) * 2 * HD);
+  b.O = a.take(N * HD * TS); b.TH = a.take(N * 2 * H * TS);
+  b.pc32 = a.get<float>(N * 32);
+  b.Zin = a.take(capU * H * TS);
+  b.dotU = a.get<float>(tiles2H * capU);
+  b.radi = a.get<float>(capI); b.normi = a.get<float>(p.B);
+  b.QK = a.get<float>(N * 2 * H); b.V32 = a.get<float>(N * H);
+  b.VT = bf ? a.take(N * H * TS) : (void*)b.V32;
+  b.VC = a.get<float>(N * H);
+  // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
+  b.A0 = a.take(P * H * TS);
+  b.PBraw = a.get<float>(P * L * 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch sequence
+// ------------------------------------------------------------------------------------------------
+struct Run {
+  const fb_model_params& p;
+  const ModelW& w;
+  GraphDev g;
+  Bufs b;
+  cudaStream_t st;
+  bool bf;
+  int H, N, Nc, Np;
+  size_t TS;
+  int rc = FB_OK;
+
+  const void* W(int64_t off) const { return bf ? (const void*)((const bf16*)p.w16 + off) : (const void*)(p.w32 + off); }
+  const float* F(int64_t off) const { return p.w32 + off; }
+  void* at(void* base, size_t elem) const { return (char*)base + elem * TS; }
+  const void* at(const void* base, size_t elem) const { return (const char*)base + elem * TS; }
+  void chk(int r) { if (rc == FB_OK && r != FB_OK) rc = r; }
+
+  // C = act(A W^T + b) with the usual optional extras
+  void gemm(const void* A, int lda, int K, int64_t w_off, int Nout, int64_t b_off, int act, int M, float* C, int ldc,
+            void* Cb, int ldcb, const float* res = nullptr, int ldres = 0, const void* A2 = nullptr, int lda2 = 0,
+            int K2 = 0, int64_t dotv_off = -1, float* dot_out = nullptr, int dot_stride = 0, const int* m_dev = nullptr) {
+    if (M <= 0) return;
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.K1 = K; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
+    a.W = W(w_off); a.bias = b_off >= 0 ? F(b_off) : nullptr; a.act = act;
+    a.res = res; a.ldres = ldres; a.C = C; a.ldc = ldc;
+    a.Cb = bf ? Cb : nullptr; a.ldcb = ldcb;
+    if (!bf && Cb != nullptr && (void*)C != Cb) {  // fp32 mode: the typed output IS the fp32 output
+      if (C == nullptr) { a.C = (float*)Cb; a.ldc = ldcb; }
+    }
+    a.dotv = dotv_off >= 0 ? F(dotv_off) : nullptr; a.dot_out = dot_out; a.dot_stride = dot_stride;
+    a.M = M; a.N = Nout; a.m_dev = m_dev;
+    chk(gemm_launch(a, bf, st));
+  }
+
+  void run_gcl(const GclW& gw, const float* x_in, float* x_out, bool need_h) {
+    const int E = p.E_ctx;
+    chk(radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st));
+    gemm(b.hT, H, H, gw.e1_rc, 2 * H, -1, FB_ACT_NONE, N, b.Pn, 2 * H, nullptr, 0);
+    chk(gcl_edge_pre(E, H, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st));
+    gemm(b.A1, H, H, gw.e2_w, H, gw.e2_b, FB_ACT_SILU, E, nullptr, 0, b.M, H);
+    const int tiles = gemm_dot_tiles(H, H, bf);
+    gemm(b.M, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_SILU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
+    chk(gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st));
+    if (need_h) {
+      gemm(b.hT, H, H, gw.n1_w, H, gw.n1_b, FB_ACT_SILU, N, nullptr, 0, b.T1, H, nullptr, 0, b.agg, H, H);
+      gemm(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h, H, b.hT, H, b.h, H);
+    }
+  }
+
+  void run_att(const AttW& aw, int layer, const float* x_in, float* x_out) {
+    const size_t P = p.P_total;
+    float* hp = b.h + (size_t)Nc * H;              // protein-side rows
+    void* hTp = at(b.hT, (size_t)Nc * H);
+    // --- cross attention (cross_att.py:24-54) on the per-complex blocks
+    gemm(b.hT, H, H, aw.ca_c_w, 4 * HD, aw.ca_c_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0);
+    gemm(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0);
+    const float* CApv = b.CAp - (size_t)Nc * 2 * HD;  // virtual base indexed by internal node id
+    chk(row_attention(g, 1, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
+                      b.PB + (size_t)(layer * 2 + 0) * P * 4, b.O, HD, bf, st));
+    gemm(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
+    gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
+    const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
+    chk(row_attention(g, 0, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
+                      b.PB + (size_t)(layer * 2 + 1) * P * 4, b.O, HD, bf, st));
+    gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
+    // transitions (model_utils.py:171-175), residual
+    gemm(hTp, H, H, aw.tp1_w, 2 * H, aw.tp1_b, FB_ACT_RELU, Np, nullptr, 0, b.TH, 2 * H);
+    gemm(b.TH, 2 * H, 2 * H, aw.tp2_w, H, aw.tp2_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
+    gemm(b.hT, H, H, aw.tc1_w, 2 * H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, 2 * H);
+    gemm(b.TH, 2 * H, 2 * H, aw.tc2_w, H, aw.tc2_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
+    // 32-channel interaction projections (cross_att.py:22,51)
+    gemm(hTp, H, H, aw.i32_p_w, 32, aw.i32_p_b, FB_ACT_NONE, Np, b.pc32 + (size_t)Nc * 32, 32, nullptr, 0);
+    gemm(b.hT, H, H, aw.i32_c_w, 32, aw.i32_c_b, FB_ACT_NONE, Nc, b.pc32, 32, nullptr, 0);
+    // --- pair path on the unique inter pairs only
+    const int capU = p.cap_int / 2;
+    const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
+    chk(pair_zin(g, capU, H, b.P0, b.pc32, F(aw.i32_o_w), F(aw.i32_o_b), b.Zin, bf, st));
+    const int tiles2 = gemm_dot_tiles(2 * H, H, bf);
+    gemm(b.Zin, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0,
+         aw.pt2v, b.dotU, capU, u_dev);
+    chk(pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st));
+    // --- interfacial attention (egnn.py:186-252)
+    chk(radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st));
+    gemm(b.hT, H, H, aw.qk_w, 2 * H, aw.qk_b, FB_ACT_NONE, N, b.QK, 2 * H, nullptr, 0);
+    gemm(b.hT, H, H, aw.v_w, H, aw.v_b, FB_ACT_NONE, N, b.V32, H, b.VT, H);
+    gemm(b.VT, H, H, aw.ac1_w, H, -1, FB_ACT_NONE, N, b.VC, H, nullptr, 0);
+    chk(inter_attention(g, H, b.QK, b.V32, b.VC, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
+                        b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st));
+  }
+
+  void tap(int slot, const float* x) {
+    if (p.trace_h) cudaMemcpyAsync(p.trace_h + (size_t)slot * N * H, b.h, sizeof(float) * (size_t)N * H, cudaMemcpyDeviceToDevice, st);
+    if (p.trace_x) cudaMemcpyAsync(p.trace_x + (size_t)slot * N * 3, x, sizeof(float) * (size_t)N * 3, cudaMemcpyDeviceToDevice, st);
+  }
+
+  void forward() {
+    const size_t P = p.P_total;
+    chk(permute_in(g, p.H_in, p.X_in, p.X_las, H, b.Hin32, b.HinT, bf, b.x_state, b.xl, st));
+    // pair_embed0 = InteractionModule(H_p, H_c)  (att_model.py:198-206, model_utils.py:219-222)
+    gemm(b.HinT, H, H, w.il_c_w, H, w.il_c_b, FB_ACT_NONE, Nc, b.pc, H, nullptr, 0);
+    gemm(at(b.HinT, (size_t)Nc * H), H, H, w.il_p_w, H, w.il_p_b, FB_ACT_NONE, Np, b.pc + (size_t)Nc * H, H, nullptr, 0);
+    chk(pair_outer(g, (int)P, H, b.pc, b.A0, bf, st));
+    gemm(b.A0, H, H, w.il_o_w, H, w.il_o_b, FB_ACT_NONE, (int)P, nullptr, 0, b.P0, H);
+    // gated pair biases of all RowAttentionBlocks at once (pair0 is layer- and iteration-invariant in v1)
+    gemm(b.P0, H, H, w.pb_w, 16 * p.n_layers, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, 16 * p.n_layers, nullptr, 0);
+    chk(pair_bias_gate((int)P, p.n_layers, b.PBraw, b.PB, st));
+    // context graph: protein coordinates are reset every iteration, so it is built once
+    chk(graph_fill_ctx(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st));
+    for (int it = 0; it < p.n_iter; ++it) {
+      const bool last = it == p.n_iter - 1;
+      chk(graph_build_inter(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st));
+      if (p.stats) cudaMemcpyAsync(p.stats + it, g.int_rowptr + N, sizeof(int), cudaMemcpyDeviceToDevice, st);
+      gemm(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H);
+      const float* xc = b.x_state;
+      float* bufs[2] = {b.xa, b.xb};
+      int k = 0;
+      for (int l = 0; l < p.n_layers; ++l) {
+        run_gcl(w.gcl[l], xc, bufs[k], true); xc = bufs[k]; k ^= 1;
+        if (last) tap(2 * l, xc);
+        run_att(w.att[l], l, xc, bufs[k]); xc = bufs[k]; k ^= 1;
+        if (last) tap(2 * l + 1, xc);
+        chk(las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st)); xc = bufs[k]; k ^= 1;
+      }
+      // the out-layer node update and linear_out only matter on the last iteration
+      // (att_model.py:232: non-final iterations discard H)
+      run_gcl(w.gcl[p.n_layers], xc, bufs[k], last); xc = bufs[k];
+      if (last) {
+        gemm(b.hT, H, H, w.out_w, H, w.out_b, FB_ACT_NONE, N, b.Hfin, H, nullptr, 0);
+        chk(permute_out_h(g, b.Hfin, H, p.H_out, st));
+      }
+      chk(masked_update_x(g, b.x_state, xc, last ? p.X_out : nullptr, st));
+    }
+  }
+};
+
+}  // namespace fb
+
+using namespace fb;
+
+static bool params_ok(const fb_model_params* p) {
+  return p && p->N > 0 && p->B > 0 && p->hidden > 0 && (p->hidden % 4) == 0 && p->hidden <= 512 && p->n_layers >= 0 &&
+         p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot < p->N;
+}
+
+extern "C" {
+
+int32_t fb_abi_version(void) { return FB_ABI_VERSION; }
+
+int32_t fb_weight_slot_count(int32_t hidden, int32_t n_layers) { return (int32_t)weights_for(hidden, n_layers).slots.size(); }
+
+int32_t fb_weight_slot_info(int32_t hidden, int32_t n_layers, int32_t i, char* name, int32_t name_cap, int64_t* rows,
+                            int64_t* cols, int64_t* offset) {
+  const ModelW& w = weights_for(hidden, n_layers);
+  if (i < 0 || i >= (int)w.slots.size()) return FB_ERR_BAD_ARG;
+  const Slot& s = w.slots[i];
+  if (name && name_cap > 0) { std::strncpy(name, s.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (rows) *rows = s.rows;
+  if (cols) *cols = s.cols;
+  if (offset) *offset = s.off;
+  return FB_OK;
+}
+
+int64_t fb_weight_arena_elems(int32_t hidden, int32_t n_layers) { return weights_for(hidden, n_layers).total; }
+
+int64_t fb_graph_workspace_bytes(const fb_model_params* p) {
+  if (!params_ok(p)) return FB_ERR_BAD_ARG;
+  Arena a(nullptr, 0, true);
+  GraphDev g;
+  plan_graph(*p, a, g);
+  return (int64_t)a.peak + 256;
+}
+
+int64_t fb_model_workspace_bytes(const fb_model_params* p) {
+  if (!params_ok(p)) return FB_ERR_BAD_ARG;
+  Arena a(nullptr, 0, true);
+  Bufs b;
+  plan_main(*p, a, b);
+  return (int64_t)a.peak + 256;
+}
+
+int32_t fb_graph_static(const fb_model_params* p, void* stream) {
+  if (!params_ok(p)) return FB_ERR_BAD_ARG;
+  Arena a(p->ws_graph, p->ws_graph_bytes, false);
+  GraphDev g;
+  plan_graph(*p, a, g);
+  if (!a.ok) return FB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = graph_prepare_static(g, (const long long*)p->bonds, (const long long*)p->las, st);
+  if (r != FB_OK) return r;
+  // the count pass needs coordinates in the internal order
+  r = permute_x(g, p->X_in, g.xtmp, st);
+  if (r != FB_OK) return r;
+  return graph_count_ctx(g, g.xtmp, p->intra_cutoff, p->inter_cutoff, st);
+}
+
+const int32_t* fb_graph_ctx_count_ptr(const fb_model_params* p) {
+  Arena a(p->ws_graph, p->ws_graph_bytes, false);
+  GraphDev g;
+  plan_graph(*p, a, g);
+  return g.ctx_rowptr + p->N;
+}
+
+int32_t fb_model_forward(const fb_model_params* p, void* stream) {
+  if (!params_ok(p) || p->E_ctx < 0) return FB_ERR_BAD_ARG;
+  const ModelW& w = weights_for(p->hidden, p->n_layers);
+  Run r{*p, w};
+  Arena ag(p->ws_graph, p->ws_graph_bytes, false);
+  plan_graph(*p, ag, r.g);
+  Arena am(p->ws_main, p->ws_main_bytes, false);
+  plan_main(*p, am, r.b);
+  if (!ag.ok || !am.ok) return FB_ERR_WORKSPACE;
+  r.g.ctx_row = r.b.ctx_row; r.g.ctx_col = r.b.ctx_col;
+  r.g.int_row = r.b.int_row; r.g.int_col = r.b.int_col; r.g.int_pair = r.b.int_pair;
+  r.st = (cudaStream_t)stream;
+  r.bf = p->bf16_mode != 0;
+  r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;
+  r.TS = r.bf ? 2 : 4;
+  r.forward();
+  if (r.rc != FB_OK) return r.rc;
+  return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_CUDA;
+}
+
+int32_t fb_edges_ref_count(int32_t N, const int32_t* cplx, const int32_t* off, const uint8_t* flags, const float* x,
+                           float intra, float inter, int32_t* ws, void* stream) {
+  int* deg = ws;
+  int* rowptr = ws + (size_t)4 * N;
+  int* fallback = rowptr + (size_t)4 * (N + 1);
+  return graph_ref_count(N, cplx, off, flags, x, intra, inter, deg, rowptr, fallback, (cudaStream_t)stream);
+}
+
+int32_t fb_edges_ref_fill(int32_t N, const int32_t* cplx, const int32_t* off, const uint8_t* flags, const float* x,
+                          float intra, float inter, int32_t* ws, const int32_t* counts_host, int64_t* ctx_out,
+                          int64_t* inter_out, void* stream) {
+  int* deg = ws;
+  int* rowptr = ws + (size_t)4 * N;
+  int* fallback = rowptr + (size_t)4 * (N + 1);
+  int* cat_base = fallback + 1;
+  const int host_base[4] = {0, counts_host[0], counts_host[0] + counts_host[1], 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemcpyAsync(cat_base, host_base, sizeof(host_base), cudaMemcpyHostToDevice, st);
+  const int e_ctx = counts_host[0] + counts_host[1] + counts_host[2];
+  return graph_ref_fill(N, cplx, off, flags, x, intra, inter, deg, rowptr, cat_base, fallback, counts_host[4],
+                        (long long*)ctx_out, e_ctx, (long long*)inter_out, counts_host[3], st);
+}
+
+int32_t fb_gemm(const fb_gemm_params* q, void* stream) {
+  if (!q) return FB_ERR_BAD_ARG;
+  GemmArgs a;
+  a.A = q->A; a.lda = q->lda; a.K1 = q->K1; a.A2 = q->A2; a.lda2 = q->lda2; a.K2 = q->K2; a.W = q->W;
+  a.bias = q->bias; a.act = q->act; a.res = q->res; a.ldres = q->ldres; a.C = q->C; a.ldc = q->ldc;
+  a.Cb = q->Cb; a.ldcb = q->ldcb; a.dotv = q->dotv; a.dot_out = q->dot_out; a.dot_stride = q->dot_stride;
+  a.M = q->M; a.N = q->N; a.m_dev = q->m_dev;
+  if (q->force_simt) return gemm_simt_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
+  return gemm_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
+}
+
+int32_t fb_gemm_dot_tiles(int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt) {
+  if (force_simt) return gemm_simt_dot_tiles(N);
+  return gemm_dot_tiles(N, K, bf16_mode != 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// Device-side description of one batch of complexes in the INTERNAL node order:
+// all compound-side nodes (glb_c + ligand atoms) of all complexes first, then all protein-side nodes
+// (glb_p + residues).  Inside a side, nodes keep the caller's order, so the dense per-complex blocks
+// the reference builds with to_dense_batch (egnn.py:260-265) are plain row slices here.
+#pragma once
+#include "common.cuh"
+
+namespace fb {
+
+struct GraphDev {
+  int N = 0, B = 0, Nc_tot = 0;
+  int n_bond = 0, n_las = 0;
+  int fb_atom = 0, fb_res = 0;          // internal ids used by the zero-inter-edge fallback
+  // layout (host-built, read-only on device)
+  const int* perm = nullptr;            // [N] internal -> caller index
+  const int* inv = nullptr;             // [N] caller -> internal index
+  const int* node_cplx = nullptr;       // [N]
+  const uint8_t* node_flags = nullptr;  // [N] bit0 protein side, bit1 global node, bit2 moves between iterations
+  const int* c_off = nullptr;           // [B+1] compound-side node range of each complex
+  const int* p_off = nullptr;           // [B+1] protein-side node range (absolute internal ids)
+  const int* pair_base = nullptr;       // [B+1] first pair row of each complex (pair = prot_local * nc1 + comp_local)
+  // bond / LAS lists in internal ids
+  int* bond_row = nullptr; int* bond_col = nullptr;   // [n_bond]
+  int* las_src = nullptr; int* las_dst = nullptr;     // [n_las]
+  int* las_deg = nullptr; int* las_rowptr = nullptr;  // [N], [N+1] CSR over destination
+  int* las_csr_src = nullptr;                         // [n_las]
+  // context graph (static per forward)
+  int* ctx_deg = nullptr; int* ctx_rowptr = nullptr;  // [N], [N+1]
+  int* ctx_row = nullptr; int* ctx_col = nullptr;     // [E_ctx]
+  // interface graph (rebuilt every refinement iteration)
+  int* int_deg = nullptr; int* int_rowptr = nullptr;  // [N], [N+1]
+  int* int_row = nullptr; int* int_col = nullptr; int* int_pair = nullptr;  // [cap_int]
+  int* int_fallback = nullptr;                        // [1]
+  float* xtmp = nullptr;                              // [3N] coordinates in internal order (count pass)
+};
+
+int graph_prepare_static(const GraphDev& g, const long long* bonds, const long long* las, cudaStream_t st);
+int graph_count_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st);
+int graph_fill_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st);
+int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st);
+
+int graph_ref_count(int N, const int* cplx, const int* off, const uint8_t* flags, const float* x,
+                    float intra, float inter, int* deg, int* rowptr, int* fallback, cudaStream_t st);
+int graph_ref_fill(int N, const int* cplx, const int* off, const uint8_t* flags, const float* x,
+                   float intra, float inter, int* deg, int* rowptr, const int* cat_base, int* fallback,
+                   int fallback_host, long long* ctx_out, int e_ctx, long long* int_out, int e_int,
+                   cudaStream_t st);
+
+}  // namespace fb

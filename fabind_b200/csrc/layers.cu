@@ -1,0 +1,552 @@
+// Non-GEMM kernels of the docking stack: edge geometry, gather-fused elementwise stages, CSR
+// segment reductions, per-complex row attention, interfacial attention and the LAS step.
+// All of them are HBM/L2-bound: one warp per row/edge, float4 accesses along the feature dimension.
+// T is the activation element type of the precision mode (float for fp32 parity mode, bf16 otherwise).
+#include "layers.h"
+
+namespace fb {
+
+static inline int warp_grid(long long n_rows) { return (int)((n_rows * 32 + 255) / 256); }
+
+// ------------------------------------------------------------------------------------------------
+// input / output permutation between the caller's node order and the internal type-sorted order
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ perm, int N, int D,
+                                   float* __restrict__ dst32, T* __restrict__ dstT) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* s = src + (size_t)perm[warp] * D;
+  for (int f = lane * 4; f < D; f += 128) {
+    const float4 v = ld4(s + f);
+    if (dst32) st4(dst32 + (size_t)warp * D + f, v);
+    if (dstT) st4(dstT + (size_t)warp * D + f, v);
+  }
+}
+
+__global__ void gather_x_kernel(const float* __restrict__ src, const int* __restrict__ perm, int N, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    const int s = perm[i];
+    dst[3 * i + 0] = src[3 * s + 0];
+    dst[3 * i + 1] = src[3 * s + 1];
+    dst[3 * i + 2] = src[3 * s + 2];
+  }
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ perm, int N, int D,
+                                    float* __restrict__ dst) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  float* d = dst + (size_t)perm[warp] * D;
+  for (int f = lane * 4; f < D; f += 128) st4(d + f, ld4(src + (size_t)warp * D + f));
+}
+
+// X[mask] = Z[mask]  (att_model.py:236,245) on the internal state, and optionally to the caller's X
+__global__ void masked_update_x_kernel(float* __restrict__ x_state, const float* __restrict__ z,
+                                       const uint8_t* __restrict__ flags, const int* __restrict__ perm, int N,
+                                       float* __restrict__ x_out_caller) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (flags[i] & 4) {
+    x_state[3 * i + 0] = z[3 * i + 0];
+    x_state[3 * i + 1] = z[3 * i + 1];
+    x_state[3 * i + 2] = z[3 * i + 2];
+  }
+  if (x_out_caller) {
+    const int d = perm[i];
+    x_out_caller[3 * d + 0] = x_state[3 * i + 0];
+    x_out_caller[3 * d + 1] = x_state[3 * i + 1];
+    x_out_caller[3 * d + 2] = x_state[3 * i + 2];
+  }
+}
+
+int permute_in(const GraphDev& g, const float* H_in, const float* X_in, const float* XL_in, int D, float* h32,
+               void* hT, bool bf16_mode, float* x, float* xl, cudaStream_t st) {
+  if (bf16_mode) gather_rows_kernel<bf16><<<warp_grid(g.N), 256, 0, st>>>(H_in, g.perm, g.N, D, h32, (bf16*)hT);
+  else gather_rows_kernel<float><<<warp_grid(g.N), 256, 0, st>>>(H_in, g.perm, g.N, D, h32, (float*)nullptr);
+  gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(X_in, g.perm, g.N, x);
+  if (XL_in) gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(XL_in, g.perm, g.N, xl);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int permute_x(const GraphDev& g, const float* X_in, float* x, cudaStream_t st) {
+  gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(X_in, g.perm, g.N, x);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int permute_out_h(const GraphDev& g, const float* h, int D, float* H_out, cudaStream_t st) {
+  scatter_rows_kernel<<<warp_grid(g.N), 256, 0, st>>>(h, g.perm, g.N, D, H_out);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int masked_update_x(const GraphDev& g, float* x_state, const float* z, float* x_out_caller, cudaStream_t st) {
+  masked_update_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(x_state, z, g.node_flags, g.perm, g.N, x_out_caller);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// coord2radial with per-sample normalisation (egnn.py:767-787): rad[e] = |x_row - x_col|^2 and
+// norm[b] = sqrt(sum over the edges of complex b of rad^2).  One CTA per complex; its edges are the
+// two contiguous CSR ranges that belong to its compound-side and protein-side rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) radial_kernel(GraphDev g, const int* __restrict__ rowptr,
+                                                     const int* __restrict__ erow, const int* __restrict__ ecol,
+                                                     const float* __restrict__ x, float* __restrict__ rad,
+                                                     float* __restrict__ norm) {
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int part = 0; part < 2; ++part) {
+    const int lo = part ? rowptr[g.p_off[b]] : rowptr[g.c_off[b]];
+    const int hi = part ? rowptr[g.p_off[b + 1]] : rowptr[g.c_off[b + 1]];
+    for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+      const int r = erow[e], c = ecol[e];
+      const float dx = x[3 * r] - x[3 * c], dy = x[3 * r + 1] - x[3 * c + 1], dz = x[3 * r + 2] - x[3 * c + 2];
+      const float d2 = dx * dx + dy * dy + dz * dz;
+      rad[e] = d2;
+      acc = fmaf(d2, d2, acc);
+    }
+  }
+  __shared__ float red[16];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) norm[b] = sqrtf(v);
+  }
+}
+
+int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* ecol, const float* x, float* rad,
+           float* norm, cudaStream_t st) {
+  radial_kernel<<<g.B, 512, 0, st>>>(g, rowptr, erow, ecol, x, rad, norm);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GCL edge stage 1 (egnn.py:75-81 with the first Linear split per node):
+//   A1[e,:] = SiLU(P[row, 0:H] + P[col, H:2H] + (rad[e]/norm[b]) * w_rad + b1)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, const int* __restrict__ ecol,
+                                    const int* __restrict__ node_cplx, const float* __restrict__ P,
+                                    const float* __restrict__ rad, const float* __restrict__ norm,
+                                    const float* __restrict__ w_rad, const float* __restrict__ b1, T* __restrict__ A1) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= E) return;
+  const int e = warp, r = erow[e], c = ecol[e];
+  const float rn = rad[e] / norm[node_cplx[r]];
+  const float* pr = P + (size_t)r * 2 * H;
+  const float* pc = P + (size_t)c * 2 * H + H;
+  for (int f = lane * 4; f < H; f += 128) {
+    const float4 a = ld4(pr + f), b = ld4(pc + f), w = ld4(w_rad + f), bb = ld4(b1 + f);
+    float4 o;
+    o.x = silu(a.x + b.x + fmaf(rn, w.x, bb.x));
+    o.y = silu(a.y + b.y + fmaf(rn, w.y, bb.y));
+    o.z = silu(a.z + b.z + fmaf(rn, w.z, bb.z));
+    o.w = silu(a.w + b.w + fmaf(rn, w.w, bb.w));
+    st4(A1 + (size_t)e * H + f, o);
+  }
+}
+
+int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node_cplx, const float* P,
+                 const float* rad, const float* norm, const float* w_rad, const float* b1, void* A1, bool bf16_mode,
+                 cudaStream_t st) {
+  if (E <= 0) return FB_OK;
+  if (bf16_mode) gcl_edge_pre_kernel<bf16><<<warp_grid(E), 256, 0, st>>>(E, H, erow, ecol, node_cplx, P, rad, norm, w_rad, b1, (bf16*)A1);
+  else gcl_edge_pre_kernel<float><<<warp_grid(E), 256, 0, st>>>(E, H, erow, ecol, node_cplx, P, rad, norm, w_rad, b1, (float*)A1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GCL node stage (egnn.py:97, 119-128): agg[r,:] = sum_e M[e,:]   (segment sum over the CSR row)
+//   x_out[r] = x[r] + clamp(mean_e (x[r]-x[col]) * s_e, +-cmax),  s_e = sum of the row-dot partials
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gcl_node_kernel(int N, int H, const int* __restrict__ rowptr, const int* __restrict__ ecol,
+                                const T* __restrict__ M, const float* __restrict__ dot, int dot_tiles, int dot_stride,
+                                const float* __restrict__ x, float cmax, T* __restrict__ agg, float* __restrict__ x_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const int r = warp, lo = rowptr[r], hi = rowptr[r + 1];
+  const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  // coordinate part: lanes over edges
+  for (int e = lo + lane; e < hi; e += 32) {
+    float s = 0.f;
+    for (int t = 0; t < dot_tiles; ++t) s += dot[(size_t)t * dot_stride + e];
+    const int c = ecol[e];
+    ax = fmaf(xr0 - x[3 * c], s, ax);
+    ay = fmaf(xr1 - x[3 * c + 1], s, ay);
+    az = fmaf(xr2 - x[3 * c + 2], s, az);
+  }
+  ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+  if (lane == 0) {
+    const float cnt = fmaxf((float)(hi - lo), 1.0f);
+    x_out[3 * r] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
+    x_out[3 * r + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
+    x_out[3 * r + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
+  }
+  if (agg == nullptr) return;
+  // feature part: lanes over features, edges sequential
+  for (int f0 = lane * 4; f0 < H; f0 += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = lo; e < hi; ++e) {
+      const float4 m = ld4(M + (size_t)e * H + f0);
+      acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+    }
+    st4(agg + (size_t)r * H + f0, acc);
+  }
+}
+
+int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
+             int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
+  if (bf16_mode) gcl_node_kernel<bf16><<<warp_grid(N), 256, 0, st>>>(N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
+  else gcl_node_kernel<float><<<warp_grid(N), 256, 0, st>>>(N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair embedding helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_complex(const int* __restrict__ pair_base, int B, int pair) {
+  int lo = 0, hi = B;  // pair_base[lo] <= pair < pair_base[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pair_base[mid] <= pair) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// A0[pair,:] = pp[prot,:] * cc[comp,:]   (InteractionModule outer product, model_utils.py:221)
+template <typename T>
+__global__ void pair_outer_kernel(GraphDev g, int P_total, int H, const float* __restrict__ pc /*[N,H]: c rows = linear_c, p rows = linear_p*/,
+                                  T* __restrict__ A0) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P_total) return;
+  const int pair = warp;
+  const int b = find_complex(g.pair_base, g.B, pair);
+  const int nc1 = g.c_off[b + 1] - g.c_off[b];
+  const int loc = pair - g.pair_base[b];
+  const int pi = g.p_off[b] + loc / nc1, ci = g.c_off[b] + loc % nc1;
+  for (int f = lane * 4; f < H; f += 128) {
+    const float4 a = ld4(pc + (size_t)pi * H + f), c = ld4(pc + (size_t)ci * H + f);
+    st4(A0 + (size_t)pair * H + f, make_float4(a.x * c.x, a.y * c.y, a.z * c.z, a.w * c.w));
+  }
+}
+
+int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0, bool bf16_mode, cudaStream_t st) {
+  if (bf16_mode) pair_outer_kernel<bf16><<<warp_grid(P_total), 256, 0, st>>>(g, P_total, H, pc, (bf16*)A0);
+  else pair_outer_kernel<float><<<warp_grid(P_total), 256, 0, st>>>(g, P_total, H, pc, (float*)A0);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// gated pair bias of every RowAttentionBlock (cross_att.py:125):  raw[pair, l*16 + blk*8 + {0..3 lin, 4..7 gate}]
+//  ->  PB[(l*2+blk) * P_total*4 + pair*4 + h] = lin * sigmoid(gate)
+__global__ void pair_bias_gate_kernel(int P_total, int L, const float* __restrict__ raw, float* __restrict__ PB) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)P_total * L * 8;
+  if (i >= total) return;
+  const int h = i & 3;
+  const int slab = (int)((i >> 2) % (L * 2));
+  const int pair = (int)(i / (8LL * L));
+  const float* rp = raw + (size_t)pair * L * 16 + slab * 8;
+  PB[(size_t)slab * P_total * 4 + (size_t)pair * 4 + h] = rp[h] * sigmoidf(rp[4 + h]);
+}
+
+int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t st) {
+  const long long total = (long long)P_total * L * 8;
+  pair_bias_gate_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(P_total, L, raw, PB);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RowAttentionBlock core (cross_att.py:118-134, model_utils.py:21-38,96-133): one warp per
+// (query node, head); keys are the nodes of the other side of the same complex.
+// 4 heads x 32 channels.  O[q, h*32+d] = sigmoid(G) * softmax_j(q.k_j/sqrt(32) + bias) v_j
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void row_attention_kernel(GraphDev g, int q_is_prot, const float* __restrict__ Q, int ldq,
+                                     const float* __restrict__ G, int ldg, const float* __restrict__ Kb, int ldk,
+                                     const float* __restrict__ Vb, int ldv, const float* __restrict__ PB,
+                                     T* __restrict__ O, int ldo) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n_q = q_is_prot ? (g.N - g.Nc_tot) : g.Nc_tot;
+  if (warp >= n_q * 4) return;
+  const int head = warp & 3;
+  const int qn = (q_is_prot ? g.Nc_tot : 0) + (warp >> 2);
+  const int b = g.node_cplx[qn];
+  const int c_lo = g.c_off[b], nc1 = g.c_off[b + 1] - c_lo, p_lo = g.p_off[b];
+  const int k_lo = q_is_prot ? c_lo : p_lo;
+  const int n_k = q_is_prot ? nc1 : (g.p_off[b + 1] - p_lo);
+  const int q_loc = qn - (q_is_prot ? p_lo : c_lo);
+  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  float q[32];
+  {
+    const float* qp = Q + (size_t)qn * ldq + head * 32;
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+      const float4 v = ld4(qp + d);
+      q[d] = v.x * scale; q[d + 1] = v.y * scale; q[d + 2] = v.z * scale; q[d + 3] = v.w * scale;
+    }
+  }
+  float m = -INFINITY, l = 0.f, acc = 0.f;  // acc: lane = channel d
+  for (int j0 = 0; j0 < n_k; j0 += 32) {
+    const int j = j0 + lane;
+    float s = -INFINITY;
+    if (j < n_k) {
+      const float* kp = Kb + (size_t)(k_lo + j) * ldk + head * 32;
+      float dsum = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; d += 4) {
+        const float4 kv = ld4(kp + d);
+        dsum = fmaf(q[d], kv.x, dsum); dsum = fmaf(q[d + 1], kv.y, dsum);
+        dsum = fmaf(q[d + 2], kv.z, dsum); dsum = fmaf(q[d + 3], kv.w, dsum);
+      }
+      const int pair = g.pair_base[b] + (q_is_prot ? (q_loc * nc1 + j) : (j * nc1 + q_loc));
+      s = dsum + PB[(size_t)pair * 4 + head];
+    }
+    const float m_new = fmaxf(m, warp_max(s));
+    const float corr = expf(m - m_new);  // m = -inf on the first chunk -> 0
+    const float p = j < n_k ? expf(s - m_new) : 0.f;
+    l = l * corr + warp_sum(p);
+    acc *= corr;
+    const int cnt = min(32, n_k - j0);
+    for (int jj = 0; jj < cnt; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, p, jj);
+      acc = fmaf(pj, Vb[(size_t)(k_lo + j0 + jj) * ldv + head * 32 + lane], acc);
+    }
+    m = m_new;
+  }
+  const float gate = sigmoidf(G[(size_t)qn * ldg + head * 32 + lane]);
+  O[(size_t)qn * ldo + head * 32 + lane] = from_f<T>(acc / l * gate);
+}
+
+int row_attention(const GraphDev& g, int q_is_prot, const float* Q, int ldq, const float* G, int ldg, const float* K,
+                  int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode, cudaStream_t st) {
+  const int n_q = q_is_prot ? (g.N - g.Nc_tot) : g.Nc_tot;
+  if (n_q <= 0) return FB_OK;
+  if (bf16_mode) row_attention_kernel<bf16><<<warp_grid((long long)n_q * 4), 256, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (bf16*)O, ldo);
+  else row_attention_kernel<float><<<warp_grid((long long)n_q * 4), 256, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (float*)O, ldo);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair path (v1: the updated pair embedding is only consumed through attn_bias_proj at the inter
+// pairs, egnn.py:208,291-294).  For every unique compound->protein inter edge u:
+//   Zin[u,:] = pair0[pair,:] + W_o32 (p32[prot,:] * c32[comp,:]) + b_o32      (cross_att.py:51)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pair_zin_kernel(GraphDev g, int H, const T* __restrict__ P0, const float* __restrict__ pc32 /*[N,32]*/,
+                                const float* __restrict__ Wo /*[H,32]*/, const float* __restrict__ bo, T* __restrict__ Zin) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int U = g.int_rowptr[g.Nc_tot];
+  if (warp >= U) return;
+  const int u = warp;
+  const int ci = g.int_row[u], pi = g.int_col[u], pair = g.int_pair[u];
+  const float t = pc32[(size_t)pi * 32 + lane] * pc32[(size_t)ci * 32 + lane];
+  for (int f0 = lane * 4; f0 < H; f0 += 128) {
+    float4 z = ld4(P0 + (size_t)pair * H + f0);
+    const float4 bb = ld4(bo + f0);
+    float o[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float tk = __shfl_sync(0xffffffffu, t, k);
+      o[0] = fmaf(Wo[(size_t)(f0 + 0) * 32 + k], tk, o[0]);
+      o[1] = fmaf(Wo[(size_t)(f0 + 1) * 32 + k], tk, o[1]);
+      o[2] = fmaf(Wo[(size_t)(f0 + 2) * 32 + k], tk, o[2]);
+      o[3] = fmaf(Wo[(size_t)(f0 + 3) * 32 + k], tk, o[3]);
+    }
+    z.x += o[0]; z.y += o[1]; z.z += o[2]; z.w += o[3];
+    st4(Zin + (size_t)u * H + f0, z);
+  }
+}
+
+int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, const float* Wo, const float* bo,
+             void* Zin, bool bf16_mode, cudaStream_t st) {
+  if (cap_u <= 0) return FB_OK;
+  if (bf16_mode) pair_zin_kernel<bf16><<<warp_grid(cap_u), 256, 0, st>>>(g, H, (const bf16*)P0, pc32, Wo, bo, (bf16*)Zin);
+  else pair_zin_kernel<float><<<warp_grid(cap_u), 256, 0, st>>>(g, H, (const float*)P0, pc32, Wo, bo, (float*)Zin);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// pb_dense[pair] = sum of row-dot partials + constant   (attn_bias_proj o pair_transition.linear_2)
+__global__ void pair_bias_finish_kernel(GraphDev g, const float* __restrict__ dot, int tiles, int stride, const float* __restrict__ cst,
+                                        float* __restrict__ pb_dense) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= g.int_rowptr[g.Nc_tot]) return;
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += dot[(size_t)t * stride + u];
+  pb_dense[g.int_pair[u]] = s + cst[0];
+}
+
+int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, int stride, const float* cst, float* pb_dense,
+                     cudaStream_t st) {
+  if (cap_u <= 0) return FB_OK;
+  pair_bias_finish_kernel<<<(cap_u + 255) / 256, 256, 0, st>>>(g, dot, tiles, stride, cst, pb_dense);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interfacial attention (egnn.py:186-252) with all first-layer GEMMs hoisted to node level:
+//   logit_e = Q[r].(K[c] + rn*k_r) + pb[pair]          alpha = softmax over the edges of row r
+//   h[r]   += sum_e alpha_e (V[c] + rn*v_r)
+//   x[r]   += clamp(sum_e alpha_e * s_e * (x[r]-x[c]), +-cmax),  s_e = w2 . SiLU(VC[c] + rn*u + b1)
+// One warp per row, single pass with an online softmax.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,2H]*/,
+                                       const float* __restrict__ V, const float* __restrict__ VC,
+                                       const float* __restrict__ k_r, const float* __restrict__ v_r,
+                                       const float* __restrict__ ac_u, const float* __restrict__ ac_b,
+                                       const float* __restrict__ ac_w2, const float* __restrict__ rad,
+                                       const float* __restrict__ norm, const float* __restrict__ pb_dense,
+                                       const float* __restrict__ x, float cmax, float* __restrict__ h, T* __restrict__ hT,
+                                       float* __restrict__ x_out, float* __restrict__ att_logit) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= g.N) return;
+  const int r = warp, lo = g.int_rowptr[r], hi = g.int_rowptr[r + 1];
+  const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
+  if (lo == hi) {
+    if (lane == 0) { x_out[3 * r] = xr0; x_out[3 * r + 1] = xr1; x_out[3 * r + 2] = xr2; }
+    return;
+  }
+  const float inv_norm = 1.0f / norm[g.node_cplx[r]];
+  // VEC float4 chunks per lane: features f = (i*32 + lane)*4
+  float4 q[VEC], acc[VEC];
+  float qkr = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int f = (i * 32 + lane) * 4;
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < H) {
+      q[i] = ld4(QK + (size_t)r * 2 * H + f);
+      const float4 kr = ld4(k_r + f);
+      qkr += q[i].x * kr.x + q[i].y * kr.y + q[i].z * kr.z + q[i].w * kr.w;
+    } else q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  qkr = warp_sum(qkr);
+  float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
+  for (int e = lo; e < hi; ++e) {
+    const int c = g.int_col[e];
+    const float rn = rad[e] * inv_norm;
+    float dot = 0.f, sdot = 0.f;
+    float4 vv[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int f = (i * 32 + lane) * 4;
+      if (f < H) {
+        const float4 kk = ld4(QK + (size_t)c * 2 * H + H + f);
+        dot += q[i].x * kk.x + q[i].y * kk.y + q[i].z * kk.z + q[i].w * kk.w;
+        const float4 vc = ld4(VC + (size_t)c * H + f), uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f);
+        sdot += w2.x * silu(vc.x + fmaf(rn, uu.x, bb.x)) + w2.y * silu(vc.y + fmaf(rn, uu.y, bb.y)) +
+                w2.z * silu(vc.z + fmaf(rn, uu.z, bb.z)) + w2.w * silu(vc.w + fmaf(rn, uu.w, bb.w));
+        const float4 v0 = ld4(V + (size_t)c * H + f), vr = ld4(v_r + f);
+        vv[i] = make_float4(fmaf(rn, vr.x, v0.x), fmaf(rn, vr.y, v0.y), fmaf(rn, vr.z, v0.z), fmaf(rn, vr.w, v0.w));
+      } else vv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    dot = warp_sum(dot);
+    sdot = warp_sum(sdot);
+    const float logit = dot + rn * qkr + pb_dense[g.int_pair[e]];
+    if (att_logit && lane == 0) att_logit[e] = logit;
+    const float m_new = fmaxf(m, logit);
+    const float corr = expf(m - m_new), p = expf(logit - m_new);
+    l = l * corr + p;
+    const float ps = p * sdot;
+    ax = ax * corr + ps * (xr0 - x[3 * c]);
+    ay = ay * corr + ps * (xr1 - x[3 * c + 1]);
+    az = az * corr + ps * (xr2 - x[3 * c + 2]);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      acc[i].x = fmaf(p, vv[i].x, acc[i].x * corr); acc[i].y = fmaf(p, vv[i].y, acc[i].y * corr);
+      acc[i].z = fmaf(p, vv[i].z, acc[i].z * corr); acc[i].w = fmaf(p, vv[i].w, acc[i].w * corr);
+    }
+    m = m_new;
+  }
+  const float il = 1.0f / l;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int f = (i * 32 + lane) * 4;
+    if (f < H) {
+      float4 hv = ld4(h + (size_t)r * H + f);
+      hv.x += acc[i].x * il; hv.y += acc[i].y * il; hv.z += acc[i].z * il; hv.w += acc[i].w * il;
+      st4(h + (size_t)r * H + f, hv);
+      if (hT) st4(hT + (size_t)r * H + f, hv);
+    }
+  }
+  if (lane == 0) {
+    x_out[3 * r] = xr0 + fminf(fmaxf(ax * il, -cmax), cmax);
+    x_out[3 * r + 1] = xr1 + fminf(fmaxf(ay * il, -cmax), cmax);
+    x_out[3 * r + 2] = xr2 + fminf(fmaxf(az * il, -cmax), cmax);
+  }
+  if (att_logit) {
+    __syncwarp();
+    for (int e = lo + lane; e < hi; e += 32) att_logit[e] = expf(att_logit[e] - m) * il;
+  }
+}
+
+int inter_attention(const GraphDev& g, int H, const float* QK, const float* V, const float* VC, const float* k_r,
+                    const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
+                    const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
+                    float* x_out, float* att, bool bf16_mode, cudaStream_t st) {
+  const int grid = warp_grid(g.N);
+#define FB_IA(T, VEC)                                                                                      \
+  inter_attention_kernel<T, VEC><<<grid, 256, 0, st>>>(g, H, QK, V, VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
+                                                       norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
+  if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
+  if (bf16_mode) {
+    if (H <= 128) FB_IA(bf16, 1); else if (H <= 256) FB_IA(bf16, 2); else FB_IA(bf16, 4);
+  } else {
+    if (H <= 128) FB_IA(float, 1); else if (H <= 256) FB_IA(float, 2); else FB_IA(float, 4);
+  }
+#undef FB_IA
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LAS constrained step (egnn.py:433-449): x_j += clamp(step * sum_{(i,j)} 4 (|xi-xj|^2 - |ri-rj|^2)(xi-xj), +-cl)
+// ------------------------------------------------------------------------------------------------
+__global__ void las_step_kernel(GraphDev g, const float* __restrict__ x, const float* __restrict__ xref, float step,
+                                float cl, float* __restrict__ x_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.N) return;
+  const float xj0 = x[3 * j], xj1 = x[3 * j + 1], xj2 = x[3 * j + 2];
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+  const int lo = g.las_rowptr[j], hi = g.las_rowptr[j + 1];
+  if (lo < hi) {
+    const float rj0 = xref[3 * j], rj1 = xref[3 * j + 1], rj2 = xref[3 * j + 2];
+    for (int e = lo; e < hi; ++e) {
+      const int i = g.las_csr_src[e];
+      const float a0 = x[3 * i] - xj0, a1 = x[3 * i + 1] - xj1, a2 = x[3 * i + 2] - xj2;
+      const float b0 = xref[3 * i] - rj0, b1 = xref[3 * i + 1] - rj1, b2 = xref[3 * i + 2] - rj2;
+      const float cur = a0 * a0 + a1 * a1 + a2 * a2, ref = b0 * b0 + b1 * b1 + b2 * b2;
+      const float k = 2.0f * (cur - ref);
+      d0 += k * (2.0f * a0); d1 += k * (2.0f * a1); d2 += k * (2.0f * a2);
+    }
+  }
+  x_out[3 * j] = xj0 + fminf(fmaxf(d0 * step, -cl), cl);
+  x_out[3 * j + 1] = xj1 + fminf(fmaxf(d1 * step, -cl), cl);
+  x_out[3 * j + 2] = xj2 + fminf(fmaxf(d2 * step, -cl), cl);
+}
+
+int las_step(const GraphDev& g, const float* x, const float* xref, float step, float cl, float* x_out, cudaStream_t st) {
+  las_step_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(g, x, xref, step, cl, x_out);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+}  // namespace fb

@@ -1,0 +1,32 @@
+#pragma once
+#include "graph.h"
+
+namespace fb {
+
+int permute_in(const GraphDev& g, const float* H_in, const float* X_in, const float* XL_in, int D, float* h32,
+               void* hT, bool bf16_mode, float* x, float* xl, cudaStream_t st);
+int permute_x(const GraphDev& g, const float* X_in, float* x, cudaStream_t st);
+int permute_out_h(const GraphDev& g, const float* h, int D, float* H_out, cudaStream_t st);
+int masked_update_x(const GraphDev& g, float* x_state, const float* z, float* x_out_caller, cudaStream_t st);
+int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* ecol, const float* x, float* rad,
+           float* norm, cudaStream_t st);
+int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node_cplx, const float* P,
+                 const float* rad, const float* norm, const float* w_rad, const float* b1, void* A1, bool bf16_mode,
+                 cudaStream_t st);
+int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
+             int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st);
+int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0, bool bf16_mode, cudaStream_t st);
+int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t st);
+int row_attention(const GraphDev& g, int q_is_prot, const float* Q, int ldq, const float* G, int ldg, const float* K,
+                  int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode, cudaStream_t st);
+int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, const float* Wo, const float* bo,
+             void* Zin, bool bf16_mode, cudaStream_t st);
+int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, int stride, const float* cst, float* pb_dense,
+                     cudaStream_t st);
+int inter_attention(const GraphDev& g, int H, const float* QK, const float* V, const float* VC, const float* k_r,
+                    const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
+                    const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
+                    float* x_out, float* att, bool bf16_mode, cudaStream_t st);
+int las_step(const GraphDev& g, const float* x, const float* xref, float step, float cl, float* x_out, cudaStream_t st);
+
+}  // namespace fb

@@ -1,0 +1,81 @@
+"""Host-side batch layout: the internal, type-sorted node order of libfabind_b200 (see csrc/graph.h).
+
+All compound-side nodes (segment 0: glb_c + ligand atoms) of all complexes come first, then all
+protein-side nodes (segment 1: glb_p + residues); inside a side nodes keep the caller's order, so the
+dense per-complex blocks the reference builds with to_dense_batch (egnn.py:260-265) are row slices.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+
+@dataclass
+class Layout:
+    N: int
+    B: int
+    Nc_tot: int
+    P_total: int
+    cap_int: int
+    fb_atom: int
+    fb_res: int
+    blob: torch.Tensor      # int32 device blob holding perm|inv|node_cplx|c_off|p_off|pair_base
+    flags: torch.Tensor     # uint8 device [N]
+    offs: dict              # name -> element offset in blob
+    orig_off: np.ndarray    # [B+1] node offsets in caller order
+    n_c: np.ndarray
+    n_p: np.ndarray
+
+    def ptr(self, name):
+        return self.blob.data_ptr() + 4 * self.offs[name]
+
+
+def build_layout(batch_id, segment_id, is_global, mask, device):
+    bid = batch_id.detach().cpu().numpy().astype(np.int64)
+    seg = segment_id.detach().cpu().numpy().astype(bool)
+    glb = is_global.detach().cpu().numpy().astype(bool)
+    msk = mask.detach().cpu().numpy().astype(bool)
+    N = bid.shape[0]
+    if N == 0:
+        raise ValueError("empty batch")
+    if np.any(np.diff(bid) < 0):
+        raise ValueError("batch_id must be sorted (as torch_geometric batches are)")
+    B = int(bid[-1]) + 1
+    counts = np.bincount(bid, minlength=B)
+    if np.any(counts == 0):
+        raise ValueError("every complex id in [0, B) must own at least one node")
+    orig_off = np.concatenate([[0], np.cumsum(counts)])
+    c_idx = np.nonzero(~seg)[0]
+    p_idx = np.nonzero(seg)[0]
+    perm = np.concatenate([c_idx, p_idx]).astype(np.int32)
+    inv = np.empty(N, dtype=np.int32)
+    inv[perm] = np.arange(N, dtype=np.int32)
+    nc1 = np.bincount(bid[c_idx], minlength=B)
+    np1 = np.bincount(bid[p_idx], minlength=B)
+    if np.any(nc1 == 0) or np.any(np1 == 0):
+        raise ValueError("every complex needs compound-side and protein-side nodes")
+    Nc_tot = int(nc1.sum())
+    c_off = np.concatenate([[0], np.cumsum(nc1)]).astype(np.int32)
+    p_off = (Nc_tot + np.concatenate([[0], np.cumsum(np1)])).astype(np.int32)
+    pair_base = np.concatenate([[0], np.cumsum(nc1 * np1)]).astype(np.int32)
+    node_cplx = bid[perm].astype(np.int32)
+    flags = (seg[perm].astype(np.uint8) | (glb[perm].astype(np.uint8) << 1) | (msk[perm].astype(np.uint8) << 2))
+    n_c = np.bincount(bid[(~seg) & (~glb)], minlength=B)
+    n_p = np.bincount(bid[seg & (~glb)], minlength=B)
+    cap_int = max(2, int(2 * (n_c * n_p).sum()))
+    # zero-inter-edge fallback pair (att_model.py:85-86): first non-global compound / protein node of complex 0
+    c0 = [i for i in range(c_off[0], c_off[1]) if not (flags[i] & 2)]
+    p0 = [i for i in range(p_off[0], p_off[1]) if not (flags[i] & 2)]
+    fb_atom = c0[0] if c0 else -1
+    fb_res = p0[0] if p0 else -1
+    parts = dict(perm=perm, inv=inv, node_cplx=node_cplx, c_off=c_off, p_off=p_off, pair_base=pair_base)
+    offs, cur, chunks = {}, 0, []
+    for k, v in parts.items():
+        offs[k] = cur
+        pad = (-len(v)) % 4
+        chunks.append(np.concatenate([v, np.zeros(pad, np.int32)]))
+        cur += len(v) + pad
+    blob = torch.from_numpy(np.concatenate(chunks)).to(device, non_blocking=True)
+    flags_t = torch.from_numpy(flags).to(device, non_blocking=True)
+    return Layout(N=N, B=B, Nc_tot=Nc_tot, P_total=int(pair_base[-1]), cap_int=cap_int, fb_atom=int(fb_atom),
+                  fb_res=int(fb_res), blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p)

@@ -1,0 +1,119 @@
+"""Thin runtime around the C ABI: weight-arena cache, scratch cache, parameter-struct assembly."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .layout import build_layout
+from .weights import pack_state_dict
+
+_scratch = {}
+
+
+def _scratch_buf(device, tag, nbytes):
+    key = (device, tag)
+    t = _scratch.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+        _scratch[key] = t
+    return t
+
+
+def current_stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class PackedWeights:
+    """fp32 (and bf16) weight arenas on the device, re-packed when any parameter changes."""
+
+    def __init__(self):
+        self.key = None
+        self.w32 = None
+        self.w16 = None
+
+    def get(self, module, hidden, n_layers, device, want_bf16):
+        params = list(module.parameters())
+        key = (device, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        if key != self.key:
+            arena = pack_state_dict(module.state_dict(), hidden, n_layers)
+            self.w32 = arena.to(device)
+            self.w16 = None
+            self.key = key
+        if want_bf16 and self.w16 is None:
+            self.w16 = self.w32.to(torch.bfloat16)
+        return self.w32, self.w16
+
+
+def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, bonds, las, X_las, cfg, bf16, trace=False):
+    """Runs fb_graph_static + fb_model_forward.  X is updated in place (reference att_model.py:236,245).
+    Returns (H_out, stats[int32 n_iter device tensor])."""
+    l = _lib.lib()
+    dev = X.device
+    if dev.type != "cuda":
+        raise RuntimeError("fabind_b200 runs on CUDA tensors only (no CPU fallback)")
+    N = X.shape[0]
+    hidden = cfg["hidden"]
+    xv = X.view(N, 3)
+    if not (xv.is_contiguous() and xv.dtype == torch.float32):
+        raise ValueError("X must be a contiguous float32 [N,1,3] tensor")
+    Hc = H.detach().to(torch.float32).contiguous()
+    if Hc.shape != (N, hidden):
+        raise ValueError(f"H must be [N, {hidden}]")
+    xl = X_las.detach().reshape(N, 3).to(torch.float32).contiguous()
+    bonds = bonds.detach().to(torch.int64).contiguous()
+    las = las.detach().to(torch.int64).contiguous()
+    lay = build_layout(batch_id, segment_id, is_global, mask, dev)
+    w32, w16 = packed.get(module, hidden, cfg["n_layers"], dev, bf16)
+    H_out = torch.empty((N, hidden), dtype=torch.float32, device=dev)
+    stats = torch.zeros(cfg["n_iter"], dtype=torch.int32, device=dev)
+
+    p = _lib.ModelParams()
+    p.N, p.B, p.Nc_tot, p.P_total = lay.N, lay.B, lay.Nc_tot, lay.P_total
+    p.hidden, p.n_layers, p.n_iter = hidden, cfg["n_layers"], cfg["n_iter"]
+    p.n_bond, p.n_las = bonds.shape[1], las.shape[1]
+    p.E_ctx, p.cap_int, p.bf16_mode = 0, lay.cap_int, 1 if bf16 else 0
+    p.fb_atom, p.fb_res = lay.fb_atom, lay.fb_res
+    p.intra_cutoff, p.inter_cutoff = cfg["intra_cutoff"], cfg["inter_cutoff"]
+    p.coord_clamp, p.las_clamp, p.las_step = cfg["coord_clamp"], cfg["las_clamp"], cfg["las_step"]
+    p.X_in, p.H_in, p.X_las = xv.data_ptr(), Hc.data_ptr(), xl.data_ptr()
+    p.bonds, p.las = bonds.data_ptr(), las.data_ptr()
+    for k in ("perm", "inv", "node_cplx", "c_off", "p_off", "pair_base"):
+        setattr(p, k, lay.ptr(k))
+    p.node_flags = lay.flags.data_ptr()
+    p.w32 = w32.data_ptr()
+    p.w16 = w16.data_ptr() if w16 is not None else None
+    p.X_out, p.H_out, p.stats = xv.data_ptr(), H_out.data_ptr(), stats.data_ptr()
+
+    tr = None
+    if trace:
+        nl = max(1, 2 * cfg["n_layers"])
+        tr = (torch.zeros((nl, N, hidden), dtype=torch.float32, device=dev),
+              torch.zeros((nl, N, 3), dtype=torch.float32, device=dev))
+        p.trace_h, p.trace_x = tr[0].data_ptr(), tr[1].data_ptr()
+    st = current_stream_ptr(dev)
+    gbytes = l.fb_graph_workspace_bytes(C.byref(p))
+    if gbytes < 0:
+        _lib.check(int(gbytes), "fb_graph_workspace_bytes")
+    wsg = _scratch_buf(dev, "graph", gbytes)
+    p.ws_graph, p.ws_graph_bytes = wsg.data_ptr(), wsg.numel()
+    _lib.check(l.fb_graph_static(C.byref(p), st), "fb_graph_static")
+    # one host read per forward: the number of context edges sizes the edge-level scratch
+    cnt_ptr = l.fb_graph_ctx_count_ptr(C.byref(p))
+    off = (cnt_ptr - wsg.data_ptr())
+    e_ctx = int(wsg[off:off + 4].view(torch.int32).item())
+    p.E_ctx = e_ctx
+    mbytes = l.fb_model_workspace_bytes(C.byref(p))
+    if mbytes < 0:
+        _lib.check(int(mbytes), "fb_model_workspace_bytes")
+    wsm = _scratch_buf(dev, "main", mbytes)
+    p.ws_main, p.ws_main_bytes = wsm.data_ptr(), wsm.numel()
+    _lib.check(l.fb_model_forward(C.byref(p), st), "fb_model_forward")
+    # keep every tensor the enqueued kernels read alive until the stream has consumed them
+    for t in (Hc, xl, bonds, las, lay.blob, lay.flags, w32, wsg, wsm):
+        t.record_stream(torch.cuda.current_stream(dev))
+    if tr is not None:
+        perm = lay.blob[lay.offs["perm"]:lay.offs["perm"] + N].long()
+        th = torch.empty_like(tr[0]); tx = torch.empty_like(tr[1])
+        th[:, perm] = tr[0]; tx[:, perm] = tr[1]
+        tr = (th, tx)
+    return H_out, stats, e_ctx, tr

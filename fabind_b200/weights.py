@@ -1,0 +1,122 @@
+"""Pack a reference-layout state_dict into the flat weight arena of libfabind_b200.
+
+The arena layout (slot names, shapes, offsets) is defined by the library (fb_weight_slot_*); this file
+only says which reference parameters each slot is derived from.  Derivations (all exact in real
+arithmetic, evaluated in float64 and rounded once):
+
+ * first Linear of every per-edge MLP is split into per-node blocks + a rank-1 radial column
+   (edge_mlp.0 at egnn.py:78, linear_kv at egnn.py:203-205 with its interleaved k/v rows);
+ * pair_transition.linear_2 followed by attn_bias_proj collapses to one vector (egnn.py:208,
+   cross_att.py:53): bias = wb.(W2 t + b2) + bb = (W2^T wb).t + (wb.b2 + bb);
+ * ac_u = coord_mlp.0.weight @ v_r (the radial column of v pushed through the next Linear).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+HD = 128
+
+
+def slots(hidden, n_layers):
+    l = _lib.lib()
+    out = []
+    name = C.create_string_buffer(64)
+    r, c, o = C.c_int64(), C.c_int64(), C.c_int64()
+    for i in range(l.fb_weight_slot_count(hidden, n_layers)):
+        _lib.check(l.fb_weight_slot_info(hidden, n_layers, i, name, 64, C.byref(r), C.byref(c), C.byref(o)),
+                   "fb_weight_slot_info")
+        out.append((name.value.decode(), r.value, c.value, o.value))
+    return out
+
+
+def _gcl(sd, p, H):
+    W1 = sd[p + "edge_mlp.0.weight"].double()
+    return {
+        "e1_rc": torch.cat([W1[:, :H], W1[:, H:2 * H]], 0), "e1_rad": W1[:, 2 * H], "e1_b": sd[p + "edge_mlp.0.bias"],
+        "e2_w": sd[p + "edge_mlp.2.weight"], "e2_b": sd[p + "edge_mlp.2.bias"],
+        "c1_w": sd[p + "coord_mlp.0.weight"], "c1_b": sd[p + "coord_mlp.0.bias"], "c2_w": sd[p + "coord_mlp.2.weight"][0],
+        "n1_w": sd[p + "node_mlp.0.weight"], "n1_b": sd[p + "node_mlp.0.bias"],
+        "n2_w": sd[p + "node_mlp.2.weight"], "n2_b": sd[p + "node_mlp.2.bias"],
+    }
+
+
+def _att(sd, p, H):
+    ca = p + "cross_attn_module."
+    pb, cb = ca + "p_attention_block.", ca + "c_attention_block."
+    z = lambda n: torch.zeros(n, dtype=torch.float64)
+    Wkv = sd[p + "linear_kv.weight"].double()
+    bkv = sd[p + "linear_kv.bias"].double()
+    W2 = sd[ca + "pair_transition.linear_2.weight"].double()
+    b2 = sd[ca + "pair_transition.linear_2.bias"].double()
+    wb = sd[p + "attn_bias_proj.weight"].double()[0]
+    bb = sd[p + "attn_bias_proj.bias"].double()[0]
+    ac1 = sd[p + "coord_mlp.0.weight"].double()
+    v_r = Wkv[1::2, 0]
+    return {
+        "ca_c_w": torch.cat([sd[pb + "mha.linear_k.weight"], sd[pb + "mha.linear_v.weight"],
+                             sd[cb + "mha.linear_q.weight"], sd[cb + "mha.linear_g.weight"]], 0),
+        "ca_c_b": torch.cat([z(3 * HD), sd[cb + "mha.linear_g.bias"].double()]),
+        "ca_p_w": torch.cat([sd[pb + "mha.linear_q.weight"], sd[pb + "mha.linear_g.weight"]], 0),
+        "ca_p_b": torch.cat([z(HD), sd[pb + "mha.linear_g.bias"].double()]),
+        "ca_p2_w": torch.cat([sd[cb + "mha.linear_k.weight"], sd[cb + "mha.linear_v.weight"]], 0),
+        "o_p_w": sd[pb + "mha.linear_o.weight"], "o_p_b": sd[pb + "mha.linear_o.bias"],
+        "o_c_w": sd[cb + "mha.linear_o.weight"], "o_c_b": sd[cb + "mha.linear_o.bias"],
+        "tp1_w": sd[ca + "p_transition.linear_1.weight"], "tp1_b": sd[ca + "p_transition.linear_1.bias"],
+        "tp2_w": sd[ca + "p_transition.linear_2.weight"], "tp2_b": sd[ca + "p_transition.linear_2.bias"],
+        "tc1_w": sd[ca + "c_transition.linear_1.weight"], "tc1_b": sd[ca + "c_transition.linear_1.bias"],
+        "tc2_w": sd[ca + "c_transition.linear_2.weight"], "tc2_b": sd[ca + "c_transition.linear_2.bias"],
+        "i32_p_w": sd[ca + "inter_layer.linear_p.weight"], "i32_p_b": sd[ca + "inter_layer.linear_p.bias"],
+        "i32_c_w": sd[ca + "inter_layer.linear_c.weight"], "i32_c_b": sd[ca + "inter_layer.linear_c.bias"],
+        "i32_o_w": sd[ca + "inter_layer.linear_out.weight"], "i32_o_b": sd[ca + "inter_layer.linear_out.bias"],
+        "pt1_w": sd[ca + "pair_transition.linear_1.weight"], "pt1_b": sd[ca + "pair_transition.linear_1.bias"],
+        "pt2v": W2.t() @ wb, "pt_c": (wb @ b2 + bb).reshape(1),
+        "qk_w": torch.cat([sd[p + "linear_q.weight"].double(), Wkv[0::2, 1:]], 0),
+        "qk_b": torch.cat([sd[p + "linear_q.bias"].double(), bkv[0::2]]), "k_r": Wkv[0::2, 0],
+        "v_w": Wkv[1::2, 1:], "v_b": bkv[1::2], "v_r": v_r,
+        "ac1_w": ac1, "ac1_b": sd[p + "coord_mlp.0.bias"], "ac2_w": sd[p + "coord_mlp.2.weight"][0],
+        "ac_u": ac1 @ v_r,
+    }
+
+
+def _top(sd, H, L):
+    rows, bias = [], []
+    for l in range(L):
+        ca = f"gnn.att_{l}.cross_attn_module."
+        for blk in ("p_attention_block.", "c_attention_block."):
+            rows += [sd[ca + blk + "linear.weight"], sd[ca + blk + "linear_g.weight"]]
+            bias += [sd[ca + blk + "linear.bias"], sd[ca + blk + "linear_g.bias"]]
+    d = {
+        "in_w": sd["gnn.linear_in.weight"], "in_b": sd["gnn.linear_in.bias"],
+        "out_w": sd["gnn.linear_out.weight"], "out_b": sd["gnn.linear_out.bias"],
+        "il_p_w": sd["inter_layer.linear_p.weight"], "il_p_b": sd["inter_layer.linear_p.bias"],
+        "il_c_w": sd["inter_layer.linear_c.weight"], "il_c_b": sd["inter_layer.linear_c.bias"],
+        "il_o_w": sd["inter_layer.linear_out.weight"], "il_o_b": sd["inter_layer.linear_out.bias"],
+    }
+    if L > 0:
+        d["pb_w"] = torch.cat(rows, 0)
+        d["pb_b"] = torch.cat(bias, 0)
+    return d
+
+
+def pack_state_dict(sd, hidden, n_layers):
+    """Returns the fp32 arena (CPU tensor) for a state_dict with the reference's v1 key names."""
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    l = _lib.lib()
+    arena = torch.zeros(l.fb_weight_arena_elems(hidden, n_layers), dtype=torch.float32)
+    groups = {"": _top(sd, hidden, n_layers)}
+    for i in range(n_layers):
+        groups[f"gcl{i}."] = _gcl(sd, f"gnn.gcl_{i}.", hidden)
+        groups[f"att{i}."] = _att(sd, f"gnn.att_{i}.", hidden)
+    groups["out."] = _gcl(sd, "gnn.out_layer.", hidden)
+    for name, rows, cols, off in slots(hidden, n_layers):
+        pre, _, base = name.rpartition(".")
+        pre = pre + "." if pre else ""
+        if rows * cols == 0:
+            continue
+        t = groups[pre][base]
+        if t.numel() != rows * cols or (t.dim() == 2 and tuple(t.shape) != (rows, cols)):
+            raise RuntimeError(f"weight slot {name}: library expects [{rows},{cols}], packer produced {tuple(t.shape)}")
+        arena[off:off + rows * cols] = t.reshape(-1).to(torch.float32)
+    return arena

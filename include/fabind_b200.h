@@ -1,0 +1,131 @@
+/* fabind_b200 -- C ABI of the B200 (sm_100a) implementation of FABind's iterative docking stack.
+ *
+ * The reference (QizhiPei/FABind) has no FFI/plugin interface: the path sits behind torch.nn.Module
+ * classes.  Each entry point below names the reference method(s) it replaces; the Python classes in
+ * fabind_b200/ (same names, constructor/forward signatures and state_dict keys as the reference)
+ * bind them through ctypes.  INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every device pointer is owned by the
+ * caller (PyTorch's caching allocator in practice); nothing here allocates device memory, synchronises
+ * the device or throws; work is enqueued on `stream` (a cudaStream_t passed as void*); the return value
+ * is 0 on success or a negative FB_ERR_* code.  Functions marked [host] touch no GPU state and work
+ * without a device.
+ */
+#ifndef FABIND_B200_H
+#define FABIND_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+
+/* One batch of complexes + model dimensions.  Node layout in caller order is the reference
+ * dataloader's [glb_c | atoms | glb_p | residues] per complex (utils/utils.py:328-335). */
+typedef struct fb_model_params {
+  /* ---- dimensions ---- */
+  int32_t N;          /* nodes in the batch */
+  int32_t B;          /* complexes */
+  int32_t Nc_tot;     /* compound-side nodes (glb_c + atoms) over the batch */
+  int32_t P_total;    /* sum over complexes of (n_p+1)*(n_c+1) dense pair rows */
+  int32_t hidden;     /* hidden_size == embed_size (512 docking stack, 128 pocket stage) */
+  int32_t n_layers;   /* MCAttEGNN depth (mean_layers) */
+  int32_t n_iter;     /* refinement iterations */
+  int32_t n_bond;     /* columns of compound_edge_index */
+  int32_t n_las;      /* columns of LAS_edge_index */
+  int32_t E_ctx;      /* context edges (bonds + geometric); read back after fb_graph_static */
+  int32_t cap_int;    /* capacity of the interface edge list: 2 * sum n_c*n_p (worst case) */
+  int32_t bf16_mode;  /* 0: fp32 parity mode (FFMA GEMMs); 1: bf16 operands, fp32 accumulate (tcgen05) */
+  int32_t fb_atom, fb_res; /* internal ids of the first ligand atom / first residue of complex 0 (att_model.py:85-86) */
+  /* ---- geometry constants, already divided by coordinate_scale ---- */
+  float intra_cutoff, inter_cutoff;   /* att_model.py:34-35 */
+  float coord_clamp;                  /* normalize_coord(10), egnn.py:378 */
+  float las_clamp, las_step;          /* normalize_coord(15), geometry_reg_step_size, egnn.py:447-448 */
+  /* ---- inputs, caller node order (device) ---- */
+  const float* X_in;        /* [N,3] */
+  const float* H_in;        /* [N,hidden] */
+  const float* X_las;       /* [N,3] batched_complex_coord_LAS */
+  const int64_t* bonds;     /* [2,n_bond] compound_edge_index */
+  const int64_t* las;       /* [2,n_las]  LAS_edge_index */
+  /* ---- layout, host-built by the binding (device, int32 unless noted) ---- */
+  const int32_t* perm;      /* [N] internal -> caller */
+  const int32_t* inv;       /* [N] caller -> internal */
+  const int32_t* node_cplx; /* [N] complex of each internal node */
+  const uint8_t* node_flags;/* [N] bit0 protein side, bit1 global, bit2 updated between iterations (mask) */
+  const int32_t* c_off;     /* [B+1] */
+  const int32_t* p_off;     /* [B+1] */
+  const int32_t* pair_base; /* [B+1] */
+  /* ---- weights: flat arenas laid out by fb_weight_slot_* ---- */
+  const float* w32;
+  const void* w16;          /* bf16 copy of the same arena (bf16_mode only) */
+  /* ---- scratch ---- */
+  void* ws_graph; size_t ws_graph_bytes;   /* >= fb_graph_workspace_bytes */
+  void* ws_main;  size_t ws_main_bytes;    /* >= fb_model_workspace_bytes */
+  /* ---- outputs, caller node order (device) ---- */
+  float* X_out;             /* [N,3]  (may alias X_in: the reference updates X in place, att_model.py:236) */
+  float* H_out;             /* [N,hidden] */
+  int32_t* stats;           /* optional [n_iter]: interface edges per iteration */
+  /* optional debug taps (INTERNAL node order): h and x after every gcl_i / att_i of the LAST iteration,
+   * slot 2*i = gcl_i, 2*i+1 = att_i (before the LAS step); [2*n_layers, N, hidden] and [2*n_layers, N, 3] */
+  float* trace_h; float* trace_x;
+} fb_model_params;
+
+/* [host] library identification */
+int32_t fb_abi_version(void);
+
+/* [host] weight arena layout for (hidden, n_layers): slot i has a name ("gcl0.e2_w", "att1.qk_w", ...),
+ * a [rows, cols] shape and an element offset into the arena.  fabind_b200/weights.py maps every slot to
+ * the reference state_dict keys it is derived from. */
+int32_t fb_weight_slot_count(int32_t hidden, int32_t n_layers);
+int32_t fb_weight_slot_info(int32_t hidden, int32_t n_layers, int32_t i, char* name, int32_t name_cap,
+                            int64_t* rows, int64_t* cols, int64_t* offset);
+int64_t fb_weight_arena_elems(int32_t hidden, int32_t n_layers);
+
+/* [host] scratch sizes */
+int64_t fb_graph_workspace_bytes(const fb_model_params* p);
+int64_t fb_model_workspace_bytes(const fb_model_params* p);
+
+/* Static part of the graph: converts bond/LAS lists to the internal order, builds the LAS CSR and counts
+ * the context edges.  After it (and a stream sync) the int at fb_graph_ctx_count_ptr(p) holds E_ctx.
+ * Replaces the context half of ComplexGraph.construct_edges (att_model.py:38-116). */
+int32_t fb_graph_static(const fb_model_params* p, void* stream);
+const int32_t* fb_graph_ctx_count_ptr(const fb_model_params* p);
+
+/* Full EfficientMCAttModel.forward (att_model.py:170-246; eval mode, refine='refine_coord'):
+ * pair_embed0, n_iter x {inter-edge rebuild, MCAttEGNN.forward (egnn.py:392-466)}, X[mask]=Z[mask]. */
+int32_t fb_model_forward(const fb_model_params* p, void* stream);
+
+/* ComplexGraph.construct_edges in the caller's node order, reference edge order (API parity).
+ * Two phases around one host read of counts[0..4] = {E_pp, E_glb_normal, E_glb_glb, E_inter, fallback}. */
+int32_t fb_edges_ref_count(int32_t N, const int32_t* cplx, const int32_t* off, const uint8_t* flags,
+                           const float* x, float intra, float inter, int32_t* ws /*[4N + 4(N+1) + 8]*/,
+                           void* stream);
+int32_t fb_edges_ref_fill(int32_t N, const int32_t* cplx, const int32_t* off, const uint8_t* flags,
+                          const float* x, float intra, float inter, int32_t* ws, const int32_t* counts_host,
+                          int64_t* ctx_out /*[2,E_ctx]*/, int64_t* inter_out /*[2,E_int]*/, void* stream);
+
+/* Generic fused linear layer used by the stack (unit-test surface):
+ * C = act([A|A2] W^T + bias) (+res).  bf16_mode selects operand type of A/A2/W/Cb. */
+typedef struct fb_gemm_params {
+  const void* A; int32_t lda; int32_t K1;
+  const void* A2; int32_t lda2; int32_t K2;
+  const void* W;
+  const float* bias; int32_t act;
+  const float* res; int32_t ldres;
+  float* C; int32_t ldc;
+  void* Cb; int32_t ldcb;
+  const float* dotv; float* dot_out; int32_t dot_stride;
+  int32_t M, N;
+  const int32_t* m_dev;
+  int32_t bf16_mode;
+  int32_t force_simt;   /* 1: never take the tcgen05 path */
+} fb_gemm_params;
+int32_t fb_gemm(const fb_gemm_params* g, void* stream);
+int32_t fb_gemm_dot_tiles(int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
