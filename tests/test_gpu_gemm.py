@@ -1,0 +1,110 @@
+"""Fused linear layer (fb_gemm) against torch on the same device, through the C ABI."""
+import ctypes as C
+
+import pytest
+import torch
+
+from fabind_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gemm(A, W, bias=None, act=0, res=None, A2=None, dotv=None, m_dev=None, bf16=False, want_cb=False,
+             force_simt=False):
+    l = _lib.lib()
+    dev = A.device
+    M, K1 = A.shape
+    K2 = A2.shape[1] if A2 is not None else 0
+    N = W.shape[0]
+    g = _lib.GemmParams()
+    dt = torch.bfloat16 if bf16 else torch.float32
+    Ad, Wd = A.to(dt).contiguous(), W.to(dt).contiguous()
+    A2d = A2.to(dt).contiguous() if A2 is not None else None
+    g.A, g.lda, g.K1 = Ad.data_ptr(), K1, K1
+    g.A2, g.lda2, g.K2 = (A2d.data_ptr() if A2d is not None else None), K2, K2
+    g.W = Wd.data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.act = act
+    g.res, g.ldres = (res.data_ptr() if res is not None else None), N
+    Cout = torch.full((M, N), float("nan"), device=dev)
+    g.C, g.ldc = Cout.data_ptr(), N
+    Cb = torch.zeros((M, N), dtype=dt, device=dev) if want_cb else None
+    g.Cb, g.ldcb = (Cb.data_ptr() if want_cb else None), N
+    tiles = l.fb_gemm_dot_tiles(N, K1 + K2, int(bf16), int(force_simt))
+    dot = torch.zeros((tiles, M), device=dev) if dotv is not None else None
+    g.dotv = dotv.data_ptr() if dotv is not None else None
+    g.dot_out = dot.data_ptr() if dot is not None else None
+    g.dot_stride = M
+    g.M, g.N = M, N
+    g.m_dev = m_dev.data_ptr() if m_dev is not None else None
+    g.bf16_mode, g.force_simt = int(bf16), int(force_simt)
+    _lib.check(l.fb_gemm(C.byref(g), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fb_gemm")
+    torch.cuda.synchronize()
+    return Cout, Cb, (dot.sum(0) if dot is not None else None)
+
+
+def ref_gemm(A, W, bias, act, res, A2, dotv, bf16):
+    if bf16:
+        A, W = A.to(torch.bfloat16).float(), W.to(torch.bfloat16).float()
+        A2 = A2.to(torch.bfloat16).float() if A2 is not None else None
+    Af = torch.cat([A, A2], 1) if A2 is not None else A
+    v = Af.double() @ W.double().t()
+    if bias is not None:
+        v = v + bias.double()
+    if act == 1:
+        v = torch.nn.functional.silu(v)
+    elif act == 2:
+        v = torch.relu(v)
+    if res is not None:
+        v = v + res.double()
+    d = (v * dotv.double()).sum(1) if dotv is not None else None
+    return v, d
+
+
+CASES = [
+    # M, N, K1, K2, act, bias, res, dot
+    (37, 64, 32, 0, 0, True, False, False),
+    (232, 512, 512, 0, 1, True, False, False),
+    (500, 1024, 512, 0, 2, True, False, True),
+    (300, 512, 512, 512, 1, True, False, False),
+    (129, 96, 48, 48, 0, False, True, False),
+    (1000, 32, 512, 0, 0, True, False, False),
+    (2824, 512, 512, 0, 1, True, False, True),
+    (64, 768, 128, 0, 0, True, True, False),
+]
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("case", CASES)
+def test_gemm_matches_torch(case, bf16):
+    M, N, K1, K2, act, has_b, has_r, has_d = case
+    torch.manual_seed(M * 7 + N)
+    dev = "cuda"
+    A = torch.randn(M, K1, device=dev)
+    A2 = torch.randn(M, K2, device=dev) if K2 else None
+    W = torch.randn(N, K1 + K2, device=dev) / (K1 + K2) ** 0.5
+    bias = torch.randn(N, device=dev) if has_b else None
+    res = torch.randn(M, N, device=dev) if has_r else None
+    dotv = torch.randn(N, device=dev) if has_d else None
+    Cout, Cb, dot = run_gemm(A, W, bias, act, res, A2, dotv, bf16=bf16, want_cb=True)
+    ref, dref = ref_gemm(A, W, bias, act, res, A2, dotv, bf16)
+    tol = 2e-5
+    err = float((Cout.double() - ref).abs().max() / ref.abs().max())
+    assert err < tol, f"C rel err {err}"
+    cb_tol = 1e-2 if bf16 else tol
+    assert float((Cb.double() - ref).abs().max() / ref.abs().max()) < cb_tol
+    if has_d:
+        derr = float((dot.double() - dref).abs().max() / dref.abs().max())
+        assert derr < 5e-5, f"dot rel err {derr}"
+
+
+def test_gemm_device_row_count():
+    dev = "cuda"
+    torch.manual_seed(0)
+    A = torch.randn(400, 64, device=dev)
+    W = torch.randn(128, 64, device=dev)
+    m_dev = torch.tensor([130], dtype=torch.int32, device=dev)
+    Cout, _, _ = run_gemm(A, W, m_dev=m_dev)
+    ref = A @ W.t()
+    assert torch.allclose(Cout[:130], ref[:130], atol=1e-4)
+    assert torch.isnan(Cout[130:]).all()   # rows beyond the device-side count are never written

@@ -1,0 +1,115 @@
+"""EfficientMCAttModel.forward on the GPU (through the C ABI) against
+ (a) the golden vectors produced by the unmodified reference, and
+ (b) the CPU oracle on larger, ragged batches at the published width.
+fp32 mode tolerance: 1e-4 relative (north star); bf16 mode reports its own, looser bound."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import fabind_oracle as orc
+from oracle import ref_shims
+from oracle.det_weights import det_state_dict
+from fabind_b200 import EfficientMCAttModel
+from fabind_b200.synthetic import make_batch
+from helpers import golden_files, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _model(hidden, L, IT, sd, precision="fp32"):
+    m = EfficientMCAttModel(ref_shims.published_args(), hidden, hidden, 1, n_layers=L, n_iter=IT,
+                            normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    m.precision = precision
+    return m
+
+
+def _run(m, b):
+    bc = b.to("cuda")
+    X, H = m(**bc.forward_args())
+    torch.cuda.synchronize()
+    return X.cpu(), H.cpu()
+
+
+def _log(name, rec):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "parity.jsonl"), "a") as f:
+        f.write(json.dumps(dict(test=name, **rec)) + "\n")
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-3])
+def test_golden_fp32(path):
+    g, r, b, sd, cfg = load_golden(path)
+    m = _model(r["hidden"], r["n_layers"], r["n_iter"], sd)
+    m.debug_trace = True
+    X, H = _run(m, b)
+    st = m.last_stats
+    e_int = st["inter_edges_per_iter"].cpu().tolist()
+    rec = dict(case=os.path.basename(path), e_int=e_int, e_int_ref=[int(e[1].shape[1]) for e in g["edges"]],
+               x_err=rel_err(X, g["X"]), h_err=rel_err(H, g["H"]))
+    th, tx = st["trace"]
+    for k, (tag, h_ref, x_ref) in enumerate(g["trace_last_iter"]):
+        rec[f"{tag}_h"] = rel_err(th[k].cpu(), h_ref)
+        rec[f"{tag}_x"] = rel_err(tx[k].cpu(), x_ref.squeeze(1))
+    _log("golden_fp32", rec)
+    nb = b.compound_edge_index.shape[1]
+    assert st["ctx_edges"] == int(g["edges"][0][0].shape[1]) + nb
+    assert e_int == rec["e_int_ref"]
+    assert rec["x_err"] < 1e-4 and rec["h_err"] < 1e-4, rec
+
+
+@pytest.mark.parametrize("hidden,L,IT,bkw", [
+    (512, 1, 1, dict(n_complexes=1, seed=0, n_c=30, n_p=200)),                                  # BASELINE config 1
+    (512, 4, 8, dict(n_complexes=2, seed=5, n_c_range=(10, 50), n_p_range=(80, 200))),          # published depth
+    (128, 1, 1, dict(n_complexes=3, seed=6, n_c_range=(10, 40), n_p_range=(150, 600))),         # pocket-stage shape
+])
+def test_oracle_fp32(hidden, L, IT, bkw):
+    b = make_batch(embed=hidden, **bkw)
+    m0 = EfficientMCAttModel(ref_shims.published_args(), hidden, hidden, 1, n_layers=L, n_iter=IT,
+                             normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m0.state_dict().items()}, 31)
+    cfg = orc.make_cfg(n_layers=L, n_iter=IT)
+    with torch.no_grad():
+        Xo, Ho, edges = orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global,
+                                          b.compound_edge_index, b.LAS_edge_index, b.X_LAS, return_edges=True)
+    m = _model(hidden, L, IT, sd)
+    X, H = _run(m, b)
+    e_int = m.last_stats["inter_edges_per_iter"].cpu().tolist()
+    rec = dict(hidden=hidden, L=L, IT=IT, x_err=rel_err(X, Xo), h_err=rel_err(H, Ho), e_int=e_int,
+               e_int_ref=[int(e[1].shape[1]) for e in edges], moved=float((Xo - b.X).abs().max()))
+    _log("oracle_fp32", rec)
+    assert e_int == rec["e_int_ref"], rec
+    assert rec["x_err"] < 1e-4 and rec["h_err"] < 1e-4, rec
+
+
+def test_bf16_mode_deviation():
+    """bf16 production mode: same path with bf16 GEMM operands.  The reference has no bf16 mode; this bound
+    is the build's own: coordinates within 0.1 normalised units (0.5 A) of the fp32 oracle after 8 iterations x 4
+    layers with the deliberately large O(1) test coordinate heads (trained heads are ~1000x smaller, egnn.py:52),
+    node features within 2% of their scale."""
+    hidden, L, IT = 512, 4, 8
+    b = make_batch(embed=hidden, n_complexes=2, seed=5, n_c_range=(10, 50), n_p_range=(80, 200))
+    m0 = EfficientMCAttModel(ref_shims.published_args(), hidden, hidden, 1, n_layers=L, n_iter=IT,
+                             normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m0.state_dict().items()}, 31)
+    cfg = orc.make_cfg(n_layers=L, n_iter=IT)
+    with torch.no_grad():
+        Xo, Ho = orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global,
+                                   b.compound_edge_index, b.LAS_edge_index, b.X_LAS)
+    m = _model(hidden, L, IT, sd, precision="bf16")
+    X, H = _run(m, b)
+    rec = dict(x_abs=float((X - Xo).abs().max()), x_err=rel_err(X, Xo), h_err=rel_err(H, Ho))
+    _log("bf16_mode", rec)
+    assert rec["x_abs"] < 0.1 and rec["h_err"] < 0.02, rec
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from fabind_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfabind_b200.so")
+    with pytest.raises(RuntimeError):
+        _lib.lib()
