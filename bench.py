@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the FABind docking stack on B200 (driver contract: see the task's bench.py section).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3             # our arm (CUDA path)
+    python bench.py --impl reference --steps 3 --warmup 1      # reference arm: the CPU port (oracle)
+    torchrun --nproc-per-node N bench.py --gpus N ...          # weak scaling: 16 complexes per GPU
+
+One step = one full EfficientMCAttModel forward (pair_embed0 + 8 refinement iterations x (4 layers +
+out layer)) over one batch of 16 PDBbind-shaped synthetic complexes (n_c=30, n_p=200, hidden 512):
+BASELINE.json configs[1].  `value` is timed with inputs resident in HBM; `e2e` goes through the public
+API with pinned HOST buffers (H2D of every input and D2H of coordinates + node features inside the
+timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN, LAYERS, ITERS, BATCH, N_C, N_P = 512, 4, 8, 16, 30, 200
+METRIC = "complexes/sec full FABind forward (8 iterations x 4 layers, hidden 512)"
+CATS = ["gemm_edge", "gemm_node", "gemm_pair", "gemm_pair0", "edge_elementwise", "attention", "graph_misc"]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def build_model(device, precision):
+    from fabind_b200 import EfficientMCAttModel
+    from fabind_b200.config import published_args
+    from fabind_b200.synthetic import randomize_coord_heads
+    torch.manual_seed(0)
+    m = EfficientMCAttModel(published_args(), HIDDEN, HIDDEN, 1, n_layers=LAYERS, n_iter=ITERS,
+                            normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    randomize_coord_heads(m, std=0.5)
+    m = m.to(device).eval()
+    m.precision = precision
+    return m
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU formulation (oracle port, all host threads) on a bounded sample."""
+    if rank != 0:
+        return
+    from oracle import fabind_oracle as orc
+    from fabind_b200.synthetic import make_batch
+    m = build_model("cpu", "fp32")
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cfg = orc.make_cfg(n_layers=LAYERS, n_iter=ITERS)
+    sample = 1
+    b = make_batch(n_complexes=sample, n_c=N_C, n_p=N_P, embed=HIDDEN, seed=0)
+    cores = torch.get_num_threads()
+
+    def step():
+        with torch.no_grad():
+            orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global,
+                              b.compound_edge_index, b.LAS_edge_index, b.X_LAS)
+    for _ in range(args.warmup):
+        step()
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(ts) / len(ts)
+    val = sample / (ms / 1e3)
+    sample_txt = f"{sample} complex (n_c={N_C}, n_p={N_P}) per step, same model/config, reference formulation on CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "complexes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch={BATCH} PDBbind-shaped synthetic complexes, full 8-iteration x 4-layer forward",
+                   "hidden": HIDDEN, "n_layers": LAYERS, "n_iter": ITERS},
+        "cpu_baseline": {"value": val, "unit": "complexes/s", "cores": cores, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": val, "unit": "complexes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from fabind_b200 import _lib
+    from fabind_b200.synthetic import make_batch
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    model = build_model(dev, args.precision)
+    host = make_batch(n_complexes=BATCH, n_c=N_C, n_p=N_P, embed=HIDDEN, seed=100 + rank)
+    for k, v in list(host.__dict__.items()):
+        if torch.is_tensor(v):
+            setattr(host, k, v.pin_memory())
+    devb = host.to(dev)
+    X0 = devb.X.clone()
+    X_master = host.X.clone().pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def dev_step():
+        devb.X.copy_(X0)
+        return model(**devb.forward_args())
+
+    def host_step():
+        host.X.copy_(X_master)       # X is updated in place by the forward: restore the pinned input
+        return model(**host.forward_args())
+
+    def timed(step_fn, steps):
+        """per-step CUDA events (max over ranks afterwards), L2 flushed between steps"""
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.fb_launch_count()
+    tot_ms = timed(dev_step, args.steps)
+    launches = lib.fb_launch_count() - l0
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    # end-to-end through the public API with host buffers
+    for _ in range(2):
+        host_step()
+    barrier()
+    e2e_ms = timed(host_step, args.steps)
+    barrier()
+    t = torch.tensor([tot_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms, e2e_ms = t.tolist()
+
+    # roofline leg: same steps with every stage bracketed by CUDA events on the launching stream
+    prof = None
+    if rank == 0:
+        lib.fb_prof_enable(1)
+        for _ in range(args.steps):
+            flush.zero_()
+            dev_step()
+        torch.cuda.synchronize(dev)
+        ms = (C.c_double * len(CATS))()
+        spans = (C.c_int64 * len(CATS))()
+        _lib.check(lib.fb_prof_read(ms, spans, len(CATS)), "fb_prof_read")
+        lib.fb_prof_enable(0)
+        prof = {c: dict(ms_per_step=ms[i] / args.steps, launches_per_step=spans[i] / args.steps) for i, c in enumerate(CATS)}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    e_ctx = model.last_stats["ctx_edges"]
+    ms_per_step = tot_ms / args.steps
+    value = world * BATCH / (ms_per_step / 1e3)
+    e2e_val = world * BATCH / (e2e_ms / args.steps / 1e3)
+    # dominant kernel = the edge-MLP GEMM (M = context edges of the batch, N = K = hidden), two launches per GCL
+    ge = prof["gemm_edge"]
+    n_edge_launch = max(ge["launches_per_step"], 1)
+    avg_ms = ge["ms_per_step"] / n_edge_launch
+    flops = 2.0 * e_ctx * HIDDEN * HIDDEN
+    achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("gemm_edge_dram_bytes_per_launch")
+    roofline = {"kernel": "edge-MLP GEMM (gemm_tc / gemm_simt), M=E_ctx N=K=512", "bound": "tensor", "achieved": achieved,
+                "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": traffic,
+                "peak_source": peaks["src"] + ", sustained figure (kernel timed inside a long step)",
+                "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg_ms,
+                "share_of_step": ge["ms_per_step"] / max(sum(v["ms_per_step"] for v in prof.values()), 1e-9)}
+    h2d = sum(v.numel() * v.element_size() for k, v in host.__dict__.items()
+              if torch.is_tensor(v) and k in ("X", "H", "X_LAS", "compound_edge_index", "LAS_edge_index"))
+    d2h = host.X.numel() * 4 + host.H.shape[0] * HIDDEN * 4
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import fabind_oracle as orc
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        cfg = orc.make_cfg(n_layers=LAYERS, n_iter=ITERS)
+        sb = make_batch(n_complexes=1, n_c=N_C, n_p=N_P, embed=HIDDEN, seed=0)
+        ts = []
+        with torch.no_grad():
+            for i in range(4):
+                t0 = time.perf_counter()
+                orc.model_forward(sd, cfg, sb.X, sb.H, sb.batch_id, sb.segment_id, sb.mask, sb.is_global,
+                                  sb.compound_edge_index, sb.LAS_edge_index, sb.X_LAS)
+                if i:
+                    ts.append(time.perf_counter() - t0)
+        cpu = {"value": 1.0 / statistics.median(ts), "unit": "complexes/s", "cores": torch.get_num_threads(),
+               "kind": "port", "sample": f"1 complex (n_c={N_C}, n_p={N_P}), 1 warm-up + 3 timed full forwards, median"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "complexes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"batch={BATCH} PDBbind-shaped synthetic complexes per GPU (n_c={N_C}, n_p={N_P}), "
+                               "full 8-iteration x 4-layer FABind forward (BASELINE.json configs[1])",
+                   "hidden": HIDDEN, "n_layers": LAYERS, "n_iter": ITERS, "global_batch": world * BATCH,
+                   "parallelism": f"dp{world} (independent complexes, no forward collective)",
+                   "l2": "flushed between steps (256 MiB memset), per-step CUDA events",
+                   "ctx_edges": e_ctx, "inter_edges_last_iter": int(model.last_stats["inter_edges_per_iter"][-1])},
+        "e2e": {"value": e2e_val, "unit": "complexes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "stage_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in prof.items()},
+        "cpu_baseline": cpu,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

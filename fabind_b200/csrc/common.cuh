@@ -24,6 +24,12 @@ typedef __nv_bfloat16 bf16;
 
 namespace fb {
 
+// host-side bookkeeping (forward.cu): number of kernels launched, optional per-category event timing
+void count_launch(int n);
+void prof_begin(int category, cudaStream_t st);
+void prof_end(cudaStream_t st);
+enum { CAT_GEMM_EDGE = 0, CAT_GEMM_NODE, CAT_GEMM_PAIR, CAT_GEMM_PAIR0, CAT_EDGE_ELEMWISE, CAT_ATTENTION, CAT_GRAPH_MISC, CAT_COUNT };
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

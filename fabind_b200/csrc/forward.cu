@@ -1,6 +1,7 @@
 // Host-side orchestration of the docking stack: weight-arena layout, scratch planning and the launch
 // sequence of EfficientMCAttModel.forward.  No allocation, no synchronisation: everything is enqueued
 // on the caller's stream.
+#include <atomic>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -11,6 +12,37 @@
 #include "layers.h"
 
 namespace fb {
+
+// ------------------------------------------------------------------------------------------------
+// bookkeeping: launch counter and optional per-category CUDA-event timing (bench.py roofline leg)
+// ------------------------------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
+
+struct ProfSpan { cudaEvent_t a, b; int cat; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_spans;       // recorded spans of the current profile window
+static std::vector<ProfSpan> g_pool;        // reusable events
+static int g_open_cat = -1;
+static cudaEvent_t g_open_a, g_open_b;
+
+void prof_begin(int cat, cudaStream_t st) {
+  if (!g_prof_on) return;
+  if (g_pool.empty()) {
+    ProfSpan s; s.cat = 0;
+    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+    g_pool.push_back(s);
+  }
+  ProfSpan s = g_pool.back(); g_pool.pop_back();
+  g_open_cat = cat; g_open_a = s.a; g_open_b = s.b;
+  cudaEventRecord(g_open_a, st);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_open_cat < 0) return;
+  cudaEventRecord(g_open_b, st);
+  g_spans.push_back({g_open_a, g_open_b, g_open_cat});
+  g_open_cat = -1;
+}
 
 constexpr int HD = 128;  // RowAttentionBlock: 4 heads x 32 channels (cross_att.py:98)
 
@@ -200,6 +232,9 @@ struct Run {
   void* at(void* base, size_t elem) const { return (char*)base + elem * TS; }
   const void* at(const void* base, size_t elem) const { return (const char*)base + elem * TS; }
   void chk(int r) { if (rc == FB_OK && r != FB_OK) rc = r; }
+  // category-tagged launch of a non-GEMM stage
+  template <typename F> void stage(int cat, F f) { prof_begin(cat, st); chk(f()); prof_end(st); }
+  int gemm_cat = CAT_GEMM_NODE;
 
   // C = act(A W^T + b) with the usual optional extras
   void gemm(const void* A, int lda, int K, int64_t w_off, int Nout, int64_t b_off, int act, int M, float* C, int ldc,
@@ -216,18 +251,27 @@ struct Run {
     }
     a.dotv = dotv_off >= 0 ? F(dotv_off) : nullptr; a.dot_out = dot_out; a.dot_stride = dot_stride;
     a.M = M; a.N = Nout; a.m_dev = m_dev;
+    prof_begin(gemm_cat, st);
     chk(gemm_launch(a, bf, st));
+    prof_end(st);
   }
 
   void run_gcl(const GclW& gw, const float* x_in, float* x_out, bool need_h) {
     const int E = p.E_ctx;
-    chk(radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st));
+    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
+    gemm_cat = CAT_GEMM_NODE;
     gemm(b.hT, H, H, gw.e1_rc, 2 * H, -1, FB_ACT_NONE, N, b.Pn, 2 * H, nullptr, 0);
-    chk(gcl_edge_pre(E, H, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st));
+    stage(CAT_EDGE_ELEMWISE, [&] {
+      return gcl_edge_pre(E, H, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st);
+    });
+    gemm_cat = CAT_GEMM_EDGE;
     gemm(b.A1, H, H, gw.e2_w, H, gw.e2_b, FB_ACT_SILU, E, nullptr, 0, b.M, H);
     const int tiles = gemm_dot_tiles(H, H, bf);
     gemm(b.M, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_SILU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
-    chk(gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st));
+    stage(CAT_EDGE_ELEMWISE, [&] {
+      return gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st);
+    });
+    gemm_cat = CAT_GEMM_NODE;
     if (need_h) {
       gemm(b.hT, H, H, gw.n1_w, H, gw.n1_b, FB_ACT_SILU, N, nullptr, 0, b.T1, H, nullptr, 0, b.agg, H, H);
       gemm(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h, H, b.hT, H, b.h, H);
@@ -238,17 +282,22 @@ struct Run {
     const size_t P = p.P_total;
     float* hp = b.h + (size_t)Nc * H;              // protein-side rows
     void* hTp = at(b.hT, (size_t)Nc * H);
+    gemm_cat = CAT_GEMM_NODE;
     // --- cross attention (cross_att.py:24-54) on the per-complex blocks
     gemm(b.hT, H, H, aw.ca_c_w, 4 * HD, aw.ca_c_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0);
     gemm(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0);
     const float* CApv = b.CAp - (size_t)Nc * 2 * HD;  // virtual base indexed by internal node id
-    chk(row_attention(g, 1, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
-                      b.PB + (size_t)(layer * 2 + 0) * P * 4, b.O, HD, bf, st));
+    stage(CAT_ATTENTION, [&] {
+      return row_attention(g, 1, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
+                           b.PB + (size_t)(layer * 2 + 0) * P * 4, b.O, HD, bf, st);
+    });
     gemm(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
     gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
     const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
-    chk(row_attention(g, 0, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
-                      b.PB + (size_t)(layer * 2 + 1) * P * 4, b.O, HD, bf, st));
+    stage(CAT_ATTENTION, [&] {
+      return row_attention(g, 0, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
+                           b.PB + (size_t)(layer * 2 + 1) * P * 4, b.O, HD, bf, st);
+    });
     gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
     // transitions (model_utils.py:171-175), residual
     gemm(hTp, H, H, aw.tp1_w, 2 * H, aw.tp1_b, FB_ACT_RELU, Np, nullptr, 0, b.TH, 2 * H);
@@ -261,18 +310,22 @@ struct Run {
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
-    chk(pair_zin(g, capU, H, b.P0, b.pc32, F(aw.i32_o_w), F(aw.i32_o_b), b.Zin, bf, st));
+    stage(CAT_ATTENTION, [&] { return pair_zin(g, capU, H, b.P0, b.pc32, F(aw.i32_o_w), F(aw.i32_o_b), b.Zin, bf, st); });
     const int tiles2 = gemm_dot_tiles(2 * H, H, bf);
+    gemm_cat = CAT_GEMM_PAIR;
     gemm(b.Zin, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0,
          aw.pt2v, b.dotU, capU, u_dev);
-    chk(pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st));
+    gemm_cat = CAT_GEMM_NODE;
+    stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
     // --- interfacial attention (egnn.py:186-252)
-    chk(radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st));
+    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
     gemm(b.hT, H, H, aw.qk_w, 2 * H, aw.qk_b, FB_ACT_NONE, N, b.QK, 2 * H, nullptr, 0);
     gemm(b.hT, H, H, aw.v_w, H, aw.v_b, FB_ACT_NONE, N, b.V32, H, b.VT, H);
     gemm(b.VT, H, H, aw.ac1_w, H, -1, FB_ACT_NONE, N, b.VC, H, nullptr, 0);
-    chk(inter_attention(g, H, b.QK, b.V32, b.VC, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
-                        b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st));
+    stage(CAT_ATTENTION, [&] {
+      return inter_attention(g, H, b.QK, b.V32, b.VC, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
+                             b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st);
+    });
   }
 
   void tap(int slot, const float* x) {
@@ -282,21 +335,27 @@ struct Run {
 
   void forward() {
     const size_t P = p.P_total;
-    chk(permute_in(g, p.H_in, p.X_in, p.X_las, H, b.Hin32, b.HinT, bf, b.x_state, b.xl, st));
+    stage(CAT_GRAPH_MISC, [&] { return permute_in(g, p.H_in, p.X_in, p.X_las, H, b.Hin32, b.HinT, bf, b.x_state, b.xl, st); });
     // pair_embed0 = InteractionModule(H_p, H_c)  (att_model.py:198-206, model_utils.py:219-222)
+    gemm_cat = CAT_GEMM_NODE;
     gemm(b.HinT, H, H, w.il_c_w, H, w.il_c_b, FB_ACT_NONE, Nc, b.pc, H, nullptr, 0);
     gemm(at(b.HinT, (size_t)Nc * H), H, H, w.il_p_w, H, w.il_p_b, FB_ACT_NONE, Np, b.pc + (size_t)Nc * H, H, nullptr, 0);
-    chk(pair_outer(g, (int)P, H, b.pc, b.A0, bf, st));
+    stage(CAT_EDGE_ELEMWISE, [&] { return pair_outer(g, (int)P, H, b.pc, b.A0, bf, st); });
+    gemm_cat = CAT_GEMM_PAIR0;
     gemm(b.A0, H, H, w.il_o_w, H, w.il_o_b, FB_ACT_NONE, (int)P, nullptr, 0, b.P0, H);
     // gated pair biases of all RowAttentionBlocks at once (pair0 is layer- and iteration-invariant in v1)
-    gemm(b.P0, H, H, w.pb_w, 16 * p.n_layers, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, 16 * p.n_layers, nullptr, 0);
-    chk(pair_bias_gate((int)P, p.n_layers, b.PBraw, b.PB, st));
+    if (p.n_layers > 0) {
+      gemm(b.P0, H, H, w.pb_w, 16 * p.n_layers, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, 16 * p.n_layers, nullptr, 0);
+      stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, p.n_layers, b.PBraw, b.PB, st); });
+    }
+    gemm_cat = CAT_GEMM_NODE;
     // context graph: protein coordinates are reset every iteration, so it is built once
-    chk(graph_fill_ctx(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st));
+    stage(CAT_GRAPH_MISC, [&] { return graph_fill_ctx(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
     for (int it = 0; it < p.n_iter; ++it) {
       const bool last = it == p.n_iter - 1;
-      chk(graph_build_inter(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st));
+      stage(CAT_GRAPH_MISC, [&] { return graph_build_inter(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
       if (p.stats) cudaMemcpyAsync(p.stats + it, g.int_rowptr + N, sizeof(int), cudaMemcpyDeviceToDevice, st);
+      gemm_cat = CAT_GEMM_NODE;
       gemm(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H);
       const float* xc = b.x_state;
       float* bufs[2] = {b.xa, b.xb};
@@ -306,16 +365,18 @@ struct Run {
         if (last) tap(2 * l, xc);
         run_att(w.att[l], l, xc, bufs[k]); xc = bufs[k]; k ^= 1;
         if (last) tap(2 * l + 1, xc);
-        chk(las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st)); xc = bufs[k]; k ^= 1;
+        stage(CAT_GRAPH_MISC, [&] { return las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st); });
+        xc = bufs[k]; k ^= 1;
       }
       // the out-layer node update and linear_out only matter on the last iteration
       // (att_model.py:232: non-final iterations discard H)
       run_gcl(w.gcl[p.n_layers], xc, bufs[k], last); xc = bufs[k];
       if (last) {
+        gemm_cat = CAT_GEMM_NODE;
         gemm(b.hT, H, H, w.out_w, H, w.out_b, FB_ACT_NONE, N, b.Hfin, H, nullptr, 0);
-        chk(permute_out_h(g, b.Hfin, H, p.H_out, st));
+        stage(CAT_GRAPH_MISC, [&] { return permute_out_h(g, b.Hfin, H, p.H_out, st); });
       }
-      chk(masked_update_x(g, b.x_state, xc, last ? p.X_out : nullptr, st));
+      stage(CAT_GRAPH_MISC, [&] { return masked_update_x(g, b.x_state, xc, last ? p.X_out : nullptr, st); });
     }
   }
 };
@@ -332,6 +393,26 @@ static bool params_ok(const fb_model_params* p) {
 extern "C" {
 
 int32_t fb_abi_version(void) { return FB_ABI_VERSION; }
+
+int64_t fb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int32_t fb_prof_enable(int32_t on) {
+  g_prof_on = on != 0;
+  return FB_OK;
+}
+
+int32_t fb_prof_read(double* ms, int64_t* spans, int32_t n_cat) {
+  // requires the recorded work to have completed (caller synchronises the stream first)
+  for (int i = 0; i < n_cat; ++i) { ms[i] = 0.0; spans[i] = 0; }
+  for (auto& s : g_spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, s.a, s.b) != cudaSuccess) return FB_ERR_CUDA;
+    if (s.cat < n_cat) { ms[s.cat] += t; spans[s.cat] += 1; }
+    g_pool.push_back(s);
+  }
+  g_spans.clear();
+  return FB_OK;
+}
 
 int32_t fb_weight_slot_count(int32_t hidden, int32_t n_layers) { return (int32_t)weights_for(hidden, n_layers).slots.size(); }
 

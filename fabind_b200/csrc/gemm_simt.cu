@@ -91,6 +91,7 @@ int gemm_simt_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
   if (bf16_mode) gemm_simt_kernel<bf16><<<grid, NT, 0, st>>>(g);
   else gemm_simt_kernel<float><<<grid, NT, 0, st>>>(g);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }

@@ -205,6 +205,7 @@ int graph_prepare_static(const GraphDev& g, const long long* bonds, const long l
   las_rows_kernel<false><<<warp_grid(g.N), 256, 0, st>>>(g);
   scan_kernel<<<1, 1024, 0, st>>>(g.las_deg, g.las_rowptr, g.N, nullptr, -1, -1);
   las_rows_kernel<true><<<warp_grid(g.N), 256, 0, st>>>(g);
+  count_launch(3 + (g.n_bond > 0) + (g.n_las > 0));
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -212,12 +213,14 @@ int graph_prepare_static(const GraphDev& g, const long long* bonds, const long l
 int graph_count_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st) {
   graph_rows_kernel<1, false><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
   scan_kernel<<<1, 1024, 0, st>>>(g.ctx_deg, g.ctx_rowptr, g.N, nullptr, -1, -1);
+  count_launch(2);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int graph_fill_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st) {
   graph_rows_kernel<1, true><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -226,6 +229,7 @@ int graph_build_inter(const GraphDev& g, const float* x, float intra, float inte
   graph_rows_kernel<2, false><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
   scan_kernel<<<1, 1024, 0, st>>>(g.int_deg, g.int_rowptr, g.N, g.int_fallback, g.fb_atom, g.fb_res);
   graph_rows_kernel<2, true><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
+  count_launch(3);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -296,6 +300,7 @@ int graph_ref_count(int N, const int* cplx, const int* off, const uint8_t* flags
   for (int k = 0; k < 4; ++k)
     scan_kernel<<<1, 1024, 0, st>>>(deg + (size_t)k * N, rowptr + (size_t)k * (N + 1), N,
                                     k == 3 ? fallback : nullptr, -1, -1);
+  count_launch(5);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -310,6 +315,7 @@ int graph_ref_fill(int N, const int* cplx, const int* off, const uint8_t* flags,
   }
   ref_rows_kernel<true><<<warp_grid(N), 256, 0, st>>>(N, cplx, off, flags, x, intra, inter, deg, rowptr, cat_base,
                                                        fallback, ctx_out, e_ctx, int_out, e_int);
+  count_launch(fallback_host ? 3 : 1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }

@@ -67,24 +67,28 @@ int permute_in(const GraphDev& g, const float* H_in, const float* X_in, const fl
   else gather_rows_kernel<float><<<warp_grid(g.N), 256, 0, st>>>(H_in, g.perm, g.N, D, h32, (float*)nullptr);
   gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(X_in, g.perm, g.N, x);
   if (XL_in) gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(XL_in, g.perm, g.N, xl);
+  count_launch(XL_in ? 3 : 2);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int permute_x(const GraphDev& g, const float* X_in, float* x, cudaStream_t st) {
   gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(X_in, g.perm, g.N, x);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int permute_out_h(const GraphDev& g, const float* h, int D, float* H_out, cudaStream_t st) {
   scatter_rows_kernel<<<warp_grid(g.N), 256, 0, st>>>(h, g.perm, g.N, D, H_out);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int masked_update_x(const GraphDev& g, float* x_state, const float* z, float* x_out_caller, cudaStream_t st) {
   masked_update_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(x_state, z, g.node_flags, g.perm, g.N, x_out_caller);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(512) radial_kernel(GraphDev g, const int* __re
 int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* ecol, const float* x, float* rad,
            float* norm, cudaStream_t st) {
   radial_kernel<<<g.B, 512, 0, st>>>(g, rowptr, erow, ecol, x, rad, norm);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -161,6 +166,7 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
   if (E <= 0) return FB_OK;
   if (bf16_mode) gcl_edge_pre_kernel<bf16><<<warp_grid(E), 256, 0, st>>>(E, H, erow, ecol, node_cplx, P, rad, norm, w_rad, b1, (bf16*)A1);
   else gcl_edge_pre_kernel<float><<<warp_grid(E), 256, 0, st>>>(E, H, erow, ecol, node_cplx, P, rad, norm, w_rad, b1, (float*)A1);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -210,6 +216,7 @@ int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, co
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
   if (bf16_mode) gcl_node_kernel<bf16><<<warp_grid(N), 256, 0, st>>>(N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
   else gcl_node_kernel<float><<<warp_grid(N), 256, 0, st>>>(N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -246,6 +253,7 @@ __global__ void pair_outer_kernel(GraphDev g, int P_total, int H, const float* _
 int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0, bool bf16_mode, cudaStream_t st) {
   if (bf16_mode) pair_outer_kernel<bf16><<<warp_grid(P_total), 256, 0, st>>>(g, P_total, H, pc, (bf16*)A0);
   else pair_outer_kernel<float><<<warp_grid(P_total), 256, 0, st>>>(g, P_total, H, pc, (float*)A0);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -266,6 +274,7 @@ __global__ void pair_bias_gate_kernel(int P_total, int L, const float* __restric
 int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t st) {
   const long long total = (long long)P_total * L * 8;
   pair_bias_gate_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(P_total, L, raw, PB);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -338,6 +347,7 @@ int row_attention(const GraphDev& g, int q_is_prot, const float* Q, int ldq, con
   if (n_q <= 0) return FB_OK;
   if (bf16_mode) row_attention_kernel<bf16><<<warp_grid((long long)n_q * 4), 256, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (bf16*)O, ldo);
   else row_attention_kernel<float><<<warp_grid((long long)n_q * 4), 256, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (float*)O, ldo);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -378,6 +388,7 @@ int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* p
   if (cap_u <= 0) return FB_OK;
   if (bf16_mode) pair_zin_kernel<bf16><<<warp_grid(cap_u), 256, 0, st>>>(g, H, (const bf16*)P0, pc32, Wo, bo, (bf16*)Zin);
   else pair_zin_kernel<float><<<warp_grid(cap_u), 256, 0, st>>>(g, H, (const float*)P0, pc32, Wo, bo, (float*)Zin);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -396,6 +407,7 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
                      cudaStream_t st) {
   if (cap_u <= 0) return FB_OK;
   pair_bias_finish_kernel<<<(cap_u + 255) / 256, 256, 0, st>>>(g, dot, tiles, stride, cst, pb_dense);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -513,6 +525,7 @@ int inter_attention(const GraphDev& g, int H, const float* QK, const float* V, c
     if (H <= 128) FB_IA(float, 1); else if (H <= 256) FB_IA(float, 2); else FB_IA(float, 4);
   }
 #undef FB_IA
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
@@ -545,6 +558,7 @@ __global__ void las_step_kernel(GraphDev g, const float* __restrict__ x, const f
 
 int las_step(const GraphDev& g, const float* x, const float* xref, float step, float cl, float* x_out, cudaStream_t st) {
   las_step_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(g, x, xref, step, cl, x_out);
+  count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }

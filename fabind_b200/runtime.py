@@ -48,20 +48,25 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     """Runs fb_graph_static + fb_model_forward.  X is updated in place (reference att_model.py:236,245).
     Returns (H_out, stats[int32 n_iter device tensor])."""
     l = _lib.lib()
-    dev = X.device
+    dev = next(module.parameters()).device
     if dev.type != "cuda":
-        raise RuntimeError("fabind_b200 runs on CUDA tensors only (no CPU fallback)")
+        raise RuntimeError("fabind_b200 runs on a CUDA device only (no CPU fallback): move the module to cuda")
+    # HOST-BUFFER mode: every input is a CPU tensor (pinned for async copies); they are copied to the device
+    # here, and X / H_out are copied back before returning.  Otherwise inputs are already device tensors.
+    host_mode = X.device.type == "cpu"
     N = X.shape[0]
     hidden = cfg["hidden"]
-    xv = X.view(N, 3)
-    if not (xv.is_contiguous() and xv.dtype == torch.float32):
+    X_host = X
+    if not (X.view(N, 3).is_contiguous() and X.dtype == torch.float32):
         raise ValueError("X must be a contiguous float32 [N,1,3] tensor")
-    Hc = H.detach().to(torch.float32).contiguous()
-    if Hc.shape != (N, hidden):
+    if tuple(H.shape) != (N, hidden):
         raise ValueError(f"H must be [N, {hidden}]")
-    xl = X_las.detach().reshape(N, 3).to(torch.float32).contiguous()
-    bonds = bonds.detach().to(torch.int64).contiguous()
-    las = las.detach().to(torch.int64).contiguous()
+    up = lambda t, dt: t.detach().to(device=dev, dtype=dt, non_blocking=True).contiguous()
+    xv = up(X.view(N, 3), torch.float32) if host_mode else X.view(N, 3)
+    Hc = up(H, torch.float32)
+    xl = up(X_las.reshape(N, 3), torch.float32)
+    bonds = up(bonds, torch.int64)
+    las = up(las, torch.int64)
     lay = build_layout(batch_id, segment_id, is_global, mask, dev)
     w32, w16 = packed.get(module, hidden, cfg["n_layers"], dev, bf16)
     H_out = torch.empty((N, hidden), dtype=torch.float32, device=dev)
@@ -109,8 +114,14 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.ws_main, p.ws_main_bytes = wsm.data_ptr(), wsm.numel()
     _lib.check(l.fb_model_forward(C.byref(p), st), "fb_model_forward")
     # keep every tensor the enqueued kernels read alive until the stream has consumed them
-    for t in (Hc, xl, bonds, las, lay.blob, lay.flags, w32, wsg, wsm):
+    for t in (xv, Hc, xl, bonds, las, lay.blob, lay.flags, w32, wsg, wsm):
         t.record_stream(torch.cuda.current_stream(dev))
+    if host_mode:
+        X_host.view(N, 3).copy_(xv, non_blocking=True)
+        H_host = torch.empty((N, hidden), dtype=torch.float32, pin_memory=True)
+        H_host.copy_(H_out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        H_out = H_host
     if tr is not None:
         perm = lay.blob[lay.offs["perm"]:lay.offs["perm"] + N].long()
         th = torch.empty_like(tr[0]); tx = torch.empty_like(tr[1])

@@ -75,6 +75,15 @@ typedef struct fb_model_params {
 /* [host] library identification */
 int32_t fb_abi_version(void);
 
+/* Instrumentation for bench.py.  fb_launch_count: kernels launched by this library since load.
+ * fb_prof_enable(1): every stage of fb_model_forward is bracketed by CUDA events on its stream, tagged
+ * with a category (0 edge GEMMs, 1 node GEMMs, 2 pair-path GEMM, 3 pair0 GEMMs, 4 edge elementwise /
+ * segment reduce, 5 attention kernels, 6 graph + geometry).  fb_prof_read (after a stream sync) returns
+ * the summed milliseconds and span count per category and clears the record. */
+int64_t fb_launch_count(void);
+int32_t fb_prof_enable(int32_t on);
+int32_t fb_prof_read(double* ms, int64_t* spans, int32_t n_cat);
+
 /* [host] weight arena layout for (hidden, n_layers): slot i has a name ("gcl0.e2_w", "att1.qk_w", ...),
  * a [rows, cols] shape and an element offset into the arena.  fabind_b200/weights.py maps every slot to
  * the reference state_dict keys it is derived from. */
