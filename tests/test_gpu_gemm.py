@@ -98,6 +98,27 @@ def test_gemm_matches_torch(case, bf16):
         assert derr < 5e-5, f"dot rel err {derr}"
 
 
+def test_gemm_tc_large_and_device_rows():
+    """tcgen05 path: many M tiles, device-side row count, row-dot epilogue, against the SIMT kernel and torch"""
+    dev = "cuda"
+    torch.manual_seed(1)
+    M, N, K = 45000, 512, 512
+    A = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    bias = torch.randn(N, device=dev)
+    dotv = torch.randn(N, device=dev)
+    m_dev = torch.tensor([44904], dtype=torch.int32, device=dev)
+    C1, Cb1, d1 = run_gemm(A, W, bias, 1, None, None, dotv, m_dev=m_dev, bf16=True, want_cb=True)
+    C2, Cb2, d2 = run_gemm(A, W, bias, 1, None, None, dotv, m_dev=m_dev, bf16=True, want_cb=True, force_simt=True)
+    ref, dref = ref_gemm(A, W, bias, 1, None, None, dotv, True)
+    n = 44904
+    assert float((C1[:n].double() - ref[:n]).abs().max() / ref.abs().max()) < 2e-5
+    assert float((C1[:n] - C2[:n]).abs().max()) < 1e-4
+    assert float((d1[:n].double() - dref[:n]).abs().max() / dref.abs().max()) < 5e-5
+    assert torch.isnan(C1[n:]).all()
+    assert float((Cb1[:n].float() - ref[:n].float()).abs().max() / ref.abs().max()) < 1e-2
+
+
 def test_gemm_device_row_count():
     dev = "cuda"
     torch.manual_seed(0)
