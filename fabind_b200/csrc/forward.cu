@@ -45,6 +45,7 @@ void prof_end(cudaStream_t st) {
 }
 
 constexpr int HD = 128;  // RowAttentionBlock: 4 heads x 32 channels (cross_att.py:98)
+constexpr int QKX = 128; // extra columns of the stacked q|k GEMM: inter_layer linear_p (32) | linear_c (32) | pad
 
 // ------------------------------------------------------------------------------------------------
 // weight arena layout
@@ -55,7 +56,7 @@ struct GclW { int64_t e1_rc, e1_rad, e1_b, e2_w, e2_b, c1_w, c1_b, c2_w, n1_w, n
 struct AttW {
   int64_t ca_c_w, ca_c_b, ca_p_w, ca_p_b, ca_p2_w, o_p_w, o_p_b, o_c_w, o_c_b;
   int64_t tp1_w, tp1_b, tp2_w, tp2_b, tc1_w, tc1_b, tc2_w, tc2_b;
-  int64_t i32_p_w, i32_p_b, i32_c_w, i32_c_b, i32_o_w, i32_o_b;
+  int64_t i32_o_w, i32_o_b;
   int64_t pt1_w, pt1_b, pt2v, pt_c;
   int64_t qk_w, qk_b, k_r, v_w, v_b, v_r, ac1_w, ac1_b, ac2_w, ac_u;
 };
@@ -103,12 +104,10 @@ static void build_weights(int H, int L, ModelW& w) {
     a.tp2_w = add(p + "tp2_w", H, 2 * H); a.tp2_b = add(p + "tp2_b", 1, H);
     a.tc1_w = add(p + "tc1_w", 2 * H, H); a.tc1_b = add(p + "tc1_b", 1, 2 * H);
     a.tc2_w = add(p + "tc2_w", H, 2 * H); a.tc2_b = add(p + "tc2_b", 1, H);
-    a.i32_p_w = add(p + "i32_p_w", 32, H); a.i32_p_b = add(p + "i32_p_b", 1, 32);
-    a.i32_c_w = add(p + "i32_c_w", 32, H); a.i32_c_b = add(p + "i32_c_b", 1, 32);
     a.i32_o_w = add(p + "i32_o_w", H, 32); a.i32_o_b = add(p + "i32_o_b", 1, H);
     a.pt1_w = add(p + "pt1_w", 2 * H, H); a.pt1_b = add(p + "pt1_b", 1, 2 * H);
     a.pt2v = add(p + "pt2v", 1, 2 * H); a.pt_c = add(p + "pt_c", 1, 1);
-    a.qk_w = add(p + "qk_w", 2 * H, H); a.qk_b = add(p + "qk_b", 1, 2 * H); a.k_r = add(p + "k_r", 1, H);
+    a.qk_w = add(p + "qk_w", 2 * H + QKX, H); a.qk_b = add(p + "qk_b", 1, 2 * H + QKX); a.k_r = add(p + "k_r", 1, H);
     a.v_w = add(p + "v_w", H, H); a.v_b = add(p + "v_b", 1, H); a.v_r = add(p + "v_r", 1, H);
     a.ac1_w = add(p + "ac1_w", H, H); a.ac1_b = add(p + "ac1_b", 1, H);
     a.ac2_w = add(p + "ac2_w", 1, H); a.ac_u = add(p + "ac_u", 1, H);
@@ -166,7 +165,7 @@ struct Bufs {
   // coordinates
   float *x_state, *xa, *xb, *xl;
   // node features
-  float *Hin32, *h, *pc, *Pn, *CAc, *CAp, *CAp2, *pc32, *QK, *V32, *VC, *Hfin;
+  float *Hin32, *h, *pc, *Pn, *CAc, *CAp, *CAp2, *QK, *V32, *VC, *Hfin;
   void *HinT, *hT, *agg, *T1, *O, *TH, *VT;
   // pair
   void *P0, *A0, *Zin; float *PBraw, *PB, *pb_dense, *dotU;
@@ -201,11 +200,10 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
   b.CAc = a.get<float>((Nc + 1) * 4 * HD); b.CAp = a.get<float>((Np + 1) * 2 * HD); b.CAp2 = a.get<float>((Np + 1) * 2 * HD);
   b.O = a.take(N * HD * TS); b.TH = a.take(N * 2 * H * TS);
-  b.pc32 = a.get<float>(N * 32);
   b.Zin = a.take(capU * H * TS);
   b.dotU = a.get<float>(tiles2H * capU);
   b.radi = a.get<float>(capI); b.normi = a.get<float>(p.B);
-  b.QK = a.get<float>(N * 2 * H); b.V32 = a.get<float>(N * H);
+  b.QK = a.get<float>(N * (2 * H + QKX)); b.V32 = a.get<float>(N * H);
   b.VT = bf ? a.take(N * H * TS) : (void*)b.V32;
   b.VC = a.get<float>(N * H);
   // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
@@ -304,13 +302,14 @@ struct Run {
     gemm(b.TH, 2 * H, 2 * H, aw.tp2_w, H, aw.tp2_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
     gemm(b.hT, H, H, aw.tc1_w, 2 * H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, 2 * H);
     gemm(b.TH, 2 * H, 2 * H, aw.tc2_w, H, aw.tc2_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
-    // 32-channel interaction projections (cross_att.py:22,51)
-    gemm(hTp, H, H, aw.i32_p_w, 32, aw.i32_p_b, FB_ACT_NONE, Np, b.pc32 + (size_t)Nc * 32, 32, nullptr, 0);
-    gemm(b.hT, H, H, aw.i32_c_w, 32, aw.i32_c_b, FB_ACT_NONE, Nc, b.pc32, 32, nullptr, 0);
+    // q | k of the interfacial attention stacked with the 32-channel interaction projections
+    // (cross_att.py:22,51: linear_p on protein rows, linear_c on compound rows) in ONE node GEMM
+    const int ldqk = 2 * H + QKX;
+    gemm(b.hT, H, H, aw.qk_w, ldqk, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, nullptr, 0);
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
-    stage(CAT_ATTENTION, [&] { return pair_zin(g, capU, H, b.P0, b.pc32, F(aw.i32_o_w), F(aw.i32_o_b), b.Zin, bf, st); });
+    stage(CAT_ATTENTION, [&] { return pair_zin(g, capU, H, b.P0, b.QK + 2 * H, ldqk, F(aw.i32_o_w), F(aw.i32_o_b), b.Zin, bf, st); });
     const int tiles2 = gemm_dot_tiles(2 * H, H, bf);
     gemm_cat = CAT_GEMM_PAIR;
     gemm(b.Zin, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0,
@@ -319,11 +318,10 @@ struct Run {
     stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
     // --- interfacial attention (egnn.py:186-252)
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
-    gemm(b.hT, H, H, aw.qk_w, 2 * H, aw.qk_b, FB_ACT_NONE, N, b.QK, 2 * H, nullptr, 0);
     gemm(b.hT, H, H, aw.v_w, H, aw.v_b, FB_ACT_NONE, N, b.V32, H, b.VT, H);
     gemm(b.VT, H, H, aw.ac1_w, H, -1, FB_ACT_NONE, N, b.VC, H, nullptr, 0);
     stage(CAT_ATTENTION, [&] {
-      return inter_attention(g, H, b.QK, b.V32, b.VC, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
+      return inter_attention(g, H, b.QK, ldqk, b.V32, b.VC, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
                              b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st);
     });
   }

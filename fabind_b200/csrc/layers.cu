@@ -175,47 +175,65 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
 // GCL node stage (egnn.py:97, 119-128): agg[r,:] = sum_e M[e,:]   (segment sum over the CSR row)
 //   x_out[r] = x[r] + clamp(mean_e (x[r]-x[col]) * s_e, +-cmax),  s_e = sum of the row-dot partials
 // ------------------------------------------------------------------------------------------------
+// One CTA (4 warps) per node: warp w takes the edges lo+w, lo+w+4, ... (4 independent streams keep
+// loads in flight; high-degree global nodes are split four ways), lanes run over features in
+// 8-byte/16-byte vectors; the four partial rows are combined through shared memory.
 template <typename T>
-__global__ void gcl_node_kernel(int N, int H, const int* __restrict__ rowptr, const int* __restrict__ ecol,
-                                const T* __restrict__ M, const float* __restrict__ dot, int dot_tiles, int dot_stride,
-                                const float* __restrict__ x, float cmax, T* __restrict__ agg, float* __restrict__ x_out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const int r = warp, lo = rowptr[r], hi = rowptr[r + 1];
-  const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
-  float ax = 0.f, ay = 0.f, az = 0.f;
-  // coordinate part: lanes over edges
-  for (int e = lo + lane; e < hi; e += 32) {
-    float s = 0.f;
-    for (int t = 0; t < dot_tiles; ++t) s += dot[(size_t)t * dot_stride + e];
-    const int c = ecol[e];
-    ax = fmaf(xr0 - x[3 * c], s, ax);
-    ay = fmaf(xr1 - x[3 * c + 1], s, ay);
-    az = fmaf(xr2 - x[3 * c + 2], s, az);
-  }
-  ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-  if (lane == 0) {
-    const float cnt = fmaxf((float)(hi - lo), 1.0f);
-    x_out[3 * r] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
-    x_out[3 * r + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
-    x_out[3 * r + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
+__global__ void __launch_bounds__(128) gcl_node_kernel(int N, int H, const int* __restrict__ rowptr,
+                                                       const int* __restrict__ ecol, const T* __restrict__ M,
+                                                       const float* __restrict__ dot, int dot_tiles, int dot_stride,
+                                                       const float* __restrict__ x, float cmax, T* __restrict__ agg,
+                                                       float* __restrict__ x_out) {
+  extern __shared__ float part[];  // [4][H]
+  const int r = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lo = rowptr[r], hi = rowptr[r + 1];
+  if (w == 0) {
+    const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int e = lo + lane; e < hi; e += 32) {
+      float s = 0.f;
+      for (int t = 0; t < dot_tiles; ++t) s += dot[(size_t)t * dot_stride + e];
+      const int c = ecol[e];
+      ax = fmaf(xr0 - x[3 * c], s, ax);
+      ay = fmaf(xr1 - x[3 * c + 1], s, ay);
+      az = fmaf(xr2 - x[3 * c + 2], s, az);
+    }
+    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+    if (lane == 0) {
+      const float cnt = fmaxf((float)(hi - lo), 1.0f);
+      x_out[3 * r] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
+      x_out[3 * r + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
+      x_out[3 * r + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
+    }
   }
   if (agg == nullptr) return;
-  // feature part: lanes over features, edges sequential
   for (int f0 = lane * 4; f0 < H; f0 += 128) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e = lo; e < hi; ++e) {
-      const float4 m = ld4(M + (size_t)e * H + f0);
-      acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+    int e = lo + w;
+    for (; e + 4 < hi; e += 8) {  // two loads in flight per warp
+      const float4 m0 = ld4(M + (size_t)e * H + f0), m1 = ld4(M + (size_t)(e + 4) * H + f0);
+      acc.x += m0.x + m1.x; acc.y += m0.y + m1.y; acc.z += m0.z + m1.z; acc.w += m0.w + m1.w;
     }
-    st4(agg + (size_t)r * H + f0, acc);
+    for (; e < hi; e += 4) {
+      const float4 m0 = ld4(M + (size_t)e * H + f0);
+      acc.x += m0.x; acc.y += m0.y; acc.z += m0.z; acc.w += m0.w;
+    }
+    *reinterpret_cast<float4*>(&part[w * H + f0]) = acc;
+  }
+  __syncthreads();
+  for (int f = threadIdx.x * 4; f < H; f += 512) {
+    const float4 a = *reinterpret_cast<const float4*>(&part[f]), b = *reinterpret_cast<const float4*>(&part[H + f]);
+    const float4 c = *reinterpret_cast<const float4*>(&part[2 * H + f]), d = *reinterpret_cast<const float4*>(&part[3 * H + f]);
+    st4(agg + (size_t)r * H + f, make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z),
+                                             (a.w + b.w) + (c.w + d.w)));
   }
 }
 
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
-  if (bf16_mode) gcl_node_kernel<bf16><<<warp_grid(N), 256, 0, st>>>(N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
-  else gcl_node_kernel<float><<<warp_grid(N), 256, 0, st>>>(N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  const int smem = 4 * H * 4;
+  if (bf16_mode) gcl_node_kernel<bf16><<<N, 128, smem, st>>>(N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
+  else gcl_node_kernel<float><<<N, 128, smem, st>>>(N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -357,37 +375,54 @@ int row_attention(const GraphDev& g, int q_is_prot, const float* Q, int ldq, con
 // pairs, egnn.py:208,291-294).  For every unique compound->protein inter edge u:
 //   Zin[u,:] = pair0[pair,:] + W_o32 (p32[prot,:] * c32[comp,:]) + b_o32      (cross_att.py:51)
 // ------------------------------------------------------------------------------------------------
+// W_o32^T is staged once per CTA in shared memory as [32][H] so that a warp reads consecutive features
+// conflict-free; warps stride over the unique pairs (their number is only known on the device).
+// pc32 holds, per node, linear_p(h) in columns [0,32) and linear_c(h) in columns [32,64).
 template <typename T>
-__global__ void pair_zin_kernel(GraphDev g, int H, const T* __restrict__ P0, const float* __restrict__ pc32 /*[N,32]*/,
-                                const float* __restrict__ Wo /*[H,32]*/, const float* __restrict__ bo, T* __restrict__ Zin) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) pair_zin_kernel(GraphDev g, int H, const T* __restrict__ P0,
+                                                       const float* __restrict__ pc32, int ld32,
+                                                       const float* __restrict__ Wo /*[H,32]*/, const float* __restrict__ bo,
+                                                       T* __restrict__ Zin) {
+  extern __shared__ float wt[];  // [32][H]
+  for (int i = threadIdx.x; i < H * 32; i += blockDim.x) {
+    const int f = i >> 5, k = i & 31;  // coalesced read of Wo[f][k]
+    wt[k * H + f] = Wo[i];
+  }
+  __syncthreads();
   const int U = g.int_rowptr[g.Nc_tot];
-  if (warp >= U) return;
-  const int u = warp;
-  const int ci = g.int_row[u], pi = g.int_col[u], pair = g.int_pair[u];
-  const float t = pc32[(size_t)pi * 32 + lane] * pc32[(size_t)ci * 32 + lane];
-  for (int f0 = lane * 4; f0 < H; f0 += 128) {
-    float4 z = ld4(P0 + (size_t)pair * H + f0);
-    const float4 bb = ld4(bo + f0);
-    float o[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      const float tk = __shfl_sync(0xffffffffu, t, k);
-      o[0] = fmaf(Wo[(size_t)(f0 + 0) * 32 + k], tk, o[0]);
-      o[1] = fmaf(Wo[(size_t)(f0 + 1) * 32 + k], tk, o[1]);
-      o[2] = fmaf(Wo[(size_t)(f0 + 2) * 32 + k], tk, o[2]);
-      o[3] = fmaf(Wo[(size_t)(f0 + 3) * 32 + k], tk, o[3]);
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int u = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); u < U; u += gridDim.x * warps_per_cta) {
+    const int ci = g.int_row[u], pi = g.int_col[u], pair = g.int_pair[u];
+    const float t = pc32[(size_t)pi * ld32 + lane] * pc32[(size_t)ci * ld32 + 32 + lane];
+    for (int f0 = lane * 4; f0 < H; f0 += 128) {
+      float4 z = ld4(P0 + (size_t)pair * H + f0);
+      float4 o = ld4(bo + f0);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float tk = __shfl_sync(0xffffffffu, t, k);
+        const float4 w = *reinterpret_cast<const float4*>(&wt[k * H + f0]);
+        o.x = fmaf(w.x, tk, o.x); o.y = fmaf(w.y, tk, o.y); o.z = fmaf(w.z, tk, o.z); o.w = fmaf(w.w, tk, o.w);
+      }
+      z.x += o.x; z.y += o.y; z.z += o.z; z.w += o.w;
+      st4(Zin + (size_t)u * H + f0, z);
     }
-    z.x += o[0]; z.y += o[1]; z.z += o[2]; z.w += o[3];
-    st4(Zin + (size_t)u * H + f0, z);
   }
 }
 
-int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, const float* Wo, const float* bo,
-             void* Zin, bool bf16_mode, cudaStream_t st) {
+int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, int ld32, const float* Wo,
+             const float* bo, void* Zin, bool bf16_mode, cudaStream_t st) {
   if (cap_u <= 0) return FB_OK;
-  if (bf16_mode) pair_zin_kernel<bf16><<<warp_grid(cap_u), 256, 0, st>>>(g, H, (const bf16*)P0, pc32, Wo, bo, (bf16*)Zin);
-  else pair_zin_kernel<float><<<warp_grid(cap_u), 256, 0, st>>>(g, H, (const float*)P0, pc32, Wo, bo, (float*)Zin);
+  const int smem = H * 32 * 4;
+  const int grid = 148 * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pair_zin_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 4);
+    cudaFuncSetAttribute(pair_zin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 4);
+    attr = true;
+  }
+  if (bf16_mode) pair_zin_kernel<bf16><<<grid, 256, smem, st>>>(g, H, (const bf16*)P0, pc32, ld32, Wo, bo, (bf16*)Zin);
+  else pair_zin_kernel<float><<<grid, 256, smem, st>>>(g, H, (const float*)P0, pc32, ld32, Wo, bo, (float*)Zin);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -420,7 +455,7 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 // One warp per row, single pass with an online softmax.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC>
-__global__ void inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,2H]*/,
+__global__ void inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | k | ...*/, int ldqk,
                                        const float* __restrict__ V, const float* __restrict__ VC,
                                        const float* __restrict__ k_r, const float* __restrict__ v_r,
                                        const float* __restrict__ ac_u, const float* __restrict__ ac_b,
@@ -445,7 +480,7 @@ __global__ void inter_attention_kernel(GraphDev g, int H, const float* __restric
     const int f = (i * 32 + lane) * 4;
     acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f < H) {
-      q[i] = ld4(QK + (size_t)r * 2 * H + f);
+      q[i] = ld4(QK + (size_t)r * ldqk + f);
       const float4 kr = ld4(k_r + f);
       qkr += q[i].x * kr.x + q[i].y * kr.y + q[i].z * kr.z + q[i].w * kr.w;
     } else q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -461,7 +496,7 @@ __global__ void inter_attention_kernel(GraphDev g, int H, const float* __restric
     for (int i = 0; i < VEC; ++i) {
       const int f = (i * 32 + lane) * 4;
       if (f < H) {
-        const float4 kk = ld4(QK + (size_t)c * 2 * H + H + f);
+        const float4 kk = ld4(QK + (size_t)c * ldqk + H + f);
         dot += q[i].x * kk.x + q[i].y * kk.y + q[i].z * kk.z + q[i].w * kk.w;
         const float4 vc = ld4(VC + (size_t)c * H + f), uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f);
         sdot += w2.x * silu(vc.x + fmaf(rn, uu.x, bb.x)) + w2.y * silu(vc.y + fmaf(rn, uu.y, bb.y)) +
@@ -510,13 +545,13 @@ __global__ void inter_attention_kernel(GraphDev g, int H, const float* __restric
   }
 }
 
-int inter_attention(const GraphDev& g, int H, const float* QK, const float* V, const float* VC, const float* k_r,
+int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* V, const float* VC, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, bool bf16_mode, cudaStream_t st) {
   const int grid = warp_grid(g.N);
 #define FB_IA(T, VEC)                                                                                      \
-  inter_attention_kernel<T, VEC><<<grid, 256, 0, st>>>(g, H, QK, V, VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
+  inter_attention_kernel<T, VEC><<<grid, 256, 0, st>>>(g, H, QK, ldqk, V, VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
                                                        norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   if (bf16_mode) {

@@ -19,11 +19,11 @@ int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0,
 int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t st);
 int row_attention(const GraphDev& g, int q_is_prot, const float* Q, int ldq, const float* G, int ldg, const float* K,
                   int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode, cudaStream_t st);
-int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, const float* Wo, const float* bo,
+int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, int ld32, const float* Wo, const float* bo,
              void* Zin, bool bf16_mode, cudaStream_t st);
 int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, int stride, const float* cst, float* pb_dense,
                      cudaStream_t st);
-int inter_attention(const GraphDev& g, int H, const float* QK, const float* V, const float* VC, const float* k_r,
+int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* V, const float* VC, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, bool bf16_mode, cudaStream_t st);

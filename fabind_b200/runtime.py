@@ -47,6 +47,14 @@ class PackedWeights:
 def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, bonds, las, X_las, cfg, bf16, trace=False):
     """Runs fb_graph_static + fb_model_forward.  X is updated in place (reference att_model.py:236,245).
     Returns (H_out, stats[int32 n_iter device tensor])."""
+    import os, time
+    _T = os.environ.get("FABIND_B200_TIMING") == "1"
+    _t = [time.perf_counter()]
+    def _mark(tag):
+        if _T:
+            torch.cuda.synchronize()
+            _t.append(time.perf_counter())
+            print(f"[timing] {tag}: {(_t[-1] - _t[-2]) * 1e3:.3f} ms")
     l = _lib.lib()
     dev = next(module.parameters()).device
     if dev.type != "cuda":
@@ -67,7 +75,9 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     xl = up(X_las.reshape(N, 3), torch.float32)
     bonds = up(bonds, torch.int64)
     las = up(las, torch.int64)
+    _mark("input staging")
     lay = build_layout(batch_id, segment_id, is_global, mask, dev)
+    _mark("build_layout")
     w32, w16 = packed.get(module, hidden, cfg["n_layers"], dev, bf16)
     H_out = torch.empty((N, hidden), dtype=torch.float32, device=dev)
     stats = torch.zeros(cfg["n_iter"], dtype=torch.int32, device=dev)
@@ -95,6 +105,7 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
         tr = (torch.zeros((nl, N, hidden), dtype=torch.float32, device=dev),
               torch.zeros((nl, N, 3), dtype=torch.float32, device=dev))
         p.trace_h, p.trace_x = tr[0].data_ptr(), tr[1].data_ptr()
+    _mark("weights+params")
     st = current_stream_ptr(dev)
     gbytes = l.fb_graph_workspace_bytes(C.byref(p))
     if gbytes < 0:
@@ -107,12 +118,17 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     off = (cnt_ptr - wsg.data_ptr())
     e_ctx = int(wsg[off:off + 4].view(torch.int32).item())
     p.E_ctx = e_ctx
+    _mark("graph_static + E_ctx read")
     mbytes = l.fb_model_workspace_bytes(C.byref(p))
     if mbytes < 0:
         _lib.check(int(mbytes), "fb_model_workspace_bytes")
     wsm = _scratch_buf(dev, "main", mbytes)
     p.ws_main, p.ws_main_bytes = wsm.data_ptr(), wsm.numel()
+    _t0 = time.perf_counter()
     _lib.check(l.fb_model_forward(C.byref(p), st), "fb_model_forward")
+    if _T:
+        print(f"[timing] fb_model_forward enqueue (host): {(time.perf_counter() - _t0) * 1e3:.3f} ms")
+    _mark("fb_model_forward (enqueue + device)")
     # keep every tensor the enqueued kernels read alive until the stream has consumed them
     for t in (xv, Hc, xl, bonds, las, lay.blob, lay.flags, w32, wsg, wsm):
         t.record_stream(torch.cuda.current_stream(dev))

@@ -17,6 +17,7 @@ import torch
 from . import _lib
 
 HD = 128
+QKX = 128   # extra columns of the stacked q|k GEMM (csrc/forward.cu)
 
 
 def slots(hidden, n_layers):
@@ -67,13 +68,15 @@ def _att(sd, p, H):
         "tp2_w": sd[ca + "p_transition.linear_2.weight"], "tp2_b": sd[ca + "p_transition.linear_2.bias"],
         "tc1_w": sd[ca + "c_transition.linear_1.weight"], "tc1_b": sd[ca + "c_transition.linear_1.bias"],
         "tc2_w": sd[ca + "c_transition.linear_2.weight"], "tc2_b": sd[ca + "c_transition.linear_2.bias"],
-        "i32_p_w": sd[ca + "inter_layer.linear_p.weight"], "i32_p_b": sd[ca + "inter_layer.linear_p.bias"],
-        "i32_c_w": sd[ca + "inter_layer.linear_c.weight"], "i32_c_b": sd[ca + "inter_layer.linear_c.bias"],
         "i32_o_w": sd[ca + "inter_layer.linear_out.weight"], "i32_o_b": sd[ca + "inter_layer.linear_out.bias"],
         "pt1_w": sd[ca + "pair_transition.linear_1.weight"], "pt1_b": sd[ca + "pair_transition.linear_1.bias"],
         "pt2v": W2.t() @ wb, "pt_c": (wb @ b2 + bb).reshape(1),
-        "qk_w": torch.cat([sd[p + "linear_q.weight"].double(), Wkv[0::2, 1:]], 0),
-        "qk_b": torch.cat([sd[p + "linear_q.bias"].double(), bkv[0::2]]), "k_r": Wkv[0::2, 0],
+        # q | k | inter_layer.linear_p (32) | inter_layer.linear_c (32) | zero pad: one stacked node GEMM
+        "qk_w": torch.cat([sd[p + "linear_q.weight"].double(), Wkv[0::2, 1:],
+                           sd[ca + "inter_layer.linear_p.weight"].double(), sd[ca + "inter_layer.linear_c.weight"].double(),
+                           torch.zeros(QKX - 64, H, dtype=torch.float64)], 0),
+        "qk_b": torch.cat([sd[p + "linear_q.bias"].double(), bkv[0::2], sd[ca + "inter_layer.linear_p.bias"].double(),
+                           sd[ca + "inter_layer.linear_c.bias"].double(), z(QKX - 64)]), "k_r": Wkv[0::2, 0],
         "v_w": Wkv[1::2, 1:], "v_b": bkv[1::2], "v_r": v_r,
         "ac1_w": ac1, "ac1_b": sd[p + "coord_mlp.0.bias"], "ac2_w": sd[p + "coord_mlp.2.weight"][0],
         "ac_u": ac1 @ v_r,

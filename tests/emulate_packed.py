@@ -161,9 +161,10 @@ def forward_emulated(sd, cfg, batch):
             h[:Nc] = h[:Nc] + F.linear(O[:Nc], W.m(pre + "o_c_w"), W.m(pre + "o_c_b"))
             h[Nc:] = h[Nc:] + F.linear(F.relu(F.linear(h[Nc:], W.m(pre + "tp1_w"), W.m(pre + "tp1_b"))), W.m(pre + "tp2_w"), W.m(pre + "tp2_b"))
             h[:Nc] = h[:Nc] + F.linear(F.relu(F.linear(h[:Nc], W.m(pre + "tc1_w"), W.m(pre + "tc1_b"))), W.m(pre + "tc2_w"), W.m(pre + "tc2_b"))
+            QK = F.linear(h, W.m(pre + "qk_w"), W.m(pre + "qk_b"))     # q | k | linear_p32 | linear_c32 | pad
             pc32 = torch.empty(N, 32)
-            pc32[Nc:] = F.linear(h[Nc:], W.m(pre + "i32_p_w"), W.m(pre + "i32_p_b"))
-            pc32[:Nc] = F.linear(h[:Nc], W.m(pre + "i32_c_w"), W.m(pre + "i32_c_b"))
+            pc32[Nc:] = QK[Nc:, 2 * H:2 * H + 32]
+            pc32[:Nc] = QK[:Nc, 2 * H + 32:2 * H + 64]
             # pair index of every inter edge
             eb = cplx_t[int_r]
             is_c = int_r < Nc
@@ -178,10 +179,9 @@ def forward_emulated(sd, cfg, batch):
             pb_dense = torch.zeros(P0.shape[0])
             pb_dense[pair[u]] = pbu
             rn = _radial(int_r, int_c, x, cplx_t, B)
-            QK = F.linear(h, W.m(pre + "qk_w"), W.m(pre + "qk_b"))
             V = F.linear(h, W.m(pre + "v_w"), W.m(pre + "v_b"))
             VC = F.linear(V, W.m(pre + "ac1_w"))
-            logit = (QK[int_r, :H] * (QK[int_c, H:] + rn[:, None] * W.m(pre + "k_r"))).sum(1) + pb_dense[pair]
+            logit = (QK[int_r, :H] * (QK[int_c, H:2 * H] + rn[:, None] * W.m(pre + "k_r"))).sum(1) + pb_dense[pair]
             mx = torch.full((N,), float("-inf")).scatter_reduce(0, int_r, logit, reduce="amax")
             e = (logit - mx[int_r]).exp()
             alpha = e / torch.zeros(N).index_add_(0, int_r, e)[int_r]
