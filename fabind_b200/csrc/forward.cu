@@ -12,6 +12,7 @@
 #include "layers.h"
 
 namespace fb {
+extern long long* g_tc_dbg;
 
 // ------------------------------------------------------------------------------------------------
 // bookkeeping: launch counter and optional per-category CUDA-event timing (bench.py roofline leg)
@@ -518,6 +519,11 @@ int32_t fb_gemm(const fb_gemm_params* q, void* stream) {
   a.M = q->M; a.N = q->N; a.m_dev = q->m_dev;
   if (q->force_simt) return gemm_simt_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
   return gemm_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
+}
+
+int32_t fb_gemm_set_debug(int64_t* dbg) {
+  fb::g_tc_dbg = (long long*)dbg;
+  return FB_OK;
 }
 
 int32_t fb_gemm_dot_tiles(int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt) {

@@ -10,6 +10,7 @@
 //
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue.
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm.h"
@@ -53,6 +54,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define FB_DBG(slot)                                                                         \
+  do {                                                                                       \
+    if (p.dbg && blockIdx.x == 0 && (blockIdx.y & 7) == 0) p.dbg[(blockIdx.y >> 3) * 8 + (slot)] = gtime(); \
+  } while (0)
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -101,6 +112,7 @@ struct Params {
   float* C; int ldc;
   bf16* Cb; int ldcb;
   const float* dotv; float* dot_out; int dot_stride;
+  long long* dbg;          // optional phase timestamps (globaltimer ns), 8 per sampled CTA
 };
 
 template <int BN, int STAGES>
@@ -108,7 +120,8 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int VEC_OFF = BAR_OFF + (2 * STAGES + 1) * 8 + 16;       // staged bias[BN] | dotv[BN]
+  static constexpr int TOTAL = VEC_OFF + 2 * BN * 4 + 1024;                 // + alignment slack
 };
 
 template <int BN, int STAGES>
@@ -127,9 +140,12 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  float* s_bias = (float*)(smem + S::VEC_OFF);
+  float* s_dot = s_bias + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.KB1 + p.KB2;
+  if (threadIdx.x == 0) FB_DBG(0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -151,6 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) FB_DBG(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -176,6 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full[s], ph);
+        if (kb == 0) FB_DBG(2);
         tcgen05_fence_after();
         const uint8_t* a_src = smem + s * S::STAGE_BYTES;
         const uint64_t adesc = make_smem_desc(a_src), bdesc = make_smem_desc(a_src + S::A_BYTES);
@@ -186,6 +204,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         }
         umma_commit(&empty[s]);   // frees the smem stage once the MMAs above have read it
       }
+      FB_DBG(3);
       umma_commit(tmem_full);     // accumulator complete
     }
   } else {
@@ -193,7 +212,14 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int m = m0 + row;
+    // stage the per-column vectors of this N tile in shared memory while the main loop runs
+    for (int t = threadIdx.x - 64; t < BN; t += 128) {
+      s_bias[t] = p.bias ? p.bias[n0 + t] : 0.f;
+      s_dot[t] = p.dotv ? p.dotv[n0 + t] : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
     mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) FB_DBG(4);
     tcgen05_fence_after();
     float dsum = 0.f;
 #pragma unroll 1
@@ -205,9 +231,10 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         float o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (p.bias) x += __ldg(p.bias + n + j);
-          x = apply_act_rt(x, p.act);
+          float x = __uint_as_float(v[j]) + s_bias[c + j];
+          // bf16 mode: fast exp/reciprocal (outputs are rounded to bf16 or feed fp32 sums at ~1e-6 rel)
+          if (p.act == FB_ACT_SILU) x = x * __frcp_rn(1.0f + __expf(-x));
+          else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
         if (p.res) {
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         }
         if (p.dotv) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dsum = fmaf(__ldg(p.dotv + n + j), o[j], dsum);
+          for (int j = 0; j < 32; ++j) dsum = fmaf(s_dot[c + j], o[j], dsum);
         }
         if (p.C) {
           float* cp = p.C + (size_t)m * p.ldc + n;
@@ -242,9 +269,11 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       }
     }
     if (p.dotv && m < M) p.dot_out[(size_t)blockIdx.x * p.dot_stride + m] = dsum;
+    if (threadIdx.x == 64) FB_DBG(5);
     tcgen05_fence_before();
   }
   __syncthreads();
+  if (threadIdx.x == 0) FB_DBG(6);
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
@@ -303,10 +332,22 @@ bool gemm_tc_supported(const GemmArgs& g) {
 
 int gemm_tc_dot_tiles(int N) { return N / tc::BN_SEL; }
 
+template <int BN, int STAGES>
+static int launch_cfg(const GemmArgs& g, cudaStream_t st);
+
+long long* g_tc_dbg = nullptr;   // set through fb_gemm_set_debug (development probe)
+
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t st) {
+  static int stages = [] { const char* e = getenv("FB_TC_STAGES"); return e ? atoi(e) : tc::STAGES_SEL; }();
+  if (stages == 4) return launch_cfg<tc::BN_SEL, 4>(g, st);
+  if (stages == 6) return launch_cfg<tc::BN_SEL, 6>(g, st);
+  return launch_cfg<tc::BN_SEL, 3>(g, st);
+}
+
+template <int BN, int STAGES>
+static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
   using namespace tc;
   if (g.M <= 0) return FB_OK;
-  constexpr int BN = BN_SEL, STAGES = STAGES_SEL;
   using S = Smem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -327,6 +368,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t st) {
   p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.m_dev = g.m_dev;
   p.bias = g.bias; p.act = g.act; p.res = g.res; p.ldres = g.ldres; p.C = g.C; p.ldc = g.ldc;
   p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb; p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
+  p.dbg = g_tc_dbg;
   dim3 grid(g.N / BN, (g.M + BM - 1) / BM);
   gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, S::TOTAL, st>>>(ma, ma2, mw, p);
   count_launch(1);
