@@ -18,7 +18,7 @@ class ModelParams(C.Structure):
         ("N", C.c_int32), ("B", C.c_int32), ("Nc_tot", C.c_int32), ("P_total", C.c_int32),
         ("hidden", C.c_int32), ("n_layers", C.c_int32), ("n_iter", C.c_int32), ("n_bond", C.c_int32),
         ("n_las", C.c_int32), ("E_ctx", C.c_int32), ("cap_int", C.c_int32), ("bf16_mode", C.c_int32),
-        ("fb_atom", C.c_int32), ("fb_res", C.c_int32),
+        ("max_c", C.c_int32), ("max_p", C.c_int32), ("fb_atom", C.c_int32), ("fb_res", C.c_int32),
         ("intra_cutoff", C.c_float), ("inter_cutoff", C.c_float), ("coord_clamp", C.c_float),
         ("las_clamp", C.c_float), ("las_step", C.c_float),
         ("X_in", C.c_void_p), ("H_in", C.c_void_p), ("X_las", C.c_void_p), ("bonds", C.c_void_p), ("las", C.c_void_p),

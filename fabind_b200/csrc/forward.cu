@@ -105,7 +105,7 @@ static void build_weights(int H, int L, ModelW& w) {
     a.tp2_w = add(p + "tp2_w", H, 2 * H); a.tp2_b = add(p + "tp2_b", 1, H);
     a.tc1_w = add(p + "tc1_w", 2 * H, H); a.tc1_b = add(p + "tc1_b", 1, 2 * H);
     a.tc2_w = add(p + "tc2_w", H, 2 * H); a.tc2_b = add(p + "tc2_b", 1, H);
-    a.i32_o_w = add(p + "i32_o_w", H, 32); a.i32_o_b = add(p + "i32_o_b", 1, H);
+    a.i32_o_w = add(p + "i32_o_w", 32, H);  /* stored transposed */ a.i32_o_b = add(p + "i32_o_b", 1, H);
     a.pt1_w = add(p + "pt1_w", 2 * H, H); a.pt1_b = add(p + "pt1_b", 1, 2 * H);
     a.pt2v = add(p + "pt2v", 1, 2 * H); a.pt_c = add(p + "pt_c", 1, 1);
     a.qk_w = add(p + "qk_w", 2 * H + QKX, H); a.qk_b = add(p + "qk_b", 1, 2 * H + QKX); a.k_r = add(p + "k_r", 1, H);
@@ -287,14 +287,14 @@ struct Run {
     gemm(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0);
     const float* CApv = b.CAp - (size_t)Nc * 2 * HD;  // virtual base indexed by internal node id
     stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 1, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
+      return row_attention(g, 1, p.max_p, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
                            b.PB + (size_t)(layer * 2 + 0) * P * 4, b.O, HD, bf, st);
     });
     gemm(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
     gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
     const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
     stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 0, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
+      return row_attention(g, 0, p.max_c, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
                            b.PB + (size_t)(layer * 2 + 1) * P * 4, b.O, HD, bf, st);
     });
     gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);

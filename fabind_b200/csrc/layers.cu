@@ -175,24 +175,50 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
 // GCL node stage (egnn.py:97, 119-128): agg[r,:] = sum_e M[e,:]   (segment sum over the CSR row)
 //   x_out[r] = x[r] + clamp(mean_e (x[r]-x[col]) * s_e, +-cmax),  s_e = sum of the row-dot partials
 // ------------------------------------------------------------------------------------------------
-// One CTA (4 warps) per node: warp w takes the edges lo+w, lo+w+4, ... (4 independent streams keep
-// loads in flight; high-degree global nodes are split four ways), lanes run over features in
-// 8-byte/16-byte vectors; the four partial rows are combined through shared memory.
+// One CTA (256 threads) per node: thread = (edge group g in 0..3, feature lane t in 0..63); a lane owns 8
+// consecutive features (16-byte loads in bf16 mode), the four edge groups take edges lo+g, lo+g+4, ...
+// with two loads in flight each, and are combined through shared memory.
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+  u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(128) gcl_node_kernel(int N, int H, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* __restrict__ rowptr,
                                                        const int* __restrict__ ecol, const T* __restrict__ M,
                                                        const float* __restrict__ dot, int dot_tiles, int dot_stride,
                                                        const float* __restrict__ x, float cmax, T* __restrict__ agg,
                                                        float* __restrict__ x_out) {
   extern __shared__ float part[];  // [4][H]
-  const int r = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x, grp = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
   const int lo = rowptr[r], hi = rowptr[r + 1];
-  if (w == 0) {
+  if (threadIdx.x < 32) {
     const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
     float ax = 0.f, ay = 0.f, az = 0.f;
     for (int e = lo + lane; e < hi; e += 32) {
       float s = 0.f;
-      for (int t = 0; t < dot_tiles; ++t) s += dot[(size_t)t * dot_stride + e];
+      for (int k = 0; k < dot_tiles; ++k) s += dot[(size_t)k * dot_stride + e];
       const int c = ecol[e];
       ax = fmaf(xr0 - x[3 * c], s, ax);
       ay = fmaf(xr1 - x[3 * c + 1], s, ay);
@@ -207,33 +233,42 @@ __global__ void __launch_bounds__(128) gcl_node_kernel(int N, int H, const int* 
     }
   }
   if (agg == nullptr) return;
-  for (int f0 = lane * 4; f0 < H; f0 += 128) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int e = lo + w;
-    for (; e + 4 < hi; e += 8) {  // two loads in flight per warp
-      const float4 m0 = ld4(M + (size_t)e * H + f0), m1 = ld4(M + (size_t)(e + 4) * H + f0);
-      acc.x += m0.x + m1.x; acc.y += m0.y + m1.y; acc.z += m0.z + m1.z; acc.w += m0.w + m1.w;
+  for (int f0 = t * 8; f0 < H; f0 += 512) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int e = lo + grp;
+    for (; e + 4 < hi; e += 8) {
+      float a[8], b[8];
+      ld8(M + (size_t)e * H + f0, a);
+      ld8(M + (size_t)(e + 4) * H + f0, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += a[i] + b[i];
     }
     for (; e < hi; e += 4) {
-      const float4 m0 = ld4(M + (size_t)e * H + f0);
-      acc.x += m0.x; acc.y += m0.y; acc.z += m0.z; acc.w += m0.w;
+      float a[8];
+      ld8(M + (size_t)e * H + f0, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += a[i];
     }
-    *reinterpret_cast<float4*>(&part[w * H + f0]) = acc;
+    st8(&part[grp * H + f0], acc);
   }
   __syncthreads();
-  for (int f = threadIdx.x * 4; f < H; f += 512) {
-    const float4 a = *reinterpret_cast<const float4*>(&part[f]), b = *reinterpret_cast<const float4*>(&part[H + f]);
-    const float4 c = *reinterpret_cast<const float4*>(&part[2 * H + f]), d = *reinterpret_cast<const float4*>(&part[3 * H + f]);
-    st4(agg + (size_t)r * H + f, make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z),
-                                             (a.w + b.w) + (c.w + d.w)));
+  if (grp == 0) {
+    for (int f0 = t * 8; f0 < H; f0 += 512) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o[i] = (part[f0 + i] + part[H + f0 + i]) + (part[2 * H + f0 + i] + part[3 * H + f0 + i]);
+      st8(agg + (size_t)r * H + f0, o);
+    }
   }
 }
 
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
+  if (H & 7) return FB_ERR_UNSUPPORTED;
   const int smem = 4 * H * 4;
-  if (bf16_mode) gcl_node_kernel<bf16><<<N, 128, smem, st>>>(N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
-  else gcl_node_kernel<float><<<N, 128, smem, st>>>(N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  if (bf16_mode) gcl_node_kernel<bf16><<<N, 256, smem, st>>>(N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
+  else gcl_node_kernel<float><<<N, 256, smem, st>>>(N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -298,73 +333,126 @@ int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// RowAttentionBlock core (cross_att.py:118-134, model_utils.py:21-38,96-133): one warp per
-// (query node, head); keys are the nodes of the other side of the same complex.
-// 4 heads x 32 channels.  O[q, h*32+d] = sigmoid(G) * softmax_j(q.k_j/sqrt(32) + bias) v_j
+// RowAttentionBlock core (cross_att.py:118-134, model_utils.py:21-38,96-133).  4 heads x 32 channels.
+//   O[q, h*32+d] = sigmoid(G) * softmax_j(q.k_j/sqrt(32) + bias) v_j
+// One CTA = (tile of 8 queries, complex, head); the keys/values of that head (the other side of the same
+// complex) are staged in shared memory 128 at a time; each of the 4 warps owns 2 queries and runs an
+// online softmax over the key chunks.  K rows are padded to 33 floats so that "lane = key" reads are
+// bank-conflict free; "lane = channel" reads of V are conflict free by construction.
 // ------------------------------------------------------------------------------------------------
+constexpr int RA_QT = 8, RA_KC = 128;
+
 template <typename T>
-__global__ void row_attention_kernel(GraphDev g, int q_is_prot, const float* __restrict__ Q, int ldq,
-                                     const float* __restrict__ G, int ldg, const float* __restrict__ Kb, int ldk,
-                                     const float* __restrict__ Vb, int ldv, const float* __restrict__ PB,
-                                     T* __restrict__ O, int ldo) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int n_q = q_is_prot ? (g.N - g.Nc_tot) : g.Nc_tot;
-  if (warp >= n_q * 4) return;
-  const int head = warp & 3;
-  const int qn = (q_is_prot ? g.Nc_tot : 0) + (warp >> 2);
-  const int b = g.node_cplx[qn];
-  const int c_lo = g.c_off[b], nc1 = g.c_off[b + 1] - c_lo, p_lo = g.p_off[b];
-  const int k_lo = q_is_prot ? c_lo : p_lo;
-  const int n_k = q_is_prot ? nc1 : (g.p_off[b + 1] - p_lo);
-  const int q_loc = qn - (q_is_prot ? p_lo : c_lo);
+__global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is_prot, const float* __restrict__ Q, int ldq,
+                                                            const float* __restrict__ G, int ldg,
+                                                            const float* __restrict__ Kb, int ldk,
+                                                            const float* __restrict__ Vb, int ldv,
+                                                            const float* __restrict__ PB, T* __restrict__ O, int ldo) {
+  __shared__ float sK[RA_KC][33];
+  __shared__ float sV[RA_KC][32];
+  const int b = blockIdx.y, head = blockIdx.z;
+  const int c_lo = g.c_off[b], nc1 = g.c_off[b + 1] - c_lo, p_lo = g.p_off[b], np1 = g.p_off[b + 1] - p_lo;
+  const int n_q = q_is_prot ? np1 : nc1, n_k = q_is_prot ? nc1 : np1;
+  const int q_lo = q_is_prot ? p_lo : c_lo, k_lo = q_is_prot ? c_lo : p_lo;
+  const int q0 = blockIdx.x * RA_QT;
+  if (q0 >= n_q) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  float q[32];
-  {
-    const float* qp = Q + (size_t)qn * ldq + head * 32;
+  // the two queries of this warp: q_loc = q0 + warp*2 + {0,1}
+  float qv[2][32];
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, acc[2] = {0.f, 0.f};
+  int qn[2];
 #pragma unroll
-    for (int d = 0; d < 32; d += 4) {
-      const float4 v = ld4(qp + d);
-      q[d] = v.x * scale; q[d + 1] = v.y * scale; q[d + 2] = v.z * scale; q[d + 3] = v.w * scale;
-    }
-  }
-  float m = -INFINITY, l = 0.f, acc = 0.f;  // acc: lane = channel d
-  for (int j0 = 0; j0 < n_k; j0 += 32) {
-    const int j = j0 + lane;
-    float s = -INFINITY;
-    if (j < n_k) {
-      const float* kp = Kb + (size_t)(k_lo + j) * ldk + head * 32;
-      float dsum = 0.f;
+  for (int u = 0; u < 2; ++u) {
+    const int q_loc = q0 + warp * 2 + u;
+    qn[u] = q_loc < n_q ? q_lo + q_loc : -1;
+    if (qn[u] >= 0) {
+      const float* qp = Q + (size_t)qn[u] * ldq + head * 32;
 #pragma unroll
       for (int d = 0; d < 32; d += 4) {
-        const float4 kv = ld4(kp + d);
-        dsum = fmaf(q[d], kv.x, dsum); dsum = fmaf(q[d + 1], kv.y, dsum);
-        dsum = fmaf(q[d + 2], kv.z, dsum); dsum = fmaf(q[d + 3], kv.w, dsum);
+        const float4 v = ld4(qp + d);
+        qv[u][d] = v.x * scale; qv[u][d + 1] = v.y * scale; qv[u][d + 2] = v.z * scale; qv[u][d + 3] = v.w * scale;
       }
-      const int pair = g.pair_base[b] + (q_is_prot ? (q_loc * nc1 + j) : (j * nc1 + q_loc));
-      s = dsum + PB[(size_t)pair * 4 + head];
+    } else {
+#pragma unroll
+      for (int d = 0; d < 32; ++d) qv[u][d] = 0.f;
     }
-    const float m_new = fmaxf(m, warp_max(s));
-    const float corr = expf(m - m_new);  // m = -inf on the first chunk -> 0
-    const float p = j < n_k ? expf(s - m_new) : 0.f;
-    l = l * corr + warp_sum(p);
-    acc *= corr;
-    const int cnt = min(32, n_k - j0);
-    for (int jj = 0; jj < cnt; ++jj) {
-      const float pj = __shfl_sync(0xffffffffu, p, jj);
-      acc = fmaf(pj, Vb[(size_t)(k_lo + j0 + jj) * ldv + head * 32 + lane], acc);
-    }
-    m = m_new;
   }
-  const float gate = sigmoidf(G[(size_t)qn * ldg + head * 32 + lane]);
-  O[(size_t)qn * ldo + head * 32 + lane] = from_f<T>(acc / l * gate);
+  for (int j0 = 0; j0 < n_k; j0 += RA_KC) {
+    const int cnt = min(RA_KC, n_k - j0);
+    __syncthreads();
+    const int cnt32 = (cnt + 31) & ~31;   // rows [cnt, cnt32) are zero-filled: they are multiplied by p == 0
+    for (int i = threadIdx.x; i < cnt32 * 8; i += 128) {
+      const int j = i >> 3, d4 = (i & 7) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (j < cnt) {
+        kv = ld4(Kb + (size_t)(k_lo + j0 + j) * ldk + head * 32 + d4);
+        vv = ld4(Vb + (size_t)(k_lo + j0 + j) * ldv + head * 32 + d4);
+      }
+      sK[j][d4] = kv.x; sK[j][d4 + 1] = kv.y; sK[j][d4 + 2] = kv.z; sK[j][d4 + 3] = kv.w;
+      *reinterpret_cast<float4*>(&sV[j][d4]) = vv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (qn[u] < 0) continue;   // warp-uniform
+      const int q_loc = qn[u] - q_lo;
+      float sc[RA_KC / 32];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < RA_KC / 32; ++t) {
+        const int j = t * 32 + lane;
+        float v = -INFINITY;
+        if (j < cnt) {
+          float dsum = 0.f;
+#pragma unroll
+          for (int d = 0; d < 32; ++d) dsum = fmaf(qv[u][d], sK[j][d], dsum);
+          const int jj = j0 + j;
+          const int pair = g.pair_base[b] + (q_is_prot ? (q_loc * nc1 + jj) : (jj * nc1 + q_loc));
+          v = dsum + PB[(size_t)pair * 4 + head];
+        }
+        sc[t] = v;
+        cmax = fmaxf(cmax, v);
+      }
+      const float m_new = fmaxf(m[u], warp_max(cmax));
+      const float corr = expf(m[u] - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int t = 0; t < RA_KC / 32; ++t) {
+        sc[t] = (t * 32 + lane < cnt) ? expf(sc[t] - m_new) : 0.f;
+        psum += sc[t];
+      }
+      l[u] = l[u] * corr + warp_sum(psum);
+      float a = acc[u] * corr;
+#pragma unroll
+      for (int t = 0; t < RA_KC / 32; ++t) {
+        if (t * 32 < cnt) {
+#pragma unroll 8
+          for (int jj = 0; jj < 32; ++jj) {
+            const float pj = __shfl_sync(0xffffffffu, sc[t], jj);
+            a = fmaf(pj, sV[t * 32 + jj][lane], a);
+          }
+        }
+      }
+      acc[u] = a;
+      m[u] = m_new;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (qn[u] < 0) continue;
+    const float gate = sigmoidf(G[(size_t)qn[u] * ldg + head * 32 + lane]);
+    O[(size_t)qn[u] * ldo + head * 32 + lane] = from_f<T>(acc[u] / l[u] * gate);
+  }
 }
 
-int row_attention(const GraphDev& g, int q_is_prot, const float* Q, int ldq, const float* G, int ldg, const float* K,
-                  int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode, cudaStream_t st) {
-  const int n_q = q_is_prot ? (g.N - g.Nc_tot) : g.Nc_tot;
-  if (n_q <= 0) return FB_OK;
-  if (bf16_mode) row_attention_kernel<bf16><<<warp_grid((long long)n_q * 4), 256, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (bf16*)O, ldo);
-  else row_attention_kernel<float><<<warp_grid((long long)n_q * 4), 256, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (float*)O, ldo);
+int row_attention(const GraphDev& g, int q_is_prot, int max_q, const float* Q, int ldq, const float* G, int ldg,
+                  const float* K, int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode,
+                  cudaStream_t st) {
+  if (max_q <= 0) return FB_OK;
+  dim3 grid((max_q + RA_QT - 1) / RA_QT, g.B, 4);
+  if (bf16_mode) row_attention_kernel<bf16><<<grid, 128, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (bf16*)O, ldo);
+  else row_attention_kernel<float><<<grid, 128, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (float*)O, ldo);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -381,13 +469,11 @@ int row_attention(const GraphDev& g, int q_is_prot, const float* Q, int ldq, con
 template <typename T>
 __global__ void __launch_bounds__(256) pair_zin_kernel(GraphDev g, int H, const T* __restrict__ P0,
                                                        const float* __restrict__ pc32, int ld32,
-                                                       const float* __restrict__ Wo /*[H,32]*/, const float* __restrict__ bo,
+                                                       const float* __restrict__ Wo /*[32,H] = linear_out.weight^T*/, const float* __restrict__ bo,
                                                        T* __restrict__ Zin) {
-  extern __shared__ float wt[];  // [32][H]
-  for (int i = threadIdx.x; i < H * 32; i += blockDim.x) {
-    const int f = i >> 5, k = i & 31;  // coalesced read of Wo[f][k]
-    wt[k * H + f] = Wo[i];
-  }
+  extern __shared__ float wt[];  // [32][H], the weight slot is stored pre-transposed
+  for (int i = threadIdx.x * 4; i < H * 32; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(&wt[i]) = *reinterpret_cast<const float4*>(&Wo[i]);
   __syncthreads();
   const int U = g.int_rowptr[g.Nc_tot];
   const int warps_per_cta = blockDim.x >> 5;
@@ -454,25 +540,31 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 //   x[r]   += clamp(sum_e alpha_e * s_e * (x[r]-x[c]), +-cmax),  s_e = w2 . SiLU(VC[c] + rn*u + b1)
 // One warp per row, single pass with an online softmax.
 // ------------------------------------------------------------------------------------------------
+// One CTA (4 warps) per row: warp w takes the edges lo+w, lo+w+4, ... with its own online softmax; the
+// four partial states (max, sum, feature accumulator, coordinate accumulator) are merged through smem.
 template <typename T, int VEC>
-__global__ void inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | k | ...*/, int ldqk,
-                                       const float* __restrict__ V, const float* __restrict__ VC,
-                                       const float* __restrict__ k_r, const float* __restrict__ v_r,
-                                       const float* __restrict__ ac_u, const float* __restrict__ ac_b,
-                                       const float* __restrict__ ac_w2, const float* __restrict__ rad,
-                                       const float* __restrict__ norm, const float* __restrict__ pb_dense,
-                                       const float* __restrict__ x, float cmax, float* __restrict__ h, T* __restrict__ hT,
-                                       float* __restrict__ x_out, float* __restrict__ att_logit) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= g.N) return;
-  const int r = warp, lo = g.int_rowptr[r], hi = g.int_rowptr[r + 1];
+__global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | k | ...*/, int ldqk,
+                                                              const float* __restrict__ V, const float* __restrict__ VC,
+                                                              const float* __restrict__ k_r, const float* __restrict__ v_r,
+                                                              const float* __restrict__ ac_u, const float* __restrict__ ac_b,
+                                                              const float* __restrict__ ac_w2, const float* __restrict__ rad,
+                                                              const float* __restrict__ norm, const float* __restrict__ pb_dense,
+                                                              const float* __restrict__ x, float cmax, float* __restrict__ h,
+                                                              T* __restrict__ hT, float* __restrict__ x_out,
+                                                              float* __restrict__ att_logit) {
+  extern __shared__ float sm[];     // [4][H] accumulators | [4] m | [4] l | [4][3] x
+  float* s_acc = sm;
+  float* s_m = sm + 4 * H;
+  float* s_l = s_m + 4;
+  float* s_x = s_l + 4;
+  const int r = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lo = g.int_rowptr[r], hi = g.int_rowptr[r + 1];
   const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
   if (lo == hi) {
-    if (lane == 0) { x_out[3 * r] = xr0; x_out[3 * r + 1] = xr1; x_out[3 * r + 2] = xr2; }
+    if (threadIdx.x == 0) { x_out[3 * r] = xr0; x_out[3 * r + 1] = xr1; x_out[3 * r + 2] = xr2; }
     return;
   }
   const float inv_norm = 1.0f / norm[g.node_cplx[r]];
-  // VEC float4 chunks per lane: features f = (i*32 + lane)*4
   float4 q[VEC], acc[VEC];
   float qkr = 0.f;
 #pragma unroll
@@ -487,7 +579,7 @@ __global__ void inter_attention_kernel(GraphDev g, int H, const float* __restric
   }
   qkr = warp_sum(qkr);
   float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-  for (int e = lo; e < hi; ++e) {
+  for (int e = lo + w; e < hi; e += 4) {
     const int c = g.int_col[e];
     const float rn = rad[e] * inv_norm;
     float dot = 0.f, sdot = 0.f;
@@ -497,11 +589,12 @@ __global__ void inter_attention_kernel(GraphDev g, int H, const float* __restric
       const int f = (i * 32 + lane) * 4;
       if (f < H) {
         const float4 kk = ld4(QK + (size_t)c * ldqk + H + f);
+        const float4 vc = ld4(VC + (size_t)c * H + f);
+        const float4 v0 = ld4(V + (size_t)c * H + f);
+        const float4 uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f), vr = ld4(v_r + f);
         dot += q[i].x * kk.x + q[i].y * kk.y + q[i].z * kk.z + q[i].w * kk.w;
-        const float4 vc = ld4(VC + (size_t)c * H + f), uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f);
         sdot += w2.x * silu(vc.x + fmaf(rn, uu.x, bb.x)) + w2.y * silu(vc.y + fmaf(rn, uu.y, bb.y)) +
                 w2.z * silu(vc.z + fmaf(rn, uu.z, bb.z)) + w2.w * silu(vc.w + fmaf(rn, uu.w, bb.w));
-        const float4 v0 = ld4(V + (size_t)c * H + f), vr = ld4(v_r + f);
         vv[i] = make_float4(fmaf(rn, vr.x, v0.x), fmaf(rn, vr.y, v0.y), fmaf(rn, vr.z, v0.z), fmaf(rn, vr.w, v0.w));
       } else vv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -523,25 +616,40 @@ __global__ void inter_attention_kernel(GraphDev g, int H, const float* __restric
     }
     m = m_new;
   }
-  const float il = 1.0f / l;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const int f = (i * 32 + lane) * 4;
-    if (f < H) {
-      float4 hv = ld4(h + (size_t)r * H + f);
-      hv.x += acc[i].x * il; hv.y += acc[i].y * il; hv.z += acc[i].z * il; hv.w += acc[i].w * il;
-      st4(h + (size_t)r * H + f, hv);
-      if (hT) st4(hT + (size_t)r * H + f, hv);
-    }
+    if (f < H) *reinterpret_cast<float4*>(&s_acc[w * H + f]) = acc[i];
   }
-  if (lane == 0) {
-    x_out[3 * r] = xr0 + fminf(fmaxf(ax * il, -cmax), cmax);
-    x_out[3 * r + 1] = xr1 + fminf(fmaxf(ay * il, -cmax), cmax);
-    x_out[3 * r + 2] = xr2 + fminf(fmaxf(az * il, -cmax), cmax);
+  if (lane == 0) { s_m[w] = m; s_l[w] = l; s_x[w * 3] = ax; s_x[w * 3 + 1] = ay; s_x[w * 3 + 2] = az; }
+  __syncthreads();
+  const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+  float sc[4], L = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { sc[k] = expf(s_m[k] - M); L += s_l[k] * sc[k]; }   // empty warps: exp(-inf) = 0
+  const float il = 1.0f / L;
+  for (int f = threadIdx.x * 4; f < H; f += 512) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&s_acc[k * H + f]);
+      o.x = fmaf(a.x, sc[k], o.x); o.y = fmaf(a.y, sc[k], o.y); o.z = fmaf(a.z, sc[k], o.z); o.w = fmaf(a.w, sc[k], o.w);
+    }
+    float4 hv = ld4(h + (size_t)r * H + f);
+    hv.x += o.x * il; hv.y += o.y * il; hv.z += o.z * il; hv.w += o.w * il;
+    st4(h + (size_t)r * H + f, hv);
+    if (hT) st4(hT + (size_t)r * H + f, hv);
+  }
+  if (threadIdx.x == 0) {
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { dx = fmaf(s_x[k * 3], sc[k], dx); dy = fmaf(s_x[k * 3 + 1], sc[k], dy); dz = fmaf(s_x[k * 3 + 2], sc[k], dz); }
+    x_out[3 * r] = xr0 + fminf(fmaxf(dx * il, -cmax), cmax);
+    x_out[3 * r + 1] = xr1 + fminf(fmaxf(dy * il, -cmax), cmax);
+    x_out[3 * r + 2] = xr2 + fminf(fmaxf(dz * il, -cmax), cmax);
   }
   if (att_logit) {
-    __syncwarp();
-    for (int e = lo + lane; e < hi; e += 32) att_logit[e] = expf(att_logit[e] - m) * il;
+    for (int e = lo + threadIdx.x; e < hi; e += 128) att_logit[e] = expf(att_logit[e] - M) * il;
   }
 }
 
@@ -549,10 +657,11 @@ int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const f
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, bool bf16_mode, cudaStream_t st) {
-  const int grid = warp_grid(g.N);
+  const int grid = g.N;
+  const int smem = (4 * H + 32) * 4;
 #define FB_IA(T, VEC)                                                                                      \
-  inter_attention_kernel<T, VEC><<<grid, 256, 0, st>>>(g, H, QK, ldqk, V, VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
-                                                       norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
+  inter_attention_kernel<T, VEC><<<grid, 128, smem, st>>>(g, H, QK, ldqk, V, VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
+                                                          norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   if (bf16_mode) {
     if (H <= 128) FB_IA(bf16, 1); else if (H <= 256) FB_IA(bf16, 2); else FB_IA(bf16, 4);

@@ -19,6 +19,8 @@ class Layout:
     cap_int: int
     fb_atom: int
     fb_res: int
+    max_c: int
+    max_p: int
     blob: torch.Tensor      # int32 device blob holding perm|inv|node_cplx|c_off|p_off|pair_base
     flags: torch.Tensor     # uint8 device [N]
     offs: dict              # name -> element offset in blob
@@ -78,4 +80,4 @@ def build_layout(batch_id, segment_id, is_global, mask, device):
     blob = torch.from_numpy(np.concatenate(chunks)).to(device, non_blocking=True)
     flags_t = torch.from_numpy(flags).to(device, non_blocking=True)
     return Layout(N=N, B=B, Nc_tot=Nc_tot, P_total=int(pair_base[-1]), cap_int=cap_int, fb_atom=int(fb_atom),
-                  fb_res=int(fb_res), blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p)
+                  fb_res=int(fb_res), max_c=int(nc1.max()), max_p=int(np1.max()), blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p)

@@ -88,6 +88,7 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.n_bond, p.n_las = bonds.shape[1], las.shape[1]
     p.E_ctx, p.cap_int, p.bf16_mode = 0, lay.cap_int, 1 if bf16 else 0
     p.fb_atom, p.fb_res = lay.fb_atom, lay.fb_res
+    p.max_c, p.max_p = lay.max_c, lay.max_p
     p.intra_cutoff, p.inter_cutoff = cfg["intra_cutoff"], cfg["inter_cutoff"]
     p.coord_clamp, p.las_clamp, p.las_step = cfg["coord_clamp"], cfg["las_clamp"], cfg["las_step"]
     p.X_in, p.H_in, p.X_las = xv.data_ptr(), Hc.data_ptr(), xl.data_ptr()

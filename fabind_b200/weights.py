@@ -68,7 +68,7 @@ def _att(sd, p, H):
         "tp2_w": sd[ca + "p_transition.linear_2.weight"], "tp2_b": sd[ca + "p_transition.linear_2.bias"],
         "tc1_w": sd[ca + "c_transition.linear_1.weight"], "tc1_b": sd[ca + "c_transition.linear_1.bias"],
         "tc2_w": sd[ca + "c_transition.linear_2.weight"], "tc2_b": sd[ca + "c_transition.linear_2.bias"],
-        "i32_o_w": sd[ca + "inter_layer.linear_out.weight"], "i32_o_b": sd[ca + "inter_layer.linear_out.bias"],
+        "i32_o_w": sd[ca + "inter_layer.linear_out.weight"].t().contiguous(), "i32_o_b": sd[ca + "inter_layer.linear_out.bias"],
         "pt1_w": sd[ca + "pair_transition.linear_1.weight"], "pt1_b": sd[ca + "pair_transition.linear_1.bias"],
         "pt2v": W2.t() @ wb, "pt_c": (wb @ b2 + bb).reshape(1),
         # q | k | inter_layer.linear_p (32) | inter_layer.linear_c (32) | zero pad: one stacked node GEMM

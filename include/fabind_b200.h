@@ -38,6 +38,7 @@ typedef struct fb_model_params {
   int32_t E_ctx;      /* context edges (bonds + geometric); read back after fb_graph_static */
   int32_t cap_int;    /* capacity of the interface edge list: 2 * sum n_c*n_p (worst case) */
   int32_t bf16_mode;  /* 0: fp32 parity mode (FFMA GEMMs); 1: bf16 operands, fp32 accumulate (tcgen05) */
+  int32_t max_c, max_p;    /* largest compound-side / protein-side node count of any complex (launch bounds) */
   int32_t fb_atom, fb_res; /* internal ids of the first ligand atom / first residue of complex 0 (att_model.py:85-86) */
   /* ---- geometry constants, already divided by coordinate_scale ---- */
   float intra_cutoff, inter_cutoff;   /* att_model.py:34-35 */
