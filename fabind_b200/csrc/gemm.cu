@@ -1,16 +1,34 @@
 // GEMM dispatch: tcgen05 (bf16 operands, TMA-fed, TMEM accumulators) when the shape qualifies,
-// otherwise the SIMT kernel.
+// otherwise the SIMT kernel.  tcgen05 has two kernels: v2 (persistent, double-buffered TMEM, default) and
+// v1 (one tile per CTA; FB_TC_V=1 selects it for A/B comparisons).
+#include <cstdlib>
+
 #include "gemm.h"
 
 namespace fb {
 
+bool gemm_tc2_shape_ok(int N);
+int gemm_tc2_dot_tiles(int N);
+int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st);
+
+static int tc_version() {
+  static int v = [] { const char* e = getenv("FB_TC_V"); return e ? atoi(e) : 2; }();
+  return v;
+}
+
 int gemm_dot_tiles(int N, int K, bool bf16_mode) {
-  if (bf16_mode && gemm_tc_shape_ok(N, K)) return gemm_tc_dot_tiles(N);
+  if (bf16_mode && gemm_tc_shape_ok(N, K)) {
+    if (tc_version() == 2 && gemm_tc2_shape_ok(N)) return gemm_tc2_dot_tiles(N);
+    return gemm_tc_dot_tiles(N);
+  }
   return gemm_simt_dot_tiles(N);
 }
 
 int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
-  if (bf16_mode && gemm_tc_supported(g)) return gemm_tc_launch(g, st);
+  if (bf16_mode && gemm_tc_supported(g)) {
+    if (tc_version() == 2 && gemm_tc2_shape_ok(g.N)) return gemm_tc2_launch(g, st);
+    return gemm_tc_launch(g, st);
+  }
   return gemm_simt_launch(g, bf16_mode, st);
 }
 

@@ -1,0 +1,267 @@
+// Persistent tcgen05 GEMM (v2):  C[M,N] = epilogue([A|A2][M,K] * W[N,K]^T), bf16 operands, fp32 accumulation.
+//
+// One CTA per SM loops over output tiles (n fastest, so CTAs running side by side share A rows in L2):
+//   warp 0      TMA producer: 64-wide K slabs of A (128 rows) and W (BN rows) into a STAGES-deep smem ring
+//   warp 1      MMA issuer: tcgen05.mma 128 x BN x 16 into one of TWO TMEM accumulator stages
+//   warps 2-9   epilogue: tcgen05.ld of the finished accumulator while the next tile's MMAs run; bias /
+//               activation / fused Linear(H,1) row-dot in the "thread = row" layout, then a 32x32 transpose
+//               through padded shared memory so that global stores (and residual loads) are row-contiguous.
+// The smem ring and its phases run continuously across tiles, so the tensor pipe only waits for TMA at the
+// very first tile.
+#include <cstdlib>
+
+#include "gemm.h"
+#include "tc_common.cuh"
+
+namespace fb {
+
+bool tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+namespace tc2 {
+using namespace tc;
+
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;   // 320
+constexpr int MAX_N = 1280;                     // bias / dot vectors staged for the whole N
+
+struct Params {
+  int M, N, KB1, KB2;
+  const int* m_dev;
+  const float* bias; int act;
+  const float* res; int ldres;
+  float* C; int ldc;
+  bf16* Cb; int ldcb;
+  const float* dotv; float* dot_out; int dot_stride;
+};
+
+template <int BN, int STAGES>
+struct Smem {
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                       // full[S] empty[S] tfull[2] tempty[2] slot
+  static constexpr int VEC_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;        // bias[MAX_N] | dotv[MAX_N]
+  static constexpr int XPOSE_OFF = VEC_OFF + 2 * MAX_N * 4;                  // EPI_WARPS x [32][33] floats
+  static constexpr int TOTAL = XPOSE_OFF + EPI_WARPS * 32 * 33 * 4 + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                               const __grid_constant__ CUtensorMap map_a2,
+                                                               const __grid_constant__ CUtensorMap map_w, Params p) {
+  using S = Smem<BN, STAGES>;
+  int M = p.M;
+  if (p.m_dev) M = min(M, *p.m_dev);
+  const int n_tiles_n = p.N / BN;
+  const int n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
+  if ((int)blockIdx.x >= n_tiles) return;   // whole CTA, before any barrier/TMEM state exists
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* s_bias = (float*)(smem + S::VEC_OFF);
+  float* s_dot = s_bias + MAX_N;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.KB1 + p.KB2;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w) : "memory");
+    if (p.KB2) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a2) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int t = threadIdx.x; t < p.N; t += THREADS) {
+    s_bias[t] = p.bias ? p.bias[t] : 0.f;
+    s_dot[t] = p.dotv ? p.dotv[t] : 0.f;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + S::A_BYTES;
+          mbar_expect_tx(&full[s], S::STAGE_BYTES);
+          if (kb < p.KB1) tma_load_2d(&map_a, &full[s], a_dst, kb * BK, m0);
+          else tma_load_2d(&map_a2, &full[s], a_dst, (kb - p.KB1) * BK, m0);
+          tma_load_2d(&map_w, &full[s], b_dst, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const int a = lt & 1;
+        mbar_wait(&tempty[a], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          const uint8_t* a_src = smem + s * S::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(a_src), bdesc = make_smem_desc(a_src + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[a]);
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int e = warp - 2;                 // 0..7
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = e >> 2;                // column half of the tile
+    constexpr int COLS = BN / 2;            // columns per warp
+    float* xp = (float*)(smem + S::XPOSE_OFF) + e * 32 * 33;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int a = lt & 1;
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      mbar_wait(&tfull[a], (lt >> 1) & 1);
+      tcgen05_fence_after();
+      const int mrow = m0 + q * 32 + lane;       // row owned in the TMEM layout
+      float dsum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < COLS; cc += 32) {
+        const int c = half * COLS + cc;           // column inside the tile
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), v);
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) + s_bias[n0 + c + j];
+          if (p.act == FB_ACT_SILU) x = x * __frcp_rn(1.0f + __expf(-x));
+          else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
+          o[j] = x;
+        }
+        if (p.dotv) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dsum = fmaf(s_dot[n0 + c + j], o[j], dsum);
+        }
+        if (p.C || p.Cb) {
+          // transpose through smem: thread = row  ->  lane = column
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = o[j];
+          __syncwarp();
+          const int ncol = n0 + c;
+          if (p.C || p.res) {
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+              const int m = m0 + q * 32 + r;
+              if (m < M) {
+                float x = xp[r * 33 + lane];
+                if (p.res) x += p.res[(size_t)m * p.ldres + ncol + lane];
+                if (p.C) p.C[(size_t)m * p.ldc + ncol + lane] = x;
+                if (p.Cb) xp[r * 33 + lane] = x;     // keep the residual-added value for the bf16 copy
+              }
+            }
+            __syncwarp();
+          }
+          if (p.Cb) {
+            const int rr = lane >> 4, cp = (lane & 15) * 2;
+#pragma unroll 4
+            for (int r = 0; r < 32; r += 2) {
+              const int m = m0 + q * 32 + r + rr;
+              if (m < M) {
+                const __nv_bfloat162 t = __floats2bfloat162_rn(xp[(r + rr) * 33 + cp], xp[(r + rr) * 33 + cp + 1]);
+                *reinterpret_cast<__nv_bfloat162*>(p.Cb + (size_t)m * p.ldcb + ncol + cp) = t;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (p.dotv && mrow < M) {
+        // two warps (column halves) share a row: partial index = 2 * n_tile + half
+        p.dot_out[(size_t)((tile % n_tiles_n) * 2 + half) * p.dot_stride + mrow] = dsum;
+      }
+      // this warp is done reading the accumulator stage
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[a])) : "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+static int launch(const GemmArgs& g, cudaStream_t st) {
+  using S = Smem<BN, STAGES>;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+      return FB_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  CUtensorMap ma, ma2, mw;
+  const int K = g.K1 + g.K2;
+  if (!tc_make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K1, (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
+  if (g.K2 > 0) {
+    if (!tc_make_map(&ma2, g.A2, (uint64_t)g.M, (uint64_t)g.K2, (uint64_t)g.lda2, BM)) return FB_ERR_CUDA;
+  } else {
+    ma2 = ma;
+  }
+  if (!tc_make_map(&mw, g.W, (uint64_t)g.N, (uint64_t)K, (uint64_t)K, BN)) return FB_ERR_CUDA;
+  Params p;
+  p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.m_dev = g.m_dev;
+  p.bias = g.bias; p.act = g.act; p.res = g.res; p.ldres = g.ldres; p.C = g.C; p.ldc = g.ldc;
+  p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb; p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
+  const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_tc2_kernel<BN, STAGES><<<grid, THREADS, S::TOTAL, st>>>(ma, ma2, mw, p);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+}  // namespace tc2
+
+bool gemm_tc2_shape_ok(int N) { return N <= tc2::MAX_N; }
+int gemm_tc2_bn(int N) { return (N % 256) == 0 ? 256 : 128; }
+int gemm_tc2_dot_tiles(int N) { return 2 * (N / gemm_tc2_bn(N)); }
+
+int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0) return FB_OK;
+  if (gemm_tc2_bn(g.N) == 256) return tc2::launch<256, 3>(g, st);
+  return tc2::launch<128, 5>(g, st);
+}
+
+}  // namespace fb
