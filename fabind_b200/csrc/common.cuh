@@ -24,6 +24,27 @@ typedef __nv_bfloat16 bf16;
 
 namespace fb {
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// Every kernel of the library is launched with programmaticStreamSerialization and starts with
+// pdl_entry(): it lets the NEXT kernel in the stream begin scheduling its CTAs (launch latency and
+// prologue overlap this kernel's tail) and then waits until the PREVIOUS grid has completed and flushed.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
+
+bool pdl_enabled();   // forward.cu (FB_PDL=0 disables the launch attribute)
+
+template <typename... KArgs, typename... Args>
+inline void fb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // host-side bookkeeping (forward.cu): number of kernels launched, optional per-category event timing
 void count_launch(int n);
 void prof_begin(int category, cudaStream_t st);

@@ -2,6 +2,7 @@
 // sequence of EfficientMCAttModel.forward.  No allocation, no synchronisation: everything is enqueued
 // on the caller's stream.
 #include <atomic>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -19,6 +20,10 @@ extern long long* g_tc_dbg;
 // ------------------------------------------------------------------------------------------------
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+  static bool on = [] { const char* e = getenv("FB_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 struct ProfSpan { cudaEvent_t a, b; int cat; };
 static bool g_prof_on = false;
@@ -166,8 +171,8 @@ struct Bufs {
   // coordinates
   float *x_state, *xa, *xb, *xl;
   // node features
-  float *Hin32, *h, *pc, *Pn, *CAc, *CAp, *CAp2, *QK, *V32, *VC, *Hfin;
-  void *HinT, *hT, *agg, *T1, *O, *TH, *VT;
+  float *Hin32, *h, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
+  void *HinT, *hT, *agg, *T1, *O, *TH, *VT, *Pn, *QKT, *VCT;
   // pair
   void *P0, *A0, *Zin; float *PBraw, *PB, *pb_dense, *dotU;
   // edge
@@ -180,7 +185,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   const size_t TS = p.bf16_mode ? 2 : 4;
   const size_t Nc = p.Nc_tot, Np = N - Nc;
   const bool bf = p.bf16_mode;
-  const size_t tilesH = gemm_dot_tiles((int)H, (int)H, bf), tiles2H = gemm_dot_tiles((int)(2 * H), (int)H, bf);
+  const size_t tilesH = gemm_dot_tiles((int)E, (int)H, (int)H, bf), tiles2H = gemm_dot_tiles((int)(capI / 2), (int)(2 * H), (int)H, bf);
   b.ctx_row = a.get<int>(E); b.ctx_col = a.get<int>(E);
   b.int_row = a.get<int>(capI); b.int_col = a.get<int>(capI); b.int_pair = a.get<int>(capI);
   b.x_state = a.get<float>(3 * N); b.xa = a.get<float>(3 * N); b.xb = a.get<float>(3 * N); b.xl = a.get<float>(3 * N);
@@ -194,7 +199,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.PB = a.get<float>(P * L * 8);
   b.pb_dense = a.get<float>(P);
   // per-sub-layer temporaries
-  b.Pn = a.get<float>(N * 2 * H);
+  b.Pn = a.take(N * 2 * H * TS);
   b.radc = a.get<float>(E); b.normc = a.get<float>(p.B);
   b.A1 = a.take(E * H * TS); b.M = a.take(E * H * TS);
   b.dotE = a.get<float>(tilesH * E);
@@ -204,9 +209,10 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.Zin = a.take(capU * H * TS);
   b.dotU = a.get<float>(tiles2H * capU);
   b.radi = a.get<float>(capI); b.normi = a.get<float>(p.B);
-  b.QK = a.get<float>(N * (2 * H + QKX)); b.V32 = a.get<float>(N * H);
-  b.VT = bf ? a.take(N * H * TS) : (void*)b.V32;
-  b.VC = a.get<float>(N * H);
+  b.QK = a.get<float>(N * (2 * H + QKX));
+  b.QKT = bf ? a.take(N * (2 * H + QKX) * TS) : (void*)b.QK;   // typed copy: K rows are gathered per inter edge
+  b.VT = a.take(N * H * TS);
+  b.VCT = a.take(N * H * TS);
   // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
   b.A0 = a.take(P * H * TS);
   b.PBraw = a.get<float>(P * L * 16);
@@ -259,13 +265,13 @@ struct Run {
     const int E = p.E_ctx;
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
     gemm_cat = CAT_GEMM_NODE;
-    gemm(b.hT, H, H, gw.e1_rc, 2 * H, -1, FB_ACT_NONE, N, b.Pn, 2 * H, nullptr, 0);
+    gemm(b.hT, H, H, gw.e1_rc, 2 * H, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * H);
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_edge_pre(E, H, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st);
     });
     gemm_cat = CAT_GEMM_EDGE;
     gemm(b.A1, H, H, gw.e2_w, H, gw.e2_b, FB_ACT_SILU, E, nullptr, 0, b.M, H);
-    const int tiles = gemm_dot_tiles(H, H, bf);
+    const int tiles = gemm_dot_tiles(E, H, H, bf);
     gemm(b.M, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_SILU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st);
@@ -306,12 +312,12 @@ struct Run {
     // q | k of the interfacial attention stacked with the 32-channel interaction projections
     // (cross_att.py:22,51: linear_p on protein rows, linear_c on compound rows) in ONE node GEMM
     const int ldqk = 2 * H + QKX;
-    gemm(b.hT, H, H, aw.qk_w, ldqk, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, nullptr, 0);
+    gemm(b.hT, H, H, aw.qk_w, ldqk, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, b.QKT, ldqk);
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
     stage(CAT_ATTENTION, [&] { return pair_zin(g, capU, H, b.P0, b.QK + 2 * H, ldqk, F(aw.i32_o_w), F(aw.i32_o_b), b.Zin, bf, st); });
-    const int tiles2 = gemm_dot_tiles(2 * H, H, bf);
+    const int tiles2 = gemm_dot_tiles(capU, 2 * H, H, bf);
     gemm_cat = CAT_GEMM_PAIR;
     gemm(b.Zin, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0,
          aw.pt2v, b.dotU, capU, u_dev);
@@ -319,10 +325,10 @@ struct Run {
     stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
     // --- interfacial attention (egnn.py:186-252)
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
-    gemm(b.hT, H, H, aw.v_w, H, aw.v_b, FB_ACT_NONE, N, b.V32, H, b.VT, H);
-    gemm(b.VT, H, H, aw.ac1_w, H, -1, FB_ACT_NONE, N, b.VC, H, nullptr, 0);
+    gemm(b.hT, H, H, aw.v_w, H, aw.v_b, FB_ACT_NONE, N, nullptr, 0, b.VT, H);
+    gemm(b.VT, H, H, aw.ac1_w, H, -1, FB_ACT_NONE, N, nullptr, 0, b.VCT, H);
     stage(CAT_ATTENTION, [&] {
-      return inter_attention(g, H, b.QK, ldqk, b.V32, b.VC, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
+      return inter_attention(g, H, b.QK, ldqk, at(b.QKT, (size_t)H), ldqk, b.VT, b.VCT, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
                              b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st);
     });
   }
@@ -526,9 +532,9 @@ int32_t fb_gemm_set_debug(int64_t* dbg) {
   return FB_OK;
 }
 
-int32_t fb_gemm_dot_tiles(int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt) {
+int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt) {
   if (force_simt) return gemm_simt_dot_tiles(N);
-  return gemm_dot_tiles(N, K, bf16_mode != 0);
+  return gemm_dot_tiles(M, N, K, bf16_mode != 0);
 }
 
 }  // extern "C"

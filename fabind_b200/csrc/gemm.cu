@@ -8,7 +8,7 @@
 namespace fb {
 
 bool gemm_tc2_shape_ok(int N);
-int gemm_tc2_dot_tiles(int N);
+int gemm_tc2_dot_tiles(int M, int N);
 int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st);
 
 static int tc_version() {
@@ -16,9 +16,9 @@ static int tc_version() {
   return v;
 }
 
-int gemm_dot_tiles(int N, int K, bool bf16_mode) {
+int gemm_dot_tiles(int M, int N, int K, bool bf16_mode) {
   if (bf16_mode && gemm_tc_shape_ok(N, K)) {
-    if (tc_version() == 2 && gemm_tc2_shape_ok(N)) return gemm_tc2_dot_tiles(N);
+    if (tc_version() == 2 && gemm_tc2_shape_ok(N)) return gemm_tc2_dot_tiles(M, N);
     return gemm_tc_dot_tiles(N);
   }
   return gemm_simt_dot_tiles(N);

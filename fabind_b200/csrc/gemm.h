@@ -22,7 +22,7 @@ struct GemmArgs {
 };
 
 // number of N tiles (= number of row-dot partials per row) the kernel chosen for `bf16` will use
-int gemm_dot_tiles(int N, int K, bool bf16_mode);
+int gemm_dot_tiles(int M, int N, int K, bool bf16_mode);
 
 // returns FB_OK or an error code; never synchronises
 int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st);

@@ -9,6 +9,7 @@ constexpr int BM = 64, BN = 64, BK = 16, NT = 256, PAD = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
+  pdl_entry();
   int M = g.M;
   if (g.m_dev) M = min(M, *g.m_dev);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -89,8 +90,8 @@ int gemm_simt_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
   const int K = g.K1 + g.K2;
   if (K <= 0 || (g.K1 & 3) || (g.K2 & 3) || (g.lda & 3) || (g.A2 && (g.lda2 & 3))) return FB_ERR_BAD_ARG;
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-  if (bf16_mode) gemm_simt_kernel<bf16><<<grid, NT, 0, st>>>(g);
-  else gemm_simt_kernel<float><<<grid, NT, 0, st>>>(g);
+  if (bf16_mode) fb_launch(gemm_simt_kernel<bf16>, dim3(grid), dim3(NT), 0, st, g);
+  else fb_launch(gemm_simt_kernel<float>, dim3(grid), dim3(NT), 0, st, g);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

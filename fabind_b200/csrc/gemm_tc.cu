@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
                                                                const __grid_constant__ CUtensorMap map_a2,
                                                                const __grid_constant__ CUtensorMap map_w, Params p) {
   using S = Smem<BN, STAGES>;
+  pdl_entry();
   int M = p.M;
   if (p.m_dev) M = min(M, *p.m_dev);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + s_bias[c + j];
           // bf16 mode: fast exp/reciprocal (outputs are rounded to bf16 or feed fp32 sums at ~1e-6 rel)
-          if (p.act == FB_ACT_SILU) x = x * __frcp_rn(1.0f + __expf(-x));
+          if (p.act == FB_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
           else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
@@ -292,7 +293,7 @@ static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
   p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb; p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
   p.dbg = g_tc_dbg;
   dim3 grid(g.N / BN, (g.M + BM - 1) / BM);
-  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, S::TOTAL, st>>>(ma, ma2, mw, p);
+  fb_launch(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(NUM_THREADS), S::TOTAL, st, ma, ma2, mw, p);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

@@ -49,12 +49,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
                                                                const __grid_constant__ CUtensorMap map_a2,
                                                                const __grid_constant__ CUtensorMap map_w, Params p) {
   using S = Smem<BN, STAGES>;
-  int M = p.M;
-  if (p.m_dev) M = min(M, *p.m_dev);
-  const int n_tiles_n = p.N / BN;
-  const int n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
-  if ((int)blockIdx.x >= n_tiles) return;   // whole CTA, before any barrier/TMEM state exists
-
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
@@ -91,6 +86,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only weights and on-chip state; activations (and the device-side row count)
+  // are produced by the previous kernel in the stream
+  pdl_wait();
+  int M = p.M;
+  if (p.m_dev) M = min(M, *p.m_dev);
+  const int n_tiles_n = p.N / BN;
+  const int n_tiles = ((M + BM - 1) / BM) * n_tiles_n;   // a CTA with no tile falls through to the teardown
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + s_bias[n0 + c + j];
-          if (p.act == FB_ACT_SILU) x = x * __frcp_rn(1.0f + __expf(-x));
+          if (p.act == FB_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
           else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
@@ -246,7 +248,7 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
   p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb; p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_tc2_kernel<BN, STAGES><<<grid, THREADS, S::TOTAL, st>>>(ma, ma2, mw, p);
+  fb_launch(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, p);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -255,12 +257,14 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
 }  // namespace tc2
 
 bool gemm_tc2_shape_ok(int N) { return N <= tc2::MAX_N; }
-int gemm_tc2_bn(int N) { return (N % 256) == 0 ? 256 : 128; }
-int gemm_tc2_dot_tiles(int N) { return 2 * (N / gemm_tc2_bn(N)); }
+// 128x256 tiles once there are enough rows to fill the machine with them; 128x128 tiles (twice the CTAs, half
+// the epilogue per CTA) for the short node-level GEMMs, which are latency-bound
+int gemm_tc2_bn(int M, int N) { return ((N % 256) == 0 && M >= 16384) ? 256 : 128; }
+int gemm_tc2_dot_tiles(int M, int N) { return 2 * (N / gemm_tc2_bn(M, N)); }
 
 int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0) return FB_OK;
-  if (gemm_tc2_bn(g.N) == 256) return tc2::launch<256, 3>(g, st);
+  if (gemm_tc2_bn(g.M, g.N) == 256) return tc2::launch<256, 3>(g, st);
   return tc2::launch<128, 5>(g, st);
 }
 

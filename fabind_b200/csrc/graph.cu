@@ -44,6 +44,7 @@ __device__ __forceinline__ int edge_category(const float* __restrict__ x, const 
 template <int MODE, bool FILL>
 __global__ void __launch_bounds__(256) graph_rows_kernel(GraphDev g, const float* __restrict__ x,
                                                          float intra, float inter) {
+  pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= g.N) return;
   const int r = warp;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256) graph_rows_kernel(GraphDev g, const float
 // the zero-edge fallback (sets the flag and gives the two designated rows degree 1).
 __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ deg, int* __restrict__ rowptr,
                                                     int n, int* fallback, int fa, int fr) {
+  pdl_entry();
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   __shared__ int fb_s;
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ deg,
 
 __global__ void convert_edges_kernel(const long long* __restrict__ e, int n_e, const int* __restrict__ inv,
                                      int* __restrict__ row, int* __restrict__ col) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_e) {
     row[i] = inv[(int)e[i]];
@@ -178,6 +181,7 @@ __global__ void convert_edges_kernel(const long long* __restrict__ e, int n_e, c
 // CSR over destination (index 1) of the LAS pairs: lasr_rowptr via count+scan, stable fill
 template <bool FILL>
 __global__ void __launch_bounds__(256) las_rows_kernel(GraphDev g) {
+  pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= g.N) return;
   const int r = warp;
@@ -200,35 +204,35 @@ static inline int warp_grid(int n_rows) { return (n_rows * 32 + 255) / 256; }
 
 int graph_prepare_static(const GraphDev& g, const long long* bonds, const long long* las,
                          cudaStream_t st) {
-  if (g.n_bond > 0) convert_edges_kernel<<<(g.n_bond + 255) / 256, 256, 0, st>>>(bonds, g.n_bond, g.inv, g.bond_row, g.bond_col);
-  if (g.n_las > 0) convert_edges_kernel<<<(g.n_las + 255) / 256, 256, 0, st>>>(las, g.n_las, g.inv, g.las_src, g.las_dst);
-  las_rows_kernel<false><<<warp_grid(g.N), 256, 0, st>>>(g);
-  scan_kernel<<<1, 1024, 0, st>>>(g.las_deg, g.las_rowptr, g.N, nullptr, -1, -1);
-  las_rows_kernel<true><<<warp_grid(g.N), 256, 0, st>>>(g);
+  if (g.n_bond > 0) fb_launch(convert_edges_kernel, dim3((g.n_bond + 255) / 256), dim3(256), 0, st, bonds, g.n_bond, g.inv, g.bond_row, g.bond_col);
+  if (g.n_las > 0) fb_launch(convert_edges_kernel, dim3((g.n_las + 255) / 256), dim3(256), 0, st, las, g.n_las, g.inv, g.las_src, g.las_dst);
+  fb_launch(las_rows_kernel<false>, dim3(warp_grid(g.N)), dim3(256), 0, st, g);
+  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.las_deg, g.las_rowptr, g.N, nullptr, -1, -1);
+  fb_launch(las_rows_kernel<true>, dim3(warp_grid(g.N)), dim3(256), 0, st, g);
   count_launch(3 + (g.n_bond > 0) + (g.n_las > 0));
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int graph_count_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st) {
-  graph_rows_kernel<1, false><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
-  scan_kernel<<<1, 1024, 0, st>>>(g.ctx_deg, g.ctx_rowptr, g.N, nullptr, -1, -1);
+  fb_launch(graph_rows_kernel<1, false>, dim3(warp_grid(g.N)), dim3(256), 0, st, g, x, intra, inter);
+  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.ctx_deg, g.ctx_rowptr, g.N, nullptr, -1, -1);
   count_launch(2);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int graph_fill_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st) {
-  graph_rows_kernel<1, true><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
+  fb_launch(graph_rows_kernel<1, true>, dim3(warp_grid(g.N)), dim3(256), 0, st, g, x, intra, inter);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st) {
-  graph_rows_kernel<2, false><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
-  scan_kernel<<<1, 1024, 0, st>>>(g.int_deg, g.int_rowptr, g.N, g.int_fallback, g.fb_atom, g.fb_res);
-  graph_rows_kernel<2, true><<<warp_grid(g.N), 256, 0, st>>>(g, x, intra, inter);
+  fb_launch(graph_rows_kernel<2, false>, dim3(warp_grid(g.N)), dim3(256), 0, st, g, x, intra, inter);
+  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.int_deg, g.int_rowptr, g.N, g.int_fallback, g.fb_atom, g.fb_res);
+  fb_launch(graph_rows_kernel<2, true>, dim3(warp_grid(g.N)), dim3(256), 0, st, g, x, intra, inter);
   count_launch(3);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(256) ref_rows_kernel(int N, const int* __restr
                                                        const int* __restrict__ cat_base /*[4]*/, const int* fallback,
                                                        long long* __restrict__ ctx_out, int e_ctx,
                                                        long long* __restrict__ int_out, int e_int) {
+  pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   const int r = warp, b = cplx[r];
@@ -287,6 +292,7 @@ __global__ void __launch_bounds__(256) ref_rows_kernel(int N, const int* __restr
 }
 
 __global__ void ref_fallback_fix_kernel(int N, int* deg, const int* off, const uint8_t* flags) {
+  pdl_entry();
   // single thread: if no inter candidate survived anywhere, give the two fallback rows degree 1
   int fa = off[0] + 1, fr = -1;
   for (int k = off[0]; k < off[1]; ++k) if ((flags[k] & 3) == 1) { fr = k; break; }
@@ -295,10 +301,10 @@ __global__ void ref_fallback_fix_kernel(int N, int* deg, const int* off, const u
 
 int graph_ref_count(int N, const int* cplx, const int* off, const uint8_t* flags, const float* x,
                     float intra, float inter, int* deg, int* rowptr, int* fallback, cudaStream_t st) {
-  ref_rows_kernel<false><<<warp_grid(N), 256, 0, st>>>(N, cplx, off, flags, x, intra, inter, deg, nullptr, nullptr,
+  fb_launch(ref_rows_kernel<false>, dim3(warp_grid(N)), dim3(256), 0, st, N, cplx, off, flags, x, intra, inter, deg, nullptr, nullptr,
                                                         nullptr, nullptr, 0, nullptr, 0);
   for (int k = 0; k < 4; ++k)
-    scan_kernel<<<1, 1024, 0, st>>>(deg + (size_t)k * N, rowptr + (size_t)k * (N + 1), N,
+    fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, deg + (size_t)k * N, rowptr + (size_t)k * (N + 1), N,
                                     k == 3 ? fallback : nullptr, -1, -1);
   count_launch(5);
   FB_CHECK_LAUNCH();
@@ -310,10 +316,10 @@ int graph_ref_fill(int N, const int* cplx, const int* off, const uint8_t* flags,
                    int fallback_host, long long* ctx_out, int e_ctx, long long* int_out, int e_int,
                    cudaStream_t st) {
   if (fallback_host) {
-    ref_fallback_fix_kernel<<<1, 1, 0, st>>>(N, deg, off, flags);
-    scan_kernel<<<1, 1024, 0, st>>>(deg + (size_t)3 * N, rowptr + (size_t)3 * (N + 1), N, nullptr, -1, -1);
+    fb_launch(ref_fallback_fix_kernel, dim3(1), dim3(1), 0, st, N, deg, off, flags);
+    fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, deg + (size_t)3 * N, rowptr + (size_t)3 * (N + 1), N, nullptr, -1, -1);
   }
-  ref_rows_kernel<true><<<warp_grid(N), 256, 0, st>>>(N, cplx, off, flags, x, intra, inter, deg, rowptr, cat_base,
+  fb_launch(ref_rows_kernel<true>, dim3(warp_grid(N)), dim3(256), 0, st, N, cplx, off, flags, x, intra, inter, deg, rowptr, cat_base,
                                                        fallback, ctx_out, e_ctx, int_out, e_int);
   count_launch(fallback_host ? 3 : 1);
   FB_CHECK_LAUNCH();

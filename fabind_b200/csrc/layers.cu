@@ -14,6 +14,7 @@ static inline int warp_grid(long long n_rows) { return (int)((n_rows * 32 + 255)
 template <typename T>
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ perm, int N, int D,
                                    float* __restrict__ dst32, T* __restrict__ dstT) {
+  pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   const float* s = src + (size_t)perm[warp] * D;
@@ -25,6 +26,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
 }
 
 __global__ void gather_x_kernel(const float* __restrict__ src, const int* __restrict__ perm, int N, float* __restrict__ dst) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) {
     const int s = perm[i];
@@ -36,6 +38,7 @@ __global__ void gather_x_kernel(const float* __restrict__ src, const int* __rest
 
 __global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __restrict__ perm, int N, int D,
                                     float* __restrict__ dst) {
+  pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   float* d = dst + (size_t)perm[warp] * D;
@@ -46,6 +49,7 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, const int* __
 __global__ void masked_update_x_kernel(float* __restrict__ x_state, const float* __restrict__ z,
                                        const uint8_t* __restrict__ flags, const int* __restrict__ perm, int N,
                                        float* __restrict__ x_out_caller) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   if (flags[i] & 4) {
@@ -63,31 +67,31 @@ __global__ void masked_update_x_kernel(float* __restrict__ x_state, const float*
 
 int permute_in(const GraphDev& g, const float* H_in, const float* X_in, const float* XL_in, int D, float* h32,
                void* hT, bool bf16_mode, float* x, float* xl, cudaStream_t st) {
-  if (bf16_mode) gather_rows_kernel<bf16><<<warp_grid(g.N), 256, 0, st>>>(H_in, g.perm, g.N, D, h32, (bf16*)hT);
-  else gather_rows_kernel<float><<<warp_grid(g.N), 256, 0, st>>>(H_in, g.perm, g.N, D, h32, (float*)nullptr);
-  gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(X_in, g.perm, g.N, x);
-  if (XL_in) gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(XL_in, g.perm, g.N, xl);
+  if (bf16_mode) fb_launch(gather_rows_kernel<bf16>, dim3(warp_grid(g.N)), dim3(256), 0, st, H_in, g.perm, g.N, D, h32, (bf16*)hT);
+  else fb_launch(gather_rows_kernel<float>, dim3(warp_grid(g.N)), dim3(256), 0, st, H_in, g.perm, g.N, D, h32, (float*)nullptr);
+  fb_launch(gather_x_kernel, dim3((g.N + 255) / 256), dim3(256), 0, st, X_in, g.perm, g.N, x);
+  if (XL_in) fb_launch(gather_x_kernel, dim3((g.N + 255) / 256), dim3(256), 0, st, XL_in, g.perm, g.N, xl);
   count_launch(XL_in ? 3 : 2);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int permute_x(const GraphDev& g, const float* X_in, float* x, cudaStream_t st) {
-  gather_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(X_in, g.perm, g.N, x);
+  fb_launch(gather_x_kernel, dim3((g.N + 255) / 256), dim3(256), 0, st, X_in, g.perm, g.N, x);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int permute_out_h(const GraphDev& g, const float* h, int D, float* H_out, cudaStream_t st) {
-  scatter_rows_kernel<<<warp_grid(g.N), 256, 0, st>>>(h, g.perm, g.N, D, H_out);
+  fb_launch(scatter_rows_kernel, dim3(warp_grid(g.N)), dim3(256), 0, st, h, g.perm, g.N, D, H_out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }
 
 int masked_update_x(const GraphDev& g, float* x_state, const float* z, float* x_out_caller, cudaStream_t st) {
-  masked_update_x_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(x_state, z, g.node_flags, g.perm, g.N, x_out_caller);
+  fb_launch(masked_update_x_kernel, dim3((g.N + 255) / 256), dim3(256), 0, st, x_state, z, g.node_flags, g.perm, g.N, x_out_caller);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -102,6 +106,7 @@ __global__ void __launch_bounds__(512) radial_kernel(GraphDev g, const int* __re
                                                      const int* __restrict__ erow, const int* __restrict__ ecol,
                                                      const float* __restrict__ x, float* __restrict__ rad,
                                                      float* __restrict__ norm) {
+  pdl_entry();
   const int b = blockIdx.x;
   float acc = 0.f;
   for (int part = 0; part < 2; ++part) {
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(512) radial_kernel(GraphDev g, const int* __re
 
 int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* ecol, const float* x, float* rad,
            float* norm, cudaStream_t st) {
-  radial_kernel<<<g.B, 512, 0, st>>>(g, rowptr, erow, ecol, x, rad, norm);
+  fb_launch(radial_kernel, dim3(g.B), dim3(512), 0, st, g, rowptr, erow, ecol, x, rad, norm);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -140,15 +145,16 @@ int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* eco
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, const int* __restrict__ ecol,
-                                    const int* __restrict__ node_cplx, const float* __restrict__ P,
+                                    const int* __restrict__ node_cplx, const T* __restrict__ P,
                                     const float* __restrict__ rad, const float* __restrict__ norm,
                                     const float* __restrict__ w_rad, const float* __restrict__ b1, T* __restrict__ A1) {
+  pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
   const int e = warp, r = erow[e], c = ecol[e];
   const float rn = rad[e] / norm[node_cplx[r]];
-  const float* pr = P + (size_t)r * 2 * H;
-  const float* pc = P + (size_t)c * 2 * H + H;
+  const T* pr = P + (size_t)r * 2 * H;
+  const T* pc = P + (size_t)c * 2 * H + H;
   for (int f = lane * 4; f < H; f += 128) {
     const float4 a = ld4(pr + f), b = ld4(pc + f), w = ld4(w_rad + f), bb = ld4(b1 + f);
     float4 o;
@@ -160,12 +166,12 @@ __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, 
   }
 }
 
-int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node_cplx, const float* P,
+int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node_cplx, const void* P,
                  const float* rad, const float* norm, const float* w_rad, const float* b1, void* A1, bool bf16_mode,
                  cudaStream_t st) {
   if (E <= 0) return FB_OK;
-  if (bf16_mode) gcl_edge_pre_kernel<bf16><<<warp_grid(E), 256, 0, st>>>(E, H, erow, ecol, node_cplx, P, rad, norm, w_rad, b1, (bf16*)A1);
-  else gcl_edge_pre_kernel<float><<<warp_grid(E), 256, 0, st>>>(E, H, erow, ecol, node_cplx, P, rad, norm, w_rad, b1, (float*)A1);
+  if (bf16_mode) fb_launch(gcl_edge_pre_kernel<bf16>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const bf16*)P, rad, norm, w_rad, b1, (bf16*)A1);
+  else fb_launch(gcl_edge_pre_kernel<float>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const float*)P, rad, norm, w_rad, b1, (float*)A1);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -210,6 +216,7 @@ __global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* 
                                                        const float* __restrict__ dot, int dot_tiles, int dot_stride,
                                                        const float* __restrict__ x, float cmax, T* __restrict__ agg,
                                                        float* __restrict__ x_out) {
+  pdl_entry();
   extern __shared__ float part[];  // [4][H]
   const int r = blockIdx.x, grp = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
   const int lo = rowptr[r], hi = rowptr[r + 1];
@@ -267,8 +274,8 @@ int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, co
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
   if (H & 7) return FB_ERR_UNSUPPORTED;
   const int smem = 4 * H * 4;
-  if (bf16_mode) gcl_node_kernel<bf16><<<N, 256, smem, st>>>(N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
-  else gcl_node_kernel<float><<<N, 256, smem, st>>>(N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(N), dim3(256), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
+  else fb_launch(gcl_node_kernel<float>, dim3(N), dim3(256), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -290,6 +297,7 @@ __device__ __forceinline__ int find_complex(const int* __restrict__ pair_base, i
 template <typename T>
 __global__ void pair_outer_kernel(GraphDev g, int P_total, int H, const float* __restrict__ pc /*[N,H]: c rows = linear_c, p rows = linear_p*/,
                                   T* __restrict__ A0) {
+  pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= P_total) return;
   const int pair = warp;
@@ -304,8 +312,8 @@ __global__ void pair_outer_kernel(GraphDev g, int P_total, int H, const float* _
 }
 
 int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0, bool bf16_mode, cudaStream_t st) {
-  if (bf16_mode) pair_outer_kernel<bf16><<<warp_grid(P_total), 256, 0, st>>>(g, P_total, H, pc, (bf16*)A0);
-  else pair_outer_kernel<float><<<warp_grid(P_total), 256, 0, st>>>(g, P_total, H, pc, (float*)A0);
+  if (bf16_mode) fb_launch(pair_outer_kernel<bf16>, dim3(warp_grid(P_total)), dim3(256), 0, st, g, P_total, H, pc, (bf16*)A0);
+  else fb_launch(pair_outer_kernel<float>, dim3(warp_grid(P_total)), dim3(256), 0, st, g, P_total, H, pc, (float*)A0);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -314,6 +322,7 @@ int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0,
 // gated pair bias of every RowAttentionBlock (cross_att.py:125):  raw[pair, l*16 + blk*8 + {0..3 lin, 4..7 gate}]
 //  ->  PB[(l*2+blk) * P_total*4 + pair*4 + h] = lin * sigmoid(gate)
 __global__ void pair_bias_gate_kernel(int P_total, int L, const float* __restrict__ raw, float* __restrict__ PB) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)P_total * L * 8;
   if (i >= total) return;
@@ -326,7 +335,7 @@ __global__ void pair_bias_gate_kernel(int P_total, int L, const float* __restric
 
 int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t st) {
   const long long total = (long long)P_total * L * 8;
-  pair_bias_gate_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(P_total, L, raw, PB);
+  fb_launch(pair_bias_gate_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, P_total, L, raw, PB);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -348,6 +357,7 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
                                                             const float* __restrict__ Kb, int ldk,
                                                             const float* __restrict__ Vb, int ldv,
                                                             const float* __restrict__ PB, T* __restrict__ O, int ldo) {
+  pdl_entry();
   __shared__ float sK[RA_KC][33];
   __shared__ float sV[RA_KC][32];
   const int b = blockIdx.y, head = blockIdx.z;
@@ -451,8 +461,8 @@ int row_attention(const GraphDev& g, int q_is_prot, int max_q, const float* Q, i
                   cudaStream_t st) {
   if (max_q <= 0) return FB_OK;
   dim3 grid((max_q + RA_QT - 1) / RA_QT, g.B, 4);
-  if (bf16_mode) row_attention_kernel<bf16><<<grid, 128, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (bf16*)O, ldo);
-  else row_attention_kernel<float><<<grid, 128, 0, st>>>(g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (float*)O, ldo);
+  if (bf16_mode) fb_launch(row_attention_kernel<bf16>, dim3(grid), dim3(128), 0, st, g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (bf16*)O, ldo);
+  else fb_launch(row_attention_kernel<float>, dim3(grid), dim3(128), 0, st, g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (float*)O, ldo);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -471,6 +481,7 @@ __global__ void __launch_bounds__(256) pair_zin_kernel(GraphDev g, int H, const 
                                                        const float* __restrict__ pc32, int ld32,
                                                        const float* __restrict__ Wo /*[32,H] = linear_out.weight^T*/, const float* __restrict__ bo,
                                                        T* __restrict__ Zin) {
+  pdl_entry();
   extern __shared__ float wt[];  // [32][H], the weight slot is stored pre-transposed
   for (int i = threadIdx.x * 4; i < H * 32; i += blockDim.x * 4)
     *reinterpret_cast<float4*>(&wt[i]) = *reinterpret_cast<const float4*>(&Wo[i]);
@@ -481,8 +492,17 @@ __global__ void __launch_bounds__(256) pair_zin_kernel(GraphDev g, int H, const 
   for (int u = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); u < U; u += gridDim.x * warps_per_cta) {
     const int ci = g.int_row[u], pi = g.int_col[u], pair = g.int_pair[u];
     const float t = pc32[(size_t)pi * ld32 + lane] * pc32[(size_t)ci * ld32 + 32 + lane];
-    for (int f0 = lane * 4; f0 < H; f0 += 128) {
-      float4 z = ld4(P0 + (size_t)pair * H + f0);
+    float4 zr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f0 = lane * 4 + i * 128;
+      if (f0 < H) zr[i] = ld4(P0 + (size_t)pair * H + f0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f0 = lane * 4 + i * 128;
+      if (f0 >= H) break;
+      float4 z = zr[i];
       float4 o = ld4(bo + f0);
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
@@ -507,8 +527,8 @@ int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* p
     cudaFuncSetAttribute(pair_zin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 4);
     attr = true;
   }
-  if (bf16_mode) pair_zin_kernel<bf16><<<grid, 256, smem, st>>>(g, H, (const bf16*)P0, pc32, ld32, Wo, bo, (bf16*)Zin);
-  else pair_zin_kernel<float><<<grid, 256, smem, st>>>(g, H, (const float*)P0, pc32, ld32, Wo, bo, (float*)Zin);
+  if (bf16_mode) fb_launch(pair_zin_kernel<bf16>, dim3(grid), dim3(256), smem, st, g, H, (const bf16*)P0, pc32, ld32, Wo, bo, (bf16*)Zin);
+  else fb_launch(pair_zin_kernel<float>, dim3(grid), dim3(256), smem, st, g, H, (const float*)P0, pc32, ld32, Wo, bo, (float*)Zin);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -517,6 +537,7 @@ int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* p
 // pb_dense[pair] = sum of row-dot partials + constant   (attn_bias_proj o pair_transition.linear_2)
 __global__ void pair_bias_finish_kernel(GraphDev g, const float* __restrict__ dot, int tiles, int stride, const float* __restrict__ cst,
                                         float* __restrict__ pb_dense) {
+  pdl_entry();
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= g.int_rowptr[g.Nc_tot]) return;
   float s = 0.f;
@@ -527,7 +548,7 @@ __global__ void pair_bias_finish_kernel(GraphDev g, const float* __restrict__ do
 int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, int stride, const float* cst, float* pb_dense,
                      cudaStream_t st) {
   if (cap_u <= 0) return FB_OK;
-  pair_bias_finish_kernel<<<(cap_u + 255) / 256, 256, 0, st>>>(g, dot, tiles, stride, cst, pb_dense);
+  fb_launch(pair_bias_finish_kernel, dim3((cap_u + 255) / 256), dim3(256), 0, st, g, dot, tiles, stride, cst, pb_dense);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -543,8 +564,9 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 // One CTA (4 warps) per row: warp w takes the edges lo+w, lo+w+4, ... with its own online softmax; the
 // four partial states (max, sum, feature accumulator, coordinate accumulator) are merged through smem.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | k | ...*/, int ldqk,
-                                                              const float* __restrict__ V, const float* __restrict__ VC,
+__global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | ...*/, int ldqk,
+                                                              const T* __restrict__ Kt, int ldk,
+                                                              const T* __restrict__ V, const T* __restrict__ VC,
                                                               const float* __restrict__ k_r, const float* __restrict__ v_r,
                                                               const float* __restrict__ ac_u, const float* __restrict__ ac_b,
                                                               const float* __restrict__ ac_w2, const float* __restrict__ rad,
@@ -552,6 +574,7 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
                                                               const float* __restrict__ x, float cmax, float* __restrict__ h,
                                                               T* __restrict__ hT, float* __restrict__ x_out,
                                                               float* __restrict__ att_logit) {
+  pdl_entry();
   extern __shared__ float sm[];     // [4][H] accumulators | [4] m | [4] l | [4][3] x
   float* s_acc = sm;
   float* s_m = sm + 4 * H;
@@ -588,7 +611,7 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
     for (int i = 0; i < VEC; ++i) {
       const int f = (i * 32 + lane) * 4;
       if (f < H) {
-        const float4 kk = ld4(QK + (size_t)c * ldqk + H + f);
+        const float4 kk = ld4(Kt + (size_t)c * ldk + f);
         const float4 vc = ld4(VC + (size_t)c * H + f);
         const float4 v0 = ld4(V + (size_t)c * H + f);
         const float4 uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f), vr = ld4(v_r + f);
@@ -653,14 +676,14 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
   }
 }
 
-int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* V, const float* VC, const float* k_r,
+int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const void* Kt, int ldk, const void* V, const void* VC, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, bool bf16_mode, cudaStream_t st) {
   const int grid = g.N;
   const int smem = (4 * H + 32) * 4;
 #define FB_IA(T, VEC)                                                                                      \
-  inter_attention_kernel<T, VEC><<<grid, 128, smem, st>>>(g, H, QK, ldqk, V, VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
+  fb_launch(inter_attention_kernel<T, VEC>, dim3(grid), dim3(128), smem, st, g, H, QK, ldqk, (const T*)Kt, ldk, (const T*)V, (const T*)VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
                                                           norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   if (bf16_mode) {
@@ -679,6 +702,7 @@ int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const f
 // ------------------------------------------------------------------------------------------------
 __global__ void las_step_kernel(GraphDev g, const float* __restrict__ x, const float* __restrict__ xref, float step,
                                 float cl, float* __restrict__ x_out) {
+  pdl_entry();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= g.N) return;
   const float xj0 = x[3 * j], xj1 = x[3 * j + 1], xj2 = x[3 * j + 2];
@@ -701,7 +725,7 @@ __global__ void las_step_kernel(GraphDev g, const float* __restrict__ x, const f
 }
 
 int las_step(const GraphDev& g, const float* x, const float* xref, float step, float cl, float* x_out, cudaStream_t st) {
-  las_step_kernel<<<(g.N + 255) / 256, 256, 0, st>>>(g, x, xref, step, cl, x_out);
+  fb_launch(las_step_kernel, dim3((g.N + 255) / 256), dim3(256), 0, st, g, x, xref, step, cl, x_out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

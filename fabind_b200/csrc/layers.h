@@ -10,7 +10,7 @@ int permute_out_h(const GraphDev& g, const float* h, int D, float* H_out, cudaSt
 int masked_update_x(const GraphDev& g, float* x_state, const float* z, float* x_out_caller, cudaStream_t st);
 int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* ecol, const float* x, float* rad,
            float* norm, cudaStream_t st);
-int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node_cplx, const float* P,
+int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node_cplx, const void* P,
                  const float* rad, const float* norm, const float* w_rad, const float* b1, void* A1, bool bf16_mode,
                  cudaStream_t st);
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
@@ -24,7 +24,7 @@ int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* p
              void* Zin, bool bf16_mode, cudaStream_t st);
 int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, int stride, const float* cst, float* pb_dense,
                      cudaStream_t st);
-int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* V, const float* VC, const float* k_r,
+int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const void* Kt, int ldk, const void* V, const void* VC, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, bool bf16_mode, cudaStream_t st);

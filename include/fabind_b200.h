@@ -133,7 +133,7 @@ typedef struct fb_gemm_params {
   int32_t force_simt;   /* 1: never take the tcgen05 path */
 } fb_gemm_params;
 int32_t fb_gemm(const fb_gemm_params* g, void* stream);
-int32_t fb_gemm_dot_tiles(int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt);
+int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt);
 /* development probe: when non-null, sampled CTAs of the tcgen05 GEMM write 8 globaltimer stamps each */
 int32_t fb_gemm_set_debug(int64_t* dbg);
 

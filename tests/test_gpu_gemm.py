@@ -30,7 +30,7 @@ def run_gemm(A, W, bias=None, act=0, res=None, A2=None, dotv=None, m_dev=None, b
     g.C, g.ldc = Cout.data_ptr(), N
     Cb = torch.zeros((M, N), dtype=dt, device=dev) if want_cb else None
     g.Cb, g.ldcb = (Cb.data_ptr() if want_cb else None), N
-    tiles = l.fb_gemm_dot_tiles(N, K1 + K2, int(bf16), int(force_simt))
+    tiles = l.fb_gemm_dot_tiles(M, N, K1 + K2, int(bf16), int(force_simt))
     dot = torch.zeros((tiles, M), device=dev) if dotv is not None else None
     g.dotv = dotv.data_ptr() if dotv is not None else None
     g.dot_out = dot.data_ptr() if dot is not None else None
