@@ -172,7 +172,7 @@ struct Bufs {
   float *x_state, *xa, *xb, *xl;
   // node features
   float *Hin32, *h, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
-  void *HinT, *hT, *agg, *T1, *O, *TH, *VT, *Pn, *QKT, *VCT;
+  void *HinT, *hT, *agg, *T1, *O, *TH, *VT, *Pn, *VCT;
   // pair
   void *P0, *A0, *Zin; float *PBraw, *PB, *pb_dense, *dotU;
   // edge
@@ -210,7 +210,6 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.dotU = a.get<float>(tiles2H * capU);
   b.radi = a.get<float>(capI); b.normi = a.get<float>(p.B);
   b.QK = a.get<float>(N * (2 * H + QKX));
-  b.QKT = bf ? a.take(N * (2 * H + QKX) * TS) : (void*)b.QK;   // typed copy: K rows are gathered per inter edge
   b.VT = a.take(N * H * TS);
   b.VCT = a.take(N * H * TS);
   // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
@@ -312,7 +311,7 @@ struct Run {
     // q | k of the interfacial attention stacked with the 32-channel interaction projections
     // (cross_att.py:22,51: linear_p on protein rows, linear_c on compound rows) in ONE node GEMM
     const int ldqk = 2 * H + QKX;
-    gemm(b.hT, H, H, aw.qk_w, ldqk, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, b.QKT, ldqk);
+    gemm(b.hT, H, H, aw.qk_w, ldqk, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, nullptr, 0);
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
@@ -328,7 +327,7 @@ struct Run {
     gemm(b.hT, H, H, aw.v_w, H, aw.v_b, FB_ACT_NONE, N, nullptr, 0, b.VT, H);
     gemm(b.VT, H, H, aw.ac1_w, H, -1, FB_ACT_NONE, N, nullptr, 0, b.VCT, H);
     stage(CAT_ATTENTION, [&] {
-      return inter_attention(g, H, b.QK, ldqk, at(b.QKT, (size_t)H), ldqk, b.VT, b.VCT, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
+      return inter_attention(g, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, b.VCT, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
                              b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st);
     });
   }

@@ -565,7 +565,7 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 // four partial states (max, sum, feature accumulator, coordinate accumulator) are merged through smem.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | ...*/, int ldqk,
-                                                              const T* __restrict__ Kt, int ldk,
+                                                              const float* __restrict__ Kt, int ldk,
                                                               const T* __restrict__ V, const T* __restrict__ VC,
                                                               const float* __restrict__ k_r, const float* __restrict__ v_r,
                                                               const float* __restrict__ ac_u, const float* __restrict__ ac_b,
@@ -676,14 +676,14 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
   }
 }
 
-int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const void* Kt, int ldk, const void* V, const void* VC, const float* k_r,
+int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, bool bf16_mode, cudaStream_t st) {
   const int grid = g.N;
   const int smem = (4 * H + 32) * 4;
 #define FB_IA(T, VEC)                                                                                      \
-  fb_launch(inter_attention_kernel<T, VEC>, dim3(grid), dim3(128), smem, st, g, H, QK, ldqk, (const T*)Kt, ldk, (const T*)V, (const T*)VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
+  fb_launch(inter_attention_kernel<T, VEC>, dim3(grid), dim3(128), smem, st, g, H, QK, ldqk, Kt, ldk, (const T*)V, (const T*)VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
                                                           norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   if (bf16_mode) {
