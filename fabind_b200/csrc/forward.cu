@@ -62,7 +62,6 @@ struct GclW { int64_t e1_rc, e1_rad, e1_b, e2_w, e2_b, c1_w, c1_b, c2_w, n1_w, n
 struct AttW {
   int64_t ca_c_w, ca_c_b, ca_p_w, ca_p_b, ca_p2_w, o_p_w, o_p_b, o_c_w, o_c_b;
   int64_t tp1_w, tp1_b, tp2_w, tp2_b, tc1_w, tc1_b, tc2_w, tc2_b;
-  int64_t i32_o_w, i32_o_b;
   int64_t pt1_w, pt1_b, pt2v, pt_c;
   int64_t qk_w, qk_b, k_r, v_w, v_b, v_r, ac1_w, ac1_b, ac2_w, ac_u;
 };
@@ -110,8 +109,7 @@ static void build_weights(int H, int L, ModelW& w) {
     a.tp2_w = add(p + "tp2_w", H, 2 * H); a.tp2_b = add(p + "tp2_b", 1, H);
     a.tc1_w = add(p + "tc1_w", 2 * H, H); a.tc1_b = add(p + "tc1_b", 1, 2 * H);
     a.tc2_w = add(p + "tc2_w", H, 2 * H); a.tc2_b = add(p + "tc2_b", 1, H);
-    a.i32_o_w = add(p + "i32_o_w", 32, H);  /* stored transposed */ a.i32_o_b = add(p + "i32_o_b", 1, H);
-    a.pt1_w = add(p + "pt1_w", 2 * H, H); a.pt1_b = add(p + "pt1_b", 1, 2 * H);
+    a.pt1_w = add(p + "pt1_w", 2 * H, H + 64); a.pt1_b = add(p + "pt1_b", 1, 2 * H);
     a.pt2v = add(p + "pt2v", 1, 2 * H); a.pt_c = add(p + "pt_c", 1, 1);
     a.qk_w = add(p + "qk_w", 2 * H + QKX, H); a.qk_b = add(p + "qk_b", 1, 2 * H + QKX); a.k_r = add(p + "k_r", 1, H);
     a.v_w = add(p + "v_w", H, H); a.v_b = add(p + "v_b", 1, H); a.v_r = add(p + "v_r", 1, H);
@@ -174,7 +172,7 @@ struct Bufs {
   float *Hin32, *h, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
   void *HinT, *hT, *agg, *T1, *O, *TH, *VT, *Pn, *VCT;
   // pair
-  void *P0, *A0, *Zin; float *PBraw, *PB, *pb_dense, *dotU;
+  void *P0, *A0, *Zg, *T64; float *PBraw, *PB, *pb_dense, *dotU;
   // edge
   float *radc, *normc, *radi, *normi, *dotE; void *A1, *M;
 };
@@ -206,7 +204,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
   b.CAc = a.get<float>((Nc + 1) * 4 * HD); b.CAp = a.get<float>((Np + 1) * 2 * HD); b.CAp2 = a.get<float>((Np + 1) * 2 * HD);
   b.O = a.take(N * HD * TS); b.TH = a.take(N * 2 * H * TS);
-  b.Zin = a.take(capU * H * TS);
+  b.Zg = a.take(capU * H * TS); b.T64 = a.take(capU * 64 * TS);
   b.dotU = a.get<float>(tiles2H * capU);
   b.radi = a.get<float>(capI); b.normi = a.get<float>(p.B);
   b.QK = a.get<float>(N * (2 * H + QKX));
@@ -315,10 +313,10 @@ struct Run {
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
-    stage(CAT_ATTENTION, [&] { return pair_zin(g, capU, H, b.P0, b.QK + 2 * H, ldqk, F(aw.i32_o_w), F(aw.i32_o_b), b.Zin, bf, st); });
+    stage(CAT_ATTENTION, [&] { return pair_gather(g, capU, H, b.P0, b.QK + 2 * H, ldqk, b.Zg, b.T64, bf, st); });
     const int tiles2 = gemm_dot_tiles(capU, 2 * H, H, bf);
     gemm_cat = CAT_GEMM_PAIR;
-    gemm(b.Zin, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0,
+    gemm(b.Zg, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, b.T64, 64, 64,
          aw.pt2v, b.dotU, capU, u_dev);
     gemm_cat = CAT_GEMM_NODE;
     stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });

@@ -15,10 +15,16 @@
 
 namespace fb {
 
+extern long long* g_tc_dbg;
 bool tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 namespace tc2 {
 using namespace tc;
+
+#define FB_DBG2(slot)                                                                     \
+  do {                                                                                   \
+    if (p.dbg && (blockIdx.x & 7) == 0) p.dbg[(blockIdx.x >> 3) * 8 + (slot)] = gtime(); \
+  } while (0)
 
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;   // 320
@@ -32,6 +38,7 @@ struct Params {
   float* C; int ldc;
   bf16* Cb; int ldcb;
   const float* dotv; float* dot_out; int dot_stride;
+  long long* dbg;
 };
 
 template <int BN, int STAGES>
@@ -50,6 +57,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
                                                                const __grid_constant__ CUtensorMap map_w, Params p) {
   using S = Smem<BN, STAGES>;
   pdl_trigger();
+  if (threadIdx.x == 0) FB_DBG2(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
@@ -88,6 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only weights and on-chip state; activations (and the device-side row count)
   // are produced by the previous kernel in the stream
+  if (threadIdx.x == 0) FB_DBG2(1);
   pdl_wait();
   int M = p.M;
   if (p.m_dev) M = min(M, *p.m_dev);
@@ -127,6 +136,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
+          if (it == 0) FB_DBG2(2);
           tcgen05_fence_after();
           const uint8_t* a_src = smem + s * S::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(a_src), bdesc = make_smem_desc(a_src + S::A_BYTES);
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
           for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&empty[s]);
         }
+        if (lt == 0) FB_DBG2(3);
         umma_commit(&tfull[a]);
       }
     }
@@ -148,11 +159,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int a = lt & 1;
       const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      // residual rows do not depend on the MMAs: for the 128-wide tiles (node-level GEMMs) fetch them into
+      // registers, in the transposed "lane = column" layout, while the main loop of this tile is running
+      constexpr bool PRE = (BN == 128);
+      float rpre[PRE ? 2 : 1][PRE ? 32 : 1];
+      if (PRE && p.res) {
+#pragma unroll
+        for (int ch = 0; ch < (PRE ? 2 : 1); ++ch) {
+#pragma unroll
+          for (int r = 0; r < (PRE ? 32 : 1); ++r) {
+            const int m = m0 + q * 32 + r;
+            rpre[ch][r] = m < M ? p.res[(size_t)m * p.ldres + n0 + half * COLS + ch * 32 + lane] : 0.f;
+          }
+        }
+      }
       mbar_wait(&tfull[a], (lt >> 1) & 1);
+      if (lt == 0 && threadIdx.x == 64) FB_DBG2(4);
       tcgen05_fence_after();
       const int mrow = m0 + q * 32 + lane;       // row owned in the TMEM layout
       float dsum = 0.f;
-#pragma unroll 1
+#pragma unroll (BN == 128 ? 2 : 1)
       for (int cc = 0; cc < COLS; cc += 32) {
         const int c = half * COLS + cc;           // column inside the tile
         uint32_t v[32];
@@ -176,14 +202,25 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
           __syncwarp();
           const int ncol = n0 + c;
           if (p.C || p.res) {
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int m = m0 + q * 32 + r;
-              if (m < M) {
-                float x = xp[r * 33 + lane];
-                if (p.res) x += p.res[(size_t)m * p.ldres + ncol + lane];
-                if (p.C) p.C[(size_t)m * p.ldc + ncol + lane] = x;
-                if (p.Cb) xp[r * 33 + lane] = x;     // keep the residual-added value for the bf16 copy
+            // C may alias res (in-place residual update of h): loads of a batch of rows are issued before any
+            // store of that batch so that they pipeline instead of serialising behind may-alias stores
+#pragma unroll (BN == 128 ? 4 : 1)
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float rv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = m0 + q * 32 + r0 + i;
+                if (PRE) rv[i] = p.res ? rpre[(cc >> 5) & 1][(r0 + i) & 31] : 0.f;
+                else rv[i] = (p.res && m < M) ? p.res[(size_t)m * p.ldres + ncol + lane] : 0.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m = m0 + q * 32 + r0 + i;
+                if (m < M) {
+                  const float x = xp[(r0 + i) * 33 + lane] + rv[i];
+                  if (p.C) p.C[(size_t)m * p.ldc + ncol + lane] = x;
+                  if (p.Cb) xp[(r0 + i) * 33 + lane] = x;     // keep the residual-added value for the bf16 copy
+                }
               }
             }
             __syncwarp();
@@ -206,6 +243,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
         // two warps (column halves) share a row: partial index = 2 * n_tile + half
         p.dot_out[(size_t)((tile % n_tiles_n) * 2 + half) * p.dot_stride + mrow] = dsum;
       }
+      if (lt == 0 && threadIdx.x == 64) FB_DBG2(5);
       // this warp is done reading the accumulator stage
       tcgen05_fence_before();
       __syncwarp();
@@ -214,6 +252,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) FB_DBG2(6);
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
@@ -246,6 +285,7 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
   p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.m_dev = g.m_dev;
   p.bias = g.bias; p.act = g.act; p.res = g.res; p.ldres = g.ldres; p.C = g.C; p.ldc = g.ldc;
   p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb; p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
+  p.dbg = g_tc_dbg;
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   fb_launch(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, p);

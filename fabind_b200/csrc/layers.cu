@@ -2,6 +2,8 @@
 // segment reductions, per-complex row attention, interfacial attention and the LAS step.
 // All of them are HBM/L2-bound: one warp per row/edge, float4 accesses along the feature dimension.
 // T is the activation element type of the precision mode (float for fp32 parity mode, bf16 otherwise).
+#include <type_traits>
+
 #include "layers.h"
 
 namespace fb {
@@ -210,6 +212,31 @@ __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+constexpr int GN_BIG = 48;   // nodes with more edges than this are reduced by the whole CTA
+
+template <typename T>
+__device__ __forceinline__ void gcl_sum_rows(const T* __restrict__ M, int H, int f0, int lo, int hi, int step, float (&acc)[8]) {
+  int e = lo;
+  for (; e + 3 * step < hi; e += 4 * step) {   // four independent 16-byte loads in flight
+    float a[8], b[8], c[8], d[8];
+    ld8(M + (size_t)e * H + f0, a);
+    ld8(M + (size_t)(e + step) * H + f0, b);
+    ld8(M + (size_t)(e + 2 * step) * H + f0, c);
+    ld8(M + (size_t)(e + 3 * step) * H + f0, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += (a[i] + b[i]) + (c[i] + d[i]);
+  }
+  for (; e < hi; e += step) {
+    float a[8];
+    ld8(M + (size_t)e * H + f0, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += a[i];
+  }
+}
+
+// CTA = 4 nodes x 64 feature lanes (8 features = one 16-byte load per lane and edge row).  The rows of a
+// node are contiguous in M (edges are in CSR order), so the common case is a short streaming reduction with
+// no shared memory; the few high-degree nodes (global nodes) are then reduced by all 256 threads.
 template <typename T>
 __global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* __restrict__ rowptr,
                                                        const int* __restrict__ ecol, const T* __restrict__ M,
@@ -218,9 +245,12 @@ __global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* 
                                                        float* __restrict__ x_out) {
   pdl_entry();
   extern __shared__ float part[];  // [4][H]
-  const int r = blockIdx.x, grp = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
-  const int lo = rowptr[r], hi = rowptr[r + 1];
-  if (threadIdx.x < 32) {
+  const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + grp;
+  int lo = 0, hi = 0;
+  if (r < N) { lo = rowptr[r]; hi = rowptr[r + 1]; }
+  // coordinate part: first warp of each group, lanes over edges
+  if (r < N && t < 32) {
     const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
     float ax = 0.f, ay = 0.f, az = 0.f;
     for (int e = lo + lane; e < hi; e += 32) {
@@ -240,33 +270,35 @@ __global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* 
     }
   }
   if (agg == nullptr) return;
-  for (int f0 = t * 8; f0 < H; f0 += 512) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int e = lo + grp;
-    for (; e + 4 < hi; e += 8) {
-      float a[8], b[8];
-      ld8(M + (size_t)e * H + f0, a);
-      ld8(M + (size_t)(e + 4) * H + f0, b);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += a[i] + b[i];
-    }
-    for (; e < hi; e += 4) {
-      float a[8];
-      ld8(M + (size_t)e * H + f0, a);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += a[i];
-    }
-    st8(&part[grp * H + f0], acc);
-  }
-  __syncthreads();
-  if (grp == 0) {
+  if (r < N && hi - lo <= GN_BIG) {
     for (int f0 = t * 8; f0 < H; f0 += 512) {
-      float o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        o[i] = (part[f0 + i] + part[H + f0 + i]) + (part[2 * H + f0 + i] + part[3 * H + f0 + i]);
-      st8(agg + (size_t)r * H + f0, o);
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      gcl_sum_rows(M, H, f0, lo, hi, 1, acc);
+      st8(agg + (size_t)r * H + f0, acc);
     }
+  }
+  // cooperative pass for the high-degree nodes of this CTA (block-uniform control flow)
+  for (int k = 0; k < 4; ++k) {
+    const int rk = blockIdx.x * 4 + k;
+    if (rk >= N) break;
+    const int lk = rowptr[rk], hk = rowptr[rk + 1];
+    if (hk - lk <= GN_BIG) continue;
+    for (int f0 = t * 8; f0 < H; f0 += 512) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      gcl_sum_rows(M, H, f0, lk + grp, hk, 4, acc);
+      st8(&part[grp * H + f0], acc);
+    }
+    __syncthreads();
+    if (grp == 0) {
+      for (int f0 = t * 8; f0 < H; f0 += 512) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = (part[f0 + i] + part[H + f0 + i]) + (part[2 * H + f0 + i] + part[3 * H + f0 + i]);
+        st8(agg + (size_t)rk * H + f0, o);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -274,8 +306,9 @@ int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, co
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
   if (H & 7) return FB_ERR_UNSUPPORTED;
   const int smem = 4 * H * 4;
-  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(N), dim3(256), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
-  else fb_launch(gcl_node_kernel<float>, dim3(N), dim3(256), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  const int grid = (N + 3) / 4;
+  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(grid), dim3(256), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
+  else fb_launch(gcl_node_kernel<float>, dim3(grid), dim3(256), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -470,65 +503,39 @@ int row_attention(const GraphDev& g, int q_is_prot, int max_q, const float* Q, i
 
 // ------------------------------------------------------------------------------------------------
 // pair path (v1: the updated pair embedding is only consumed through attn_bias_proj at the inter
-// pairs, egnn.py:208,291-294).  For every unique compound->protein inter edge u:
-//   Zin[u,:] = pair0[pair,:] + W_o32 (p32[prot,:] * c32[comp,:]) + b_o32      (cross_att.py:51)
+// pairs, egnn.py:208,291-294).  For every unique compound->protein inter edge u the pair-transition
+// input  pair0[pair] + W_o32 (p32[prot] * c32[comp]) + b_o32  (cross_att.py:51) is NOT materialised:
+// its two parts are handed to the pair GEMM as a K-concatenated operand  [ pair0[pair] | p32*c32 | 0 ]
+// against [ W1 | W1 W_o32 | 0 ]  (weights.py folds W_o32 and b_o32 into the first transition Linear).
+// This kernel only gathers: Zg[u,:] = pair0[pair[u],:],  T64[u,0:32] = p32[prot]*c32[comp], T64[u,32:64] = 0.
 // ------------------------------------------------------------------------------------------------
-// W_o32^T is staged once per CTA in shared memory as [32][H] so that a warp reads consecutive features
-// conflict-free; warps stride over the unique pairs (their number is only known on the device).
-// pc32 holds, per node, linear_p(h) in columns [0,32) and linear_c(h) in columns [32,64).
 template <typename T>
-__global__ void __launch_bounds__(256) pair_zin_kernel(GraphDev g, int H, const T* __restrict__ P0,
-                                                       const float* __restrict__ pc32, int ld32,
-                                                       const float* __restrict__ Wo /*[32,H] = linear_out.weight^T*/, const float* __restrict__ bo,
-                                                       T* __restrict__ Zin) {
+__global__ void __launch_bounds__(256) pair_gather_kernel(GraphDev g, int H, const T* __restrict__ P0,
+                                                          const float* __restrict__ pc32, int ld32,
+                                                          T* __restrict__ Zg, T* __restrict__ T64) {
   pdl_entry();
-  extern __shared__ float wt[];  // [32][H], the weight slot is stored pre-transposed
-  for (int i = threadIdx.x * 4; i < H * 32; i += blockDim.x * 4)
-    *reinterpret_cast<float4*>(&wt[i]) = *reinterpret_cast<const float4*>(&Wo[i]);
-  __syncthreads();
   const int U = g.int_rowptr[g.Nc_tot];
-  const int warps_per_cta = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  for (int u = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); u < U; u += gridDim.x * warps_per_cta) {
+  const int wpc = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int u = blockIdx.x * wpc + (threadIdx.x >> 5); u < U; u += gridDim.x * wpc) {
     const int ci = g.int_row[u], pi = g.int_col[u], pair = g.int_pair[u];
     const float t = pc32[(size_t)pi * ld32 + lane] * pc32[(size_t)ci * ld32 + 32 + lane];
-    float4 zr[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f0 = lane * 4 + i * 128;
-      if (f0 < H) zr[i] = ld4(P0 + (size_t)pair * H + f0);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f0 = lane * 4 + i * 128;
-      if (f0 >= H) break;
-      float4 z = zr[i];
-      float4 o = ld4(bo + f0);
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const float tk = __shfl_sync(0xffffffffu, t, k);
-        const float4 w = *reinterpret_cast<const float4*>(&wt[k * H + f0]);
-        o.x = fmaf(w.x, tk, o.x); o.y = fmaf(w.y, tk, o.y); o.z = fmaf(w.z, tk, o.z); o.w = fmaf(w.w, tk, o.w);
-      }
-      z.x += o.x; z.y += o.y; z.z += o.z; z.w += o.w;
-      st4(Zin + (size_t)u * H + f0, z);
+    T64[(size_t)u * 64 + lane] = from_f<T>(t);
+    T64[(size_t)u * 64 + 32 + lane] = from_f<T>(0.f);
+    for (int f0 = lane * 8; f0 < H; f0 += 256) {
+      float v[8];
+      ld8(P0 + (size_t)pair * H + f0, v);
+      st8(Zg + (size_t)u * H + f0, v);
     }
   }
 }
 
-int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, int ld32, const float* Wo,
-             const float* bo, void* Zin, bool bf16_mode, cudaStream_t st) {
+int pair_gather(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, int ld32, void* Zg, void* T64,
+                bool bf16_mode, cudaStream_t st) {
   if (cap_u <= 0) return FB_OK;
-  const int smem = H * 32 * 4;
-  const int grid = 148 * 2;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(pair_zin_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 4);
-    cudaFuncSetAttribute(pair_zin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 32 * 4);
-    attr = true;
-  }
-  if (bf16_mode) fb_launch(pair_zin_kernel<bf16>, dim3(grid), dim3(256), smem, st, g, H, (const bf16*)P0, pc32, ld32, Wo, bo, (bf16*)Zin);
-  else fb_launch(pair_zin_kernel<float>, dim3(grid), dim3(256), smem, st, g, H, (const float*)P0, pc32, ld32, Wo, bo, (float*)Zin);
+  if (H & 7) return FB_ERR_UNSUPPORTED;
+  const int grid = 148 * 4;
+  if (bf16_mode) fb_launch(pair_gather_kernel<bf16>, dim3(grid), dim3(256), 0, st, g, H, (const bf16*)P0, pc32, ld32, (bf16*)Zg, (bf16*)T64);
+  else fb_launch(pair_gather_kernel<float>, dim3(grid), dim3(256), 0, st, g, H, (const float*)P0, pc32, ld32, (float*)Zg, (float*)T64);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -602,42 +609,68 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
   }
   qkr = warp_sum(qkr);
   float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-  for (int e = lo + w; e < hi; e += 4) {
-    const int c = g.int_col[e];
-    const float rn = rad[e] * inv_norm;
-    float dot = 0.f, sdot = 0.f;
-    float4 vv[VEC];
+  constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: approximate exp / reciprocal
+  // two edges per trip: their gathers and warp reductions are independent and overlap
+  for (int e = lo + w; e < hi; e += 8) {
+    const bool two = e + 4 < hi;
+    const int ee[2] = {e, two ? e + 4 : e};
+    int cc[2];
+    float rn[2], dot[2] = {0.f, 0.f}, sdot[2] = {0.f, 0.f};
+    float4 vv[2][VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int f = (i * 32 + lane) * 4;
-      if (f < H) {
-        const float4 kk = ld4(Kt + (size_t)c * ldk + f);
-        const float4 vc = ld4(VC + (size_t)c * H + f);
-        const float4 v0 = ld4(V + (size_t)c * H + f);
-        const float4 uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f), vr = ld4(v_r + f);
-        dot += q[i].x * kk.x + q[i].y * kk.y + q[i].z * kk.z + q[i].w * kk.w;
-        sdot += w2.x * silu(vc.x + fmaf(rn, uu.x, bb.x)) + w2.y * silu(vc.y + fmaf(rn, uu.y, bb.y)) +
-                w2.z * silu(vc.z + fmaf(rn, uu.z, bb.z)) + w2.w * silu(vc.w + fmaf(rn, uu.w, bb.w));
-        vv[i] = make_float4(fmaf(rn, vr.x, v0.x), fmaf(rn, vr.y, v0.y), fmaf(rn, vr.z, v0.z), fmaf(rn, vr.w, v0.w));
-      } else vv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < 2; ++u) {
+      cc[u] = g.int_col[ee[u]];
+      rn[u] = rad[ee[u]] * inv_norm;
     }
-    dot = warp_sum(dot);
-    sdot = warp_sum(sdot);
-    const float logit = dot + rn * qkr + pb_dense[g.int_pair[e]];
-    if (att_logit && lane == 0) att_logit[e] = logit;
-    const float m_new = fmaxf(m, logit);
-    const float corr = expf(m - m_new), p = expf(logit - m_new);
-    l = l * corr + p;
-    const float ps = p * sdot;
-    ax = ax * corr + ps * (xr0 - x[3 * c]);
-    ay = ay * corr + ps * (xr1 - x[3 * c + 1]);
-    az = az * corr + ps * (xr2 - x[3 * c + 2]);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      acc[i].x = fmaf(p, vv[i].x, acc[i].x * corr); acc[i].y = fmaf(p, vv[i].y, acc[i].y * corr);
-      acc[i].z = fmaf(p, vv[i].z, acc[i].z * corr); acc[i].w = fmaf(p, vv[i].w, acc[i].w * corr);
+    for (int u = 0; u < 2; ++u) {
+      const int c = cc[u];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int f = (i * 32 + lane) * 4;
+        if (f < H) {
+          const float4 kk = ld4(Kt + (size_t)c * ldk + f);
+          const float4 vc = ld4(VC + (size_t)c * H + f);
+          const float4 v0 = ld4(V + (size_t)c * H + f);
+          const float4 uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f), vr = ld4(v_r + f);
+          dot[u] += q[i].x * kk.x + q[i].y * kk.y + q[i].z * kk.z + q[i].w * kk.w;
+          const float t0 = vc.x + fmaf(rn[u], uu.x, bb.x), t1 = vc.y + fmaf(rn[u], uu.y, bb.y);
+          const float t2 = vc.z + fmaf(rn[u], uu.z, bb.z), t3 = vc.w + fmaf(rn[u], uu.w, bb.w);
+          if (FAST) {
+            sdot[u] += w2.x * __fdividef(t0, 1.0f + __expf(-t0)) + w2.y * __fdividef(t1, 1.0f + __expf(-t1)) +
+                       w2.z * __fdividef(t2, 1.0f + __expf(-t2)) + w2.w * __fdividef(t3, 1.0f + __expf(-t3));
+          } else {
+            sdot[u] += w2.x * silu(t0) + w2.y * silu(t1) + w2.z * silu(t2) + w2.w * silu(t3);
+          }
+          vv[u][i] = make_float4(fmaf(rn[u], vr.x, v0.x), fmaf(rn[u], vr.y, v0.y), fmaf(rn[u], vr.z, v0.z), fmaf(rn[u], vr.w, v0.w));
+        } else vv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    m = m_new;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o); dot[1] += __shfl_xor_sync(0xffffffffu, dot[1], o);
+      sdot[0] += __shfl_xor_sync(0xffffffffu, sdot[0], o); sdot[1] += __shfl_xor_sync(0xffffffffu, sdot[1], o);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const int c = cc[u];
+      const float logit = dot[u] + rn[u] * qkr + pb_dense[g.int_pair[ee[u]]];
+      if (att_logit && lane == 0) att_logit[ee[u]] = logit;
+      const float m_new = fmaxf(m, logit);
+      const float corr = expf(m - m_new), p = expf(logit - m_new);
+      l = l * corr + p;
+      const float ps = p * sdot[u];
+      ax = ax * corr + ps * (xr0 - x[3 * c]);
+      ay = ay * corr + ps * (xr1 - x[3 * c + 1]);
+      az = az * corr + ps * (xr2 - x[3 * c + 2]);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        acc[i].x = fmaf(p, vv[u][i].x, acc[i].x * corr); acc[i].y = fmaf(p, vv[u][i].y, acc[i].y * corr);
+        acc[i].z = fmaf(p, vv[u][i].z, acc[i].z * corr); acc[i].w = fmaf(p, vv[u][i].w, acc[i].w * corr);
+      }
+      m = m_new;
+    }
   }
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {

@@ -20,8 +20,8 @@ int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t
 int row_attention(const GraphDev& g, int q_is_prot, int max_q, const float* Q, int ldq, const float* G, int ldg,
                   const float* K, int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode,
                   cudaStream_t st);
-int pair_zin(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, int ld32, const float* Wo, const float* bo,
-             void* Zin, bool bf16_mode, cudaStream_t st);
+int pair_gather(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, int ld32, void* Zg, void* T64,
+                bool bf16_mode, cudaStream_t st);
 int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, int stride, const float* cst, float* pb_dense,
                      cudaStream_t st);
 int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, const float* k_r,

@@ -6,6 +6,8 @@ arithmetic, evaluated in float64 and rounded once):
 
  * first Linear of every per-edge MLP is split into per-node blocks + a rank-1 radial column
    (edge_mlp.0 at egnn.py:78, linear_kv at egnn.py:203-205 with its interleaved k/v rows);
+ * the 32-channel InteractionModule output (cross_att.py:51) is folded into pair_transition.linear_1
+   (K-concatenated operand, see csrc/layers.cu::pair_gather_kernel);
  * pair_transition.linear_2 followed by attn_bias_proj collapses to one vector (egnn.py:208,
    cross_att.py:53): bias = wb.(W2 t + b2) + bb = (W2^T wb).t + (wb.b2 + bb);
  * ac_u = coord_mlp.0.weight @ v_r (the radial column of v pushed through the next Linear).
@@ -49,6 +51,7 @@ def _att(sd, p, H):
     z = lambda n: torch.zeros(n, dtype=torch.float64)
     Wkv = sd[p + "linear_kv.weight"].double()
     bkv = sd[p + "linear_kv.bias"].double()
+    W1p = sd[ca + "pair_transition.linear_1.weight"].double()
     W2 = sd[ca + "pair_transition.linear_2.weight"].double()
     b2 = sd[ca + "pair_transition.linear_2.bias"].double()
     wb = sd[p + "attn_bias_proj.weight"].double()[0]
@@ -68,8 +71,10 @@ def _att(sd, p, H):
         "tp2_w": sd[ca + "p_transition.linear_2.weight"], "tp2_b": sd[ca + "p_transition.linear_2.bias"],
         "tc1_w": sd[ca + "c_transition.linear_1.weight"], "tc1_b": sd[ca + "c_transition.linear_1.bias"],
         "tc2_w": sd[ca + "c_transition.linear_2.weight"], "tc2_b": sd[ca + "c_transition.linear_2.bias"],
-        "i32_o_w": sd[ca + "inter_layer.linear_out.weight"].t().contiguous(), "i32_o_b": sd[ca + "inter_layer.linear_out.bias"],
-        "pt1_w": sd[ca + "pair_transition.linear_1.weight"], "pt1_b": sd[ca + "pair_transition.linear_1.bias"],
+        # first pair-transition Linear with the 32-channel interaction output folded in:
+        #   W1 (pair0 + Wo t + bo) + b1 = [W1 | W1 Wo | 0] [pair0 | t | 0] + (b1 + W1 bo)
+        "pt1_w": torch.cat([W1p, W1p @ sd[ca + "inter_layer.linear_out.weight"].double(), torch.zeros(2 * H, 32, dtype=torch.float64)], 1),
+        "pt1_b": sd[ca + "pair_transition.linear_1.bias"].double() + W1p @ sd[ca + "inter_layer.linear_out.bias"].double(),
         "pt2v": W2.t() @ wb, "pt_c": (wb @ b2 + bb).reshape(1),
         # q | k | inter_layer.linear_p (32) | inter_layer.linear_c (32) | zero pad: one stacked node GEMM
         "qk_w": torch.cat([sd[p + "linear_q.weight"].double(), Wkv[0::2, 1:],

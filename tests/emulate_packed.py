@@ -174,8 +174,8 @@ def forward_emulated(sd, cfg, batch):
             nc1_t = c_off_t[1:] - c_off_t[:-1]
             pair = torch.from_numpy(pair_base.astype(np.int64))[eb] + (pi - p_off_t[eb]) * nc1_t[eb] + (ci - c_off_t[eb])
             u = is_c.nonzero().squeeze(1)
-            zin = P0[pair[u]] + F.linear(pc32[pi[u]] * pc32[ci[u]], W.m(pre + "i32_o_w").t(), W.m(pre + "i32_o_b"))
-            pbu = F.relu(F.linear(zin, W.m(pre + "pt1_w"), W.m(pre + "pt1_b"))) @ W.m(pre + "pt2v") + W.m(pre + "pt_c")
+            zcat = torch.cat([P0[pair[u]], pc32[pi[u]] * pc32[ci[u]], torch.zeros(u.numel(), 32)], 1)   # [pair0 | t | 0]
+            pbu = F.relu(F.linear(zcat, W.m(pre + "pt1_w"), W.m(pre + "pt1_b"))) @ W.m(pre + "pt2v") + W.m(pre + "pt_c")
             pb_dense = torch.zeros(P0.shape[0])
             pb_dense[pair[u]] = pbu
             rn = _radial(int_r, int_c, x, cplx_t, B)
