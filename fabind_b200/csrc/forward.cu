@@ -51,6 +51,7 @@ void prof_end(cudaStream_t st) {
 }
 
 constexpr int HD = 128;  // RowAttentionBlock: 4 heads x 32 channels (cross_att.py:98)
+static inline int pb_cols(int L) { return (16 * L + 127) / 128 * 128; }
 constexpr int QKX = 128; // extra columns of the stacked q|k GEMM: inter_layer linear_p (32) | linear_c (32) | pad
 
 // ------------------------------------------------------------------------------------------------
@@ -86,7 +87,8 @@ static void build_weights(int H, int L, ModelW& w) {
   w.il_p_w = add("il_p_w", H, H); w.il_p_b = add("il_p_b", 1, H);
   w.il_c_w = add("il_c_w", H, H); w.il_c_b = add("il_c_b", 1, H);
   w.il_o_w = add("il_o_w", H, H); w.il_o_b = add("il_o_b", 1, H);
-  w.pb_w = add("pb_w", 16 * L, H); w.pb_b = add("pb_b", 1, 16 * L);
+  // pair-bias projections of all layers, zero-padded to a multiple of 128 outputs so the GEMM tiles on tcgen05
+  w.pb_w = add("pb_w", pb_cols(L), H); w.pb_b = add("pb_b", 1, pb_cols(L));
   for (int i = 0; i <= L; ++i) {
     const std::string p = i < L ? "gcl" + std::to_string(i) + "." : std::string("out.");
     GclW g;
@@ -212,7 +214,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.VCT = a.take(N * H * TS);
   // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
   b.A0 = a.take(P * H * TS);
-  b.PBraw = a.get<float>(P * L * 16);
+  b.PBraw = a.get<float>(P * pb_cols((int)L));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,8 +349,9 @@ struct Run {
     gemm(b.A0, H, H, w.il_o_w, H, w.il_o_b, FB_ACT_NONE, (int)P, nullptr, 0, b.P0, H);
     // gated pair biases of all RowAttentionBlocks at once (pair0 is layer- and iteration-invariant in v1)
     if (p.n_layers > 0) {
-      gemm(b.P0, H, H, w.pb_w, 16 * p.n_layers, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, 16 * p.n_layers, nullptr, 0);
-      stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, p.n_layers, b.PBraw, b.PB, st); });
+      const int pbc = pb_cols(p.n_layers);
+      gemm(b.P0, H, H, w.pb_w, pbc, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, pbc, nullptr, 0);
+      stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, p.n_layers, b.PBraw, pbc, b.PB, st); });
     }
     gemm_cat = CAT_GEMM_NODE;
     // context graph: protein coordinates are reset every iteration, so it is built once

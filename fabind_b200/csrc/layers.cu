@@ -354,7 +354,7 @@ int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0,
 
 // gated pair bias of every RowAttentionBlock (cross_att.py:125):  raw[pair, l*16 + blk*8 + {0..3 lin, 4..7 gate}]
 //  ->  PB[(l*2+blk) * P_total*4 + pair*4 + h] = lin * sigmoid(gate)
-__global__ void pair_bias_gate_kernel(int P_total, int L, const float* __restrict__ raw, float* __restrict__ PB) {
+__global__ void pair_bias_gate_kernel(int P_total, int L, const float* __restrict__ raw, int ld_raw, float* __restrict__ PB) {
   pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)P_total * L * 8;
@@ -362,13 +362,13 @@ __global__ void pair_bias_gate_kernel(int P_total, int L, const float* __restric
   const int h = i & 3;
   const int slab = (int)((i >> 2) % (L * 2));
   const int pair = (int)(i / (8LL * L));
-  const float* rp = raw + (size_t)pair * L * 16 + slab * 8;
+  const float* rp = raw + (size_t)pair * ld_raw + slab * 8;
   PB[(size_t)slab * P_total * 4 + (size_t)pair * 4 + h] = rp[h] * sigmoidf(rp[4 + h]);
 }
 
-int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t st) {
+int pair_bias_gate(int P_total, int L, const float* raw, int ld_raw, float* PB, cudaStream_t st) {
   const long long total = (long long)P_total * L * 8;
-  fb_launch(pair_bias_gate_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, P_total, L, raw, PB);
+  fb_launch(pair_bias_gate_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, P_total, L, raw, ld_raw, PB);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

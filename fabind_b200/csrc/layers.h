@@ -16,7 +16,7 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st);
 int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0, bool bf16_mode, cudaStream_t st);
-int pair_bias_gate(int P_total, int L, const float* raw, float* PB, cudaStream_t st);
+int pair_bias_gate(int P_total, int L, const float* raw, int ld_raw, float* PB, cudaStream_t st);
 int row_attention(const GraphDev& g, int q_is_prot, int max_q, const float* Q, int ldq, const float* G, int ldg,
                   const float* K, int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode,
                   cudaStream_t st);

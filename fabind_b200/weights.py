@@ -103,8 +103,9 @@ def _top(sd, H, L):
         "il_o_w": sd["inter_layer.linear_out.weight"], "il_o_b": sd["inter_layer.linear_out.bias"],
     }
     if L > 0:
-        d["pb_w"] = torch.cat(rows, 0)
-        d["pb_b"] = torch.cat(bias, 0)
+        pad = (-16 * L) % 128     # zero rows: the slot is padded to a multiple of 128 outputs
+        d["pb_w"] = torch.cat(rows + [torch.zeros(pad, H)], 0)
+        d["pb_b"] = torch.cat(bias + [torch.zeros(pad)], 0)
     return d
 
 

@@ -102,7 +102,7 @@ def forward_emulated(sd, cfg, batch):
         pp, cc = pc[p_off[b]:p_off[b + 1]], pc[c_off[b]:c_off[b + 1]]
         P0.append(F.linear((pp[:, None, :] * cc[None, :, :]).reshape(-1, H), W.m("il_o_w"), W.m("il_o_b")))
     P0 = torch.cat(P0)
-    raw = F.linear(P0, W.m("pb_w"), W.m("pb_b")).view(-1, L, 2, 2, 4)
+    raw = F.linear(P0, W.m("pb_w"), W.m("pb_b"))[:, :16 * L].reshape(-1, L, 2, 2, 4)
     PB = raw[:, :, :, 0] * torch.sigmoid(raw[:, :, :, 1])          # [P, L, blk, head]
 
     (ctx_r, ctx_c), _ = _edges(x_state, lay_np, intra, inter, bonds_int)
