@@ -11,6 +11,11 @@ def published_args(**over):
         fix_pocket=False, rm_LAS_constrained_optim=False, random_n_iter=True, refine="refine_coord",
         ablation_no_attention=False, ablation_no_attention_with_cross_attn=False,
         geometry_reg_step_size=0.001, coordinate_scale=5.0, inter_cutoff=10, intra_cutoff=8,
+        # L2 wrapper (models/model.py): published command + argparse defaults (main_fabind.py:43-191)
+        mean_layers=4, n_iter=8, pocket_pred_layers=1, pocket_pred_n_iter=1, hidden_size=512,
+        pocket_pred_hidden_size=128, stage_prob=0.25, use_esm2_feat=True, esm2_concat_raw=False, gs_tau=1.0,
+        gs_hard=False, pocket_radius=20.0, local_eval=False, train_pred_pocket_noise=0.0,
+        compound_coords_init_mode="pocket_center_rdkit", center_dist_threshold=4.0,
     )
     for k, v in over.items():
         setattr(a, k, v)

@@ -145,3 +145,145 @@ def randomize_coord_heads(module, std=0.5, seed=1234):
             if name.endswith("coord_mlp.2.weight") or name.endswith("coord_mlp.linear2.weight"):
                 p.copy_(torch.randn(p.shape, generator=g) * std / (p.shape[1] ** 0.5) * 4.0)
     return module
+
+
+# ------------------------------------------------------------------------------------------------------
+# Whole-protein docking batches for the L2 wrapper (models/model.py): a duck-typed stand-in for the
+# collated torch_geometric HeteroData the reference dataloader produces (utils/utils.py:202-442).
+# ------------------------------------------------------------------------------------------------------
+class _Store:
+    """attribute bag (one node/edge store of a HeteroData)"""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def to(self, device):
+        return _Store(**{k: (v.to(device) if torch.is_tensor(v) else v) for k, v in self.__dict__.items()})
+
+
+class HeteroBatch:
+    """`data['compound'].batch`, `data['complex', 'c2c', 'complex'].edge_index`, `data.pocket_idx` ... as the
+    reference's model.forward / model.inference access them."""
+
+    def __init__(self):
+        object.__setattr__(self, "_stores", {})
+
+    def __getitem__(self, key):
+        if key not in self._stores:
+            self._stores[key] = _Store()
+        return self._stores[key]
+
+    def to(self, device):
+        out = HeteroBatch()
+        for k, v in self._stores.items():
+            out._stores[k] = v.to(device)
+        for k, v in self.__dict__.items():
+            if k != "_stores":
+                setattr(out, k, v.to(device) if torch.is_tensor(v) else v)
+        return out
+
+    def clone(self):
+        out = HeteroBatch()
+        for k, v in self._stores.items():
+            out._stores[k] = _Store(**{a: (t.clone() if torch.is_tensor(t) else t) for a, t in v.__dict__.items()})
+        for k, v in self.__dict__.items():
+            if k != "_stores":
+                setattr(out, k, v.clone() if torch.is_tensor(v) else v)
+        return out
+
+
+def make_docking_batch(n_complexes=2, seed=0, n_c_range=(10, 40), L_range=(150, 400), protein_feat=1280,
+                       pocket_radius=20.0):
+    """Whole proteins (jittered 5.2 A lattice inside a sphere, centred like utils.py:209-211), a ligand random
+    walk near a surface-ish site, torchdrug-like 56-d atom features and ESM-like 1280-d residue features."""
+    rng = np.random.default_rng(seed)
+    d = HeteroBatch()
+    comp_feats, comp_coords, comp_rdkit, comp_batch = [], [], [], []
+    prot_feats, prot_xyz, prot_batch, pocket_idx = [], [], [], []
+    wp_coords, wp_las, wp_seg, wp_mask, wp_glb, wp_batch, wp_c2c, wp_LAS = [], [], [], [], [], [], [], []
+    cx_coords, cx_las, cx_seg, cx_mask, cx_glb, cx_batch, cx_c2c, cx_LAS = [], [], [], [], [], [], [], []
+    ael_x, ael_b, lel_x, lel_b = [], [], [], []
+    pocket_xyz, pocket_batch, keep_all, dis_map, centers = [], [], [], [], []
+    off_wp = off_cx = 0
+    for b in range(n_complexes):
+        nc = int(rng.integers(n_c_range[0], n_c_range[1] + 1))
+        L = int(rng.integers(L_range[0], L_range[1] + 1))
+        half = 2
+        while (2 * half + 1) ** 3 < 2 * L + 64:
+            half += 1
+        gl = np.arange(-half, half + 1, dtype=np.float64) * 5.2
+        pts = np.stack(np.meshgrid(gl, gl, gl, indexing="ij"), -1).reshape(-1, 3) + rng.uniform(-1, 1, size=((2 * half + 1) ** 3, 3))
+        site = rng.normal(size=3)
+        site = site / np.linalg.norm(site) * 9.0                 # binding site 9 A off the protein centre
+        keep_pts = np.linalg.norm(pts - site, axis=1) > 6.0        # cavity
+        pts = pts[keep_pts]
+        order = np.argsort(np.linalg.norm(pts, axis=1), kind="stable")[:L]
+        order.sort()
+        prot = pts[order]
+        prot = prot - prot.mean(0)                                  # utils.py:209-211
+        site = site - pts[order].mean(0)
+        lig = np.zeros((nc, 3))
+        for i in range(1, nc):
+            for _ in range(64):
+                step = rng.normal(size=3)
+                step *= 1.5 / np.linalg.norm(step)
+                base = lig[i - 1] if rng.uniform() < 0.8 else lig[rng.integers(0, i)]
+                cand = base + step
+                if np.linalg.norm(cand) < 5.0 and (i < 2 or np.min(np.linalg.norm(lig[:i] - cand, axis=1)) > 1.1):
+                    break
+            lig[i] = cand
+        lig_true = lig + site                                       # ground-truth pose
+        dm = np.linalg.norm(lig[:, None] - lig[None], axis=-1)
+        np.fill_diagonal(dm, 1e9)
+        bonds = np.argwhere(dm < 1.7)
+        las = np.argwhere(dm < 2.7)
+        rdkit = lig + rng.normal(scale=0.3, size=lig.shape)        # "rdkit conformer"
+        com = lig_true.mean(0)
+        keep = np.linalg.norm(prot - com, axis=1) < pocket_radius
+        if keep.sum() < 5:
+            keep[:100] = True
+        pocket = prot[keep]
+        coords_init = rdkit - rdkit.mean(0) + pocket.mean(0)        # pocket_center_rdkit, utils.py:319
+        z = np.zeros((1, 3))
+        n_wp, n_cx = nc + L + 2, nc + int(keep.sum()) + 2
+        wp_coords.append(np.concatenate([z, coords_init - coords_init.mean(0), z, prot]))
+        wp_las.append(np.concatenate([z, rdkit, z, np.zeros_like(prot)]))
+        cx_coords.append(np.concatenate([z, coords_init, z, pocket]))
+        cx_las.append(np.concatenate([z, rdkit, z, np.zeros_like(pocket)]))
+        for (n, seg_l, msk_l, glb_l, bat_l) in ((n_wp, wp_seg, wp_mask, wp_glb, wp_batch), (n_cx, cx_seg, cx_mask, cx_glb, cx_batch)):
+            s = np.zeros(n, dtype=np.float32); s[nc + 1:] = 1
+            m = np.zeros(n, dtype=bool); m[:nc + 2] = True
+            g = np.zeros(n, dtype=bool); g[0] = True; g[nc + 1] = True
+            seg_l.append(s); msk_l.append(m); glb_l.append(g); bat_l.append(np.full(n, b))
+        wp_c2c.append(bonds.T + 1 + off_wp); wp_LAS.append(las.T + 1 + off_wp)
+        cx_c2c.append(bonds.T + 1 + off_cx); cx_LAS.append(las.T + 1 + off_cx)
+        ael_x.append(bonds + 1); ael_b.append(np.full(len(bonds), b))
+        lel_x.append(las + 1); lel_b.append(np.full(len(las), b))
+        comp_feats.append(rng.normal(scale=0.5, size=(nc, 56))); comp_coords.append(coords_init); comp_rdkit.append(rdkit)
+        comp_batch.append(np.full(nc, b))
+        prot_feats.append(rng.normal(scale=0.3, size=(L, protein_feat))); prot_xyz.append(prot); prot_batch.append(np.full(L, b))
+        pocket_idx.append(keep.astype(np.int32)); keep_all.append(keep)
+        pocket_xyz.append(pocket); pocket_batch.append(np.full(int(keep.sum()), b))
+        dmap = np.linalg.norm(pocket[:, None] - lig_true[None], axis=-1).reshape(-1)
+        dis_map.append(np.minimum(dmap, 10.0)); centers.append(com)
+        off_wp += n_wp; off_cx += n_cx
+    f = lambda a, ax=0: torch.from_numpy(np.concatenate(a, ax)).float()
+    li = lambda a, ax=0: torch.from_numpy(np.concatenate(a, ax).astype(np.int64))
+    d['compound'].node_feats = f(comp_feats); d['compound'].node_coords = f(comp_coords)
+    d['compound'].rdkit_coords = f(comp_rdkit); d['compound'].batch = li(comp_batch)
+    d['protein_whole'].node_feats = f(prot_feats); d['protein_whole'].batch = li(prot_batch)
+    d['pocket'].batch = li(pocket_batch); d['pocket'].keepNode = torch.from_numpy(np.concatenate(keep_all))
+    for name, (co, la, sg, mk, gb, bt, c2c, LAS) in {
+            'complex_whole_protein': (wp_coords, wp_las, wp_seg, wp_mask, wp_glb, wp_batch, wp_c2c, wp_LAS),
+            'complex': (cx_coords, cx_las, cx_seg, cx_mask, cx_glb, cx_batch, cx_c2c, cx_LAS)}.items():
+        d[name].node_coords = f(co); d[name].node_coords_LAS = f(la)
+        d[name].segment = torch.from_numpy(np.concatenate(sg)); d[name].mask = torch.from_numpy(np.concatenate(mk))
+        d[name].is_global = torch.from_numpy(np.concatenate(gb)); d[name].batch = li(bt)
+        d[name, 'c2c', name].edge_index = li(c2c, 1); d[name, 'LAS', name].edge_index = li(LAS, 1)
+    d['compound_atom_edge_list'].x = li(ael_x); d['compound_atom_edge_list'].batch = li(ael_b)
+    d['LAS_edge_list'].x = li(lel_x); d['LAS_edge_list'].batch = li(lel_b)
+    d.node_xyz = f(pocket_xyz); d.node_xyz_whole = f(prot_xyz)
+    d.coords_center = torch.from_numpy(np.stack(centers)).float()
+    d.pocket_idx = torch.from_numpy(np.concatenate(pocket_idx))
+    d.dis_map = f(dis_map)
+    return d

@@ -137,6 +137,33 @@ int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, in
 /* development probe: when non-null, sampled CTAs of the tcgen05 GEMM write 8 globaltimer stamps each */
 int32_t fb_gemm_set_debug(int64_t* dbg);
 
+/* ---- L2 wrapper ops (reference: models/model.py, IaBNet_mean_and_pocket_prediction_cls_coords_dependent) ---- */
+/* out[i,:] = scale * src_{kind[i]}[idx[i],:] (a null source gives zeros): the [glb_c | atoms | glb_p | residues]
+ * feature / coordinate assembly of model.py:104-115,205-253 and every boolean-mask row selection */
+int32_t fb_assemble_rows(float* out, int32_t M, int32_t D, const uint8_t* kind, const int32_t* idx, const float* s0,
+                         const float* s1, const float* s2, const float* s3, float scale, void* stream);
+/* torch.nn.LayerNorm (model.py:22,352-353) */
+int32_t fb_layernorm(const float* x, int32_t M, int32_t D, const float* gamma, const float* beta, float eps, float* out,
+                     void* stream);
+/* predicted pocket centre: mode 0 = model.forward eval path (model.py:146-158), mode 1 = model.inference (:423-437) */
+int32_t fb_pocket_center(const float* logit, const float* xyz, const int32_t* prot_off, int32_t B, float tau, int32_t hard,
+                         int32_t mode, float* centers, void* stream);
+/* get_keepNode_tensor (utils/utils.py:147-158) + the "<5 residues -> first 100" rule (model.py:199-202) */
+int32_t fb_pocket_mask(const float* xyz, const int32_t* prot_off, int32_t B, const float* centers, float radius, uint8_t* keep,
+                       int32_t* less5, void* stream);
+/* ligand start pose: lig - mean(lig) + mean(pocket) per complex (model.py:227) */
+int32_t fb_ligand_place(const float* lig, const int32_t* comp_off, const float* pocket, const int32_t* pocket_off, int32_t B,
+                        float* out, void* stream);
+/* distance head (model.py:349-365): outer product operand, then (after fb_gemm with the row-dot epilogue) sigmoid*10 and cdist */
+int32_t fb_head_outer(const float* pocket_ln, const float* comp_ln, const int32_t* pocket_off, const int32_t* comp_off,
+                      const int32_t* pair_off, int32_t B, int32_t n_pairs, int32_t H, void* Z, int32_t bf16_mode, void* stream);
+int32_t fb_head_finish(const float* dot, int32_t tiles, int32_t stride, const float* b2, const float* pocket_xyz,
+                       const float* lig_xyz, const int32_t* pocket_off, const int32_t* comp_off, const int32_t* pair_off,
+                       int32_t B, int32_t n_pairs, float scale, float* y_pred, float* y_coords, void* stream);
+int32_t fb_pair_dist(const float* pocket_xyz, const float* lig_xyz, const int32_t* pocket_off, const int32_t* comp_off,
+                     const int32_t* pair_off, int32_t B, int32_t n_pairs, float cap, float* out, void* stream);
+int32_t fb_dot_finish(const float* dot, int32_t tiles, int32_t stride, int32_t M, const float* bias, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,10 @@ def det_tensor(name, shape, seed=0):
         bound = 0.05
     else:
         bound = 0.1
-    return torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32))
+    t = torch.from_numpy(rng.uniform(-bound, bound, size=shape).astype(np.float32))
+    if name.endswith("layernorm.weight"):
+        t = 1.0 + t
+    return t
 
 
 def det_state_dict(shapes, seed=0):

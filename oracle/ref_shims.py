@@ -118,6 +118,41 @@ def load_reference(flavour="v1"):
     return mods
 
 
+def _install_utils_stub():
+    """`models/model.py:8` imports two helpers from utils.utils, whose own imports (rdkit, torchmetrics, ...) are
+    not installed.  They are restated here from their definitions (utils/utils.py:147-158, 687-699)."""
+    if "utils.utils" in sys.modules:
+        return
+    def get_keepNode_tensor(protein_node_xyz, pocket_radius, add_noise_to_com, chosen_pocket_com):
+        if add_noise_to_com:
+            chosen_pocket_com = chosen_pocket_com + add_noise_to_com * (2 * torch.rand_like(chosen_pocket_com) - 1)
+        dis = torch.sqrt(torch.sum((protein_node_xyz - chosen_pocket_com.unsqueeze(0)) ** 2, dim=-1))
+        return dis < pocket_radius
+
+    def gumbel_softmax_no_random(logits, tau=1, hard=False, eps=1e-10, dim=-1):
+        y_soft = (logits / tau).softmax(dim)
+        if hard:
+            index = y_soft.max(dim, keepdim=True)[1]
+            y_hard = torch.zeros_like(logits, memory_format=torch.legacy_contiguous_format).scatter_(dim, index, 1.0)
+            return y_hard - y_soft.detach() + y_soft
+        return y_soft
+    pkg = types.ModuleType("utils")
+    mod = types.ModuleType("utils.utils")
+    mod.get_keepNode_tensor = get_keepNode_tensor
+    mod.gumbel_softmax_no_random = gumbel_softmax_no_random
+    pkg.utils = mod
+    sys.modules["utils"] = pkg
+    sys.modules["utils.utils"] = mod
+
+
+def load_reference_model_module():
+    """The reference's L2 wrapper `models.model` (v1), imported unmodified."""
+    mods = load_reference("v1")
+    _install_utils_stub()
+    mods.model = importlib.import_module("models.model")
+    return mods
+
+
 def published_args(**over):
     """The flags of the published v1 evaluation command (F/test_fabind.py:182) that the path reads."""
     from fabind_b200.config import published_args as _pa

@@ -89,5 +89,26 @@ def main():
               "E_int", [int(e[1].shape[1]) for e in edges])
 
 
+def main_l2():
+    """goldens for the L2 wrapper (models/model.py): forward(stage=2) in eval mode and inference()"""
+    from fabind_b200.synthetic import make_docking_batch
+    mods = ref_shims.load_reference_model_module()
+    cases = {"l2_h64_p32_l2_it2": (64, 32, 2, 2, dict(n_complexes=3, seed=1), 41)}
+    for name, (emb, pemb, L, IT, bkw, wseed) in cases.items():
+        args = ref_shims.published_args(mean_layers=L, n_iter=IT)
+        m = mods.model.IaBNet_mean_and_pocket_prediction_cls_coords_dependent(args, emb, pemb).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+        d = make_docking_batch(**bkw)
+        with torch.no_grad():
+            fwd = m(d.clone(), stage=2)
+            inf = m.inference(d.clone())
+        torch.save({"recipe": dict(emb=emb, pemb=pemb, mean_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed),
+                    "shapes": shapes, "forward": [t.clone() if torch.is_tensor(t) else t for t in fwd],
+                    "inference": inf[0].clone(), "torch": torch.__version__}, os.path.join(OUT, name + ".pt"))
+        print(name, [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd])
+
+
 if __name__ == "__main__":
     main()
+    main_l2()

@@ -12,7 +12,22 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "v1_*.pt")))
+
+
+def l2_golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "l2_*.pt")))
+
+
+def load_l2_golden(path):
+    from fabind_b200.config import published_args
+    from fabind_b200.synthetic import make_docking_batch
+    g = torch.load(path, map_location="cpu", weights_only=False)
+    r = g["recipe"]
+    args = published_args(mean_layers=r["mean_layers"], n_iter=r["n_iter"])
+    data = make_docking_batch(**r["batch"])
+    sd = det_state_dict(g["shapes"], r["weight_seed"])
+    return g, r, args, data, sd
 
 
 def load_golden(path):
