@@ -64,7 +64,7 @@ struct AttW {
   int64_t ca_c_w, ca_c_b, ca_p_w, ca_p_b, ca_p2_w, o_p_w, o_p_b, o_c_w, o_c_b;
   int64_t tp1_w, tp1_b, tp2_w, tp2_b, tc1_w, tc1_b, tc2_w, tc2_b;
   int64_t pt1_w, pt1_b, pt2v, pt_c;
-  int64_t qk_w, qk_b, k_r, v_w, v_b, v_r, ac1_w, ac1_b, ac2_w, ac_u;
+  int64_t qk_w, qk_b, k_r, v_r, ac1_b, ac2_w, ac_u;
 };
 struct ModelW {
   int64_t in_w, in_b, out_w, out_b, il_p_w, il_p_b, il_c_w, il_c_b, il_o_w, il_o_b, pb_w, pb_b;
@@ -113,9 +113,10 @@ static void build_weights(int H, int L, ModelW& w) {
     a.tc2_w = add(p + "tc2_w", H, 2 * H); a.tc2_b = add(p + "tc2_b", 1, H);
     a.pt1_w = add(p + "pt1_w", 2 * H, H + 64); a.pt1_b = add(p + "pt1_b", 1, 2 * H);
     a.pt2v = add(p + "pt2v", 1, 2 * H); a.pt_c = add(p + "pt_c", 1, 1);
-    a.qk_w = add(p + "qk_w", 2 * H + QKX, H); a.qk_b = add(p + "qk_b", 1, 2 * H + QKX); a.k_r = add(p + "k_r", 1, H);
-    a.v_w = add(p + "v_w", H, H); a.v_b = add(p + "v_b", 1, H); a.v_r = add(p + "v_r", 1, H);
-    a.ac1_w = add(p + "ac1_w", H, H); a.ac1_b = add(p + "ac1_b", 1, H);
+    // one stacked node GEMM: q | k | inter32_p | inter32_c | pad  ||  v | vc   (vc = coord_mlp.0 applied to v, folded)
+    a.qk_w = add(p + "qk_w", 4 * H + QKX, H); a.qk_b = add(p + "qk_b", 1, 4 * H + QKX); a.k_r = add(p + "k_r", 1, H);
+    a.v_r = add(p + "v_r", 1, H);
+    a.ac1_b = add(p + "ac1_b", 1, H);
     a.ac2_w = add(p + "ac2_w", 1, H); a.ac_u = add(p + "ac_u", 1, H);
     w.att.push_back(a);
   }
@@ -210,8 +211,8 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.dotU = a.get<float>(tiles2H * capU);
   b.radi = a.get<float>(capI); b.normi = a.get<float>(p.B);
   b.QK = a.get<float>(N * (2 * H + QKX));
-  b.VT = a.take(N * H * TS);
-  b.VCT = a.take(N * H * TS);
+  b.VT = a.take(N * 2 * H * TS);   // [N, 2H] typed: v | vc
+  b.VCT = nullptr;
   // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
   b.A0 = a.take(P * H * TS);
   b.PBraw = a.get<float>(P * pb_cols((int)L));
@@ -243,7 +244,8 @@ struct Run {
   // C = act(A W^T + b) with the usual optional extras
   void gemm(const void* A, int lda, int K, int64_t w_off, int Nout, int64_t b_off, int act, int M, float* C, int ldc,
             void* Cb, int ldcb, const float* res = nullptr, int ldres = 0, const void* A2 = nullptr, int lda2 = 0,
-            int K2 = 0, int64_t dotv_off = -1, float* dot_out = nullptr, int dot_stride = 0, const int* m_dev = nullptr) {
+            int K2 = 0, int64_t dotv_off = -1, float* dot_out = nullptr, int dot_stride = 0, const int* m_dev = nullptr,
+            int n_split = 0) {
     if (M <= 0) return;
     GemmArgs a;
     a.A = A; a.lda = lda; a.K1 = K; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
@@ -254,7 +256,8 @@ struct Run {
       if (C == nullptr) { a.C = (float*)Cb; a.ldc = ldcb; }
     }
     a.dotv = dotv_off >= 0 ? F(dotv_off) : nullptr; a.dot_out = dot_out; a.dot_stride = dot_stride;
-    a.M = M; a.N = Nout; a.m_dev = m_dev;
+    a.M = M; a.N = Nout; a.m_dev = m_dev; a.n_split = n_split;
+    if (n_split > 0) { a.C = C; a.ldc = ldc; a.Cb = Cb; a.ldcb = ldcb; }   // both outputs are live in either precision
     prof_begin(gemm_cat, st);
     chk(gemm_launch(a, bf, st));
     prof_end(st);
@@ -311,7 +314,8 @@ struct Run {
     // q | k of the interfacial attention stacked with the 32-channel interaction projections
     // (cross_att.py:22,51: linear_p on protein rows, linear_c on compound rows) in ONE node GEMM
     const int ldqk = 2 * H + QKX;
-    gemm(b.hT, H, H, aw.qk_w, ldqk, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, nullptr, 0);
+    gemm(b.hT, H, H, aw.qk_w, ldqk + 2 * H, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, b.VT, 2 * H, nullptr, 0, nullptr, 0, 0, -1,
+         nullptr, 0, nullptr, ldqk);
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
@@ -324,10 +328,8 @@ struct Run {
     stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
     // --- interfacial attention (egnn.py:186-252)
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
-    gemm(b.hT, H, H, aw.v_w, H, aw.v_b, FB_ACT_NONE, N, nullptr, 0, b.VT, H);
-    gemm(b.VT, H, H, aw.ac1_w, H, -1, FB_ACT_NONE, N, nullptr, 0, b.VCT, H);
     stage(CAT_ATTENTION, [&] {
-      return inter_attention(g, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, b.VCT, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
+      return inter_attention(g, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
                              b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st);
     });
   }

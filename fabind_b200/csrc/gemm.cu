@@ -27,6 +27,7 @@ int gemm_dot_tiles(int M, int N, int K, bool bf16_mode) {
 int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
   if (bf16_mode && gemm_tc_supported(g)) {
     if (tc_version() == 2 && gemm_tc2_shape_ok(g.N)) return gemm_tc2_launch(g, st);
+    if (g.n_split > 0) return gemm_simt_launch(g, bf16_mode, st);   // v1 kernel has no column routing
     return gemm_tc_launch(g, st);
   }
   return gemm_simt_launch(g, bf16_mode, st);

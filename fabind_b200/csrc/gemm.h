@@ -18,6 +18,7 @@ struct GemmArgs {
   // row-dot epilogue: dot_out[nt * dot_stride + m] = sum_{n in N-tile nt} dotv[n] * value(m, n)
   const float* dotv = nullptr; float* dot_out = nullptr; int dot_stride = 0;
   int M = 0, N = 0;
+  int n_split = 0;                                       // >0: columns < n_split go to C only, the rest to Cb only (at column n - n_split)
   const int* m_dev = nullptr;                            // optional device-side row count (<= M)
 };
 

@@ -68,8 +68,13 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
         if (g.bias) v += g.bias[n];
         v = apply_act_rt(v, g.act);
         if (g.res) v += g.res[(size_t)m * g.ldres + n];
-        if (g.C) g.C[(size_t)m * g.ldc + n] = v;
-        if (Cb) Cb[(size_t)m * g.ldcb + n] = from_f<T>(v);
+        if (g.n_split > 0) {
+          if (n < g.n_split) { if (g.C) g.C[(size_t)m * g.ldc + n] = v; }
+          else if (Cb) Cb[(size_t)m * g.ldcb + (n - g.n_split)] = from_f<T>(v);
+        } else {
+          if (g.C) g.C[(size_t)m * g.ldc + n] = v;
+          if (Cb) Cb[(size_t)m * g.ldcb + n] = from_f<T>(v);
+        }
         if (g.dotv) dsum = fmaf(g.dotv[n], v, dsum);
       }
     }

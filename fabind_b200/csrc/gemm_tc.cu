@@ -243,6 +243,7 @@ bool tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
 bool gemm_tc_shape_ok(int N, int K) { return N >= tc::BN_SEL && (N % tc::BN_SEL) == 0 && K >= 64 && (K % 64) == 0; }
 
 bool gemm_tc_supported(const GemmArgs& g) {
+  if (g.n_split > 0 && (g.n_split % 128)) return false;
   if (!gemm_tc_shape_ok(g.N, g.K1 + g.K2)) return false;
   if ((g.K1 % 64) || (g.K2 % 64) || g.K1 <= 0) return false;
   if ((g.lda % 8) || ((uintptr_t)g.A & 15) || ((uintptr_t)g.W & 15)) return false;

@@ -28,7 +28,7 @@ using namespace tc;
 
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;   // 320
-constexpr int MAX_N = 1280;                     // bias / dot vectors staged for the whole N
+constexpr int MAX_N = 2304;                     // bias / dot vectors staged for the whole N
 
 struct Params {
   int M, N, KB1, KB2;
@@ -38,6 +38,7 @@ struct Params {
   float* C; int ldc;
   bf16* Cb; int ldcb;
   const float* dotv; float* dot_out; int dot_stride;
+  int n_split;
   long long* dbg;
 };
 
@@ -195,13 +196,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) dsum = fmaf(s_dot[n0 + c + j], o[j], dsum);
         }
-        if (p.C || p.Cb) {
+        const int ncol0 = n0 + c;
+        float* const outC = (p.n_split > 0 && ncol0 >= p.n_split) ? nullptr : p.C;
+        bf16* const outCb = (p.n_split > 0 && ncol0 < p.n_split) ? nullptr : p.Cb;
+        const int cb_shift = p.n_split > 0 ? p.n_split : 0;
+        if (outC || outCb) {
           // transpose through smem: thread = row  ->  lane = column
 #pragma unroll
           for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = o[j];
           __syncwarp();
           const int ncol = n0 + c;
-          if (p.C || p.res) {
+          if (outC || p.res) {
             // C may alias res (in-place residual update of h): loads of a batch of rows are issued before any
             // store of that batch so that they pipeline instead of serialising behind may-alias stores
 #pragma unroll (BN == 128 ? 4 : 1)
@@ -218,21 +223,21 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
                 const int m = m0 + q * 32 + r0 + i;
                 if (m < M) {
                   const float x = xp[(r0 + i) * 33 + lane] + rv[i];
-                  if (p.C) p.C[(size_t)m * p.ldc + ncol + lane] = x;
-                  if (p.Cb) xp[(r0 + i) * 33 + lane] = x;     // keep the residual-added value for the bf16 copy
+                  if (outC) outC[(size_t)m * p.ldc + ncol + lane] = x;
+                  if (outCb) xp[(r0 + i) * 33 + lane] = x;     // keep the residual-added value for the bf16 copy
                 }
               }
             }
             __syncwarp();
           }
-          if (p.Cb) {
+          if (outCb) {
             const int rr = lane >> 4, cp = (lane & 15) * 2;
 #pragma unroll 4
             for (int r = 0; r < 32; r += 2) {
               const int m = m0 + q * 32 + r + rr;
               if (m < M) {
                 const __nv_bfloat162 t = __floats2bfloat162_rn(xp[(r + rr) * 33 + cp], xp[(r + rr) * 33 + cp + 1]);
-                *reinterpret_cast<__nv_bfloat162*>(p.Cb + (size_t)m * p.ldcb + ncol + cp) = t;
+                *reinterpret_cast<__nv_bfloat162*>(outCb + (size_t)m * p.ldcb + (ncol - cb_shift) + cp) = t;
               }
             }
           }
@@ -285,6 +290,7 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
   p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.m_dev = g.m_dev;
   p.bias = g.bias; p.act = g.act; p.res = g.res; p.ldres = g.ldres; p.C = g.C; p.ldc = g.ldc;
   p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb; p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
+  p.n_split = g.n_split;
   p.dbg = g_tc_dbg;
   const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;

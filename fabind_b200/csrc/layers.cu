@@ -573,7 +573,7 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | ...*/, int ldqk,
                                                               const float* __restrict__ Kt, int ldk,
-                                                              const T* __restrict__ V, const T* __restrict__ VC,
+                                                              const T* __restrict__ V, const T* __restrict__ VC, int ldv,
                                                               const float* __restrict__ k_r, const float* __restrict__ v_r,
                                                               const float* __restrict__ ac_u, const float* __restrict__ ac_b,
                                                               const float* __restrict__ ac_w2, const float* __restrict__ rad,
@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
         const int f = (i * 32 + lane) * 4;
         if (f < H) {
           const float4 kk = ld4(Kt + (size_t)c * ldk + f);
-          const float4 vc = ld4(VC + (size_t)c * H + f);
-          const float4 v0 = ld4(V + (size_t)c * H + f);
+          const float4 vc = ld4(VC + (size_t)c * ldv + f);
+          const float4 v0 = ld4(V + (size_t)c * ldv + f);
           const float4 uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f), vr = ld4(v_r + f);
           dot[u] += q[i].x * kk.x + q[i].y * kk.y + q[i].z * kk.z + q[i].w * kk.w;
           const float t0 = vc.x + fmaf(rn[u], uu.x, bb.x), t1 = vc.y + fmaf(rn[u], uu.y, bb.y);
@@ -709,14 +709,14 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
   }
 }
 
-int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, const float* k_r,
+int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, int ldv, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, bool bf16_mode, cudaStream_t st) {
   const int grid = g.N;
   const int smem = (4 * H + 32) * 4;
 #define FB_IA(T, VEC)                                                                                      \
-  fb_launch(inter_attention_kernel<T, VEC>, dim3(grid), dim3(128), smem, st, g, H, QK, ldqk, Kt, ldk, (const T*)V, (const T*)VC, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
+  fb_launch(inter_attention_kernel<T, VEC>, dim3(grid), dim3(128), smem, st, g, H, QK, ldqk, Kt, ldk, (const T*)V, (const T*)VC, ldv, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
                                                           norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   if (bf16_mode) {

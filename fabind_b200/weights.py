@@ -76,14 +76,15 @@ def _att(sd, p, H):
         "pt1_w": torch.cat([W1p, W1p @ sd[ca + "inter_layer.linear_out.weight"].double(), torch.zeros(2 * H, 32, dtype=torch.float64)], 1),
         "pt1_b": sd[ca + "pair_transition.linear_1.bias"].double() + W1p @ sd[ca + "inter_layer.linear_out.bias"].double(),
         "pt2v": W2.t() @ wb, "pt_c": (wb @ b2 + bb).reshape(1),
-        # q | k | inter_layer.linear_p (32) | inter_layer.linear_c (32) | zero pad: one stacked node GEMM
+        # ONE stacked node GEMM:  q | k | inter_layer.linear_p (32) | inter_layer.linear_c (32) | zero pad  ||  v | vc
+        # with vc = coord_mlp.0.weight @ (v rows): the Linear that follows v is folded (its bias is added per edge)
         "qk_w": torch.cat([sd[p + "linear_q.weight"].double(), Wkv[0::2, 1:],
                            sd[ca + "inter_layer.linear_p.weight"].double(), sd[ca + "inter_layer.linear_c.weight"].double(),
-                           torch.zeros(QKX - 64, H, dtype=torch.float64)], 0),
+                           torch.zeros(QKX - 64, H, dtype=torch.float64), Wkv[1::2, 1:], ac1 @ Wkv[1::2, 1:]], 0),
         "qk_b": torch.cat([sd[p + "linear_q.bias"].double(), bkv[0::2], sd[ca + "inter_layer.linear_p.bias"].double(),
-                           sd[ca + "inter_layer.linear_c.bias"].double(), z(QKX - 64)]), "k_r": Wkv[0::2, 0],
-        "v_w": Wkv[1::2, 1:], "v_b": bkv[1::2], "v_r": v_r,
-        "ac1_w": ac1, "ac1_b": sd[p + "coord_mlp.0.bias"], "ac2_w": sd[p + "coord_mlp.2.weight"][0],
+                           sd[ca + "inter_layer.linear_c.bias"].double(), z(QKX - 64), bkv[1::2], ac1 @ bkv[1::2]]),
+        "k_r": Wkv[0::2, 0], "v_r": v_r,
+        "ac1_b": sd[p + "coord_mlp.0.bias"], "ac2_w": sd[p + "coord_mlp.2.weight"][0],
         "ac_u": ac1 @ v_r,
     }
 

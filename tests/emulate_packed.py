@@ -179,8 +179,7 @@ def forward_emulated(sd, cfg, batch):
             pb_dense = torch.zeros(P0.shape[0])
             pb_dense[pair[u]] = pbu
             rn = _radial(int_r, int_c, x, cplx_t, B)
-            V = F.linear(h, W.m(pre + "v_w"), W.m(pre + "v_b"))
-            VC = F.linear(V, W.m(pre + "ac1_w"))
+            V, VC = QK[:, 2 * H + 128:3 * H + 128], QK[:, 3 * H + 128:]      # stacked GEMM: ... || v | vc
             logit = (QK[int_r, :H] * (QK[int_c, H:2 * H] + rn[:, None] * W.m(pre + "k_r"))).sum(1) + pb_dense[pair]
             mx = torch.full((N,), float("-inf")).scatter_reduce(0, int_r, logit, reduce="amax")
             e = (logit - mx[int_r]).exp()
