@@ -102,22 +102,41 @@ def build_model(device, precision):
     return m
 
 
-def pick_threads(step):
-    """The CPU port is timed with the thread count that serves it best on this host (torchrun exports
-    OMP_NUM_THREADS=1; more threads than ~physical cores per socket can be slower): try a few, keep the fastest."""
+def pick_threads():
+    """Thread count for the CPU port: probed in SUBPROCESSES (OMP_NUM_THREADS fixed per probe, one warm-up + one
+    timed forward each, hard time limit) so the parent never re-sizes a live OpenMP pool; the fastest wins.
+    torchrun exports OMP_NUM_THREADS=1, which would otherwise starve the reference arm."""
     n = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, n) if c <= n} | {min(n, 8)})
-    best, best_t = None, None
+    cands = sorted({c for c in (16, 32, n) if c <= n}) or [n]
+    best, best_t = n, None
     for c in cands:
-        torch.set_num_threads(c)
-        step()                      # warm-up at this setting
-        t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best, best_t = c, dt
-    torch.set_num_threads(best)
+        env = dict(os.environ, OMP_NUM_THREADS=str(c), MKL_NUM_THREADS=str(c))
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-probe"], env=env,
+                               capture_output=True, text=True, timeout=45)
+            t = float(r.stdout.strip().splitlines()[-1])
+        except Exception:
+            continue
+        if best_t is None or t < best_t:
+            best, best_t = c, t
     return best
+
+
+def reference_probe():
+    from oracle import fabind_oracle as orc
+    from fabind_b200.synthetic import make_batch
+    m = build_model("cpu", "fp32")
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cfg = orc.make_cfg(n_layers=LAYERS, n_iter=ITERS)
+    b = make_batch(n_complexes=1, n_c=N_C, n_p=N_P, embed=HIDDEN, seed=0)
+    ts = []
+    with torch.no_grad():
+        for _ in range(2):
+            t0 = time.perf_counter()
+            orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global,
+                              b.compound_edge_index, b.LAS_edge_index, b.X_LAS)
+            ts.append(time.perf_counter() - t0)
+    print(ts[-1])
 
 
 def reference_arm(args, rank, world):
@@ -136,7 +155,8 @@ def reference_arm(args, rank, world):
         with torch.no_grad():
             orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global,
                               b.compound_edge_index, b.LAS_edge_index, b.X_LAS)
-    cores = pick_threads(step)
+    cores = pick_threads()
+    torch.set_num_threads(cores)
     for _ in range(args.warmup):
         step()
     ts = []
@@ -172,6 +192,9 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference-probe":
+        reference_probe()
+        return
     if args.impl == "reference":
         reference_arm(args, rank, world)
         return
@@ -296,15 +319,17 @@ def main():
             with torch.no_grad():
                 orc.model_forward(sd, cfg, sb.X, sb.H, sb.batch_id, sb.segment_id, sb.mask, sb.is_global,
                                   sb.compound_edge_index, sb.LAS_edge_index, sb.X_LAS)
-        cores = pick_threads(cstep)
+        cores = pick_threads()
+        torch.set_num_threads(cores)
+        cstep()
         ts = []
         for i in range(3):
             t0 = time.perf_counter()
             cstep()
             ts.append(time.perf_counter() - t0)
         cpu = {"value": 1.0 / statistics.median(ts), "unit": "complexes/s", "cores": cores, "kind": "port",
-               "sample": f"1 complex (n_c={N_C}, n_p={N_P}), thread count picked from {{8,16,32,all}} by a trial "
-                         "forward, then 3 timed full forwards, median"}
+               "sample": f"1 complex (n_c={N_C}, n_p={N_P}); thread count picked from {{16,32,all}} by subprocess "
+                         "probes, then 1 warm-up + 3 timed full forwards, median"}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "complexes/s", "n_gpus": world, "steps": args.steps,
