@@ -32,6 +32,18 @@ class ModelParams(C.Structure):
     ]
 
 
+class EgnnExtra(C.Structure):
+    _fields_ = [
+        ("steps", C.c_int32), ("E_int", C.c_int32),
+        ("ctx_rowptr", C.c_void_p), ("ctx_row", C.c_void_p), ("ctx_col", C.c_void_p),
+        ("int_rowptr", C.c_void_p), ("int_row", C.c_void_p), ("int_col", C.c_void_p), ("int_pair", C.c_void_p),
+        ("pair0", C.c_void_p), ("att_out", C.c_void_p),
+    ]
+
+
+STEP_LINEAR_IN, STEP_GCL, STEP_ATT, STEP_LAS, STEP_OUT_LAYER, STEP_LINEAR_OUT = 1, 2, 4, 8, 16, 32
+
+
 class GemmParams(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("lda", C.c_int32), ("K1", C.c_int32),
@@ -60,6 +72,7 @@ EXPORTS = {
     "fb_graph_static": (C.c_int32, [C.POINTER(ModelParams), C.c_void_p]),
     "fb_graph_ctx_count_ptr": (C.c_void_p, [C.POINTER(ModelParams)]),
     "fb_model_forward": (C.c_int32, [C.POINTER(ModelParams), C.c_void_p]),
+    "fb_egnn_forward": (C.c_int32, [C.POINTER(ModelParams), C.POINTER(EgnnExtra), C.c_void_p]),
     "fb_edges_ref_count": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                        C.c_float, C.c_void_p, C.c_void_p]),
     "fb_edges_ref_fill": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,

@@ -285,7 +285,7 @@ struct Run {
     }
   }
 
-  void run_att(const AttW& aw, int layer, const float* x_in, float* x_out) {
+  void run_att(const AttW& aw, int layer, const float* x_in, float* x_out, float* att = nullptr) {
     const size_t P = p.P_total;
     float* hp = b.h + (size_t)Nc * H;              // protein-side rows
     void* hTp = at(b.hT, (size_t)Nc * H);
@@ -330,13 +330,54 @@ struct Run {
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
     stage(CAT_ATTENTION, [&] {
       return inter_attention(g, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
-                             b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, nullptr, bf, st);
+                             b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, bf, st);
     });
   }
 
   void tap(int slot, const float* x) {
     if (p.trace_h) cudaMemcpyAsync(p.trace_h + (size_t)slot * N * H, b.h, sizeof(float) * (size_t)N * H, cudaMemcpyDeviceToDevice, st);
     if (p.trace_x) cudaMemcpyAsync(p.trace_x + (size_t)slot * N * 3, x, sizeof(float) * (size_t)N * 3, cudaMemcpyDeviceToDevice, st);
+  }
+
+  // one MCAttEGNN pass (or a subset of its steps) on caller-supplied graphs
+  void forward_egnn(const fb_egnn_extra& e) {
+    const size_t P = p.P_total;
+    stage(CAT_GRAPH_MISC, [&] { return permute_in(g, p.H_in, p.X_in, p.X_las, H, b.Hin32, b.HinT, bf, b.x_state, b.xl, st); });
+    auto cp = [&](void* dst, const void* src, size_t bytes) { if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st); };
+    cp(g.ctx_rowptr, e.ctx_rowptr, sizeof(int) * (N + 1));
+    cp(g.ctx_row, e.ctx_row, sizeof(int) * p.E_ctx); cp(g.ctx_col, e.ctx_col, sizeof(int) * p.E_ctx);
+    cp(g.int_rowptr, e.int_rowptr, sizeof(int) * (N + 1));
+    cp(g.int_row, e.int_row, sizeof(int) * e.E_int); cp(g.int_col, e.int_col, sizeof(int) * e.E_int);
+    cp(g.int_pair, e.int_pair, sizeof(int) * e.E_int);
+    gemm_cat = CAT_GEMM_NODE;
+    if (e.steps & FB_STEP_LINEAR_IN) gemm(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H);
+    else chk(convert_copy(b.Hin32, (size_t)N * H, b.h, bf ? b.hT : nullptr, bf, st));
+    if ((e.steps & FB_STEP_ATT) && p.n_layers > 0) {
+      chk(convert_copy(e.pair0, P * H, nullptr, b.P0, bf, st));
+      const int pbc = pb_cols(p.n_layers);
+      gemm_cat = CAT_GEMM_PAIR0;
+      gemm(b.P0, H, H, w.pb_w, pbc, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, pbc, nullptr, 0);
+      stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, p.n_layers, b.PBraw, pbc, b.PB, st); });
+      gemm_cat = CAT_GEMM_NODE;
+    }
+    const float* xc = b.x_state;
+    float* bufs[2] = {b.xa, b.xb};
+    int k = 0;
+    for (int l = 0; l < p.n_layers; ++l) {
+      if (e.steps & FB_STEP_GCL) { run_gcl(w.gcl[l], xc, bufs[k], true); xc = bufs[k]; k ^= 1; }
+      if (e.steps & FB_STEP_ATT) {
+        run_att(w.att[l], l, xc, bufs[k], e.att_out ? e.att_out + (size_t)l * e.E_int : nullptr); xc = bufs[k]; k ^= 1;
+      }
+      if (e.steps & FB_STEP_LAS) { chk(las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st)); xc = bufs[k]; k ^= 1; }
+    }
+    if (e.steps & FB_STEP_OUT_LAYER) { run_gcl(w.gcl[p.n_layers], xc, bufs[k], true); xc = bufs[k]; k ^= 1; }
+    if (e.steps & FB_STEP_LINEAR_OUT) {
+      gemm(b.hT, H, H, w.out_w, H, w.out_b, FB_ACT_NONE, N, b.Hfin, H, nullptr, 0);
+      chk(permute_out_h(g, b.Hfin, H, p.H_out, st));
+    } else {
+      chk(permute_out_h(g, b.h, H, p.H_out, st));
+    }
+    chk(permute_out_x(g, xc, p.X_out, st));
   }
 
   void forward() {
@@ -394,7 +435,7 @@ using namespace fb;
 
 static bool params_ok(const fb_model_params* p) {
   return p && p->N > 0 && p->B > 0 && p->hidden > 0 && (p->hidden % 4) == 0 && p->hidden <= 512 && p->n_layers >= 0 &&
-         p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot < p->N;
+         p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot <= p->N;
 }
 
 extern "C" {
@@ -491,6 +532,28 @@ int32_t fb_model_forward(const fb_model_params* p, void* stream) {
   r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;
   r.TS = r.bf ? 2 : 4;
   r.forward();
+  if (r.rc != FB_OK) return r.rc;
+  return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_CUDA;
+}
+
+int32_t fb_egnn_forward(const fb_model_params* p, const fb_egnn_extra* e, void* stream) {
+  if (!p || !e || p->N <= 0 || p->B <= 0 || p->hidden <= 0 || (p->hidden % 8) || p->hidden > 512 || p->E_ctx < 0) return FB_ERR_BAD_ARG;
+  if ((e->steps & FB_STEP_ATT) && (!e->pair0 || p->Nc_tot <= 0 || p->Nc_tot >= p->N)) return FB_ERR_BAD_ARG;
+  if (e->E_int > p->cap_int) return FB_ERR_BAD_ARG;
+  const ModelW& w = weights_for(p->hidden, p->n_layers);
+  Run r{*p, w};
+  Arena ag(p->ws_graph, p->ws_graph_bytes, false);
+  plan_graph(*p, ag, r.g);
+  Arena am(p->ws_main, p->ws_main_bytes, false);
+  plan_main(*p, am, r.b);
+  if (!ag.ok || !am.ok) return FB_ERR_WORKSPACE;
+  r.g.ctx_row = r.b.ctx_row; r.g.ctx_col = r.b.ctx_col;
+  r.g.int_row = r.b.int_row; r.g.int_col = r.b.int_col; r.g.int_pair = r.b.int_pair;
+  r.st = (cudaStream_t)stream;
+  r.bf = p->bf16_mode != 0;
+  r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;
+  r.TS = r.bf ? 2 : 4;
+  r.forward_egnn(*e);
   if (r.rc != FB_OK) return r.rc;
   return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_CUDA;
 }

@@ -2,6 +2,7 @@
 // segment reductions, per-complex row attention, interfacial attention and the LAS step.
 // All of them are HBM/L2-bound: one warp per row/edge, float4 accesses along the feature dimension.
 // T is the activation element type of the precision mode (float for fp32 parity mode, bf16 otherwise).
+#include <algorithm>
 #include <type_traits>
 
 #include "layers.h"
@@ -80,6 +81,44 @@ int permute_in(const GraphDev& g, const float* H_in, const float* X_in, const fl
 
 int permute_x(const GraphDev& g, const float* X_in, float* x, cudaStream_t st) {
   fb_launch(gather_x_kernel, dim3((g.N + 255) / 256), dim3(256), 0, st, X_in, g.perm, g.N, x);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+__global__ void scatter_x_kernel(const float* __restrict__ src, const int* __restrict__ perm, int N, float* __restrict__ dst) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    const int d = perm[i];
+    dst[3 * d + 0] = src[3 * i + 0]; dst[3 * d + 1] = src[3 * i + 1]; dst[3 * d + 2] = src[3 * i + 2];
+  }
+}
+
+int permute_out_x(const GraphDev& g, const float* x, float* X_out, cudaStream_t st) {
+  fb_launch(scatter_x_kernel, dim3((g.N + 255) / 256), dim3(256), 0, st, x, g.perm, g.N, X_out);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// dst (fp32 and/or typed) = src, element-wise (feature tables handed in by the caller)
+template <typename T>
+__global__ void convert_kernel(const float* __restrict__ src, size_t n4, float* __restrict__ d32, T* __restrict__ dT) {
+  pdl_entry();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = ld4(src + 4 * i);
+    if (d32) st4(d32 + 4 * i, v);
+    if (dT) st4(dT + 4 * i, v);
+  }
+}
+
+int convert_copy(const float* src, size_t n, float* d32, void* dT, bool bf16_mode, cudaStream_t st) {
+  if (n == 0) return FB_OK;
+  if (n & 3) return FB_ERR_BAD_ARG;
+  const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, 148 * 8);
+  if (bf16_mode) fb_launch(convert_kernel<bf16>, dim3(grid), dim3(256), 0, st, src, n / 4, d32, (bf16*)dT);
+  else fb_launch(convert_kernel<float>, dim3(grid), dim3(256), 0, st, src, n / 4, d32, (float*)dT);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

@@ -6,6 +6,8 @@ namespace fb {
 int permute_in(const GraphDev& g, const float* H_in, const float* X_in, const float* XL_in, int D, float* h32,
                void* hT, bool bf16_mode, float* x, float* xl, cudaStream_t st);
 int permute_x(const GraphDev& g, const float* X_in, float* x, cudaStream_t st);
+int permute_out_x(const GraphDev& g, const float* x, float* X_out, cudaStream_t st);
+int convert_copy(const float* src, size_t n, float* d32, void* dT, bool bf16_mode, cudaStream_t st);
 int permute_out_h(const GraphDev& g, const float* h, int D, float* H_out, cudaStream_t st);
 int masked_update_x(const GraphDev& g, float* x_state, const float* z, float* x_out_caller, cudaStream_t st);
 int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* ecol, const float* x, float* rad,

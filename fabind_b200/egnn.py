@@ -7,8 +7,20 @@ CUDA stack driven by ``att_model.EfficientMCAttModel``.
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .cross_att import CrossAttentionModule
-from .model_utils import InteractionModule, _standalone
+from .model_utils import InteractionModule
+
+
+def _geom(args, coord_clamp, step=0.001):
+    scale = float(getattr(args, "coordinate_scale", 5.0))
+    return dict(intra_cutoff=float(args.intra_cutoff) / scale, inter_cutoff=float(args.inter_cutoff) / scale,
+                coord_clamp=float(coord_clamp), las_clamp=15.0 / scale, las_step=float(step))
+
+
+def _eval_only(mod):
+    if mod.training:
+        raise NotImplementedError("fabind_b200: the training path (dropout + backward kernels) is not built yet; call .eval()")
 
 
 def _check_args(args):
@@ -40,9 +52,18 @@ class MC_E_GCL(nn.Module):
         torch.nn.init.xavier_uniform_(layer.weight, gain=0.001)
         self.coord_mlp = nn.Sequential(nn.Linear(hidden_nf, hidden_nf), act_fn, layer)
         self.coord_change_maximum = coord_change_maximum
+        self.precision = "fp32"
 
-    def forward(self, *a, **k):
-        _standalone("MC_E_GCL")
+    def forward(self, h, edge_index, coord, edge_attr=None, node_attr=None, batch_id=None):
+        """egnn.py:130-144 on a caller-supplied edge list -> (h, coord)."""
+        from .substack import egnn_forward
+        _eval_only(self)
+        if edge_attr is not None or node_attr is not None or batch_id is None:
+            raise NotImplementedError("fabind_b200: MC_E_GCL.forward needs batch_id and takes no edge/node attributes")
+        hidden = h.shape[1]
+        ho, xo, _ = egnn_forward(self, self.args, "gnn.gcl_0.", hidden, 1, _lib.STEP_GCL, h, coord, edge_index, None, None, None,
+                                 batch_id, None, None, _geom(self.args, self.coord_change_maximum), bf16=self.precision == "bf16")
+        return ho, xo
 
 
 class MC_Att_L(nn.Module):
@@ -69,9 +90,19 @@ class MC_Att_L(nn.Module):
         # (egnn.py:180-182 vs 266-284); kept so that state_dict keys match
         self.inter_layer = InteractionModule(input_nf, output_nf, hidden_nf, opm=opm, rm_layernorm=args.rm_layernorm)
         self.attn_bias_proj = nn.Linear(hidden_nf, 1)
+        self.precision = "fp32"
 
-    def forward(self, *a, **k):
-        _standalone("MC_Att_L")
+    def forward(self, h, edge_index, coord, edge_attr=None, segment_id=None, batch_id=None, reduced_tuple=None,
+                pair_embed_batched=None, pair_mask=None, LAS_mask=None, p_p_dist_embed=None, c_c_dist_embed=None):
+        """egnn.py:308-333 on a caller-supplied (symmetric) inter edge list -> (h, coord, attention weights)."""
+        from .substack import egnn_forward
+        _eval_only(self)
+        if edge_attr is not None or segment_id is None or batch_id is None or pair_embed_batched is None:
+            raise NotImplementedError("fabind_b200: MC_Att_L.forward needs segment_id, batch_id and pair_embed_batched")
+        ho, xo, atts = egnn_forward(self, self.args, "gnn.att_0.", self.hidden_nf, 1, _lib.STEP_ATT, h, coord, None, edge_index, None,
+                                    None, batch_id, segment_id, pair_embed_batched, _geom(self.args, self.coord_change_maximum),
+                                    bf16=self.precision == "bf16", want_att=True)
+        return ho, xo, atts[0]
 
 
 class MCAttEGNN(nn.Module):
@@ -102,5 +133,17 @@ class MCAttEGNN(nn.Module):
         self.out_layer = MC_E_GCL(args, hidden_nf, hidden_nf, hidden_nf, n_channel, edges_in_d=in_edge_nf, act_fn=act_fn,
                                   residual=residual, coord_change_maximum=cmax)
 
-    def forward(self, *a, **k):
-        _standalone("MCAttEGNN")
+    def forward(self, h, x, ctx_edges, att_edges, LAS_edge_list, batched_complex_coord_LAS, segment_id=None, batch_id=None,
+                reduced_tuple=None, pair_embed_batched=None, pair_mask=None, LAS_mask=None, p_p_dist_embed=None,
+                c_c_dist_embed=None, mask=None, ctx_edge_attr=None, att_edge_attr=None, return_attention=False):
+        """egnn.py:392-466 on caller-supplied graphs -> (h, x[, atts])."""
+        from .substack import egnn_forward
+        _eval_only(self)
+        if ctx_edge_attr is not None or att_edge_attr is not None or segment_id is None or batch_id is None:
+            raise NotImplementedError("fabind_b200: MCAttEGNN.forward needs segment_id/batch_id and takes no edge attributes")
+        steps = (_lib.STEP_LINEAR_IN | _lib.STEP_GCL | _lib.STEP_ATT | _lib.STEP_LAS | _lib.STEP_OUT_LAYER | _lib.STEP_LINEAR_OUT)
+        ho, xo, atts = egnn_forward(self, self.args, "gnn.", self.hidden_nf, self.n_layers, steps, h, x, ctx_edges, att_edges,
+                                    LAS_edge_list, batched_complex_coord_LAS, batch_id, segment_id, pair_embed_batched,
+                                    _geom(self.args, self.normalize_coord(10), self.geometry_reg_step_size),
+                                    bf16=getattr(self, "precision", "fp32") == "bf16", want_att=return_attention)
+        return (ho, xo, atts) if return_attention else (ho, xo)

@@ -32,7 +32,7 @@ class Layout:
         return self.blob.data_ptr() + 4 * self.offs[name]
 
 
-def build_layout(batch_id, segment_id, is_global, mask, device):
+def build_layout(batch_id, segment_id, is_global, mask, device, allow_single_side=False):
     bid = batch_id.detach().cpu().numpy().astype(np.int64)
     seg = segment_id.detach().cpu().numpy().astype(bool)
     glb = is_global.detach().cpu().numpy().astype(bool)
@@ -54,7 +54,7 @@ def build_layout(batch_id, segment_id, is_global, mask, device):
     inv[perm] = np.arange(N, dtype=np.int32)
     nc1 = np.bincount(bid[c_idx], minlength=B)
     np1 = np.bincount(bid[p_idx], minlength=B)
-    if np.any(nc1 == 0) or np.any(np1 == 0):
+    if (np.any(nc1 == 0) or np.any(np1 == 0)) and not allow_single_side:
         raise ValueError("every complex needs compound-side and protein-side nodes")
     Nc_tot = int(nc1.sum())
     c_off = np.concatenate([[0], np.cumsum(nc1)]).astype(np.int32)
@@ -80,4 +80,4 @@ def build_layout(batch_id, segment_id, is_global, mask, device):
     blob = torch.from_numpy(np.concatenate(chunks)).to(device, non_blocking=True)
     flags_t = torch.from_numpy(flags).to(device, non_blocking=True)
     return Layout(N=N, B=B, Nc_tot=Nc_tot, P_total=int(pair_base[-1]), cap_int=cap_int, fb_atom=int(fb_atom),
-                  fb_res=int(fb_res), max_c=int(nc1.max()), max_p=int(np1.max()), blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p)
+                  fb_res=int(fb_res), max_c=int(nc1.max()), max_p=int(np1.max()) if len(np1) else 0, blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p)

@@ -107,6 +107,28 @@ const int32_t* fb_graph_ctx_count_ptr(const fb_model_params* p);
  * pair_embed0, n_iter x {inter-edge rebuild, MCAttEGNN.forward (egnn.py:392-466)}, X[mask]=Z[mask]. */
 int32_t fb_model_forward(const fb_model_params* p, void* stream);
 
+/* One MCAttEGNN pass -- or one of its sub-layers -- on caller-supplied graphs: the entry behind the stand-alone
+ * `MCAttEGNN.forward` (egnn.py:392-466), `MC_E_GCL.forward` (:130-144) and `MC_Att_L.forward` (:308-333).
+ * Graph arrays are device int32 in the INTERNAL node numbering, sorted by row (CSR); `pair0` is the dense pair
+ * embedding re-packed to [P_total, hidden] rows (prot_local * nc1 + comp_local inside each complex). */
+#define FB_STEP_LINEAR_IN  1
+#define FB_STEP_GCL        2   /* gcl_i of every layer */
+#define FB_STEP_ATT        4   /* att_i of every layer */
+#define FB_STEP_LAS        8   /* LAS step after every att_i */
+#define FB_STEP_OUT_LAYER  16
+#define FB_STEP_LINEAR_OUT 32
+typedef struct fb_egnn_extra {
+  int32_t steps;                 /* FB_STEP_* mask */
+  int32_t E_int;                 /* interface edges supplied */
+  const int32_t* ctx_rowptr;     /* [N+1] */
+  const int32_t* ctx_row; const int32_t* ctx_col;           /* [E_ctx] */
+  const int32_t* int_rowptr;     /* [N+1] */
+  const int32_t* int_row; const int32_t* int_col; const int32_t* int_pair;   /* [E_int] */
+  const float* pair0;            /* [P_total, hidden] fp32 or NULL when FB_STEP_ATT is off */
+  float* att_out;                /* optional [n_layers, E_int]: attention weights in the supplied edge order */
+} fb_egnn_extra;
+int32_t fb_egnn_forward(const fb_model_params* p, const fb_egnn_extra* e, void* stream);
+
 /* ComplexGraph.construct_edges in the caller's node order, reference edge order (API parity).
  * Two phases around one host read of counts[0..4] = {E_pp, E_glb_normal, E_glb_glb, E_inter, fallback}. */
 int32_t fb_edges_ref_count(int32_t N, const int32_t* cplx, const int32_t* off, const uint8_t* flags,
