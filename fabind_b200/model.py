@@ -241,19 +241,53 @@ class IaBNet_mean_and_pocket_prediction_cls_coords_dependent(nn.Module):
         s.update(nP=nP, pocket_off=pocket_off, pocket_xyz=pocket_xyz, seg=seg, glb=glb, co=co, pk=pk, lig=lig)
         return Xo, Ho
 
+    def _dock_stage1(self, s, data):
+        """model.py:302-334 (final_stage == 1): the dataloader's ground-truth pocket crop and pre-built complex graph."""
+        dev, B, H, scale = s["dev"], s["B"], s["H"], self.coordinate_scale
+        cx = data['complex']
+        kept = np.nonzero(data['pocket'].keepNode.cpu().numpy().astype(bool))[0]
+        pb = data['pocket'].batch.cpu().numpy()
+        nP = np.bincount(pb, minlength=B)
+        pocket_off = np.concatenate([[0], np.cumsum(nP)]).astype(np.int32)
+        nA, comp_off = s["nA"], s["comp_off"]
+        kind, idx_f = [], []
+        for b in range(B):
+            kind += [0] + [1] * nA[b] + [2] + [3] * nP[b]
+            idx_f += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(kept[pocket_off[b]:pocket_off[b + 1]])
+        Ncx = len(kind)
+        Hc = _assemble(Ncx, H, kind, idx_f, [self.glb_c, s["comp_out"], self.glb_p, s["prot_out"]], 1.0, dev)
+        rows = np.arange(Ncx)
+        X = _select(cx.node_coords.to(dev, torch.float32), rows, 1.0 / scale).unsqueeze(-2)
+        XL = _select(cx.node_coords_LAS.to(dev, torch.float32), rows, 1.0 / scale).unsqueeze(-2)
+        seg = cx.segment.cpu().numpy().astype(bool)
+        glb = cx.is_global.cpu().numpy().astype(bool)
+        self.complex_model.precision = self.precision
+        Xo, Ho = self.complex_model(
+            X.contiguous(), Hc, batch_id=cx.batch, segment_id=cx.segment, mask=cx.mask, is_global=cx.is_global,
+            compound_edge_index=data['complex', 'c2c', 'complex'].edge_index.to(dev),
+            LAS_edge_index=data['complex', 'LAS', 'complex'].edge_index.to(dev), batched_complex_coord_LAS=XL.contiguous(),
+            LAS_mask=None)
+        s.update(nP=nP, pocket_off=pocket_off, pocket_xyz=data.node_xyz.to(dev, torch.float32).contiguous(), seg=seg, glb=glb,
+                 co=_i32(comp_off, dev), pk=_i32(pocket_off, dev), lig=data['compound'].node_coords.to(dev, torch.float32).contiguous(),
+                 less5=0)
+        return Xo, Ho
+
     # ---------------------------------------------------------------------------------------------------
     def forward(self, data, stage=1, train=False):
+        """eval semantics of model.py:82-369: `final_stage = stage` (:170-171); stage 1 = dataloader pocket, 2 = predicted."""
         if self.training:
             raise NotImplementedError("fabind_b200: the training path is not built yet; call .eval()")
-        if stage != 2:
-            raise NotImplementedError("fabind_b200: eval semantics with stage=2 (predicted pocket) is built; stage 1 "
-                                      "(ground-truth pocket from the dataloader) only re-routes inputs and is not wired yet")
+        if stage not in (1, 2):
+            raise ValueError("stage must be 1 or 2")
         l = _lib.lib()
         with torch.no_grad():
             s = self._pocket_stage(data)
             dev, B, H, scale = s["dev"], s["B"], s["H"], self.coordinate_scale
             centers = self._centers(s, data, mode=0)
-            Xo, Ho = self._dock(s, data, centers)
+            if stage == 2:
+                Xo, Ho = self._dock(s, data, centers)
+            else:
+                Xo, Ho = self._dock_stage1(s, data)
             seg, glb = s["seg"], s["glb"]
             p_rows, c_rows = np.nonzero(seg & ~glb)[0], np.nonzero(~seg & ~glb)[0]
             pocket_out = _layernorm(_select(Ho, p_rows), self.layernorm)
@@ -279,8 +313,11 @@ class IaBNet_mean_and_pocket_prediction_cls_coords_dependent(nn.Module):
                                         qo.data_ptr(), B, Q, float(scale), y_pred.data_ptr(), y_coords.data_ptr(), st),
                        "fb_head_finish")
             dis_map = torch.empty(Q, dtype=torch.float32, device=dev)
-            _lib.check(l.fb_pair_dist(s["pocket_xyz"].data_ptr(), s["lig"].data_ptr(), s["pk"].data_ptr(), s["co"].data_ptr(),
-                                      qo.data_ptr(), B, Q, 10.0, dis_map.data_ptr(), st), "fb_pair_dist")
+            if stage == 1:
+                dis_map = data.dis_map.to(dev)
+            else:
+                _lib.check(l.fb_pair_dist(s["pocket_xyz"].data_ptr(), s["lig"].data_ptr(), s["pk"].data_ptr(), s["co"].data_ptr(),
+                                          qo.data_ptr(), B, Q, 10.0, dis_map.data_ptr(), st), "fb_pair_dist")
             compound_coords_out = _select(Xo.view(-1, 3), c_rows, scale)
             # dense [B, Lmax] views of the per-residue quantities (to_dense_batch, model.py:138-144)
             nL, prot_off = s["nL"], s["prot_off"]

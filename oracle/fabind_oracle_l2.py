@@ -130,8 +130,26 @@ def _dock(sd, args, di):
                              di['seg'], di['mask'], di['glb'], di['c2c'], di['las'], (di['XL'] / scale).unsqueeze(-2))
 
 
+def _stage1_inputs(sd, args, data, B, comp_out, prot_out):
+    """model.py:302-320: dataloader pocket crop (`data['pocket'].keepNode`) and the pre-built `data['complex']` graph."""
+    cb, pkb = data['compound'].batch, data['pocket'].batch
+    pemb = prot_out[data['pocket'].keepNode]
+    feats = []
+    for i in range(B):
+        feats += [sd['glb_c'], comp_out[cb == i], sd['glb_p'], pemb[pkb == i]]
+    cx = data['complex']
+    return dict(H=torch.cat(feats), X=cx.node_coords, XL=cx.node_coords_LAS, seg=cx.segment.to(torch.bool), mask=cx.mask,
+                glb=cx.is_global, batch=cx.batch, c2c=data['complex', 'c2c', 'complex'].edge_index,
+                las=data['complex', 'LAS', 'complex'].edge_index, pocket_xyz=data.node_xyz, pocket_batch=pkb,
+                dis_map=data.dis_map, less5=0)
+
+
 def forward_stage2(sd, args, data):
-    """model.py:82-369 with model.eval(), stage=2, train=False."""
+    return forward_eval(sd, args, data, 2)
+
+
+def forward_eval(sd, args, data, stage):
+    """model.py:82-369 with model.eval(), train=False: final_stage = stage (:170-171)."""
     scale = args.coordinate_scale
     B, comp_out, prot_out, logit = pocket_stage(sd, args, data)
     pbw = data['protein_whole'].batch
@@ -145,7 +163,8 @@ def forward_stage2(sd, args, data):
     one_hot = gumbel_softmax_no_random(torch.log(prob), args.gs_tau, args.gs_hard)
     w = (one_hot[:, :, 1] * pmask).unsqueeze(-1)
     centers = (w * coords_dense).sum(dim=1) / w.sum(dim=1)
-    di = _docking_inputs(sd, args, data, B, comp_out, prot_out, centers)
+    di = (_docking_inputs(sd, args, data, B, comp_out, prot_out, centers) if stage == 2
+          else _stage1_inputs(sd, args, data, B, comp_out, prot_out))
     X, H = _dock(sd, args, di)
     # head (model.py:336-367)
     seg, glb = di['seg'], di['glb']

@@ -102,9 +102,11 @@ def main_l2():
         d = make_docking_batch(**bkw)
         with torch.no_grad():
             fwd = m(d.clone(), stage=2)
+            fwd1 = m(d.clone(), stage=1)
             inf = m.inference(d.clone())
         torch.save({"recipe": dict(emb=emb, pemb=pemb, mean_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed),
                     "shapes": shapes, "forward": [t.clone() if torch.is_tensor(t) else t for t in fwd],
+                    "forward_stage1": [t.clone() if torch.is_tensor(t) else t for t in fwd1],
                     "inference": inf[0].clone(), "torch": torch.__version__}, os.path.join(OUT, name + ".pt"))
         print(name, [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd])
 

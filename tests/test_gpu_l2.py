@@ -49,6 +49,10 @@ def test_l2_golden(path):
     inf = m.inference(data.to("cuda"))
     e = rel_err(inf[0].cpu(), g["inference"])
     assert e < 1e-4, e
+    out1 = m(data.to("cuda"), stage=1)
+    torch.cuda.synchronize()
+    rec1 = _compare(out1, g["forward_stage1"], "l2_golden_forward_stage1")
+    assert max(rec1.values()) < 1e-4, rec1
 
 
 def test_l2_vs_oracle_published_width():

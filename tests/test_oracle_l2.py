@@ -12,8 +12,9 @@ def test_l2_oracle_matches_golden(path):
     g, r, args, data, sd = load_l2_golden(path)
     with torch.no_grad():
         out = l2.forward_stage2(sd, args, data.clone())
+        out1 = l2.forward_eval(sd, args, data.clone(), 1)
         inf = l2.inference(sd, args, data.clone())
-    for i, (a, b) in enumerate(zip(out, g["forward"])):
+    for i, (a, b) in enumerate(list(zip(out, g["forward"])) + list(zip(out1, g["forward_stage1"]))):
         if torch.is_tensor(b):
             assert a.shape == b.shape, i
             if b.dtype in (torch.bool, torch.int32, torch.int64):
