@@ -34,6 +34,17 @@ __device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
 
 bool pdl_enabled();   // forward.cu (FB_PDL=0 disables the launch attribute)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices have it for a kernel
+template <typename K>
+inline bool ensure_smem_optin(K kernel, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev < 64 && (done_mask >> dev) & 1ull) return true;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+  if (dev < 64) done_mask |= 1ull << dev;
+  return true;
+}
+
 template <typename... KArgs, typename... Args>
 inline void fb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};

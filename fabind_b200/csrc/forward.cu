@@ -434,7 +434,7 @@ struct Run {
 using namespace fb;
 
 static bool params_ok(const fb_model_params* p) {
-  return p && p->N > 0 && p->B > 0 && p->hidden > 0 && (p->hidden % 4) == 0 && p->hidden <= 512 && p->n_layers >= 0 &&
+  return p && p->N > 0 && p->B > 0 && p->hidden > 0 && (p->hidden % 8) == 0 && p->hidden <= 512 && p->n_layers >= 0 &&
          p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot <= p->N;
 }
 

@@ -8,15 +8,6 @@
 namespace fb {
 
 bool gemm_tc2_shape_ok(int N);
-bool gemm_ws_supported(const GemmArgs& g);
-int gemm_ws_dot_tiles(int N);
-int gemm_ws_launch(const GemmArgs& g, cudaStream_t st);
-
-// shapes served by the weight-stationary kernel (long M, K <= 512, 2..8 column slices of 128)
-static bool ws_shape_ok(int M, int N, int K) {
-  static int on = [] { const char* e = getenv("FB_WS"); return e ? atoi(e) : 1; }();
-  return on && M >= 16384 && K >= 64 && K <= 512 && (K % 64) == 0 && (N % 128) == 0 && N / 128 >= 2 && N / 128 <= 8;
-}
 int gemm_tc2_dot_tiles(int M, int N);
 int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st);
 
@@ -27,7 +18,6 @@ static int tc_version() {
 
 int gemm_dot_tiles(int M, int N, int K, bool bf16_mode) {
   if (bf16_mode && gemm_tc_shape_ok(N, K)) {
-    if (tc_version() == 2 && ws_shape_ok(M, N, K)) return gemm_ws_dot_tiles(N);
     if (tc_version() == 2 && gemm_tc2_shape_ok(N)) return gemm_tc2_dot_tiles(M, N);
     return gemm_tc_dot_tiles(N);
   }
@@ -36,10 +26,6 @@ int gemm_dot_tiles(int M, int N, int K, bool bf16_mode) {
 
 int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
   if (bf16_mode && gemm_tc_supported(g)) {
-    if (tc_version() == 2 && ws_shape_ok(g.M, g.N, g.K1 + g.K2)) {
-      if (gemm_ws_supported(g)) return gemm_ws_launch(g, st);
-      if (g.dotv) return FB_ERR_UNSUPPORTED;   // the caller sized its row-dot partials for the weight-stationary kernel
-    }
     if (tc_version() == 2 && gemm_tc2_shape_ok(g.N)) return gemm_tc2_launch(g, st);
     if (g.n_split > 0) return gemm_simt_launch(g, bf16_mode, st);   // v1 kernel has no column routing
     return gemm_tc_launch(g, st);

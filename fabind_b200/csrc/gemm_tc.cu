@@ -273,12 +273,8 @@ static int launch_cfg(const GemmArgs& g, cudaStream_t st) {
   using namespace tc;
   if (g.M <= 0) return FB_OK;
   using S = Smem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
-      return FB_ERR_CUDA;
-    attr_set = true;
-  }
+  static unsigned long long optin = 0;
+  if (!ensure_smem_optin(gemm_tc_kernel<BN, STAGES>, S::TOTAL, optin)) return FB_ERR_CUDA;
   CUtensorMap ma, ma2, mw;
   const int K = g.K1 + g.K2;
   if (!make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K1, (uint64_t)g.lda, BM)) return FB_ERR_CUDA;

@@ -267,15 +267,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
 template <int BN, int STAGES>
 static int launch(const GemmArgs& g, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
-  static bool attr_set = false;
+  static unsigned long long optin = 0;
   static int num_sms = 0;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
-      return FB_ERR_CUDA;
+  if (!ensure_smem_optin(gemm_tc2_kernel<BN, STAGES>, S::TOTAL, optin)) return FB_ERR_CUDA;
+  if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
   }
   CUtensorMap ma, ma2, mw;
   const int K = g.K1 + g.K2;
