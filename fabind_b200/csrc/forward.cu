@@ -201,7 +201,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.pb_dense = a.get<float>(P);
   // per-sub-layer temporaries
   b.Pn = a.take(N * 2 * H * TS);
-  b.radc = a.get<float>(E); b.normc = a.get<float>(p.B);
+  b.radc = a.get<float>(E); b.normc = a.get<float>((size_t)p.B * RAD_SLICES);
   b.A1 = a.take(E * H * TS); b.M = a.take(E * H * TS);
   b.dotE = a.get<float>(tilesH * E);
   b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
@@ -209,7 +209,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.O = a.take(N * HD * TS); b.TH = a.take(N * 2 * H * TS);
   b.Zg = a.take(capU * H * TS); b.T64 = a.take(capU * 64 * TS);
   b.dotU = a.get<float>(tiles2H * capU);
-  b.radi = a.get<float>(capI); b.normi = a.get<float>(p.B);
+  b.radi = a.get<float>(capI); b.normi = a.get<float>((size_t)p.B * RAD_SLICES);
   b.QK = a.get<float>(N * (2 * H + QKX));
   b.VT = a.take(N * 2 * H * TS);   // [N, 2H] typed: v | vc
   b.VCT = nullptr;
@@ -295,14 +295,14 @@ struct Run {
     gemm(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0);
     const float* CApv = b.CAp - (size_t)Nc * 2 * HD;  // virtual base indexed by internal node id
     stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 1, p.max_p, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
+      return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
                            b.PB + (size_t)(layer * 2 + 0) * P * 4, b.O, HD, bf, st);
     });
     gemm(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
     gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
     const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
     stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 0, p.max_c, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
+      return row_attention(g, 0, p.max_c, p.max_p, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
                            b.PB + (size_t)(layer * 2 + 1) * P * 4, b.O, HD, bf, st);
     });
     gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);

@@ -140,20 +140,21 @@ int masked_update_x(const GraphDev& g, float* x_state, const float* z, float* x_
 
 // ------------------------------------------------------------------------------------------------
 // coord2radial with per-sample normalisation (egnn.py:767-787): rad[e] = |x_row - x_col|^2 and
-// norm[b] = sqrt(sum over the edges of complex b of rad^2).  One CTA per complex; its edges are the
-// two contiguous CSR ranges that belong to its compound-side and protein-side rows.
+// norm[b] = sqrt(sum over the edges of complex b of rad^2), delivered as RAD_SLICES partial sums per complex
+// (grid = complexes x slices; consumers finish the sum with radial_norm()).  A complex's edges are the two
+// contiguous CSR ranges that belong to its compound-side and protein-side rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) radial_kernel(GraphDev g, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(256) radial_kernel(GraphDev g, const int* __restrict__ rowptr,
                                                      const int* __restrict__ erow, const int* __restrict__ ecol,
                                                      const float* __restrict__ x, float* __restrict__ rad,
-                                                     float* __restrict__ norm) {
+                                                     float* __restrict__ part) {
   pdl_entry();
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, sl = blockIdx.y;
   float acc = 0.f;
-  for (int part = 0; part < 2; ++part) {
-    const int lo = part ? rowptr[g.p_off[b]] : rowptr[g.c_off[b]];
-    const int hi = part ? rowptr[g.p_off[b + 1]] : rowptr[g.c_off[b + 1]];
-    for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+  for (int half = 0; half < 2; ++half) {
+    const int lo = half ? rowptr[g.p_off[b]] : rowptr[g.c_off[b]];
+    const int hi = half ? rowptr[g.p_off[b + 1]] : rowptr[g.c_off[b + 1]];
+    for (int e = lo + sl * blockDim.x + threadIdx.x; e < hi; e += RAD_SLICES * blockDim.x) {
       const int r = erow[e], c = ecol[e];
       const float dx = x[3 * r] - x[3 * c], dy = x[3 * r + 1] - x[3 * c + 1], dz = x[3 * r + 2] - x[3 * c + 2];
       const float d2 = dx * dx + dy * dy + dz * dz;
@@ -161,20 +162,20 @@ __global__ void __launch_bounds__(512) radial_kernel(GraphDev g, const int* __re
       acc = fmaf(d2, d2, acc);
     }
   }
-  __shared__ float red[16];
+  __shared__ float red[8];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
     float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) norm[b] = sqrtf(v);
+    if (threadIdx.x == 0) part[b * RAD_SLICES + sl] = v;   // fixed slice assignment: deterministic
   }
 }
 
 int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* ecol, const float* x, float* rad,
-           float* norm, cudaStream_t st) {
-  fb_launch(radial_kernel, dim3(g.B), dim3(512), 0, st, g, rowptr, erow, ecol, x, rad, norm);
+           float* part, cudaStream_t st) {
+  fb_launch(radial_kernel, dim3(g.B, RAD_SLICES), dim3(256), 0, st, g, rowptr, erow, ecol, x, rad, part);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -190,20 +191,22 @@ __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, 
                                     const float* __restrict__ rad, const float* __restrict__ norm,
                                     const float* __restrict__ w_rad, const float* __restrict__ b1, T* __restrict__ A1) {
   pdl_entry();
+  constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: approximate exp / reciprocal
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
   const int e = warp, r = erow[e], c = ecol[e];
-  const float rn = rad[e] / norm[node_cplx[r]];
+  const float rn = rad[e] / radial_norm(norm, node_cplx[r]);
   const T* pr = P + (size_t)r * 2 * H;
   const T* pc = P + (size_t)c * 2 * H + H;
-  for (int f = lane * 4; f < H; f += 128) {
-    const float4 a = ld4(pr + f), b = ld4(pc + f), w = ld4(w_rad + f), bb = ld4(b1 + f);
-    float4 o;
-    o.x = silu(a.x + b.x + fmaf(rn, w.x, bb.x));
-    o.y = silu(a.y + b.y + fmaf(rn, w.y, bb.y));
-    o.z = silu(a.z + b.z + fmaf(rn, w.z, bb.z));
-    o.w = silu(a.w + b.w + fmaf(rn, w.w, bb.w));
-    st4(A1 + (size_t)e * H + f, o);
+  for (int f = lane * 8; f < H; f += 256) {
+    float a[8], b[8], w[8], bb[8], o[8];
+    ld8(pr + f, a); ld8(pc + f, b); ld8(w_rad + f, w); ld8(b1 + f, bb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = a[i] + b[i] + fmaf(rn, w[i], bb[i]);
+      o[i] = FAST ? __fdividef(t, 1.0f + __expf(-t)) : silu(t);
+    }
+    st8(A1 + (size_t)e * H + f, o);
   }
 }
 
@@ -225,32 +228,6 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
 // One CTA (256 threads) per node: thread = (edge group g in 0..3, feature lane t in 0..63); a lane owns 8
 // consecutive features (16-byte loads in bf16 mode), the four edge groups take edges lo+g, lo+g+4, ...
 // with two loads in flight each, and are combined through shared memory.
-__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-    v[2 * i] = f.x; v[2 * i + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
-  uint4 u;
-  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-  u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
-  u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
-  *reinterpret_cast<uint4*>(p) = u;
-}
-
 constexpr int GN_BIG = 48;   // nodes with more edges than this are reduced by the whole CTA
 
 template <typename T>
@@ -421,32 +398,34 @@ int pair_bias_gate(int P_total, int L, const float* raw, int ld_raw, float* PB, 
 // online softmax over the key chunks.  K rows are padded to 33 floats so that "lane = key" reads are
 // bank-conflict free; "lane = channel" reads of V are conflict free by construction.
 // ------------------------------------------------------------------------------------------------
-constexpr int RA_QT = 8, RA_KC = 128;
+constexpr int RA_KC = 128;
 
-template <typename T>
-__global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is_prot, const float* __restrict__ Q, int ldq,
+// NQ queries per warp (4 warps per CTA); KC = key-chunk capacity of the shared-memory staging (32..128)
+template <typename T, int NQ>
+__global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is_prot, int KC, const float* __restrict__ Q, int ldq,
                                                             const float* __restrict__ G, int ldg,
                                                             const float* __restrict__ Kb, int ldk,
                                                             const float* __restrict__ Vb, int ldv,
                                                             const float* __restrict__ PB, T* __restrict__ O, int ldo) {
   pdl_entry();
-  __shared__ float sK[RA_KC][33];
-  __shared__ float sV[RA_KC][32];
+  extern __shared__ float ra_smem[];
+  float* sK = ra_smem;              // [KC][33]
+  float* sV = ra_smem + KC * 33;    // [KC][32]
   const int b = blockIdx.y, head = blockIdx.z;
   const int c_lo = g.c_off[b], nc1 = g.c_off[b + 1] - c_lo, p_lo = g.p_off[b], np1 = g.p_off[b + 1] - p_lo;
   const int n_q = q_is_prot ? np1 : nc1, n_k = q_is_prot ? nc1 : np1;
   const int q_lo = q_is_prot ? p_lo : c_lo, k_lo = q_is_prot ? c_lo : p_lo;
-  const int q0 = blockIdx.x * RA_QT;
+  const int q0 = blockIdx.x * (4 * NQ);
   if (q0 >= n_q) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  // the two queries of this warp: q_loc = q0 + warp*2 + {0,1}
-  float qv[2][32];
-  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, acc[2] = {0.f, 0.f};
-  int qn[2];
+  float qv[NQ][32];
+  float m[NQ], l[NQ], acc[NQ];
+  int qn[NQ];
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int q_loc = q0 + warp * 2 + u;
+  for (int u = 0; u < NQ; ++u) {
+    m[u] = -INFINITY; l[u] = 0.f; acc[u] = 0.f;
+    const int q_loc = q0 + warp * NQ + u;
     qn[u] = q_loc < n_q ? q_lo + q_loc : -1;
     if (qn[u] >= 0) {
       const float* qp = Q + (size_t)qn[u] * ldq + head * 32;
@@ -460,8 +439,8 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
       for (int d = 0; d < 32; ++d) qv[u][d] = 0.f;
     }
   }
-  for (int j0 = 0; j0 < n_k; j0 += RA_KC) {
-    const int cnt = min(RA_KC, n_k - j0);
+  for (int j0 = 0; j0 < n_k; j0 += KC) {
+    const int cnt = min(KC, n_k - j0);
     __syncthreads();
     const int cnt32 = (cnt + 31) & ~31;   // rows [cnt, cnt32) are zero-filled: they are multiplied by p == 0
     for (int i = threadIdx.x; i < cnt32 * 8; i += 128) {
@@ -471,12 +450,13 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
         kv = ld4(Kb + (size_t)(k_lo + j0 + j) * ldk + head * 32 + d4);
         vv = ld4(Vb + (size_t)(k_lo + j0 + j) * ldv + head * 32 + d4);
       }
-      sK[j][d4] = kv.x; sK[j][d4 + 1] = kv.y; sK[j][d4 + 2] = kv.z; sK[j][d4 + 3] = kv.w;
-      *reinterpret_cast<float4*>(&sV[j][d4]) = vv;
+      float* kr = sK + j * 33 + d4;
+      kr[0] = kv.x; kr[1] = kv.y; kr[2] = kv.z; kr[3] = kv.w;
+      *reinterpret_cast<float4*>(sV + j * 32 + d4) = vv;
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NQ; ++u) {
       if (qn[u] < 0) continue;   // warp-uniform
       const int q_loc = qn[u] - q_lo;
       float sc[RA_KC / 32];
@@ -487,8 +467,9 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
         float v = -INFINITY;
         if (j < cnt) {
           float dsum = 0.f;
+          const float* kr = sK + j * 33;
 #pragma unroll
-          for (int d = 0; d < 32; ++d) dsum = fmaf(qv[u][d], sK[j][d], dsum);
+          for (int d = 0; d < 32; ++d) dsum = fmaf(qv[u][d], kr[d], dsum);
           const int jj = j0 + j;
           const int pair = g.pair_base[b] + (q_is_prot ? (q_loc * nc1 + jj) : (jj * nc1 + q_loc));
           v = dsum + PB[(size_t)pair * 4 + head];
@@ -512,7 +493,7 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
 #pragma unroll 8
           for (int jj = 0; jj < 32; ++jj) {
             const float pj = __shfl_sync(0xffffffffu, sc[t], jj);
-            a = fmaf(pj, sV[t * 32 + jj][lane], a);
+            a = fmaf(pj, sV[(t * 32 + jj) * 32 + lane], a);
           }
         }
       }
@@ -521,20 +502,27 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
     }
   }
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
+  for (int u = 0; u < NQ; ++u) {
     if (qn[u] < 0) continue;
     const float gate = sigmoidf(G[(size_t)qn[u] * ldg + head * 32 + lane]);
     O[(size_t)qn[u] * ldo + head * 32 + lane] = from_f<T>(acc[u] / l[u] * gate);
   }
 }
 
-int row_attention(const GraphDev& g, int q_is_prot, int max_q, const float* Q, int ldq, const float* G, int ldg,
+int row_attention(const GraphDev& g, int q_is_prot, int max_q, int max_k, const float* Q, int ldq, const float* G, int ldg,
                   const float* K, int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode,
                   cudaStream_t st) {
   if (max_q <= 0) return FB_OK;
-  dim3 grid((max_q + RA_QT - 1) / RA_QT, g.B, 4);
-  if (bf16_mode) fb_launch(row_attention_kernel<bf16>, dim3(grid), dim3(128), 0, st, g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (bf16*)O, ldo);
-  else fb_launch(row_attention_kernel<float>, dim3(grid), dim3(128), 0, st, g, q_is_prot, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (float*)O, ldo);
+  const int KC = max_k >= RA_KC ? RA_KC : ((max_k + 31) & ~31);           // smem sized to the keys that exist
+  const int smem = KC * (33 + 32) * 4;
+  // few long key lists (compound queries over a pocket): one query per warp so that more CTAs share the work
+  const bool one = max_q <= 64;
+  const int qt = one ? 4 : 8;
+  dim3 grid((max_q + qt - 1) / qt, g.B, 4);
+#define FB_RA(T, NQ) fb_launch(row_attention_kernel<T, NQ>, grid, dim3(128), smem, st, g, q_is_prot, KC, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (T*)O, ldo)
+  if (bf16_mode) { if (one) FB_RA(bf16, 1); else FB_RA(bf16, 2); }
+  else { if (one) FB_RA(float, 1); else FB_RA(float, 2); }
+#undef FB_RA
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -633,7 +621,7 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
     if (threadIdx.x == 0) { x_out[3 * r] = xr0; x_out[3 * r + 1] = xr1; x_out[3 * r + 2] = xr2; }
     return;
   }
-  const float inv_norm = 1.0f / norm[g.node_cplx[r]];
+  const float inv_norm = 1.0f / radial_norm(norm, g.node_cplx[r]);
   float4 q[VEC], acc[VEC];
   float qkr = 0.f;
 #pragma unroll

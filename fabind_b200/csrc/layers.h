@@ -19,7 +19,7 @@ int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, co
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st);
 int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0, bool bf16_mode, cudaStream_t st);
 int pair_bias_gate(int P_total, int L, const float* raw, int ld_raw, float* PB, cudaStream_t st);
-int row_attention(const GraphDev& g, int q_is_prot, int max_q, const float* Q, int ldq, const float* G, int ldg,
+int row_attention(const GraphDev& g, int q_is_prot, int max_q, int max_k, const float* Q, int ldq, const float* G, int ldg,
                   const float* K, int ldk, const float* V, int ldv, const float* PB, void* O, int ldo, bool bf16_mode,
                   cudaStream_t st);
 int pair_gather(const GraphDev& g, int cap_u, int H, const void* P0, const float* pc32, int ld32, void* Zg, void* T64,
