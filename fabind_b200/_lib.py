@@ -79,6 +79,7 @@ EXPORTS = {
                                       C.c_float, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
     "fb_gemm": (C.c_int32, [C.POINTER(GemmParams), C.c_void_p]),
+    "fb_gemm_pair": (C.c_int32, [C.POINTER(GemmParams), C.POINTER(GemmParams), C.c_void_p]),
     "fb_gemm_dot_tiles": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "fb_gemm_set_debug": (C.c_int32, [C.c_void_p]),
     "fb_assemble_rows": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -241,12 +241,11 @@ struct Run {
   template <typename F> void stage(int cat, F f) { prof_begin(cat, st); chk(f()); prof_end(st); }
   int gemm_cat = CAT_GEMM_NODE;
 
-  // C = act(A W^T + b) with the usual optional extras
-  void gemm(const void* A, int lda, int K, int64_t w_off, int Nout, int64_t b_off, int act, int M, float* C, int ldc,
-            void* Cb, int ldcb, const float* res = nullptr, int ldres = 0, const void* A2 = nullptr, int lda2 = 0,
-            int K2 = 0, int64_t dotv_off = -1, float* dot_out = nullptr, int dot_stride = 0, const int* m_dev = nullptr,
-            int n_split = 0) {
-    if (M <= 0) return;
+  // arguments of  C = act(A W^T + b)  with the usual optional extras
+  GemmArgs mk(const void* A, int lda, int K, int64_t w_off, int Nout, int64_t b_off, int act, int M, float* C, int ldc,
+              void* Cb, int ldcb, const float* res = nullptr, int ldres = 0, const void* A2 = nullptr, int lda2 = 0,
+              int K2 = 0, int64_t dotv_off = -1, float* dot_out = nullptr, int dot_stride = 0, const int* m_dev = nullptr,
+              int n_split = 0) {
     GemmArgs a;
     a.A = A; a.lda = lda; a.K1 = K; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
     a.W = W(w_off); a.bias = b_off >= 0 ? F(b_off) : nullptr; a.act = act;
@@ -258,8 +257,20 @@ struct Run {
     a.dotv = dotv_off >= 0 ? F(dotv_off) : nullptr; a.dot_out = dot_out; a.dot_stride = dot_stride;
     a.M = M; a.N = Nout; a.m_dev = m_dev; a.n_split = n_split;
     if (n_split > 0) { a.C = C; a.ldc = ldc; a.Cb = Cb; a.ldcb = ldcb; }   // both outputs are live in either precision
+    return a;
+  }
+  void gemm(const GemmArgs& a) {
+    if (a.M <= 0) return;
     prof_begin(gemm_cat, st);
     chk(gemm_launch(a, bf, st));
+    prof_end(st);
+  }
+  template <typename... Ts> void gemm(const void* A, Ts... ts) { gemm(mk(A, ts...)); }
+  // compound-side + protein-side problems of one stage (disjoint row ranges of the same activation buffer)
+  void gemm_pair(const GemmArgs& c, const GemmArgs& pr) {
+    if (c.M <= 0 || pr.M <= 0) { gemm(c); gemm(pr); return; }
+    prof_begin(gemm_cat, st);
+    chk(gemm_launch_pair(c, pr, bf, st));
     prof_end(st);
   }
 
@@ -291,8 +302,8 @@ struct Run {
     void* hTp = at(b.hT, (size_t)Nc * H);
     gemm_cat = CAT_GEMM_NODE;
     // --- cross attention (cross_att.py:24-54) on the per-complex blocks
-    gemm(b.hT, H, H, aw.ca_c_w, 4 * HD, aw.ca_c_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0);
-    gemm(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0);
+    gemm_pair(mk(b.hT, H, H, aw.ca_c_w, 4 * HD, aw.ca_c_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0),
+              mk(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0));
     const float* CApv = b.CAp - (size_t)Nc * 2 * HD;  // virtual base indexed by internal node id
     stage(CAT_ATTENTION, [&] {
       return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
@@ -307,10 +318,11 @@ struct Run {
     });
     gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
     // transitions (model_utils.py:171-175), residual
-    gemm(hTp, H, H, aw.tp1_w, 2 * H, aw.tp1_b, FB_ACT_RELU, Np, nullptr, 0, b.TH, 2 * H);
-    gemm(b.TH, 2 * H, 2 * H, aw.tp2_w, H, aw.tp2_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
-    gemm(b.hT, H, H, aw.tc1_w, 2 * H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, 2 * H);
-    gemm(b.TH, 2 * H, 2 * H, aw.tc2_w, H, aw.tc2_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
+    void* THp = at(b.TH, (size_t)Nc * 2 * H);
+    gemm_pair(mk(b.hT, H, H, aw.tc1_w, 2 * H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, 2 * H),
+              mk(hTp, H, H, aw.tp1_w, 2 * H, aw.tp1_b, FB_ACT_RELU, Np, nullptr, 0, THp, 2 * H));
+    gemm_pair(mk(b.TH, 2 * H, 2 * H, aw.tc2_w, H, aw.tc2_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H),
+              mk(THp, 2 * H, 2 * H, aw.tp2_w, H, aw.tp2_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H));
     // q | k of the interfacial attention stacked with the 32-channel interaction projections
     // (cross_att.py:22,51: linear_p on protein rows, linear_c on compound rows) in ONE node GEMM
     const int ldqk = 2 * H + QKX;
@@ -385,8 +397,8 @@ struct Run {
     stage(CAT_GRAPH_MISC, [&] { return permute_in(g, p.H_in, p.X_in, p.X_las, H, b.Hin32, b.HinT, bf, b.x_state, b.xl, st); });
     // pair_embed0 = InteractionModule(H_p, H_c)  (att_model.py:198-206, model_utils.py:219-222)
     gemm_cat = CAT_GEMM_NODE;
-    gemm(b.HinT, H, H, w.il_c_w, H, w.il_c_b, FB_ACT_NONE, Nc, b.pc, H, nullptr, 0);
-    gemm(at(b.HinT, (size_t)Nc * H), H, H, w.il_p_w, H, w.il_p_b, FB_ACT_NONE, Np, b.pc + (size_t)Nc * H, H, nullptr, 0);
+    gemm_pair(mk(b.HinT, H, H, w.il_c_w, H, w.il_c_b, FB_ACT_NONE, Nc, b.pc, H, nullptr, 0),
+              mk(at(b.HinT, (size_t)Nc * H), H, H, w.il_p_w, H, w.il_p_b, FB_ACT_NONE, Np, b.pc + (size_t)Nc * H, H, nullptr, 0));
     stage(CAT_EDGE_ELEMWISE, [&] { return pair_outer(g, (int)P, H, b.pc, b.A0, bf, st); });
     gemm_cat = CAT_GEMM_PAIR0;
     gemm(b.A0, H, H, w.il_o_w, H, w.il_o_b, FB_ACT_NONE, (int)P, nullptr, 0, b.P0, H);
@@ -581,15 +593,25 @@ int32_t fb_edges_ref_fill(int32_t N, const int32_t* cplx, const int32_t* off, co
                         (long long*)ctx_out, e_ctx, (long long*)inter_out, counts_host[3], st);
 }
 
-int32_t fb_gemm(const fb_gemm_params* q, void* stream) {
-  if (!q) return FB_ERR_BAD_ARG;
+static GemmArgs gemm_args_from(const fb_gemm_params* q) {
   GemmArgs a;
   a.A = q->A; a.lda = q->lda; a.K1 = q->K1; a.A2 = q->A2; a.lda2 = q->lda2; a.K2 = q->K2; a.W = q->W;
   a.bias = q->bias; a.act = q->act; a.res = q->res; a.ldres = q->ldres; a.C = q->C; a.ldc = q->ldc;
   a.Cb = q->Cb; a.ldcb = q->ldcb; a.dotv = q->dotv; a.dot_out = q->dot_out; a.dot_stride = q->dot_stride;
   a.M = q->M; a.N = q->N; a.m_dev = q->m_dev;
+  return a;
+}
+
+int32_t fb_gemm(const fb_gemm_params* q, void* stream) {
+  if (!q) return FB_ERR_BAD_ARG;
+  const GemmArgs a = gemm_args_from(q);
   if (q->force_simt) return gemm_simt_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
   return gemm_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
+}
+
+int32_t fb_gemm_pair(const fb_gemm_params* q0, const fb_gemm_params* q1, void* stream) {
+  if (!q0 || !q1 || q0->bf16_mode != q1->bf16_mode) return FB_ERR_BAD_ARG;
+  return gemm_launch_pair(gemm_args_from(q0), gemm_args_from(q1), q0->bf16_mode != 0, (cudaStream_t)stream);
 }
 
 int32_t fb_gemm_set_debug(int64_t* dbg) {

@@ -10,6 +10,7 @@ namespace fb {
 bool gemm_tc2_shape_ok(int N);
 int gemm_tc2_dot_tiles(int M, int N);
 int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st);
+int gemm_tc2_launch_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t st);
 
 static int tc_version() {
   static int v = [] { const char* e = getenv("FB_TC_V"); return e ? atoi(e) : 2; }();
@@ -31,6 +32,16 @@ int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
     return gemm_tc_launch(g, st);
   }
   return gemm_simt_launch(g, bf16_mode, st);
+}
+
+int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, bool bf16_mode, cudaStream_t st) {
+  static const bool group = [] { const char* e = getenv("FB_NO_GROUP"); return !(e && atoi(e)); }();
+  if (group && bf16_mode && tc_version() == 2 && gemm_tc_supported(g0) && gemm_tc_supported(g1)) {
+    const int r = gemm_tc2_launch_pair(g0, g1, st);
+    if (r != FB_ERR_UNSUPPORTED) return r;
+  }
+  const int r = gemm_launch(g0, bf16_mode, st);
+  return r != FB_OK ? r : gemm_launch(g1, bf16_mode, st);
 }
 
 }  // namespace fb

@@ -28,6 +28,10 @@ int gemm_dot_tiles(int M, int N, int K, bool bf16_mode);
 // returns FB_OK or an error code; never synchronises
 int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st);
 
+// two independent problems over disjoint row ranges of one activation buffer (g1.A = g0.A + r * lda, same K):
+// one grouped launch when the tcgen05 path can take it, otherwise two launches
+int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, bool bf16_mode, cudaStream_t st);
+
 // implemented per backend
 int gemm_simt_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st);
 int gemm_simt_dot_tiles(int N);

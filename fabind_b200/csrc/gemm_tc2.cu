@@ -29,9 +29,11 @@ using namespace tc;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;   // 320
 constexpr int MAX_N = 2304;                     // bias / dot vectors staged for the whole N
+constexpr int MAX_N1 = 1024;                    // widest second problem of a grouped launch
 
 struct Params {
   int M, N, KB1, KB2;
+  int m_begin;             // first row of this problem in A / res / C / Cb (grouped launches share A)
   const int* m_dev;
   const float* bias; int act;
   const float* res; int ldres;
@@ -48,14 +50,19 @@ struct Smem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;                       // full[S] empty[S] tfull[2] tempty[2] slot
   static constexpr int VEC_OFF = BAR_OFF + (2 * STAGES + 4) * 8 + 16;        // bias[MAX_N] | dotv[MAX_N]
-  static constexpr int XPOSE_OFF = VEC_OFF + 2 * MAX_N * 4;                  // EPI_WARPS x [32][33] floats
+  static constexpr int VEC1_OFF = VEC_OFF + 2 * MAX_N * 4;                   // bias of the second (grouped) problem
+  static constexpr int XPOSE_OFF = VEC1_OFF + MAX_N1 * 4;                    // EPI_WARPS x [32][33] floats
   static constexpr int TOTAL = XPOSE_OFF + EPI_WARPS * 32 * 33 * 4 + 1024;   // + alignment slack
 };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                const __grid_constant__ CUtensorMap map_a2,
-                                                               const __grid_constant__ CUtensorMap map_w, Params p) {
+                                                               const __grid_constant__ CUtensorMap map_w,
+                                                               const __grid_constant__ CUtensorMap map_w2,
+                                                               const __grid_constant__ Params p, const __grid_constant__ Params p2) {
+  // `q` (p2.M > 0) is an optional SECOND problem sharing A and K with `p` (different rows, weights, outputs):
+  // its tiles are appended to p's, so two short GEMMs that do not depend on each other cost one launch.
   using S = Smem<BN, STAGES>;
   pdl_trigger();
   if (threadIdx.x == 0) FB_DBG2(0);
@@ -68,6 +75,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
   float* s_bias = (float*)(smem + S::VEC_OFF);
   float* s_dot = s_bias + MAX_N;
+  float* s_bias1 = (float*)(smem + S::VEC1_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.KB1 + p.KB2;
@@ -76,6 +84,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w) : "memory");
     if (p.KB2) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a2) : "memory");
+    if (p2.M > 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w2) : "memory");
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -91,6 +100,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
     s_bias[t] = p.bias ? p.bias[t] : 0.f;
     s_dot[t] = p.dotv ? p.dotv[t] : 0.f;
   }
+  if (p2.M > 0) for (int t = threadIdx.x; t < p2.N; t += THREADS) s_bias1[t] = p2.bias ? p2.bias[t] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -102,14 +112,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
   int M = p.M;
   if (p.m_dev) M = min(M, *p.m_dev);
   const int n_tiles_n = p.N / BN;
-  const int n_tiles = ((M + BM - 1) / BM) * n_tiles_n;   // a CTA with no tile falls through to the teardown
+  const int tiles0 = ((M + BM - 1) / BM) * n_tiles_n;
+  const int ntn1 = p2.M > 0 ? p2.N / BN : 1;
+  const int n_tiles = tiles0 + (p2.M > 0 ? ((p2.M + BM - 1) / BM) * ntn1 : 0);   // a CTA with no tile falls through
+  // tile -> (problem, first row, first column)
+  auto decode = [&](int tile, int& m0, int& n0) -> bool {
+    if (tile < tiles0) { m0 = p.m_begin + (tile / n_tiles_n) * BM; n0 = (tile % n_tiles_n) * BN; return false; }
+    const int t = tile - tiles0;
+    m0 = p2.m_begin + (t / ntn1) * BM; n0 = (t % ntn1) * BN;
+    return true;
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+        int m0, n0;
+        const bool second = decode(tile, m0, n0);
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -119,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
           mbar_expect_tx(&full[s], S::STAGE_BYTES);
           if (kb < p.KB1) tma_load_2d(&map_a, &full[s], a_dst, kb * BK, m0);
           else tma_load_2d(&map_a2, &full[s], a_dst, (kb - p.KB1) * BK, m0);
-          tma_load_2d(&map_w, &full[s], b_dst, kb * BK, n0);
+          tma_load_2d(second ? &map_w2 : &map_w, &full[s], b_dst, kb * BK, n0);
         }
       }
     }
@@ -159,18 +179,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
     int lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int a = lt & 1;
-      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      int m0, n0;
+      const bool second = decode(tile, m0, n0);
+      const Params& pp = second ? p2 : p;
+      const float* sb = second ? s_bias1 : s_bias;
+      const int m_end = second ? p2.m_begin + p2.M : p.m_begin + M;
       // residual rows do not depend on the MMAs: for the 128-wide tiles (node-level GEMMs) fetch them into
       // registers, in the transposed "lane = column" layout, while the main loop of this tile is running
       constexpr bool PRE = (BN == 128);
       float rpre[PRE ? 2 : 1][PRE ? 32 : 1];
-      if (PRE && p.res) {
+      if (PRE && pp.res) {
 #pragma unroll
         for (int ch = 0; ch < (PRE ? 2 : 1); ++ch) {
 #pragma unroll
           for (int r = 0; r < (PRE ? 32 : 1); ++r) {
             const int m = m0 + q * 32 + r;
-            rpre[ch][r] = m < M ? p.res[(size_t)m * p.ldres + n0 + half * COLS + ch * 32 + lane] : 0.f;
+            rpre[ch][r] = m < m_end ? pp.res[(size_t)m * pp.ldres + n0 + half * COLS + ch * 32 + lane] : 0.f;
           }
         }
       }
@@ -187,26 +211,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
         float o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + s_bias[n0 + c + j];
-          if (p.act == FB_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
-          else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
+          float x = __uint_as_float(v[j]) + sb[n0 + c + j];
+          if (pp.act == FB_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
+          else if (pp.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
-        if (p.dotv) {
+        if (p.dotv && !second) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) dsum = fmaf(s_dot[n0 + c + j], o[j], dsum);
         }
         const int ncol0 = n0 + c;
-        float* const outC = (p.n_split > 0 && ncol0 >= p.n_split) ? nullptr : p.C;
-        bf16* const outCb = (p.n_split > 0 && ncol0 < p.n_split) ? nullptr : p.Cb;
-        const int cb_shift = p.n_split > 0 ? p.n_split : 0;
+        float* const outC = (pp.n_split > 0 && ncol0 >= pp.n_split) ? nullptr : pp.C;
+        bf16* const outCb = (pp.n_split > 0 && ncol0 < pp.n_split) ? nullptr : pp.Cb;
+        const int cb_shift = pp.n_split > 0 ? pp.n_split : 0;
         if (outC || outCb) {
           // transpose through smem: thread = row  ->  lane = column
 #pragma unroll
           for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = o[j];
           __syncwarp();
           const int ncol = n0 + c;
-          if (outC || p.res) {
+          if (outC || pp.res) {
             // C may alias res (in-place residual update of h): loads of a batch of rows are issued before any
             // store of that batch so that they pipeline instead of serialising behind may-alias stores
 #pragma unroll (BN == 128 ? 4 : 1)
@@ -215,15 +239,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int m = m0 + q * 32 + r0 + i;
-                if (PRE) rv[i] = p.res ? rpre[(cc >> 5) & 1][(r0 + i) & 31] : 0.f;
-                else rv[i] = (p.res && m < M) ? p.res[(size_t)m * p.ldres + ncol + lane] : 0.f;
+                if (PRE) rv[i] = pp.res ? rpre[(cc >> 5) & 1][(r0 + i) & 31] : 0.f;
+                else rv[i] = (pp.res && m < m_end) ? pp.res[(size_t)m * pp.ldres + ncol + lane] : 0.f;
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int m = m0 + q * 32 + r0 + i;
-                if (m < M) {
+                if (m < m_end) {
                   const float x = xp[(r0 + i) * 33 + lane] + rv[i];
-                  if (outC) outC[(size_t)m * p.ldc + ncol + lane] = x;
+                  if (outC) outC[(size_t)m * pp.ldc + ncol + lane] = x;
                   if (outCb) xp[(r0 + i) * 33 + lane] = x;     // keep the residual-added value for the bf16 copy
                 }
               }
@@ -235,16 +259,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
 #pragma unroll 4
             for (int r = 0; r < 32; r += 2) {
               const int m = m0 + q * 32 + r + rr;
-              if (m < M) {
+              if (m < m_end) {
                 const __nv_bfloat162 t = __floats2bfloat162_rn(xp[(r + rr) * 33 + cp], xp[(r + rr) * 33 + cp + 1]);
-                *reinterpret_cast<__nv_bfloat162*>(outCb + (size_t)m * p.ldcb + (ncol - cb_shift) + cp) = t;
+                *reinterpret_cast<__nv_bfloat162*>(outCb + (size_t)m * pp.ldcb + (ncol - cb_shift) + cp) = t;
               }
             }
           }
           __syncwarp();
         }
       }
-      if (p.dotv && mrow < M) {
+      if (p.dotv && !second && mrow < m_end) {
         // two warps (column halves) share a row: partial index = 2 * n_tile + half
         p.dot_out[(size_t)((tile % n_tiles_n) * 2 + half) * p.dot_stride + mrow] = dsum;
       }
@@ -264,8 +288,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
   }
 }
 
+static void fill_params(Params& p, const GemmArgs& g, int m_begin) {
+  // outputs are indexed by absolute row (m_begin + local row): rebase the row-0 pointers accordingly
+  auto rebase = [&](const void* ptr, int ld, int esz) -> const void* {
+    return ptr ? (const void*)((uintptr_t)ptr - (uintptr_t)m_begin * (size_t)ld * esz) : nullptr;
+  };
+  p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.m_dev = g.m_dev; p.m_begin = m_begin;
+  p.bias = g.bias; p.act = g.act;
+  p.res = (const float*)rebase(g.res, g.ldres, 4); p.ldres = g.ldres;
+  p.C = (float*)rebase(g.C, g.ldc, 4); p.ldc = g.ldc;
+  p.Cb = (bf16*)rebase(g.Cb, g.ldcb, 2); p.ldcb = g.ldcb;
+  p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
+  p.n_split = g.n_split;
+  p.dbg = g_tc_dbg;
+}
+
+// g1 (optional): second problem on rows [m_begin1, m_begin1 + g1->M) of the same A buffer
 template <int BN, int STAGES>
-static int launch(const GemmArgs& g, cudaStream_t st) {
+static int launch(const GemmArgs& g, const GemmArgs* g1, int m_begin1, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
   static unsigned long long optin = 0;
   static int num_sms = 0;
@@ -275,24 +315,30 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  CUtensorMap ma, ma2, mw;
+  CUtensorMap ma, ma2, mw, mw2;
   const int K = g.K1 + g.K2;
-  if (!tc_make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K1, (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
+  const int rows = g1 ? (m_begin1 + g1->M > g.M ? m_begin1 + g1->M : g.M) : g.M;
+  if (!tc_make_map(&ma, g.A, (uint64_t)rows, (uint64_t)g.K1, (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
   if (g.K2 > 0) {
     if (!tc_make_map(&ma2, g.A2, (uint64_t)g.M, (uint64_t)g.K2, (uint64_t)g.lda2, BM)) return FB_ERR_CUDA;
   } else {
     ma2 = ma;
   }
   if (!tc_make_map(&mw, g.W, (uint64_t)g.N, (uint64_t)K, (uint64_t)K, BN)) return FB_ERR_CUDA;
-  Params p;
-  p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.m_dev = g.m_dev;
-  p.bias = g.bias; p.act = g.act; p.res = g.res; p.ldres = g.ldres; p.C = g.C; p.ldc = g.ldc;
-  p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb; p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride;
-  p.n_split = g.n_split;
-  p.dbg = g_tc_dbg;
-  const int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  Params p, p2;
+  fill_params(p, g, 0);
+  int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  if (g1) {
+    if (!tc_make_map(&mw2, g1->W, (uint64_t)g1->N, (uint64_t)K, (uint64_t)K, BN)) return FB_ERR_CUDA;
+    fill_params(p2, *g1, m_begin1);
+    tiles += ((g1->M + BM - 1) / BM) * (g1->N / BN);
+  } else {
+    mw2 = mw;
+    p2 = p;
+    p2.M = 0;
+  }
   const int grid = tiles < num_sms ? tiles : num_sms;
-  fb_launch(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, p);
+  fb_launch(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, mw2, p, p2);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -308,8 +354,24 @@ int gemm_tc2_dot_tiles(int M, int N) { return 2 * (N / gemm_tc2_bn(M, N)); }
 
 int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0) return FB_OK;
-  if (gemm_tc2_bn(g.M, g.N) == 256) return tc2::launch<256, 3>(g, st);
-  return tc2::launch<128, 5>(g, st);
+  if (gemm_tc2_bn(g.M, g.N) == 256) return tc2::launch<256, 3>(g, nullptr, 0, st);
+  return tc2::launch<128, 5>(g, nullptr, 0, st);
+}
+
+// Two independent GEMMs over disjoint row ranges of ONE activation buffer (same K, different weights and
+// outputs) in one launch.  Returns FB_ERR_UNSUPPORTED when the pair cannot be grouped; the caller then launches
+// the two problems one after the other.
+int gemm_tc2_launch_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t st) {
+  if (g0.M <= 0 || g1.M <= 0) return FB_ERR_UNSUPPORTED;
+  if (g0.K2 || g1.K2 || g0.K1 != g1.K1 || g0.lda != g1.lda || g0.m_dev || g1.m_dev || g1.dotv) return FB_ERR_UNSUPPORTED;
+  if (g0.N > tc2::MAX_N || g1.N > tc2::MAX_N1 || (g0.N % 128) || (g1.N % 128)) return FB_ERR_UNSUPPORTED;
+  if (gemm_tc2_bn(g0.M, g0.N) != 128 || gemm_tc2_bn(g1.M, g1.N) != 128) return FB_ERR_UNSUPPORTED;
+  const ptrdiff_t off = (const char*)g1.A - (const char*)g0.A;
+  const ptrdiff_t row = (ptrdiff_t)g0.lda * 2;
+  if (off < 0 || off % row) return FB_ERR_UNSUPPORTED;
+  const ptrdiff_t m_begin1 = off / row;
+  if (m_begin1 < g0.M) return FB_ERR_UNSUPPORTED;   // ranges must not overlap
+  return tc2::launch<128, 5>(g0, &g1, (int)m_begin1, st);
 }
 
 }  // namespace fb

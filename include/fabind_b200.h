@@ -155,6 +155,10 @@ typedef struct fb_gemm_params {
   int32_t force_simt;   /* 1: never take the tcgen05 path */
 } fb_gemm_params;
 int32_t fb_gemm(const fb_gemm_params* g, void* stream);
+/* two layers over disjoint row ranges of ONE activation buffer (g1->A = g0->A + r*lda rows, r >= g0->M, same K):
+ * one grouped tcgen05 launch when both qualify, otherwise the two launches in order.  This is how the stack runs
+ * the compound-side / protein-side linears of a stage (cross_att.py:24-54, model_utils.py:171-175). */
+int32_t fb_gemm_pair(const fb_gemm_params* g0, const fb_gemm_params* g1, void* stream);
 int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt);
 /* development probe: when non-null, sampled CTAs of the tcgen05 GEMM write 8 globaltimer stamps each */
 int32_t fb_gemm_set_debug(int64_t* dbg);

@@ -129,3 +129,60 @@ def test_gemm_device_row_count():
     ref = A @ W.t()
     assert torch.allclose(Cout[:130], ref[:130], atol=1e-4)
     assert torch.isnan(Cout[130:]).all()   # rows beyond the device-side count are never written
+
+
+def _params(A, W, bias, act, res, Cout, Cb, M, bf16, dotv=None, dot=None):
+    g = _lib.GemmParams()
+    K = A.shape[1]
+    g.A, g.lda, g.K1 = A.data_ptr(), K, K
+    g.A2, g.lda2, g.K2 = None, 0, 0
+    g.W = W.data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.act = act
+    g.res, g.ldres = (res.data_ptr() if res is not None else None), W.shape[0]
+    g.C, g.ldc = (Cout.data_ptr() if Cout is not None else None), W.shape[0]
+    g.Cb, g.ldcb = (Cb.data_ptr() if Cb is not None else None), W.shape[0]
+    g.dotv = dotv.data_ptr() if dotv is not None else None
+    g.dot_out = dot.data_ptr() if dot is not None else None
+    g.dot_stride = M
+    g.M, g.N = M, W.shape[0]
+    g.m_dev = None
+    g.bf16_mode, g.force_simt = int(bf16), 0
+    return g
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("shape", [(232, 2592, 512, 512, 256, 1), (700, 3000, 512, 1024, 1024, 2), (130, 129, 1024, 512, 512, 0),
+                                   (90, 500, 64, 96, 32, 1)])
+def test_gemm_pair_matches_two_launches(shape, bf16):
+    """grouped launch (compound-side rows | protein-side rows of one buffer, different weights) == two layers"""
+    M0, M1, K, N0, N1, act = shape
+    dev = "cuda"
+    torch.manual_seed(M0 + N1)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    A = torch.randn(M0 + M1, K, device=dev).to(dt).contiguous()
+    W0 = (torch.randn(N0, K, device=dev) / K ** 0.5).to(dt).contiguous()
+    W1 = (torch.randn(N1, K, device=dev) / K ** 0.5).to(dt).contiguous()
+    b0, b1 = torch.randn(N0, device=dev), torch.randn(N1, device=dev)
+    # in-place residual on the first problem (C aliases res), typed copy on both
+    res0 = torch.randn(M0, N0, device=dev)
+    C0 = res0.clone()
+    C1 = torch.full((M1, N1), float("nan"), device=dev)
+    Cb0 = torch.zeros(M0, N0, dtype=dt, device=dev)
+    Cb1 = torch.zeros(M1, N1, dtype=dt, device=dev)
+    g0 = _params(A[:M0], W0, b0, act, C0, C0, Cb0, M0, bf16)
+    g1 = _params(A[M0:], W1, b1, act, None, C1, Cb1, M1, bf16)
+    l = _lib.lib()
+    n0 = l.fb_launch_count()
+    _lib.check(l.fb_gemm_pair(C.byref(g0), C.byref(g1), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fb_gemm_pair")
+    torch.cuda.synchronize()
+    launches = l.fb_launch_count() - n0
+    if bf16 and K % 64 == 0 and N0 % 128 == 0 and N1 % 128 == 0:
+        assert launches == 1, "the pair was expected to take the grouped tcgen05 launch"
+    r0, _ = ref_gemm(A[:M0].float(), W0.float(), b0, act, res0, None, None, bf16)
+    r1, _ = ref_gemm(A[M0:].float(), W1.float(), b1, act, None, None, None, bf16)
+    for got, ref in ((C0, r0), (C1, r1)):
+        assert float((got.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+    cb_tol = 1e-2 if bf16 else 2e-5
+    for got, ref in ((Cb0, r0), (Cb1, r1)):
+        assert float((got.double() - ref).abs().max() / ref.abs().max()) < cb_tol
