@@ -55,12 +55,12 @@ struct Smem {
   static constexpr int TOTAL = XPOSE_OFF + EPI_WARPS * 32 * 33 * 4 + 1024;   // + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool GROUPED>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                const __grid_constant__ CUtensorMap map_a2,
                                                                const __grid_constant__ CUtensorMap map_w,
                                                                const __grid_constant__ CUtensorMap map_w2,
-                                                               const __grid_constant__ Params p, const __grid_constant__ Params p2) {
+                                                               const Params p, const Params p2) {
   // `q` (p2.M > 0) is an optional SECOND problem sharing A and K with `p` (different rows, weights, outputs):
   // its tiles are appended to p's, so two short GEMMs that do not depend on each other cost one launch.
   using S = Smem<BN, STAGES>;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w) : "memory");
     if (p.KB2) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a2) : "memory");
-    if (p2.M > 0) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w2) : "memory");
+    if (GROUPED) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w2) : "memory");
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
     s_bias[t] = p.bias ? p.bias[t] : 0.f;
     s_dot[t] = p.dotv ? p.dotv[t] : 0.f;
   }
-  if (p2.M > 0) for (int t = threadIdx.x; t < p2.N; t += THREADS) s_bias1[t] = p2.bias ? p2.bias[t] : 0.f;
+  if (GROUPED) for (int t = threadIdx.x; t < p2.N; t += THREADS) s_bias1[t] = p2.bias ? p2.bias[t] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -113,11 +113,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
   if (p.m_dev) M = min(M, *p.m_dev);
   const int n_tiles_n = p.N / BN;
   const int tiles0 = ((M + BM - 1) / BM) * n_tiles_n;
-  const int ntn1 = p2.M > 0 ? p2.N / BN : 1;
-  const int n_tiles = tiles0 + (p2.M > 0 ? ((p2.M + BM - 1) / BM) * ntn1 : 0);   // a CTA with no tile falls through
+  const int ntn1 = GROUPED ? p2.N / BN : 1;
+  const int n_tiles = tiles0 + (GROUPED ? ((p2.M + BM - 1) / BM) * ntn1 : 0);   // a CTA with no tile falls through
   // tile -> (problem, first row, first column)
   auto decode = [&](int tile, int& m0, int& n0) -> bool {
-    if (tile < tiles0) { m0 = p.m_begin + (tile / n_tiles_n) * BM; n0 = (tile % n_tiles_n) * BN; return false; }
+    if (!GROUPED || tile < tiles0) { m0 = (tile / n_tiles_n) * BM; n0 = (tile % n_tiles_n) * BN; return false; }
     const int t = tile - tiles0;
     m0 = p2.m_begin + (t / ntn1) * BM; n0 = (t % ntn1) * BN;
     return true;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
           mbar_expect_tx(&full[s], S::STAGE_BYTES);
           if (kb < p.KB1) tma_load_2d(&map_a, &full[s], a_dst, kb * BK, m0);
           else tma_load_2d(&map_a2, &full[s], a_dst, (kb - p.KB1) * BK, m0);
-          tma_load_2d(second ? &map_w2 : &map_w, &full[s], b_dst, kb * BK, n0);
+          tma_load_2d((GROUPED && second) ? &map_w2 : &map_w, &full[s], b_dst, kb * BK, n0);
         }
       }
     }
@@ -181,9 +181,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
       const int a = lt & 1;
       int m0, n0;
       const bool second = decode(tile, m0, n0);
-      const Params& pp = second ? p2 : p;
-      const float* sb = second ? s_bias1 : s_bias;
-      const int m_end = second ? p2.m_begin + p2.M : p.m_begin + M;
+      // per-tile copy of the epilogue description: plain kernel-parameter operands when not grouped
+      struct { const float* res; int ldres, act, n_split; float* C; int ldc; bf16* Cb; int ldcb; } pp;
+      if (GROUPED && second) pp = {p2.res, p2.ldres, p2.act, p2.n_split, p2.C, p2.ldc, p2.Cb, p2.ldcb};
+      else pp = {p.res, p.ldres, p.act, p.n_split, p.C, p.ldc, p.Cb, p.ldcb};
+      const float* sb = (GROUPED && second) ? s_bias1 : s_bias;
+      const int m_end = (GROUPED && second) ? p2.m_begin + p2.M : M;
       // residual rows do not depend on the MMAs: for the 128-wide tiles (node-level GEMMs) fetch them into
       // registers, in the transposed "lane = column" layout, while the main loop of this tile is running
       constexpr bool PRE = (BN == 128);
@@ -309,7 +312,9 @@ static int launch(const GemmArgs& g, const GemmArgs* g1, int m_begin1, cudaStrea
   using S = Smem<BN, STAGES>;
   static unsigned long long optin = 0;
   static int num_sms = 0;
-  if (!ensure_smem_optin(gemm_tc2_kernel<BN, STAGES>, S::TOTAL, optin)) return FB_ERR_CUDA;
+  auto kern = g1 ? gemm_tc2_kernel<BN, STAGES, true> : gemm_tc2_kernel<BN, STAGES, false>;
+  static unsigned long long optin_g = 0;
+  if (!ensure_smem_optin(kern, S::TOTAL, g1 ? optin_g : optin)) return FB_ERR_CUDA;
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -338,7 +343,7 @@ static int launch(const GemmArgs& g, const GemmArgs* g1, int m_begin1, cudaStrea
     p2.M = 0;
   }
   const int grid = tiles < num_sms ? tiles : num_sms;
-  fb_launch(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, mw2, p, p2);
+  fb_launch(kern, dim3(grid), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, mw2, p, p2);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
