@@ -25,6 +25,13 @@ bool pdl_enabled() {
   return on;
 }
 
+// diagnostic only (scripts/skip_probe.sh): FB_SKIP_CATS=<bitmask> drops every launch of the masked categories so the
+// in-situ (PDL-overlapped) cost of a category can be read off as a difference of step times; results are garbage
+static int skip_mask() {
+  static int m = [] { const char* e = getenv("FB_SKIP_CATS"); return e ? atoi(e) : 0; }();
+  return m;
+}
+
 struct ProfSpan { cudaEvent_t a, b; int cat; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_spans;       // recorded spans of the current profile window
@@ -238,7 +245,10 @@ struct Run {
   const void* at(const void* base, size_t elem) const { return (const char*)base + elem * TS; }
   void chk(int r) { if (rc == FB_OK && r != FB_OK) rc = r; }
   // category-tagged launch of a non-GEMM stage
-  template <typename F> void stage(int cat, F f) { prof_begin(cat, st); chk(f()); prof_end(st); }
+  template <typename F> void stage(int cat, F f) {
+    if (skip_mask() >> cat & 1) return;
+    prof_begin(cat, st); chk(f()); prof_end(st);
+  }
   int gemm_cat = CAT_GEMM_NODE;
 
   // arguments of  C = act(A W^T + b)  with the usual optional extras
@@ -260,7 +270,7 @@ struct Run {
     return a;
   }
   void gemm(const GemmArgs& a) {
-    if (a.M <= 0) return;
+    if (a.M <= 0 || (skip_mask() >> gemm_cat & 1)) return;
     prof_begin(gemm_cat, st);
     chk(gemm_launch(a, bf, st));
     prof_end(st);
@@ -268,7 +278,7 @@ struct Run {
   template <typename... Ts> void gemm(const void* A, Ts... ts) { gemm(mk(A, ts...)); }
   // compound-side + protein-side problems of one stage (disjoint row ranges of the same activation buffer)
   void gemm_pair(const GemmArgs& c, const GemmArgs& pr) {
-    if (c.M <= 0 || pr.M <= 0) { gemm(c); gemm(pr); return; }
+    if (c.M <= 0 || pr.M <= 0 || (skip_mask() >> gemm_cat & 1)) { gemm(c); gemm(pr); return; }
     prof_begin(gemm_cat, st);
     chk(gemm_launch_pair(c, pr, bf, st));
     prof_end(st);

@@ -240,6 +240,19 @@ bool tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
   return tc::make_map(m, ptr, rows, cols, ld, box_rows);
 }
 
+// output / residual tiles of the v3 epilogue: box = 32 rows x 128 bytes (32 fp32 or 64 bf16 columns), 128B swizzle
+bool tc_make_map_out(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t rows, uint64_t cols, uint64_t ld) {
+  tc::EncodeTiledFn fn = tc::encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * (is_f32 ? 4u : 2u)};
+  const cuuint32_t box[2] = {is_f32 ? 32u : 64u, 32u};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool gemm_tc_shape_ok(int N, int K) { return N >= tc::BN_SEL && (N % tc::BN_SEL) == 0 && K >= 64 && (K % 64) == 0; }
 
 bool gemm_tc_supported(const GemmArgs& g) {
