@@ -76,6 +76,15 @@ __device__ __forceinline__ float warp_max(float v) {
 // SiLU as torch computes it: x / (1 + exp(-x))  (full-precision expf, no fast-math)
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+// bf16-mode SiLU: x * sigmoid(x) with sigmoid(x) = 0.5 + 0.5 tanh(x/2) -- ONE MUFU op (tanh.approx, rel. error ~2^-11,
+// below the bf16 rounding of the result) instead of ex2 + rcp; the SFU pipe (16 ops/clk/SM) is what bounds the
+// SiLU epilogues and the edge pre-activation kernel
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  const float hx = 0.5f * x;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+  return fmaf(hx, t, hx);
+}
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {

@@ -184,7 +184,7 @@ struct Bufs {
   // pair
   void *P0, *A0, *Zg, *T64; float *PBraw, *PB, *pb_dense, *dotU;
   // edge
-  float *radc, *normc, *radi, *normi, *dotE; void *A1, *M;
+  float *radc, *normc, *radi, *normi, *dotE, *lgt, *sde; void *A1, *M;
 };
 
 static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
@@ -216,7 +216,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.O = a.take(N * HD * TS); b.TH = a.take(N * 2 * H * TS);
   b.Zg = a.take(capU * H * TS); b.T64 = a.take(capU * 64 * TS);
   b.dotU = a.get<float>(tiles2H * capU);
-  b.radi = a.get<float>(capI); b.normi = a.get<float>((size_t)p.B * RAD_SLICES);
+  b.radi = a.get<float>(capI); b.lgt = a.get<float>(capI); b.sde = a.get<float>(capI); b.normi = a.get<float>((size_t)p.B * RAD_SLICES);
   b.QK = a.get<float>(N * (2 * H + QKX));
   b.VT = a.take(N * 2 * H * TS);   // [N, 2H] typed: v | vc
   b.VCT = nullptr;
@@ -351,8 +351,8 @@ struct Run {
     // --- interfacial attention (egnn.py:186-252)
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
     stage(CAT_ATTENTION, [&] {
-      return inter_attention(g, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
-                             b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, bf, st);
+      return inter_attention(g, p.cap_int, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
+                             b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, b.lgt, b.sde, bf, st);
     });
   }
 

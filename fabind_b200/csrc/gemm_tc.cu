@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + s_bias[c + j];
           // bf16 mode: fast exp/reciprocal (outputs are rounded to bf16 or feed fp32 sums at ~1e-6 rel)
-          if (p.act == FB_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
+          if (p.act == FB_ACT_SILU) x = silu_fast(x);
           else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc2_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + sb[n0 + c + j];
-          if (pp.act == FB_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
+          if (pp.act == FB_ACT_SILU) x = silu_fast(x);
           else if (pp.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }

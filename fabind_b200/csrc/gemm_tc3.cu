@@ -71,6 +71,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 16-byte piece j (0..7) of row r (0..31) inside a 128B-swizzled box
 __device__ __forceinline__ uint32_t sw_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
@@ -199,7 +200,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int half = e >> 2;                // column half of the tile
     constexpr int COLS = BN / 2;            // columns per warp
     constexpr int NCH = COLS / 32;          // 32-column pieces per warp and tile
-    static_assert(NS == 1 || (NS == 3 && NCH == 2), "staging layout");
+    static_assert(NS == 1 || NS == 2 || (NS == 3 && NCH == 2), "staging layout");
     uint8_t* const slots = smem + S::STAGING_OFF + e * NS * SLOT;
     uint64_t* const rbar = &resbar[e];
     uint32_t rphase = 0;
@@ -254,7 +255,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bv[ch], j);
-          if (pp.act == FB_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
+          if (pp.act == FB_ACT_SILU) x = silu_fast(x);
           else if (pp.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
@@ -266,8 +267,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int ncol0 = n0 + c;
         const bool want_c = pp.has_c && !(pp.n_split > 0 && ncol0 >= pp.n_split);
         const bool want_cb = pp.has_cb && !(pp.n_split > 0 && ncol0 < pp.n_split);
-        uint8_t* const fs = slots + (NS == 3 ? ch : 0) * SLOT;
-        uint8_t* const bs = slots + (NS == 3 ? 2 : 0) * SLOT;
+        // NS == 2 (256-wide tiles, one stored output): two boxes used alternately, so a store only waits for the
+        // one issued two boxes earlier
+        uint8_t* const fs = slots + (NS == 3 ? ch : NS == 2 ? (ch & 1) : 0) * SLOT;
+        uint8_t* const bs = slots + (NS == 3 ? 2 : NS == 2 ? ((ch >> 1) & 1) : 0) * SLOT;
         if (has_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -277,6 +280,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         if (want_c) {
           if (NS == 1) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+          if (NS == 2) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(fs + sw_off(lane, j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -288,6 +292,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         if (want_cb) {
           if (NS == 1 && (ch & 1) == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+          if (NS == 2 && (ch & 1) == 0) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -396,10 +401,11 @@ static int pick_bn(const GemmArgs& g) {
 int gemm_tc2_bn(int M, int N);
 
 // FB_ERR_UNSUPPORTED -> the caller falls back to the v2 kernel
-// v3 wins on the short (node-level) problems, where the prologue/epilogue latency is the cost; on the long edge-level
-// problems its per-warp staging boxes throttle the epilogue and v2 stays ahead (measured: edge GEMMs 3.4 vs 5.2 ms/step)
+// FB_TC3_MAXM (diagnostic): problems with more rows go to the v2 kernel.  With ONE staging box per epilogue warp the
+// 256-wide tiles of v3 lost to v2 on the long edge-level GEMMs (5.2 vs 3.4 ms/step); with two alternating boxes v3
+// is ahead there too (2.6 vs 3.0 ms/step), so the default is "no limit".
 static int tc3_max_m() {
-  static int m = [] { const char* e = getenv("FB_TC3_MAXM"); return e ? atoi(e) : 16383; }();
+  static int m = [] { const char* e = getenv("FB_TC3_MAXM"); return e ? atoi(e) : 1 << 30; }();
   return m;
 }
 
@@ -410,7 +416,7 @@ int gemm_tc3_launch(const GemmArgs& g, cudaStream_t st) {
   if (g.n_split > 0 && (g.n_split % 64)) return FB_ERR_UNSUPPORTED;
   const int bn = tc3::pick_bn(g);
   if (g.dotv && bn != gemm_tc2_bn(g.M, g.N)) return FB_ERR_UNSUPPORTED;  // the partial count is planned from (M, N) alone
-  if (bn == 256) return tc3::launch<256, 4, 1>(g, nullptr, 0, st);
+  if (bn == 256) return tc3::launch<256, 3, 2>(g, nullptr, 0, st);
   return tc3::launch<128, 4, 3>(g, nullptr, 0, st);
 }
 

@@ -185,13 +185,16 @@ int radial(const GraphDev& g, const int* rowptr, const int* erow, const int* eco
 // GCL edge stage 1 (egnn.py:75-81 with the first Linear split per node):
 //   A1[e,:] = SiLU(P[row, 0:H] + P[col, H:2H] + (rad[e]/norm[b]) * w_rad + b1)
 // ------------------------------------------------------------------------------------------------
+// One warp per edge, lane = 8 consecutive features (16-byte gathers in bf16 mode); 32 registers, so all 64 warp slots
+// of an SM stay filled (a grid-stride variant with register-resident w_rad/b1 and two edges in flight needed 136
+// registers and ran 3x slower).  bf16 mode uses the one-MUFU SiLU.
 template <typename T>
 __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, const int* __restrict__ ecol,
                                     const int* __restrict__ node_cplx, const T* __restrict__ P,
                                     const float* __restrict__ rad, const float* __restrict__ norm,
                                     const float* __restrict__ w_rad, const float* __restrict__ b1, T* __restrict__ A1) {
   pdl_entry();
-  constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: approximate exp / reciprocal
+  constexpr bool FAST = !std::is_same<T, float>::value;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
   const int e = warp, r = erow[e], c = ecol[e];
@@ -204,7 +207,7 @@ __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = a[i] + b[i] + fmaf(rn, w[i], bb[i]);
-      o[i] = FAST ? __fdividef(t, 1.0f + __expf(-t)) : silu(t);
+      o[i] = FAST ? silu_fast(t) : silu(t);
     }
     st8(A1 + (size_t)e * H + f, o);
   }
@@ -214,6 +217,7 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
                  const float* rad, const float* norm, const float* w_rad, const float* b1, void* A1, bool bf16_mode,
                  cudaStream_t st) {
   if (E <= 0) return FB_OK;
+  if (H & 7) return FB_ERR_UNSUPPORTED;
   if (bf16_mode) fb_launch(gcl_edge_pre_kernel<bf16>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const bf16*)P, rad, norm, w_rad, b1, (bf16*)A1);
   else fb_launch(gcl_edge_pre_kernel<float>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const float*)P, rad, norm, w_rad, b1, (float*)A1);
   count_launch(1);
@@ -250,19 +254,42 @@ __device__ __forceinline__ void gcl_sum_rows(const T* __restrict__ M, int H, int
   }
 }
 
+// bf16 rows: keep the four in-flight rows as raw 16-byte vectors and unpack one at a time (register budget of the
+// 1024-thread CTA is 32 per thread)
+__device__ __forceinline__ void acc_bf16x8(const uint4& u, float (&acc)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+  }
+}
+__device__ __forceinline__ void gcl_sum_rows(const bf16* __restrict__ M, int H, int f0, int lo, int hi, int step, float (&acc)[8]) {
+  int e = lo;
+  const bf16* p = M + (size_t)e * H + f0;
+  const size_t st = (size_t)step * H;
+  for (; e + 3 * step < hi; e += 4 * step, p += 4 * st) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + st);
+    const uint4 c = *reinterpret_cast<const uint4*>(p + 2 * st), d = *reinterpret_cast<const uint4*>(p + 3 * st);
+    acc_bf16x8(a, acc); acc_bf16x8(b, acc); acc_bf16x8(c, acc); acc_bf16x8(d, acc);
+  }
+  for (; e < hi; e += step, p += st) acc_bf16x8(*reinterpret_cast<const uint4*>(p), acc);
+}
+
 // CTA = 4 nodes x 64 feature lanes (8 features = one 16-byte load per lane and edge row).  The rows of a
 // node are contiguous in M (edges are in CSR order), so the common case is a short streaming reduction with
 // no shared memory; the few high-degree nodes (global nodes) are then reduced by all 256 threads.
 template <typename T>
-__global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* __restrict__ rowptr,
-                                                       const int* __restrict__ ecol, const T* __restrict__ M,
-                                                       const float* __restrict__ dot, int dot_tiles, int dot_stride,
-                                                       const float* __restrict__ x, float cmax, T* __restrict__ agg,
-                                                       float* __restrict__ x_out) {
+__global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const int* __restrict__ rowptr,
+                                                        const int* __restrict__ ecol, const T* __restrict__ M,
+                                                        const float* __restrict__ dot, int dot_tiles, int dot_stride,
+                                                        const float* __restrict__ x, float cmax, T* __restrict__ agg,
+                                                        float* __restrict__ x_out) {
   pdl_entry();
-  extern __shared__ float part[];  // [4][H]
+  extern __shared__ float part[];  // [G][H]
+  const int G = blockDim.x >> 6;   // node groups (64 feature lanes each) per CTA
   const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 4 + grp;
+  const int r = blockIdx.x * G + grp;
   int lo = 0, hi = 0;
   if (r < N) { lo = rowptr[r]; hi = rowptr[r + 1]; }
   // coordinate part: first warp of each group, lanes over edges
@@ -293,26 +320,24 @@ __global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* 
       st8(agg + (size_t)r * H + f0, acc);
     }
   }
-  // cooperative pass for the high-degree nodes of this CTA (block-uniform control flow)
-  for (int k = 0; k < 4; ++k) {
-    const int rk = blockIdx.x * 4 + k;
+  // cooperative pass for the high-degree nodes (global nodes) of this CTA: all G groups stride over the edge
+  // rows of the node, so its ~200 rows cost ~200/G/4 load round trips (block-uniform control flow)
+  for (int k = 0; k < G; ++k) {
+    const int rk = blockIdx.x * G + k;
     if (rk >= N) break;
     const int lk = rowptr[rk], hk = rowptr[rk + 1];
     if (hk - lk <= GN_BIG) continue;
     for (int f0 = t * 8; f0 < H; f0 += 512) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      gcl_sum_rows(M, H, f0, lk + grp, hk, 4, acc);
+      gcl_sum_rows(M, H, f0, lk + grp, hk, G, acc);
       st8(&part[grp * H + f0], acc);
     }
     __syncthreads();
-    if (grp == 0) {
-      for (int f0 = t * 8; f0 < H; f0 += 512) {
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o[i] = (part[f0 + i] + part[H + f0 + i]) + (part[2 * H + f0 + i] + part[3 * H + f0 + i]);
-        st8(agg + (size_t)rk * H + f0, o);
-      }
+    // fixed summation order over the groups: deterministic
+    for (int f = threadIdx.x; f < H; f += blockDim.x) {
+      float o = 0.f;
+      for (int j = 0; j < G; ++j) o += part[j * H + f];
+      agg[(size_t)rk * H + f] = from_f<T>(o);
     }
     __syncthreads();
   }
@@ -321,10 +346,11 @@ __global__ void __launch_bounds__(256) gcl_node_kernel(int N, int H, const int* 
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
   if (H & 7) return FB_ERR_UNSUPPORTED;
-  const int smem = 4 * H * 4;
-  const int grid = (N + 3) / 4;
-  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(grid), dim3(256), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
-  else fb_launch(gcl_node_kernel<float>, dim3(grid), dim3(256), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  const int G = 16;
+  const int smem = G * H * 4;
+  const int grid = (N + G - 1) / G;
+  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
+  else fb_launch(gcl_node_kernel<float>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -398,11 +424,14 @@ int pair_bias_gate(int P_total, int L, const float* raw, int ld_raw, float* PB, 
 // online softmax over the key chunks.  K rows are padded to 33 floats so that "lane = key" reads are
 // bank-conflict free; "lane = channel" reads of V are conflict free by construction.
 // ------------------------------------------------------------------------------------------------
-constexpr int RA_KC = 128;
+constexpr int RA_KC = 256;
 
-// NQ queries per warp (4 warps per CTA); KC = key-chunk capacity of the shared-memory staging (32..128)
+// CTA = (tile of NW*NQ queries, complex, head), NW = blockDim/32 warps with NQ queries each.  The keys/values of that
+// head are staged in shared memory (all of them when n_k <= 256, else 256 at a time with an online softmax across
+// chunks); the scaled queries sit in shared memory too (broadcast reads), so the register footprint stays small and
+// many warps are resident: the kernel is a chain of global -> smem -> compute latencies, not throughput.
 template <typename T, int NQ>
-__global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is_prot, int KC, const float* __restrict__ Q, int ldq,
+__global__ void __launch_bounds__(512) row_attention_kernel(GraphDev g, int q_is_prot, int KC, const float* __restrict__ Q, int ldq,
                                                             const float* __restrict__ G, int ldg,
                                                             const float* __restrict__ Kb, int ldk,
                                                             const float* __restrict__ Vb, int ldv,
@@ -411,15 +440,16 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
   extern __shared__ float ra_smem[];
   float* sK = ra_smem;              // [KC][33]
   float* sV = ra_smem + KC * 33;    // [KC][32]
+  float* sQ = sV + KC * 32;         // [NW*NQ][32]
+  const int NW = blockDim.x >> 5;
   const int b = blockIdx.y, head = blockIdx.z;
   const int c_lo = g.c_off[b], nc1 = g.c_off[b + 1] - c_lo, p_lo = g.p_off[b], np1 = g.p_off[b + 1] - p_lo;
   const int n_q = q_is_prot ? np1 : nc1, n_k = q_is_prot ? nc1 : np1;
   const int q_lo = q_is_prot ? p_lo : c_lo, k_lo = q_is_prot ? c_lo : p_lo;
-  const int q0 = blockIdx.x * (4 * NQ);
+  const int q0 = blockIdx.x * (NW * NQ);
   if (q0 >= n_q) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  float qv[NQ][32];
   float m[NQ], l[NQ], acc[NQ];
   int qn[NQ];
 #pragma unroll
@@ -427,23 +457,13 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
     m[u] = -INFINITY; l[u] = 0.f; acc[u] = 0.f;
     const int q_loc = q0 + warp * NQ + u;
     qn[u] = q_loc < n_q ? q_lo + q_loc : -1;
-    if (qn[u] >= 0) {
-      const float* qp = Q + (size_t)qn[u] * ldq + head * 32;
-#pragma unroll
-      for (int d = 0; d < 32; d += 4) {
-        const float4 v = ld4(qp + d);
-        qv[u][d] = v.x * scale; qv[u][d + 1] = v.y * scale; qv[u][d + 2] = v.z * scale; qv[u][d + 3] = v.w * scale;
-      }
-    } else {
-#pragma unroll
-      for (int d = 0; d < 32; ++d) qv[u][d] = 0.f;
-    }
+    sQ[(warp * NQ + u) * 32 + lane] = qn[u] >= 0 ? Q[(size_t)qn[u] * ldq + head * 32 + lane] * scale : 0.f;
   }
   for (int j0 = 0; j0 < n_k; j0 += KC) {
     const int cnt = min(KC, n_k - j0);
     __syncthreads();
     const int cnt32 = (cnt + 31) & ~31;   // rows [cnt, cnt32) are zero-filled: they are multiplied by p == 0
-    for (int i = threadIdx.x; i < cnt32 * 8; i += 128) {
+    for (int i = threadIdx.x; i < cnt32 * 8; i += blockDim.x) {
       const int j = i >> 3, d4 = (i & 7) * 4;
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (j < cnt) {
@@ -459,20 +479,27 @@ __global__ void __launch_bounds__(128) row_attention_kernel(GraphDev g, int q_is
     for (int u = 0; u < NQ; ++u) {
       if (qn[u] < 0) continue;   // warp-uniform
       const int q_loc = qn[u] - q_lo;
+      const float* qv = sQ + (warp * NQ + u) * 32;
       float sc[RA_KC / 32];
       float cmax = -INFINITY;
 #pragma unroll
       for (int t = 0; t < RA_KC / 32; ++t) {
         const int j = t * 32 + lane;
         float v = -INFINITY;
-        if (j < cnt) {
-          float dsum = 0.f;
-          const float* kr = sK + j * 33;
+        if (t * 32 < cnt) {              // warp-uniform
+          if (j < cnt) {
+            float dsum = 0.f;
+            const float* kr = sK + j * 33;
 #pragma unroll
-          for (int d = 0; d < 32; ++d) dsum = fmaf(qv[u][d], kr[d], dsum);
-          const int jj = j0 + j;
-          const int pair = g.pair_base[b] + (q_is_prot ? (q_loc * nc1 + jj) : (jj * nc1 + q_loc));
-          v = dsum + PB[(size_t)pair * 4 + head];
+            for (int d = 0; d < 32; d += 4) {
+              const float4 q4 = *reinterpret_cast<const float4*>(qv + d);
+              dsum = fmaf(q4.x, kr[d], dsum); dsum = fmaf(q4.y, kr[d + 1], dsum);
+              dsum = fmaf(q4.z, kr[d + 2], dsum); dsum = fmaf(q4.w, kr[d + 3], dsum);
+            }
+            const int jj = j0 + j;
+            const int pair = g.pair_base[b] + (q_is_prot ? (q_loc * nc1 + jj) : (jj * nc1 + q_loc));
+            v = dsum + PB[(size_t)pair * 4 + head];
+          }
         }
         sc[t] = v;
         cmax = fmaxf(cmax, v);
@@ -514,14 +541,20 @@ int row_attention(const GraphDev& g, int q_is_prot, int max_q, int max_k, const 
                   cudaStream_t st) {
   if (max_q <= 0) return FB_OK;
   const int KC = max_k >= RA_KC ? RA_KC : ((max_k + 31) & ~31);           // smem sized to the keys that exist
-  const int smem = KC * (33 + 32) * 4;
-  // few long key lists (compound queries over a pocket): one query per warp so that more CTAs share the work
+  // few queries over long key lists (compound queries over a pocket): one query per warp, 8 warps, so that more CTAs
+  // share the work; many queries over short key lists: 16 warps x 2 queries
   const bool one = max_q <= 64;
-  const int qt = one ? 4 : 8;
-  dim3 grid((max_q + qt - 1) / qt, g.B, 4);
-#define FB_RA(T, NQ) fb_launch(row_attention_kernel<T, NQ>, grid, dim3(128), smem, st, g, q_is_prot, KC, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (T*)O, ldo)
-  if (bf16_mode) { if (one) FB_RA(bf16, 1); else FB_RA(bf16, 2); }
-  else { if (one) FB_RA(float, 1); else FB_RA(float, 2); }
+  const int nw = one ? 8 : 16, nq = one ? 1 : 2;
+  const int smem = (KC * (33 + 32) + nw * nq * 32) * 4;
+  dim3 grid((max_q + nw * nq - 1) / (nw * nq), g.B, 4);
+  static unsigned long long done[4] = {0, 0, 0, 0};
+#define FB_RA(T, NQ, slot)                                                                                              \
+  do {                                                                                                                  \
+    if (!ensure_smem_optin(row_attention_kernel<T, NQ>, (RA_KC * 65 + 16 * 2 * 32) * 4, done[slot])) return FB_ERR_CUDA; \
+    fb_launch(row_attention_kernel<T, NQ>, grid, dim3(nw * 32), smem, st, g, q_is_prot, KC, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (T*)O, ldo); \
+  } while (0)
+  if (bf16_mode) { if (one) FB_RA(bf16, 1, 0); else FB_RA(bf16, 2, 1); }
+  else { if (one) FB_RA(float, 1, 2); else FB_RA(float, 2, 3); }
 #undef FB_RA
   count_launch(1);
   FB_CHECK_LAUNCH();
@@ -595,25 +628,65 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 //   x[r]   += clamp(sum_e alpha_e * s_e * (x[r]-x[c]), +-cmax),  s_e = w2 . SiLU(VC[c] + rn*u + b1)
 // One warp per row, single pass with an online softmax.
 // ------------------------------------------------------------------------------------------------
-// One CTA (4 warps) per row: warp w takes the edges lo+w, lo+w+4, ... with its own online softmax; the
-// four partial states (max, sum, feature accumulator, coordinate accumulator) are merged through smem.
+// Two phases, both with short dependency chains and many resident warps (the previous single kernel -- CTA per row,
+// whole 4 KB gathers, online softmax -- ran 6 waves of latency-bound CTAs at 25 % occupancy):
+//   phase 1, one warp per EDGE:   logit_e and s_e  (K / VC gathers, two warp reductions)
+//   phase 2, one CTA per ROW:     softmax over the row's logits, sum_e alpha_e V[c] (thread = 4 features), coordinates
 template <typename T, int VEC>
-__global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H, const float* __restrict__ QK /*[N,ldqk]: q | ...*/, int ldqk,
-                                                              const float* __restrict__ Kt, int ldk,
-                                                              const T* __restrict__ V, const T* __restrict__ VC, int ldv,
-                                                              const float* __restrict__ k_r, const float* __restrict__ v_r,
-                                                              const float* __restrict__ ac_u, const float* __restrict__ ac_b,
-                                                              const float* __restrict__ ac_w2, const float* __restrict__ rad,
-                                                              const float* __restrict__ norm, const float* __restrict__ pb_dense,
-                                                              const float* __restrict__ x, float cmax, float* __restrict__ h,
-                                                              T* __restrict__ hT, float* __restrict__ x_out,
-                                                              float* __restrict__ att_logit) {
+__global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, const float* __restrict__ QK, int ldqk,
+                                                          const float* __restrict__ Kt, int ldk, const T* __restrict__ VC, int ldv,
+                                                          const float* __restrict__ k_r, const float* __restrict__ ac_u,
+                                                          const float* __restrict__ ac_b, const float* __restrict__ ac_w2,
+                                                          const float* __restrict__ rad, const float* __restrict__ norm,
+                                                          const float* __restrict__ pb_dense, float* __restrict__ logit,
+                                                          float* __restrict__ sdot_out) {
+  constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: one-MUFU SiLU
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  // the four weight vectors are staged in shared memory (they are not produced by the previous kernel: staged before
+  // the PDL wait); registers are left for the gathers so that 32 warps stay resident per SM
+  extern __shared__ float il_w[];   // k_r | ac_u | ac_b | ac_w2, H floats each
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    il_w[i] = k_r[i]; il_w[H + i] = ac_u[i]; il_w[2 * H + i] = ac_b[i]; il_w[3 * H + i] = ac_w2[i];
+  }
   pdl_entry();
-  extern __shared__ float sm[];     // [4][H] accumulators | [4] m | [4] l | [4][3] x
-  float* s_acc = sm;
-  float* s_m = sm + 4 * H;
-  float* s_l = s_m + 4;
-  float* s_x = s_l + 4;
+  __syncthreads();
+  const int E = g.int_rowptr[g.N];
+  for (int e = warp; e < E; e += n_warps) {
+    const int r = g.int_row[e], c = g.int_col[e];
+    const float rn = rad[e] / radial_norm(norm, g.node_cplx[r]);
+    const float pb = pb_dense[g.int_pair[e]];
+    float dot = 0.f, sd = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int f = (i * 32 + lane) * 4;
+      if (f < H) {
+        const float4 q = ld4(QK + (size_t)r * ldqk + f);
+        const float4 kk = ld4(Kt + (size_t)c * ldk + f);
+        const float4 vc = ld4(VC + (size_t)c * ldv + f);
+        const float4 kr = *reinterpret_cast<const float4*>(il_w + f), uu = *reinterpret_cast<const float4*>(il_w + H + f);
+        const float4 bb = *reinterpret_cast<const float4*>(il_w + 2 * H + f), w2 = *reinterpret_cast<const float4*>(il_w + 3 * H + f);
+        dot += q.x * fmaf(rn, kr.x, kk.x) + q.y * fmaf(rn, kr.y, kk.y) + q.z * fmaf(rn, kr.z, kk.z) + q.w * fmaf(rn, kr.w, kk.w);
+        const float t0 = vc.x + fmaf(rn, uu.x, bb.x), t1 = vc.y + fmaf(rn, uu.y, bb.y);
+        const float t2 = vc.z + fmaf(rn, uu.z, bb.z), t3 = vc.w + fmaf(rn, uu.w, bb.w);
+        if (FAST) sd += w2.x * silu_fast(t0) + w2.y * silu_fast(t1) + w2.z * silu_fast(t2) + w2.w * silu_fast(t3);
+        else sd += w2.x * silu(t0) + w2.y * silu(t1) + w2.z * silu(t2) + w2.w * silu(t3);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); sd += __shfl_xor_sync(0xffffffffu, sd, o); }
+    if (lane == 0) { logit[e] = dot + pb; sdot_out[e] = sd; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) inter_aggregate_kernel(GraphDev g, int H, const T* __restrict__ V, int ldv,
+                                                              const float* __restrict__ v_r, const float* __restrict__ rad,
+                                                              const float* __restrict__ norm, const float* __restrict__ logit,
+                                                              const float* __restrict__ sdot, const float* __restrict__ x, float cmax,
+                                                              float* __restrict__ h, T* __restrict__ hT, float* __restrict__ x_out,
+                                                              float* __restrict__ att) {
+  pdl_entry();
   const int r = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lo = g.int_rowptr[r], hi = g.int_rowptr[r + 1];
   const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
@@ -621,138 +694,88 @@ __global__ void __launch_bounds__(128) inter_attention_kernel(GraphDev g, int H,
     if (threadIdx.x == 0) { x_out[3 * r] = xr0; x_out[3 * r + 1] = xr1; x_out[3 * r + 2] = xr2; }
     return;
   }
+  // softmax statistics of the row (every warp computes them redundantly: no block barrier on this path)
+  float mx = -INFINITY;
+  for (int e = lo + lane; e < hi; e += 32) mx = fmaxf(mx, logit[e]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int e = lo + lane; e < hi; e += 32) sum += expf(logit[e] - mx);
+  sum = warp_sum(sum);
+  const float il = 1.0f / sum;
   const float inv_norm = 1.0f / radial_norm(norm, g.node_cplx[r]);
-  float4 q[VEC], acc[VEC];
-  float qkr = 0.f;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int f = (i * 32 + lane) * 4;
-    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (f < H) {
-      q[i] = ld4(QK + (size_t)r * ldqk + f);
-      const float4 kr = ld4(k_r + f);
-      qkr += q[i].x * kr.x + q[i].y * kr.y + q[i].z * kr.z + q[i].w * kr.w;
-    } else q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  qkr = warp_sum(qkr);
-  float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f, az = 0.f;
-  constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: approximate exp / reciprocal
-  // two edges per trip: their gathers and warp reductions are independent and overlap
-  for (int e = lo + w; e < hi; e += 8) {
-    const bool two = e + 4 < hi;
-    const int ee[2] = {e, two ? e + 4 : e};
-    int cc[2];
-    float rn[2], dot[2] = {0.f, 0.f}, sdot[2] = {0.f, 0.f};
-    float4 vv[2][VEC];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      cc[u] = g.int_col[ee[u]];
-      rn[u] = rad[ee[u]] * inv_norm;
+  if (w == 0) {
+    // coordinates (egnn.py:240-252) and the normalised attention weights, lanes over edges
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int e = lo + lane; e < hi; e += 32) {
+      const float p = expf(logit[e] - mx) * il;
+      if (att) att[e] = p;
+      const int c = g.int_col[e];
+      const float ps = p * sdot[e];
+      ax = fmaf(ps, xr0 - x[3 * c], ax); ay = fmaf(ps, xr1 - x[3 * c + 1], ay); az = fmaf(ps, xr2 - x[3 * c + 2], az);
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = cc[u];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int f = (i * 32 + lane) * 4;
-        if (f < H) {
-          const float4 kk = ld4(Kt + (size_t)c * ldk + f);
-          const float4 vc = ld4(VC + (size_t)c * ldv + f);
-          const float4 v0 = ld4(V + (size_t)c * ldv + f);
-          const float4 uu = ld4(ac_u + f), bb = ld4(ac_b + f), w2 = ld4(ac_w2 + f), vr = ld4(v_r + f);
-          dot[u] += q[i].x * kk.x + q[i].y * kk.y + q[i].z * kk.z + q[i].w * kk.w;
-          const float t0 = vc.x + fmaf(rn[u], uu.x, bb.x), t1 = vc.y + fmaf(rn[u], uu.y, bb.y);
-          const float t2 = vc.z + fmaf(rn[u], uu.z, bb.z), t3 = vc.w + fmaf(rn[u], uu.w, bb.w);
-          if (FAST) {
-            sdot[u] += w2.x * __fdividef(t0, 1.0f + __expf(-t0)) + w2.y * __fdividef(t1, 1.0f + __expf(-t1)) +
-                       w2.z * __fdividef(t2, 1.0f + __expf(-t2)) + w2.w * __fdividef(t3, 1.0f + __expf(-t3));
-          } else {
-            sdot[u] += w2.x * silu(t0) + w2.y * silu(t1) + w2.z * silu(t2) + w2.w * silu(t3);
-          }
-          vv[u][i] = make_float4(fmaf(rn[u], vr.x, v0.x), fmaf(rn[u], vr.y, v0.y), fmaf(rn[u], vr.z, v0.z), fmaf(rn[u], vr.w, v0.w));
-        } else vv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o); dot[1] += __shfl_xor_sync(0xffffffffu, dot[1], o);
-      sdot[0] += __shfl_xor_sync(0xffffffffu, sdot[0], o); sdot[1] += __shfl_xor_sync(0xffffffffu, sdot[1], o);
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
-      const int c = cc[u];
-      const float logit = dot[u] + rn[u] * qkr + pb_dense[g.int_pair[ee[u]]];
-      if (att_logit && lane == 0) att_logit[ee[u]] = logit;
-      const float m_new = fmaxf(m, logit);
-      const float corr = expf(m - m_new), p = expf(logit - m_new);
-      l = l * corr + p;
-      const float ps = p * sdot[u];
-      ax = ax * corr + ps * (xr0 - x[3 * c]);
-      ay = ay * corr + ps * (xr1 - x[3 * c + 1]);
-      az = az * corr + ps * (xr2 - x[3 * c + 2]);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        acc[i].x = fmaf(p, vv[u][i].x, acc[i].x * corr); acc[i].y = fmaf(p, vv[u][i].y, acc[i].y * corr);
-        acc[i].z = fmaf(p, vv[u][i].z, acc[i].z * corr); acc[i].w = fmaf(p, vv[u][i].w, acc[i].w * corr);
-      }
-      m = m_new;
+    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+    if (lane == 0) {
+      x_out[3 * r] = xr0 + fminf(fmaxf(ax, -cmax), cmax);
+      x_out[3 * r + 1] = xr1 + fminf(fmaxf(ay, -cmax), cmax);
+      x_out[3 * r + 2] = xr2 + fminf(fmaxf(az, -cmax), cmax);
     }
   }
+  // features: thread = 4 consecutive features; sum_e alpha_e (V[c] + rn_e v_r) = sum_e alpha_e V[c] + (sum_e alpha_e rn_e) v_r
+  const int f = threadIdx.x * 4;
+  if (f >= H) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float arn = 0.f;
+  int e = lo;
+  for (; e + 3 < hi; e += 4) {   // four gathers in flight
+    float p[4]; float4 v[4];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int f = (i * 32 + lane) * 4;
-    if (f < H) *reinterpret_cast<float4*>(&s_acc[w * H + f]) = acc[i];
-  }
-  if (lane == 0) { s_m[w] = m; s_l[w] = l; s_x[w * 3] = ax; s_x[w * 3 + 1] = ay; s_x[w * 3 + 2] = az; }
-  __syncthreads();
-  const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-  float sc[4], L = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { sc[k] = expf(s_m[k] - M); L += s_l[k] * sc[k]; }   // empty warps: exp(-inf) = 0
-  const float il = 1.0f / L;
-  for (int f = threadIdx.x * 4; f < H; f += 512) {
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&s_acc[k * H + f]);
-      o.x = fmaf(a.x, sc[k], o.x); o.y = fmaf(a.y, sc[k], o.y); o.z = fmaf(a.z, sc[k], o.z); o.w = fmaf(a.w, sc[k], o.w);
+    for (int u = 0; u < 4; ++u) {
+      const int c = g.int_col[e + u];
+      v[u] = ld4(V + (size_t)c * ldv + f);
+      p[u] = expf(logit[e + u] - mx) * il;
+      arn = fmaf(p[u], rad[e + u], arn);
     }
-    float4 hv = ld4(h + (size_t)r * H + f);
-    hv.x += o.x * il; hv.y += o.y * il; hv.z += o.z * il; hv.w += o.w * il;
-    st4(h + (size_t)r * H + f, hv);
-    if (hT) st4(hT + (size_t)r * H + f, hv);
-  }
-  if (threadIdx.x == 0) {
-    float dx = 0.f, dy = 0.f, dz = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { dx = fmaf(s_x[k * 3], sc[k], dx); dy = fmaf(s_x[k * 3 + 1], sc[k], dy); dz = fmaf(s_x[k * 3 + 2], sc[k], dz); }
-    x_out[3 * r] = xr0 + fminf(fmaxf(dx * il, -cmax), cmax);
-    x_out[3 * r + 1] = xr1 + fminf(fmaxf(dy * il, -cmax), cmax);
-    x_out[3 * r + 2] = xr2 + fminf(fmaxf(dz * il, -cmax), cmax);
+    for (int u = 0; u < 4; ++u) {
+      acc.x = fmaf(p[u], v[u].x, acc.x); acc.y = fmaf(p[u], v[u].y, acc.y);
+      acc.z = fmaf(p[u], v[u].z, acc.z); acc.w = fmaf(p[u], v[u].w, acc.w);
+    }
   }
-  if (att_logit) {
-    for (int e = lo + threadIdx.x; e < hi; e += 128) att_logit[e] = expf(att_logit[e] - M) * il;
+  for (; e < hi; ++e) {
+    const int c = g.int_col[e];
+    const float4 v = ld4(V + (size_t)c * ldv + f);
+    const float p = expf(logit[e] - mx) * il;
+    arn = fmaf(p, rad[e], arn);
+    acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y); acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
   }
+  arn *= inv_norm;
+  const float4 vr = ld4(v_r + f);
+  float4 hv = ld4(h + (size_t)r * H + f);
+  hv.x += fmaf(arn, vr.x, acc.x); hv.y += fmaf(arn, vr.y, acc.y); hv.z += fmaf(arn, vr.z, acc.z); hv.w += fmaf(arn, vr.w, acc.w);
+  st4(h + (size_t)r * H + f, hv);
+  if (hT) st4(hT + (size_t)r * H + f, hv);
 }
 
-int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, int ldv, const float* k_r,
+int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, int ldv, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
-                    float* x_out, float* att, bool bf16_mode, cudaStream_t st) {
-  const int grid = g.N;
-  const int smem = (4 * H + 32) * 4;
-#define FB_IA(T, VEC)                                                                                      \
-  fb_launch(inter_attention_kernel<T, VEC>, dim3(grid), dim3(128), smem, st, g, H, QK, ldqk, Kt, ldk, (const T*)V, (const T*)VC, ldv, k_r, v_r, ac_u, ac_b, ac_w2, rad, \
-                                                          norm, pb_dense, x, cmax, h, (T*)hT, x_out, att)
+                    float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st) {
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
+  const int grid1 = std::max(1, std::min(148 * 8, (cap_int + 7) / 8));
+#define FB_IL(T, VEC)                                                                                                        \
+  fb_launch(inter_logit_kernel<T, VEC>, dim3(grid1), dim3(256), 4 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
+            ac_w2, rad, norm, pb_dense, logit_ws, sdot_ws)
   if (bf16_mode) {
-    if (H <= 128) FB_IA(bf16, 1); else if (H <= 256) FB_IA(bf16, 2); else FB_IA(bf16, 4);
+    if (H <= 128) FB_IL(bf16, 1); else if (H <= 256) FB_IL(bf16, 2); else FB_IL(bf16, 4);
+    fb_launch(inter_aggregate_kernel<bf16>, dim3(g.N), dim3(128), 0, st, g, H, (const bf16*)V, ldv, v_r, rad, norm, logit_ws, sdot_ws, x,
+              cmax, h, (bf16*)hT, x_out, att);
   } else {
-    if (H <= 128) FB_IA(float, 1); else if (H <= 256) FB_IA(float, 2); else FB_IA(float, 4);
+    if (H <= 128) FB_IL(float, 1); else if (H <= 256) FB_IL(float, 2); else FB_IL(float, 4);
+    fb_launch(inter_aggregate_kernel<float>, dim3(g.N), dim3(128), 0, st, g, H, (const float*)V, ldv, v_r, rad, norm, logit_ws, sdot_ws, x,
+              cmax, h, (float*)hT, x_out, att);
   }
-#undef FB_IA
-  count_launch(1);
+#undef FB_IL
+  count_launch(2);
   FB_CHECK_LAUNCH();
   return FB_OK;
 }

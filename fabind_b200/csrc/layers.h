@@ -26,10 +26,10 @@ int pair_gather(const GraphDev& g, int cap_u, int H, const void* P0, const float
                 bool bf16_mode, cudaStream_t st);
 int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, int stride, const float* cst, float* pb_dense,
                      cudaStream_t st);
-int inter_attention(const GraphDev& g, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, int ldv, const float* k_r,
+int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, int ldv, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
-                    float* x_out, float* att, bool bf16_mode, cudaStream_t st);
+                    float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st);
 int las_step(const GraphDev& g, const float* x, const float* xref, float step, float cl, float* x_out, cudaStream_t st);
 
 }  // namespace fb

@@ -1,8 +1,10 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum[,...] --csv` launch list per kernel (durations only)."""
 import collections, csv, re, sys
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 tot, cnt = collections.defaultdict(float), collections.Counter()
 for row in csv.DictReader(lines):
+    if row["Metric Name"] != "gpu__time_duration.sum":
+        continue
     v = float(row["Metric Value"].replace(",", ""))
     v = v / 1e3 if row["Metric Unit"] == "ns" else (v * 1e3 if row["Metric Unit"] == "ms" else v)
     name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
