@@ -20,3 +20,13 @@ def published_args(**over):
     for k, v in over.items():
         setattr(a, k, v)
     return a
+
+
+def published_args_plus(**over):
+    """FABind+ published training/evaluation flags (FABind_plus/README.md:125-141) on top of the shared ones;
+    argparse defaults from FABind_plus/fabind/utils/parsing.py:169-195."""
+    a = published_args(mean_layers=5, use_ln_mlp=True, mlp_hidden_scale=1, dropout=0.1, mha_heads=4,
+                       rel_dis_pair_bias="no", inter_additional_mlp=False, only_last_LAS=False)
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a

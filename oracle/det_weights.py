@@ -4,7 +4,7 @@ The reference checkpoints are not available, so gol
 produced with weights that can be regenerated anywhere from (key name, shape, seed) alone:
 numpy PCG64 streams keyed by a CRC of the parameter name.  Matrices follow the fan-in-uniform
 scale of torch.nn.Linear's default init; the final coordinate-head rows -- which the reference
-initialises with xavier gain 0.001 (models/egnn.py:52,164) and which would leave coordinates
+initialises with xavier gain 0.001 (models/egnn.py:52,164; FABind+ models/egnn.py:41,135) and which would leave coordinates
 frozen -- get an O(1) scale so clamps, the LAS step and the moving inter-edge set are exercised.
 """
 import zlib
@@ -21,6 +21,8 @@ def det_tensor(name, shape, seed=0):
         bound = 1.0 / np.sqrt(fan_in)
         if name.endswith("coord_mlp.2.weight"):
             bound = 16.0 / np.sqrt(fan_in)
+        if name.endswith("coord_mlp.linear2.weight"):   # FABind+: the head reads LayerNorm'd ReLU features (larger)
+            bound = 3.0 / np.sqrt(fan_in)
     elif len(shape) == 1:
         bound = 0.05
     else:

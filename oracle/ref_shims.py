@@ -157,3 +157,8 @@ def published_args(**over):
     """The flags of the published v1 evaluation command (F/test_fabind.py:182) that the path reads."""
     from fabind_b200.config import published_args as _pa
     return _pa(**over)
+
+
+def published_args_plus(**over):
+    from fabind_b200.config import published_args_plus as _pa
+    return _pa(**over)

@@ -89,6 +89,57 @@ def main():
               "E_int", [int(e[1].shape[1]) for e in edges])
 
 
+PLUS_CASES = {
+    "plus_h64_l2_it2_ragged": (64, 2, 2, dict(n_complexes=3, seed=1, n_c_range=(8, 30), n_p_range=(40, 90)), 31, False),
+    "plus_h128_l1_it1_cfg1": (128, 1, 1, dict(n_complexes=1, seed=0, n_c=30, n_p=200), 32, False),
+    "plus_h32_l1_it2_fallback": (32, 1, 2, dict(n_complexes=1, seed=4, n_c=5, n_p=24), 34, True),
+}
+
+
+def main_plus():
+    """FABind+ weight layout (LayerNorm MLPs, propagated pair embedding): EfficientMCAttModel.forward -> (X, H, pair)"""
+    mods = ref_shims.load_reference("plus")
+    for name, (hidden, L, IT, bkw, wseed, far) in PLUS_CASES.items():
+        args = ref_shims.published_args_plus()
+        scale = args.coordinate_scale
+        m = mods.att_model.EfficientMCAttModel(
+            args, hidden, hidden, 1, n_edge_feats=0, n_layers=L, n_iter=IT, inter_cutoff=args.inter_cutoff,
+            intra_cutoff=args.intra_cutoff, normalize_coord=lambda x: x / scale, unnormalize_coord=lambda x: x * scale).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+        b = make_batch(embed=hidden, **bkw)
+        if far:
+            nc = b.n_c[0]
+            b.X[1:nc + 1] += 20.0
+        traces, hooks, last = [], [], {"it": -1}
+        hooks.append(m.gnn.register_forward_pre_hook(lambda mod, inp: last.__setitem__("it", last["it"] + 1)))
+        for i in range(L):
+            for kind in ("gcl", "att"):
+                def hk(mod, inp, out, tag=f"{kind}_{i}"):
+                    if last["it"] == IT - 1:
+                        traces.append((tag, out[0].detach().clone(), out[1].detach().clone()))
+                hooks.append(getattr(m.gnn, f"{kind}_{i}").register_forward_hook(hk))
+        edges = []
+        orig = m.extract_edges.forward
+
+        def rec(X, bid, seg, glb):
+            r = orig(X, bid, seg, glb)
+            edges.append((r[0].to(torch.int32).clone(), r[1].to(torch.int32).clone()))
+            return r
+        m.extract_edges.forward = rec
+        with torch.no_grad():
+            X, H, pair = m(**b.clone().forward_args())
+        for h in hooks:
+            h.remove()
+        torch.save({
+            "recipe": dict(hidden=hidden, n_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, far_ligand=far, flavour="plus"),
+            "shapes": shapes, "X": X.clone(), "H": H.clone(), "pair": pair.clone(), "edges": edges,
+            "trace_last_iter": traces, "torch": torch.__version__,
+        }, os.path.join(OUT, name + ".pt"))
+        print(name, "X", tuple(X.shape), "pair", tuple(pair.shape), "moved", float((X - b.X).abs().max()),
+              "E_int", [int(e[1].shape[1]) for e in edges])
+
+
 def main_l2():
     """goldens for the L2 wrapper (models/model.py): forward(stage=2) in eval mode and inference()"""
     from fabind_b200.synthetic import make_docking_batch
@@ -112,5 +163,10 @@ def main_l2():
 
 
 if __name__ == "__main__":
-    main()
-    main_l2()
+    which = sys.argv[1:] or ["v1", "l2", "plus"]
+    if "v1" in which:
+        main()
+    if "l2" in which:
+        main_l2()
+    if "plus" in which:
+        main_plus()

@@ -15,6 +15,10 @@ def golden_files():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, "v1_*.pt")))
 
 
+def plus_golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "plus_*.pt")))
+
+
 def l2_golden_files():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, "l2_*.pt")))
 

@@ -62,3 +62,22 @@ def test_edges_bit_exact_near_cutoff():
         c2, i2, r2 = orc.build_edges(X, b.batch_id, b.segment_id, b.is_global, 8 / 5.0, 10 / 5.0)
     assert torch.equal(ctx, c2) and torch.equal(inter, i2)
     assert torch.equal(red[0], r2[0]) and torch.equal(red[1], r2[1])
+
+
+def test_plus_full_forward():
+    """FABind+ layout against the live FABind+ modules."""
+    from oracle import fabind_plus_oracle as orcp
+    hidden, L, IT = 48, 2, 2
+    mods = ref_shims.load_reference("plus")
+    args = ref_shims.published_args_plus()
+    m = mods.att_model.EfficientMCAttModel(
+        args, hidden, hidden, 1, n_edge_feats=0, n_layers=L, n_iter=IT, inter_cutoff=10, intra_cutoff=8,
+        normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0).eval()
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 23)
+    m.load_state_dict(sd, strict=True)
+    b = make_batch(embed=hidden, n_complexes=3, seed=7, n_c_range=(5, 25), n_p_range=(30, 70))
+    with torch.no_grad():
+        Xr, Hr, Pr = m(**b.clone().forward_args())
+        Xo, Ho, Po = orcp.model_forward(sd, orc.make_cfg(n_layers=L, n_iter=IT), b.X, b.H, b.batch_id, b.segment_id, b.mask,
+                                        b.is_global, b.compound_edge_index, b.LAS_edge_index, b.X_LAS)
+    assert rel_err(Xo, Xr) < 2e-6 and rel_err(Ho, Hr) < 2e-5 and rel_err(Po, Pr) < 2e-5
