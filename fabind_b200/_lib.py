@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfabind_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "CUDA launch error", -4: "unsupported configuration"}
 
@@ -29,6 +29,7 @@ class ModelParams(C.Structure):
         ("ws_main", C.c_void_p), ("ws_main_bytes", C.c_size_t),
         ("X_out", C.c_void_p), ("H_out", C.c_void_p), ("stats", C.c_void_p),
         ("trace_h", C.c_void_p), ("trace_x", C.c_void_p),
+        ("flavour", C.c_int32), ("pair_out", C.c_void_p),
     ]
 
 
@@ -41,6 +42,7 @@ class EgnnExtra(C.Structure):
     ]
 
 
+FLAVOUR_V1, FLAVOUR_PLUS = 0, 1
 STEP_LINEAR_IN, STEP_GCL, STEP_ATT, STEP_LAS, STEP_OUT_LAYER, STEP_LINEAR_OUT = 1, 2, 4, 8, 16, 32
 
 
@@ -67,6 +69,10 @@ EXPORTS = {
     "fb_weight_slot_info": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32,
                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fb_weight_arena_elems": (C.c_int64, [C.c_int32, C.c_int32]),
+    "fb_weight_slot_count_f": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "fb_weight_slot_info_f": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32,
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fb_weight_arena_elems_f": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "fb_graph_workspace_bytes": (C.c_int64, [C.POINTER(ModelParams)]),
     "fb_model_workspace_bytes": (C.c_int64, [C.POINTER(ModelParams)]),
     "fb_graph_static": (C.c_int32, [C.POINTER(ModelParams), C.c_void_p]),

@@ -73,10 +73,27 @@ struct AttW {
   int64_t pt1_w, pt1_b, pt2v, pt_c;
   int64_t qk_w, qk_b, k_r, v_r, ac1_b, ac2_w, ac_u;
 };
+// FABind+ layout (LayerNorm -> Linear -> ReLU -> Linear [-> ReLU] MLPs, P/models/model_utils.py:10-74)
+static inline int dp_of(int H) { return (2 * H + 1 + 63) / 64 * 64; }   // 2H+1 edge-MLP features padded to a multiple of 64
+struct GclPW {
+  int64_t e1_rc, e1_rad, e1_g, e1_c0, e2_w, e2_b;          // edge_mlp: LN folded into the hoisted first Linear
+  int64_t cl_g, cl_b, c1_w, c1_b, c2_w;                     // coord_mlp: explicit LN, Linear+ReLU, row-dot
+  int64_t nl_g, nl_b, n1_w, n1_b, n2_w, n2_b;               // node_mlp: explicit LN over [h | agg]
+};
+struct AttPW {
+  int64_t ca_c_w, ca_c_b, ca_p_w, ca_p_b, ca_p2_w, o_p_w, o_p_b, o_c_w, o_c_b;
+  int64_t tpl_g, tpl_b, tp1_w, tp1_b, tp2_w, tp2_b, tcl_g, tcl_b, tc1_w, tc1_b, tc2_w, tc2_b;
+  int64_t pb_w, pb_b;                                       // pair-bias projections of THIS layer (pair changes per layer)
+  int64_t zo_w, zo_b, zl_g, zl_b, pt1_w, pt1_b, pt2_w, pt2_b, wb, pt_c;
+  int64_t qk_w, qk_b, k_r, v_r, ac_c0, ac2_w, ac_u, ac_g, ac_r;
+};
 struct ModelW {
   int64_t in_w, in_b, out_w, out_b, il_p_w, il_p_b, il_c_w, il_c_b, il_o_w, il_o_b, pb_w, pb_b;
   std::vector<GclW> gcl;  // n_layers + 1 (last = out_layer)
   std::vector<AttW> att;
+  std::vector<GclPW> gclp;
+  std::vector<AttPW> attp;
+  int flavour = 0;
   int64_t total = 0;
   std::vector<Slot> slots;
 };
@@ -130,13 +147,72 @@ static void build_weights(int H, int L, ModelW& w) {
   w.total = off;
 }
 
-static const ModelW& weights_for(int H, int L) {
-  static std::vector<std::pair<std::pair<int, int>, ModelW*>> cache;
+static void build_weights_plus(int H, int L, ModelW& w) {
+  int64_t off = 0;
+  auto add = [&](const std::string& name, int64_t rows, int64_t cols) {
+    const int64_t o = off;
+    w.slots.push_back({name, rows, cols, o});
+    off += (rows * cols + 63) / 64 * 64;
+    return o;
+  };
+  const int Dp = dp_of(H);
+  w.flavour = 1;
+  w.in_w = add("in_w", H, H); w.in_b = add("in_b", 1, H);
+  w.out_w = add("out_w", H, H); w.out_b = add("out_b", 1, H);
+  w.il_p_w = add("il_p_w", H, H); w.il_p_b = add("il_p_b", 1, H);
+  w.il_c_w = add("il_c_w", H, H); w.il_c_b = add("il_c_b", 1, H);
+  w.il_o_w = add("il_o_w", H, H); w.il_o_b = add("il_o_b", 1, H);
+  w.pb_w = w.pb_b = 0;
+  for (int i = 0; i <= L; ++i) {
+    const std::string p = i < L ? "gcl" + std::to_string(i) + "." : std::string("out.");
+    GclPW g;
+    g.e1_rc = add(p + "e1_rc", 2 * Dp, H); g.e1_rad = add(p + "e1_rad", 1, Dp); g.e1_g = add(p + "e1_g", 1, Dp);
+    g.e1_c0 = add(p + "e1_c0", 1, Dp);
+    g.e2_w = add(p + "e2_w", H, Dp); g.e2_b = add(p + "e2_b", 1, H);
+    g.cl_g = add(p + "cl_g", 1, H); g.cl_b = add(p + "cl_b", 1, H);
+    g.c1_w = add(p + "c1_w", H, H); g.c1_b = add(p + "c1_b", 1, H); g.c2_w = add(p + "c2_w", 1, H);
+    g.nl_g = add(p + "nl_g", 1, 2 * H); g.nl_b = add(p + "nl_b", 1, 2 * H);
+    g.n1_w = add(p + "n1_w", 2 * H, 2 * H); g.n1_b = add(p + "n1_b", 1, 2 * H);
+    g.n2_w = add(p + "n2_w", H, 2 * H); g.n2_b = add(p + "n2_b", 1, H);
+    w.gclp.push_back(g);
+  }
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "att" + std::to_string(i) + ".";
+    AttPW a;
+    a.ca_c_w = add(p + "ca_c_w", 4 * HD, H); a.ca_c_b = add(p + "ca_c_b", 1, 4 * HD);
+    a.ca_p_w = add(p + "ca_p_w", 2 * HD, H); a.ca_p_b = add(p + "ca_p_b", 1, 2 * HD);
+    a.ca_p2_w = add(p + "ca_p2_w", 2 * HD, H);
+    a.o_p_w = add(p + "o_p_w", H, HD); a.o_p_b = add(p + "o_p_b", 1, H);
+    a.o_c_w = add(p + "o_c_w", H, HD); a.o_c_b = add(p + "o_c_b", 1, H);
+    a.tpl_g = add(p + "tpl_g", 1, H); a.tpl_b = add(p + "tpl_b", 1, H);
+    a.tp1_w = add(p + "tp1_w", H, H); a.tp1_b = add(p + "tp1_b", 1, H);
+    a.tp2_w = add(p + "tp2_w", H, H); a.tp2_b = add(p + "tp2_b", 1, H);
+    a.tcl_g = add(p + "tcl_g", 1, H); a.tcl_b = add(p + "tcl_b", 1, H);
+    a.tc1_w = add(p + "tc1_w", H, H); a.tc1_b = add(p + "tc1_b", 1, H);
+    a.tc2_w = add(p + "tc2_w", H, H); a.tc2_b = add(p + "tc2_b", 1, H);
+    a.pb_w = add(p + "pb_w", 128, H); a.pb_b = add(p + "pb_b", 1, 128);
+    a.zo_w = add(p + "zo_w", 32, H) /* inter_layer.linear_out.weight TRANSPOSED */; a.zo_b = add(p + "zo_b", 1, H);
+    a.zl_g = add(p + "zl_g", 1, H); a.zl_b = add(p + "zl_b", 1, H);
+    a.pt1_w = add(p + "pt1_w", H, H); a.pt1_b = add(p + "pt1_b", 1, H);
+    a.pt2_w = add(p + "pt2_w", H, H); a.pt2_b = add(p + "pt2_b", 1, H);
+    a.wb = add(p + "wb", 1, H); a.pt_c = add(p + "pt_c", 1, 1);
+    a.qk_w = add(p + "qk_w", 4 * H + QKX, H); a.qk_b = add(p + "qk_b", 1, 4 * H + QKX); a.k_r = add(p + "k_r", 1, H);
+    a.v_r = add(p + "v_r", 1, H);
+    a.ac_c0 = add(p + "ac_c0", 1, H); a.ac2_w = add(p + "ac2_w", 1, H); a.ac_u = add(p + "ac_u", 1, H);
+    a.ac_g = add(p + "ac_g", 1, H); a.ac_r = add(p + "ac_r", 1, 2);
+    w.attp.push_back(a);
+  }
+  w.total = off;
+}
+
+static const ModelW& weights_for(int H, int L, int flavour = 0) {
+  struct Key { int H, L, f; ModelW* w; };
+  static std::vector<Key> cache;
   for (auto& kv : cache)
-    if (kv.first.first == H && kv.first.second == L) return *kv.second;
+    if (kv.H == H && kv.L == L && kv.f == flavour) return *kv.w;
   ModelW* w = new ModelW();
-  build_weights(H, L, *w);
-  cache.push_back({{H, L}, w});
+  if (flavour == 1) build_weights_plus(H, L, *w); else build_weights(H, L, *w);
+  cache.push_back({H, L, flavour, w});
   return *w;
 }
 
@@ -184,7 +260,9 @@ struct Bufs {
   // pair
   void *P0, *A0, *Zg, *T64; float *PBraw, *PB, *pb_dense, *dotU;
   // edge
-  float *radc, *normc, *radi, *normi, *dotE, *lgt, *sde; void *A1, *M;
+  float *radc, *normc, *radi, *normi, *dotE, *lgt, *sde;
+  // FABind+ only
+  float *hstat, *vstat, *dotP; void *M2, *TH2, *Tn, *PairA, *PairB, *Zl, *Zh; void *A1, *M;
 };
 
 static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
@@ -194,6 +272,8 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   const size_t Nc = p.Nc_tot, Np = N - Nc;
   const bool bf = p.bf16_mode;
   const size_t tilesH = gemm_dot_tiles((int)E, (int)H, (int)H, bf), tiles2H = gemm_dot_tiles((int)(capI / 2), (int)(2 * H), (int)H, bf);
+  const bool plus = p.flavour == FB_FLAVOUR_PLUS;
+  const size_t Dp = dp_of((int)H);
   b.ctx_row = a.get<int>(E); b.ctx_col = a.get<int>(E);
   b.int_row = a.get<int>(capI); b.int_col = a.get<int>(capI); b.int_pair = a.get<int>(capI);
   b.x_state = a.get<float>(3 * N); b.xa = a.get<float>(3 * N); b.xb = a.get<float>(3 * N); b.xl = a.get<float>(3 * N);
@@ -204,12 +284,18 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.Hfin = a.get<float>(N * H);
   b.pc = a.get<float>(N * H);
   b.P0 = a.take(P * H * TS);
-  b.PB = a.get<float>(P * L * 8);
+  b.PB = a.get<float>(P * (plus ? 1 : L) * 8);
   b.pb_dense = a.get<float>(P);
   // per-sub-layer temporaries
-  b.Pn = a.take(N * 2 * H * TS);
+  b.Pn = a.take(N * 2 * (plus ? Dp : H) * TS);
   b.radc = a.get<float>(E); b.normc = a.get<float>((size_t)p.B * RAD_SLICES);
-  b.A1 = a.take(E * H * TS); b.M = a.take(E * H * TS);
+  b.A1 = a.take(E * (plus ? Dp : H) * TS); b.M = a.take(E * H * TS);
+  if (plus) {
+    b.hstat = a.get<float>(3 * N); b.vstat = a.get<float>(3 * N);
+    b.M2 = a.take(E * H * TS); b.TH2 = a.take(N * 2 * H * TS); b.Tn = a.take(N * H * TS);
+    b.PairA = a.take(P * H * TS); b.PairB = a.take(P * H * TS); b.Zl = a.take(P * H * TS); b.Zh = a.take(P * H * TS);
+    b.dotP = a.get<float>((size_t)gemm_dot_tiles((int)P, (int)H, (int)H, bf) * P);
+  }
   b.dotE = a.get<float>(tilesH * E);
   b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
   b.CAc = a.get<float>((Nc + 1) * 4 * HD); b.CAp = a.get<float>((Np + 1) * 2 * HD); b.CAp2 = a.get<float>((Np + 1) * 2 * HD);
@@ -222,7 +308,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.VCT = nullptr;
   // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
   b.A0 = a.take(P * H * TS);
-  b.PBraw = a.get<float>(P * pb_cols((int)L));
+  b.PBraw = a.get<float>(P * (plus ? 128 : pb_cols((int)L)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,6 +442,97 @@ struct Run {
     });
   }
 
+  // ---- FABind+ layout -------------------------------------------------------------------------------------------
+  static constexpr float LN_EPS = 1e-5f;   // torch.nn.LayerNorm default (P/models/model_utils.py:15,37,60)
+
+  // MC_E_GCL (P/models/egnn.py:44-115)
+  void run_gcl_plus(const GclPW& gw, const float* x_in, float* x_out, bool need_h) {
+    const int E = p.E_ctx, Dp = dp_of(H);
+    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
+    // per-node sums of h and h^2: the LayerNorm statistics of [h_row | h_col | radial] are assembled per edge
+    stage(CAT_EDGE_ELEMWISE, [&] { return row_stats(b.h, H, N, H, nullptr, b.hstat, false, st); });
+    gemm_cat = CAT_GEMM_NODE;
+    gemm(b.hT, H, H, gw.e1_rc, 2 * Dp, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * Dp);
+    stage(CAT_EDGE_ELEMWISE, [&] {
+      return gcl_edge_pre_plus(E, H, Dp, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.hstat, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_g),
+                               F(gw.e1_c0), LN_EPS, b.A1, bf, st);
+    });
+    gemm_cat = CAT_GEMM_EDGE;
+    gemm(b.A1, Dp, Dp, gw.e2_w, H, gw.e2_b, FB_ACT_RELU, E, nullptr, 0, b.M, H);
+    // coord_mlp = MLPwoBias: LayerNorm on the edge message, Linear + ReLU, Linear(H,1) as the row-dot epilogue
+    stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(b.M, true, H, H, nullptr, 0, 0, E, F(gw.cl_g), F(gw.cl_b), LN_EPS, b.M2, H, bf, st); });
+    const int tiles = gemm_dot_tiles(E, H, H, bf);
+    gemm(b.M2, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_RELU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
+    stage(CAT_EDGE_ELEMWISE, [&] {
+      return gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st);
+    });
+    gemm_cat = CAT_GEMM_NODE;
+    if (need_h) {
+      // node_mlp = MLPwithLastAct on [h | agg], residual
+      stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(b.h, false, H, H, b.agg, H, H, N, F(gw.nl_g), F(gw.nl_b), LN_EPS, b.TH, 2 * H, bf, st); });
+      gemm(b.TH, 2 * H, 2 * H, gw.n1_w, 2 * H, gw.n1_b, FB_ACT_RELU, N, nullptr, 0, b.TH2, 2 * H);
+      gemm(b.TH2, 2 * H, 2 * H, gw.n2_w, H, gw.n2_b, FB_ACT_RELU, N, b.h, H, b.hT, H, b.h, H);
+    }
+  }
+
+  // MC_Att_L (P/models/egnn.py:269-300) with CrossAttentionModule (P/models/cross_att.py:20-45); the pair embedding is
+  // read from pair_in and the updated one written to pair_out (every pair row, carried to the next layer)
+  void run_att_plus(const AttPW& aw, const void* pair_in, void* pair_out, const float* x_in, float* x_out, float* att = nullptr) {
+    const size_t P = p.P_total;
+    float* hp = b.h + (size_t)Nc * H;
+    void* hTp = at(b.hT, (size_t)Nc * H);
+    // gated pair biases of the two RowAttentionBlocks from the CURRENT pair embedding (cross_att.py:80-82)
+    gemm_cat = CAT_GEMM_PAIR0;
+    gemm(pair_in, H, H, aw.pb_w, 128, aw.pb_b, FB_ACT_NONE, (int)P, b.PBraw, 128, nullptr, 0);
+    stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, 1, b.PBraw, 128, b.PB, st); });
+    gemm_cat = CAT_GEMM_NODE;
+    gemm_pair(mk(b.hT, H, H, aw.ca_c_w, 4 * HD, aw.ca_c_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0),
+              mk(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0));
+    const float* CApv = b.CAp - (size_t)Nc * 2 * HD;
+    stage(CAT_ATTENTION, [&] {
+      return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD, b.PB, b.O, HD, bf, st);
+    });
+    gemm(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
+    gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
+    const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
+    stage(CAT_ATTENTION, [&] {
+      return row_attention(g, 0, p.max_c, p.max_p, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
+                           b.PB + P * 4, b.O, HD, bf, st);
+    });
+    gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
+    // transitions = MLPwithLastAct (LN, Linear+ReLU, Linear+ReLU), residual
+    void* Tnp = at(b.Tn, (size_t)Nc * H);
+    void* THp = at(b.TH, (size_t)Nc * H);
+    stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(b.h, false, H, H, nullptr, 0, 0, Nc, F(aw.tcl_g), F(aw.tcl_b), LN_EPS, b.Tn, H, bf, st); });
+    stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(hp, false, H, H, nullptr, 0, 0, Np, F(aw.tpl_g), F(aw.tpl_b), LN_EPS, Tnp, H, bf, st); });
+    gemm_pair(mk(b.Tn, H, H, aw.tc1_w, H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, H),
+              mk(Tnp, H, H, aw.tp1_w, H, aw.tp1_b, FB_ACT_RELU, Np, nullptr, 0, THp, H));
+    gemm_pair(mk(b.TH, H, H, aw.tc2_w, H, aw.tc2_b, FB_ACT_RELU, Nc, b.h, H, b.hT, H, b.h, H),
+              mk(THp, H, H, aw.tp2_w, H, aw.tp2_b, FB_ACT_RELU, Np, hp, H, hTp, H, hp, H));
+    // q | k | inter32_p | inter32_c | pad  ||  v | vc   (vc = (coord_mlp.linear1 * gamma) applied to v, folded)
+    const int ldqk = 2 * H + QKX;
+    gemm(b.hT, H, H, aw.qk_w, ldqk + 2 * H, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, b.VT, 2 * H, nullptr, 0, nullptr, 0, 0, -1,
+         nullptr, 0, nullptr, ldqk);
+    // pair <- MLPwithLastAct(pair + inter32(p, c)) on every pair row; attn_bias_proj of the result as the row-dot epilogue
+    stage(CAT_ATTENTION, [&] {
+      return pair_zin_plus(g, (int)P, H, pair_in, b.QK + 2 * H, ldqk, F(aw.zo_w), F(aw.zo_b), F(aw.zl_g), F(aw.zl_b), LN_EPS, b.Zl, bf, st);
+    });
+    gemm_cat = CAT_GEMM_PAIR;
+    gemm(b.Zl, H, H, aw.pt1_w, H, aw.pt1_b, FB_ACT_RELU, (int)P, nullptr, 0, b.Zh, H);
+    const int tilesP = gemm_dot_tiles((int)P, H, H, bf);
+    gemm(b.Zh, H, H, aw.pt2_w, H, aw.pt2_b, FB_ACT_RELU, (int)P, nullptr, 0, pair_out, H, nullptr, 0, nullptr, 0, 0, aw.wb, b.dotP, (int)P);
+    gemm_cat = CAT_GEMM_NODE;
+    stage(CAT_ATTENTION, [&] { return pair_bias_all((int)P, b.dotP, tilesP, (int)P, F(aw.pt_c), b.pb_dense, st); });
+    // interfacial attention; coordinate head = MLPwoBias on v_e with its LayerNorm folded (per-node sums of v)
+    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
+    stage(CAT_ATTENTION, [&] { return row_stats(b.VT, 2 * H, N, H, F(aw.v_r), b.vstat, bf, st); });
+    stage(CAT_ATTENTION, [&] {
+      return inter_attention(g, p.cap_int, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac_c0),
+                             F(aw.ac2_w), b.radi, b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, b.lgt,
+                             b.sde, bf, st, F(aw.ac_g), F(aw.ac_r), b.vstat, LN_EPS);
+    });
+  }
+
   void tap(int slot, const float* x) {
     if (p.trace_h) cudaMemcpyAsync(p.trace_h + (size_t)slot * N * H, b.h, sizeof(float) * (size_t)N * H, cudaMemcpyDeviceToDevice, st);
     if (p.trace_x) cudaMemcpyAsync(p.trace_x + (size_t)slot * N * 3, x, sizeof(float) * (size_t)N * 3, cudaMemcpyDeviceToDevice, st);
@@ -413,7 +590,8 @@ struct Run {
     gemm_cat = CAT_GEMM_PAIR0;
     gemm(b.A0, H, H, w.il_o_w, H, w.il_o_b, FB_ACT_NONE, (int)P, nullptr, 0, b.P0, H);
     // gated pair biases of all RowAttentionBlocks at once (pair0 is layer- and iteration-invariant in v1)
-    if (p.n_layers > 0) {
+    const bool plus = w.flavour == 1;
+    if (p.n_layers > 0 && !plus) {
       const int pbc = pb_cols(p.n_layers);
       gemm(b.P0, H, H, w.pb_w, pbc, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, pbc, nullptr, 0);
       stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, p.n_layers, b.PBraw, pbc, b.PB, st); });
@@ -430,17 +608,29 @@ struct Run {
       const float* xc = b.x_state;
       float* bufs[2] = {b.xa, b.xb};
       int k = 0;
+      const void* pair_cur = b.P0;   // FABind+: every iteration restarts from pair_embed0 (P/models/att_model.py:209-218)
       for (int l = 0; l < p.n_layers; ++l) {
-        run_gcl(w.gcl[l], xc, bufs[k], true); xc = bufs[k]; k ^= 1;
+        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true); else run_gcl(w.gcl[l], xc, bufs[k], true);
+        xc = bufs[k]; k ^= 1;
         if (last) tap(2 * l, xc);
-        run_att(w.att[l], l, xc, bufs[k]); xc = bufs[k]; k ^= 1;
+        if (plus) {
+          void* pair_next = (l & 1) ? b.PairB : b.PairA;
+          run_att_plus(w.attp[l], pair_cur, pair_next, xc, bufs[k]);
+          pair_cur = pair_next;
+        } else {
+          run_att(w.att[l], l, xc, bufs[k]);
+        }
+        xc = bufs[k]; k ^= 1;
         if (last) tap(2 * l + 1, xc);
         stage(CAT_GRAPH_MISC, [&] { return las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st); });
         xc = bufs[k]; k ^= 1;
       }
       // the out-layer node update and linear_out only matter on the last iteration
       // (att_model.py:232: non-final iterations discard H)
-      run_gcl(w.gcl[p.n_layers], xc, bufs[k], last); xc = bufs[k];
+      if (plus) run_gcl_plus(w.gclp[p.n_layers], xc, bufs[k], last); else run_gcl(w.gcl[p.n_layers], xc, bufs[k], last);
+      xc = bufs[k];
+      if (last && plus && p.pair_out)
+        stage(CAT_GRAPH_MISC, [&] { return pair_unpack(g, (int)P, H, p.max_p, p.max_c, pair_cur, p.pair_out, bf, st); });
       if (last) {
         gemm_cat = CAT_GEMM_NODE;
         gemm(b.hT, H, H, w.out_w, H, w.out_b, FB_ACT_NONE, N, b.Hfin, H, nullptr, 0);
@@ -457,7 +647,7 @@ using namespace fb;
 
 static bool params_ok(const fb_model_params* p) {
   return p && p->N > 0 && p->B > 0 && p->hidden > 0 && (p->hidden % 8) == 0 && p->hidden <= 512 && p->n_layers >= 0 &&
-         p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot <= p->N;
+         p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot <= p->N && (p->flavour == FB_FLAVOUR_V1 || p->flavour == FB_FLAVOUR_PLUS);
 }
 
 extern "C" {
@@ -500,6 +690,24 @@ int32_t fb_weight_slot_info(int32_t hidden, int32_t n_layers, int32_t i, char* n
 
 int64_t fb_weight_arena_elems(int32_t hidden, int32_t n_layers) { return weights_for(hidden, n_layers).total; }
 
+int32_t fb_weight_slot_count_f(int32_t hidden, int32_t n_layers, int32_t flavour) {
+  return (int32_t)weights_for(hidden, n_layers, flavour).slots.size();
+}
+
+int32_t fb_weight_slot_info_f(int32_t hidden, int32_t n_layers, int32_t flavour, int32_t i, char* name, int32_t name_cap, int64_t* rows,
+                              int64_t* cols, int64_t* offset) {
+  const ModelW& w = weights_for(hidden, n_layers, flavour);
+  if (i < 0 || i >= (int)w.slots.size()) return FB_ERR_BAD_ARG;
+  const Slot& s = w.slots[i];
+  if (name && name_cap > 0) { std::strncpy(name, s.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (rows) *rows = s.rows;
+  if (cols) *cols = s.cols;
+  if (offset) *offset = s.off;
+  return FB_OK;
+}
+
+int64_t fb_weight_arena_elems_f(int32_t hidden, int32_t n_layers, int32_t flavour) { return weights_for(hidden, n_layers, flavour).total; }
+
 int64_t fb_graph_workspace_bytes(const fb_model_params* p) {
   if (!params_ok(p)) return FB_ERR_BAD_ARG;
   Arena a(nullptr, 0, true);
@@ -540,7 +748,7 @@ const int32_t* fb_graph_ctx_count_ptr(const fb_model_params* p) {
 
 int32_t fb_model_forward(const fb_model_params* p, void* stream) {
   if (!params_ok(p) || p->E_ctx < 0) return FB_ERR_BAD_ARG;
-  const ModelW& w = weights_for(p->hidden, p->n_layers);
+  const ModelW& w = weights_for(p->hidden, p->n_layers, p->flavour);
   Run r{*p, w};
   Arena ag(p->ws_graph, p->ws_graph_bytes, false);
   plan_graph(*p, ag, r.g);
@@ -562,6 +770,7 @@ int32_t fb_egnn_forward(const fb_model_params* p, const fb_egnn_extra* e, void* 
   if (!p || !e || p->N <= 0 || p->B <= 0 || p->hidden <= 0 || (p->hidden % 8) || p->hidden > 512 || p->E_ctx < 0) return FB_ERR_BAD_ARG;
   if ((e->steps & FB_STEP_ATT) && (!e->pair0 || p->Nc_tot <= 0 || p->Nc_tot >= p->N)) return FB_ERR_BAD_ARG;
   if (e->E_int > p->cap_int) return FB_ERR_BAD_ARG;
+  if (p->flavour != FB_FLAVOUR_V1) return FB_ERR_UNSUPPORTED;   // stand-alone sub-layers: v1 layout only
   const ModelW& w = weights_for(p->hidden, p->n_layers);
   Run r{*p, w};
   Arena ag(p->ws_graph, p->ws_graph_bytes, false);

@@ -632,22 +632,29 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 // whole 4 KB gathers, online softmax -- ran 6 waves of latency-bound CTAs at 25 % occupancy):
 //   phase 1, one warp per EDGE:   logit_e and s_e  (K / VC gathers, two warp reductions)
 //   phase 2, one CTA per ROW:     softmax over the row's logits, sum_e alpha_e V[c] (thread = 4 features), coordinates
-template <typename T, int VEC>
+// PLUS (FABind+ layout): the coordinate head is MLPwoBias = LayerNorm -> Linear -> ReLU -> Linear(no bias) on
+// v_e = V[c] + rn_e v_r (P/models/egnn.py:243-247); the LayerNorm is folded like in gcl_edge_pre_plus:
+//   t = rstd_e (VC[c] + rn_e u - mu_e g) + c0,  s_e = w2 . ReLU(t),  VC = (W1*gamma) V,  u = (W1*gamma) v_r,  g = (W1*gamma) 1
+// with mu_e / rstd_e from the per-node sums vstat[c] = {sum V, sum V^2, sum V*v_r} and ac_r = {sum v_r, sum v_r^2}.
+template <typename T, int VEC, bool PLUS>
 __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, const float* __restrict__ QK, int ldqk,
                                                           const float* __restrict__ Kt, int ldk, const T* __restrict__ VC, int ldv,
                                                           const float* __restrict__ k_r, const float* __restrict__ ac_u,
                                                           const float* __restrict__ ac_b, const float* __restrict__ ac_w2,
+                                                          const float* __restrict__ ac_g, const float* __restrict__ ac_r,
+                                                          const float* __restrict__ vstat, float eps,
                                                           const float* __restrict__ rad, const float* __restrict__ norm,
                                                           const float* __restrict__ pb_dense, float* __restrict__ logit,
                                                           float* __restrict__ sdot_out) {
   constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: one-MUFU SiLU
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  // the four weight vectors are staged in shared memory (they are not produced by the previous kernel: staged before
+  // the weight vectors are staged in shared memory (they are not produced by the previous kernel: staged before
   // the PDL wait); registers are left for the gathers so that 32 warps stay resident per SM
-  extern __shared__ float il_w[];   // k_r | ac_u | ac_b | ac_w2, H floats each
+  extern __shared__ float il_w[];   // k_r | ac_u | ac_b | ac_w2 | (ac_g), H floats each
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     il_w[i] = k_r[i]; il_w[H + i] = ac_u[i]; il_w[2 * H + i] = ac_b[i]; il_w[3 * H + i] = ac_w2[i];
+    if (PLUS) il_w[4 * H + i] = ac_g[i];
   }
   pdl_entry();
   __syncthreads();
@@ -656,6 +663,13 @@ __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, con
     const int r = g.int_row[e], c = g.int_col[e];
     const float rn = rad[e] / radial_norm(norm, g.node_cplx[r]);
     const float pb = pb_dense[g.int_pair[e]];
+    float mu = 0.f, rstd = 1.f;
+    if (PLUS) {
+      const float invH = 1.0f / (float)H;
+      mu = (vstat[3 * c] + rn * ac_r[0]) * invH;
+      const float ex2 = (vstat[3 * c + 1] + 2.0f * rn * vstat[3 * c + 2] + rn * rn * ac_r[1]) * invH;
+      rstd = rsqrtf(fmaxf(ex2 - mu * mu, 0.f) + eps);
+    }
     float dot = 0.f, sd = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -667,10 +681,17 @@ __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, con
         const float4 kr = *reinterpret_cast<const float4*>(il_w + f), uu = *reinterpret_cast<const float4*>(il_w + H + f);
         const float4 bb = *reinterpret_cast<const float4*>(il_w + 2 * H + f), w2 = *reinterpret_cast<const float4*>(il_w + 3 * H + f);
         dot += q.x * fmaf(rn, kr.x, kk.x) + q.y * fmaf(rn, kr.y, kk.y) + q.z * fmaf(rn, kr.z, kk.z) + q.w * fmaf(rn, kr.w, kk.w);
-        const float t0 = vc.x + fmaf(rn, uu.x, bb.x), t1 = vc.y + fmaf(rn, uu.y, bb.y);
-        const float t2 = vc.z + fmaf(rn, uu.z, bb.z), t3 = vc.w + fmaf(rn, uu.w, bb.w);
-        if (FAST) sd += w2.x * silu_fast(t0) + w2.y * silu_fast(t1) + w2.z * silu_fast(t2) + w2.w * silu_fast(t3);
-        else sd += w2.x * silu(t0) + w2.y * silu(t1) + w2.z * silu(t2) + w2.w * silu(t3);
+        if (PLUS) {
+          const float4 gg = *reinterpret_cast<const float4*>(il_w + 4 * H + f);
+          const float t0 = fmaf(rstd, vc.x + fmaf(rn, uu.x, -mu * gg.x), bb.x), t1 = fmaf(rstd, vc.y + fmaf(rn, uu.y, -mu * gg.y), bb.y);
+          const float t2 = fmaf(rstd, vc.z + fmaf(rn, uu.z, -mu * gg.z), bb.z), t3 = fmaf(rstd, vc.w + fmaf(rn, uu.w, -mu * gg.w), bb.w);
+          sd += w2.x * fmaxf(t0, 0.f) + w2.y * fmaxf(t1, 0.f) + w2.z * fmaxf(t2, 0.f) + w2.w * fmaxf(t3, 0.f);
+        } else {
+          const float t0 = vc.x + fmaf(rn, uu.x, bb.x), t1 = vc.y + fmaf(rn, uu.y, bb.y);
+          const float t2 = vc.z + fmaf(rn, uu.z, bb.z), t3 = vc.w + fmaf(rn, uu.w, bb.w);
+          if (FAST) sd += w2.x * silu_fast(t0) + w2.y * silu_fast(t1) + w2.z * silu_fast(t2) + w2.w * silu_fast(t3);
+          else sd += w2.x * silu(t0) + w2.y * silu(t1) + w2.z * silu(t2) + w2.w * silu(t3);
+        }
       }
     }
 #pragma unroll
@@ -759,12 +780,18 @@ __global__ void __launch_bounds__(128) inter_aggregate_kernel(GraphDev g, int H,
 int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int ldqk, const float* Kt, int ldk, const void* V, const void* VC, int ldv, const float* k_r,
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
-                    float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st) {
+                    float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st,
+                    const float* ac_g, const float* ac_r, const float* vstat, float eps) {
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   const int grid1 = std::max(1, std::min(148 * 8, (cap_int + 7) / 8));
+  const bool plus = vstat != nullptr;
 #define FB_IL(T, VEC)                                                                                                        \
-  fb_launch(inter_logit_kernel<T, VEC>, dim3(grid1), dim3(256), 4 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
-            ac_w2, rad, norm, pb_dense, logit_ws, sdot_ws)
+  do {                                                                                                                       \
+    if (plus) fb_launch(inter_logit_kernel<T, VEC, true>, dim3(grid1), dim3(256), 5 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
+                        ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws);                                \
+    else fb_launch(inter_logit_kernel<T, VEC, false>, dim3(grid1), dim3(256), 4 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
+                   ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws);                                     \
+  } while (0)
   if (bf16_mode) {
     if (H <= 128) FB_IL(bf16, 1); else if (H <= 256) FB_IL(bf16, 2); else FB_IL(bf16, 4);
     fb_launch(inter_aggregate_kernel<bf16>, dim3(g.N), dim3(128), 0, st, g, H, (const bf16*)V, ldv, v_r, rad, norm, logit_ws, sdot_ws, x,

@@ -1,0 +1,326 @@
+// Kernels that only the FABind+ weight layout needs (FABind_plus/fabind/models/model_utils.py:10-74: every MLP is
+// LayerNorm -> Linear -> ReLU -> Linear (-> ReLU); models/cross_att.py:43-45: the pair embedding is updated on ALL
+// pair rows and carried to the next layer).  The LayerNorm in front of a per-edge MLP is folded through the node-level
+// hoisting of its first Linear:
+//     W1 LN(z) + b1 = rstd_e * ( (W1*gamma) z  -  mu_e * (W1*gamma) 1 ) + (W1 beta + b1)
+// with z = [h_row | h_col | radial]: (W1*gamma) z is a sum of two per-NODE projections (one node GEMM) plus a rank-1
+// radial term, and the per-EDGE statistics mu_e / rstd_e come from per-node sums of h and h^2.
+// All kernels: one warp per row/edge, 16-byte accesses along the feature dimension.  T = float (fp32 parity mode) / bf16.
+#include <algorithm>
+#include <type_traits>
+
+#include "layers.h"
+
+namespace fb {
+
+static inline int warp_grid_p(long long n_rows) { return (int)((n_rows * 32 + 255) / 256); }
+
+// ------------------------------------------------------------------------------------------------
+// per-row statistics: out[r] = { sum_f x, sum_f x^2, sum_f x*w }   (w optional)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void row_stats_kernel(const T* __restrict__ x, int ld, int M, int H, const float* __restrict__ w, float* __restrict__ out) {
+  pdl_entry();
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= M) return;
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int f = lane * 4; f < H; f += 128) {
+    const float4 v = ld4(x + (size_t)r * ld + f);
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    if (w) { const float4 q = ld4(w + f); s3 += (v.x * q.x + v.y * q.y) + (v.z * q.z + v.w * q.w); }
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+  if (lane == 0) { out[3 * r] = s1; out[3 * r + 1] = s2; out[3 * r + 2] = s3; }
+}
+
+int row_stats(const void* x, int ld, int M, int H, const float* w, float* out, bool typed_bf16, cudaStream_t st) {
+  if (M <= 0) return FB_OK;
+  if (H & 3) return FB_ERR_UNSUPPORTED;
+  if (typed_bf16) fb_launch(row_stats_kernel<bf16>, dim3(warp_grid_p(M)), dim3(256), 0, st, (const bf16*)x, ld, M, H, w, out);
+  else fb_launch(row_stats_kernel<float>, dim3(warp_grid_p(M)), dim3(256), 0, st, (const float*)x, ld, M, H, w, out);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the concatenation [x1 (H1 cols, type T1) | x2 (H2 cols, type T2)] of each row -> out (type TO)
+// (torch.nn.LayerNorm: biased variance, eps inside the square root).  Two-pass in registers.  x2 may be null.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 8;   // up to 8 * 128 = 1024 features per row
+template <typename T1, typename T2, typename TO>
+__global__ void ln_rows_kernel(const T1* __restrict__ x1, int ld1, int H1, const T2* __restrict__ x2, int ld2, int H2, int M,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                               TO* __restrict__ out, int ldo) {
+  pdl_entry();
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= M) return;
+  const int D = H1 + H2;
+  float4 v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int f = (k * 32 + lane) * 4;
+    if (f < D) {
+      v[k] = f < H1 ? ld4(x1 + (size_t)r * ld1 + f) : ld4(x2 + (size_t)r * ld2 + (f - H1));
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float mu = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int f = (k * 32 + lane) * 4;
+    if (f < D) {
+      const float a = v[k].x - mu, b = v[k].y - mu, c = v[k].z - mu, d = v[k].w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int k = 0; k < LN_MAXV; ++k) {
+    const int f = (k * 32 + lane) * 4;
+    if (f < D) {
+      const float4 gm = ld4(gamma + f), bt = ld4(beta + f);
+      st4(out + (size_t)r * ldo + f, make_float4(fmaf((v[k].x - mu) * rstd, gm.x, bt.x), fmaf((v[k].y - mu) * rstd, gm.y, bt.y),
+                                                 fmaf((v[k].z - mu) * rstd, gm.z, bt.z), fmaf((v[k].w - mu) * rstd, gm.w, bt.w)));
+    }
+  }
+}
+
+// x1: fp32 (x1_typed == false) or typed; x2 (optional): typed; out: typed
+int ln_rows(const void* x1, bool x1_typed, int ld1, int H1, const void* x2, int ld2, int H2, int M, const float* gamma,
+            const float* beta, float eps, void* out, int ldo, bool bf16_mode, cudaStream_t st) {
+  if (M <= 0) return FB_OK;
+  if ((H1 & 3) || (H2 & 3) || H1 + H2 > LN_MAXV * 128) return FB_ERR_UNSUPPORTED;
+  const dim3 grid(warp_grid_p(M)), blk(256);
+  if (!bf16_mode) {
+    fb_launch(ln_rows_kernel<float, float, float>, grid, blk, 0, st, (const float*)x1, ld1, H1, (const float*)x2, ld2, H2, M, gamma, beta, eps, (float*)out, ldo);
+  } else if (x1_typed) {
+    fb_launch(ln_rows_kernel<bf16, bf16, bf16>, grid, blk, 0, st, (const bf16*)x1, ld1, H1, (const bf16*)x2, ld2, H2, M, gamma, beta, eps, (bf16*)out, ldo);
+  } else {
+    fb_launch(ln_rows_kernel<float, bf16, bf16>, grid, blk, 0, st, (const float*)x1, ld1, H1, (const bf16*)x2, ld2, H2, M, gamma, beta, eps, (bf16*)out, ldo);
+  }
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FABind+ GCL edge stage 1 (P/models/egnn.py:44-57 with MLPwithLastAct, model_utils.py:32-53):
+//   A1[e, j] = ReLU( rstd_e * (Pr[row, j] + Pc[col, j] + rn_e * w_rad[j] - mu_e * g[j]) + c0[j] ),   j < Dp
+// mu_e / rstd_e: LayerNorm statistics of [h_row | h_col | rn_e] (D = 2H+1 values) from the per-node sums.
+// P is [N, 2*Dp] (row part | col part), Dp = D rounded up to 64 (padded columns are zero in every operand).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gcl_edge_pre_plus_kernel(int E, int H, int Dp, const int* __restrict__ erow, const int* __restrict__ ecol,
+                                         const int* __restrict__ node_cplx, const T* __restrict__ P, const float* __restrict__ hstat,
+                                         const float* __restrict__ rad, const float* __restrict__ norm,
+                                         const float* __restrict__ w_rad, const float* __restrict__ gsum, const float* __restrict__ c0,
+                                         float eps, T* __restrict__ A1) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= E) return;
+  const int e = warp, r = erow[e], c = ecol[e];
+  const float rn = rad[e] / radial_norm(norm, node_cplx[r]);
+  const float invD = 1.0f / (float)(2 * H + 1);
+  const float mu = (hstat[3 * r] + hstat[3 * c] + rn) * invD;
+  // E[(x-mu)^2] = E[x^2] - mu^2, accumulated in fp32 from the per-node sums
+  const float var = fmaxf((hstat[3 * r + 1] + hstat[3 * c + 1] + rn * rn) * invD - mu * mu, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const T* pr = P + (size_t)r * 2 * Dp;
+  const T* pc = P + (size_t)c * 2 * Dp + Dp;
+  for (int f = lane * 8; f < Dp; f += 256) {
+    float a[8], b[8], w[8], gg[8], cc[8], o[8];
+    ld8(pr + f, a); ld8(pc + f, b); ld8(w_rad + f, w); ld8(gsum + f, gg); ld8(c0 + f, cc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaxf(fmaf(rstd, a[i] + b[i] + fmaf(rn, w[i], -mu * gg[i]), cc[i]), 0.f);
+    st8(A1 + (size_t)e * Dp + f, o);
+  }
+}
+
+int gcl_edge_pre_plus(int E, int H, int Dp, const int* erow, const int* ecol, const int* node_cplx, const void* P,
+                      const float* hstat, const float* rad, const float* norm, const float* w_rad, const float* gsum,
+                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st) {
+  if (E <= 0) return FB_OK;
+  if (Dp & 7) return FB_ERR_UNSUPPORTED;
+  if (bf16_mode) fb_launch(gcl_edge_pre_plus_kernel<bf16>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const bf16*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (bf16*)A1);
+  else fb_launch(gcl_edge_pre_plus_kernel<float>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const float*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (float*)A1);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FABind+ pair-transition input (P/models/cross_att.py:43-45):
+//   Zl[pair, :] = LayerNorm( pair[pair, :] + W_o32 (p32[prot] * c32[comp]) + b_o32 )       for EVERY pair row
+// One warp per pair row; W_o32 ([H, 32], fp32) staged in shared memory transposed to [32][H] so that a lane reads its
+// features with 16-byte accesses.  pc32: [N, ld32] with the 32 interaction channels of protein rows at column 0 and
+// of compound rows at column 32 (the stacked q|k GEMM writes them there).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_complex_p(const int* __restrict__ pair_base, int B, int pair) {
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pair_base[mid] <= pair) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// R pair rows per warp share every shared-memory read of W_o32 (the kernel is bound by those reads, not by HBM).
+constexpr int PZ_R = 4;
+// FULL: H == VEC * 128 exactly, so every "feature < H" guard is compiled out (no BSSY/BSYNC pairs inside the k loop).
+template <typename T, int VEC, bool FULL>
+__global__ void __launch_bounds__(256) pair_zin_plus_kernel(GraphDev g, int P_total, int H_rt, const T* __restrict__ pair,
+                                                            const float* __restrict__ pc32, int ld32, const float* __restrict__ Wo /*[32,H] (pre-transposed)*/,
+                                                            const float* __restrict__ bo, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, T* __restrict__ Zl) {
+  const int H = FULL ? VEC * 128 : H_rt;
+  extern __shared__ float zs[];   // [32][H] W_o32^T
+  for (int i = threadIdx.x * 4; i < H * 32; i += blockDim.x * 4) *reinterpret_cast<float4*>(zs + i) = ld4(Wo + i);
+  pdl_entry();
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float invH = 1.0f / (float)H;
+  for (int pr0 = warp * PZ_R; pr0 < P_total; pr0 += n_warps * PZ_R) {
+    float t[PZ_R];
+    float4 z[PZ_R][VEC];
+#pragma unroll
+    for (int r = 0; r < PZ_R; ++r) {
+      const int pr = min(pr0 + r, P_total - 1);   // tail rows recompute the last row (never stored)
+      const int b = find_complex_p(g.pair_base, g.B, pr);
+      const int nc1 = g.c_off[b + 1] - g.c_off[b];
+      const int loc = pr - g.pair_base[b];
+      const int pi = g.p_off[b] + loc / nc1, ci = g.c_off[b] + loc % nc1;
+      t[r] = pc32[(size_t)pi * ld32 + lane] * pc32[(size_t)ci * ld32 + 32 + lane];   // lane = interaction channel
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int f = (i * 32 + lane) * 4;
+        if (FULL || f < H) {
+          const float4 p4 = ld4(pair + (size_t)pr * H + f), b4 = ld4(bo + f);
+          z[r][i] = make_float4(p4.x + b4.x, p4.y + b4.y, p4.z + b4.z, p4.w + b4.w);
+        }
+      }
+    }
+#pragma unroll 2
+    for (int k = 0; k < 32; ++k) {
+      float tk[PZ_R];
+#pragma unroll
+      for (int r = 0; r < PZ_R; ++r) tk[r] = __shfl_sync(0xffffffffu, t[r], k);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int f = (i * 32 + lane) * 4;
+        if (FULL || f < H) {
+          const float4 w4 = *reinterpret_cast<const float4*>(zs + k * H + f);
+#pragma unroll
+          for (int r = 0; r < PZ_R; ++r) {
+            z[r][i].x = fmaf(tk[r], w4.x, z[r][i].x); z[r][i].y = fmaf(tk[r], w4.y, z[r][i].y);
+            z[r][i].z = fmaf(tk[r], w4.z, z[r][i].z); z[r][i].w = fmaf(tk[r], w4.w, z[r][i].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < PZ_R; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int f = (i * 32 + lane) * 4;
+        if (FULL || f < H) s += (z[r][i].x + z[r][i].y) + (z[r][i].z + z[r][i].w);
+      }
+      const float mu = warp_sum(s) * invH;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int f = (i * 32 + lane) * 4;
+        if (FULL || f < H) {
+          const float a = z[r][i].x - mu, bq = z[r][i].y - mu, c = z[r][i].z - mu, d = z[r][i].w - mu;
+          q += (a * a + bq * bq) + (c * c + d * d);
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) * invH + eps);
+      if (pr0 + r < P_total) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const int f = (i * 32 + lane) * 4;
+          if (FULL || f < H) {
+            const float4 gm = ld4(gamma + f), bt = ld4(beta + f);
+            st4(Zl + (size_t)(pr0 + r) * H + f,
+                make_float4(fmaf((z[r][i].x - mu) * rstd, gm.x, bt.x), fmaf((z[r][i].y - mu) * rstd, gm.y, bt.y),
+                            fmaf((z[r][i].z - mu) * rstd, gm.z, bt.z), fmaf((z[r][i].w - mu) * rstd, gm.w, bt.w)));
+          }
+        }
+      }
+    }
+  }
+}
+
+int pair_zin_plus(const GraphDev& g, int P_total, int H, const void* pair, const float* pc32, int ld32, const float* Wo,
+                  const float* bo, const float* gamma, const float* beta, float eps, void* Zl, bool bf16_mode, cudaStream_t st) {
+  if (P_total <= 0) return FB_OK;
+  if ((H & 3) || H > 512) return FB_ERR_UNSUPPORTED;
+  const int smem = H * 32 * 4;
+  const int grid = std::max(1, std::min(148 * 2, (P_total + 8 * PZ_R - 1) / (8 * PZ_R)));
+  static unsigned long long done[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define FB_PZ_(T, VEC, FULL, slot)                                                                              \
+  do {                                                                                                          \
+    if (!ensure_smem_optin(pair_zin_plus_kernel<T, VEC, FULL>, 512 * 32 * 4, done[slot])) return FB_ERR_CUDA;    \
+    fb_launch(pair_zin_plus_kernel<T, VEC, FULL>, dim3(grid), dim3(256), smem, st, g, P_total, H, (const T*)pair, pc32, ld32, Wo, bo, \
+              gamma, beta, eps, (T*)Zl);                                                                        \
+  } while (0)
+#define FB_PZ(T, VEC, slot) do { if (H == (VEC) * 128) FB_PZ_(T, VEC, true, slot); else FB_PZ_(T, VEC, false, (slot) + 1); } while (0)
+  if (bf16_mode) { if (H <= 128) FB_PZ(bf16, 1, 0); else if (H <= 256) FB_PZ(bf16, 2, 2); else FB_PZ(bf16, 4, 4); }
+  else { if (H <= 128) FB_PZ(float, 1, 6); else if (H <= 256) FB_PZ(float, 2, 8); else FB_PZ(float, 4, 10); }
+#undef FB_PZ_
+#undef FB_PZ
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// pb_dense[pair] = sum of the row-dot partial tiles + constant, for every pair row (attn_bias_proj on the new pair embedding)
+__global__ void pair_bias_all_kernel(int P_total, const float* __restrict__ dot, int tiles, int stride, const float* __restrict__ cst,
+                                     float* __restrict__ pb_dense) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P_total) return;
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += dot[(size_t)t * stride + i];
+  pb_dense[i] = s + cst[0];
+}
+
+int pair_bias_all(int P_total, const float* dot, int tiles, int stride, const float* cst, float* pb_dense, cudaStream_t st) {
+  if (P_total <= 0) return FB_OK;
+  fb_launch(pair_bias_all_kernel, dim3((P_total + 255) / 256), dim3(256), 0, st, P_total, dot, tiles, stride, cst, pb_dense);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// packed pair rows [P_total, H] (typed) -> the reference's dense zero-padded [B, max_p, max_c, H] fp32 block
+// (to_dense_batch layout, P/models/att_model.py:223); the caller zero-fills `out` first
+template <typename T>
+__global__ void pair_unpack_kernel(GraphDev g, int P_total, int H, int max_p, int max_c, const T* __restrict__ pair, float* __restrict__ out) {
+  pdl_entry();
+  const int pr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (pr >= P_total) return;
+  const int b = find_complex_p(g.pair_base, g.B, pr);
+  const int nc1 = g.c_off[b + 1] - g.c_off[b];
+  const int loc = pr - g.pair_base[b];
+  const int pi = loc / nc1, ci = loc % nc1;
+  float* dst = out + (((size_t)b * max_p + pi) * max_c + ci) * H;
+  for (int f = lane * 4; f < H; f += 128) st4(dst + f, ld4(pair + (size_t)pr * H + f));
+}
+
+int pair_unpack(const GraphDev& g, int P_total, int H, int max_p, int max_c, const void* pair, float* out, bool bf16_mode, cudaStream_t st) {
+  if (P_total <= 0) return FB_OK;
+  if (bf16_mode) fb_launch(pair_unpack_kernel<bf16>, dim3(warp_grid_p(P_total)), dim3(256), 0, st, g, P_total, H, max_p, max_c, (const bf16*)pair, out);
+  else fb_launch(pair_unpack_kernel<float>, dim3(warp_grid_p(P_total)), dim3(256), 0, st, g, P_total, H, max_p, max_c, (const float*)pair, out);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+}  // namespace fb

@@ -1,0 +1,62 @@
+"""Drop-in replacement for FABind_plus/fabind/models/att_model.py: `ComplexGraph` (shared with v1: the edge rules are
+identical, att_model.py:29-126) and `EfficientMCAttModel` whose forward returns `(X, H, pair_embed_batched)`
+(att_model.py:166-223).  Inference semantics (eval mode, refine='refine_coord')."""
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..att_model import ComplexGraph  # noqa: F401
+from ..runtime import PackedWeights, model_forward
+from .egnn import MCAttEGNN, _check_args_plus
+from .model_utils import InteractionModule
+
+
+class EfficientMCAttModel(nn.Module):
+    """att_model.py:131-223"""
+
+    def __init__(self, args, embed_size, hidden_size, n_channel, n_edge_feats=0, n_layers=5, dropout=0.1, n_iter=5,
+                 dense=False, inter_cutoff=10, intra_cutoff=8, normalize_coord=None, unnormalize_coord=None):
+        super().__init__()
+        _check_args_plus(args)
+        if getattr(args, "ablation_no_attention", False) or getattr(args, "ablation_no_attention_with_cross_attn", False):
+            raise NotImplementedError("ablation variants are out of scope (not used by any published configuration)")
+        if getattr(args, "refine", "refine_coord") != "refine_coord":
+            raise NotImplementedError("only refine='refine_coord' (the published mode) is built")
+        if embed_size != hidden_size:
+            raise NotImplementedError("embed_size must equal hidden_size (true for both FABind+ stages)")
+        self.n_iter = n_iter
+        self.args = args
+        self.random_n_iter = args.random_n_iter
+        self.hidden_size, self.n_layers = hidden_size, n_layers
+        self.gnn = MCAttEGNN(args, embed_size, hidden_size, hidden_size, n_channel, n_edge_feats, n_layers=n_layers,
+                             residual=True, dropout=dropout, dense=dense, normalize_coord=normalize_coord,
+                             unnormalize_coord=unnormalize_coord, geometry_reg_step_size=args.geometry_reg_step_size)
+        self.extract_edges = ComplexGraph(args, inter_cutoff=inter_cutoff, intra_cutoff=intra_cutoff,
+                                          normalize_coord=normalize_coord, unnormalize_coord=unnormalize_coord)
+        self.inter_layer = InteractionModule(hidden_size, hidden_size, hidden_size, rm_layernorm=args.rm_layernorm)
+        self._cfg = dict(hidden=hidden_size, n_layers=n_layers, n_iter=n_iter,
+                         intra_cutoff=float(normalize_coord(intra_cutoff)), inter_cutoff=float(normalize_coord(inter_cutoff)),
+                         coord_clamp=float(normalize_coord(10)), las_clamp=float(normalize_coord(15)),
+                         las_step=float(args.geometry_reg_step_size), flavour=_lib.FLAVOUR_PLUS)
+        self._packed = PackedWeights()
+        self.precision = os.environ.get("FABIND_B200_PRECISION", "fp32")
+        self.return_pair = True    # False: skip the dense [B, max_p, max_c, H] fp32 copy of the pair embedding (returns None)
+        self.last_stats = None
+        self.debug_trace = False
+
+    def forward(self, X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index,
+                batched_complex_coord_LAS, LAS_mask=None):
+        if self.training:
+            raise NotImplementedError("fabind_b200: the training path (dropout + backward kernels) is not built yet; "
+                                      "call .eval()")
+        if self.precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        with torch.no_grad():
+            H_out, stats, e_ctx, tr, pair = model_forward(self, self._packed, X, H, batch_id, segment_id, mask, is_global,
+                                                          compound_edge_index, LAS_edge_index, batched_complex_coord_LAS,
+                                                          self._cfg, self.precision == "bf16", trace=self.debug_trace,
+                                                          want_pair=self.return_pair)
+        self.last_stats = dict(inter_edges_per_iter=stats, ctx_edges=e_ctx, trace=tr)
+        return X, H_out, pair

@@ -31,11 +31,11 @@ class PackedWeights:
         self.w32 = None
         self.w16 = None
 
-    def get(self, module, hidden, n_layers, device, want_bf16):
+    def get(self, module, hidden, n_layers, device, want_bf16, flavour=0):
         params = list(module.parameters())
-        key = (device, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        key = (device, flavour, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
         if key != self.key:
-            arena = pack_state_dict(module.state_dict(), hidden, n_layers)
+            arena = pack_state_dict(module.state_dict(), hidden, n_layers, flavour)
             self.w32 = arena.to(device)
             self.w16 = None
             self.key = key
@@ -44,9 +44,11 @@ class PackedWeights:
         return self.w32, self.w16
 
 
-def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, bonds, las, X_las, cfg, bf16, trace=False):
+def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, bonds, las, X_las, cfg, bf16, trace=False,
+                  want_pair=None):
     """Runs fb_graph_static + fb_model_forward.  X is updated in place (reference att_model.py:236,245).
-    Returns (H_out, stats[int32 n_iter device tensor])."""
+    Returns (H_out, stats[int32 n_iter device tensor], E_ctx, trace) and, for the FABind+ layout (`want_pair` not None),
+    additionally the dense pair embedding [B, max_p, max_c, hidden] (or None when want_pair is False)."""
     import os, time
     _T = os.environ.get("FABIND_B200_TIMING") == "1"
     _t = [time.perf_counter()]
@@ -78,7 +80,8 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     _mark("input staging")
     lay = build_layout(batch_id, segment_id, is_global, mask, dev)
     _mark("build_layout")
-    w32, w16 = packed.get(module, hidden, cfg["n_layers"], dev, bf16)
+    flavour = cfg.get("flavour", _lib.FLAVOUR_V1)
+    w32, w16 = packed.get(module, hidden, cfg["n_layers"], dev, bf16, flavour)
     H_out = torch.empty((N, hidden), dtype=torch.float32, device=dev)
     stats = torch.zeros(cfg["n_iter"], dtype=torch.int32, device=dev)
 
@@ -99,6 +102,11 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.w32 = w32.data_ptr()
     p.w16 = w16.data_ptr() if w16 is not None else None
     p.X_out, p.H_out, p.stats = xv.data_ptr(), H_out.data_ptr(), stats.data_ptr()
+    p.flavour = flavour
+    pair = None
+    if flavour == _lib.FLAVOUR_PLUS and want_pair:
+        pair = torch.zeros((lay.B, lay.max_p, lay.max_c, hidden), dtype=torch.float32, device=dev)
+        p.pair_out = pair.data_ptr()
 
     tr = None
     if trace:
@@ -144,4 +152,8 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
         th = torch.empty_like(tr[0]); tx = torch.empty_like(tr[1])
         th[:, perm] = tr[0]; tx[:, perm] = tr[1]
         tr = (th, tx)
+    if want_pair is not None:
+        if host_mode and pair is not None:
+            pair = pair.cpu()
+        return H_out, stats, e_ctx, tr, pair
     return H_out, stats, e_ctx, tr

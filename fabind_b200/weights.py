@@ -22,14 +22,14 @@ HD = 128
 QKX = 128   # extra columns of the stacked q|k GEMM (csrc/forward.cu)
 
 
-def slots(hidden, n_layers):
+def slots(hidden, n_layers, flavour=0):
     l = _lib.lib()
     out = []
     name = C.create_string_buffer(64)
     r, c, o = C.c_int64(), C.c_int64(), C.c_int64()
-    for i in range(l.fb_weight_slot_count(hidden, n_layers)):
-        _lib.check(l.fb_weight_slot_info(hidden, n_layers, i, name, 64, C.byref(r), C.byref(c), C.byref(o)),
-                   "fb_weight_slot_info")
+    for i in range(l.fb_weight_slot_count_f(hidden, n_layers, flavour)):
+        _lib.check(l.fb_weight_slot_info_f(hidden, n_layers, flavour, i, name, 64, C.byref(r), C.byref(c), C.byref(o)),
+                   "fb_weight_slot_info_f")
         out.append((name.value.decode(), r.value, c.value, o.value))
     return out
 
@@ -110,17 +110,101 @@ def _top(sd, H, L):
     return d
 
 
-def pack_state_dict(sd, hidden, n_layers):
-    """Returns the fp32 arena (CPU tensor) for a state_dict with the reference's v1 key names."""
+# ---- FABind+ layout (FABind_plus/fabind/models/model_utils.py:32-74: LayerNorm -> Linear -> ReLU -> Linear [-> ReLU]) ----
+# A LayerNorm in front of a Linear is folded as  W LN(z) + b = rstd * ((W*gamma) z - mu * (W*gamma) 1) + (W beta + b);
+# see csrc/plus.cu.  Explicit LayerNorms (coord_mlp / node_mlp of the GCL, the three transitions) keep gamma / beta.
+
+def dp_of(H):
+    """2H+1 edge-MLP features padded to a multiple of 64 (csrc/forward.cu::dp_of)"""
+    return (2 * H + 1 + 63) // 64 * 64
+
+
+def _pad_rows(t, rows):
+    return torch.cat([t, torch.zeros((rows - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype)], 0)
+
+
+def _gcl_plus(sd, p, H):
+    D, Dp = 2 * H + 1, dp_of(H)
+    g = sd[p + "edge_mlp.layernorm.weight"].double()
+    bt = sd[p + "edge_mlp.layernorm.bias"].double()
+    W1 = sd[p + "edge_mlp.linear1.weight"].double()
+    if tuple(W1.shape) != (D, D):
+        raise NotImplementedError("fabind_b200 (FABind+ layout): --mlp-hidden-scale 1 only (the published value)")
+    W1g = W1 * g[None, :]
+    W2 = sd[p + "edge_mlp.linear2.weight"].double()
+    return {
+        "e1_rc": torch.cat([_pad_rows(W1g[:, :H], Dp), _pad_rows(W1g[:, H:2 * H], Dp)], 0),
+        "e1_rad": _pad_rows(W1g[:, 2 * H], Dp), "e1_g": _pad_rows(W1g.sum(1), Dp),
+        "e1_c0": _pad_rows(W1 @ bt + sd[p + "edge_mlp.linear1.bias"].double(), Dp),
+        "e2_w": torch.cat([W2, torch.zeros(H, Dp - D, dtype=torch.float64)], 1), "e2_b": sd[p + "edge_mlp.linear2.bias"],
+        "cl_g": sd[p + "coord_mlp.layernorm.weight"], "cl_b": sd[p + "coord_mlp.layernorm.bias"],
+        "c1_w": sd[p + "coord_mlp.linear1.weight"], "c1_b": sd[p + "coord_mlp.linear1.bias"],
+        "c2_w": sd[p + "coord_mlp.linear2.weight"][0],
+        "nl_g": sd[p + "node_mlp.layernorm.weight"], "nl_b": sd[p + "node_mlp.layernorm.bias"],
+        "n1_w": sd[p + "node_mlp.linear1.weight"], "n1_b": sd[p + "node_mlp.linear1.bias"],
+        "n2_w": sd[p + "node_mlp.linear2.weight"], "n2_b": sd[p + "node_mlp.linear2.bias"],
+    }
+
+
+def _att_plus(sd, p, H):
+    ca = p + "cross_attn_module."
+    pb, cb = ca + "p_attention_block.", ca + "c_attention_block."
+    z = lambda n: torch.zeros(n, dtype=torch.float64)
+    Wkv = sd[p + "linear_kv.weight"].double()
+    bkv = sd[p + "linear_kv.bias"].double()
+    v_r = Wkv[1::2, 0]
+    ac1 = sd[p + "coord_mlp.linear1.weight"].double()
+    ac1g = ac1 * sd[p + "coord_mlp.layernorm.weight"].double()[None, :]
+    d = {
+        "ca_c_w": torch.cat([sd[pb + "mha.linear_k.weight"], sd[pb + "mha.linear_v.weight"],
+                             sd[cb + "mha.linear_q.weight"], sd[cb + "mha.linear_g.weight"]], 0),
+        "ca_c_b": torch.cat([z(3 * HD), sd[cb + "mha.linear_g.bias"].double()]),
+        "ca_p_w": torch.cat([sd[pb + "mha.linear_q.weight"], sd[pb + "mha.linear_g.weight"]], 0),
+        "ca_p_b": torch.cat([z(HD), sd[pb + "mha.linear_g.bias"].double()]),
+        "ca_p2_w": torch.cat([sd[cb + "mha.linear_k.weight"], sd[cb + "mha.linear_v.weight"]], 0),
+        "o_p_w": sd[pb + "mha.linear_o.weight"], "o_p_b": sd[pb + "mha.linear_o.bias"],
+        "o_c_w": sd[cb + "mha.linear_o.weight"], "o_c_b": sd[cb + "mha.linear_o.bias"],
+        # gated pair-bias projections of THIS layer's two RowAttentionBlocks (the pair embedding changes per layer)
+        "pb_w": _pad_rows(torch.cat([sd[pb + "linear.weight"], sd[pb + "linear_g.weight"],
+                                     sd[cb + "linear.weight"], sd[cb + "linear_g.weight"]], 0), 128),
+        "pb_b": _pad_rows(torch.cat([sd[pb + "linear.bias"], sd[pb + "linear_g.bias"],
+                                     sd[cb + "linear.bias"], sd[cb + "linear_g.bias"]], 0), 128),
+        "zo_w": sd[ca + "inter_layer.linear_out.weight"].t().contiguous(), "zo_b": sd[ca + "inter_layer.linear_out.bias"],
+        "zl_g": sd[ca + "pair_transition.layernorm.weight"], "zl_b": sd[ca + "pair_transition.layernorm.bias"],
+        "pt1_w": sd[ca + "pair_transition.linear1.weight"], "pt1_b": sd[ca + "pair_transition.linear1.bias"],
+        "pt2_w": sd[ca + "pair_transition.linear2.weight"], "pt2_b": sd[ca + "pair_transition.linear2.bias"],
+        "wb": sd[p + "attn_bias_proj.weight"][0], "pt_c": sd[p + "attn_bias_proj.bias"].reshape(1),
+        # q | k | inter_layer.linear_p (32) | inter_layer.linear_c (32) | zero pad  ||  v | vc, vc = (linear1*gamma) v
+        "qk_w": torch.cat([sd[p + "linear_q.weight"].double(), Wkv[0::2, 1:],
+                           sd[ca + "inter_layer.linear_p.weight"].double(), sd[ca + "inter_layer.linear_c.weight"].double(),
+                           torch.zeros(QKX - 64, H, dtype=torch.float64), Wkv[1::2, 1:], ac1g @ Wkv[1::2, 1:]], 0),
+        "qk_b": torch.cat([sd[p + "linear_q.bias"].double(), bkv[0::2], sd[ca + "inter_layer.linear_p.bias"].double(),
+                           sd[ca + "inter_layer.linear_c.bias"].double(), z(QKX - 64), bkv[1::2], ac1g @ bkv[1::2]]),
+        "k_r": Wkv[0::2, 0], "v_r": v_r,
+        "ac_c0": ac1 @ sd[p + "coord_mlp.layernorm.bias"].double() + sd[p + "coord_mlp.linear1.bias"].double(),
+        "ac2_w": sd[p + "coord_mlp.linear2.weight"][0], "ac_u": ac1g @ v_r, "ac_g": ac1g.sum(1),
+        "ac_r": torch.stack([v_r.sum(), (v_r * v_r).sum()]),
+    }
+    for t, key in (("tp", "p_transition."), ("tc", "c_transition.")):
+        d[t + "l_g"], d[t + "l_b"] = sd[ca + key + "layernorm.weight"], sd[ca + key + "layernorm.bias"]
+        d[t + "1_w"], d[t + "1_b"] = sd[ca + key + "linear1.weight"], sd[ca + key + "linear1.bias"]
+        d[t + "2_w"], d[t + "2_b"] = sd[ca + key + "linear2.weight"], sd[ca + key + "linear2.bias"]
+    return d
+
+
+def pack_state_dict(sd, hidden, n_layers, flavour=0):
+    """Returns the fp32 arena (CPU tensor) for a state_dict with the reference's key names
+    (flavour 0: FABind v1 layout, 1: FABind+ layout)."""
     sd = {k: v.detach().cpu() for k, v in sd.items()}
     l = _lib.lib()
-    arena = torch.zeros(l.fb_weight_arena_elems(hidden, n_layers), dtype=torch.float32)
-    groups = {"": _top(sd, hidden, n_layers)}
+    arena = torch.zeros(l.fb_weight_arena_elems_f(hidden, n_layers, flavour), dtype=torch.float32)
+    gcl, att = (_gcl_plus, _att_plus) if flavour == 1 else (_gcl, _att)
+    groups = {"": _top(sd, hidden, 0 if flavour == 1 else n_layers)}
     for i in range(n_layers):
-        groups[f"gcl{i}."] = _gcl(sd, f"gnn.gcl_{i}.", hidden)
-        groups[f"att{i}."] = _att(sd, f"gnn.att_{i}.", hidden)
-    groups["out."] = _gcl(sd, "gnn.out_layer.", hidden)
-    for name, rows, cols, off in slots(hidden, n_layers):
+        groups[f"gcl{i}."] = gcl(sd, f"gnn.gcl_{i}.", hidden)
+        groups[f"att{i}."] = att(sd, f"gnn.att_{i}.", hidden)
+    groups["out."] = gcl(sd, "gnn.out_layer.", hidden)
+    for name, rows, cols, off in slots(hidden, n_layers, flavour):
         pre, _, base = name.rpartition(".")
         pre = pre + "." if pre else ""
         if rows * cols == 0:

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 1
+#define FB_ABI_VERSION 2
 
 /* One batch of complexes + model dimensions.  Node layout in caller order is the reference
  * dataloader's [glb_c | atoms | glb_p | residues] per complex (utils/utils.py:328-335). */
@@ -71,7 +71,14 @@ typedef struct fb_model_params {
   /* optional debug taps (INTERNAL node order): h and x after every gcl_i / att_i of the LAST iteration,
    * slot 2*i = gcl_i, 2*i+1 = att_i (before the LAS step); [2*n_layers, N, hidden] and [2*n_layers, N, 3] */
   float* trace_h; float* trace_x;
+  /* ---- ABI 2: weight layout of the stack ---- */
+  int32_t flavour;          /* FB_FLAVOUR_V1 (FABind, models/egnn.py) or FB_FLAVOUR_PLUS (FABind+: LayerNorm MLPs,
+                             * pair embedding propagated layer to layer, FABind_plus/fabind/models/{egnn,cross_att,model_utils}.py) */
+  float* pair_out;          /* FB_FLAVOUR_PLUS, optional: pair embedding after the last layer of the last iteration in the
+                             * reference's dense layout [B, max_p, max_c, hidden] (P/models/att_model.py:223); zero-filled by the caller */
 } fb_model_params;
+#define FB_FLAVOUR_V1 0
+#define FB_FLAVOUR_PLUS 1
 
 /* [host] library identification */
 int32_t fb_abi_version(void);
@@ -92,6 +99,11 @@ int32_t fb_weight_slot_count(int32_t hidden, int32_t n_layers);
 int32_t fb_weight_slot_info(int32_t hidden, int32_t n_layers, int32_t i, char* name, int32_t name_cap,
                             int64_t* rows, int64_t* cols, int64_t* offset);
 int64_t fb_weight_arena_elems(int32_t hidden, int32_t n_layers);
+/* same for a given flavour (the three functions above describe FB_FLAVOUR_V1) */
+int32_t fb_weight_slot_count_f(int32_t hidden, int32_t n_layers, int32_t flavour);
+int32_t fb_weight_slot_info_f(int32_t hidden, int32_t n_layers, int32_t flavour, int32_t i, char* name, int32_t name_cap,
+                              int64_t* rows, int64_t* cols, int64_t* offset);
+int64_t fb_weight_arena_elems_f(int32_t hidden, int32_t n_layers, int32_t flavour);
 
 /* [host] scratch sizes */
 int64_t fb_graph_workspace_bytes(const fb_model_params* p);

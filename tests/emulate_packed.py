@@ -19,9 +19,9 @@ HD = 128
 
 
 class Arena:
-    def __init__(self, sd, H, L):
-        self.a = pack_state_dict(sd, H, L)
-        self.s = {n: (r, c, o) for n, r, c, o in slots(H, L)}
+    def __init__(self, sd, H, L, flavour=0):
+        self.a = pack_state_dict(sd, H, L, flavour)
+        self.s = {n: (r, c, o) for n, r, c, o in slots(H, L, flavour)}
 
     def m(self, name):
         r, c, o = self.s[name]
@@ -68,10 +68,14 @@ def _radial(row, col, x, cplx_t, B):
     return d2 / nrm[cplx_t[row]]
 
 
-def forward_emulated(sd, cfg, batch):
+def forward_emulated(sd, cfg, batch, flavour=0):
+    """flavour 0: FABind v1 layout -> (X, H, stats); 1: FABind+ layout -> (X, H, stats, pair [P_total, H] packed rows)"""
     H = batch.H.shape[1]
     L = cfg.n_layers
-    W = Arena(sd, H, L)
+    plus = flavour == 1
+    W = Arena(sd, H, L, flavour)
+    Dp = (2 * H + 1 + 63) // 64 * 64
+    EPS = 1e-5
     lay = build_layout(batch.batch_id, batch.segment_id, batch.is_global, batch.mask, "cpu")
     o = lay.offs
     blob = lay.blob.numpy()
@@ -102,8 +106,10 @@ def forward_emulated(sd, cfg, batch):
         pp, cc = pc[p_off[b]:p_off[b + 1]], pc[c_off[b]:c_off[b + 1]]
         P0.append(F.linear((pp[:, None, :] * cc[None, :, :]).reshape(-1, H), W.m("il_o_w"), W.m("il_o_b")))
     P0 = torch.cat(P0)
-    raw = F.linear(P0, W.m("pb_w"), W.m("pb_b"))[:, :16 * L].reshape(-1, L, 2, 2, 4)
-    PB = raw[:, :, :, 0] * torch.sigmoid(raw[:, :, :, 1])          # [P, L, blk, head]
+    if not plus:
+        raw = F.linear(P0, W.m("pb_w"), W.m("pb_b"))[:, :16 * L].reshape(-1, L, 2, 2, 4)
+        PB = raw[:, :, :, 0] * torch.sigmoid(raw[:, :, :, 1])          # [P, L, blk, head]
+    pair_last = None
 
     (ctx_r, ctx_c), _ = _edges(x_state, lay_np, intra, inter, bonds_int)
     stats = []
@@ -190,15 +196,115 @@ def forward_emulated(sd, cfg, batch):
             dx = torch.zeros(N, 3).index_add_(0, int_r, (x[int_r] - x[int_c]) * (alpha * se)[:, None])
             return h, x + dx.clamp(-cmax, cmax)
 
+        def ln(z, gname, bname):
+            return F.layer_norm(z, (z.shape[-1],), W.m(gname), W.m(bname), EPS)
+
+        def row_stats(t, w=None):
+            return t.sum(1), (t * t).sum(1), (t * w).sum(1) if w is not None else None
+
+        def gcl_plus(pre, h, x, need_h=True):
+            rn = _radial(ctx_r, ctx_c, x, cplx_t, B)
+            s1, s2, _ = row_stats(h)
+            Pn = F.linear(h, W.m(pre + "e1_rc"))          # [N, 2*Dp]
+            D = 2 * H + 1
+            mu = (s1[ctx_r] + s1[ctx_c] + rn) / D
+            var = ((s2[ctx_r] + s2[ctx_c] + rn * rn) / D - mu * mu).clamp(min=0)
+            rstd = torch.rsqrt(var + EPS)
+            A1 = F.relu(rstd[:, None] * (Pn[ctx_r, :Dp] + Pn[ctx_c, Dp:] + rn[:, None] * W.m(pre + "e1_rad")
+                                         - mu[:, None] * W.m(pre + "e1_g")) + W.m(pre + "e1_c0"))
+            M = F.relu(F.linear(A1, W.m(pre + "e2_w"), W.m(pre + "e2_b")))
+            M2 = ln(M, pre + "cl_g", pre + "cl_b")
+            s = F.relu(F.linear(M2, W.m(pre + "c1_w"), W.m(pre + "c1_b"))) @ W.m(pre + "c2_w")
+            deg = torch.zeros(N).index_add_(0, ctx_r, torch.ones(ctx_r.numel())).clamp(min=1)
+            dx = torch.zeros(N, 3).index_add_(0, ctx_r, (x[ctx_r] - x[ctx_c]) * s[:, None]) / deg[:, None]
+            x_new = x + dx.clamp(-cmax, cmax)
+            if need_h:
+                agg = torch.zeros(N, H).index_add_(0, ctx_r, M)
+                t0 = ln(torch.cat([h, agg], 1), pre + "nl_g", pre + "nl_b")
+                t1 = F.relu(F.linear(t0, W.m(pre + "n1_w"), W.m(pre + "n1_b")))
+                h = h + F.relu(F.linear(t1, W.m(pre + "n2_w"), W.m(pre + "n2_b")))
+            return h, x_new
+
+        def att_plus(pre, pair_in, h, x):
+            h = h.clone()
+            raw = F.linear(pair_in, W.m(pre + "pb_w"), W.m(pre + "pb_b"))[:, :16].reshape(-1, 2, 2, 4)
+            PBl = raw[:, :, 0] * torch.sigmoid(raw[:, :, 1])          # [P, blk, head]
+            CAc = F.linear(h[:Nc], W.m(pre + "ca_c_w"), W.m(pre + "ca_c_b"))
+            CAp = F.linear(h[Nc:], W.m(pre + "ca_p_w"), W.m(pre + "ca_p_b"))
+            O = torch.zeros(N, HD)
+            for b in range(B):
+                cs, ps = slice(c_off[b], c_off[b + 1]), slice(p_off[b], p_off[b + 1])
+                psl = slice(p_off[b] - Nc, p_off[b + 1] - Nc)
+                nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
+                bias = PBl[pair_base[b]:pair_base[b + 1], 0].view(np1, nc1, 4)
+                O[ps] = rowatt(CAp[psl, :HD], CAp[psl, HD:], CAc[cs, :HD], CAc[cs, HD:2 * HD], bias)
+            h[Nc:] = h[Nc:] + F.linear(O[Nc:], W.m(pre + "o_p_w"), W.m(pre + "o_p_b"))
+            CAp2 = F.linear(h[Nc:], W.m(pre + "ca_p2_w"))
+            for b in range(B):
+                cs = slice(c_off[b], c_off[b + 1])
+                psl = slice(p_off[b] - Nc, p_off[b + 1] - Nc)
+                nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
+                bias = PBl[pair_base[b]:pair_base[b + 1], 1].view(np1, nc1, 4).transpose(0, 1)
+                O[cs] = rowatt(CAc[cs, 2 * HD:3 * HD], CAc[cs, 3 * HD:], CAp2[psl, :HD], CAp2[psl, HD:], bias)
+            h[:Nc] = h[:Nc] + F.linear(O[:Nc], W.m(pre + "o_c_w"), W.m(pre + "o_c_b"))
+            for t, sl in (("tc", slice(0, Nc)), ("tp", slice(Nc, N))):
+                t0 = ln(h[sl], pre + t + "l_g", pre + t + "l_b")
+                t1 = F.relu(F.linear(t0, W.m(pre + t + "1_w"), W.m(pre + t + "1_b")))
+                h[sl] = h[sl] + F.relu(F.linear(t1, W.m(pre + t + "2_w"), W.m(pre + t + "2_b")))
+            QK = F.linear(h, W.m(pre + "qk_w"), W.m(pre + "qk_b"))
+            # pair <- MLPwithLastAct(pair + inter32(p, c)) on every pair row
+            pi_all, ci_all = [], []
+            for b in range(B):
+                nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
+                pi_all.append(torch.arange(p_off[b], p_off[b + 1]).repeat_interleave(nc1))
+                ci_all.append(torch.arange(c_off[b], c_off[b + 1]).repeat(np1))
+            pi_all, ci_all = torch.cat(pi_all), torch.cat(ci_all)
+            t32 = QK[pi_all, 2 * H:2 * H + 32] * QK[ci_all, 2 * H + 32:2 * H + 64]
+            Zl = ln(pair_in + (t32 @ W.m(pre + "zo_w") + W.m(pre + "zo_b")), pre + "zl_g", pre + "zl_b")
+            Zh = F.relu(F.linear(Zl, W.m(pre + "pt1_w"), W.m(pre + "pt1_b")))
+            pair_out = F.relu(F.linear(Zh, W.m(pre + "pt2_w"), W.m(pre + "pt2_b")))
+            pb_dense = pair_out @ W.m(pre + "wb") + W.m(pre + "pt_c")
+            eb = cplx_t[int_r]
+            is_c = int_r < Nc
+            ci = torch.where(is_c, int_r, int_c)
+            pi = torch.where(is_c, int_c, int_r)
+            c_off_t, p_off_t = torch.from_numpy(c_off.astype(np.int64)), torch.from_numpy(p_off.astype(np.int64))
+            nc1_t = c_off_t[1:] - c_off_t[:-1]
+            pair = torch.from_numpy(pair_base.astype(np.int64))[eb] + (pi - p_off_t[eb]) * nc1_t[eb] + (ci - c_off_t[eb])
+            rn = _radial(int_r, int_c, x, cplx_t, B)
+            V, VC = QK[:, 2 * H + 128:3 * H + 128], QK[:, 3 * H + 128:]
+            logit = (QK[int_r, :H] * (QK[int_c, H:2 * H] + rn[:, None] * W.m(pre + "k_r"))).sum(1) + pb_dense[pair]
+            mx = torch.full((N,), float("-inf")).scatter_reduce(0, int_r, logit, reduce="amax")
+            e = (logit - mx[int_r]).exp()
+            alpha = e / torch.zeros(N).index_add_(0, int_r, e)[int_r]
+            v_r = W.m(pre + "v_r")
+            ve = V[int_c] + rn[:, None] * v_r
+            h = h + torch.zeros(N, H).index_add_(0, int_r, alpha[:, None] * ve)
+            s1, s2, s3 = row_stats(V, v_r)
+            acr = W.m(pre + "ac_r")
+            mu = (s1[int_c] + rn * acr[0]) / H
+            ex2 = (s2[int_c] + 2 * rn * s3[int_c] + rn * rn * acr[1]) / H
+            rstd = torch.rsqrt((ex2 - mu * mu).clamp(min=0) + EPS)
+            t = rstd[:, None] * (VC[int_c] + rn[:, None] * W.m(pre + "ac_u") - mu[:, None] * W.m(pre + "ac_g")) + W.m(pre + "ac_c0")
+            se = F.relu(t) @ W.m(pre + "ac2_w")
+            dx = torch.zeros(N, 3).index_add_(0, int_r, (x[int_r] - x[int_c]) * (alpha * se)[:, None])
+            return h, x + dx.clamp(-cmax, cmax), pair_out
+
+        pair_cur = P0
         for l in range(L):
-            h, x = gcl(f"gcl{l}.", h, x)
-            h, x = att(f"att{l}.", l, h, x)
+            if plus:
+                h, x = gcl_plus(f"gcl{l}.", h, x)
+                h, x, pair_cur = att_plus(f"att{l}.", pair_cur, h, x)
+            else:
+                h, x = gcl(f"gcl{l}.", h, x)
+                h, x = att(f"att{l}.", l, h, x)
             a, bb = las_int
             cur = ((x[a] - x[bb]) ** 2).sum(1)
             ref = ((xl[a] - xl[bb]) ** 2).sum(1)
             force = 2 * (cur - ref)[:, None] * (2 * (x[a] - x[bb]))
             x = x + (torch.zeros(N, 3).index_add_(0, bb, force) * cfg.geometry_reg_step_size).clamp(-lcl, lcl)
-        h, x = gcl("out.", h, x, need_h=last)
+        h, x = gcl_plus("out.", h, x, need_h=last) if plus else gcl("out.", h, x, need_h=last)
+        pair_last = pair_cur
         if last:
             h_final = F.linear(h, W.m("out_w"), W.m("out_b"))
         x_state = torch.where(moves[:, None], x, x_state)
@@ -206,4 +312,6 @@ def forward_emulated(sd, cfg, batch):
     X_out[permt, 0] = x_state
     H_out = torch.empty_like(batch.H)
     H_out[permt] = h_final
+    if plus:
+        return X_out, H_out, stats, pair_last
     return X_out, H_out, stats

@@ -16,15 +16,16 @@ def test_exports_match_header():
     for name in declared:
         assert hasattr(l, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
-    assert l.fb_abi_version() == 1
+    assert l.fb_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_weight_slots_are_disjoint_and_cover_arena():
     l = _lib.lib()
-    for hidden, L in [(128, 1), (512, 4), (64, 2)]:
-        s = slots(hidden, L)
-        end = 0
-        for name, r, c, off in s:
-            assert off >= end, name
-            end = off + r * c
-        assert end <= l.fb_weight_arena_elems(hidden, L)
+    for flavour in (0, 1):
+        for hidden, L in [(128, 1), (512, 4), (64, 2)]:
+            s = slots(hidden, L, flavour)
+            end = 0
+            for name, r, c, off in s:
+                assert off >= end, name
+                end = off + r * c
+            assert end <= l.fb_weight_arena_elems_f(hidden, L, flavour)

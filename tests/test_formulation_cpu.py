@@ -4,7 +4,7 @@ unmodified reference.  Validates fabind_b200/weights.py and fabind_b200/layout.p
 import pytest
 import torch
 
-from helpers import golden_files, load_golden, rel_err
+from helpers import golden_files, plus_golden_files, load_golden, rel_err
 from emulate_packed import forward_emulated
 
 
@@ -16,3 +16,28 @@ def test_refactored_formulation_matches_reference(path):
     assert stats == [int(e[1].shape[1]) for e in g["edges"]]
     assert rel_err(X, g["X"]) < 1e-5
     assert rel_err(H, g["H"]) < 1e-4
+
+
+def _dense_pair(pair_rows, lay_b, H):
+    """packed pair rows [P_total, H] -> the reference's dense [B, max Np', max Nc', H] block"""
+    B = len(lay_b)
+    mp, mc = max(n for n, _ in lay_b), max(c for _, c in lay_b)
+    out = torch.zeros(B, mp, mc, H)
+    o = 0
+    for b, (np1, nc1) in enumerate(lay_b):
+        out[b, :np1, :nc1] = pair_rows[o:o + np1 * nc1].view(np1, nc1, H)
+        o += np1 * nc1
+    return out
+
+
+@pytest.mark.parametrize("path", plus_golden_files(), ids=lambda p: p.split("/")[-1][:-3])
+def test_refactored_formulation_matches_reference_plus(path):
+    """FABind+ layout: LayerNorm folded through the hoisted first Linear (per-node sums -> per-edge statistics)."""
+    g, r, b, sd, cfg = load_golden(path)
+    with torch.no_grad():
+        X, H, stats, pair = forward_emulated(sd, cfg, b, flavour=1)
+    assert stats == [int(e[1].shape[1]) for e in g["edges"]]
+    assert rel_err(X, g["X"]) < 1e-5
+    assert rel_err(H, g["H"]) < 1e-4
+    dims = [(int(b.n_p[i]) + 1, int(b.n_c[i]) + 1) for i in range(len(b.n_c))]
+    assert rel_err(_dense_pair(pair, dims, H.shape[1]), g["pair"]) < 1e-4
