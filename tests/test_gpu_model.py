@@ -113,3 +113,20 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfabind_b200.so")
     with pytest.raises(RuntimeError):
         _lib.lib()
+
+
+def test_sharded_forward_real_module_single_rank():
+    """fabind_b200.shard (the N>1 host logic, gloo-tested on CPU) driving the CUDA module: taking complexes {0,2} out
+    of a ragged batch gives those complexes' rows of the full-batch result (complexes are independent)."""
+    from fabind_b200 import shard
+    hidden, L, IT = 64, 2, 2
+    b = make_batch(embed=hidden, n_complexes=3, seed=8, n_c_range=(8, 20), n_p_range=(30, 60))
+    m0 = EfficientMCAttModel(ref_shims.published_args(), hidden, hidden, 1, n_layers=L, n_iter=IT,
+                             normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m0.state_dict().items()}, 5)
+    m = _model(hidden, L, IT, sd)
+    fa = b.to("cuda").forward_args()
+    sub, idx = shard.take_complexes({k: (v.clone() if torch.is_tensor(v) else v) for k, v in fa.items()}, [0, 2])
+    Xs, Hs = m(**sub)
+    Xf, Hf = shard.sharded_forward(m, fa)
+    assert rel_err(Xs, Xf[idx]) < 1e-5 and rel_err(Hs, Hf[idx]) < 1e-5
