@@ -26,7 +26,10 @@ def published_args_plus(**over):
     """FABind+ published training/evaluation flags (FABind_plus/README.md:125-141) on top of the shared ones;
     argparse defaults from FABind_plus/fabind/utils/parsing.py:169-195."""
     a = published_args(mean_layers=5, use_ln_mlp=True, mlp_hidden_scale=1, dropout=0.1, mha_heads=4,
-                       rel_dis_pair_bias="no", inter_additional_mlp=False, only_last_LAS=False)
+                       rel_dis_pair_bias="no", inter_additional_mlp=False, only_last_LAS=False,
+                       # L2 wrapper FABindPlus (models/model.py): README.md:125-141 + parsing.py:106,158-160,196-199
+                       use_for_radius_pred="ligand", pocket_radius_buffer=5.0, min_pocket_radius=20.0, force_fix_radius=False,
+                       dis_map_thres=15.0, use_clustering=False, confidence_training=False, stack_mlp=False, geom_reg_steps=1)
     for k, v in over.items():
         setattr(a, k, v)
     return a

@@ -2,6 +2,8 @@
 // feature/coordinate assembly, LayerNorm, soft / hard pocket centre, pocket mask, ligand placement and the
 // pairwise-distance head.  C ABI at the bottom (declared in include/fabind_b200.h).
 #include "../../include/fabind_b200.h"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace fb {
@@ -152,17 +154,17 @@ __global__ void head_outer_kernel(const float* __restrict__ P, const float* __re
 __global__ void head_finish_kernel(const float* __restrict__ dot, int tiles, int stride, const float* __restrict__ b2,
                                    const float* __restrict__ pxyz, const float* __restrict__ lxyz,
                                    const int* __restrict__ poff, const int* __restrict__ coff, const int* __restrict__ qoff, int B,
-                                   float scale, float* __restrict__ y_pred, float* __restrict__ y_coords) {
+                                   float scale, float cap, float* __restrict__ y_pred, float* __restrict__ y_coords) {
   pdl_entry();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= qoff[B]) return;
   float s = b2[0];
   for (int t = 0; t < tiles; ++t) s += dot[(size_t)t * stride + q];
-  y_pred[q] = 10.0f / (1.0f + expf(-s));
+  y_pred[q] = cap / (1.0f + expf(-s));
   const int b = seg_find(qoff, B, q), loc = q - qoff[b], nc = coff[b + 1] - coff[b];
   const int pi = poff[b] + loc / nc, ci = coff[b] + loc % nc;
   const float dx = pxyz[3 * pi] - lxyz[3 * ci], dy = pxyz[3 * pi + 1] - lxyz[3 * ci + 1], dz = pxyz[3 * pi + 2] - lxyz[3 * ci + 2];
-  y_coords[q] = fminf(fmaxf(scale * sqrtf(dx * dx + dy * dy + dz * dz), 0.f), 10.f);
+  y_coords[q] = fminf(fmaxf(scale * sqrtf(dx * dx + dy * dy + dz * dz), 0.f), cap);
 }
 
 // flat pair distances min(|a_i - b_j|, cap) per complex (model.py:286-287: the dis_map label)
@@ -187,6 +189,100 @@ __global__ void dot_finish_kernel(const float* __restrict__ dot, int tiles, int 
   float s = bias ? bias[0] : 0.f;
   for (int t = 0; t < tiles; ++t) s += dot[(size_t)t * stride + m];
   out[m] = s;
+}
+
+
+// ---- FABind+ wrapper (FABind_plus/fabind/models/model.py::FABindPlus) -------------------------------------------------------
+// LayerNorm gathered from an arbitrary row list of a [*, D] fp32 table, output fp32 or bf16 (the A operand of the distance
+// head: rows pair[b, 1+i, 1+j, :] of the dense pair embedding, P/models/model.py:379-384)
+template <typename TO>
+__global__ void layernorm_rows_kernel(const float* __restrict__ x, const int* __restrict__ rows, int M, int D,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, TO* __restrict__ out) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* r = x + (size_t)(rows ? rows[warp] : warp) * D;
+  float s = 0.f;
+  for (int f = lane; f < D; f += 32) s += r[f];
+  const float mean = warp_sum(s) / (float)D;
+  float v = 0.f;
+  for (int f = lane; f < D; f += 32) { const float d = r[f] - mean; v = fmaf(d, d, v); }
+  const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)D + eps);
+  for (int f = lane; f < D; f += 32) {
+    const float y = (r[f] - mean) * rstd * gamma[f] + beta[f];
+    if constexpr (std::is_same<TO, float>::value) out[(size_t)warp * D + f] = y;
+    else out[(size_t)warp * D + f] = __float2bfloat16(y);
+  }
+}
+
+// out[b, :] = sum of rows off[b]..off[b+1] of src (the ligand-atom sum in front of the pocket radius head, model.py:110-114)
+__global__ void segment_sum_rows_kernel(const float* __restrict__ src, int D, const int* __restrict__ off, float* __restrict__ out) {
+  pdl_entry();
+  const int b = blockIdx.x;
+  for (int f = threadIdx.x; f < D; f += blockDim.x) {
+    float s = 0.f;
+    for (int i = off[b]; i < off[b + 1]; ++i) s += src[(size_t)i * D + f];
+    out[(size_t)b * D + f] = s;
+  }
+}
+
+// FABind+ pocket crop: radius_pred = relu(head output); crop radius = radius_pred * buffer (buffer <= 2) or + buffer, floored at
+// min_radius, or the fixed radius when fixed_radius >= 0 (model.py:223-231); then the same predicate / "<5 -> first 100" rule
+__global__ void __launch_bounds__(256) pocket_mask_r_kernel(const float* __restrict__ xyz, const int* __restrict__ off,
+                                                            const float* __restrict__ centers, const float* __restrict__ radius_raw,
+                                                            float buffer, float min_radius, float fixed_radius,
+                                                            uint8_t* __restrict__ keep, int* __restrict__ less5,
+                                                            float* __restrict__ radius_pred) {
+  pdl_entry();
+  __shared__ float red[32];
+  const int b = blockIdx.x, lo = off[b], hi = off[b + 1];
+  const float rp = fmaxf(radius_raw[b], 0.f);
+  float radius = buffer <= 2.0f ? __fmul_rn(rp, buffer) : __fadd_rn(rp, buffer);
+  if (radius < min_radius) radius = min_radius;
+  if (fixed_radius >= 0.f) radius = fixed_radius;
+  if (threadIdx.x == 0) radius_pred[b] = rp;
+  const float cx = centers[3 * b], cy = centers[3 * b + 1], cz = centers[3 * b + 2];
+  float n = 0.f;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float dx = __fsub_rn(xyz[3 * i], cx), dy = __fsub_rn(xyz[3 * i + 1], cy), dz = __fsub_rn(xyz[3 * i + 2], cz);
+    const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const bool k = d < radius;
+    keep[i] = k ? 1 : 0;
+    n += k ? 1.f : 0.f;
+  }
+  n = block_sum(n, red);
+  if (n < 5.f) {
+    for (int i = lo + threadIdx.x; i < min(hi, lo + 100); i += blockDim.x) keep[i] = 1;
+    if (threadIdx.x == 0) less5[b] = 1;
+  } else if (threadIdx.x == 0) less5[b] = 0;
+}
+
+// per-segment mean of [n,3] rows and the rows re-centred on it (pocket_coords - pocket_coords.mean(0), model.py:255-258)
+__global__ void __launch_bounds__(256) center_rows3_kernel(const float* __restrict__ xyz, const int* __restrict__ off,
+                                                           float* __restrict__ centered, float* __restrict__ mean) {
+  pdl_entry();
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float m[3] = {0.f, 0.f, 0.f};
+  for (int i = off[b] + threadIdx.x; i < off[b + 1]; i += blockDim.x) { m[0] += xyz[3 * i]; m[1] += xyz[3 * i + 1]; m[2] += xyz[3 * i + 2]; }
+  const float n = (float)(off[b + 1] - off[b]);
+  for (int k = 0; k < 3; ++k) m[k] = block_sum(m[k], red) / n;
+  if (threadIdx.x < 3) mean[3 * b + threadIdx.x] = m[threadIdx.x];
+  for (int i = off[b] + threadIdx.x; i < off[b + 1]; i += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) centered[3 * i + k] = xyz[3 * i + k] - m[k];
+  }
+}
+
+// out = xyz + sign * shift[segment]   (data.coords -= centre, model.py:257; prediction + pocket_center_bias, model.py:684)
+__global__ void shift_rows3_kernel(const float* __restrict__ xyz, const int* __restrict__ off, int B, const float* __restrict__ shift,
+                                   float sign, float* __restrict__ out) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= off[B]) return;
+  const int b = seg_find(off, B, i);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[3 * i + k] = xyz[3 * i + k] + sign * shift[3 * b + k];
 }
 
 }  // namespace fb
@@ -249,12 +345,64 @@ int32_t fb_head_outer(const float* pocket_ln, const float* comp_ln, const int32_
   return FB_OK;
 }
 
+int32_t fb_head_finish_cap(const float* dot, int32_t tiles, int32_t stride, const float* b2, const float* pocket_xyz,
+                           const float* lig_xyz, const int32_t* pocket_off, const int32_t* comp_off, const int32_t* pair_off,
+                           int32_t B, int32_t n_pairs, float scale, float cap, float* y_pred, float* y_coords, void* stream) {
+  if (n_pairs <= 0) return FB_OK;
+  fb_launch(head_finish_kernel, dim3((n_pairs + 255) / 256), dim3(256), 0, (cudaStream_t)stream, dot, tiles, stride, b2, pocket_xyz,
+            lig_xyz, pocket_off, comp_off, pair_off, B, scale, cap, y_pred, y_coords);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
 int32_t fb_head_finish(const float* dot, int32_t tiles, int32_t stride, const float* b2, const float* pocket_xyz,
                        const float* lig_xyz, const int32_t* pocket_off, const int32_t* comp_off, const int32_t* pair_off,
                        int32_t B, int32_t n_pairs, float scale, float* y_pred, float* y_coords, void* stream) {
-  if (n_pairs <= 0) return FB_OK;
-  fb_launch(head_finish_kernel, dim3((n_pairs + 255) / 256), dim3(256), 0, (cudaStream_t)stream, dot, tiles, stride, b2, pocket_xyz,
-            lig_xyz, pocket_off, comp_off, pair_off, B, scale, y_pred, y_coords);
+  return fb_head_finish_cap(dot, tiles, stride, b2, pocket_xyz, lig_xyz, pocket_off, comp_off, pair_off, B, n_pairs, scale, 10.0f,
+                            y_pred, y_coords, stream);
+}
+
+int32_t fb_layernorm_rows(const float* x, const int32_t* rows, int32_t M, int32_t D, const float* gamma, const float* beta, float eps,
+                          void* out, int32_t out_bf16, void* stream) {
+  if (M <= 0) return FB_OK;
+  if (out_bf16) fb_launch(layernorm_rows_kernel<__nv_bfloat16>, dim3((M * 32 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x, rows, M, D, gamma, beta, eps, (__nv_bfloat16*)out);
+  else fb_launch(layernorm_rows_kernel<float>, dim3((M * 32 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x, rows, M, D, gamma, beta, eps, (float*)out);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_segment_sum_rows(const float* src, int32_t D, const int32_t* off, int32_t B, float* out, void* stream) {
+  if (B <= 0) return FB_OK;
+  fb_launch(segment_sum_rows_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, src, D, off, out);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_pocket_mask_r(const float* xyz, const int32_t* prot_off, int32_t B, const float* centers, const float* radius_raw,
+                         float buffer, float min_radius, float fixed_radius, uint8_t* keep, int32_t* less5, float* radius_pred,
+                         void* stream) {
+  fb_launch(pocket_mask_r_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, xyz, prot_off, centers, radius_raw, buffer, min_radius,
+            fixed_radius, keep, less5, radius_pred);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_center_rows3(const float* xyz, const int32_t* off, int32_t B, float* centered, float* mean, void* stream) {
+  if (B <= 0) return FB_OK;
+  fb_launch(center_rows3_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, xyz, off, centered, mean);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_shift_rows3(const float* xyz, const int32_t* off, int32_t B, int32_t n_rows, const float* shift, float sign, float* out,
+                       void* stream) {
+  if (n_rows <= 0) return FB_OK;
+  fb_launch(shift_rows3_kernel, dim3((n_rows + 255) / 256), dim3(256), 0, (cudaStream_t)stream, xyz, off, B, shift, sign, out);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

@@ -3,3 +3,4 @@ LayerNorm MLPs, pair embedding propagated layer to layer).  Same class names, co
 keys as the reference; the forward pass is `fb_model_forward` with `flavour = FB_FLAVOUR_PLUS`."""
 from .att_model import ComplexGraph, EfficientMCAttModel  # noqa: F401
 from .egnn import MC_E_GCL, MC_Att_L, MCAttEGNN  # noqa: F401
+from .model import FABindPlus, get_model  # noqa: F401

@@ -202,6 +202,28 @@ int32_t fb_pair_dist(const float* pocket_xyz, const float* lig_xyz, const int32_
                      const int32_t* pair_off, int32_t B, int32_t n_pairs, float cap, float* out, void* stream);
 int32_t fb_dot_finish(const float* dot, int32_t tiles, int32_t stride, int32_t M, const float* bias, float* out, void* stream);
 
+/* ---- FABind+ wrapper ops (reference: FABind_plus/fabind/models/model.py, FABindPlus) ---- */
+/* LayerNorm of the rows x[rows[i], :] (rows == NULL: identity) to fp32 or bf16: the A operand of the MLP distance head on
+ * pair[:, 1:, 1:] (model.py:379-384) */
+int32_t fb_layernorm_rows(const float* x, const int32_t* rows, int32_t M, int32_t D, const float* gamma, const float* beta, float eps,
+                          void* out, int32_t out_bf16, void* stream);
+/* out[b,:] = sum of rows off[b]..off[b+1]: ligand-atom sum in front of pocket_radius_head (model.py:110-114) */
+int32_t fb_segment_sum_rows(const float* src, int32_t D, const int32_t* off, int32_t B, float* out, void* stream);
+/* per-complex crop radius from the radius head (relu, buffer rule, floor, optional fixed radius; model.py:223-231), then
+ * get_keepNode_tensor + the "<5 -> first 100" rule; radius_pred[b] = relu(radius_raw[b]) */
+int32_t fb_pocket_mask_r(const float* xyz, const int32_t* prot_off, int32_t B, const float* centers, const float* radius_raw,
+                         float buffer, float min_radius, float fixed_radius /* < 0: not forced */, uint8_t* keep, int32_t* less5,
+                         float* radius_pred, void* stream);
+/* pocket re-centred on its own mean + that mean = pocket_center_bias (model.py:255-258) */
+int32_t fb_center_rows3(const float* xyz, const int32_t* off, int32_t B, float* centered, float* mean, void* stream);
+/* out = xyz + sign * shift[segment]: data.coords -= centre (model.py:257), prediction + pocket_center_bias (model.py:684) */
+int32_t fb_shift_rows3(const float* xyz, const int32_t* off, int32_t B, int32_t n_rows, const float* shift, float sign, float* out,
+                       void* stream);
+/* fb_head_finish with the value range as a parameter (--dis-map-thres, model.py:385-390) */
+int32_t fb_head_finish_cap(const float* dot, int32_t tiles, int32_t stride, const float* b2, const float* pocket_xyz,
+                           const float* lig_xyz, const int32_t* pocket_off, const int32_t* comp_off, const int32_t* pair_off,
+                           int32_t B, int32_t n_pairs, float scale, float cap, float* y_pred, float* y_coords, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

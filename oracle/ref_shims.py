@@ -145,9 +145,9 @@ def _install_utils_stub():
     sys.modules["utils.utils"] = mod
 
 
-def load_reference_model_module():
-    """The reference's L2 wrapper `models.model` (v1), imported unmodified."""
-    mods = load_reference("v1")
+def load_reference_model_module(flavour="v1"):
+    """The reference's L2 wrapper `models.model` (v1: IaBNet_..., plus: FABindPlus), imported unmodified."""
+    mods = load_reference(flavour)
     _install_utils_stub()
     mods.model = importlib.import_module("models.model")
     return mods

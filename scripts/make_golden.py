@@ -162,8 +162,43 @@ def main_l2():
         print(name, [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd])
 
 
+def main_l2_plus():
+    """goldens for the FABind+ L2 wrapper (FABind_plus/fabind/models/model.py::FABindPlus): forward(stage=2) in eval mode
+    (13-tuple + the in-place shift of data.coords) and inference()"""
+    from fabind_b200.synthetic import make_docking_batch
+    mods = ref_shims.load_reference_model_module("plus")
+    cases = {
+        # published crop rule (radius = max(pred + 5, 20))
+        "l2plus_h64_p32_l2_it2": (64, 32, 2, 2, dict(n_complexes=3, seed=1), 51, dict()),
+        # per-complex predicted radius actually decides the crop (multiplicative buffer, no floor)
+        "l2plus_h32_p32_l1_it2_radius": (32, 32, 1, 2, dict(n_complexes=2, seed=2, L_range=(120, 220)), 52,
+                                         dict(pocket_radius_buffer=1.5, min_pocket_radius=0.0)),
+    }
+    for name, (emb, pemb, L, IT, bkw, wseed, over) in cases.items():
+        args = ref_shims.published_args_plus(mean_layers=L, n_iter=IT, **over)
+        m = mods.model.FABindPlus(args, emb, pemb).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        sd = det_state_dict(shapes, wseed)
+        if over:   # a radius head whose output lands in the 8-20 A range for these inputs
+            sd["pocket_radius_head.linear2.bias"] = torch.full_like(sd["pocket_radius_head.linear2.bias"], 9.0)
+        m.load_state_dict(sd, strict=True)
+        d = make_docking_batch(**bkw)
+        with torch.no_grad():
+            d2 = d.clone()
+            fwd = m(d2, stage=2)
+            inf = m.inference(d.clone())
+        torch.save({"recipe": dict(emb=emb, pemb=pemb, mean_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, args_over=over,
+                                   radius_bias=9.0 if over else None),
+                    "shapes": shapes, "forward": [t.clone() if torch.is_tensor(t) else t for t in fwd],
+                    "coords_after": d2.coords.clone(), "inference": inf[0].clone(), "torch": torch.__version__},
+                   os.path.join(OUT, name + ".pt"))
+        print(name, [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd], "radius", fwd[11].flatten().tolist())
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["v1", "l2", "plus"]
+    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus"]
+    if "l2plus" in which:
+        main_l2_plus()
     if "v1" in which:
         main()
     if "l2" in which:

@@ -51,3 +51,34 @@ def rel_err(a, b):
     tensor's own scale so that exact zeros do not blow it up."""
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def l2plus_golden_files():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "l2plus_*.pt")))
+
+
+def load_l2plus_golden(path):
+    from fabind_b200.config import published_args_plus
+    from fabind_b200.synthetic import make_docking_batch
+    g = torch.load(path, map_location="cpu", weights_only=False)
+    r = g["recipe"]
+    args = published_args_plus(mean_layers=r["mean_layers"], n_iter=r["n_iter"], **r["args_over"])
+    data = make_docking_batch(**r["batch"])
+    sd = det_state_dict(g["shapes"], r["weight_seed"])
+    if r["radius_bias"] is not None:
+        sd["pocket_radius_head.linear2.bias"] = torch.full_like(sd["pocket_radius_head.linear2.bias"], r["radius_bias"])
+    return g, r, args, data, sd
+
+
+def compare_tuple(mine, ref, tol=1e-5):
+    """element-wise comparison of a model.forward return tuple: exact for bool/int tensors and python scalars"""
+    assert len(mine) == len(ref)
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        if torch.is_tensor(b):
+            assert tuple(a.shape) == tuple(b.shape), (i, a.shape, b.shape)
+            if b.dtype in (torch.bool, torch.int32, torch.int64):
+                assert torch.equal(a.cpu().to(b.dtype), b), i
+            else:
+                assert rel_err(a, b) < tol, (i, rel_err(a, b))
+        else:
+            assert a == b, i

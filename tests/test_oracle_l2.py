@@ -54,3 +54,24 @@ def test_l2_oracle_vs_live_reference():
         if torch.is_tensor(b) and b.dtype.is_floating_point:
             assert rel_err(a, b) < 1e-5
     assert rel_err(mi[0], ri[0]) < 1e-5
+
+
+# ---- FABind+ wrapper (FABind_plus/fabind/models/model.py::FABindPlus) -------------------------------------------------
+from oracle import fabind_plus_oracle_l2 as l2p          # noqa: E402
+from helpers import l2plus_golden_files, load_l2plus_golden, compare_tuple   # noqa: E402
+
+
+@pytest.mark.parametrize("path", l2plus_golden_files(), ids=lambda p: p.split("/")[-1][:-3])
+def test_l2plus_oracle_matches_golden(path):
+    g, r, args, data, sd = load_l2plus_golden(path)
+    with torch.no_grad():
+        d2 = data.clone()
+        out = l2p.forward_stage2(sd, args, d2)
+        inf = l2p.inference(sd, args, data.clone())
+    compare_tuple(out, g["forward"])
+    assert rel_err(d2.coords, g["coords_after"]) < 1e-6          # in-place shift of the ground-truth pose (model.py:257)
+    assert rel_err(inf[0], g["inference"]) < 1e-5
+
+
+def test_l2plus_golden_present():
+    assert len(l2plus_golden_files()) >= 2
