@@ -13,6 +13,7 @@ int gemm_tc2_dot_tiles(int M, int N);
 int gemm_tc2_launch(const GemmArgs& g, cudaStream_t st);
 int gemm_tc2_launch_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t st);
 int gemm_tc3_launch(const GemmArgs& g, cudaStream_t st);
+int gemm_tc4_launch(const GemmArgs& g, cudaStream_t st);
 int gemm_tc3_launch_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t st);
 
 static int tc_version() {
@@ -31,6 +32,9 @@ int gemm_dot_tiles(int M, int N, int K, bool bf16_mode) {
 int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
   if (bf16_mode && gemm_tc_supported(g)) {
     if (tc_version() == 3) {
+      // long (edge-level / pair-level) problems: CTA pairs (tcgen05 cta_group::2), a third less operand traffic per MMA
+      const int r4 = gemm_tc4_launch(g, st);
+      if (r4 != FB_ERR_UNSUPPORTED) return r4;
       const int r = gemm_tc3_launch(g, st);
       if (r != FB_ERR_UNSUPPORTED) return r;
     }

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gemm(A, W, bias=None, act=0, res=None, A2=None, dotv=None, m_dev=None, bf16=False, want_cb=False,
-             force_simt=False):
+             force_simt=False, want_c=True):
     l = _lib.lib()
     dev = A.device
     M, K1 = A.shape
@@ -27,7 +27,7 @@ def run_gemm(A, W, bias=None, act=0, res=None, A2=None, dotv=None, m_dev=None, b
     g.act = act
     g.res, g.ldres = (res.data_ptr() if res is not None else None), N
     Cout = torch.full((M, N), float("nan"), device=dev)
-    g.C, g.ldc = Cout.data_ptr(), N
+    g.C, g.ldc = (Cout.data_ptr() if want_c else None), N
     Cb = torch.zeros((M, N), dtype=dt, device=dev) if want_cb else None
     g.Cb, g.ldcb = (Cb.data_ptr() if want_cb else None), N
     tiles = l.fb_gemm_dot_tiles(M, N, K1 + K2, int(bf16), int(force_simt))
@@ -186,3 +186,31 @@ def test_gemm_pair_matches_two_launches(shape, bf16):
     cb_tol = 1e-2 if bf16 else 2e-5
     for got, ref in ((Cb0, r0), (Cb1, r1)):
         assert float((got.double() - ref).abs().max() / ref.abs().max()) < cb_tol
+
+
+@pytest.mark.parametrize("M,N,K,act,use_dot,out", [
+    (45000, 512, 512, 1, False, "cb"),      # edge MLP second Linear (SiLU, bf16 store)
+    (45000, 512, 512, 1, True, "none"),     # coordinate head: row-dot epilogue only
+    (44904, 512, 1088, 2, False, "cb"),     # FABind+ edge MLP (K = 17 slabs, ReLU)
+    (16384 + 100, 1024, 512, 0, True, "c"),  # last pair tile: the second CTA has no live row; fp32 store
+    (99696, 512, 512, 2, True, "cb"),       # FABind+ pair transition (all pair rows), ReLU + row-dot + bf16 store
+    (20000, 256, 64, 0, False, "c"),        # one k-slab, one column tile
+])
+def test_gemm_cta_pair_kernel(M, N, K, act, use_dot, out):
+    """the cta_group::2 kernel (gemm_tc4.cu: 256x256 tiles on CTA pairs) on the shapes the stack sends it, against torch"""
+    dev = "cuda"
+    torch.manual_seed(3)
+    A = torch.randn(M, K, device=dev)
+    W = torch.randn(N, K, device=dev) / K ** 0.5
+    bias = torch.randn(N, device=dev)
+    dotv = torch.randn(N, device=dev) if use_dot else None
+    C1, Cb1, d1 = run_gemm(A, W, bias, act, None, None, dotv, bf16=True, want_cb=out == "cb", want_c=out == "c")
+    ref, dref = ref_gemm(A, W, bias, act, None, None, dotv, True)
+    scale = ref.abs().max()
+    if out == "c":
+        assert float((C1.double() - ref).abs().max() / scale) < 2e-5
+    if out == "cb":
+        assert float((Cb1.double() - ref).abs().max() / scale) < 1e-2
+        assert float((Cb1.double() - ref).abs().mean() / ref.abs().mean()) < 3e-3
+    if use_dot:
+        assert float((d1.double() - dref).abs().max() / dref.abs().max()) < 5e-5
