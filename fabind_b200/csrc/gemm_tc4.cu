@@ -230,11 +230,16 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(&tfull[a], (lt >> 1) & 1);
       tcgen05_fence_after();
       float dsum = 0.f;
+      // TMEM loads are software-pipelined: the load of chunk ch+1 is in flight while chunk ch is processed
+      uint32_t vv[2][32];
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * COLS);
+      tmem_ld32_issue(tbase, vv[0]);
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int c = half * COLS + ch * 32;      // column inside the tile
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), v);
+        uint32_t (&v)[32] = vv[ch & 1];
+        tmem_ld32_wait(v);
+        if (ch + 1 < NCH) tmem_ld32_issue(tbase + (uint32_t)((ch + 1) * 32), vv[(ch + 1) & 1]);
         if (ch == NCH - 1) {
           // accumulator stage drained: hand it back to the leader's MMA warp before the stores
           tcgen05_fence_before();
