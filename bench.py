@@ -300,7 +300,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("gemm_edge_dram_bytes_per_launch")
-    roofline = {"kernel": "edge-MLP GEMM (gemm_tc / gemm_simt), M=E_ctx N=K=512", "bound": "tensor", "achieved": achieved,
+    roofline = {"kernel": "edge-MLP GEMM (tc4::gemm_tc4_kernel, tcgen05 cta_group::2 CTA pairs, 256x256 tiles), M=E_ctx N=K=512", "bound": "tensor", "achieved": achieved,
                 "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"], "traffic": traffic,
                 "peak_source": peaks["src"] + ", sustained figure (kernel timed inside a long step)",
                 "algorithmic_flops_per_launch": flops, "avg_launch_ms": avg_ms,
