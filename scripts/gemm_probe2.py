@@ -19,9 +19,9 @@ for (M, N, K, act, both) in [(3712, 512, 512, 0, False), (3712, 512, 512, 0, Tru
     g.M, g.N = M, N; g.bf16_mode = 1
     for _ in range(3):
         l.fb_gemm(C.byref(g), st)
-    dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(8192, dtype=torch.int64, device=dev)
     l.fb_gemm_set_debug(C.c_void_p(dbg.data_ptr())); l.fb_gemm(C.byref(g), st); torch.cuda.synchronize(); l.fb_gemm_set_debug(None)
-    d = dbg.view(-1, 8).cpu().double(); d = d[d[:, 0] > 0]
+    d = dbg[:148 * 8].view(-1, 8).cpu().double(); d = d[d[:, 0] > 0]
     rel = d[:, 1:7] - d[:, 0:1]
     names = ["setup done", "first TMA landed", "tile0 MMA issued", "tile0 accum ready", "tile0 epilogue done", "exit"]
     print(json.dumps(dict(M=M, N=N, K=K, act=act, both=both, ctas=int(d.shape[0]),
