@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfabind_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "CUDA launch error", -4: "unsupported configuration"}
 
@@ -30,6 +30,7 @@ class ModelParams(C.Structure):
         ("X_out", C.c_void_p), ("H_out", C.c_void_p), ("stats", C.c_void_p),
         ("trace_h", C.c_void_p), ("trace_x", C.c_void_p),
         ("flavour", C.c_int32), ("pair_out", C.c_void_p),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint32), ("dropout_colonly", C.c_int32),
     ]
 
 
@@ -57,6 +58,8 @@ class GemmParams(C.Structure):
         ("dotv", C.c_void_p), ("dot_out", C.c_void_p), ("dot_stride", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32), ("m_dev", C.c_void_p),
         ("bf16_mode", C.c_int32), ("force_simt", C.c_int32),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_site", C.c_uint32), ("drop_row0", C.c_int32),
+        ("drop_colonly", C.c_int32),
     ]
 
 

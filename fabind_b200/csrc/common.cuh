@@ -34,6 +34,44 @@ __device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
 
 bool pdl_enabled();   // forward.cu (FB_PDL=0 disables the launch attribute)
 
+// ---- dropout (FABind+ sampling mode: the reference runs the whole model in train() mode, P/test_sampling_fabind.py:118-124) ----
+// Counter-based masks: keep(seed, site, row, col) is a pure function, so every kernel that touches an activation can evaluate
+// it in place (GEMM epilogues, edge kernels) and a CPU restatement can reproduce it bit for bit (tests/emulate_packed.py).
+//   site = which nn.Dropout of the reference (layer / sub-module, see forward.cu::Site), row = internal row id of the
+//   activation (node / context edge / interface edge / pair row), col = feature column.  colonly = 1 ignores the row: a
+//   mask that is invariant to row order, used to pin the PLACEMENT of every mask against the unmodified reference.
+struct DropCfg {
+  float p = 0.f, scale = 1.f;      // scale = 1 / (1 - p)
+  uint32_t thresh = 0;             // keep iff hash >= thresh,  thresh = p * 2^32
+  uint32_t seed = 0, site = 0;
+  int row0 = 0;                    // added to the kernel-local row index
+  int colonly = 0;
+};
+__host__ __device__ __forceinline__ uint32_t fb_drop_hash(uint32_t seed, uint32_t site, uint32_t row, uint32_t col) {
+  uint32_t x = seed ^ (site * 0x9E3779B1u);
+  x ^= row * 0x85EBCA77u;
+  x = ((x << 13) | (x >> 19)) * 0xC2B2AE3Du;
+  x ^= col * 0x27D4EB2Fu;
+  x ^= x >> 15; x *= 0x2C1B3C6Du;
+  x ^= x >> 12; x *= 0x297A2D39u;
+  x ^= x >> 15;
+  return x;
+}
+__device__ __forceinline__ float drop_apply(float x, const DropCfg& d, int row, int col) {
+  const uint32_t h = fb_drop_hash(d.seed, d.site, d.colonly ? 0u : (uint32_t)(row + d.row0), (uint32_t)col);
+  return h >= d.thresh ? x * d.scale : 0.f;
+}
+inline DropCfg make_drop(float p, uint32_t seed, uint32_t site, int row0, int colonly) {
+  DropCfg d;
+  if (p > 0.f) {
+    d.p = p; d.scale = 1.0f / (1.0f - p);
+    const double t = (double)p * 4294967296.0;
+    d.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    d.seed = seed; d.site = site; d.row0 = row0; d.colonly = colonly;
+  }
+  return d;
+}
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices have it for a kernel
 template <typename K>
 inline bool ensure_smem_optin(K kernel, int bytes, unsigned long long& done_mask) {

@@ -337,6 +337,18 @@ struct Run {
   }
   int gemm_cat = CAT_GEMM_NODE;
 
+  // ---- dropout sites of the FABind+ stack (one per nn.Dropout of the reference; tests/emulate_packed.py and the patched
+  // reference of scripts/make_golden.py use the same numbering): site = (layer + 1) * 32 + local, layer = -1 for the stack's
+  // own dropout, n_layers for out_layer; the iteration enters through the seed
+  enum Site { S_EDGE1 = 0, S_EDGE2, S_GCOORD, S_NODE1, S_NODE2, S_PATT, S_CATT, S_PTR1, S_PTR2, S_CTR1, S_CTR2, S_PAIR1, S_PAIR2,
+              S_AGG, S_ACOORD, S_IN, S_OUT };
+  int cur_it = 0, cur_layer = -1;
+  DropCfg dr(int local, int row0 = 0) const {
+    return make_drop(p.dropout_p, p.dropout_seed + 0x632BE5ABu * (uint32_t)cur_it, (uint32_t)((cur_layer + 1) * 32 + local), row0,
+                     p.dropout_colonly);
+  }
+  static GemmArgs wd(GemmArgs a, const DropCfg& d) { a.drop = d; return a; }
+
   // arguments of  C = act(A W^T + b)  with the usual optional extras
   GemmArgs mk(const void* A, int lda, int K, int64_t w_off, int Nout, int64_t b_off, int act, int M, float* C, int ldc,
               void* Cb, int ldcb, const float* res = nullptr, int ldres = 0, const void* A2 = nullptr, int lda2 = 0,
@@ -455,14 +467,15 @@ struct Run {
     gemm(b.hT, H, H, gw.e1_rc, 2 * Dp, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * Dp);
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_edge_pre_plus(E, H, Dp, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.hstat, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_g),
-                               F(gw.e1_c0), LN_EPS, b.A1, bf, st);
+                               F(gw.e1_c0), LN_EPS, b.A1, bf, st, dr(S_EDGE1));
     });
     gemm_cat = CAT_GEMM_EDGE;
-    gemm(b.A1, Dp, Dp, gw.e2_w, H, gw.e2_b, FB_ACT_RELU, E, nullptr, 0, b.M, H);
+    gemm(wd(mk(b.A1, Dp, Dp, gw.e2_w, H, gw.e2_b, FB_ACT_RELU, E, nullptr, 0, b.M, H), dr(S_EDGE2)));
     // coord_mlp = MLPwoBias: LayerNorm on the edge message, Linear + ReLU, Linear(H,1) as the row-dot epilogue
     stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(b.M, true, H, H, nullptr, 0, 0, E, F(gw.cl_g), F(gw.cl_b), LN_EPS, b.M2, H, bf, st); });
     const int tiles = gemm_dot_tiles(E, H, H, bf);
-    gemm(b.M2, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_RELU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
+    gemm(wd(mk(b.M2, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_RELU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E),
+            dr(S_GCOORD)));
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st);
     });
@@ -470,8 +483,8 @@ struct Run {
     if (need_h) {
       // node_mlp = MLPwithLastAct on [h | agg], residual
       stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(b.h, false, H, H, b.agg, H, H, N, F(gw.nl_g), F(gw.nl_b), LN_EPS, b.TH, 2 * H, bf, st); });
-      gemm(b.TH, 2 * H, 2 * H, gw.n1_w, 2 * H, gw.n1_b, FB_ACT_RELU, N, nullptr, 0, b.TH2, 2 * H);
-      gemm(b.TH2, 2 * H, 2 * H, gw.n2_w, H, gw.n2_b, FB_ACT_RELU, N, b.h, H, b.hT, H, b.h, H);
+      gemm(wd(mk(b.TH, 2 * H, 2 * H, gw.n1_w, 2 * H, gw.n1_b, FB_ACT_RELU, N, nullptr, 0, b.TH2, 2 * H), dr(S_NODE1)));
+      gemm(wd(mk(b.TH2, 2 * H, 2 * H, gw.n2_w, H, gw.n2_b, FB_ACT_RELU, N, b.h, H, b.hT, H, b.h, H), dr(S_NODE2)));
     }
   }
 
@@ -492,23 +505,23 @@ struct Run {
     stage(CAT_ATTENTION, [&] {
       return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD, b.PB, b.O, HD, bf, st);
     });
-    gemm(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
+    gemm(wd(mk(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H), dr(S_PATT, Nc)));
     gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
     const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
     stage(CAT_ATTENTION, [&] {
       return row_attention(g, 0, p.max_c, p.max_p, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
                            b.PB + P * 4, b.O, HD, bf, st);
     });
-    gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
+    gemm(wd(mk(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H), dr(S_CATT)));
     // transitions = MLPwithLastAct (LN, Linear+ReLU, Linear+ReLU), residual
     void* Tnp = at(b.Tn, (size_t)Nc * H);
     void* THp = at(b.TH, (size_t)Nc * H);
     stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(b.h, false, H, H, nullptr, 0, 0, Nc, F(aw.tcl_g), F(aw.tcl_b), LN_EPS, b.Tn, H, bf, st); });
     stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(hp, false, H, H, nullptr, 0, 0, Np, F(aw.tpl_g), F(aw.tpl_b), LN_EPS, Tnp, H, bf, st); });
-    gemm_pair(mk(b.Tn, H, H, aw.tc1_w, H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, H),
-              mk(Tnp, H, H, aw.tp1_w, H, aw.tp1_b, FB_ACT_RELU, Np, nullptr, 0, THp, H));
-    gemm_pair(mk(b.TH, H, H, aw.tc2_w, H, aw.tc2_b, FB_ACT_RELU, Nc, b.h, H, b.hT, H, b.h, H),
-              mk(THp, H, H, aw.tp2_w, H, aw.tp2_b, FB_ACT_RELU, Np, hp, H, hTp, H, hp, H));
+    gemm_pair(wd(mk(b.Tn, H, H, aw.tc1_w, H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, H), dr(S_CTR1)),
+              wd(mk(Tnp, H, H, aw.tp1_w, H, aw.tp1_b, FB_ACT_RELU, Np, nullptr, 0, THp, H), dr(S_PTR1, Nc)));
+    gemm_pair(wd(mk(b.TH, H, H, aw.tc2_w, H, aw.tc2_b, FB_ACT_RELU, Nc, b.h, H, b.hT, H, b.h, H), dr(S_CTR2)),
+              wd(mk(THp, H, H, aw.tp2_w, H, aw.tp2_b, FB_ACT_RELU, Np, hp, H, hTp, H, hp, H), dr(S_PTR2, Nc)));
     // q | k | inter32_p | inter32_c | pad  ||  v | vc   (vc = (coord_mlp.linear1 * gamma) applied to v, folded)
     const int ldqk = 2 * H + QKX;
     gemm(b.hT, H, H, aw.qk_w, ldqk + 2 * H, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, b.VT, 2 * H, nullptr, 0, nullptr, 0, 0, -1,
@@ -518,9 +531,10 @@ struct Run {
       return pair_zin_plus(g, (int)P, H, pair_in, b.QK + 2 * H, ldqk, F(aw.zo_w), F(aw.zo_b), F(aw.zl_g), F(aw.zl_b), LN_EPS, b.Zl, bf, st);
     });
     gemm_cat = CAT_GEMM_PAIR;
-    gemm(b.Zl, H, H, aw.pt1_w, H, aw.pt1_b, FB_ACT_RELU, (int)P, nullptr, 0, b.Zh, H);
+    gemm(wd(mk(b.Zl, H, H, aw.pt1_w, H, aw.pt1_b, FB_ACT_RELU, (int)P, nullptr, 0, b.Zh, H), dr(S_PAIR1)));
     const int tilesP = gemm_dot_tiles((int)P, H, H, bf);
-    gemm(b.Zh, H, H, aw.pt2_w, H, aw.pt2_b, FB_ACT_RELU, (int)P, nullptr, 0, pair_out, H, nullptr, 0, nullptr, 0, 0, aw.wb, b.dotP, (int)P);
+    gemm(wd(mk(b.Zh, H, H, aw.pt2_w, H, aw.pt2_b, FB_ACT_RELU, (int)P, nullptr, 0, pair_out, H, nullptr, 0, nullptr, 0, 0, aw.wb, b.dotP,
+               (int)P), dr(S_PAIR2)));
     gemm_cat = CAT_GEMM_NODE;
     stage(CAT_ATTENTION, [&] { return pair_bias_all((int)P, b.dotP, tilesP, (int)P, F(aw.pt_c), b.pb_dense, st); });
     // interfacial attention; coordinate head = MLPwoBias on v_e with its LayerNorm folded (per-node sums of v)
@@ -529,7 +543,7 @@ struct Run {
     stage(CAT_ATTENTION, [&] {
       return inter_attention(g, p.cap_int, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac_c0),
                              F(aw.ac2_w), b.radi, b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, b.lgt,
-                             b.sde, bf, st, F(aw.ac_g), F(aw.ac_r), b.vstat, LN_EPS);
+                             b.sde, bf, st, F(aw.ac_g), F(aw.ac_r), b.vstat, LN_EPS, dr(S_ACOORD), dr(S_AGG));
     });
   }
 
@@ -604,12 +618,14 @@ struct Run {
       stage(CAT_GRAPH_MISC, [&] { return graph_build_inter(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
       if (p.stats) cudaMemcpyAsync(p.stats + it, g.int_rowptr + N, sizeof(int), cudaMemcpyDeviceToDevice, st);
       gemm_cat = CAT_GEMM_NODE;
-      gemm(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H);
+      cur_it = it; cur_layer = -1;
+      gemm(wd(mk(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H), dr(S_IN)));
       const float* xc = b.x_state;
       float* bufs[2] = {b.xa, b.xb};
       int k = 0;
       const void* pair_cur = b.P0;   // FABind+: every iteration restarts from pair_embed0 (P/models/att_model.py:209-218)
       for (int l = 0; l < p.n_layers; ++l) {
+        cur_layer = l;
         if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true); else run_gcl(w.gcl[l], xc, bufs[k], true);
         xc = bufs[k]; k ^= 1;
         if (last) tap(2 * l, xc);
@@ -627,12 +643,15 @@ struct Run {
       }
       // the out-layer node update and linear_out only matter on the last iteration
       // (att_model.py:232: non-final iterations discard H)
+      cur_layer = p.n_layers;
       if (plus) run_gcl_plus(w.gclp[p.n_layers], xc, bufs[k], last); else run_gcl(w.gcl[p.n_layers], xc, bufs[k], last);
       xc = bufs[k];
       if (last && plus && p.pair_out)
         stage(CAT_GRAPH_MISC, [&] { return pair_unpack(g, (int)P, H, p.max_p, p.max_c, pair_cur, p.pair_out, bf, st); });
       if (last) {
         gemm_cat = CAT_GEMM_NODE;
+        cur_layer = -1;
+        if (p.dropout_p > 0.f) stage(CAT_EDGE_ELEMWISE, [&] { return dropout_rows(b.h, b.hT, N, H, bf, dr(S_OUT), st); });
         gemm(b.hT, H, H, w.out_w, H, w.out_b, FB_ACT_NONE, N, b.Hfin, H, nullptr, 0);
         stage(CAT_GRAPH_MISC, [&] { return permute_out_h(g, b.Hfin, H, p.H_out, st); });
       }
@@ -647,7 +666,8 @@ using namespace fb;
 
 static bool params_ok(const fb_model_params* p) {
   return p && p->N > 0 && p->B > 0 && p->hidden > 0 && (p->hidden % 8) == 0 && p->hidden <= 512 && p->n_layers >= 0 &&
-         p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot <= p->N && (p->flavour == FB_FLAVOUR_V1 || p->flavour == FB_FLAVOUR_PLUS);
+         p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot <= p->N && (p->flavour == FB_FLAVOUR_V1 || p->flavour == FB_FLAVOUR_PLUS) &&
+         p->dropout_p >= 0.f && p->dropout_p < 1.f && !(p->dropout_p > 0.f && p->flavour != FB_FLAVOUR_PLUS);
 }
 
 extern "C" {
@@ -818,6 +838,7 @@ static GemmArgs gemm_args_from(const fb_gemm_params* q) {
   a.bias = q->bias; a.act = q->act; a.res = q->res; a.ldres = q->ldres; a.C = q->C; a.ldc = q->ldc;
   a.Cb = q->Cb; a.ldcb = q->ldcb; a.dotv = q->dotv; a.dot_out = q->dot_out; a.dot_stride = q->dot_stride;
   a.M = q->M; a.N = q->N; a.m_dev = q->m_dev;
+  a.drop = make_drop(q->drop_p, q->drop_seed, q->drop_site, q->drop_row0, q->drop_colonly);
   return a;
 }
 

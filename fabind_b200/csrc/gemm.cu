@@ -38,6 +38,7 @@ int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st) {
       const int r = gemm_tc3_launch(g, st);
       if (r != FB_ERR_UNSUPPORTED) return r;
     }
+    if (g.drop.p > 0.f) return gemm_simt_launch(g, bf16_mode, st);   // only v3 / v4 / SIMT carry the dropout epilogue
     if (tc_version() >= 2 && gemm_tc2_shape_ok(g.N)) return gemm_tc2_launch(g, st);
     if (g.n_split > 0) return gemm_simt_launch(g, bf16_mode, st);   // v1 kernel has no column routing
     return gemm_tc_launch(g, st);
@@ -49,7 +50,7 @@ int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, bool bf16_mode, cud
   static const bool group = [] { const char* e = getenv("FB_NO_GROUP"); return !(e && atoi(e)); }();
   if (group && bf16_mode && tc_version() >= 2 && gemm_tc_supported(g0) && gemm_tc_supported(g1)) {
     int r = tc_version() == 3 ? gemm_tc3_launch_pair(g0, g1, st) : FB_ERR_UNSUPPORTED;
-    if (r == FB_ERR_UNSUPPORTED) r = gemm_tc2_launch_pair(g0, g1, st);
+    if (r == FB_ERR_UNSUPPORTED && g0.drop.p <= 0.f && g1.drop.p <= 0.f) r = gemm_tc2_launch_pair(g0, g1, st);
     if (r != FB_ERR_UNSUPPORTED) return r;
   }
   const int r = gemm_launch(g0, bf16_mode, st);

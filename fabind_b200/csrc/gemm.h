@@ -20,6 +20,7 @@ struct GemmArgs {
   int M = 0, N = 0;
   int n_split = 0;                                       // >0: columns < n_split go to C only, the rest to Cb only (at column n - n_split)
   const int* m_dev = nullptr;                            // optional device-side row count (<= M)
+  DropCfg drop;                                          // dropout after the activation, before residual / row-dot / stores
 };
 
 // number of N tiles (= number of row-dot partials per row) the kernel chosen for `bf16` will use

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
         float v = acc[i][j];
         if (g.bias) v += g.bias[n];
         v = apply_act_rt(v, g.act);
+        if (g.drop.p > 0.f) v = drop_apply(v, g.drop, m, n);
         if (g.res) v += g.res[(size_t)m * g.ldres + n];
         if (g.n_split > 0) {
           if (n < g.n_split) { if (g.C) g.C[(size_t)m * g.ldc + n] = v; }

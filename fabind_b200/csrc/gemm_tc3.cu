@@ -46,6 +46,7 @@ struct Prob {
   int has_res, has_c, has_cb;
   const float* dotv; float* dot_out; int dot_stride;
   int n_split;
+  DropCfg drop;
 };
 struct Params {
   Prob q0, q1;
@@ -259,6 +260,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           else if (pp.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
+        if (pp.drop.p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = drop_apply(o[j], pp.drop, lrow0 + lane, n0 + c + j);
+        }
         if (use_dot) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) dsum = fmaf(__shfl_sync(0xffffffffu, dv[ch], j), o[j], dsum);
@@ -337,6 +342,7 @@ static bool fill_prob(Prob& q, const GemmArgs& g, int m_begin, CUtensorMap* mc, 
   q.has_res = g.res != nullptr; q.has_c = g.C != nullptr; q.has_cb = g.Cb != nullptr;
   q.dotv = g.dotv; q.dot_out = g.dot_out; q.dot_stride = g.dot_stride;
   q.n_split = g.n_split;
+  q.drop = g.drop;
   const int nc = g.n_split > 0 ? g.n_split : g.N, ncb = g.n_split > 0 ? g.N - g.n_split : g.N;
   if (g.C && !tc_make_map_out(mc, g.C, true, (uint64_t)g.M, (uint64_t)nc, (uint64_t)g.ldc)) return false;
   if (g.Cb && !tc_make_map_out(mcb, g.Cb, false, (uint64_t)g.M, (uint64_t)ncb, (uint64_t)g.ldcb)) return false;

@@ -43,6 +43,7 @@ struct Params {
   const float* dotv; float* dot_out; int dot_stride;
   int n_split;
   const int* m_dev;
+  DropCfg drop;
 };
 
 struct Smem {
@@ -255,6 +256,10 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
+        if (p.drop.p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = drop_apply(o[j], p.drop, lrow0 + lane, n0 + c + j);
+        }
         if (use_dot) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) dsum = fmaf(__shfl_sync(0xffffffffu, dv[ch], j), o[j], dsum);
@@ -335,7 +340,7 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
   Params p;
   p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK;
   p.bias = g.bias; p.act = g.act; p.has_c = g.C != nullptr; p.has_cb = g.Cb != nullptr;
-  p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride; p.n_split = g.n_split; p.m_dev = g.m_dev;
+  p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride; p.n_split = g.n_split; p.m_dev = g.m_dev; p.drop = g.drop;
   const int tiles = ((g.M + PM - 1) / PM) * (g.N / BN);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
   fb_launch(gemm_tc4_kernel, dim3(2 * pairs), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, mc, mcb, p);

@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, con
                                                           const float* __restrict__ vstat, float eps,
                                                           const float* __restrict__ rad, const float* __restrict__ norm,
                                                           const float* __restrict__ pb_dense, float* __restrict__ logit,
-                                                          float* __restrict__ sdot_out) {
+                                                          float* __restrict__ sdot_out, DropCfg dc) {
   constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: one-MUFU SiLU
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -685,7 +685,12 @@ __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, con
           const float4 gg = *reinterpret_cast<const float4*>(il_w + 4 * H + f);
           const float t0 = fmaf(rstd, vc.x + fmaf(rn, uu.x, -mu * gg.x), bb.x), t1 = fmaf(rstd, vc.y + fmaf(rn, uu.y, -mu * gg.y), bb.y);
           const float t2 = fmaf(rstd, vc.z + fmaf(rn, uu.z, -mu * gg.z), bb.z), t3 = fmaf(rstd, vc.w + fmaf(rn, uu.w, -mu * gg.w), bb.w);
-          sd += w2.x * fmaxf(t0, 0.f) + w2.y * fmaxf(t1, 0.f) + w2.z * fmaxf(t2, 0.f) + w2.w * fmaxf(t3, 0.f);
+          float r0 = fmaxf(t0, 0.f), r1 = fmaxf(t1, 0.f), r2 = fmaxf(t2, 0.f), r3 = fmaxf(t3, 0.f);
+          if (dc.p > 0.f) {   // coord_mlp.dropout between ReLU and the bias-free Linear (P/models/model_utils.py:70-71)
+            r0 = drop_apply(r0, dc, e, f); r1 = drop_apply(r1, dc, e, f + 1);
+            r2 = drop_apply(r2, dc, e, f + 2); r3 = drop_apply(r3, dc, e, f + 3);
+          }
+          sd += w2.x * r0 + w2.y * r1 + w2.z * r2 + w2.w * r3;
         } else {
           const float t0 = vc.x + fmaf(rn, uu.x, bb.x), t1 = vc.y + fmaf(rn, uu.y, bb.y);
           const float t2 = vc.z + fmaf(rn, uu.z, bb.z), t3 = vc.w + fmaf(rn, uu.w, bb.w);
@@ -706,7 +711,7 @@ __global__ void __launch_bounds__(128) inter_aggregate_kernel(GraphDev g, int H,
                                                               const float* __restrict__ norm, const float* __restrict__ logit,
                                                               const float* __restrict__ sdot, const float* __restrict__ x, float cmax,
                                                               float* __restrict__ h, T* __restrict__ hT, float* __restrict__ x_out,
-                                                              float* __restrict__ att) {
+                                                              float* __restrict__ att, DropCfg da) {
   pdl_entry();
   const int r = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lo = g.int_rowptr[r], hi = g.int_rowptr[r + 1];
@@ -772,7 +777,12 @@ __global__ void __launch_bounds__(128) inter_aggregate_kernel(GraphDev g, int H,
   arn *= inv_norm;
   const float4 vr = ld4(v_r + f);
   float4 hv = ld4(h + (size_t)r * H + f);
-  hv.x += fmaf(arn, vr.x, acc.x); hv.y += fmaf(arn, vr.y, acc.y); hv.z += fmaf(arn, vr.z, acc.z); hv.w += fmaf(arn, vr.w, acc.w);
+  float4 ag = make_float4(fmaf(arn, vr.x, acc.x), fmaf(arn, vr.y, acc.y), fmaf(arn, vr.z, acc.z), fmaf(arn, vr.w, acc.w));
+  if (da.p > 0.f) {   // MC_Att_L.node_model: agg = dropout(agg) (P/models/egnn.py:204)
+    ag.x = drop_apply(ag.x, da, r, f); ag.y = drop_apply(ag.y, da, r, f + 1);
+    ag.z = drop_apply(ag.z, da, r, f + 2); ag.w = drop_apply(ag.w, da, r, f + 3);
+  }
+  hv.x += ag.x; hv.y += ag.y; hv.z += ag.z; hv.w += ag.w;
   st4(h + (size_t)r * H + f, hv);
   if (hT) st4(hT + (size_t)r * H + f, hv);
 }
@@ -781,25 +791,25 @@ int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int 
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st,
-                    const float* ac_g, const float* ac_r, const float* vstat, float eps) {
+                    const float* ac_g, const float* ac_r, const float* vstat, float eps, DropCfg drop_coord, DropCfg drop_agg) {
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   const int grid1 = std::max(1, std::min(148 * 8, (cap_int + 7) / 8));
   const bool plus = vstat != nullptr;
 #define FB_IL(T, VEC)                                                                                                        \
   do {                                                                                                                       \
     if (plus) fb_launch(inter_logit_kernel<T, VEC, true>, dim3(grid1), dim3(256), 5 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
-                        ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws);                                \
+                        ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord);                    \
     else fb_launch(inter_logit_kernel<T, VEC, false>, dim3(grid1), dim3(256), 4 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
-                   ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws);                                     \
+                   ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord);                         \
   } while (0)
   if (bf16_mode) {
     if (H <= 128) FB_IL(bf16, 1); else if (H <= 256) FB_IL(bf16, 2); else FB_IL(bf16, 4);
     fb_launch(inter_aggregate_kernel<bf16>, dim3(g.N), dim3(128), 0, st, g, H, (const bf16*)V, ldv, v_r, rad, norm, logit_ws, sdot_ws, x,
-              cmax, h, (bf16*)hT, x_out, att);
+              cmax, h, (bf16*)hT, x_out, att, drop_agg);
   } else {
     if (H <= 128) FB_IL(float, 1); else if (H <= 256) FB_IL(float, 2); else FB_IL(float, 4);
     fb_launch(inter_aggregate_kernel<float>, dim3(g.N), dim3(128), 0, st, g, H, (const float*)V, ldv, v_r, rad, norm, logit_ws, sdot_ws, x,
-              cmax, h, (float*)hT, x_out, att);
+              cmax, h, (float*)hT, x_out, att, drop_agg);
   }
 #undef FB_IL
   count_launch(2);

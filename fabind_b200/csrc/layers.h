@@ -30,14 +30,16 @@ int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int 
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st,
-                    const float* ac_g = nullptr, const float* ac_r = nullptr, const float* vstat = nullptr, float eps = 1e-5f);
+                    const float* ac_g = nullptr, const float* ac_r = nullptr, const float* vstat = nullptr, float eps = 1e-5f,
+                    DropCfg drop_coord = DropCfg(), DropCfg drop_agg = DropCfg());
 // ---- FABind+ layout (plus.cu) ----
 int row_stats(const void* x, int ld, int M, int H, const float* w, float* out, bool typed_bf16, cudaStream_t st);
 int ln_rows(const void* x1, bool x1_typed, int ld1, int H1, const void* x2, int ld2, int H2, int M, const float* gamma,
             const float* beta, float eps, void* out, int ldo, bool bf16_mode, cudaStream_t st);
 int gcl_edge_pre_plus(int E, int H, int Dp, const int* erow, const int* ecol, const int* node_cplx, const void* P,
                       const float* hstat, const float* rad, const float* norm, const float* w_rad, const float* gsum,
-                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st);
+                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st, DropCfg drop = DropCfg());
+int dropout_rows(float* x, void* xT, int M, int H, bool bf16_mode, DropCfg drop, cudaStream_t st);
 int pair_zin_plus(const GraphDev& g, int P_total, int H, const void* pair, const float* pc32, int ld32, const float* Wo,
                   const float* bo, const float* gamma, const float* beta, float eps, void* Zl, bool bf16_mode, cudaStream_t st);
 int pair_bias_all(int P_total, const float* dot, int tiles, int stride, const float* cst, float* pb_dense, cudaStream_t st);

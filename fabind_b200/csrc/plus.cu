@@ -118,7 +118,7 @@ __global__ void gcl_edge_pre_plus_kernel(int E, int H, int Dp, const int* __rest
                                          const int* __restrict__ node_cplx, const T* __restrict__ P, const float* __restrict__ hstat,
                                          const float* __restrict__ rad, const float* __restrict__ norm,
                                          const float* __restrict__ w_rad, const float* __restrict__ gsum, const float* __restrict__ c0,
-                                         float eps, T* __restrict__ A1) {
+                                         float eps, T* __restrict__ A1, DropCfg dc) {
   pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
@@ -136,17 +136,21 @@ __global__ void gcl_edge_pre_plus_kernel(int E, int H, int Dp, const int* __rest
     ld8(pr + f, a); ld8(pc + f, b); ld8(w_rad + f, w); ld8(gsum + f, gg); ld8(c0 + f, cc);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = fmaxf(fmaf(rstd, a[i] + b[i] + fmaf(rn, w[i], -mu * gg[i]), cc[i]), 0.f);
+    if (dc.p > 0.f) {   // edge_mlp.dropout1 (P/models/model_utils.py:50); padded columns are zero either way
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = drop_apply(o[i], dc, e, f + i);
+    }
     st8(A1 + (size_t)e * Dp + f, o);
   }
 }
 
 int gcl_edge_pre_plus(int E, int H, int Dp, const int* erow, const int* ecol, const int* node_cplx, const void* P,
                       const float* hstat, const float* rad, const float* norm, const float* w_rad, const float* gsum,
-                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st) {
+                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st, DropCfg drop) {
   if (E <= 0) return FB_OK;
   if (Dp & 7) return FB_ERR_UNSUPPORTED;
-  if (bf16_mode) fb_launch(gcl_edge_pre_plus_kernel<bf16>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const bf16*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (bf16*)A1);
-  else fb_launch(gcl_edge_pre_plus_kernel<float>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const float*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (float*)A1);
+  if (bf16_mode) fb_launch(gcl_edge_pre_plus_kernel<bf16>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const bf16*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (bf16*)A1, drop);
+  else fb_launch(gcl_edge_pre_plus_kernel<float>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const float*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (float*)A1, drop);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -294,6 +298,32 @@ __global__ void pair_bias_all_kernel(int P_total, const float* __restrict__ dot,
 int pair_bias_all(int P_total, const float* dot, int tiles, int stride, const float* cst, float* pb_dense, cudaStream_t st) {
   if (P_total <= 0) return FB_OK;
   fb_launch(pair_bias_all_kernel, dim3((P_total + 255) / 256), dim3(256), 0, st, P_total, dot, tiles, stride, cst, pb_dense);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+// in-place dropout of the residual stream (fp32) and its typed copy: MCAttEGNN `h = self.dropout(h)` in front of linear_out
+// (P/models/egnn.py:428)
+template <typename T>
+__global__ void dropout_rows_kernel(float* __restrict__ x, T* __restrict__ xT, int M, int H, DropCfg dc) {
+  pdl_entry();
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= M) return;
+  for (int f = lane * 4; f < H; f += 128) {
+    float4 v = ld4(x + (size_t)r * H + f);
+    v.x = drop_apply(v.x, dc, r, f); v.y = drop_apply(v.y, dc, r, f + 1);
+    v.z = drop_apply(v.z, dc, r, f + 2); v.w = drop_apply(v.w, dc, r, f + 3);
+    st4(x + (size_t)r * H + f, v);
+    if (xT && (void*)xT != (void*)x) st4(xT + (size_t)r * H + f, v);
+  }
+}
+
+int dropout_rows(float* x, void* xT, int M, int H, bool bf16_mode, DropCfg drop, cudaStream_t st) {
+  if (M <= 0 || drop.p <= 0.f) return FB_OK;
+  if (H & 3) return FB_ERR_UNSUPPORTED;
+  if (bf16_mode) fb_launch(dropout_rows_kernel<bf16>, dim3(warp_grid_p(M)), dim3(256), 0, st, x, (bf16*)xT, M, H, drop);
+  else fb_launch(dropout_rows_kernel<float>, dim3(warp_grid_p(M)), dim3(256), 0, st, x, (float*)xT, M, H, drop);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

@@ -43,20 +43,33 @@ class EfficientMCAttModel(nn.Module):
         self._packed = PackedWeights()
         self.precision = os.environ.get("FABIND_B200_PRECISION", "fp32")
         self.return_pair = True    # False: skip the dense [B, max_p, max_c, H] fp32 copy of the pair embedding (returns None)
+        # train() mode = the reference's SAMPLING mode (P/test_sampling_fabind.py:118-124 runs the model in train() mode
+        # under no_grad so that every nn.Dropout is active): masks are applied in-kernel, keyed by `dropout_seed`
+        # (None: drawn from torch's global generator per call, like nn.Dropout) -- see fabind_b200/dropout.py
+        self.dropout_p = float(getattr(args, "dropout", 0.0))
+        self.dropout_seed = None
+        self.dropout_colonly = False   # tests: column-only masks (row-order invariant) to pin mask placement
         self.last_stats = None
         self.debug_trace = False
 
     def forward(self, X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index,
                 batched_complex_coord_LAS, LAS_mask=None):
+        dropout, n_iter = None, None
         if self.training:
-            raise NotImplementedError("fabind_b200: the training path (dropout + backward kernels) is not built yet; "
-                                      "call .eval()")
+            if torch.is_grad_enabled():
+                raise NotImplementedError("fabind_b200: backward kernels are not built; train() mode is served as the "
+                                          "reference's dropout SAMPLING mode only - wrap the call in torch.no_grad()")
+            seed = self.dropout_seed if self.dropout_seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+            dropout = (self.dropout_p, seed, self.dropout_colonly)
+            if self.random_n_iter:        # att_model.py:199-202: iter_i = random.randint(1, n_iter) in training mode
+                import random
+                n_iter = random.randint(1, self.n_iter)
         if self.precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         with torch.no_grad():
             H_out, stats, e_ctx, tr, pair = model_forward(self, self._packed, X, H, batch_id, segment_id, mask, is_global,
                                                           compound_edge_index, LAS_edge_index, batched_complex_coord_LAS,
                                                           self._cfg, self.precision == "bf16", trace=self.debug_trace,
-                                                          want_pair=self.return_pair)
+                                                          want_pair=self.return_pair, dropout=dropout, n_iter=n_iter)
         self.last_stats = dict(inter_edges_per_iter=stats, ctx_edges=e_ctx, trace=tr)
         return X, H_out, pair

@@ -45,7 +45,7 @@ class PackedWeights:
 
 
 def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, bonds, las, X_las, cfg, bf16, trace=False,
-                  want_pair=None):
+                  want_pair=None, dropout=None, n_iter=None):
     """Runs fb_graph_static + fb_model_forward.  X is updated in place (reference att_model.py:236,245).
     Returns (H_out, stats[int32 n_iter device tensor], E_ctx, trace) and, for the FABind+ layout (`want_pair` not None),
     additionally the dense pair embedding [B, max_p, max_c, hidden] (or None when want_pair is False)."""
@@ -103,6 +103,10 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.w16 = w16.data_ptr() if w16 is not None else None
     p.X_out, p.H_out, p.stats = xv.data_ptr(), H_out.data_ptr(), stats.data_ptr()
     p.flavour = flavour
+    if n_iter is not None:                       # training-mode `random_n_iter` draw (att_model.py:210-211)
+        p.n_iter = int(n_iter)
+    if dropout is not None and dropout[0] > 0:   # (p, seed, colonly): FABind+ sampling mode
+        p.dropout_p, p.dropout_seed, p.dropout_colonly = float(dropout[0]), int(dropout[1]) & 0xFFFFFFFF, int(bool(dropout[2]))
     pair = None
     if flavour == _lib.FLAVOUR_PLUS and want_pair:
         pair = torch.zeros((lay.B, lay.max_p, lay.max_c, hidden), dtype=torch.float32, device=dev)

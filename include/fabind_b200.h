@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 2
+#define FB_ABI_VERSION 3
 
 /* One batch of complexes + model dimensions.  Node layout in caller order is the reference
  * dataloader's [glb_c | atoms | glb_p | residues] per complex (utils/utils.py:328-335). */
@@ -76,6 +76,12 @@ typedef struct fb_model_params {
                              * pair embedding propagated layer to layer, FABind_plus/fabind/models/{egnn,cross_att,model_utils}.py) */
   float* pair_out;          /* FB_FLAVOUR_PLUS, optional: pair embedding after the last layer of the last iteration in the
                              * reference's dense layout [B, max_p, max_c, hidden] (P/models/att_model.py:223); zero-filled by the caller */
+  /* ---- ABI 3: dropout (FABind+ sampling mode runs the model in train() mode, P/test_sampling_fabind.py:118-124) ----
+   * dropout_p > 0 applies a mask at every nn.Dropout site of the FABind+ stack (P/models/model_utils.py:26,49-50,70;
+   * P/models/egnn.py:204,365,428; P/models/cross_att.py:82), keep = hash(seed + iteration, site, row, col) >= p * 2^32, kept
+   * values scaled by 1/(1-p).  dropout_colonly = 1 drops whole feature columns (row ignored): test mode that pins the
+   * placement of every mask against the unmodified reference.  FB_FLAVOUR_PLUS only. */
+  float dropout_p; uint32_t dropout_seed; int32_t dropout_colonly;
 } fb_model_params;
 #define FB_FLAVOUR_V1 0
 #define FB_FLAVOUR_PLUS 1
@@ -165,6 +171,8 @@ typedef struct fb_gemm_params {
   const int32_t* m_dev;
   int32_t bf16_mode;
   int32_t force_simt;   /* 1: never take the tcgen05 path */
+  /* ABI 3: dropout after the activation, before residual / row-dot / stores (0 = off); row index = row + drop_row0 */
+  float drop_p; uint32_t drop_seed; uint32_t drop_site; int32_t drop_row0; int32_t drop_colonly;
 } fb_gemm_params;
 int32_t fb_gemm(const fb_gemm_params* g, void* stream);
 /* two layers over disjoint row ranges of ONE activation buffer (g1->A = g0->A + r*lda rows, r >= g0->M, same K):

@@ -162,6 +162,93 @@ def main_l2():
         print(name, [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd])
 
 
+def patch_reference_dropout(model, L, seed, p):
+    """Replace every nn.Dropout of the (unmodified) FABind+ reference model by a deterministic COLUMN-ONLY mask drawn from the
+    library's mask function (fabind_b200/dropout.py): the mask depends on (seed + iteration, site, feature column) only, so it
+    is invariant to the reference's row orders / dense padding and pins the placement and scaling of every mask."""
+    import re
+    import torch.nn as nn
+    from fabind_b200.dropout import keep_mask, site_id, iter_seed
+    state = dict(it=-1, stack_calls=0)
+
+    class ColDrop(nn.Module):
+        def __init__(self, resolve):
+            super().__init__()
+            self.resolve = resolve
+
+        def forward(self, x):
+            if not self.training:
+                return x
+            site = self.resolve()
+            m = keep_mask(iter_seed(seed, state["it"]), site, 1, x.shape[-1], p, colonly=True)[0]
+            return x * m
+
+    def pre_hook(mod, inp):
+        state["it"] += 1
+        state["stack_calls"] = 0
+    model.gnn.register_forward_pre_hook(pre_hook)
+
+    def stack_site():
+        state["stack_calls"] += 1
+        return site_id(-1, "stack_in" if state["stack_calls"] == 1 else "stack_out")
+    table = {"edge_mlp.dropout1": "edge1", "edge_mlp.dropout2": "edge2", "node_mlp.dropout1": "node1", "node_mlp.dropout2": "node2",
+             "cross_attn_module.p_attention_block.dropout": "patt", "cross_attn_module.c_attention_block.dropout": "catt",
+             "cross_attn_module.p_transition.dropout1": "ptr1", "cross_attn_module.p_transition.dropout2": "ptr2",
+             "cross_attn_module.c_transition.dropout1": "ctr1", "cross_attn_module.c_transition.dropout2": "ctr2",
+             "cross_attn_module.pair_transition.dropout1": "pair1", "cross_attn_module.pair_transition.dropout2": "pair2"}
+    n = 0
+    for name, mod in list(model.named_modules()):
+        if not isinstance(mod, nn.Dropout):
+            continue
+        parent = model
+        parts = name.split(".")
+        for q in parts[:-1]:
+            parent = getattr(parent, q)
+        if name == "gnn.dropout":
+            new = ColDrop(stack_site)
+        else:
+            m = re.match(r"gnn\.(gcl_(\d+)|att_(\d+)|out_layer)\.(.*)", name)
+            assert m, name
+            layer = L if m.group(1) == "out_layer" else int(m.group(2) or m.group(3))
+            rest = m.group(4)
+            if m.group(1).startswith("att") and rest == "dropout":
+                key = "agg"
+            elif rest == "coord_mlp.dropout":
+                key = "acoord" if m.group(1).startswith("att") else "gcoord"
+            else:
+                key = table[rest]
+            new = ColDrop(lambda s=site_id(layer, key): s)
+        setattr(parent, parts[-1], new)
+        n += 1
+    return n
+
+
+def main_plus_dropout():
+    """FABind+ stack in train() mode (the reference's sampling mode) with every nn.Dropout replaced by a column-only mask"""
+    mods = ref_shims.load_reference("plus")
+    cases = {"plusdrop_h64_l2_it2": (64, 2, 2, dict(n_complexes=2, seed=1, n_c_range=(8, 20), n_p_range=(40, 70)), 35, 1234, 0.1)}
+    for name, (hidden, L, IT, bkw, wseed, dseed, pdrop) in cases.items():
+        args = ref_shims.published_args_plus(dropout=pdrop, random_n_iter=False)
+        scale = args.coordinate_scale
+        m = mods.att_model.EfficientMCAttModel(
+            args, hidden, hidden, 1, n_edge_feats=0, n_layers=L, n_iter=IT, inter_cutoff=args.inter_cutoff,
+            intra_cutoff=args.intra_cutoff, normalize_coord=lambda x: x / scale, unnormalize_coord=lambda x: x * scale)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+        n = patch_reference_dropout(m, L, dseed, pdrop)
+        m.train()
+        b = make_batch(embed=hidden, **bkw)
+        with torch.no_grad():
+            X, H, pair = m(**b.clone().forward_args())
+            m.eval()
+            Xe, He, _ = m(**b.clone().forward_args())
+        torch.save({"recipe": dict(hidden=hidden, n_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, far_ligand=False,
+                                   flavour="plus", dropout_p=pdrop, dropout_seed=dseed, patched_dropouts=n),
+                    "shapes": shapes, "X": X.clone(), "H": H.clone(), "pair": pair.clone(), "edges": [],
+                    "torch": torch.__version__}, os.path.join(OUT, name + ".pt"))
+        print(name, "patched", n, "dropouts; train-vs-eval deviation H", float((H - He).abs().max()), "X", float((X - Xe).abs().max()))
+
+
 def main_l2_plus():
     """goldens for the FABind+ L2 wrapper (FABind_plus/fabind/models/model.py::FABindPlus): forward(stage=2) in eval mode
     (13-tuple + the in-place shift of data.coords) and inference()"""
@@ -196,9 +283,11 @@ def main_l2_plus():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus"]
+    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop"]
     if "l2plus" in which:
         main_l2_plus()
+    if "plusdrop" in which:
+        main_plus_dropout()
     if "v1" in which:
         main()
     if "l2" in which:

@@ -68,8 +68,11 @@ def _radial(row, col, x, cplx_t, B):
     return d2 / nrm[cplx_t[row]]
 
 
-def forward_emulated(sd, cfg, batch, flavour=0):
-    """flavour 0: FABind v1 layout -> (X, H, stats); 1: FABind+ layout -> (X, H, stats, pair [P_total, H] packed rows)"""
+def forward_emulated(sd, cfg, batch, flavour=0, dropout=None):
+    """flavour 0: FABind v1 layout -> (X, H, stats); 1: FABind+ layout -> (X, H, stats, pair [P_total, H] packed rows).
+    dropout = (p, seed, colonly): FABind+ train-mode masks with the library's counter-based mask function
+    (fabind_b200/dropout.py), at the sites and row ids csrc/forward.cu uses."""
+    from fabind_b200.dropout import keep_mask, site_id, iter_seed
     H = batch.H.shape[1]
     L = cfg.n_layers
     plus = flavour == 1
@@ -110,17 +113,27 @@ def forward_emulated(sd, cfg, batch, flavour=0):
         raw = F.linear(P0, W.m("pb_w"), W.m("pb_b"))[:, :16 * L].reshape(-1, L, 2, 2, 4)
         PB = raw[:, :, :, 0] * torch.sigmoid(raw[:, :, :, 1])          # [P, L, blk, head]
     pair_last = None
+    state = dict(it=0)
+
+    def drop(t, layer, name, row0=0):
+        if dropout is None or dropout[0] <= 0:
+            return t
+        pdrop, seed, colonly = dropout
+        return t * keep_mask(iter_seed(seed, state["it"]), site_id(layer, name), t.shape[0], t.shape[1], pdrop, colonly, row0)
 
     (ctx_r, ctx_c), _ = _edges(x_state, lay_np, intra, inter, bonds_int)
     stats = []
     h_final = None
     for it in range(cfg.n_iter):
         last = it == cfg.n_iter - 1
+        state["it"] = it
         _, (int_r, int_c) = _edges(x_state, lay_np, intra, inter, bonds_int)
         if int_r.numel() == 0:
             int_r, int_c = torch.tensor([lay.fb_atom, lay.fb_res]), torch.tensor([lay.fb_res, lay.fb_atom])
         stats.append(int(int_r.numel()))
         h = F.linear(Hin, W.m("in_w"), W.m("in_b"))
+        if plus:
+            h = drop(h, -1, "stack_in")
         x = x_state.clone()
 
         def gcl(pre, h, x, need_h=True):
@@ -202,7 +215,7 @@ def forward_emulated(sd, cfg, batch, flavour=0):
         def row_stats(t, w=None):
             return t.sum(1), (t * t).sum(1), (t * w).sum(1) if w is not None else None
 
-        def gcl_plus(pre, h, x, need_h=True):
+        def gcl_plus(pre, h, x, need_h=True, layer=0):
             rn = _radial(ctx_r, ctx_c, x, cplx_t, B)
             s1, s2, _ = row_stats(h)
             Pn = F.linear(h, W.m(pre + "e1_rc"))          # [N, 2*Dp]
@@ -212,20 +225,21 @@ def forward_emulated(sd, cfg, batch, flavour=0):
             rstd = torch.rsqrt(var + EPS)
             A1 = F.relu(rstd[:, None] * (Pn[ctx_r, :Dp] + Pn[ctx_c, Dp:] + rn[:, None] * W.m(pre + "e1_rad")
                                          - mu[:, None] * W.m(pre + "e1_g")) + W.m(pre + "e1_c0"))
-            M = F.relu(F.linear(A1, W.m(pre + "e2_w"), W.m(pre + "e2_b")))
+            A1 = drop(A1, layer, "edge1")
+            M = drop(F.relu(F.linear(A1, W.m(pre + "e2_w"), W.m(pre + "e2_b"))), layer, "edge2")
             M2 = ln(M, pre + "cl_g", pre + "cl_b")
-            s = F.relu(F.linear(M2, W.m(pre + "c1_w"), W.m(pre + "c1_b"))) @ W.m(pre + "c2_w")
+            s = drop(F.relu(F.linear(M2, W.m(pre + "c1_w"), W.m(pre + "c1_b"))), layer, "gcoord") @ W.m(pre + "c2_w")
             deg = torch.zeros(N).index_add_(0, ctx_r, torch.ones(ctx_r.numel())).clamp(min=1)
             dx = torch.zeros(N, 3).index_add_(0, ctx_r, (x[ctx_r] - x[ctx_c]) * s[:, None]) / deg[:, None]
             x_new = x + dx.clamp(-cmax, cmax)
             if need_h:
                 agg = torch.zeros(N, H).index_add_(0, ctx_r, M)
                 t0 = ln(torch.cat([h, agg], 1), pre + "nl_g", pre + "nl_b")
-                t1 = F.relu(F.linear(t0, W.m(pre + "n1_w"), W.m(pre + "n1_b")))
-                h = h + F.relu(F.linear(t1, W.m(pre + "n2_w"), W.m(pre + "n2_b")))
+                t1 = drop(F.relu(F.linear(t0, W.m(pre + "n1_w"), W.m(pre + "n1_b"))), layer, "node1")
+                h = h + drop(F.relu(F.linear(t1, W.m(pre + "n2_w"), W.m(pre + "n2_b"))), layer, "node2")
             return h, x_new
 
-        def att_plus(pre, pair_in, h, x):
+        def att_plus(pre, pair_in, h, x, layer=0):
             h = h.clone()
             raw = F.linear(pair_in, W.m(pre + "pb_w"), W.m(pre + "pb_b"))[:, :16].reshape(-1, 2, 2, 4)
             PBl = raw[:, :, 0] * torch.sigmoid(raw[:, :, 1])          # [P, blk, head]
@@ -238,7 +252,7 @@ def forward_emulated(sd, cfg, batch, flavour=0):
                 nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
                 bias = PBl[pair_base[b]:pair_base[b + 1], 0].view(np1, nc1, 4)
                 O[ps] = rowatt(CAp[psl, :HD], CAp[psl, HD:], CAc[cs, :HD], CAc[cs, HD:2 * HD], bias)
-            h[Nc:] = h[Nc:] + F.linear(O[Nc:], W.m(pre + "o_p_w"), W.m(pre + "o_p_b"))
+            h[Nc:] = h[Nc:] + drop(F.linear(O[Nc:], W.m(pre + "o_p_w"), W.m(pre + "o_p_b")), layer, "patt", Nc)
             CAp2 = F.linear(h[Nc:], W.m(pre + "ca_p2_w"))
             for b in range(B):
                 cs = slice(c_off[b], c_off[b + 1])
@@ -246,11 +260,11 @@ def forward_emulated(sd, cfg, batch, flavour=0):
                 nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
                 bias = PBl[pair_base[b]:pair_base[b + 1], 1].view(np1, nc1, 4).transpose(0, 1)
                 O[cs] = rowatt(CAc[cs, 2 * HD:3 * HD], CAc[cs, 3 * HD:], CAp2[psl, :HD], CAp2[psl, HD:], bias)
-            h[:Nc] = h[:Nc] + F.linear(O[:Nc], W.m(pre + "o_c_w"), W.m(pre + "o_c_b"))
-            for t, sl in (("tc", slice(0, Nc)), ("tp", slice(Nc, N))):
+            h[:Nc] = h[:Nc] + drop(F.linear(O[:Nc], W.m(pre + "o_c_w"), W.m(pre + "o_c_b")), layer, "catt")
+            for t, sl, r0 in (("tc", slice(0, Nc), 0), ("tp", slice(Nc, N), Nc)):
                 t0 = ln(h[sl], pre + t + "l_g", pre + t + "l_b")
-                t1 = F.relu(F.linear(t0, W.m(pre + t + "1_w"), W.m(pre + t + "1_b")))
-                h[sl] = h[sl] + F.relu(F.linear(t1, W.m(pre + t + "2_w"), W.m(pre + t + "2_b")))
+                t1 = drop(F.relu(F.linear(t0, W.m(pre + t + "1_w"), W.m(pre + t + "1_b"))), layer, "ctr1" if t == "tc" else "ptr1", r0)
+                h[sl] = h[sl] + drop(F.relu(F.linear(t1, W.m(pre + t + "2_w"), W.m(pre + t + "2_b"))), layer, "ctr2" if t == "tc" else "ptr2", r0)
             QK = F.linear(h, W.m(pre + "qk_w"), W.m(pre + "qk_b"))
             # pair <- MLPwithLastAct(pair + inter32(p, c)) on every pair row
             pi_all, ci_all = [], []
@@ -261,8 +275,8 @@ def forward_emulated(sd, cfg, batch, flavour=0):
             pi_all, ci_all = torch.cat(pi_all), torch.cat(ci_all)
             t32 = QK[pi_all, 2 * H:2 * H + 32] * QK[ci_all, 2 * H + 32:2 * H + 64]
             Zl = ln(pair_in + (t32 @ W.m(pre + "zo_w") + W.m(pre + "zo_b")), pre + "zl_g", pre + "zl_b")
-            Zh = F.relu(F.linear(Zl, W.m(pre + "pt1_w"), W.m(pre + "pt1_b")))
-            pair_out = F.relu(F.linear(Zh, W.m(pre + "pt2_w"), W.m(pre + "pt2_b")))
+            Zh = drop(F.relu(F.linear(Zl, W.m(pre + "pt1_w"), W.m(pre + "pt1_b"))), layer, "pair1")
+            pair_out = drop(F.relu(F.linear(Zh, W.m(pre + "pt2_w"), W.m(pre + "pt2_b"))), layer, "pair2")
             pb_dense = pair_out @ W.m(pre + "wb") + W.m(pre + "pt_c")
             eb = cplx_t[int_r]
             is_c = int_r < Nc
@@ -279,22 +293,22 @@ def forward_emulated(sd, cfg, batch, flavour=0):
             alpha = e / torch.zeros(N).index_add_(0, int_r, e)[int_r]
             v_r = W.m(pre + "v_r")
             ve = V[int_c] + rn[:, None] * v_r
-            h = h + torch.zeros(N, H).index_add_(0, int_r, alpha[:, None] * ve)
+            h = h + drop(torch.zeros(N, H).index_add_(0, int_r, alpha[:, None] * ve), layer, "agg")
             s1, s2, s3 = row_stats(V, v_r)
             acr = W.m(pre + "ac_r")
             mu = (s1[int_c] + rn * acr[0]) / H
             ex2 = (s2[int_c] + 2 * rn * s3[int_c] + rn * rn * acr[1]) / H
             rstd = torch.rsqrt((ex2 - mu * mu).clamp(min=0) + EPS)
             t = rstd[:, None] * (VC[int_c] + rn[:, None] * W.m(pre + "ac_u") - mu[:, None] * W.m(pre + "ac_g")) + W.m(pre + "ac_c0")
-            se = F.relu(t) @ W.m(pre + "ac2_w")
+            se = drop(F.relu(t), layer, "acoord") @ W.m(pre + "ac2_w")
             dx = torch.zeros(N, 3).index_add_(0, int_r, (x[int_r] - x[int_c]) * (alpha * se)[:, None])
             return h, x + dx.clamp(-cmax, cmax), pair_out
 
         pair_cur = P0
         for l in range(L):
             if plus:
-                h, x = gcl_plus(f"gcl{l}.", h, x)
-                h, x, pair_cur = att_plus(f"att{l}.", pair_cur, h, x)
+                h, x = gcl_plus(f"gcl{l}.", h, x, layer=l)
+                h, x, pair_cur = att_plus(f"att{l}.", pair_cur, h, x, layer=l)
             else:
                 h, x = gcl(f"gcl{l}.", h, x)
                 h, x = att(f"att{l}.", l, h, x)
@@ -303,9 +317,11 @@ def forward_emulated(sd, cfg, batch, flavour=0):
             ref = ((xl[a] - xl[bb]) ** 2).sum(1)
             force = 2 * (cur - ref)[:, None] * (2 * (x[a] - x[bb]))
             x = x + (torch.zeros(N, 3).index_add_(0, bb, force) * cfg.geometry_reg_step_size).clamp(-lcl, lcl)
-        h, x = gcl_plus("out.", h, x, need_h=last) if plus else gcl("out.", h, x, need_h=last)
+        h, x = gcl_plus("out.", h, x, need_h=last, layer=L) if plus else gcl("out.", h, x, need_h=last)
         pair_last = pair_cur
         if last:
+            if plus:
+                h = drop(h, -1, "stack_out")
             h_final = F.linear(h, W.m("out_w"), W.m("out_b"))
         x_state = torch.where(moves[:, None], x, x_state)
     X_out = torch.empty_like(batch.X)

@@ -41,3 +41,22 @@ def test_refactored_formulation_matches_reference_plus(path):
     assert rel_err(H, g["H"]) < 1e-4
     dims = [(int(b.n_p[i]) + 1, int(b.n_c[i]) + 1) for i in range(len(b.n_c))]
     assert rel_err(_dense_pair(pair, dims, H.shape[1]), g["pair"]) < 1e-4
+
+
+def test_dropout_placement_matches_patched_reference():
+    """FABind+ sampling mode (train() under no_grad): every nn.Dropout of the UNMODIFIED reference was replaced by a
+    column-only mask from the library's mask function (scripts/make_golden.py::patch_reference_dropout); the emulated launch
+    sequence with the same masks at the library's 17 sites per layer must reproduce the reference's train-mode outputs."""
+    import glob, os
+    from helpers import GOLDEN_DIR
+    for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "plusdrop_*.pt"))):
+        g, r, b, sd, cfg = load_golden(path)
+        with torch.no_grad():
+            X, H, stats, pair = forward_emulated(sd, cfg, b, flavour=1, dropout=(r["dropout_p"], r["dropout_seed"], True))
+        assert rel_err(X, g["X"]) < 1e-5
+        assert rel_err(H, g["H"]) < 1e-4
+        dims = [(int(b.n_p[i]) + 1, int(b.n_c[i]) + 1) for i in range(len(b.n_c))]
+        assert rel_err(_dense_pair(pair, dims, H.shape[1]), g["pair"]) < 1e-4
+        # and the masks matter: eval-mode emulation is far away
+        Xe, He, _, _ = forward_emulated(sd, cfg, b, flavour=1)
+        assert rel_err(He, g["H"]) > 1e-2

@@ -1,0 +1,111 @@
+"""FABind+ sampling mode on the GPU: train() under no_grad runs the stack with every nn.Dropout site active (the reference's
+`--infer-dropout` path, P/test_sampling_fabind.py:118-124).  The masks are the library's counter-based function
+(fabind_b200/dropout.py); parity is pinned two ways:
+ (a) column-only masks against the UNMODIFIED reference in train() mode with its nn.Dropout modules patched to the same masks
+     (placement and scaling of all 17 sites per layer), and
+ (b) full row x column masks against the CPU emulation of the launch sequence with the same mask function (row identities)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import ref_shims
+from fabind_b200.plus import EfficientMCAttModel
+from helpers import GOLDEN_DIR, load_golden, rel_err
+from emulate_packed import forward_emulated
+
+pytestmark = pytest.mark.gpu
+FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "plusdrop_*.pt")))
+
+
+def _model(r, sd, precision="fp32"):
+    args = ref_shims.published_args_plus(dropout=r["dropout_p"], random_n_iter=False)
+    m = EfficientMCAttModel(args, r["hidden"], r["hidden"], 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                            normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    m.precision = precision
+    m.dropout_seed = r["dropout_seed"]
+    return m
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1][:-3])
+def test_column_masks_match_patched_reference(path):
+    g, r, b, sd, cfg = load_golden(path)
+    m = _model(r, sd)
+    m.dropout_colonly = True
+    with torch.no_grad():
+        X, H, pair = m(**b.to("cuda").forward_args())
+    assert rel_err(X, g["X"]) < 1e-4 and rel_err(H, g["H"]) < 1e-4 and rel_err(pair, g["pair"]) < 1e-4
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("/")[-1][:-3])
+def test_full_masks_match_emulation(path):
+    g, r, b, sd, cfg = load_golden(path)
+    with torch.no_grad():
+        Xe, He, _, _ = forward_emulated(sd, cfg, b, flavour=1, dropout=(r["dropout_p"], r["dropout_seed"], False))
+    m = _model(r, sd)
+    with torch.no_grad():
+        X, H, pair = m(**b.to("cuda").forward_args())
+    assert rel_err(X, Xe) < 1e-4 and rel_err(H, He) < 1e-4
+    assert rel_err(H, g["H"]) > 1e-2       # different masks than the column-only golden: really a different sample
+
+
+def test_sampling_mode_semantics():
+    g, r, b, sd, cfg = load_golden(FILES[0])
+    m = _model(r, sd, precision="bf16")
+    with pytest.raises(NotImplementedError):      # train() with autograd on = training, which is not built
+        m(**b.to("cuda").forward_args())
+    outs = []
+    for seed in (1, 1, 2):
+        m.dropout_seed = seed
+        with torch.no_grad():
+            X, H, _ = m(**b.to("cuda").forward_args())
+        outs.append((X.clone(), H.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])      # same seed: same sample, bit for bit
+    assert float((outs[0][1] - outs[2][1]).abs().max()) > 1e-3                               # another seed: another sample
+    m.dropout_seed = None                                                                     # unseeded: torch's generator
+    torch.manual_seed(0)
+    with torch.no_grad():
+        a = m(**b.to("cuda").forward_args())[1].clone()
+        c = m(**b.to("cuda").forward_args())[1].clone()
+    assert float((a - c).abs().max()) > 1e-3
+    m.eval()
+    with torch.no_grad():
+        e1 = m(**b.to("cuda").forward_args())[1].clone()
+        e2 = m(**b.to("cuda").forward_args())[1].clone()
+    assert torch.equal(e1, e2)
+
+
+def test_gemm_dropout_keep_rate():
+    """fb_gemm with the dropout epilogue: kept fraction ~ 1 - p, kept values scaled by 1/(1-p), every GEMM kernel agrees"""
+    import ctypes as C
+    from fabind_b200 import _lib
+    l = _lib.lib()
+    res = {}
+    for name, (M, bf, simt) in dict(simt=(3000, False, True), tc3=(3000, True, False), tc4=(20000, True, False)).items():
+        torch.manual_seed(0)
+        A = torch.randn(M, 512, device="cuda")
+        W = torch.randn(512, 512, device="cuda") / 512 ** 0.5
+        dt = torch.bfloat16 if bf else torch.float32
+        Ad, Wd = A.to(dt).contiguous(), W.to(dt).contiguous()
+        out = {}
+        for p in (0.0, 0.25):
+            Cout = torch.zeros(M, 512, device="cuda")
+            q = _lib.GemmParams()
+            q.A, q.lda, q.K1 = Ad.data_ptr(), 512, 512
+            q.W, q.act = Wd.data_ptr(), 0
+            q.C, q.ldc, q.M, q.N = Cout.data_ptr(), 512, M, 512
+            q.bf16_mode, q.force_simt = int(bf), int(simt)
+            q.drop_p, q.drop_seed, q.drop_site, q.drop_row0, q.drop_colonly = p, 77, 5, 11, 0
+            _lib.check(l.fb_gemm(C.byref(q), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fb_gemm")
+            torch.cuda.synchronize()
+            out[p] = Cout
+        kept = out[0.25] != 0
+        assert abs(float(kept.float().mean()) - 0.75) < 0.01, name
+        assert torch.allclose(out[0.25][kept], out[0.0][kept] / 0.75, rtol=1e-5, atol=1e-6), name
+        res[name] = kept[:3000].cpu()
+    assert torch.equal(res["simt"], res["tc3"]) and torch.equal(res["simt"], res["tc4"])       # one mask function everywhere
+    from fabind_b200.dropout import keep_mask
+    assert torch.equal(res["simt"], keep_mask(77, 5, 3000, 512, 0.25, row0=11) > 0)
