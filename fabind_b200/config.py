@@ -29,7 +29,10 @@ def published_args_plus(**over):
                        rel_dis_pair_bias="no", inter_additional_mlp=False, only_last_LAS=False,
                        # L2 wrapper FABindPlus (models/model.py): README.md:125-141 + parsing.py:106,158-160,196-199
                        use_for_radius_pred="ligand", pocket_radius_buffer=5.0, min_pocket_radius=20.0, force_fix_radius=False,
-                       dis_map_thres=15.0, use_clustering=False, confidence_training=False, stack_mlp=False, geom_reg_steps=1)
+                       dis_map_thres=15.0, use_clustering=False, confidence_training=False, stack_mlp=False, geom_reg_steps=1,
+                       # sampling-based model (README.md:196-211, parsing.py): confidence head + DBSCAN pocket clustering
+                       confidence_dropout=0.2, confidence_use_ln_mlp=True, confidence_mlp_hidden_scale=1, dbscan_eps=9.0,
+                       dbscan_min_samples=2, choose_cluster_prob=0.5, infer_dropout=True)
     for k, v in over.items():
         setattr(a, k, v)
     return a

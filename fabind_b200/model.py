@@ -40,8 +40,9 @@ def _i32(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
 
 
-def _gemm(A, W, bias=None, act=0, dotv=None, bf16=False):
-    """act(A W^T + bias)  (returns [M,N]);  with dotv: returns (dot partials [tiles, M], tiles) and stores nothing."""
+def _gemm(A, W, bias=None, act=0, dotv=None, bf16=False, drop=None):
+    """act(A W^T + bias)  (returns [M,N]);  with dotv: returns (dot partials [tiles, M], tiles) and stores nothing.
+    drop = (p, seed, site, colonly): dropout after the activation (FABind+ sampling mode)."""
     l = _lib.lib()
     dev = A.device
     M, K = A.shape
@@ -50,6 +51,8 @@ def _gemm(A, W, bias=None, act=0, dotv=None, bf16=False):
     g.A, g.lda, g.K1 = A.data_ptr(), K, K
     g.W, g.bias, g.act = W.data_ptr(), _p(bias), act
     g.M, g.N, g.bf16_mode, g.force_simt = M, N, int(bf16), 0
+    if drop is not None and drop[0] > 0:
+        g.drop_p, g.drop_seed, g.drop_site, g.drop_row0, g.drop_colonly = float(drop[0]), int(drop[1]) & 0xFFFFFFFF, int(drop[2]), 0, int(bool(drop[3]))
     st = current_stream_ptr(dev)
     if dotv is not None:
         tiles = l.fb_gemm_dot_tiles(M, N, K, int(bf16), 0)

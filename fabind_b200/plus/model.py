@@ -11,13 +11,16 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..model import _assemble, _gemm, _i32, _select
+from ..model import _assemble, _gemm, _i32, _layernorm, _select
 from ..runtime import current_stream_ptr
 from .att_model import EfficientMCAttModel
-from .model_utils import MLP
+from .model_utils import MLP, MLP4Confidence
 
 
-def _mlp_scalar(x, mlp, rows=None, bf16=False):
+HEAD_SITES = dict(pocket_radius_head=3000, protein_to_pocket=3001, distmap_mlp=3002)   # dropout sites of the wrapper's MLP heads
+
+
+def _mlp_scalar(x, mlp, rows=None, bf16=False, drop=None):
     """MLP with out_channels=1 (LayerNorm -> Linear+ReLU -> Linear(.,1)): fb_layernorm_rows + tcgen05/FFMA GEMM whose epilogue
     carries the final Linear(.,1) as a row-dot.  Returns (dot partials [tiles, M], tiles, M); the caller adds linear2.bias."""
     l = _lib.lib()
@@ -29,7 +32,7 @@ def _mlp_scalar(x, mlp, rows=None, bf16=False):
                                    mlp.layernorm.bias.data_ptr(), float(mlp.layernorm.eps), z.data_ptr(), int(bf16),
                                    current_stream_ptr(dev)), "fb_layernorm_rows")
     W1 = mlp.linear1.weight.to(torch.bfloat16) if bf16 else mlp.linear1.weight
-    dot, tiles = _gemm(z[:M], W1, mlp.linear1.bias, act=2, dotv=mlp.linear2.weight[0].contiguous(), bf16=bf16)
+    dot, tiles = _gemm(z[:M], W1, mlp.linear1.bias, act=2, dotv=mlp.linear2.weight[0].contiguous(), bf16=bf16, drop=drop)
     return dot, tiles, M
 
 
@@ -46,8 +49,8 @@ class FABindPlus(nn.Module):
         super().__init__()
         if getattr(args, "use_for_radius_pred", "ligand") != "ligand":
             raise NotImplementedError("fabind_b200 implements the published FABind+ configuration: --use-for-radius-pred ligand")
-        if getattr(args, "use_clustering", False) or getattr(args, "confidence_training", False) or getattr(args, "only_last_LAS", False):
-            raise NotImplementedError("fabind_b200: clustering / confidence head / only_last_LAS are not built")
+        if getattr(args, "only_last_LAS", False):
+            raise NotImplementedError("fabind_b200: only_last_LAS is not built (off in the published configuration)")
         self.args = args
         self.coordinate_scale = args.coordinate_scale
         self.normalize_coord = lambda x: x / self.coordinate_scale
@@ -73,8 +76,40 @@ class FABindPlus(nn.Module):
         for lin in (self.protein_linear_whole_protein, self.compound_linear_whole_protein, self.embedding_shrink,
                     self.embedding_enlarge):
             nn.init.xavier_uniform_(lin.weight, gain=0.001)
-        self.confidence_training = False
+        # confidence head of the sampling-based model (model.py:51-56,393-398): MLP4Confidence on the per-complex sum of node features
+        self.confidence_training = getattr(args, "confidence_training", False)
+        if self.confidence_training:
+            if args.stack_mlp:
+                self.ranking_mlp_pre = MLP4Confidence(args, embedding_channels=embedding_channels, n=args.confidence_mlp_hidden_scale,
+                                                      out_channels=embedding_channels)
+            self.ranking_score_mlp = MLP4Confidence(args, embedding_channels=embedding_channels, n=args.confidence_mlp_hidden_scale,
+                                                    out_channels=1)
+        if getattr(args, "use_clustering", False):
+            from sklearn.cluster import DBSCAN       # host-side, exactly as the reference (model.py:57-61)
+            self.dbscan_module = DBSCAN(eps=args.dbscan_eps, min_samples=args.dbscan_min_samples)
         self.precision = "fp32"     # also forwarded to the two stacks
+        # train() under no_grad = the reference's sampling mode (P/test_sampling_fabind.py:118-124): dropout active in both stacks
+        # and the three MLP heads (confidence modules stay in eval mode there); masks keyed by `dropout_seed` (None: drawn per call)
+        self.dropout_seed = None
+        self.dropout_colonly = False
+
+    def _sampling_setup(self):
+        """returns (p, seed, colonly) or None; seeds the two stacks"""
+        if not self.training:
+            return None
+        if torch.is_grad_enabled():
+            raise NotImplementedError("fabind_b200: backward kernels are not built; train() mode is served as the reference's "
+                                      "dropout SAMPLING mode only - wrap the call in torch.no_grad()")
+        seed = self.dropout_seed if self.dropout_seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        self.complex_model.dropout_seed = seed
+        self.pocket_pred_model.dropout_seed = (seed + 0x51ED27) & 0xFFFFFFFF
+        for m in (self.complex_model, self.pocket_pred_model):
+            m.dropout_colonly = self.dropout_colonly
+        return (float(self.args.dropout), seed, self.dropout_colonly)
+
+    def _head_drop(self, name):
+        d = getattr(self, "_drop", None)
+        return None if d is None else (d[0], d[1], HEAD_SITES[name], d[2])
 
     def _lin(self, x, lin, act=0):
         return _gemm(x.contiguous(), lin.weight, lin.bias, act)
@@ -121,10 +156,10 @@ class FABindPlus(nn.Module):
         co = _i32(comp_off, dev)
         comp_sum = torch.empty((B, H), dtype=torch.float32, device=dev)
         _lib.check(l.fb_segment_sum_rows(comp_out.data_ptr(), H, co.data_ptr(), B, comp_sum.data_ptr(), st), "fb_segment_sum_rows")
-        dot, tiles, _ = _mlp_scalar(comp_sum, self.pocket_radius_head)
+        dot, tiles, _ = _mlp_scalar(comp_sum, self.pocket_radius_head, drop=self._head_drop("pocket_radius_head"))
         radius_raw = _dot_finish(dot, tiles, B, self.pocket_radius_head.linear2.bias)
         # per-residue pocket logit (model.py:124-129)
-        dot, tiles, M = _mlp_scalar(prot_out, self.protein_to_pocket)
+        dot, tiles, M = _mlp_scalar(prot_out, self.protein_to_pocket, drop=self._head_drop("protein_to_pocket"))
         logit = _dot_finish(dot, tiles, M, self.protein_to_pocket.linear2.bias)
         xyz = data.node_xyz_whole.to(dev, torch.float32).contiguous()
         po = _i32(prot_off, dev)
@@ -133,6 +168,56 @@ class FABindPlus(nn.Module):
                                       int(bool(self.args.gs_hard)), 0, centers.data_ptr(), st), "fb_pocket_center")
         return dict(B=B, dev=dev, H=H, cb=cb, pbw=pbw, nA=nA, nL=nL, comp_off=comp_off, prot_off=prot_off, comp_out=comp_out,
                     prot_out=prot_out, logit=logit, radius_raw=radius_raw, xyz_whole=xyz, prot_off_dev=po, co=co, centers=centers)
+
+    def _cluster_centers(self, s):
+        """model.py:147-167 (--use-clustering): host-side DBSCAN over the predicted pocket residues and python `random` draws,
+        exactly as the reference does it (it moves the coordinates to numpy there too); the chosen centres go back to the device."""
+        if not getattr(self.args, "use_clustering", False):
+            return
+        import random
+        B, nL, prot_off = s["B"], s["nL"], s["prot_off"]
+        Lmax = int(nL.max())
+        logit = s["logit"].cpu()
+        xyz = s["xyz_whole"].cpu()
+        centers = s["centers"].cpu().clone()
+        out = torch.zeros_like(centers)
+        for i in range(B):
+            dense_logit = torch.zeros(Lmax)
+            dense_xyz = torch.zeros(Lmax, 3)
+            dense_logit[:nL[i]] = logit[prot_off[i]:prot_off[i + 1]]
+            dense_xyz[:nL[i]] = xyz[prot_off[i]:prot_off[i + 1]]
+            prob = dense_logit.sigmoid()                       # padded positions: sigmoid(0) = 0.5, as in the reference
+            pos = dense_xyz[prob > 0.5]
+            if pos.shape[0] < 50:
+                top = torch.argsort(prob)[-50:]
+                sel = torch.full(prob.shape, False)
+                sel[top] = True
+                pos = dense_xyz[sel]
+            pos = pos.numpy()
+            clustering = self.dbscan_module.fit(pos)
+            cid = random.randint(0, clustering.labels_.max())
+            if random.random() < self.args.choose_cluster_prob:
+                out[i] = torch.tensor(pos[clustering.labels_ == cid].mean(axis=0))
+            else:
+                out[i] = centers[i]
+        s["centers"] = out.to(s["dev"])
+
+    def _mlp4conf(self, x, mlp, act_last=0):
+        z = _layernorm(x, mlp.layernorm) if self.args.confidence_use_ln_mlp else x
+        return _gemm(_gemm(z.contiguous(), mlp.linear1.weight, mlp.linear1.bias, act=2), mlp.linear2.weight, mlp.linear2.bias, act=act_last)
+
+    def _confidence(self, s, Ho):
+        """model.py:393-398: MLP4Confidence heads on scatter_add(complex_out, complex_batch); evaluated without dropout (the
+        sampling scripts keep `ranking*` modules in eval mode, P/test_sampling_fabind.py:120-123)."""
+        l = _lib.lib()
+        dev, B, H = s["dev"], s["B"], s["H"]
+        node_off = _i32(np.concatenate([[0], np.cumsum(s["nA"] + s["nP"] + 2)]), dev)
+        hidden = torch.empty((B, H), dtype=torch.float32, device=dev)
+        _lib.check(l.fb_segment_sum_rows(Ho.contiguous().data_ptr(), H, node_off.data_ptr(), B, hidden.data_ptr(),
+                                         current_stream_ptr(dev)), "fb_segment_sum_rows")
+        if self.args.stack_mlp:
+            hidden = self._mlp4conf(hidden, self.ranking_mlp_pre, act_last=2)
+        return self._mlp4conf(hidden, self.ranking_score_mlp).squeeze(-1)
 
     def _dock(self, s, data, want_pair):
         """model.py:202-341 / 505-626: crop by the predicted centre and radius, re-centre, re-assemble, run the docking stack."""
@@ -198,8 +283,13 @@ class FABindPlus(nn.Module):
     # ---------------------------------------------------------------------------------------------------
     def forward(self, data, stage=2, train=False):
         """eval semantics of model.py:63-401 with stage=2, train=False (the predicted pocket is used for docking)."""
-        if self.training or train:
-            raise NotImplementedError("fabind_b200: the training path is not built yet; call .eval() and pass train=False")
+        if train:
+            raise NotImplementedError("fabind_b200: the training path (teacher forcing + backward) is not built; pass train=False")
+        self._drop = self._sampling_setup()
+        if self._drop is not None:
+            raise NotImplementedError("fabind_b200 (FABind+): forward() in train() mode draws gumbel noise for the pocket centre "
+                                      "(model.py:136-137); sampling is served through inference() / sample(), the entry point of "
+                                      "the reference's sampling script (inference_sampling_fabind.py:181)")
         if stage != 2:
             raise NotImplementedError("fabind_b200 (FABind+): stage=1 is the teacher-forcing path of training; use stage=2")
         l = _lib.lib()
@@ -207,7 +297,10 @@ class FABindPlus(nn.Module):
         with torch.no_grad():
             s = self._pocket_stage(data)
             dev, B, H, scale = s["dev"], s["B"], s["H"], self.coordinate_scale
-            Xo, Ho, pair = self._dock(s, data, want_pair=True)
+            self._cluster_centers(s)
+            Xo, Ho, pair = self._dock(s, data, want_pair=not self.confidence_training)
+            if self.confidence_training:
+                return self._forward_confidence(s, data, Xo, Ho)
             st = current_stream_ptr(dev)
             seg, glb = s["seg"], s["glb"]
             c_rows = np.nonzero(~seg & ~glb)[0]
@@ -223,7 +316,7 @@ class FABindPlus(nn.Module):
             rows = np.concatenate([((b * max_p + 1 + np.arange(nP[b]))[:, None] * max_c + 1 + np.arange(nA[b])[None, :]).reshape(-1)
                                    for b in range(B)]) if Q else np.zeros(0, np.int64)
             bf = self.precision == "bf16"
-            dot, tiles, _ = _mlp_scalar(pair.view(-1, H), self.distmap_mlp, rows=_i32(rows, dev), bf16=bf)
+            dot, tiles, _ = _mlp_scalar(pair.view(-1, H), self.distmap_mlp, rows=_i32(rows, dev), bf16=bf, drop=self._head_drop("distmap_mlp"))
             y_pred = torch.empty(Q, dtype=torch.float32, device=dev)
             y_coords = torch.empty(Q, dtype=torch.float32, device=dev)
             _lib.check(l.fb_head_finish_cap(dot.data_ptr(), tiles, dot.shape[1], self.distmap_mlp.linear2.bias.data_ptr(),
@@ -260,19 +353,68 @@ class FABindPlus(nn.Module):
             return (compound_coords_out, data['compound'].batch, y_pred, y_coords, cls_dense, pocket_cls, pmask, coords_dense,
                     s["centers"], dis_map, s["less5"], s["radius_pred"], s["bias"])
 
+    def _dense_cls(self, s):
+        B, nL, prot_off, dev = s["B"], s["nL"], s["prot_off"], s["dev"]
+        Lmax = int(nL.max())
+        kind = np.zeros(B * Lmax, np.uint8); idx = np.zeros(B * Lmax, np.int32)
+        mask_h = np.zeros((B, Lmax), bool)
+        for b in range(B):
+            kind[b * Lmax:b * Lmax + nL[b]] = 1
+            idx[b * Lmax:b * Lmax + nL[b]] = np.arange(prot_off[b], prot_off[b + 1])
+            mask_h[b, :nL[b]] = True
+        cls_dense = _assemble(B * Lmax, 1, kind, idx, [None, s["logit"].view(-1, 1)], 1.0, dev).view(B, Lmax)
+        return cls_dense, torch.from_numpy(mask_h).to(dev), kind, idx, Lmax
+
+    def _forward_confidence(self, s, data, Xo, Ho):
+        """return tuple of model.py:399 (confidence_training)"""
+        l = _lib.lib()
+        dev, B = s["dev"], s["B"]
+        c_rows = np.nonzero(~s["seg"] & ~s["glb"])[0]
+        if getattr(data, "coords", None) is not None:        # data.coords -= pocket centre (model.py:257)
+            gt = data.coords.to(dev, torch.float32).contiguous()
+            gt_out = torch.empty_like(gt)
+            _lib.check(l.fb_shift_rows3(gt.data_ptr(), s["co"].data_ptr(), B, gt.shape[0], s["bias"].data_ptr(), -1.0, gt_out.data_ptr(),
+                                        current_stream_ptr(dev)), "fb_shift_rows3")
+            data.coords = gt_out.to(data.coords.device)
+        cls_dense, pmask, _, _, _ = self._dense_cls(s)
+        return (_select(Xo.view(-1, 3), c_rows, self.coordinate_scale), data['compound'].batch, cls_dense, pmask, s["less5"],
+                self._confidence(s, Ho), s["bias"])
+
+    def sample(self, data_fn, n_samples, seed=0):
+        """Sampling-based FABind+ (P/test_sampling_fabind.py:126-131, P/inference_sampling_fabind.py:168-185): `n_samples` passes of
+        `inference` in train() mode (dropout masks keyed by seed + k), returning the list of (coords, batch[, confidence]).
+        `data_fn()` must return a fresh batch per pass (inference mutates nothing, the forward path shifts data.coords)."""
+        was_training = self.training
+        self.train()
+        for name, sub in self.named_modules():
+            if name.startswith("confidence") or name.startswith("ranking"):
+                sub.eval()
+        outs = []
+        try:
+            with torch.no_grad():
+                for k in range(n_samples):
+                    self.dropout_seed = (int(seed) + 7919 * k) & 0x7FFFFFFF
+                    outs.append(self.inference(data_fn()))
+        finally:
+            self.dropout_seed = None
+            self.train(was_training)
+        return outs
+
     def inference(self, data):
-        if self.training:
-            raise NotImplementedError("fabind_b200: the training path is not built yet; call .eval()")
+        self._drop = self._sampling_setup()
         l = _lib.lib()
         with torch.no_grad():
             s = self._pocket_stage(data)
-            Xo, _, _ = self._dock(s, data, want_pair=False)
+            self._cluster_centers(s)
+            Xo, Ho, _ = self._dock(s, data, want_pair=False)
             dev = s["dev"]
             c_rows = np.nonzero(~s["seg"] & ~s["glb"])[0]
             pred = _select(Xo.view(-1, 3), c_rows, self.coordinate_scale)
             out = torch.empty_like(pred)      # move back to whole-protein coordinates (model.py:684)
             _lib.check(l.fb_shift_rows3(pred.data_ptr(), s["co"].data_ptr(), s["B"], pred.shape[0], s["bias"].data_ptr(), 1.0,
                                         out.data_ptr(), current_stream_ptr(dev)), "fb_shift_rows3")
+            if self.confidence_training:
+                return out, data['compound'].batch, self._confidence(s, Ho)
             return out, data['compound'].batch
 
 

@@ -46,3 +46,21 @@ class MLPwithLastAct(_LnMlp):
 class MLPwoBias(_LnMlp):
     """model_utils.py:55-74 (linear2 without bias)"""
     _last_bias = False
+
+
+class MLP4Confidence(nn.Module):
+    """model_utils.py:76-97: confidence / ranking head MLP (optional LayerNorm, own dropout rate; evaluated in eval mode by the
+    sampling scripts, P/test_sampling_fabind.py:120-123)."""
+
+    def __init__(self, args, embedding_channels=256, out_channels=256, n=4):
+        super().__init__()
+        self.args = args
+        if args.confidence_use_ln_mlp:
+            self.layernorm = nn.LayerNorm(embedding_channels)
+        if args.confidence_dropout > 0:
+            self.dropout = nn.Dropout(args.confidence_dropout)
+        self.linear1 = nn.Linear(embedding_channels, n * embedding_channels)
+        self.linear2 = nn.Linear(n * embedding_channels, out_channels)
+
+    def forward(self, *a, **k):
+        _standalone("MLP4Confidence")

@@ -148,6 +148,12 @@ def _install_utils_stub():
 def load_reference_model_module(flavour="v1"):
     """The reference's L2 wrapper `models.model` (v1: IaBNet_..., plus: FABindPlus), imported unmodified."""
     mods = load_reference(flavour)
+    if "mlflow" not in sys.modules:     # P/models/model.py:58-60 only calls mlflow.sklearn.autolog(disable=True); not installed here
+        ml = types.ModuleType("mlflow")
+        ml.sklearn = types.ModuleType("mlflow.sklearn")
+        ml.sklearn.autolog = lambda **kw: None
+        sys.modules["mlflow"] = ml
+        sys.modules["mlflow.sklearn"] = ml.sklearn
     _install_utils_stub()
     mods.model = importlib.import_module("models.model")
     return mods

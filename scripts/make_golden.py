@@ -162,7 +162,7 @@ def main_l2():
         print(name, [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd])
 
 
-def patch_reference_dropout(model, L, seed, p):
+def patch_reference_dropout(model, L, seed, p, prefix=""):
     """Replace every nn.Dropout of the (unmodified) FABind+ reference model by a deterministic COLUMN-ONLY mask drawn from the
     library's mask function (fabind_b200/dropout.py): the mask depends on (seed + iteration, site, feature column) only, so it
     is invariant to the reference's row orders / dense padding and pins the placement and scaling of every mask."""
@@ -186,7 +186,10 @@ def patch_reference_dropout(model, L, seed, p):
     def pre_hook(mod, inp):
         state["it"] += 1
         state["stack_calls"] = 0
-    model.gnn.register_forward_pre_hook(pre_hook)
+    stack = model
+    for q in [q for q in prefix.split(".") if q]:
+        stack = getattr(stack, q)
+    stack.gnn.register_forward_pre_hook(pre_hook)
 
     def stack_site():
         state["stack_calls"] += 1
@@ -197,10 +200,10 @@ def patch_reference_dropout(model, L, seed, p):
              "cross_attn_module.c_transition.dropout1": "ctr1", "cross_attn_module.c_transition.dropout2": "ctr2",
              "cross_attn_module.pair_transition.dropout1": "pair1", "cross_attn_module.pair_transition.dropout2": "pair2"}
     n = 0
-    for name, mod in list(model.named_modules()):
+    for name, mod in list(stack.named_modules()):
         if not isinstance(mod, nn.Dropout):
             continue
-        parent = model
+        parent = stack
         parts = name.split(".")
         for q in parts[:-1]:
             parent = getattr(parent, q)
@@ -249,6 +252,50 @@ def main_plus_dropout():
         print(name, "patched", n, "dropouts; train-vs-eval deviation H", float((H - He).abs().max()), "X", float((X - Xe).abs().max()))
 
 
+def main_l2_plus_sampling():
+    """FABindPlus.inference in the reference's sampling mode: train() with the ranking modules in eval (test_sampling_fabind.py:
+    118-124), every nn.Dropout patched to a column-only mask, DBSCAN clustering of the pocket centre and the confidence head on,
+    python `random` seeded (cluster choice + random_n_iter draws)."""
+    import random
+    import torch.nn as nn
+    from fabind_b200.dropout import keep_mask
+    from fabind_b200.plus.model import HEAD_SITES
+    from fabind_b200.synthetic import make_docking_batch
+    mods = ref_shims.load_reference_model_module("plus")
+    emb, pemb, L, IT, bkw, wseed, dseed, pdrop = 64, 32, 2, 2, dict(n_complexes=3, seed=1), 53, 4321, 0.1
+    args = ref_shims.published_args_plus(mean_layers=L, n_iter=IT, dropout=pdrop, confidence_training=True, stack_mlp=True,
+                                         use_clustering=True, random_n_iter=True)
+    m = mods.model.FABindPlus(args, emb, pemb)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+    n = patch_reference_dropout(m, L, dseed, pdrop, prefix="complex_model")
+    n += patch_reference_dropout(m, args.pocket_pred_layers, (dseed + 0x51ED27) & 0xFFFFFFFF, pdrop, prefix="pocket_pred_model")
+
+    class HeadDrop(nn.Module):
+        def __init__(self, site):
+            super().__init__()
+            self.site = site
+
+        def forward(self, x):
+            return x * keep_mask(dseed, self.site, 1, x.shape[-1], pdrop, colonly=True)[0] if self.training else x
+    for name, site in HEAD_SITES.items():
+        getattr(m, name).dropout = HeadDrop(site)
+        n += 1
+    m.train()
+    for name, sub in m.named_modules():
+        if name.startswith("confidence") or name.startswith("ranking"):
+            sub.eval()
+    d = make_docking_batch(**bkw)
+    random.seed(99)
+    with torch.no_grad():
+        coords, batch, conf = m.inference(d.clone())
+    torch.save({"recipe": dict(emb=emb, pemb=pemb, mean_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, dropout_p=pdrop,
+                               dropout_seed=dseed, random_seed=99, patched_dropouts=n),
+                "shapes": shapes, "coords": coords.clone(), "confidence": conf.clone(), "torch": torch.__version__},
+               os.path.join(OUT, "l2plussample_h64_p32_l2_it2.pt"))
+    print("l2plussample", "patched", n, "coords", tuple(coords.shape), "confidence", conf.tolist())
+
+
 def main_l2_plus():
     """goldens for the FABind+ L2 wrapper (FABind_plus/fabind/models/model.py::FABindPlus): forward(stage=2) in eval mode
     (13-tuple + the in-place shift of data.coords) and inference()"""
@@ -283,11 +330,13 @@ def main_l2_plus():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop"]
+    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample"]
     if "l2plus" in which:
         main_l2_plus()
     if "plusdrop" in which:
         main_plus_dropout()
+    if "l2plussample" in which:
+        main_l2_plus_sampling()
     if "v1" in which:
         main()
     if "l2" in which:

@@ -109,3 +109,35 @@ def test_gemm_dropout_keep_rate():
     assert torch.equal(res["simt"], res["tc3"]) and torch.equal(res["simt"], res["tc4"])       # one mask function everywhere
     from fabind_b200.dropout import keep_mask
     assert torch.equal(res["simt"], keep_mask(77, 5, 3000, 512, 0.25, row0=11) > 0)
+
+
+def test_wrapper_sampling_matches_patched_reference():
+    """FABindPlus.inference in sampling mode (train(), ranking modules in eval, DBSCAN pocket clustering, confidence head,
+    random_n_iter draws from python `random`): coordinates and confidence scores against the UNMODIFIED reference run the same
+    way with its nn.Dropout modules patched to the library's column-only masks (scripts/make_golden.py::main_l2_plus_sampling)."""
+    import random
+    from fabind_b200.config import published_args_plus
+    from fabind_b200.plus import FABindPlus
+    from fabind_b200.synthetic import make_docking_batch
+    from oracle.det_weights import det_state_dict
+    g = torch.load(os.path.join(GOLDEN_DIR, "l2plussample_h64_p32_l2_it2.pt"), map_location="cpu", weights_only=False)
+    r = g["recipe"]
+    args = published_args_plus(mean_layers=r["mean_layers"], n_iter=r["n_iter"], dropout=r["dropout_p"], confidence_training=True,
+                               stack_mlp=True, use_clustering=True, random_n_iter=True)
+    m = FABindPlus(args, r["emb"], r["pemb"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(g["shapes"])
+    m.load_state_dict(det_state_dict(g["shapes"], r["weight_seed"]), strict=True)
+    m = m.cuda().train()
+    for name, sub in m.named_modules():
+        if name.startswith("confidence") or name.startswith("ranking"):
+            sub.eval()
+    m.dropout_seed, m.dropout_colonly = r["dropout_seed"], True
+    data = make_docking_batch(**r["batch"]).to("cuda")
+    random.seed(r["random_seed"])
+    with torch.no_grad():
+        coords, batch, conf = m.inference(data)
+    assert rel_err(coords, g["coords"]) < 1e-4
+    assert rel_err(conf, g["confidence"]) < 1e-4
+    # sample(): n passes with different masks -> different poses, the API the sampling scripts need
+    outs = m.sample(lambda: make_docking_batch(**r["batch"]).to("cuda"), 3, seed=5)
+    assert len(outs) == 3 and float((outs[0][0] - outs[1][0]).abs().max()) > 1e-4
