@@ -14,6 +14,7 @@ from .. import _lib
 from ..model import _assemble, _gemm, _i32, _layernorm, _select
 from ..runtime import current_stream_ptr
 from .att_model import EfficientMCAttModel
+from .dbscan import dbscan_labels
 from .model_utils import MLP, MLP4Confidence
 
 
@@ -194,10 +195,11 @@ class FABindPlus(nn.Module):
                 sel[top] = True
                 pos = dense_xyz[sel]
             pos = pos.numpy()
-            clustering = self.dbscan_module.fit(pos)
-            cid = random.randint(0, clustering.labels_.max())
+            # same labels as self.dbscan_module.fit(pos).labels_ (tests/test_dbscan.py) without sklearn's per-call overhead
+            labels = dbscan_labels(pos, self.args.dbscan_eps, self.args.dbscan_min_samples)
+            cid = random.randint(0, labels.max())
             if random.random() < self.args.choose_cluster_prob:
-                out[i] = torch.tensor(pos[clustering.labels_ == cid].mean(axis=0))
+                out[i] = torch.tensor(pos[labels == cid].mean(axis=0))
             else:
                 out[i] = centers[i]
         s["centers"] = out.to(s["dev"])

@@ -1,6 +1,8 @@
 """Side benchmarks for the other BASELINE.json configs the round-1 build covers (the graded line is bench.py):
   config 1: single complex (n_c=30, n_p=200), 1 layer x 1 iteration, fp32 parity mode
   config 3: batch=64 with pocket prediction + docking stack (L2 wrapper), ligands 10-80 atoms, bf16
+  config 4: FABind+ sampling mode, per-GPU share: batch=32 complexes, one dropout sample per pass (40 passes per complex in the
+            reference's protocol), whole FABindPlus.inference (pocket stage + DBSCAN + docking stack + confidence head), bf16
 Each prints one JSON line with complexes/s on the device (CUDA events, L2 flushed between steps)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -55,3 +57,50 @@ ms = timed(f3, steps=5, warmup=2)
 nres = int(d3['protein_whole'].batch.shape[0])
 print(json.dumps(dict(config="3: batch=64, pocket prediction + docking stack + distance head (L2 wrapper)", dtype="bf16",
                       ms_per_batch=round(ms, 2), complexes_per_s=round(64e3 / ms, 1), residues_total=nres)))
+
+# ---- config 4 (FABind+ sampling mode; random_n_iter off so that every pass does the full 8 iterations)
+from fabind_b200.config import published_args_plus
+from fabind_b200.plus import FABindPlus, EfficientMCAttModel as PlusStack
+import random
+if "4" in (sys.argv[1:] or ["1", "3", "4"]):
+    a4 = published_args_plus(confidence_training=True, stack_mlp=True, use_clustering=True, random_n_iter=False)
+    m4 = FABindPlus(a4, 512, 128)
+    randomize_coord_heads(m4)
+    m4 = m4.to(dev).train()
+    for name, sub in m4.named_modules():
+        if name.startswith("confidence") or name.startswith("ranking"):
+            sub.eval()
+    m4.precision = "bf16"
+    d4 = make_docking_batch(32, seed=4, n_c_range=(10, 80), L_range=(150, 800)).to(dev)
+    random.seed(0)
+    k = [0]
+    def f4():
+        k[0] += 1
+        m4.dropout_seed = k[0]
+        with torch.no_grad():
+            m4.inference(d4)
+    ms = timed(f4, steps=5, warmup=2)
+    print(json.dumps(dict(config="4: FABind+ sampling mode, batch=32 x 1 dropout sample per pass (FABindPlus.inference: pocket stage, "
+                                 "DBSCAN clustering, 5-layer x 8-iteration docking stack with in-kernel dropout, confidence head)",
+                          dtype="bf16", ms_per_pass=round(ms, 2), instances_per_s=round(32e3 / ms, 1),
+                          complexes_per_s_at_40_samples=round(32e3 / ms / 40, 2))))
+    # the docking stack alone at the config-2 shape, eval vs sampling mode (cost of the in-kernel masks)
+    torch.manual_seed(0)
+    ms_ = {}
+    st4 = PlusStack(published_args_plus(random_n_iter=False), 512, 512, 1, n_layers=5, n_iter=8, normalize_coord=lambda x: x / 5.0,
+                    unnormalize_coord=lambda x: x * 5.0)
+    randomize_coord_heads(st4)
+    st4 = st4.to(dev)
+    st4.precision, st4.return_pair = "bf16", False
+    b4 = make_batch(n_complexes=16, n_c=30, n_p=200, seed=0).to(dev)
+    X4 = b4.X.clone()
+    for mode in ("eval", "sampling"):
+        st4.train(mode == "sampling")
+        def fs():
+            b4.X.copy_(X4)
+            with torch.no_grad():
+                st4(**b4.forward_args())
+        ms_[mode] = round(timed(fs, steps=5, warmup=2), 2)
+    print(json.dumps(dict(config="FABind+ docking stack, batch=16 (n_c=30, n_p=200), 5 layers x 8 iterations", dtype="bf16",
+                          ms_eval=ms_["eval"], ms_sampling=ms_["sampling"], complexes_per_s_eval=round(16e3 / ms_["eval"], 1),
+                          instances_per_s_sampling=round(16e3 / ms_["sampling"], 1))))
