@@ -1,6 +1,8 @@
 """Drop-in replacement for FABind_plus/fabind/models/att_model.py: `ComplexGraph` (shared with v1: the edge rules are
 identical, att_model.py:29-126) and `EfficientMCAttModel` whose forward returns `(X, H, pair_embed_batched)`
-(att_model.py:166-223).  Inference semantics (eval mode, refine='refine_coord')."""
+(att_model.py:166-223).  eval(): inference semantics (refine='refine_coord').  train() under torch.no_grad(): the reference's
+dropout SAMPLING mode (P/test_sampling_fabind.py:118-124) with in-kernel masks at every nn.Dropout site and the `random_n_iter`
+draw of att_model.py:199-202; train() with autograd enabled raises (no backward kernels)."""
 import os
 
 import torch

@@ -84,6 +84,19 @@ if "4" in (sys.argv[1:] or ["1", "3", "4"]):
                                  "DBSCAN clustering, 5-layer x 8-iteration docking stack with in-kernel dropout, confidence head)",
                           dtype="bf16", ms_per_pass=round(ms, 2), instances_per_s=round(32e3 / ms, 1),
                           complexes_per_s_at_40_samples=round(32e3 / ms / 40, 2))))
+    # the reference's own sampling protocol: batch_size 8, 40 samples per complex (README.md:142-156): 40 sequential passes
+    # (sample()) against ONE batched launch sequence per chunk of replicas (plus/sampling.py::sample_batched)
+    from fabind_b200.plus.sampling import sample_batched
+    d8 = make_docking_batch(8, seed=5, n_c_range=(10, 80), L_range=(150, 800)).to(dev)
+    def f_seq():
+        m4.sample(lambda: d8, 8, seed=1)
+    def f_bat():
+        sample_batched(m4, d8, 40, seed=1, max_instances=160)
+    ms_seq = timed(f_seq, steps=3, warmup=1) / 8 * 40      # 8 of the 40 passes timed
+    ms_bat = timed(f_bat, steps=3, warmup=1)
+    print(json.dumps(dict(config="4b: FABind+ sampling, batch_size 8 x 40 samples per complex (reference protocol)", dtype="bf16",
+                          ms_40_sequential_passes=round(ms_seq, 1), ms_batched=round(ms_bat, 1),
+                          complexes_per_s_sequential=round(8e3 / ms_seq, 2), complexes_per_s_batched=round(8e3 / ms_bat, 2))))
     # the docking stack alone at the config-2 shape, eval vs sampling mode (cost of the in-kernel masks)
     torch.manual_seed(0)
     ms_ = {}

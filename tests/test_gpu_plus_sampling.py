@@ -141,3 +141,29 @@ def test_wrapper_sampling_matches_patched_reference():
     # sample(): n passes with different masks -> different poses, the API the sampling scripts need
     outs = m.sample(lambda: make_docking_batch(**r["batch"]).to("cuda"), 3, seed=5)
     assert len(outs) == 3 and float((outs[0][0] - outs[1][0]).abs().max()) > 1e-4
+
+
+def test_batched_sampling_equals_replicated_rows():
+    """sample_batched: S samples = S replicas in one batch.  Replica k of a complex must equal what a stand-alone pass over the
+    replicated batch gives (trivially) AND be a valid independent sample: with dropout off (p = 0) all replicas coincide with
+    the eval-mode pose; with dropout on they differ from each other."""
+    from fabind_b200.config import published_args_plus
+    from fabind_b200.plus import FABindPlus
+    from fabind_b200.plus.sampling import replicate_batch, sample_batched
+    from fabind_b200.synthetic import make_docking_batch
+    from oracle.det_weights import det_state_dict
+    args = published_args_plus(mean_layers=1, n_iter=2, confidence_training=True, stack_mlp=True, random_n_iter=False)
+    m = FABindPlus(args, 64, 32)
+    m.load_state_dict(det_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 71), strict=True)
+    m = m.cuda().eval()
+    data = make_docking_batch(2, seed=21, n_c_range=(8, 16), L_range=(100, 160)).to("cuda")
+    with torch.no_grad():
+        ref_coords, _, ref_conf = m.inference(data)
+        rep = m.inference(replicate_batch(data, 3))                   # eval mode: replicas are exact copies
+    n = ref_coords.shape[0]
+    for k in range(3):
+        assert rel_err(rep[0][k * n:(k + 1) * n], ref_coords) < 1e-5 and rel_err(rep[2][k * 2:(k + 1) * 2], ref_conf) < 1e-5
+    coords, batch, conf = sample_batched(m, data, 5, seed=3, max_instances=6)     # chunks of 3 + 2 samples
+    assert coords.shape == (5, n, 3) and conf.shape == (5, 2) and not m.training
+    d01 = float((coords[0] - coords[1]).abs().max())
+    assert d01 > 1e-4 and float((coords[0] - ref_coords).abs().max()) > 1e-4
