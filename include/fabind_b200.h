@@ -232,6 +232,17 @@ int32_t fb_head_finish_cap(const float* dot, int32_t tiles, int32_t stride, cons
                            const float* lig_xyz, const int32_t* pocket_off, const int32_t* comp_off, const int32_t* pair_off,
                            int32_t B, int32_t n_pairs, float scale, float cap, float* y_pred, float* y_coords, void* stream);
 
+/* ---- ligand post-optimisation (reference: utils/post_optim_utils.py:36-64 `post_optimize_compound_coords`, called per ligand
+ * on the CPU by fabind_inference.py:285-316) ----
+ * B ligands in one launch (one CTA each, all `epochs` Adam steps inside the kernel).  Atoms of ligand b are rows
+ * atom_off[b]..atom_off[b+1] of ref_coords / pred_coords / out_coords ([n,3] fp32).  las_edges = NULL: rigid mode (all pairs
+ * constrained, post_optim_utils.py:31); otherwise [2, n_las_total] ligand-LOCAL atom ids, edges of ligand b at
+ * las_off[b]..las_off[b+1] (LAS mask + 1.22 A excluded volume, post_optim_utils.py:25-29).  out_loss[b] = loss before the last
+ * step, out_rmsd[b] = RMSD of the result to ref_coords (the function's 2nd and 3rd return values). */
+int32_t fb_post_optimize(const float* ref_coords, const float* pred_coords, const int32_t* atom_off, int32_t B, int32_t max_atoms,
+                         const int32_t* las_edges, const int32_t* las_off, int32_t n_las_total, int32_t epochs, float lr,
+                         float* out_coords, float* out_loss, float* out_rmsd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

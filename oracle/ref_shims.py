@@ -168,3 +168,20 @@ def published_args(**over):
 def published_args_plus(**over):
     from fabind_b200.config import published_args_plus as _pa
     return _pa(**over)
+
+
+def load_reference_post_optim():
+    """`utils/post_optim_utils.py` of the v1 reference, imported unmodified (it imports rdkit only for its SDF writers)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present")
+    install_shims()
+    for name in ("rdkit", "rdkit.Chem", "rdkit.Geometry"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["rdkit"].Chem = sys.modules["rdkit.Chem"]
+    sys.modules["rdkit.Geometry"].Point3D = object
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_post_optim_utils", os.path.join(REF_V1, "utils", "post_optim_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

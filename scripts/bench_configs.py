@@ -30,6 +30,7 @@ def timed(fn, steps=10, warmup=3):
 
 
 torch.manual_seed(0)
+WHICH = sys.argv[1:] or ["1", "3", "4"]
 # ---- config 1
 m1 = EfficientMCAttModel(published_args(), 512, 512, 1, n_layers=1, n_iter=1, normalize_coord=lambda x: x / 5.0,
                          unnormalize_coord=lambda x: x * 5.0)
@@ -39,7 +40,7 @@ b1 = make_batch(n_complexes=1, n_c=30, n_p=200, seed=0).to(dev)
 X0 = b1.X.clone()
 def f1():
     b1.X.copy_(X0); m1(**b1.forward_args())
-for prec in ("fp32", "bf16"):
+for prec in (("fp32", "bf16") if "1" in WHICH else ()):
     m1.precision = prec
     ms = timed(f1)
     print(json.dumps(dict(config="1: single complex, 1 layer x 1 iteration", dtype=prec, ms_per_forward=round(ms, 3),
@@ -53,16 +54,17 @@ m3.precision = "bf16"
 d3 = make_docking_batch(64, seed=3, n_c_range=(10, 80), L_range=(150, 800)).to(dev)
 def f3():
     m3(d3, stage=2)
-ms = timed(f3, steps=5, warmup=2)
+ms = timed(f3, steps=5, warmup=2) if "3" in WHICH else float("nan")
 nres = int(d3['protein_whole'].batch.shape[0])
-print(json.dumps(dict(config="3: batch=64, pocket prediction + docking stack + distance head (L2 wrapper)", dtype="bf16",
+if "3" in WHICH:
+  print(json.dumps(dict(config="3: batch=64, pocket prediction + docking stack + distance head (L2 wrapper)", dtype="bf16",
                       ms_per_batch=round(ms, 2), complexes_per_s=round(64e3 / ms, 1), residues_total=nres)))
 
 # ---- config 4 (FABind+ sampling mode; random_n_iter off so that every pass does the full 8 iterations)
 from fabind_b200.config import published_args_plus
 from fabind_b200.plus import FABindPlus, EfficientMCAttModel as PlusStack
 import random
-if "4" in (sys.argv[1:] or ["1", "3", "4"]):
+if "4" in WHICH:
     a4 = published_args_plus(confidence_training=True, stack_mlp=True, use_clustering=True, random_n_iter=False)
     m4 = FABindPlus(a4, 512, 128)
     randomize_coord_heads(m4)
@@ -117,3 +119,22 @@ if "4" in (sys.argv[1:] or ["1", "3", "4"]):
     print(json.dumps(dict(config="FABind+ docking stack, batch=16 (n_c=30, n_p=200), 5 layers x 8 iterations", dtype="bf16",
                           ms_eval=ms_["eval"], ms_sampling=ms_["sampling"], complexes_per_s_eval=round(16e3 / ms_["eval"], 1),
                           instances_per_s_sampling=round(16e3 / ms_["sampling"], 1))))
+
+# ---- ligand post-optimisation (post_optim_utils.py): 64 ligands x 1000 Adam steps in one launch vs the reference's per-ligand CPU loop
+if "post" in WHICH or len(sys.argv) == 1:
+    import numpy as np
+    from fabind_b200.post_optim import post_optimize_batch
+    from fabind_b200.synthetic import _one_complex
+    from oracle.post_optim_oracle import post_optimize as po_cpu
+    refs, preds, batch, las_l, las_b = [], [], [], [], []
+    rng = np.random.default_rng(0)
+    for b in range(64):
+        n = int(rng.integers(10, 81))
+        _, lig, _, las, lig_ref = _one_complex(rng, n, 30)
+        refs.append(torch.tensor(lig_ref, dtype=torch.float32)); preds.append(torch.tensor(lig + rng.normal(scale=0.8, size=lig.shape), dtype=torch.float32))
+        batch.append(torch.full((n,), b)); las_l.append(torch.tensor(las.T.copy())); las_b.append(torch.full((las.shape[0],), b))
+    R, P_, Bt, L_, Lb = torch.cat(refs).to(dev), torch.cat(preds).to(dev), torch.cat(batch).to(dev), torch.cat(las_l, 1).to(dev), torch.cat(las_b).to(dev)
+    ms = timed(lambda: post_optimize_batch(R, P_, Bt, L_, Lb, total_epoch=1000), steps=3, warmup=1)
+    t0 = time.perf_counter(); po_cpu(refs[0], preds[0], 1000, las_l[0]); cpu_s = time.perf_counter() - t0
+    print(json.dumps(dict(config="post-optimisation: 64 ligands (10-80 atoms) x 1000 Adam steps, one launch", ms=round(ms, 2),
+                          ligands_per_s=round(64e3 / ms, 1), cpu_port_s_per_ligand=round(cpu_s, 3), cpu_atoms=int(refs[0].shape[0]))))

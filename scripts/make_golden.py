@@ -296,6 +296,25 @@ def main_l2_plus_sampling():
     print("l2plussample", "patched", n, "coords", tuple(coords.shape), "confidence", conf.tolist())
 
 
+def main_post_optim():
+    """post_optimize_compound_coords (utils/post_optim_utils.py:36-64) run unmodified on synthetic ligands"""
+    import numpy as np
+    from fabind_b200.synthetic import _one_complex
+    ref = ref_shims.load_reference_post_optim()
+    cases = []
+    for n, shift, epochs, rigid in ((24, 0.0, 10, False), (24, 0.0, 10, True), (40, 0.0, 10, False), (24, 0.0, 100, False),
+                                    (24, 0.0, 100, True), (18, 12.0, 1000, False), (40, 30.0, 1000, False), (60, 30.0, 1000, False)):
+        rng = np.random.default_rng(100 + n + int(shift) + epochs + rigid)
+        _, lig, _, las, lig_ref = _one_complex(rng, n, 30)
+        refc = torch.tensor(lig_ref, dtype=torch.float32)
+        pred = torch.tensor(lig + rng.normal(scale=0.8, size=lig.shape) + shift, dtype=torch.float32)
+        las_t = torch.tensor(las.T.copy(), dtype=torch.long)
+        x, loss, rmsd = ref.post_optimize_compound_coords(refc, pred, total_epoch=epochs, LAS_edge_index=None if rigid else las_t)
+        cases.append(dict(n=n, epochs=epochs, rigid=rigid, ref=refc, pred=pred, las=las_t, x=x.clone(), loss=float(loss), rmsd=float(rmsd)))
+        print("postopt", n, epochs, rigid, "loss", loss, "rmsd", rmsd)
+    torch.save({"cases": cases, "torch": torch.__version__}, os.path.join(OUT, "postopt_cases.pt"))
+
+
 def main_l2_plus():
     """goldens for the FABind+ L2 wrapper (FABind_plus/fabind/models/model.py::FABindPlus): forward(stage=2) in eval mode
     (13-tuple + the in-place shift of data.coords) and inference()"""
@@ -330,13 +349,15 @@ def main_l2_plus():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample"]
+    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample", "postopt"]
     if "l2plus" in which:
         main_l2_plus()
     if "plusdrop" in which:
         main_plus_dropout()
     if "l2plussample" in which:
         main_l2_plus_sampling()
+    if "postopt" in which:
+        main_post_optim()
     if "v1" in which:
         main()
     if "l2" in which:
