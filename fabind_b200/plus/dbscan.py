@@ -10,29 +10,37 @@ sklearn on random inputs in tests/test_dbscan.py.  Host logic on both sides of t
 import numpy as np
 from scipy.sparse import csr_matrix
 from scipy.sparse.csgraph import connected_components
+from scipy.spatial import cKDTree
 
 
 def dbscan_labels(points, eps, min_samples):
-    x = np.asarray(points, dtype=np.float64)
+    x = np.ascontiguousarray(points, dtype=np.float64)
     n = x.shape[0]
     labels = np.full(n, -1, dtype=np.int64)
     if n == 0:
         return labels
-    d2 = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
-    adj = d2 <= float(eps) ** 2                     # radius_neighbors: distance <= eps, the point itself included
-    core = adj.sum(1) >= min_samples
-    idx = np.nonzero(core)[0]
-    if idx.size == 0:
+    # neighbour pairs i < j with distance <= eps (radius_neighbors semantics; the point itself counts towards min_samples)
+    pairs = cKDTree(x).query_pairs(float(eps), output_type="ndarray")
+    deg = np.bincount(pairs.ravel(), minlength=n) + 1
+    core = deg >= min_samples
+    if not core.any():
         return labels
-    _, comp = connected_components(csr_matrix(adj[np.ix_(idx, idx)]), directed=False)
-    # number the components in order of their lowest-index core point (sklearn's discovery order)
-    first = np.full(comp.max() + 1, n, dtype=np.int64)
-    np.minimum.at(first, comp, np.arange(idx.size))
-    rank = np.empty_like(first)
-    rank[np.argsort(first, kind="stable")] = np.arange(first.size)
-    labels[idx] = rank[comp]
+    cc = pairs[core[pairs[:, 0]] & core[pairs[:, 1]]]
+    g = csr_matrix((np.ones(len(cc), dtype=np.int8), (cc[:, 0], cc[:, 1])), shape=(n, n))
+    _, comp = connected_components(g, directed=False)
+    idx = np.nonzero(core)[0]
+    comp_c = comp[idx]
+    # number the components of core points in order of their lowest-index core point (sklearn's discovery order)
+    uniq, first = np.unique(comp_c, return_index=True)
+    rank = np.empty(comp.max() + 1, dtype=np.int64)
+    rank[uniq[np.argsort(first, kind="stable")]] = np.arange(uniq.size)
+    labels[idx] = rank[comp_c]
     # border points: reached first by the earliest-expanded (lowest-numbered) cluster among their core neighbours
-    border = np.nonzero(~core & (adj & core[None, :]).any(1))[0]
-    for b in border:
-        labels[b] = labels[np.nonzero(adj[b] & core)[0]].min()
+    big = np.iinfo(np.int64).max
+    best = np.full(n, big, dtype=np.int64)
+    for a_, b_ in ((0, 1), (1, 0)):
+        sel = ~core[pairs[:, a_]] & core[pairs[:, b_]]
+        np.minimum.at(best, pairs[sel, a_], labels[pairs[sel, b_]])
+    hit = ~core & (best != big)
+    labels[hit] = best[hit]
     return labels
