@@ -79,6 +79,20 @@ def _assemble(M, D, kind, idx, srcs, scale, dev):
     return out
 
 
+def complex_layout_np(nA, nX, src_x=None):
+    """Row plan of the reference's per-complex [glb_c | atoms | glb_p | residues] assembly (model.py:104-115,205-253) for all
+    complexes at once: kind (0 glb_c, 1 atom, 2 glb_p, 3 residue), the source row of every atom / residue row (atoms and residues
+    are consumed in order; `src_x` gives the residue source rows, default 0..sum(nX)-1), and the node attributes derived from it."""
+    nA, nX = np.asarray(nA, dtype=np.int64), np.asarray(nX, dtype=np.int64)
+    B = len(nA)
+    lens = np.stack([np.ones(B, np.int64), nA, np.ones(B, np.int64), nX], 1).reshape(-1)
+    kind = np.repeat(np.tile(np.arange(4, dtype=np.uint8), B), lens)
+    idx = np.zeros(kind.shape[0], dtype=np.int32)
+    idx[kind == 1] = np.arange(int(nA.sum()), dtype=np.int32)
+    idx[kind == 3] = np.arange(int(nX.sum()), dtype=np.int32) if src_x is None else np.asarray(src_x, dtype=np.int32)
+    return kind, idx
+
+
 def _select(src, idx, scale=1.0):
     """rows src[idx] (the reference's boolean-mask selections), optionally scaled"""
     return _assemble(len(idx), src.shape[1], np.ones(len(idx), np.uint8), idx, [None, src], scale, src.device)
@@ -145,10 +159,7 @@ class IaBNet_mean_and_pocket_prediction_cls_coords_dependent(nn.Module):
         prot_off = np.concatenate([[0], np.cumsum(nL)]).astype(np.int32)
         comp = self._lin(data['compound'].node_feats.to(dev, torch.float32), self.compound_linear_whole_protein)
         prot = self._lin(data['protein_whole'].node_feats.to(dev, torch.float32), self.protein_linear_whole_protein)
-        kind, idx = [], []
-        for b in range(B):
-            kind += [0] + [1] * nA[b] + [2] + [3] * nL[b]
-            idx += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(range(prot_off[b], prot_off[b + 1]))
+        kind, idx = complex_layout_np(nA, nL)
         Nw = len(kind)
         x = _assemble(Nw, H, kind, idx, [self.glb_c, comp, self.glb_p, prot], 1.0, dev)
         x = self._lin(x, self.embedding_shrink)
@@ -202,7 +213,7 @@ class IaBNet_mean_and_pocket_prediction_cls_coords_dependent(nn.Module):
         keep_h = keep.cpu().numpy().astype(bool)         # the one host read of this stage: sizes of the cropped graphs
         s["keep"], s["less5"] = keep_h, int(less5.sum().item())
         kept = np.nonzero(keep_h)[0]
-        nP = np.array([keep_h[s["prot_off"][b]:s["prot_off"][b + 1]].sum() for b in range(B)])
+        nP = np.add.reduceat(keep_h.astype(np.int64), s["prot_off"][:-1]) if B else np.zeros(0, np.int64)
         pocket_off = np.concatenate([[0], np.cumsum(nP)]).astype(np.int32)
         nA, comp_off = s["nA"], s["comp_off"]
         pocket_xyz = _select(xyz, kept)                                             # [Pk,3], original units
@@ -211,17 +222,10 @@ class IaBNet_mean_and_pocket_prediction_cls_coords_dependent(nn.Module):
         co, pk = _i32(comp_off, dev), _i32(pocket_off, dev)
         _lib.check(l.fb_ligand_place(lig.data_ptr(), co.data_ptr(), pocket_xyz.data_ptr(), pk.data_ptr(), B, lig_init.data_ptr(),
                                      current_stream_ptr(dev)), "fb_ligand_place")
-        kind, idx_f, idx_x = [], [], []
-        seg, msk, glb, bat = [], [], [], []
-        for b in range(B):
-            n = nA[b] + nP[b] + 2
-            kind += [0] + [1] * nA[b] + [2] + [3] * nP[b]
-            idx_f += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(kept[pocket_off[b]:pocket_off[b + 1]])
-            idx_x += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(range(pocket_off[b], pocket_off[b + 1]))
-            sg = np.zeros(n, bool); sg[nA[b] + 1:] = True
-            mk = np.zeros(n, bool); mk[:nA[b] + 2] = True
-            gb = np.zeros(n, bool); gb[0] = True; gb[nA[b] + 1] = True
-            seg.append(sg); msk.append(mk); glb.append(gb); bat.append(np.full(n, b, np.int64))
+        kind, idx_f = complex_layout_np(nA, nP, kept)             # features: residue rows come from the whole-protein table
+        _, idx_x = complex_layout_np(nA, nP)                      # coordinates: from the cropped pocket table
+        seg, msk, glb = kind >= 2, kind <= 2, (kind == 0) | (kind == 2)
+        bat = np.repeat(np.arange(B, dtype=np.int64), nA + nP + 2)
         Ncx = len(kind)
         Hc = _assemble(Ncx, H, kind, idx_f, [self.glb_c, s["comp_out"], self.glb_p, s["prot_out"]], 1.0, dev)
         X = _assemble(Ncx, 3, kind, idx_x, [None, lig_init, None, pocket_xyz], 1.0 / scale, dev).unsqueeze(-2)
@@ -234,7 +238,6 @@ class IaBNet_mean_and_pocket_prediction_cls_coords_dependent(nn.Module):
         ael, lel = data['compound_atom_edge_list'], data['LAS_edge_list']
         c2c = (ael.x.cpu().numpy() + node_off[ael.batch.cpu().numpy()][:, None]).T
         las = (lel.x.cpu().numpy() + node_off[lel.batch.cpu().numpy()][:, None]).T
-        seg, msk, glb, bat = (np.concatenate(a) for a in (seg, msk, glb, bat))
         self.complex_model.precision = self.precision
         Xo, Ho = self.complex_model(
             X.contiguous(), Hc, batch_id=torch.from_numpy(bat), segment_id=torch.from_numpy(seg), mask=torch.from_numpy(msk),
@@ -253,10 +256,7 @@ class IaBNet_mean_and_pocket_prediction_cls_coords_dependent(nn.Module):
         nP = np.bincount(pb, minlength=B)
         pocket_off = np.concatenate([[0], np.cumsum(nP)]).astype(np.int32)
         nA, comp_off = s["nA"], s["comp_off"]
-        kind, idx_f = [], []
-        for b in range(B):
-            kind += [0] + [1] * nA[b] + [2] + [3] * nP[b]
-            idx_f += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(kept[pocket_off[b]:pocket_off[b + 1]])
+        kind, idx_f = complex_layout_np(nA, nP, kept)
         Ncx = len(kind)
         Hc = _assemble(Ncx, H, kind, idx_f, [self.glb_c, s["comp_out"], self.glb_p, s["prot_out"]], 1.0, dev)
         rows = np.arange(Ncx)

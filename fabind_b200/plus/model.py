@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..model import _assemble, _gemm, _i32, _layernorm, _select
+from ..model import _assemble, _gemm, _i32, _layernorm, _select, complex_layout_np
 from ..runtime import current_stream_ptr
 from .att_model import EfficientMCAttModel
 from .dbscan import dbscan_labels
@@ -130,10 +130,7 @@ class FABindPlus(nn.Module):
         prot_off = np.concatenate([[0], np.cumsum(nL)]).astype(np.int32)
         comp = self._lin(data['compound'].node_feats.to(dev, torch.float32), self.compound_linear_whole_protein)
         prot = self._lin(data['protein_whole'].node_feats.to(dev, torch.float32), self.protein_linear_whole_protein)
-        kind, idx = [], []
-        for b in range(B):
-            kind += [0] + [1] * nA[b] + [2] + [3] * nL[b]
-            idx += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(range(prot_off[b], prot_off[b + 1]))
+        kind, idx = complex_layout_np(nA, nL)
         Nw = len(kind)
         x = _assemble(Nw, H, kind, idx, [self.glb_c, comp, self.glb_p, prot], 1.0, dev)
         x = self._lin(x, self.embedding_shrink)
@@ -239,7 +236,7 @@ class FABindPlus(nn.Module):
         keep_h = keep.cpu().numpy().astype(bool)         # the one host read of this stage: sizes of the cropped graphs
         s["less5"], s["radius_pred"] = int(less5.sum().item()), radius_pred
         kept = np.nonzero(keep_h)[0]
-        nP = np.array([keep_h[s["prot_off"][b]:s["prot_off"][b + 1]].sum() for b in range(B)])
+        nP = np.add.reduceat(keep_h.astype(np.int64), s["prot_off"][:-1]) if B else np.zeros(0, np.int64)
         pocket_off = np.concatenate([[0], np.cumsum(nP)]).astype(np.int32)
         nA, comp_off, co = s["nA"], s["comp_off"], s["co"]
         pk = _i32(pocket_off, dev)
@@ -251,17 +248,10 @@ class FABindPlus(nn.Module):
         lig_init = torch.empty_like(lig)
         _lib.check(l.fb_ligand_place(lig.data_ptr(), co.data_ptr(), pocket_xyz.data_ptr(), pk.data_ptr(), B, lig_init.data_ptr(), st),
                    "fb_ligand_place")
-        kind, idx_f, idx_x = [], [], []
-        seg, msk, glb, bat = [], [], [], []
-        for b in range(B):
-            n = nA[b] + nP[b] + 2
-            kind += [0] + [1] * nA[b] + [2] + [3] * nP[b]
-            idx_f += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(kept[pocket_off[b]:pocket_off[b + 1]])
-            idx_x += [0] + list(range(comp_off[b], comp_off[b + 1])) + [0] + list(range(pocket_off[b], pocket_off[b + 1]))
-            sg = np.zeros(n, bool); sg[nA[b] + 1:] = True
-            mk = np.zeros(n, bool); mk[:nA[b] + 2] = True
-            gb = np.zeros(n, bool); gb[0] = True; gb[nA[b] + 1] = True
-            seg.append(sg); msk.append(mk); glb.append(gb); bat.append(np.full(n, b, np.int64))
+        kind, idx_f = complex_layout_np(nA, nP, kept)             # features: residue rows come from the whole-protein table
+        _, idx_x = complex_layout_np(nA, nP)                      # coordinates: from the cropped pocket table
+        seg, msk, glb = kind >= 2, kind <= 2, (kind == 0) | (kind == 2)
+        bat = np.repeat(np.arange(B, dtype=np.int64), nA + nP + 2)
         Ncx = len(kind)
         Hc = _assemble(Ncx, H, kind, idx_f, [self.glb_c, s["comp_out"], self.glb_p, s["prot_out"]], 1.0, dev)
         X = _assemble(Ncx, 3, kind, idx_x, [None, lig_init, None, pocket_xyz], 1.0 / scale, dev).unsqueeze(-2)
@@ -271,7 +261,6 @@ class FABindPlus(nn.Module):
         ael, lel = data['compound_atom_edge_list'], data['LAS_edge_list']
         c2c = (ael.x.cpu().numpy() + node_off[ael.batch.cpu().numpy()][:, None]).T
         las = (lel.x.cpu().numpy() + node_off[lel.batch.cpu().numpy()][:, None]).T
-        seg, msk, glb, bat = (np.concatenate(v) for v in (seg, msk, glb, bat))
         self.complex_model.precision = self.precision
         self.complex_model.return_pair = want_pair
         Xo, Ho, pair = self.complex_model(
