@@ -51,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
