@@ -53,9 +53,11 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // {log(1-p), log p} / tau of the clamped sigmoid (gumbel_softmax_no_random, utils.py:687-699), optional
 // straight-through hard one-hot.  mode 1: model.inference (model.py:423-437): mean of the residues whose
 // rounded sigmoid is 1, soft weights (unclamped) when none is.
+// noise (optional, mode 0 only): [n_res, 2] gumbel samples added to {log(1-p), log p} before the softmax = F.gumbel_softmax of
+// the FABind+ train()-mode forward (P/models/model.py:136-137)
 __global__ void __launch_bounds__(256) pocket_center_kernel(const float* __restrict__ logit, const float* __restrict__ xyz,
                                                             const int* __restrict__ off, float tau, int hard, int mode,
-                                                            float* __restrict__ centers) {
+                                                            float* __restrict__ centers, const float* __restrict__ noise) {
   pdl_entry();
   __shared__ float red[32];
   const int b = blockIdx.x, lo = off[b], hi = off[b + 1];
@@ -67,7 +69,9 @@ __global__ void __launch_bounds__(256) pocket_center_kernel(const float* __restr
       p1 = fminf(fmaxf(p1, 1e-6f), 1.0f - 1e-6f);
       p0 = fminf(fmaxf(p0, 1e-6f), 1.0f - 1e-6f);
     }
-    const float l0 = logf(p0) / tau, l1 = logf(p1) / tau;
+    float l0 = logf(p0), l1 = logf(p1);
+    if (noise) { l0 += noise[2 * i]; l1 += noise[2 * i + 1]; }
+    l0 /= tau; l1 /= tau;
     const float mx = fmaxf(l0, l1);
     const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
     float w = e1 / (e0 + e1);
@@ -311,7 +315,17 @@ int32_t fb_layernorm(const float* x, int32_t M, int32_t D, const float* gamma, c
 
 int32_t fb_pocket_center(const float* logit, const float* xyz, const int32_t* prot_off, int32_t B, float tau, int32_t hard,
                          int32_t mode, float* centers, void* stream) {
-  fb_launch(pocket_center_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, logit, xyz, prot_off, tau, hard, mode, centers);
+  fb_launch(pocket_center_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, logit, xyz, prot_off, tau, hard, mode, centers,
+            (const float*)nullptr);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_pocket_center_gumbel(const float* logit, const float* noise, const float* xyz, const int32_t* prot_off, int32_t B, float tau,
+                                int32_t hard, float* centers, void* stream) {
+  if (!noise) return FB_ERR_BAD_ARG;
+  fb_launch(pocket_center_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, logit, xyz, prot_off, tau, hard, 0, centers, noise);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

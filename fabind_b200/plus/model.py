@@ -116,7 +116,7 @@ class FABindPlus(nn.Module):
         return _gemm(x.contiguous(), lin.weight, lin.bias, act)
 
     # ---------------------------------------------------------------------------------------------------
-    def _pocket_stage(self, data):
+    def _pocket_stage(self, data, gumbel=False):
         """model.py:72-139"""
         l = _lib.lib()
         dev = self.glb_c.device
@@ -162,8 +162,19 @@ class FABindPlus(nn.Module):
         xyz = data.node_xyz_whole.to(dev, torch.float32).contiguous()
         po = _i32(prot_off, dev)
         centers = torch.empty((B, 3), dtype=torch.float32, device=dev)
-        _lib.check(l.fb_pocket_center(logit.data_ptr(), xyz.data_ptr(), po.data_ptr(), B, float(self.args.gs_tau),
-                                      int(bool(self.args.gs_hard)), 0, centers.data_ptr(), st), "fb_pocket_center")
+        if gumbel:
+            # train()-mode forward: F.gumbel_softmax (model.py:136-137); the noise comes from torch's generator exactly as there
+            # (gumbels = -empty.exponential_().log()), or from `self.gumbel_noise` ([n_res, 2], tests)
+            noise = getattr(self, "gumbel_noise", None)
+            if noise is None:
+                noise = -torch.empty((logit.shape[0], 2), dtype=torch.float32, device=dev).exponential_().log()
+            noise = noise.to(dev, torch.float32).contiguous()
+            _lib.check(l.fb_pocket_center_gumbel(logit.data_ptr(), noise.data_ptr(), xyz.data_ptr(), po.data_ptr(), B,
+                                                 float(self.args.gs_tau), int(bool(self.args.gs_hard)), centers.data_ptr(), st),
+                       "fb_pocket_center_gumbel")
+        else:
+            _lib.check(l.fb_pocket_center(logit.data_ptr(), xyz.data_ptr(), po.data_ptr(), B, float(self.args.gs_tau),
+                                          int(bool(self.args.gs_hard)), 0, centers.data_ptr(), st), "fb_pocket_center")
         return dict(B=B, dev=dev, H=H, cb=cb, pbw=pbw, nA=nA, nL=nL, comp_off=comp_off, prot_off=prot_off, comp_out=comp_out,
                     prot_out=prot_out, logit=logit, radius_raw=radius_raw, xyz_whole=xyz, prot_off_dev=po, co=co, centers=centers)
 
@@ -277,16 +288,12 @@ class FABindPlus(nn.Module):
         if train:
             raise NotImplementedError("fabind_b200: the training path (teacher forcing + backward) is not built; pass train=False")
         self._drop = self._sampling_setup()
-        if self._drop is not None:
-            raise NotImplementedError("fabind_b200 (FABind+): forward() in train() mode draws gumbel noise for the pocket centre "
-                                      "(model.py:136-137); sampling is served through inference() / sample(), the entry point of "
-                                      "the reference's sampling script (inference_sampling_fabind.py:181)")
         if stage != 2:
             raise NotImplementedError("fabind_b200 (FABind+): stage=1 is the teacher-forcing path of training; use stage=2")
         l = _lib.lib()
         a = self.args
         with torch.no_grad():
-            s = self._pocket_stage(data)
+            s = self._pocket_stage(data, gumbel=self.pocket_pred_model.training)
             dev, B, H, scale = s["dev"], s["B"], s["H"], self.coordinate_scale
             self._cluster_centers(s)
             Xo, Ho, pair = self._dock(s, data, want_pair=not self.confidence_training)

@@ -227,6 +227,10 @@ int32_t fb_center_rows3(const float* xyz, const int32_t* off, int32_t B, float* 
 /* out = xyz + sign * shift[segment]: data.coords -= centre (model.py:257), prediction + pocket_center_bias (model.py:684) */
 int32_t fb_shift_rows3(const float* xyz, const int32_t* off, int32_t B, int32_t n_rows, const float* shift, float sign, float* out,
                        void* stream);
+/* soft pocket centre with gumbel noise: F.gumbel_softmax(log_prob, tau, hard) of the train()-mode forward (model.py:136-137);
+ * noise = [n_res, 2] samples of -log(Exp(1)) supplied by the caller (torch's generator) */
+int32_t fb_pocket_center_gumbel(const float* logit, const float* noise, const float* xyz, const int32_t* prot_off, int32_t B, float tau,
+                                int32_t hard, float* centers, void* stream);
 /* fb_head_finish with the value range as a parameter (--dis-map-thres, model.py:385-390) */
 int32_t fb_head_finish_cap(const float* dot, int32_t tiles, int32_t stride, const float* b2, const float* pocket_xyz,
                            const float* lig_xyz, const int32_t* pocket_off, const int32_t* comp_off, const int32_t* pair_off,

@@ -315,6 +315,65 @@ def main_post_optim():
     torch.save({"cases": cases, "torch": torch.__version__}, os.path.join(OUT, "postopt_cases.pt"))
 
 
+def main_l2_plus_train_forward():
+    """FABindPlus.forward(data, stage=2) in train() mode (what test_sampling_fabind.py's validate() calls): column-only dropout
+    masks as above plus F.gumbel_softmax replaced by the same formula on INJECTED gumbel samples (model.py:136-137)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from fabind_b200.dropout import keep_mask
+    from fabind_b200.plus.model import HEAD_SITES
+    from fabind_b200.synthetic import make_docking_batch
+    mods = ref_shims.load_reference_model_module("plus")
+    emb, pemb, L, IT, bkw, wseed, dseed, pdrop = 64, 32, 2, 2, dict(n_complexes=3, seed=1), 54, 777, 0.1
+    args = ref_shims.published_args_plus(mean_layers=L, n_iter=IT, dropout=pdrop, random_n_iter=False)
+    m = mods.model.FABindPlus(args, emb, pemb)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+    n = patch_reference_dropout(m, L, dseed, pdrop, prefix="complex_model")
+    n += patch_reference_dropout(m, args.pocket_pred_layers, (dseed + 0x51ED27) & 0xFFFFFFFF, pdrop, prefix="pocket_pred_model")
+
+    class HeadDrop(nn.Module):
+        def __init__(self, site):
+            super().__init__()
+            self.site = site
+
+        def forward(self, x):
+            return x * keep_mask(dseed, self.site, 1, x.shape[-1], pdrop, colonly=True)[0] if self.training else x
+    for name, site in HEAD_SITES.items():
+        getattr(m, name).dropout = HeadDrop(site)
+    m.train()
+    d = make_docking_batch(**bkw)
+    pbw = d['protein_whole'].batch
+    g = torch.Generator().manual_seed(5)
+    noise = -torch.empty((pbw.shape[0], 2)).exponential_(generator=g).log()           # flat [n_res, 2]
+    B = int(pbw.max()) + 1
+    counts = torch.bincount(pbw, minlength=B)
+    pos = torch.arange(pbw.shape[0]) - (torch.cumsum(counts, 0) - counts)[pbw]
+    dense = torch.zeros((B, int(counts.max()), 2))
+    dense[pbw, pos] = noise
+
+    def gumbel_softmax(logits, tau=1, hard=False, eps=1e-10, dim=-1):                  # torch/nn/functional.py, noise injected
+        y_soft = ((logits + dense) / tau).softmax(dim)
+        if hard:
+            index = y_soft.max(dim, keepdim=True)[1]
+            y_hard = torch.zeros_like(logits).scatter_(dim, index, 1.0)
+            return y_hard - y_soft.detach() + y_soft
+        return y_soft
+    orig = F.gumbel_softmax
+    F.gumbel_softmax = gumbel_softmax
+    try:
+        with torch.no_grad():
+            d2 = d.clone()
+            fwd = m(d2, stage=2)
+    finally:
+        F.gumbel_softmax = orig
+    torch.save({"recipe": dict(emb=emb, pemb=pemb, mean_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, dropout_p=pdrop,
+                               dropout_seed=dseed),
+                "shapes": shapes, "noise": noise, "forward": [t.clone() if torch.is_tensor(t) else t for t in fwd],
+                "coords_after": d2.coords.clone(), "torch": torch.__version__}, os.path.join(OUT, "l2plustrainfwd_h64_p32_l2_it2.pt"))
+    print("l2plustrainfwd", [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd])
+
+
 def main_l2_plus():
     """goldens for the FABind+ L2 wrapper (FABind_plus/fabind/models/model.py::FABindPlus): forward(stage=2) in eval mode
     (13-tuple + the in-place shift of data.coords) and inference()"""
@@ -349,7 +408,7 @@ def main_l2_plus():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample", "postopt"]
+    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample", "postopt", "l2plustrainfwd"]
     if "l2plus" in which:
         main_l2_plus()
     if "plusdrop" in which:
@@ -358,6 +417,8 @@ if __name__ == "__main__":
         main_l2_plus_sampling()
     if "postopt" in which:
         main_post_optim()
+    if "l2plustrainfwd" in which:
+        main_l2_plus_train_forward()
     if "v1" in which:
         main()
     if "l2" in which:

@@ -167,3 +167,37 @@ def test_batched_sampling_equals_replicated_rows():
     assert coords.shape == (5, n, 3) and conf.shape == (5, 2) and not m.training
     d01 = float((coords[0] - coords[1]).abs().max())
     assert d01 > 1e-4 and float((coords[0] - ref_coords).abs().max()) > 1e-4
+
+
+def test_wrapper_train_mode_forward_matches_patched_reference():
+    """FABindPlus.forward(data, stage=2) in train() mode (the call of test_sampling_fabind.py's validate()): gumbel-softmax pocket
+    centre on injected noise + column-only dropout masks, all 13 outputs against the unmodified reference run the same way."""
+    from fabind_b200.config import published_args_plus
+    from fabind_b200.plus import FABindPlus
+    from fabind_b200.synthetic import make_docking_batch
+    from oracle.det_weights import det_state_dict
+    g = torch.load(os.path.join(GOLDEN_DIR, "l2plustrainfwd_h64_p32_l2_it2.pt"), map_location="cpu", weights_only=False)
+    r = g["recipe"]
+    args = published_args_plus(mean_layers=r["mean_layers"], n_iter=r["n_iter"], dropout=r["dropout_p"], random_n_iter=False)
+    m = FABindPlus(args, r["emb"], r["pemb"])
+    m.load_state_dict(det_state_dict(g["shapes"], r["weight_seed"]), strict=True)
+    m = m.cuda().train()
+    m.dropout_seed, m.dropout_colonly, m.gumbel_noise = r["dropout_seed"], True, g["noise"]
+    data = make_docking_batch(**r["batch"]).to("cuda")
+    with torch.no_grad():
+        out = m(data, stage=2)
+    ref = g["forward"]
+    assert len(out) == len(ref) == 13
+    for i, (a, b) in enumerate(zip(out, ref)):
+        if torch.is_tensor(b):
+            assert tuple(a.shape) == tuple(b.shape), i
+            if b.dtype.is_floating_point:
+                if i == 11:
+                    assert float((a.cpu() - b).abs().max()) < 1e-3, i       # relu(radius head) near its threshold
+                else:
+                    assert rel_err(a, b) < 1e-4, (i, rel_err(a, b))
+            else:
+                assert torch.equal(a.cpu().to(b.dtype), b), i
+        else:
+            assert a == b, i
+    assert rel_err(data.coords.cpu(), g["coords_after"]) < 1e-5
