@@ -7,6 +7,7 @@
 // radial term, and the per-EDGE statistics mu_e / rstd_e come from per-node sums of h and h^2.
 // All kernels: one warp per row/edge, 16-byte accesses along the feature dimension.  T = float (fp32 parity mode) / bf16.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "layers.h"
@@ -261,10 +262,145 @@ __global__ void __launch_bounds__(256) pair_zin_plus_kernel(GraphDev g, int P_to
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16 mode, H % 32 == 0: the same operation with the 32-channel product W_o32 t on the tensor cores (mma.sync m16n8k16, bf16
+// operands, fp32 accumulation): the SIMT kernel above spends 16k FMA per pair row (1.6 GFMA per launch at B = 16) plus the
+// shared-memory reads of W_o32 and ran at 139 us per launch, 17 % of a FABind+ forward; here a warp owns 16 pair rows, the
+// product costs 8 mma per 32 output features, and the kernel is bound by its HBM traffic (pair read, Zl written).
+// Two passes over the feature chunks: pass 1 accumulates the LayerNorm statistics of z = pair + W_o32 t + b, pass 2 recomputes z
+// (the pair row comes back from L1/L2) and stores the normalised row -- z itself (512 values x 2 rows per lane) never has to live
+// in registers.  Feature <-> MMA column mapping: tile j (8 columns), column n: feature (j/4)*32 + (n/2)*8 + (j%4)*2 + (n%2), so
+// that the accumulator fragments of four consecutive tiles give every lane 8 CONSECUTIVE features (16-byte pair loads / stores).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(256) pair_zin_plus_mma_kernel(GraphDev g, int P_total, int H, const bf16* __restrict__ pair,
+                                                                const float* __restrict__ pc32, int ld32,
+                                                                const float* __restrict__ WoT /*[32,H]*/, const float* __restrict__ bo,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float eps, bf16* __restrict__ Zl) {
+  extern __shared__ __align__(16) unsigned char pz_smem[];
+  const int n_tiles = H >> 3;
+  uint2* bfrag = reinterpret_cast<uint2*>(pz_smem);                      // [n_tiles][2 k-steps][32 lanes]
+  float* sb = reinterpret_cast<float*>(bfrag + n_tiles * 64);             // bo | gamma | beta, H floats each
+  for (int i = threadIdx.x; i < n_tiles * 64; i += blockDim.x) {
+    const int ln = i & 31, s = (i >> 5) & 1, j = i >> 6;
+    const int gq = ln >> 2, t = ln & 3;
+    const int f = (j >> 2) * 32 + (gq >> 1) * 8 + (j & 3) * 2 + (gq & 1);   // feature of MMA column n = gq of tile j
+    const int k0 = 16 * s + 2 * t;
+    bfrag[i] = make_uint2(pack_bf16x2(WoT[(size_t)k0 * H + f], WoT[(size_t)(k0 + 1) * H + f]),
+                          pack_bf16x2(WoT[(size_t)(k0 + 8) * H + f], WoT[(size_t)(k0 + 9) * H + f]));
+  }
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { sb[i] = bo[i]; sb[H + i] = gamma[i]; sb[2 * H + i] = beta[i]; }
+  pdl_entry();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float invH = 1.0f / (float)H;
+  const int n_chunks = H >> 5;
+  for (int pr0 = warp * 16; pr0 < P_total; pr0 += n_warps * 16) {
+    // this lane's two pair rows (fragment rows gq and gq + 8) and their interaction operand t = p32[prot] * c32[comp]
+    uint32_t a[2][4];
+    const bf16* prow[2];
+    int rows[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pr = min(pr0 + gq + 8 * h, P_total - 1);
+      rows[h] = pr;
+      const int b = find_complex_p(g.pair_base, g.B, pr);
+      const int nc1 = g.c_off[b + 1] - g.c_off[b];
+      const int loc = pr - g.pair_base[b];
+      const float* pp = pc32 + (size_t)(g.p_off[b] + loc / nc1) * ld32;
+      const float* cc = pc32 + (size_t)(g.c_off[b] + loc % nc1) * ld32 + 32;
+      prow[h] = pair + (size_t)pr * H;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int k0 = 16 * s + 2 * t;
+        const float2 p0 = *reinterpret_cast<const float2*>(pp + k0), c0 = *reinterpret_cast<const float2*>(cc + k0);
+        const float2 p1 = *reinterpret_cast<const float2*>(pp + k0 + 8), c1 = *reinterpret_cast<const float2*>(cc + k0 + 8);
+        a[s][h] = pack_bf16x2(p0.x * c0.x, p0.y * c0.y);          // a0 (row gq) / a1 (row gq + 8): k = k0, k0 + 1
+        a[s][2 + h] = pack_bf16x2(p1.x * c1.x, p1.y * c1.y);      // a2 / a3: k = k0 + 8, k0 + 9
+      }
+    }
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+    float mu[2] = {0.f, 0.f}, rstd[2] = {1.f, 1.f};
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 2
+      for (int m = 0; m < n_chunks; ++m) {
+        float acc[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) { acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.f; }
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) mma_bf16_16816(acc[jj], a[s], bfrag[((4 * m + jj) * 2 + s) * 32 + lane]);
+        const int f0 = 32 * m + 8 * t;           // this lane's 8 consecutive features of the chunk
+        const float4 b0 = *reinterpret_cast<const float4*>(sb + f0), b1 = *reinterpret_cast<const float4*>(sb + f0 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float pv[8];
+          ld8(prow[h] + f0, pv);
+          float z[8];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            z[2 * jj] = pv[2 * jj] + bb[2 * jj] + acc[jj][2 * h];
+            z[2 * jj + 1] = pv[2 * jj + 1] + bb[2 * jj + 1] + acc[jj][2 * h + 1];
+          }
+          if (pass == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s1[h] += z[i]; s2[h] = fmaf(z[i], z[i], s2[h]); }
+          } else if (pr0 + gq + 8 * h < P_total) {
+            const float4 g0 = *reinterpret_cast<const float4*>(sb + H + f0), g1 = *reinterpret_cast<const float4*>(sb + H + f0 + 4);
+            const float4 t0 = *reinterpret_cast<const float4*>(sb + 2 * H + f0), t1 = *reinterpret_cast<const float4*>(sb + 2 * H + f0 + 4);
+            const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaf((z[i] - mu[h]) * rstd[h], gm[i], bt[i]);
+            st8(Zl + (size_t)rows[h] * H + f0, o);
+          }
+        }
+      }
+      if (pass == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          // the four lanes of a quad hold disjoint feature subsets of the same two rows
+          s1[h] += __shfl_xor_sync(0xffffffffu, s1[h], 1); s1[h] += __shfl_xor_sync(0xffffffffu, s1[h], 2);
+          s2[h] += __shfl_xor_sync(0xffffffffu, s2[h], 1); s2[h] += __shfl_xor_sync(0xffffffffu, s2[h], 2);
+          mu[h] = s1[h] * invH;
+          rstd[h] = rsqrtf(fmaxf(s2[h] * invH - mu[h] * mu[h], 0.f) + eps);
+        }
+      }
+    }
+  }
+}
+
 int pair_zin_plus(const GraphDev& g, int P_total, int H, const void* pair, const float* pc32, int ld32, const float* Wo,
                   const float* bo, const float* gamma, const float* beta, float eps, void* Zl, bool bf16_mode, cudaStream_t st) {
   if (P_total <= 0) return FB_OK;
   if ((H & 3) || H > 512) return FB_ERR_UNSUPPORTED;
+  static const bool use_mma = [] { const char* e = getenv("FB_PZ_MMA"); return !(e && atoi(e) == 0); }();
+  if (bf16_mode && (H & 31) == 0 && use_mma) {
+    const int smem_m = (H >> 3) * 64 * 8 + 3 * H * 4;
+    const int grid_m = std::max(1, std::min(148 * 4, (P_total + 127) / 128));
+    static unsigned long long done_m = 0;
+    if (!ensure_smem_optin(pair_zin_plus_mma_kernel, 512 / 8 * 64 * 8 + 3 * 512 * 4, done_m)) return FB_ERR_CUDA;
+    fb_launch(pair_zin_plus_mma_kernel, dim3(grid_m), dim3(256), smem_m, st, g, P_total, H, (const bf16*)pair, pc32, ld32, Wo, bo, gamma,
+              beta, eps, (bf16*)Zl);
+    count_launch(1);
+    FB_CHECK_LAUNCH();
+    return FB_OK;
+  }
   const int smem = H * 32 * 4;
   const int grid = std::max(1, std::min(148 * 2, (P_total + 8 * PZ_R - 1) / (8 * PZ_R)));
   static unsigned long long done[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
