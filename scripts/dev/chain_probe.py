@@ -1,7 +1,7 @@
 """Development probe: latency of a CHAIN of dependent node-level GEMMs (each reads the previous output), with the
 per-kernel phase timestamps (globaltimer) of sampled CTAs, to see where the time between kernels goes."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ctypes as C
 import torch
 from fabind_b200 import _lib

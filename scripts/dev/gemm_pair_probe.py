@@ -1,6 +1,6 @@
 """Development probe: device time of the long GEMM shapes with the CTA-pair kernel (default) or the v3 kernel (FB_TC4=0)."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ctypes as C
 import torch
 from fabind_b200 import _lib

@@ -1,6 +1,6 @@
 """Development probe: phase timeline of the persistent tcgen05 GEMM (first tile of sampled CTAs)."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ctypes as C
 import torch
 from fabind_b200 import _lib

@@ -1,6 +1,6 @@
 """Development probe: event-timed tcgen05 GEMM for every shape the docking stack launches (B=16)."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import ctypes as C
 import torch
 from fabind_b200 import _lib

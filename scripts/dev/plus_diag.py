@@ -1,7 +1,7 @@
 """Development aid (FABind+ layout): (1) per-sub-layer deviation of bf16 mode from fp32 mode on the GPU, (2) per-stage
 CUDA-event breakdown of one forward at the config-4 per-GPU shape."""
 import ctypes as C, json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import ref_shims
 from oracle.det_weights import det_state_dict

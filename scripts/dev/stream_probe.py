@@ -1,6 +1,6 @@
 """Experiment: throughput when the batch of 16 is split into S sub-batches issued on S streams by S host threads."""
 import sys, os, time, threading
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 from fabind_b200.synthetic import make_batch
