@@ -180,7 +180,8 @@ int32_t fb_gemm(const fb_gemm_params* g, void* stream);
  * the compound-side / protein-side linears of a stage (cross_att.py:24-54, model_utils.py:171-175). */
 int32_t fb_gemm_pair(const fb_gemm_params* g0, const fb_gemm_params* g1, void* stream);
 int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt);
-/* development probe: when non-null, sampled CTAs of the tcgen05 GEMM write 8 globaltimer stamps each */
+/* development probe: when non-null, sampled CTAs of the tcgen05 GEMMs write globaltimer stamps; the buffer must hold at least
+ * 8192 int64 (slots up to 2048 + 19 * 16 + 15 are written) */
 int32_t fb_gemm_set_debug(int64_t* dbg);
 
 /* ---- L2 wrapper ops (reference: models/model.py, IaBNet_mean_and_pocket_prediction_cls_coords_dependent) ---- */

@@ -1,0 +1,106 @@
+"""Host-side logic that needs no GPU: node layout, weight packing (both layouts), the dropout mask function, batch replication
+for batched sampling, argument validation of the host-only C-ABI entry points."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from fabind_b200 import _lib
+from fabind_b200.dropout import keep_mask, drop_hash, threshold, site_id, iter_seed
+from fabind_b200.layout import build_layout
+from fabind_b200.synthetic import make_batch, make_docking_batch
+from fabind_b200.weights import pack_state_dict, slots
+from oracle.det_weights import det_state_dict
+from oracle import ref_shims
+
+
+def test_layout_is_a_type_sorted_permutation():
+    b = make_batch(n_complexes=4, seed=2, n_c_range=(3, 9), n_p_range=(5, 20), embed=8)
+    lay = build_layout(b.batch_id, b.segment_id, b.is_global, b.mask, "cpu")
+    o, blob = lay.offs, lay.blob.numpy()
+    N = lay.N
+    perm, inv = blob[o["perm"]:o["perm"] + N], blob[o["inv"]:o["inv"] + N]
+    assert sorted(perm.tolist()) == list(range(N)) and np.array_equal(inv[perm], np.arange(N))
+    seg = b.segment_id.numpy().astype(bool)
+    assert not seg[perm[:lay.Nc_tot]].any() and seg[perm[lay.Nc_tot:]].all()            # compound side first, then protein side
+    assert np.all(np.diff(b.batch_id.numpy()[perm[:lay.Nc_tot]]) >= 0)                   # caller order kept inside a side
+    c_off, p_off = blob[o["c_off"]:o["c_off"] + lay.B + 1], blob[o["p_off"]:o["p_off"] + lay.B + 1]
+    pair_base = blob[o["pair_base"]:o["pair_base"] + lay.B + 1]
+    assert c_off[0] == 0 and c_off[-1] == lay.Nc_tot == p_off[0] and p_off[-1] == N
+    assert np.array_equal(np.diff(pair_base), np.diff(c_off) * np.diff(p_off)) and pair_base[-1] == lay.P_total
+    assert lay.cap_int == 2 * int((np.array(b.n_c) * np.array(b.n_p)).sum())
+
+
+def test_layout_rejects_bad_batches():
+    b = make_batch(n_complexes=2, seed=1, n_c=3, n_p=5, embed=8)
+    with pytest.raises(ValueError):
+        build_layout(b.batch_id.flip(0), b.segment_id, b.is_global, b.mask, "cpu")       # unsorted batch ids
+    with pytest.raises(ValueError):
+        build_layout(b.batch_id, torch.zeros_like(b.segment_id), b.is_global, b.mask, "cpu")   # no protein side
+
+
+@pytest.mark.parametrize("flavour", [0, 1])
+def test_weight_packing_fills_every_slot(flavour):
+    """every slot the library declares is produced by the packer with the declared shape, from the reference's key set"""
+    from fabind_b200 import EfficientMCAttModel as V1
+    from fabind_b200.plus import EfficientMCAttModel as Plus
+    hidden, L = 64, 2
+    args = ref_shims.published_args_plus() if flavour else ref_shims.published_args()
+    m = (Plus if flavour else V1)(args, hidden, hidden, 1, n_layers=L, n_iter=1, normalize_coord=lambda x: x / 5.0,
+                                  unnormalize_coord=lambda x: x * 5.0)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 3)
+    arena = pack_state_dict(sd, hidden, L, flavour)
+    assert arena.dtype == torch.float32 and torch.isfinite(arena).all()
+    for name, r, c, off in slots(hidden, L, flavour):
+        blk = arena[off:off + r * c]
+        if not any(t in name for t in ("ca_c_b", "ca_p_b")):       # these carry structural zeros only in part
+            assert float(blk.abs().sum()) > 0, name
+
+
+def test_dropout_mask_function():
+    assert threshold(0.1) == int(float(np.float32(0.1)) * 2 ** 32) and threshold(0.0) == 0
+    m = keep_mask(11, site_id(2, "pair1"), 4000, 256, 0.1)
+    assert abs(float((m > 0).float().mean()) - 0.9) < 0.005 and abs(float(m.max()) - 1 / 0.9) < 1e-6
+    rows = (m > 0).float().mean(1)
+    assert float(rows.std()) < 0.03                                              # no row / column structure
+    assert not torch.equal(m, keep_mask(12, site_id(2, "pair1"), 4000, 256, 0.1))         # seed matters
+    assert not torch.equal(m, keep_mask(11, site_id(2, "pair2"), 4000, 256, 0.1))         # site matters
+    assert not torch.equal(m, keep_mask(iter_seed(11, 1), site_id(2, "pair1"), 4000, 256, 0.1))   # iteration matters
+    assert torch.equal(keep_mask(11, 5, 10, 64, 0.3, row0=7)[0], keep_mask(11, 5, 20, 64, 0.3)[7])  # row0 = offset of a row block
+    h = drop_hash(1, 2, np.arange(8), np.arange(8))
+    assert h.dtype == np.uint64 and int(h.max()) < 2 ** 32
+
+
+def test_replicate_batch_is_consistent():
+    from fabind_b200.plus.sampling import replicate_batch
+    d = make_docking_batch(2, seed=3, n_c_range=(4, 8), L_range=(30, 50))
+    r = replicate_batch(d, 3)
+    B = 2
+    n_atoms, n_res, n_wp = d['compound'].batch.shape[0], d['protein_whole'].batch.shape[0], d['complex_whole_protein'].batch.shape[0]
+    assert r['compound'].batch.tolist() == sum([[int(v) + k * B for v in d['compound'].batch] for k in range(3)], [])
+    assert torch.equal(r['compound'].node_feats[n_atoms:2 * n_atoms], d['compound'].node_feats)
+    assert torch.equal(r.node_xyz_whole[2 * n_res:], d.node_xyz_whole)
+    e, e0 = r['complex_whole_protein', 'c2c', 'complex_whole_protein'].edge_index, d['complex_whole_protein', 'c2c', 'complex_whole_protein'].edge_index
+    assert torch.equal(e[:, e0.shape[1]:2 * e0.shape[1]], e0 + n_wp)
+    wb = r['complex_whole_protein'].batch
+    assert torch.equal(wb[e[0]], wb[e[1]])                                        # every bond stays inside its replica
+    assert torch.equal(r['compound_atom_edge_list'].x[:d['compound_atom_edge_list'].x.shape[0]], d['compound_atom_edge_list'].x)
+
+
+def test_host_entry_points_validate_arguments():
+    l = _lib.lib()
+    p = _lib.ModelParams()
+    assert l.fb_graph_workspace_bytes(C.byref(p)) == -1 and l.fb_model_workspace_bytes(C.byref(p)) == -1      # all-zero params
+    p.N, p.B, p.Nc_tot, p.P_total, p.hidden, p.n_layers, p.n_iter = 100, 2, 20, 800, 64, 2, 2
+    p.cap_int, p.E_ctx = 3200, 900
+    assert l.fb_graph_workspace_bytes(C.byref(p)) > 0 and l.fb_model_workspace_bytes(C.byref(p)) > 0
+    plus = l.fb_model_workspace_bytes(C.byref(p))
+    p.flavour = _lib.FLAVOUR_PLUS
+    assert l.fb_model_workspace_bytes(C.byref(p)) > plus                          # FABind+ keeps pair ping-pong buffers
+    p.hidden = 1024
+    assert l.fb_model_workspace_bytes(C.byref(p)) == -1                           # hidden > 512 is not built
+    p.hidden, p.flavour, p.dropout_p = 64, _lib.FLAVOUR_V1, 0.1
+    assert l.fb_model_workspace_bytes(C.byref(p)) == -1                           # dropout is a FABind+ (sampling) feature
+    assert l.fb_weight_slot_info_f(64, 2, 1, 10 ** 6, None, 0, None, None, None) == -1
+    assert l.fb_gemm(None, None) == -1 and l.fb_gemm_dot_tiles(45000, 512, 512, 1, 0) == 4
