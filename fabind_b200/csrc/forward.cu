@@ -445,12 +445,15 @@ struct Run {
     gemm(b.Zg, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, b.T64, 64, 64,
          aw.pt2v, b.dotU, capU, u_dev);
     gemm_cat = CAT_GEMM_NODE;
-    stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
+    // FB_PB_FOLD=0 (A/B): separate pair_bias_finish launch + dense scatter instead of reading the row-dot partials in inter_logit
+    static const bool pb_fold = [] { const char* e = getenv("FB_PB_FOLD"); return !(e && atoi(e) == 0); }();
+    if (!pb_fold) stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
     // --- interfacial attention (egnn.py:186-252)
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
     stage(CAT_ATTENTION, [&] {
       return inter_attention(g, p.cap_int, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
-                             b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, b.lgt, b.sde, bf, st);
+                             b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, b.lgt, b.sde, bf, st,
+                             nullptr, nullptr, nullptr, 1e-5f, DropCfg(), DropCfg(), pb_fold ? b.dotU : nullptr, tiles2, capU, F(aw.pt_c));
     });
   }
 

@@ -636,6 +636,8 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 // v_e = V[c] + rn_e v_r (P/models/egnn.py:243-247); the LayerNorm is folded like in gcl_edge_pre_plus:
 //   t = rstd_e (VC[c] + rn_e u - mu_e g) + c0,  s_e = w2 . ReLU(t),  VC = (W1*gamma) V,  u = (W1*gamma) v_r,  g = (W1*gamma) 1
 // with mu_e / rstd_e from the per-node sums vstat[c] = {sum V, sum V^2, sum V*v_r} and ac_r = {sum v_r, sum v_r^2}.
+struct PbDot { const float* dot = nullptr; int tiles = 0, stride = 0, n_u = 0; const float* cst = nullptr; };
+
 template <typename T, int VEC, bool PLUS>
 __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, const float* __restrict__ QK, int ldqk,
                                                           const float* __restrict__ Kt, int ldk, const T* __restrict__ VC, int ldv,
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, con
                                                           const float* __restrict__ vstat, float eps,
                                                           const float* __restrict__ rad, const float* __restrict__ norm,
                                                           const float* __restrict__ pb_dense, float* __restrict__ logit,
-                                                          float* __restrict__ sdot_out, DropCfg dc) {
+                                                          float* __restrict__ sdot_out, DropCfg dc, PbDot pd) {
   constexpr bool FAST = !std::is_same<T, float>::value;   // bf16 mode: one-MUFU SiLU
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -662,7 +664,22 @@ __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, con
   for (int e = warp; e < E; e += n_warps) {
     const int r = g.int_row[e], c = g.int_col[e];
     const float rn = rad[e] / radial_norm(norm, g.node_cplx[r]);
-    const float pb = pb_dense[g.int_pair[e]];
+    float pb;
+    if (pd.dot) {
+      // v1: attention bias of the pair straight from the row-dot partials of the pair GEMM (one row per UNIQUE pair = per
+      // compound->protein edge u, which is that edge's own index; a protein->compound edge looks its mirror up in the compound
+      // row, whose columns are sorted) -- saves the pair_bias_finish launch and the dense scatter
+      int u = e;
+      if (e >= g.int_rowptr[g.Nc_tot]) {
+        int lo = g.int_rowptr[c], hi = g.int_rowptr[c + 1] - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.int_col[mid] < r) lo = mid + 1; else hi = mid; }
+        u = lo;
+      }
+      pb = pd.cst[0];
+      for (int t = 0; t < pd.tiles; ++t) pb += pd.dot[(size_t)t * pd.stride + u];
+    } else {
+      pb = pb_dense[g.int_pair[e]];
+    }
     float mu = 0.f, rstd = 1.f;
     if (PLUS) {
       const float invH = 1.0f / (float)H;
@@ -791,16 +808,19 @@ int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int 
                     const float* v_r, const float* ac_u, const float* ac_b, const float* ac_w2, const float* rad,
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st,
-                    const float* ac_g, const float* ac_r, const float* vstat, float eps, DropCfg drop_coord, DropCfg drop_agg) {
+                    const float* ac_g, const float* ac_r, const float* vstat, float eps, DropCfg drop_coord, DropCfg drop_agg,
+                    const float* pb_dot, int pb_tiles, int pb_stride, const float* pb_cst) {
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
+  PbDot pd;
+  if (pb_dot) { pd.dot = pb_dot; pd.tiles = pb_tiles; pd.stride = pb_stride; pd.cst = pb_cst; pd.n_u = -1; }
   const int grid1 = std::max(1, std::min(148 * 8, (cap_int + 7) / 8));
   const bool plus = vstat != nullptr;
 #define FB_IL(T, VEC)                                                                                                        \
   do {                                                                                                                       \
     if (plus) fb_launch(inter_logit_kernel<T, VEC, true>, dim3(grid1), dim3(256), 5 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
-                        ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord);                    \
+                        ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord, pd);                \
     else fb_launch(inter_logit_kernel<T, VEC, false>, dim3(grid1), dim3(256), 4 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
-                   ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord);                         \
+                   ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord, pd);                     \
   } while (0)
   if (bf16_mode) {
     if (H <= 128) FB_IL(bf16, 1); else if (H <= 256) FB_IL(bf16, 2); else FB_IL(bf16, 4);

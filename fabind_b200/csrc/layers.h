@@ -31,7 +31,9 @@ int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int 
                     const float* norm, const float* pb_dense, const float* x, float cmax, float* h, void* hT,
                     float* x_out, float* att, float* logit_ws, float* sdot_ws, bool bf16_mode, cudaStream_t st,
                     const float* ac_g = nullptr, const float* ac_r = nullptr, const float* vstat = nullptr, float eps = 1e-5f,
-                    DropCfg drop_coord = DropCfg(), DropCfg drop_agg = DropCfg());
+                    DropCfg drop_coord = DropCfg(), DropCfg drop_agg = DropCfg(),
+                    // v1: pair bias from the pair GEMM's row-dot partials instead of pb_dense (see inter_logit_kernel)
+                    const float* pb_dot = nullptr, int pb_tiles = 0, int pb_stride = 0, const float* pb_cst = nullptr);
 // ---- FABind+ layout (plus.cu) ----
 int row_stats(const void* x, int ld, int M, int H, const float* w, float* out, bool typed_bf16, cudaStream_t st);
 int ln_rows(const void* x1, bool x1_typed, int ld1, int H1, const void* x2, int ld2, int H2, int M, const float* gamma,

@@ -42,7 +42,7 @@ def packed_arena(module, args, hidden, n_layers, prefix, device):
 def _csr(edges, inv, N):
     r = inv[edges[0]]
     c = inv[edges[1]]
-    order = np.argsort(r, kind="stable")
+    order = np.lexsort((c, r))     # rows ascending, columns ascending inside a row (inter_logit looks mirror edges up by bisection)
     rowptr = np.concatenate([[0], np.cumsum(np.bincount(r, minlength=N))]).astype(np.int32)
     return rowptr, r[order].astype(np.int32), c[order].astype(np.int32), order
 
