@@ -80,3 +80,58 @@ def test_batch_independence_and_determinism():
     one.LAS_edge_index = (b.LAS_edge_index[:, lm] - 5 * n).contiguous()
     X1, H1 = _run(m, one)
     assert rel_err(X1, Xa[sl]) < 1e-5 and rel_err(H1, Ha[sl]) < 1e-5
+
+
+# ---- FABind+ layout at its published size (5 layers x 8 iterations, hidden 512, 16 complexes) --------------------------------
+def _plus_model(precision="fp32", head_std=0.5):
+    from fabind_b200.config import published_args_plus
+    from fabind_b200.plus import EfficientMCAttModel as PlusModel
+    torch.manual_seed(0)
+    m = PlusModel(published_args_plus(random_n_iter=False), 512, 512, 1, n_layers=5, n_iter=8, normalize_coord=lambda x: x / 5.0,
+                  unnormalize_coord=lambda x: x * 5.0)
+    randomize_coord_heads(m, std=head_std)
+    m = m.cuda().eval()
+    m.precision = precision
+    return m
+
+
+def _run_plus(m, b):
+    with torch.no_grad():
+        X, H, pair = m(**b.to("cuda").forward_args())
+    torch.cuda.synchronize()
+    return X.cpu(), H.cpu(), pair.cpu()
+
+
+def test_plus_equivariance_full_size():
+    """rigid motion of the inputs: coordinates follow, node features AND the propagated pair embedding are invariant.
+    Coordinate heads 10x smaller than in the v1 test: with O(1) heads the LayerNorm stack amplifies a single borderline edge flip
+    (the cutoffs are <= comparisons on rotated fp32 coordinates) over the 8 iterations - see test_gpu_plus.py on the same effect."""
+    m = _plus_model(head_std=0.05)
+    b = make_batch(n_complexes=16, n_c=30, n_p=200, seed=101)
+    X0, H0, P0 = _run_plus(m, b)
+    b2 = b.clone()
+    R, t = _rotation(9), torch.tensor([-0.22, 0.4, 0.05])
+    b2.X = (b.X.squeeze(1) @ R.T + t).unsqueeze(1).contiguous()
+    b2.X_LAS = (b.X_LAS.squeeze(1) @ R.T).unsqueeze(1).contiguous()
+    X1, H1, P1 = _run_plus(m, b2)
+    X0r = (X0.squeeze(1) @ R.T + t).unsqueeze(1)
+    errs = (rel_err(X1, X0r), rel_err(H1, H0), rel_err(P1, P0), float((X0 - b.X).abs().max()))
+    assert errs[3] > 0.05, errs                       # the ligands did move
+    assert errs[0] < 5e-3 and errs[1] < 5e-3 and errs[2] < 5e-3, errs
+
+
+def test_plus_determinism_eval_and_sampling():
+    """no atomics on the path: eval mode and sampling mode (fixed seed) are bit-reproducible at full size in the bf16 production
+    mode; the dense pair embedding is zero outside every complex's own block"""
+    m = _plus_model("bf16")
+    b = make_batch(n_complexes=16, n_c_range=(10, 40), n_p_range=(120, 200), seed=102)
+    a, c = _run_plus(m, b), _run_plus(m, b)
+    assert all(torch.equal(u, v) for u, v in zip(a, c))
+    pair = a[2]
+    for i in range(16):
+        assert float(pair[i, b.n_p[i] + 1:].abs().sum()) == 0.0 and float(pair[i, :, b.n_c[i] + 1:].abs().sum()) == 0.0
+    m.train()
+    m.dropout_seed = 17
+    s1, s2 = _run_plus(m, b), _run_plus(m, b)
+    assert all(torch.equal(u, v) for u, v in zip(s1, s2))
+    assert float((s1[1] - a[1]).abs().max()) > 1e-3          # and it is a different sample than the eval pass
