@@ -3,7 +3,8 @@
 Same constructor signature, parameter names/shapes (reference checkpoints load with strict=True) and the return tuples of
 `forward(data, stage=2)` in eval mode (model.py:63-401: the 13-tuple, plus the in-place shift of `data.coords`) and
 `inference(data)` (model.py:403-697).  Published configuration (README.md:125-141): --use-for-radius-pred ligand, no clustering,
-no confidence head; `stage=1` (teacher forcing with the dataloader's pocket) is a training-time path and raises.
+`stage=1` (the dataloader's pocket) and `stage=2` (predicted pocket) in eval mode, sampling mode under train() + no_grad,
+optional DBSCAN clustering and confidence head; `train=True` raises.
 All arithmetic runs in libfabind_b200 kernels; the host side does index bookkeeping only.
 """
 import numpy as np
@@ -282,23 +283,83 @@ class FABindPlus(nn.Module):
         s.update(nP=nP, pocket_off=pocket_off, pocket_xyz=pocket_xyz, seg=seg, glb=glb, pk=pk, lig=lig, bias=bias)
         return Xo, Ho, pair
 
+    def _dock_stage1(self, s, data, want_pair):
+        """model.py:169-197 (stage == 1): the dataloader's pocket (`data['pocket'].keepNode`) and pre-built complex graph; the ligand
+        is re-centred on its own mean, the pocket moved by `data.pocket_residue_center`; `data['complex'].node_coords` and
+        `data.coords` are updated like the reference does in place."""
+        l = _lib.lib()
+        dev, B, H, scale = s["dev"], s["B"], s["H"], self.coordinate_scale
+        st = current_stream_ptr(dev)
+        cx = data['complex']
+        kept = np.nonzero(data['pocket'].keepNode.cpu().numpy().astype(bool))[0]
+        nP = np.bincount(data['pocket'].batch.cpu().numpy(), minlength=B)
+        pocket_off = np.concatenate([[0], np.cumsum(nP)]).astype(np.int32)
+        nA, co = s["nA"], s["co"]
+        pk = _i32(pocket_off, dev)
+        kind, idx_f = complex_layout_np(nA, nP, kept)
+        _, idx_x = complex_layout_np(nA, nP)
+        Ncx = len(kind)
+        Hc = _assemble(Ncx, H, kind, idx_f, [self.glb_c, s["comp_out"], self.glb_p, s["prot_out"]], 1.0, dev)
+        cxc = cx.node_coords.to(dev, torch.float32).contiguous()
+        lig_raw = _select(cxc, np.nonzero(kind == 1)[0])
+        pocket_raw = _select(cxc, np.nonzero(kind == 3)[0])
+        lig_c = torch.empty_like(lig_raw)
+        lig_mean = torch.empty((B, 3), dtype=torch.float32, device=dev)
+        _lib.check(l.fb_center_rows3(lig_raw.data_ptr(), co.data_ptr(), B, lig_c.data_ptr(), lig_mean.data_ptr(), st), "fb_center_rows3")
+        prc = data.pocket_residue_center.to(dev, torch.float32).contiguous()
+        pocket_s = torch.empty_like(pocket_raw)
+        _lib.check(l.fb_shift_rows3(pocket_raw.data_ptr(), pk.data_ptr(), B, pocket_raw.shape[0], prc.data_ptr(), -1.0,
+                                    pocket_s.data_ptr(), st), "fb_shift_rows3")
+        Xun = _assemble(Ncx, 3, kind, idx_x, [None, lig_c, None, pocket_s], 1.0, dev)
+        cx.node_coords = Xun.to(cx.node_coords.device)                                # in-place effect of model.py:179-182
+        if getattr(data, "coords", None) is not None:                                 # model.py:184
+            gt = data.coords.to(dev, torch.float32).contiguous()
+            gt_out = torch.empty_like(gt)
+            _lib.check(l.fb_shift_rows3(gt.data_ptr(), co.data_ptr(), B, gt.shape[0], prc.data_ptr(), -1.0, gt_out.data_ptr(), st),
+                       "fb_shift_rows3")
+            data.coords = gt_out.to(data.coords.device)
+        X = _select(Xun, np.arange(Ncx), 1.0 / scale).unsqueeze(-2)
+        XL = _select(cx.node_coords_LAS.to(dev, torch.float32), np.arange(Ncx), 1.0 / scale).unsqueeze(-2)
+        seg, glb = kind >= 2, (kind == 0) | (kind == 2)
+        self.complex_model.precision = self.precision
+        self.complex_model.return_pair = want_pair
+        Xo, Ho, pair = self.complex_model(
+            X.contiguous(), Hc, batch_id=cx.batch, segment_id=cx.segment, mask=cx.mask, is_global=cx.is_global,
+            compound_edge_index=data['complex', 'c2c', 'complex'].edge_index.to(dev),
+            LAS_edge_index=data['complex', 'LAS', 'complex'].edge_index.to(dev), batched_complex_coord_LAS=XL.contiguous(), LAS_mask=None)
+        bias = torch.zeros((B, 3), dtype=torch.float32, device=dev)
+        # pocket_radius_pred = relu(head) is still returned in stage 1 (model.py:114,399): the crop kernel delivers it (its mask is unused)
+        xyz, a = s["xyz_whole"], self.args
+        keep = torch.empty(xyz.shape[0], dtype=torch.uint8, device=dev)
+        less5 = torch.empty(B, dtype=torch.int32, device=dev)
+        radius_pred = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        _lib.check(l.fb_pocket_mask_r(xyz.data_ptr(), s["prot_off_dev"].data_ptr(), B, s["centers"].data_ptr(), s["radius_raw"].data_ptr(),
+                                      float(a.pocket_radius_buffer), float(a.min_pocket_radius), -1.0, keep.data_ptr(), less5.data_ptr(),
+                                      radius_pred.data_ptr(), st), "fb_pocket_mask_r")
+        s.update(nP=nP, pocket_off=pocket_off, pocket_xyz=data.node_xyz.to(dev, torch.float32).contiguous(), seg=seg, glb=glb, pk=pk,
+                 lig=lig_raw, bias=bias, less5=0, radius_pred=radius_pred)
+        return Xo, Ho, pair
+
     # ---------------------------------------------------------------------------------------------------
     def forward(self, data, stage=2, train=False):
         """eval semantics of model.py:63-401 with stage=2, train=False (the predicted pocket is used for docking)."""
         if train:
             raise NotImplementedError("fabind_b200: the training path (teacher forcing + backward) is not built; pass train=False")
         self._drop = self._sampling_setup()
-        if stage != 2:
-            raise NotImplementedError("fabind_b200 (FABind+): stage=1 is the teacher-forcing path of training; use stage=2")
+        if stage not in (1, 2):
+            raise ValueError("stage must be 1 or 2")
         l = _lib.lib()
         a = self.args
         with torch.no_grad():
             s = self._pocket_stage(data, gumbel=self.pocket_pred_model.training)
             dev, B, H, scale = s["dev"], s["B"], s["H"], self.coordinate_scale
             self._cluster_centers(s)
-            Xo, Ho, pair = self._dock(s, data, want_pair=not self.confidence_training)
+            if stage == 1:
+                Xo, Ho, pair = self._dock_stage1(s, data, want_pair=not self.confidence_training)
+            else:
+                Xo, Ho, pair = self._dock(s, data, want_pair=not self.confidence_training)
             if self.confidence_training:
-                return self._forward_confidence(s, data, Xo, Ho)
+                return self._forward_confidence(s, data, Xo, Ho, shift_coords=stage == 2)
             st = current_stream_ptr(dev)
             seg, glb = s["seg"], s["glb"]
             c_rows = np.nonzero(~seg & ~glb)[0]
@@ -321,6 +382,14 @@ class FABindPlus(nn.Module):
                                             pocket_n.data_ptr(), lig_n.data_ptr(), s["pk"].data_ptr(), s["co"].data_ptr(), qo.data_ptr(),
                                             B, Q, float(scale), float(a.dis_map_thres), y_pred.data_ptr(), y_coords.data_ptr(), st),
                        "fb_head_finish_cap")
+            if stage == 1:
+                compound_coords_out = _select(Xo.view(-1, 3), c_rows, scale)
+                cls_dense, pmask, kind, idx, Lmax = self._dense_cls(s)
+                coords_dense = _assemble(B * Lmax, 3, kind, idx, [None, s["xyz_whole"]], 1.0, dev).view(B, Lmax, 3)
+                pocket_cls = torch.zeros((B, Lmax), dtype=data.pocket_idx.dtype, device=dev)
+                pocket_cls[pmask] = data.pocket_idx.to(dev)
+                return (compound_coords_out, data['compound'].batch, y_pred, y_coords, cls_dense, pocket_cls, pmask, coords_dense,
+                        s["centers"], data.dis_map.to(dev), 0, s["radius_pred"], s["bias"])
             # label-side bookkeeping the reference does inside forward: dis_map against the shifted ligand, data.coords -= centre
             lig_shift = torch.empty_like(s["lig"])
             _lib.check(l.fb_shift_rows3(s["lig"].data_ptr(), s["co"].data_ptr(), B, s["lig"].shape[0], s["bias"].data_ptr(), -1.0,
@@ -363,12 +432,12 @@ class FABindPlus(nn.Module):
         cls_dense = _assemble(B * Lmax, 1, kind, idx, [None, s["logit"].view(-1, 1)], 1.0, dev).view(B, Lmax)
         return cls_dense, torch.from_numpy(mask_h).to(dev), kind, idx, Lmax
 
-    def _forward_confidence(self, s, data, Xo, Ho):
+    def _forward_confidence(self, s, data, Xo, Ho, shift_coords=True):
         """return tuple of model.py:399 (confidence_training)"""
         l = _lib.lib()
         dev, B = s["dev"], s["B"]
         c_rows = np.nonzero(~s["seg"] & ~s["glb"])[0]
-        if getattr(data, "coords", None) is not None:        # data.coords -= pocket centre (model.py:257)
+        if shift_coords and getattr(data, "coords", None) is not None:        # data.coords -= pocket centre (model.py:257)
             gt = data.coords.to(dev, torch.float32).contiguous()
             gt_out = torch.empty_like(gt)
             _lib.check(l.fb_shift_rows3(gt.data_ptr(), s["co"].data_ptr(), B, gt.shape[0], s["bias"].data_ptr(), -1.0, gt_out.data_ptr(),

@@ -204,7 +204,7 @@ def make_docking_batch(n_complexes=2, seed=0, n_c_range=(10, 40), L_range=(150, 
     cx_coords, cx_las, cx_seg, cx_mask, cx_glb, cx_batch, cx_c2c, cx_LAS = [], [], [], [], [], [], [], []
     ael_x, ael_b, lel_x, lel_b = [], [], [], []
     pocket_xyz, pocket_batch, keep_all, dis_map, centers = [], [], [], [], []
-    lig_true_all = []
+    lig_true_all, pocket_centers = [], []
     off_wp = off_cx = 0
     for b in range(n_complexes):
         nc = int(rng.integers(n_c_range[0], n_c_range[1] + 1))
@@ -266,7 +266,7 @@ def make_docking_batch(n_complexes=2, seed=0, n_c_range=(10, 40), L_range=(150, 
         pocket_idx.append(keep.astype(np.int32)); keep_all.append(keep)
         pocket_xyz.append(pocket); pocket_batch.append(np.full(int(keep.sum()), b))
         dmap = np.linalg.norm(pocket[:, None] - lig_true[None], axis=-1).reshape(-1)
-        dis_map.append(np.minimum(dmap, 10.0)); centers.append(com); lig_true_all.append(lig_true)
+        dis_map.append(np.minimum(dmap, 10.0)); centers.append(com); lig_true_all.append(lig_true); pocket_centers.append(pocket.mean(0))
         off_wp += n_wp; off_cx += n_cx
     f = lambda a, ax=0: torch.from_numpy(np.concatenate(a, ax)).float()
     li = lambda a, ax=0: torch.from_numpy(np.concatenate(a, ax).astype(np.int64))
@@ -287,5 +287,6 @@ def make_docking_batch(n_complexes=2, seed=0, n_c_range=(10, 40), L_range=(150, 
     d.coords_center = torch.from_numpy(np.stack(centers)).float()
     d.pocket_idx = torch.from_numpy(np.concatenate(pocket_idx))
     d.dis_map = f(dis_map)
+    d.pocket_residue_center = torch.from_numpy(np.stack(pocket_centers)).float()   # FABind+ dataloader field (P/models/model.py:179)
     d.coords = f(lig_true_all)            # ground-truth ligand pose (FABind+ model.forward shifts it in place, P/models/model.py:257)
     return d

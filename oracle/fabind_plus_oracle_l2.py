@@ -137,8 +137,34 @@ def _dock(sd, args, di):
                               (di['XL'] / scale).unsqueeze(-2))
 
 
+def stage1_inputs(sd, args, data, B, comp_out, prot_out):
+    """model.py:169-197 (stage == 1, teacher forcing with the dataloader's pocket): ligand re-centred on its own mean, pocket
+    moved by `data.pocket_residue_center`; mutates data['complex'].node_coords and data.coords like the reference."""
+    cb, pkb, cxb = data['compound'].batch, data['pocket'].batch, data['complex'].batch
+    pemb = prot_out[data['pocket'].keepNode]
+    feats = []
+    for i in range(B):
+        n_c = int((cb == i).sum())
+        tc = data['complex'].node_coords[cxb == i]
+        tc[1:n_c + 1] = tc[1:n_c + 1] - tc[1:n_c + 1].mean(dim=0)
+        tc[n_c + 2:] = tc[n_c + 2:] - data.pocket_residue_center[i].unsqueeze(0)
+        data['complex'].node_coords[cxb == i] = tc
+        data.coords[cb == i] = data.coords[cb == i] - data.pocket_residue_center[i].unsqueeze(0)
+        feats += [sd['glb_c'], comp_out[cb == i], sd['glb_p'], pemb[pkb == i]]
+    cx = data['complex']
+    return dict(H=torch.cat(feats), X=cx.node_coords, XL=cx.node_coords_LAS, seg=cx.segment.to(torch.bool), mask=cx.mask,
+                glb=cx.is_global, batch=cx.batch, c2c=data['complex', 'c2c', 'complex'].edge_index,
+                las=data['complex', 'LAS', 'complex'].edge_index, pocket_xyz=data.node_xyz, pocket_batch=pkb,
+                dis_map=data.dis_map, less5=0, bias=torch.zeros((B, 3)))
+
+
 def forward_stage2(sd, args, data):
-    """model.py:63-401 with model.eval(), stage=2, train=False -> the reference's 13-tuple (mutates data.coords)."""
+    return forward_eval(sd, args, data, 2)
+
+
+def forward_eval(sd, args, data, stage):
+    """model.py:63-401 with model.eval(), train=False -> the reference's 13-tuple (mutates data.coords).  stage 2: predicted
+    pocket; stage 1: the dataloader's pocket (the periodic test evaluation of main_fabind.py:179)."""
     if getattr(args, "only_last_LAS", False) or getattr(args, "use_clustering", False):
         raise NotImplementedError
     scale = args.coordinate_scale
@@ -146,7 +172,10 @@ def forward_stage2(sd, args, data):
     pbw, cb = data['protein_whole'].batch, data['compound'].batch
     cls_dense, pmask, coords_dense, centers = soft_centers(args, logit, pbw, B, data)
     pocket_cls, _ = _dense(data.pocket_idx, pbw, B, fill=0)
-    di = docking_inputs(sd, args, data, B, comp_out, prot_out, centers, radius_pred, shift_data_coords=True)
+    if stage == 1:
+        di = stage1_inputs(sd, args, data, B, comp_out, prot_out)
+    else:
+        di = docking_inputs(sd, args, data, B, comp_out, prot_out, centers, radius_pred, shift_data_coords=True)
     X, H, pair = _dock(sd, args, di)
     seg, glb = di['seg'], di['glb']
     lig_xyz = X[~seg & ~glb].squeeze(-2)

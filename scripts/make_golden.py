@@ -399,10 +399,15 @@ def main_l2_plus():
             d2 = d.clone()
             fwd = m(d2, stage=2)
             inf = m.inference(d.clone())
+            d1 = d.clone()
+            fwd1 = m(d1, stage=1)
         torch.save({"recipe": dict(emb=emb, pemb=pemb, mean_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, args_over=over,
                                    radius_bias=9.0 if over else None),
                     "shapes": shapes, "forward": [t.clone() if torch.is_tensor(t) else t for t in fwd],
-                    "coords_after": d2.coords.clone(), "inference": inf[0].clone(), "torch": torch.__version__},
+                    "coords_after": d2.coords.clone(), "inference": inf[0].clone(),
+                    "forward_stage1": [t.clone() if torch.is_tensor(t) else t for t in fwd1],
+                    "coords_after_stage1": d1.coords.clone(), "complex_coords_after_stage1": d1['complex'].node_coords.clone(),
+                    "torch": torch.__version__},
                    os.path.join(OUT, name + ".pt"))
         print(name, [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd], "radius", fwd[11].flatten().tolist())
 

@@ -57,6 +57,14 @@ def test_l2plus_golden(path):
     assert rel_err(d.coords.cpu(), g["coords_after"]) < 1e-5          # in-place shift of data.coords (model.py:257)
     inf = m.inference(data.to("cuda"))
     assert rel_err(inf[0].cpu(), g["inference"]) < 1e-4
+    # stage 1: the dataloader's pocket (main_fabind.py:179 evaluates the test set this way), incl. the in-place coordinate shifts
+    d1 = data.to("cuda")
+    out1 = m(d1, stage=1)
+    torch.cuda.synchronize()
+    rec1 = _compare(out1, g["forward_stage1"], "l2plus_golden_forward_stage1", skip=(11,) if float(g["forward_stage1"][11].max()) < 1e-2 else ())
+    assert max(rec1.values()) < 1e-4, rec1
+    assert rel_err(d1.coords.cpu(), g["coords_after_stage1"]) < 1e-5
+    assert rel_err(d1['complex'].node_coords.cpu(), g["complex_coords_after_stage1"]) < 1e-5
 
 
 def test_l2plus_vs_oracle_published_width():

@@ -71,6 +71,12 @@ def test_l2plus_oracle_matches_golden(path):
     compare_tuple(out, g["forward"])
     assert rel_err(d2.coords, g["coords_after"]) < 1e-6          # in-place shift of the ground-truth pose (model.py:257)
     assert rel_err(inf[0], g["inference"]) < 1e-5
+    with torch.no_grad():                                        # stage 1: the dataloader's pocket (model.py:169-197)
+        d1 = data.clone()
+        out1 = l2p.forward_eval(sd, args, d1, 1)
+    compare_tuple(out1, g["forward_stage1"])
+    assert rel_err(d1.coords, g["coords_after_stage1"]) < 1e-6
+    assert rel_err(d1['complex'].node_coords, g["complex_coords_after_stage1"]) < 1e-6
 
 
 def test_l2plus_golden_present():
