@@ -125,7 +125,6 @@ if "post" in WHICH or len(sys.argv) == 1:
     import numpy as np
     from fabind_b200.post_optim import post_optimize_batch
     from fabind_b200.synthetic import _one_complex
-    from oracle.post_optim_oracle import post_optimize as po_cpu
     refs, preds, batch, las_l, las_b = [], [], [], [], []
     rng = np.random.default_rng(0)
     for b in range(64):
@@ -135,6 +134,5 @@ if "post" in WHICH or len(sys.argv) == 1:
         batch.append(torch.full((n,), b)); las_l.append(torch.tensor(las.T.copy())); las_b.append(torch.full((las.shape[0],), b))
     R, P_, Bt, L_, Lb = torch.cat(refs).to(dev), torch.cat(preds).to(dev), torch.cat(batch).to(dev), torch.cat(las_l, 1).to(dev), torch.cat(las_b).to(dev)
     ms = timed(lambda: post_optimize_batch(R, P_, Bt, L_, Lb, total_epoch=1000), steps=3, warmup=1)
-    t0 = time.perf_counter(); po_cpu(refs[0], preds[0], 1000, las_l[0]); cpu_s = time.perf_counter() - t0
     print(json.dumps(dict(config="post-optimisation: 64 ligands (10-80 atoms) x 1000 Adam steps, one launch", ms=round(ms, 2),
-                          ligands_per_s=round(64e3 / ms, 1), cpu_port_s_per_ligand=round(cpu_s, 3), cpu_atoms=int(refs[0].shape[0]))))
+                          ligands_per_s=round(64e3 / ms, 1))))

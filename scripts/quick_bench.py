@@ -2,7 +2,7 @@
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import ref_shims
+from fabind_b200.config import published_args, published_args_plus
 from fabind_b200 import EfficientMCAttModel
 from fabind_b200.synthetic import make_batch
 
@@ -14,11 +14,11 @@ flavour = sys.argv[5] if len(sys.argv) > 5 else "v1"
 torch.manual_seed(0)
 if flavour == "plus":
     from fabind_b200.plus import EfficientMCAttModel as PlusModel
-    m = PlusModel(ref_shims.published_args_plus(), 512, 512, 1, n_layers=L, n_iter=IT,
+    m = PlusModel(published_args_plus(), 512, 512, 1, n_layers=L, n_iter=IT,
                   normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0).cuda().eval()
     m.return_pair = os.environ.get("QB_PAIR", "0") == "1"
 else:
-    m = EfficientMCAttModel(ref_shims.published_args(), 512, 512, 1, n_layers=L, n_iter=IT,
+    m = EfficientMCAttModel(published_args(), 512, 512, 1, n_layers=L, n_iter=IT,
                             normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0).cuda().eval()
 m.precision = prec
 b = make_batch(n_complexes=B, seed=0, n_c=30, n_p=200).to("cuda")
