@@ -568,25 +568,47 @@ struct Run {
     gemm_cat = CAT_GEMM_NODE;
     if (e.steps & FB_STEP_LINEAR_IN) gemm(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H);
     else chk(convert_copy(b.Hin32, (size_t)N * H, b.h, bf ? b.hT : nullptr, bf, st));
+    const bool plus = w.flavour == 1;
     if ((e.steps & FB_STEP_ATT) && p.n_layers > 0) {
       chk(convert_copy(e.pair0, P * H, nullptr, b.P0, bf, st));
-      const int pbc = pb_cols(p.n_layers);
-      gemm_cat = CAT_GEMM_PAIR0;
-      gemm(b.P0, H, H, w.pb_w, pbc, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, pbc, nullptr, 0);
-      stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, p.n_layers, b.PBraw, pbc, b.PB, st); });
-      gemm_cat = CAT_GEMM_NODE;
+      if (!plus) {
+        const int pbc = pb_cols(p.n_layers);
+        gemm_cat = CAT_GEMM_PAIR0;
+        gemm(b.P0, H, H, w.pb_w, pbc, w.pb_b, FB_ACT_NONE, (int)P, b.PBraw, pbc, nullptr, 0);
+        stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, p.n_layers, b.PBraw, pbc, b.PB, st); });
+        gemm_cat = CAT_GEMM_NODE;
+      }
     }
     const float* xc = b.x_state;
     float* bufs[2] = {b.xa, b.xb};
     int k = 0;
+    const void* pair_cur = b.P0;   // FABind+: propagated layer to layer (P/models/egnn.py:380-392)
     for (int l = 0; l < p.n_layers; ++l) {
-      if (e.steps & FB_STEP_GCL) { run_gcl(w.gcl[l], xc, bufs[k], true); xc = bufs[k]; k ^= 1; }
+      cur_layer = l;
+      if (e.steps & FB_STEP_GCL) {
+        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true); else run_gcl(w.gcl[l], xc, bufs[k], true);
+        xc = bufs[k]; k ^= 1;
+      }
       if (e.steps & FB_STEP_ATT) {
-        run_att(w.att[l], l, xc, bufs[k], e.att_out ? e.att_out + (size_t)l * e.E_int : nullptr); xc = bufs[k]; k ^= 1;
+        float* att_l = e.att_out ? e.att_out + (size_t)l * e.E_int : nullptr;
+        if (plus) {
+          void* pair_next = (l & 1) ? b.PairB : b.PairA;
+          run_att_plus(w.attp[l], pair_cur, pair_next, xc, bufs[k], att_l);
+          pair_cur = pair_next;
+        } else {
+          run_att(w.att[l], l, xc, bufs[k], att_l);
+        }
+        xc = bufs[k]; k ^= 1;
       }
       if (e.steps & FB_STEP_LAS) { chk(las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st)); xc = bufs[k]; k ^= 1; }
     }
-    if (e.steps & FB_STEP_OUT_LAYER) { run_gcl(w.gcl[p.n_layers], xc, bufs[k], true); xc = bufs[k]; k ^= 1; }
+    if (e.steps & FB_STEP_OUT_LAYER) {
+      cur_layer = p.n_layers;
+      if (plus) run_gcl_plus(w.gclp[p.n_layers], xc, bufs[k], true); else run_gcl(w.gcl[p.n_layers], xc, bufs[k], true);
+      xc = bufs[k]; k ^= 1;
+    }
+    if (plus && (e.steps & FB_STEP_ATT) && p.pair_out)
+      chk(pair_unpack(g, (int)P, H, p.max_p, p.max_c, pair_cur, p.pair_out, bf, st));
     if (e.steps & FB_STEP_LINEAR_OUT) {
       gemm(b.hT, H, H, w.out_w, H, w.out_b, FB_ACT_NONE, N, b.Hfin, H, nullptr, 0);
       chk(permute_out_h(g, b.Hfin, H, p.H_out, st));
@@ -793,8 +815,9 @@ int32_t fb_egnn_forward(const fb_model_params* p, const fb_egnn_extra* e, void* 
   if (!p || !e || p->N <= 0 || p->B <= 0 || p->hidden <= 0 || (p->hidden % 8) || p->hidden > 512 || p->E_ctx < 0) return FB_ERR_BAD_ARG;
   if ((e->steps & FB_STEP_ATT) && (!e->pair0 || p->Nc_tot <= 0 || p->Nc_tot >= p->N)) return FB_ERR_BAD_ARG;
   if (e->E_int > p->cap_int) return FB_ERR_BAD_ARG;
-  if (p->flavour != FB_FLAVOUR_V1) return FB_ERR_UNSUPPORTED;   // stand-alone sub-layers: v1 layout only
-  const ModelW& w = weights_for(p->hidden, p->n_layers);
+  if (p->flavour != FB_FLAVOUR_V1 && p->flavour != FB_FLAVOUR_PLUS) return FB_ERR_BAD_ARG;
+  if (p->dropout_p != 0.f) return FB_ERR_UNSUPPORTED;           // sampling mode goes through fb_model_forward
+  const ModelW& w = weights_for(p->hidden, p->n_layers, p->flavour);
   Run r{*p, w};
   Arena ag(p->ws_graph, p->ws_graph_bytes, false);
   plan_graph(*p, ag, r.g);

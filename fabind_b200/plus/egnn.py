@@ -2,11 +2,12 @@
 
 Same class names, constructor signatures and parameter names as the reference so that `load_state_dict(strict=True)`
 of a FABind+ checkpoint works.  The layers run inside the fused CUDA stack driven by `att_model.EfficientMCAttModel`;
-called on their own they raise (the stand-alone sub-layer entry point `fb_egnn_forward` serves the v1 layout only)."""
+called on their own they run the same kernels on caller-supplied graphs through `fb_egnn_forward` (eval semantics)."""
 import torch
 import torch.nn as nn
 
-from ..egnn import _check_args
+from .. import _lib
+from ..egnn import _check_args, _geom, _eval_only
 from ..model_utils import _standalone
 from .cross_att import CrossAttentionModule
 from .model_utils import InteractionModule, MLPwithLastAct, MLPwoBias
@@ -38,9 +39,18 @@ class MC_E_GCL(nn.Module):
         self.coord_mlp = MLPwoBias(args, embedding_channels=hidden_nf, n=n, out_channels=n_channel)
         torch.nn.init.xavier_uniform_(self.coord_mlp.linear2.weight, gain=0.001)
         self.coord_change_maximum = coord_change_maximum
+        self.precision = "fp32"
 
-    def forward(self, *a, **k):
-        _standalone("MC_E_GCL (FABind+ layout)")
+    def forward(self, h, edge_index, coord, edge_attr=None, node_attr=None, batch_id=None):
+        """egnn.py:100-115 on a caller-supplied edge list -> (h, coord)."""
+        from ..substack import egnn_forward
+        _eval_only(self)
+        if edge_attr is not None or node_attr is not None or batch_id is None:
+            raise NotImplementedError("fabind_b200: MC_E_GCL.forward needs batch_id and takes no edge/node attributes")
+        ho, xo, _, _ = egnn_forward(self, self.args, "gnn.gcl_0.", h.shape[1], 1, _lib.STEP_GCL, h, coord, edge_index, None, None, None,
+                                    batch_id, None, None, _geom(self.args, self.coord_change_maximum), bf16=self.precision == "bf16",
+                                    flavour=_lib.FLAVOUR_PLUS)
+        return ho, xo
 
 
 class MC_Att_L(nn.Module):
@@ -65,9 +75,19 @@ class MC_Att_L(nn.Module):
         # constructed (and checkpointed) by the reference but unused when add_cross_attn_layer is on (egnn.py:147-149)
         self.inter_layer = InteractionModule(input_nf, output_nf, hidden_nf, opm=opm, rm_layernorm=args.rm_layernorm)
         self.attn_bias_proj = nn.Linear(hidden_nf, 1)
+        self.precision = "fp32"
 
-    def forward(self, *a, **k):
-        _standalone("MC_Att_L (FABind+ layout)")
+    def forward(self, h, edge_index, coord, edge_attr=None, segment_id=None, batch_id=None, reduced_tuple=None,
+                pair_embed_batched=None, pair_mask=None, LAS_mask=None, p_p_dist_embed=None, c_c_dist_embed=None):
+        """egnn.py:280-300 on a caller-supplied (symmetric) inter edge list -> (h, coord, attention weights, pair_embed_batched)."""
+        from ..substack import egnn_forward
+        _eval_only(self)
+        if edge_attr is not None or segment_id is None or batch_id is None or pair_embed_batched is None:
+            raise NotImplementedError("fabind_b200: MC_Att_L.forward needs segment_id, batch_id and pair_embed_batched")
+        ho, xo, atts, pair = egnn_forward(self, self.args, "gnn.att_0.", self.hidden_nf, 1, _lib.STEP_ATT, h, coord, None, edge_index, None,
+                                          None, batch_id, segment_id, pair_embed_batched, _geom(self.args, self.coord_change_maximum),
+                                          bf16=self.precision == "bf16", want_att=True, flavour=_lib.FLAVOUR_PLUS)
+        return ho, xo, atts[0], pair
 
 
 class MCAttEGNN(nn.Module):
@@ -98,5 +118,18 @@ class MCAttEGNN(nn.Module):
         self.out_layer = MC_E_GCL(args, hidden_nf, hidden_nf, hidden_nf, n_channel, edges_in_d=in_edge_nf, act_fn=act_fn,
                                   residual=residual, coord_change_maximum=cmax)
 
-    def forward(self, *a, **k):
-        _standalone("MCAttEGNN (FABind+ layout)")
+    def forward(self, h, x, ctx_edges, att_edges, LAS_edge_list, batched_complex_coord_LAS, segment_id=None, batch_id=None,
+                reduced_tuple=None, pair_embed_batched=None, pair_mask=None, LAS_mask=None, p_p_dist_embed=None,
+                c_c_dist_embed=None, mask=None, ctx_edge_attr=None, att_edge_attr=None, return_attention=False):
+        """egnn.py:359-433 on caller-supplied graphs -> (h, x[, atts], pair_embed_batched)."""
+        from ..substack import egnn_forward
+        _eval_only(self)
+        if ctx_edge_attr is not None or att_edge_attr is not None or segment_id is None or batch_id is None:
+            raise NotImplementedError("fabind_b200: MCAttEGNN.forward needs segment_id/batch_id and takes no edge attributes")
+        steps = (_lib.STEP_LINEAR_IN | _lib.STEP_GCL | _lib.STEP_ATT | _lib.STEP_LAS | _lib.STEP_OUT_LAYER | _lib.STEP_LINEAR_OUT)
+        ho, xo, atts, pair = egnn_forward(self, self.args, "gnn.", self.hidden_nf, self.n_layers, steps, h, x, ctx_edges, att_edges,
+                                          LAS_edge_list, batched_complex_coord_LAS, batch_id, segment_id, pair_embed_batched,
+                                          _geom(self.args, self.normalize_coord(10), self.geometry_reg_step_size),
+                                          bf16=getattr(self, "precision", "fp32") == "bf16", want_att=return_attention,
+                                          flavour=_lib.FLAVOUR_PLUS)
+        return (ho, xo, atts, pair) if return_attention else (ho, xo, pair)

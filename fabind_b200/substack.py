@@ -14,26 +14,33 @@ from .weights import pack_state_dict
 _templates = {}
 
 
-def _template_sd(args, hidden, n_layers):
+def _template_sd(args, hidden, n_layers, flavour=0):
     """zero-filled state_dict with the full EfficientMCAttModel key set (slots a sub-module does not own stay zero)"""
-    key = (hidden, n_layers)
+    key = (hidden, n_layers, flavour)
     if key not in _templates:
-        from .att_model import EfficientMCAttModel
+        if flavour == 1:
+            from .plus.att_model import EfficientMCAttModel
+        else:
+            from .att_model import EfficientMCAttModel
         m = EfficientMCAttModel(args, hidden, hidden, 1, n_layers=n_layers, n_iter=1, normalize_coord=lambda x: x / 5.0,
                                 unnormalize_coord=lambda x: x * 5.0)
         _templates[key] = {k: torch.zeros_like(v) for k, v in m.state_dict().items()}
     return dict(_templates[key])
 
 
-def packed_arena(module, args, hidden, n_layers, prefix, device):
+def packed_arena(module, args, hidden, n_layers, prefix, device, flavour=0):
     params = list(module.parameters())
     key = (device, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
     cache = getattr(module, "_fb_arena", None)
     if cache is None or cache[0] != key:
-        sd = _template_sd(args, hidden, n_layers)
+        sd = _template_sd(args, hidden, n_layers, flavour)
         for k, v in module.state_dict().items():
             sd[prefix + k] = v.detach().cpu()
-        w32 = pack_state_dict(sd, hidden, n_layers).to(device)
+        if flavour == 1:      # LayerNorm scales of slots the sub-module does not own: 1 keeps the folded packing finite
+            for k in sd:
+                if k.endswith("layernorm.weight") and not k.startswith(prefix):
+                    sd[k] = torch.ones_like(sd[k])
+        w32 = pack_state_dict(sd, hidden, n_layers, flavour).to(device)
         cache = (key, w32, None)
         module._fb_arena = cache
     return cache
@@ -48,8 +55,9 @@ def _csr(edges, inv, N):
 
 
 def egnn_forward(module, args, prefix, hidden, n_layers, steps, h, x, ctx_edges, att_edges, las_edges, x_las, batch_id,
-                 segment_id, pair_embed_batched, geom, bf16=False, want_att=False):
-    """Returns (h_out [N,H], x_out [N,1,3], atts or None).  Inputs are device (or CPU) tensors in the caller's order."""
+                 segment_id, pair_embed_batched, geom, bf16=False, want_att=False, flavour=0):
+    """Returns (h_out [N,H], x_out [N,1,3], atts or None) and, for the FABind+ layout (flavour 1) with an attention step,
+    additionally the propagated dense pair embedding.  Inputs are device (or CPU) tensors in the caller's order."""
     l = _lib.lib()
     dev = next(module.parameters()).device
     if dev.type != "cuda":
@@ -81,7 +89,7 @@ def egnn_forward(module, args, prefix, hidden, n_layers, steps, h, x, ctx_edges,
     las = las_edges.detach().to(dev, torch.int64).contiguous() if las_edges is not None else torch.zeros((2, 0), dtype=torch.int64, device=dev)
     up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     g_dev = [up(a) for a in (crp, crow, ccol, irp, irow, icol, ipair)]
-    _, w32, w16 = packed_arena(module, args, hidden, n_layers, prefix, dev)
+    _, w32, w16 = packed_arena(module, args, hidden, n_layers, prefix, dev, flavour)
     if bf16 and w16 is None:
         w16 = w32.to(torch.bfloat16)
         module._fb_arena = (module._fb_arena[0], w32, w16)
@@ -116,6 +124,11 @@ def egnn_forward(module, args, prefix, hidden, n_layers, steps, h, x, ctx_edges,
     p.node_flags = lay.flags.data_ptr()
     p.w32, p.w16 = w32.data_ptr(), (w16.data_ptr() if w16 is not None else None)
     p.X_out, p.H_out = X_out.data_ptr(), H_out.data_ptr()
+    p.flavour = flavour
+    pair_out = None
+    if flavour == 1 and (steps & _lib.STEP_ATT):
+        pair_out = torch.zeros((lay.B, lay.max_p, lay.max_c, hidden), dtype=torch.float32, device=dev)
+        p.pair_out = pair_out.data_ptr()
     st = current_stream_ptr(dev)
     gb = l.fb_graph_workspace_bytes(C.byref(p))
     wsg = _scratch_buf(dev, "graph", gb)
@@ -140,4 +153,6 @@ def egnn_forward(module, args, prefix, hidden, n_layers, steps, h, x, ctx_edges,
             a = torch.empty(E_int, dtype=torch.float32, device=dev)
             a[ot] = att[i, :E_int]
             atts.append(a)
+    if flavour == 1:
+        return H_out, X_out.view(N, 1, 3), atts, pair_out
     return H_out, X_out.view(N, 1, 3), atts

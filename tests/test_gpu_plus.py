@@ -119,10 +119,13 @@ def test_plus_bf16_mode_deviation(IT, big_heads):
     assert rec["x_abs"] < 0.15 and rec["h_err_99"] < 0.03 and rec["h_mean"] < 0.01 and rec["pair_mean"] < 0.01, rec
 
 
-def test_plus_submodules_raise_alone():
+def test_plus_training_with_autograd_raises():
+    """train() with autograd enabled = training, which is not built (train() under no_grad is the sampling mode, see
+    test_gpu_plus_sampling.py); the weight containers of the attention block raise when called on their own"""
     m, _ = _model(64, 1, 1)
     with pytest.raises(NotImplementedError):
-        m.gnn.gcl_0(None)
+        m.gnn.att_0.cross_attn_module(None)
     m.train()
+    b = make_batch(embed=64, n_complexes=1, seed=0, n_c=5, n_p=10).to("cuda")
     with pytest.raises(NotImplementedError):
-        m(None, None, None, None, None, None, None, None, None)
+        m(**b.forward_args())
