@@ -317,9 +317,11 @@ def initial_pair(sd, H, layout):
 
 
 def model_forward(sd, cfg, X, H, batch_id, segment_id, mask, is_global, compound_edge_index,
-                  LAS_edge_index, X_LAS, trace=None, return_edges=False):
+                  LAS_edge_index, X_LAS, trace=None, return_edges=False, grad_last_iter_only=False):
     """Returns (X, H) like the reference; X is updated on a copy (the reference mutates its
-    argument in place, att_model.py:236,245 -- callers that want that effect copy back)."""
+    argument in place, att_model.py:236,245 -- callers that want that effect copy back).
+    grad_last_iter_only: autograd semantics of refine='refine_coord' (att_model.py:227-245): every iteration but the last runs
+    under no_grad (graph construction always does); used by the gradient goldens that pin this oracle for the training path."""
     X = X.clone()
     layout = complex_layout(batch_id, segment_id)
     pair0 = initial_pair(sd, H, layout)
@@ -328,13 +330,15 @@ def model_forward(sd, cfg, X, H, batch_id, segment_id, mask, is_global, compound
     edges_seen = []
     H_out = None
     for r in range(cfg.n_iter):
-        ctx, inter, _ = build_edges(X, batch_id, segment_id, is_global, intra, inter_c)
+        with torch.no_grad():
+            ctx, inter, _ = build_edges(X, batch_id, segment_id, is_global, intra, inter_c)
         ctx = torch.cat([compound_edge_index, ctx], dim=1)   # att_model.py:231
         if return_edges:
             edges_seen.append((ctx, inter))
         tr = [] if trace is not None else None
-        h_new, Z, atts = egnn_forward(sd, "gnn.", cfg, H, X, ctx, inter, LAS_edge_index, X_LAS,
-                                      batch_id, segment_id, pair0, layout, trace=tr)
+        with torch.set_grad_enabled(torch.is_grad_enabled() and (not grad_last_iter_only or r == cfg.n_iter - 1)):
+            h_new, Z, atts = egnn_forward(sd, "gnn.", cfg, H, X, ctx, inter, LAS_edge_index, X_LAS,
+                                          batch_id, segment_id, pair0, layout, trace=tr)
         if trace is not None:
             trace.append((r, tr, atts))
         X[mask] = Z[mask]

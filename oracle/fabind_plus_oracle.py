@@ -134,7 +134,7 @@ def dense_pair(pair_blocks):
 
 
 def model_forward(sd, cfg, X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index, X_LAS,
-                  trace=None, return_edges=False):
+                  trace=None, return_edges=False, grad_last_iter_only=False):
     """EfficientMCAttModel.forward (models/att_model.py:166-223), eval mode -> (X, H, pair_embed_batched)."""
     X = X.clone()
     layout = complex_layout(batch_id, segment_id)
@@ -144,13 +144,16 @@ def model_forward(sd, cfg, X, H, batch_id, segment_id, mask, is_global, compound
     edges_seen = []
     H_out, pair = None, None
     for r in range(cfg.n_iter):
-        ctx, inter, _ = build_edges(X, batch_id, segment_id, is_global, intra, inter_c)
+        with torch.no_grad():
+            ctx, inter, _ = build_edges(X, batch_id, segment_id, is_global, intra, inter_c)
         ctx = torch.cat([compound_edge_index, ctx], dim=1)
         if return_edges:
             edges_seen.append((ctx, inter))
         tr = [] if trace is not None else None
-        h_new, Z, atts, pair = egnn_forward(sd, "gnn.", cfg, H, X, ctx, inter, LAS_edge_index, X_LAS, batch_id,
-                                            segment_id, pair0, layout, trace=tr)
+        # refine='refine_coord' (att_model.py:196-218): every iteration but the last under no_grad
+        with torch.set_grad_enabled(torch.is_grad_enabled() and (not grad_last_iter_only or r == cfg.n_iter - 1)):
+            h_new, Z, atts, pair = egnn_forward(sd, "gnn.", cfg, H, X, ctx, inter, LAS_edge_index, X_LAS, batch_id,
+                                                segment_id, pair0, layout, trace=tr)
         if trace is not None:
             trace.append((r, tr, atts))
         X[mask] = Z[mask]

@@ -374,6 +374,37 @@ def main_l2_plus_train_forward():
     print("l2plustrainfwd", [tuple(t.shape) if torch.is_tensor(t) else t for t in fwd])
 
 
+def main_grad():
+    """Parameter gradients of the UNMODIFIED reference stacks (eval mode = no dropout, autograd on) for a fixed linear read-out
+    of (X, H[, pair]): pins the oracles' autograd path (refine_coord: only the last iteration carries gradients), the checker
+    of the training path (BASELINE config 5) that later rounds build."""
+    for flavour in ("v1", "plus"):
+        mods = ref_shims.load_reference(flavour)
+        args = ref_shims.published_args_plus(dropout=0.0) if flavour == "plus" else ref_shims.published_args()
+        hidden, L, IT, bkw, wseed = 32, 1, 2, dict(n_complexes=2, seed=6, n_c_range=(5, 9), n_p_range=(14, 22)), 91
+        scale = args.coordinate_scale
+        m = mods.att_model.EfficientMCAttModel(args, hidden, hidden, 1, n_edge_feats=0, n_layers=L, n_iter=IT,
+                                               inter_cutoff=args.inter_cutoff, intra_cutoff=args.intra_cutoff,
+                                               normalize_coord=lambda x: x / scale, unnormalize_coord=lambda x: x * scale).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+        b = make_batch(embed=hidden, **bkw)
+        g = torch.Generator().manual_seed(17)
+        out = m(**b.clone().forward_args())
+        rx, rh = torch.randn(out[0].shape, generator=g), torch.randn(out[1].shape, generator=g)
+        loss = (out[0] * rx).sum() + (out[1] * rh).sum()
+        if flavour == "plus":
+            rp = torch.randn(out[2].shape, generator=g) * 0.1
+            loss = loss + (out[2] * rp).sum()
+        loss.backward()
+        grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in m.named_parameters()}
+        torch.save({"recipe": dict(hidden=hidden, n_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, far_ligand=False,
+                                   flavour=flavour, readout_seed=17),
+                    "shapes": shapes, "loss": float(loss), "grads": grads, "torch": torch.__version__},
+                   os.path.join(OUT, f"grad_{flavour}_h32_l1_it2.pt"))
+        print("grad", flavour, "loss", float(loss), "params with grad", sum(v is not None for v in grads.values()), "/", len(grads))
+
+
 def main_l2_plus():
     """goldens for the FABind+ L2 wrapper (FABind_plus/fabind/models/model.py::FABindPlus): forward(stage=2) in eval mode
     (13-tuple + the in-place shift of data.coords) and inference()"""
@@ -413,7 +444,7 @@ def main_l2_plus():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample", "postopt", "l2plustrainfwd"]
+    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample", "postopt", "l2plustrainfwd", "grad"]
     if "l2plus" in which:
         main_l2_plus()
     if "plusdrop" in which:
@@ -422,6 +453,8 @@ if __name__ == "__main__":
         main_l2_plus_sampling()
     if "postopt" in which:
         main_post_optim()
+    if "grad" in which:
+        main_grad()
     if "l2plustrainfwd" in which:
         main_l2_plus_train_forward()
     if "v1" in which:
