@@ -192,10 +192,13 @@ def _att_plus(sd, p, H):
     return d
 
 
-def pack_state_dict(sd, hidden, n_layers, flavour=0):
+def pack_state_dict(sd, hidden, n_layers, flavour=0, differentiable=False):
     """Returns the fp32 arena (CPU tensor) for a state_dict with the reference's key names
-    (flavour 0: FABind v1 layout, 1: FABind+ layout)."""
-    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    (flavour 0: FABind v1 layout, 1: FABind+ layout).  differentiable=True keeps the autograd graph from the reference
+    parameters to the arena (every derivation is a torch expression): gradients w.r.t. arena slots map back to reference
+    parameters by the chain rule -- how a training path in this formulation returns `state_dict`-shaped gradients
+    (tests/test_formulation_cpu.py::test_refactored_formulation_gradients)."""
+    sd = {k: (v.cpu() if differentiable else v.detach().cpu()) for k, v in sd.items()}
     l = _lib.lib()
     arena = torch.zeros(l.fb_weight_arena_elems_f(hidden, n_layers, flavour), dtype=torch.float32)
     gcl, att = (_gcl_plus, _att_plus) if flavour == 1 else (_gcl, _att)

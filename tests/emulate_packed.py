@@ -19,8 +19,8 @@ HD = 128
 
 
 class Arena:
-    def __init__(self, sd, H, L, flavour=0):
-        self.a = pack_state_dict(sd, H, L, flavour)
+    def __init__(self, sd, H, L, flavour=0, differentiable=False):
+        self.a = pack_state_dict(sd, H, L, flavour, differentiable=differentiable)
         self.s = {n: (r, c, o) for n, r, c, o in slots(H, L, flavour)}
 
     def m(self, name):
@@ -34,7 +34,7 @@ def _edges(x, lay_np, intra, inter, bonds_int):
     N = x.shape[0]
     cplx, flags, c_off, p_off = lay_np["node_cplx"], lay_np["flags"], lay_np["c_off"], lay_np["p_off"]
     ctx_r, ctx_c, int_r, int_c = [], [], [], []
-    xs = x.numpy().astype(np.float32)
+    xs = x.detach().numpy().astype(np.float32)
     for r in range(N):
         b = cplx[r]
         for e in range(bonds_int.shape[1]):
@@ -68,7 +68,7 @@ def _radial(row, col, x, cplx_t, B):
     return d2 / nrm[cplx_t[row]]
 
 
-def forward_emulated(sd, cfg, batch, flavour=0, dropout=None):
+def forward_emulated(sd, cfg, batch, flavour=0, dropout=None, differentiable=False):
     """flavour 0: FABind v1 layout -> (X, H, stats); 1: FABind+ layout -> (X, H, stats, pair [P_total, H] packed rows).
     dropout = (p, seed, colonly): FABind+ train-mode masks with the library's counter-based mask function
     (fabind_b200/dropout.py), at the sites and row ids csrc/forward.cu uses."""
@@ -76,7 +76,7 @@ def forward_emulated(sd, cfg, batch, flavour=0, dropout=None):
     H = batch.H.shape[1]
     L = cfg.n_layers
     plus = flavour == 1
-    W = Arena(sd, H, L, flavour)
+    W = Arena(sd, H, L, flavour, differentiable)
     Dp = (2 * H + 1 + 63) // 64 * 64
     EPS = 1e-5
     lay = build_layout(batch.batch_id, batch.segment_id, batch.is_global, batch.mask, "cpu")
@@ -159,27 +159,30 @@ def forward_emulated(sd, cfg, batch, flavour=0, dropout=None):
             return (o * torch.sigmoid(g).view(-1, 4, 32)).reshape(-1, 128)
 
         def att(pre, l, h, x):
-            h = h.clone()
-            CAc = F.linear(h[:Nc], W.m(pre + "ca_c_w"), W.m(pre + "ca_c_b"))
-            CAp = F.linear(h[Nc:], W.m(pre + "ca_p_w"), W.m(pre + "ca_p_b"))
-            O = torch.zeros(N, HD)
+            # (no in-place updates of h: the emulation is also differentiated, see test_refactored_formulation_gradients)
+            hc, hp = h[:Nc], h[Nc:]
+            CAc = F.linear(hc, W.m(pre + "ca_c_w"), W.m(pre + "ca_c_b"))
+            CAp = F.linear(hp, W.m(pre + "ca_p_w"), W.m(pre + "ca_p_b"))
+            Op = []
             for b in range(B):
-                cs, ps = slice(c_off[b], c_off[b + 1]), slice(p_off[b], p_off[b + 1])
+                cs = slice(c_off[b], c_off[b + 1])
                 psl = slice(p_off[b] - Nc, p_off[b + 1] - Nc)
                 nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
                 bias = PB[pair_base[b]:pair_base[b + 1], l, 0].view(np1, nc1, 4)
-                O[ps] = rowatt(CAp[psl, :HD], CAp[psl, HD:], CAc[cs, :HD], CAc[cs, HD:2 * HD], bias)
-            h[Nc:] = h[Nc:] + F.linear(O[Nc:], W.m(pre + "o_p_w"), W.m(pre + "o_p_b"))
-            CAp2 = F.linear(h[Nc:], W.m(pre + "ca_p2_w"))
+                Op.append(rowatt(CAp[psl, :HD], CAp[psl, HD:], CAc[cs, :HD], CAc[cs, HD:2 * HD], bias))
+            hp = hp + F.linear(torch.cat(Op), W.m(pre + "o_p_w"), W.m(pre + "o_p_b"))
+            CAp2 = F.linear(hp, W.m(pre + "ca_p2_w"))
+            Oc = []
             for b in range(B):
                 cs = slice(c_off[b], c_off[b + 1])
                 psl = slice(p_off[b] - Nc, p_off[b + 1] - Nc)
                 nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
                 bias = PB[pair_base[b]:pair_base[b + 1], l, 1].view(np1, nc1, 4).transpose(0, 1)
-                O[cs] = rowatt(CAc[cs, 2 * HD:3 * HD], CAc[cs, 3 * HD:], CAp2[psl, :HD], CAp2[psl, HD:], bias)
-            h[:Nc] = h[:Nc] + F.linear(O[:Nc], W.m(pre + "o_c_w"), W.m(pre + "o_c_b"))
-            h[Nc:] = h[Nc:] + F.linear(F.relu(F.linear(h[Nc:], W.m(pre + "tp1_w"), W.m(pre + "tp1_b"))), W.m(pre + "tp2_w"), W.m(pre + "tp2_b"))
-            h[:Nc] = h[:Nc] + F.linear(F.relu(F.linear(h[:Nc], W.m(pre + "tc1_w"), W.m(pre + "tc1_b"))), W.m(pre + "tc2_w"), W.m(pre + "tc2_b"))
+                Oc.append(rowatt(CAc[cs, 2 * HD:3 * HD], CAc[cs, 3 * HD:], CAp2[psl, :HD], CAp2[psl, HD:], bias))
+            hc = hc + F.linear(torch.cat(Oc), W.m(pre + "o_c_w"), W.m(pre + "o_c_b"))
+            hp = hp + F.linear(F.relu(F.linear(hp, W.m(pre + "tp1_w"), W.m(pre + "tp1_b"))), W.m(pre + "tp2_w"), W.m(pre + "tp2_b"))
+            hc = hc + F.linear(F.relu(F.linear(hc, W.m(pre + "tc1_w"), W.m(pre + "tc1_b"))), W.m(pre + "tc2_w"), W.m(pre + "tc2_b"))
+            h = torch.cat([hc, hp])
             QK = F.linear(h, W.m(pre + "qk_w"), W.m(pre + "qk_b"))     # q | k | linear_p32 | linear_c32 | pad
             pc32 = torch.empty(N, 32)
             pc32[Nc:] = QK[Nc:, 2 * H:2 * H + 32]
@@ -240,31 +243,34 @@ def forward_emulated(sd, cfg, batch, flavour=0, dropout=None):
             return h, x_new
 
         def att_plus(pre, pair_in, h, x, layer=0):
-            h = h.clone()
+            hc, hp = h[:Nc], h[Nc:]
             raw = F.linear(pair_in, W.m(pre + "pb_w"), W.m(pre + "pb_b"))[:, :16].reshape(-1, 2, 2, 4)
             PBl = raw[:, :, 0] * torch.sigmoid(raw[:, :, 1])          # [P, blk, head]
-            CAc = F.linear(h[:Nc], W.m(pre + "ca_c_w"), W.m(pre + "ca_c_b"))
-            CAp = F.linear(h[Nc:], W.m(pre + "ca_p_w"), W.m(pre + "ca_p_b"))
-            O = torch.zeros(N, HD)
+            CAc = F.linear(hc, W.m(pre + "ca_c_w"), W.m(pre + "ca_c_b"))
+            CAp = F.linear(hp, W.m(pre + "ca_p_w"), W.m(pre + "ca_p_b"))
+            Op = []
             for b in range(B):
-                cs, ps = slice(c_off[b], c_off[b + 1]), slice(p_off[b], p_off[b + 1])
+                cs = slice(c_off[b], c_off[b + 1])
                 psl = slice(p_off[b] - Nc, p_off[b + 1] - Nc)
                 nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
                 bias = PBl[pair_base[b]:pair_base[b + 1], 0].view(np1, nc1, 4)
-                O[ps] = rowatt(CAp[psl, :HD], CAp[psl, HD:], CAc[cs, :HD], CAc[cs, HD:2 * HD], bias)
-            h[Nc:] = h[Nc:] + drop(F.linear(O[Nc:], W.m(pre + "o_p_w"), W.m(pre + "o_p_b")), layer, "patt", Nc)
-            CAp2 = F.linear(h[Nc:], W.m(pre + "ca_p2_w"))
+                Op.append(rowatt(CAp[psl, :HD], CAp[psl, HD:], CAc[cs, :HD], CAc[cs, HD:2 * HD], bias))
+            hp = hp + drop(F.linear(torch.cat(Op), W.m(pre + "o_p_w"), W.m(pre + "o_p_b")), layer, "patt", Nc)
+            CAp2 = F.linear(hp, W.m(pre + "ca_p2_w"))
+            Oc = []
             for b in range(B):
                 cs = slice(c_off[b], c_off[b + 1])
                 psl = slice(p_off[b] - Nc, p_off[b + 1] - Nc)
                 nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
                 bias = PBl[pair_base[b]:pair_base[b + 1], 1].view(np1, nc1, 4).transpose(0, 1)
-                O[cs] = rowatt(CAc[cs, 2 * HD:3 * HD], CAc[cs, 3 * HD:], CAp2[psl, :HD], CAp2[psl, HD:], bias)
-            h[:Nc] = h[:Nc] + drop(F.linear(O[:Nc], W.m(pre + "o_c_w"), W.m(pre + "o_c_b")), layer, "catt")
-            for t, sl, r0 in (("tc", slice(0, Nc), 0), ("tp", slice(Nc, N), Nc)):
-                t0 = ln(h[sl], pre + t + "l_g", pre + t + "l_b")
+                Oc.append(rowatt(CAc[cs, 2 * HD:3 * HD], CAc[cs, 3 * HD:], CAp2[psl, :HD], CAp2[psl, HD:], bias))
+            hc = hc + drop(F.linear(torch.cat(Oc), W.m(pre + "o_c_w"), W.m(pre + "o_c_b")), layer, "catt")
+            sides = {}
+            for t, hs, r0 in (("tc", hc, 0), ("tp", hp, Nc)):
+                t0 = ln(hs, pre + t + "l_g", pre + t + "l_b")
                 t1 = drop(F.relu(F.linear(t0, W.m(pre + t + "1_w"), W.m(pre + t + "1_b"))), layer, "ctr1" if t == "tc" else "ptr1", r0)
-                h[sl] = h[sl] + drop(F.relu(F.linear(t1, W.m(pre + t + "2_w"), W.m(pre + t + "2_b"))), layer, "ctr2" if t == "tc" else "ptr2", r0)
+                sides[t] = hs + drop(F.relu(F.linear(t1, W.m(pre + t + "2_w"), W.m(pre + t + "2_b"))), layer, "ctr2" if t == "tc" else "ptr2", r0)
+            h = torch.cat([sides["tc"], sides["tp"]])
             QK = F.linear(h, W.m(pre + "qk_w"), W.m(pre + "qk_b"))
             # pair <- MLPwithLastAct(pair + inter32(p, c)) on every pair row
             pi_all, ci_all = [], []
@@ -324,6 +330,8 @@ def forward_emulated(sd, cfg, batch, flavour=0, dropout=None):
                 h = drop(h, -1, "stack_out")
             h_final = F.linear(h, W.m("out_w"), W.m("out_b"))
         x_state = torch.where(moves[:, None], x, x_state)
+        if not last:
+            x_state = x_state.detach()    # refine_coord: earlier iterations run under no_grad in the reference (att_model.py:227-236)
     X_out = torch.empty_like(batch.X)
     X_out[permt, 0] = x_state
     H_out = torch.empty_like(batch.H)

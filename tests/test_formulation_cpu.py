@@ -60,3 +60,37 @@ def test_dropout_placement_matches_patched_reference():
         # and the masks matter: eval-mode emulation is far away
         Xe, He, _, _ = forward_emulated(sd, cfg, b, flavour=1)
         assert rel_err(He, g["H"]) > 1e-2
+
+
+def test_refactored_formulation_gradients():
+    """The refactored formulation TRAINS like the reference: autograd through the differentiable weight packing
+    (fabind_b200/weights.py, LayerNorm folding / first-Linear hoisting / collapsed pair-bias vector included) and the emulated
+    launch sequence gives, by the chain rule, the parameter gradients of the unmodified reference (tests/golden/grad_*.pt).
+    CPU groundwork for the backward kernels of the training path (BASELINE config 5)."""
+    import glob, os
+    from helpers import GOLDEN_DIR
+    for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_*.pt"))):
+        g, r, b, sd, cfg = load_golden(path)
+        plus = r["flavour"] == "plus"
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        out = forward_emulated(sd, cfg, b, flavour=1 if plus else 0, differentiable=True)
+        gen = torch.Generator().manual_seed(r["readout_seed"])
+        rx, rh = torch.randn(out[0].shape, generator=gen), torch.randn(out[1].shape, generator=gen)
+        loss = (out[0] * rx).sum() + (out[1] * rh).sum()
+        if plus:
+            dims = [(int(b.n_p[i]) + 1, int(b.n_c[i]) + 1) for i in range(len(b.n_c))]
+            pair = _dense_pair(out[3], dims, out[1].shape[1])
+            loss = loss + (pair * (torch.randn(pair.shape, generator=gen) * 0.1)).sum()
+        loss.backward()
+        assert abs(float(loss) - g["loss"]) < 1e-4 * abs(g["loss"]), (float(loss), g["loss"])
+        gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+        n = 0
+        for k, ref in g["grads"].items():
+            if ref is None:
+                continue
+            mine = sd[k].grad
+            assert mine is not None, k
+            err = float((mine - ref).abs().max())
+            assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
+            n += 1
+        assert n >= 80
