@@ -110,3 +110,42 @@ def max_over_ranks(ms, device=None, group=None):
     t = torch.tensor([float(ms)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+# ---- training side of the data parallelism: ONE all-reduce of all gradients per step -------------------
+def allreduce_gradients(params, group=None, average=True, buffer=None):
+    """Sum (or average) the gradients of `params` over the ranks with a SINGLE collective on one flat fp32 buffer (the reference
+    trains under DDP with `find_unused_parameters=True`, FABind/fabind/main_fabind.py:198-200: 36-45 M fp32 gradients, the unused
+    `att_i.inter_layer.*` parameters contribute zeros).  Parameters whose `.grad` is None on this rank are treated as zero and
+    receive the reduced value if any rank had one.  Backend-agnostic (NCCL on the GPU box, gloo in the CPU tests).
+    Returns the flat buffer (re-usable through `buffer=` to avoid re-allocation)."""
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return buffer
+    n = sum(p.numel() for p in params)
+    dev = params[0].device
+    if buffer is None or buffer.numel() != n or buffer.device != dev:
+        buffer = torch.empty(n, dtype=torch.float32, device=dev)
+    o = 0
+    for p in params:
+        k = p.numel()
+        if p.grad is None:
+            buffer[o:o + k].zero_()
+        else:
+            buffer[o:o + k].copy_(p.grad.reshape(-1))
+        o += k
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        dist.all_reduce(buffer, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            buffer.div_(world)
+    o = 0
+    for p in params:
+        k = p.numel()
+        g = buffer[o:o + k].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        o += k
+    return buffer

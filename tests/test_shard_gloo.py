@@ -95,3 +95,39 @@ def test_sharded_forward_world2_matches_single_process():
         # per-sample norms (identical here: same code on the same rows)
         assert torch.allclose(X, Xr, atol=1e-6) and torch.allclose(H, Hr, atol=1e-5), rank
         assert t == 11.0            # max over ranks of (10, 11)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.zeros(7, 5)), torch.nn.Parameter(torch.zeros(11)), torch.nn.Parameter(torch.zeros(3, 3)),
+              torch.nn.Parameter(torch.zeros(2), requires_grad=False)]
+        ps[0].grad = torch.full((7, 5), float(rank + 1))
+        ps[1].grad = torch.arange(11.0) * (rank + 1)
+        if rank == 1:
+            ps[2].grad = torch.ones(3, 3)            # unused on rank 0 (find_unused_parameters semantics)
+        buf = shard.allreduce_gradients(ps, average=True)
+        q.put((rank, [p.grad.clone() if p.grad is not None else None for p in ps], buf.numel()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gradient_allreduce_world2():
+    """one flat all-reduce for all gradients: mean over ranks, missing gradients count as zero, frozen parameters untouched"""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, grads, n in res:
+        assert n == 35 + 11 + 9
+        assert torch.equal(grads[0], torch.full((7, 5), 1.5)) and torch.equal(grads[1], torch.arange(11.0) * 1.5)
+        assert torch.equal(grads[2], torch.full((3, 3), 0.5)) and grads[3] is None
