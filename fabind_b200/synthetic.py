@@ -87,17 +87,53 @@ def _one_complex(rng, n_c, n_p, spacing=5.2, jitter=1.0, cavity=6.0):
     return prot, lig, bonds, las, lig_ref
 
 
+def _real_complex(rng, ca, lig_true, bonds, pocket_radius=20.0):
+    """One complex from real geometry (SURVEY.md §8d option A): pocket = CA atoms within `pocket_radius` of the ligand
+    centroid, coordinates centred on the pocket mean; start pose = the true pose under a random rotation, centred on the
+    pocket mean ('redocking' mode, utils/utils.py:321-323); LAS reference = the true pose (:338-346); LAS pairs = bonded
+    atoms and atoms two bonds apart."""
+    ca, lig_true = np.asarray(ca, np.float64), np.asarray(lig_true, np.float64)
+    keep = np.linalg.norm(ca - lig_true.mean(0), axis=1) < pocket_radius
+    prot = ca[keep]
+    centre = prot.mean(0)
+    prot, lig_true = prot - centre, lig_true - centre
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    rot = lig_true @ R.T
+    lig = rot - rot.mean(0) + prot.mean(0)
+    n = len(lig)
+    adj = np.zeros((n, n), dtype=bool)
+    adj[bonds[0], bonds[1]] = True
+    two = (adj.astype(np.int64) @ adj.astype(np.int64)) > 0
+    las = adj | two
+    np.fill_diagonal(las, False)
+    return prot, lig, np.asarray(bonds).T, np.argwhere(las), lig_true
+
+
 def make_batch(n_complexes=1, n_c=30, n_p=200, embed=512, seed=0, coordinate_scale=5.0,
-               n_c_range=None, n_p_range=None, feature_std=0.1):
-    """Seeded batch; `n_c_range`/`n_p_range` = (lo, hi) inclusive draw ragged sizes."""
+               n_c_range=None, n_p_range=None, feature_std=0.1, geometry=None, ids=None):
+    """Seeded batch; `n_c_range`/`n_p_range` = (lo, hi) inclusive draw ragged sizes.  `geometry` (a mapping holding
+    `<id>_ca`, `<id>_lig`, `<id>_bonds`, e.g. the loaded tests/golden/real_geometry.npz) with `ids` builds the batch from
+    real pockets instead of the lattice."""
     rng = np.random.default_rng(seed)
+    if geometry is not None:
+        n_complexes = len(ids)
     Xs, XL, Hs, bid, seg, msk, glb, bonds_all, las_all = [], [], [], [], [], [], [], [], []
     ncs, nps = [], []
     off = 0
     for b in range(n_complexes):
         nc = int(rng.integers(n_c_range[0], n_c_range[1] + 1)) if n_c_range else n_c
         np_ = int(rng.integers(n_p_range[0], n_p_range[1] + 1)) if n_p_range else n_p
-        prot, lig, bonds, las, lig_ref = _one_complex(rng, nc, np_)
+        if geometry is not None:
+            prot, lig, bonds, las, lig_ref = _real_complex(rng, geometry[ids[b] + "_ca"], geometry[ids[b] + "_lig"],
+                                                           geometry[ids[b] + "_bonds"])
+            nc, np_ = len(lig), len(prot)
+        else:
+            prot, lig, bonds, las, lig_ref = _one_complex(rng, nc, np_)
         n = nc + np_ + 2
         x = np.concatenate([np.zeros((1, 3)), lig, np.zeros((1, 3)), prot], 0)
         xl = np.concatenate([np.zeros((1, 3)), lig_ref, np.zeros((1, 3)), np.zeros_like(prot)], 0)
@@ -132,6 +168,15 @@ def make_batch(n_complexes=1, n_c=30, n_p=200, embed=512, seed=0, coordinate_sca
         is_global=torch.from_numpy(np.concatenate(glb)),
         compound_edge_index=cat_i(bonds_all), LAS_edge_index=cat_i(las_all), X_LAS=XLt,
         n_c=ncs, n_p=nps)
+
+
+def batch_from_recipe(embed, batch_kwargs, fixture_dir=None):
+    """make_batch from a fixture recipe; a `geometry` entry names an .npz under `fixture_dir`."""
+    kw = dict(batch_kwargs)
+    if isinstance(kw.get("geometry"), str):
+        import os
+        kw["geometry"] = np.load(os.path.join(fixture_dir, kw["geometry"]))
+    return make_batch(embed=embed, **kw)
 
 
 def randomize_coord_heads(module, std=0.5, seed=1234):

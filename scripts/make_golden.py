@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import ref_shims                      # noqa: E402
 from oracle.det_weights import det_state_dict     # noqa: E402
-from fabind_b200.synthetic import make_batch      # noqa: E402
+from fabind_b200.synthetic import make_batch, batch_from_recipe      # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -25,6 +25,8 @@ CASES = {
     "v1_h128_l1_it1_cfg1": (128, 1, 1, dict(n_complexes=1, seed=0, n_c=30, n_p=200), 12, False),
     "v1_h32_l1_it2_noedge": (32, 1, 2, dict(n_complexes=2, seed=3, n_c=6, n_p=30), 13, True),
     "v1_h32_l1_it2_fallback": (32, 1, 2, dict(n_complexes=1, seed=4, n_c=5, n_p=24), 14, True),
+    # real pockets (scripts/make_real_geometry.py; SURVEY.md §8d geometry option A), true pose randomly rotated
+    "v1_h32_l2_it3_real": (32, 2, 3, dict(seed=2, geometry="real_geometry.npz", ids=["6efk", "6g3c", "6n93", "6npi"]), 15, False),
 }
 
 
@@ -45,7 +47,7 @@ def main():
     mods = ref_shims.load_reference("v1")
     for name, (hidden, L, IT, bkw, wseed, far) in CASES.items():
         m, shapes = build_reference(mods, hidden, L, IT, wseed)
-        b = make_batch(embed=hidden, **bkw)
+        b = batch_from_recipe(hidden, bkw, OUT)
         if far:  # push the first complex's ligand 100 A away: no inter edge -> fallback (att_model.py:85)
             nc = b.n_c[0]
             b.X[1:nc + 1] += 20.0
@@ -93,6 +95,7 @@ PLUS_CASES = {
     "plus_h64_l2_it2_ragged": (64, 2, 2, dict(n_complexes=3, seed=1, n_c_range=(8, 30), n_p_range=(40, 90)), 31, False),
     "plus_h128_l1_it1_cfg1": (128, 1, 1, dict(n_complexes=1, seed=0, n_c=30, n_p=200), 32, False),
     "plus_h32_l1_it2_fallback": (32, 1, 2, dict(n_complexes=1, seed=4, n_c=5, n_p=24), 34, True),
+    "plus_h32_l2_it2_real": (32, 2, 2, dict(seed=3, geometry="real_geometry.npz", ids=["6g3c", "6npi"]), 35, False),
 }
 
 
@@ -107,7 +110,7 @@ def main_plus():
             intra_cutoff=args.intra_cutoff, normalize_coord=lambda x: x / scale, unnormalize_coord=lambda x: x * scale).eval()
         shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
         m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
-        b = make_batch(embed=hidden, **bkw)
+        b = batch_from_recipe(hidden, bkw, OUT)
         if far:
             nc = b.n_c[0]
             b.X[1:nc + 1] += 20.0
@@ -240,7 +243,7 @@ def main_plus_dropout():
         m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
         n = patch_reference_dropout(m, L, dseed, pdrop)
         m.train()
-        b = make_batch(embed=hidden, **bkw)
+        b = batch_from_recipe(hidden, bkw, OUT)
         with torch.no_grad():
             X, H, pair = m(**b.clone().forward_args())
             m.eval()
@@ -388,7 +391,7 @@ def main_grad():
                                                normalize_coord=lambda x: x / scale, unnormalize_coord=lambda x: x * scale).eval()
         shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
         m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
-        b = make_batch(embed=hidden, **bkw)
+        b = batch_from_recipe(hidden, bkw, OUT)
         g = torch.Generator().manual_seed(17)
         out = m(**b.clone().forward_args())
         rx, rh = torch.randn(out[0].shape, generator=g), torch.randn(out[1].shape, generator=g)

@@ -4,7 +4,7 @@ import os
 
 import torch
 
-from fabind_b200.synthetic import make_batch
+from fabind_b200.synthetic import make_batch, batch_from_recipe
 from oracle.det_weights import det_state_dict
 from oracle import fabind_oracle as orc
 
@@ -37,7 +37,7 @@ def load_l2_golden(path):
 def load_golden(path):
     g = torch.load(path, map_location="cpu", weights_only=False)
     r = g["recipe"]
-    b = make_batch(embed=r["hidden"], **r["batch"])
+    b = batch_from_recipe(r["hidden"], r["batch"], GOLDEN_DIR)
     if r["far_ligand"]:
         nc = b.n_c[0]
         b.X[1:nc + 1] += 20.0
