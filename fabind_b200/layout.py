@@ -62,6 +62,8 @@ def build_layout(batch_id, segment_id, is_global, mask, device, allow_single_sid
     np1 = np.bincount(bid[p_idx], minlength=B)
     if (np.any(nc1 == 0) or np.any(np1 == 0)) and not allow_single_side:
         raise ValueError("every complex needs compound-side and protein-side nodes")
+    if int((nc1.astype(np.int64) * np1.astype(np.int64)).sum()) * 2 >= 2 ** 31:
+        raise ValueError("batch too large for the library's 32-bit row indices: split it (fabind_b200.shard.take_complexes)")
     Nc_tot = int(nc1.sum())
     c_off = np.concatenate([[0], np.cumsum(nc1)]).astype(np.int32)
     p_off = (Nc_tot + np.concatenate([[0], np.cumsum(np1)])).astype(np.int32)
