@@ -41,52 +41,106 @@ def load_peaks():
 
 
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region.  In-process NVML polling (every ~10 ms, device
+    picked by UUID so CUDA_VISIBLE_DEVICES does not matter); if NVML is unusable, the recipe's `nvidia-smi -lms`
+    subprocess, started early so that it is already streaming when the timed region begins.  Only samples whose
+    host timestamp falls inside [begin(), end()] are reported."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.samples, self.t0, self.t1 = index, None, [], None, None
+        self.stop_flag, self.thread, self.source, self.mx = False, None, None, 0.0
+
+    # -- NVML -------------------------------------------------------------------------------------------------
+    def _nvml_open(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)          # fail here, not in the thread
+        return nv, h, bits
+
+    def _nvml_pump(self, nv, h, bits):
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((time.perf_counter(), mhz, [n for b, n in bits if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.010)
+
+    # -- nvidia-smi fallback ----------------------------------------------------------------------------------
+    def _smi_pump(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mhz = float(f[0])
+                self.mx = max(self.mx, float(f[1]))
+            except ValueError:
+                continue
+            self.samples.append((time.perf_counter(), mhz,
+                                 [n for n, v in zip(self.NAMES, f[3:7]) if v.lower().startswith("active")]))
 
     def start(self):
+        try:
+            nv, h, bits = self._nvml_open()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_pump, args=(nv, h, bits), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_pump, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        t0 = self.t0 if self.t0 is not None else float("-inf")
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:
             return None
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        reasons = sorted({n for s in inside for n in s[2]})
+        return dict(sm_mhz=statistics.median(s[1] for s in inside), sm_max_mhz=self.mx, reasons=reasons,
+                    samples=len(inside), source=self.source)
 
 
 def build_model(device, precision):
@@ -245,23 +299,24 @@ def main():
         torch.cuda.synchronize(dev)
         return sum(a.elapsed_time(b) for a, b in evs)
 
-    for _ in range(args.warmup):
-        dev_step()
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()               # before the warm-up, so the sampler is already streaming when timing starts
+    for _ in range(args.warmup):
+        dev_step()
+    for _ in range(2):
+        host_step()
+    barrier()
+    clocks.begin()
     l0 = lib.fb_launch_count()
     tot_ms = timed(dev_step, args.steps)
     launches = lib.fb_launch_count() - l0
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     # end-to-end through the public API with host buffers
-    for _ in range(2):
-        host_step()
-    barrier()
     e2e_ms = timed(host_step, args.steps)
     barrier()
+    clocks.end()
+    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([tot_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
