@@ -19,8 +19,9 @@ HD = 128
 
 
 class Arena:
-    def __init__(self, sd, H, L, flavour=0, differentiable=False):
-        self.a = pack_state_dict(sd, H, L, flavour, differentiable=differentiable)
+    def __init__(self, sd, H, L, flavour=0, differentiable=False, arena=None):
+        # arena: an already packed (possibly requires_grad) flat tensor -- gradients w.r.t. the arena itself
+        self.a = pack_state_dict(sd, H, L, flavour, differentiable=differentiable) if arena is None else arena
         self.s = {n: (r, c, o) for n, r, c, o in slots(H, L, flavour)}
 
     def m(self, name):
@@ -68,7 +69,7 @@ def _radial(row, col, x, cplx_t, B):
     return d2 / nrm[cplx_t[row]]
 
 
-def forward_emulated(sd, cfg, batch, flavour=0, dropout=None, differentiable=False):
+def forward_emulated(sd, cfg, batch, flavour=0, dropout=None, differentiable=False, arena=None):
     """flavour 0: FABind v1 layout -> (X, H, stats); 1: FABind+ layout -> (X, H, stats, pair [P_total, H] packed rows).
     dropout = (p, seed, colonly): FABind+ train-mode masks with the library's counter-based mask function
     (fabind_b200/dropout.py), at the sites and row ids csrc/forward.cu uses."""
@@ -76,7 +77,7 @@ def forward_emulated(sd, cfg, batch, flavour=0, dropout=None, differentiable=Fal
     H = batch.H.shape[1]
     L = cfg.n_layers
     plus = flavour == 1
-    W = Arena(sd, H, L, flavour, differentiable)
+    W = Arena(sd, H, L, flavour, differentiable, arena)
     Dp = (2 * H + 1 + 63) // 64 * 64
     EPS = 1e-5
     lay = build_layout(batch.batch_id, batch.segment_id, batch.is_global, batch.mask, "cpu")
