@@ -378,13 +378,13 @@ def main():
         torch.set_num_threads(cores)
         cstep()
         ts = []
-        for i in range(3):
+        for i in range(8):
             t0 = time.perf_counter()
             cstep()
             ts.append(time.perf_counter() - t0)
         cpu = {"value": 1.0 / statistics.median(ts), "unit": "complexes/s", "cores": cores, "kind": "port",
                "sample": f"1 complex (n_c={N_C}, n_p={N_P}); thread count picked from {{16,32,all}} by subprocess "
-                         "probes, then 1 warm-up + 3 timed full forwards, median"}
+                         "probes, then 1 warm-up + 8 timed full forwards, median"}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "complexes/s", "n_gpus": world, "steps": args.steps,
