@@ -290,8 +290,12 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
   const int G = blockDim.x >> 6;   // node groups (64 feature lanes each) per CTA
   const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
   const int r = blockIdx.x * G + grp;
+  // row pointers of the CTA's G nodes, read once: the cooperative pass below walks them serially
+  __shared__ int s_rp[33];
+  if (threadIdx.x <= G) s_rp[threadIdx.x] = rowptr[min(blockIdx.x * G + (int)threadIdx.x, N)];
+  __syncthreads();
   int lo = 0, hi = 0;
-  if (r < N) { lo = rowptr[r]; hi = rowptr[r + 1]; }
+  if (r < N) { lo = s_rp[grp]; hi = s_rp[grp + 1]; }
   // coordinate part: first warp of each group, lanes over edges
   if (r < N && t < 32) {
     const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
   for (int k = 0; k < G; ++k) {
     const int rk = blockIdx.x * G + k;
     if (rk >= N) break;
-    const int lk = rowptr[rk], hk = rowptr[rk + 1];
+    const int lk = s_rp[k], hk = s_rp[k + 1];
     if (hk - lk <= GN_BIG) continue;
     for (int f0 = t * 8; f0 < H; f0 += 512) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(512) row_attention_kernel(GraphDev g, int q_is
   if (q0 >= n_q) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  float m[NQ], l[NQ], acc[NQ];
+  float m[NQ], l[NQ], acc[NQ], graw[NQ];
   int qn[NQ];
 #pragma unroll
   for (int u = 0; u < NQ; ++u) {
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(512) row_attention_kernel(GraphDev g, int q_is
     const int q_loc = q0 + warp * NQ + u;
     qn[u] = q_loc < n_q ? q_lo + q_loc : -1;
     sQ[(warp * NQ + u) * 32 + lane] = qn[u] >= 0 ? Q[(size_t)qn[u] * ldq + head * 32 + lane] * scale : 0.f;
+    graw[u] = qn[u] >= 0 ? G[(size_t)qn[u] * ldg + head * 32 + lane] : 0.f;   // gate: fetched up front, used at the very end
   }
   for (int j0 = 0; j0 < n_k; j0 += KC) {
     const int cnt = min(KC, n_k - j0);
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(512) row_attention_kernel(GraphDev g, int q_is
 #pragma unroll
   for (int u = 0; u < NQ; ++u) {
     if (qn[u] < 0) continue;
-    const float gate = sigmoidf(G[(size_t)qn[u] * ldg + head * 32 + lane]);
+    const float gate = sigmoidf(graw[u]);
     O[(size_t)qn[u] * ldo + head * 32 + lane] = from_f<T>(acc[u] / l[u] * gate);
   }
 }
