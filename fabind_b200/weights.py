@@ -217,3 +217,17 @@ def pack_state_dict(sd, hidden, n_layers, flavour=0, differentiable=False):
             raise RuntimeError(f"weight slot {name}: library expects [{rows},{cols}], packer produced {tuple(t.shape)}")
         arena[off:off + rows * cols] = t.reshape(-1).to(torch.float32)
     return arena
+
+
+def arena_grads_to_state_dict(sd, arena_grad, hidden, n_layers, flavour=0):
+    """Chain rule of the packer: gradient w.r.t. the flat weight arena (what backward kernels of this formulation produce:
+    hoisted first Linears, folded LayerNorms, collapsed pair-bias vector, stacked projections) -> gradients keyed and shaped
+    like the reference `state_dict` (what an optimizer over the drop-in modules' parameters consumes).  Parameters the
+    formulation never reads (`att_i.inter_layer.*` of the v1 layout, unused in the reference too) come back as zeros, which is
+    what the flat gradient all-reduce (`shard.allreduce_gradients`) expects.  Host-side, a few ms; float32 like the arena."""
+    leaves = {k: v.detach().cpu().to(torch.float32).clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    full = dict(sd)
+    full.update(leaves)
+    arena = pack_state_dict(full, hidden, n_layers, flavour, differentiable=True)
+    arena.backward(arena_grad.detach().cpu().to(torch.float32).reshape(-1))
+    return {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}

@@ -138,14 +138,15 @@ def test_explicit_backward_matches_autograd_and_reference():
         H, L = r["hidden"], r["n_layers"]
         ga, rx, rh, n = _explicit_vs_autograd(sd, cfg, b, H, L, r["readout_seed"])
         assert n >= 40
-        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-        pack_state_dict(sdg, H, L, 0, differentiable=True).backward(ga)      # chain rule of the packer
+        from fabind_b200.weights import arena_grads_to_state_dict
+        pg = arena_grads_to_state_dict(sd, ga, H, L, 0)                       # chain rule of the packer
+        assert set(pg) == set(sd) and all(float(v.abs().max()) == 0.0 for k, v in pg.items() if ".att_0.inter_layer." in k)
         gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
         m = 0
         for k, ref in g["grads"].items():
             if ref is None:
                 continue
-            err = float((sdg[k].grad - ref).abs().max())
+            err = float((pg[k] - ref).abs().max())
             assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
             m += 1
         assert m >= 80
