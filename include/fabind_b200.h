@@ -248,6 +248,42 @@ int32_t fb_post_optimize(const float* ref_coords, const float* pred_coords, cons
                          const int32_t* las_edges, const int32_t* las_off, int32_t n_las_total, int32_t epochs, float lr,
                          float* out_coords, float* out_loss, float* out_rmsd, void* stream);
 
+/* ---- reverse-pass primitives of the training path (fp32; BASELINE config 5).  The reference trains through torch autograd
+ * (main_fabind.py:380-401: loss.backward() over models/egnn.py, cross_att.py, model_utils.py); these are the launches of the
+ * hand-derived reverse pass of this library's formulation (specified and pinned in tests/emulate_backward.py), orchestrated
+ * by fabind_b200/backward.py.  Data-gradient GEMMs dX = dY W are fb_gemm on a transposed weight.  `act`: 0 none, 1 SiLU,
+ * 2 ReLU.  Scatter directions use fp32 atomics into caller-initialised buffers. ---- */
+/* Y = act(Z): re-materialise an activation from the saved pre-activation */
+int32_t fb_act_fwd(const float* Z, float* Y, int64_t n, int32_t act, void* stream);
+/* dZ = dY * act'(Z)  (in place allowed: dZ == dY) */
+int32_t fb_act_bwd(const float* Z, const float* dY, float* dZ, int64_t n, int32_t act, void* stream);
+/* dZ[m,n] = u[m] v[n] act'(Z[m,n]): reverse of a Linear(H,1) head behind an activation (coord_mlp, egnn.py:54-60) */
+int32_t fb_outer_act_bwd(const float* Z, const float* u, const float* v, float* dZ, int32_t M, int32_t N, int32_t act, void* stream);
+/* out[n] += sum_m w[m] A[m,n] (w == NULL: column sums): bias gradients and rank-1 (radial) column gradients */
+int32_t fb_colsum(const float* A, int32_t lda, int32_t M, int32_t N, const float* w, float* out, void* stream);
+/* out[m] = sum_n A[m,n] v[n] */
+int32_t fb_rowdot(const float* A, int32_t lda, int32_t M, int32_t N, const float* v, float* out, void* stream);
+/* dst[idx[e], :D] += src[e, :D]: reverse of the per-edge gathers of node rows (egnn.py:78 `h[row], h[col]`) */
+int32_t fb_scatter_add_rows(const float* src, int32_t lds, const int32_t* idx, int32_t E, int32_t D, float* dst, int32_t ldd,
+                            void* stream);
+/* dst[e, :D] += src[idx[e], :D]: reverse of unsorted_segment_sum (egnn.py:790-805) */
+int32_t fb_gather_add_rows(const float* src, int32_t lds, const int32_t* idx, int32_t E, int32_t D, float* dst, int32_t ldd,
+                           void* stream);
+/* dW[n,k] += sum_m dY[m,n] X[m,k]: weight gradient of y = x W^T */
+int32_t fb_gemm_wgrad(const float* dY, int32_t ldy, const float* X, int32_t ldx, int32_t M, int32_t N, int32_t K, float* dW,
+                      int32_t ldw, void* stream);
+/* reverse of x_new = x + clamp(sum_e (x[row]-x[col]) s_e / cnt, +-cmax) (egnn.py:85-98 with cnt = max(degree,1); egnn.py:228-233
+ * with cnt == NULL): ds[e], dx += ... ; dx holds dx_new on entry, step = the unclamped forward step */
+int32_t fb_coord_step_bwd(const float* x, const int32_t* row, const int32_t* col, int32_t E, const float* s, const float* step,
+                          const float* cnt, float cmax, const float* dx_new, float* dx, float* ds, void* stream);
+/* reverse of coord2radial with norm_type per_sample (egnn.py:767-787): nrm[b] = the forward's per-complex norm, drn[e] the
+ * gradient of the normalised radial, dot_zeroed[B] scratch (zero on entry), dx accumulated */
+int32_t fb_radial_bwd(const float* x, const int32_t* row, const int32_t* col, int32_t E, const int32_t* node_cplx, const float* nrm,
+                      const float* drn, float* dot_zeroed, float* dx, void* stream);
+/* reverse of the LAS constrained step (egnn.py:433-449): acc = the unclamped forward step, dx holds dx_new on entry */
+int32_t fb_las_bwd(const float* x, const float* xref, const int32_t* a_idx, const int32_t* b_idx, int32_t E, const float* acc,
+                   float step_size, float lcl, const float* dx_new, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
