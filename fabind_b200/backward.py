@@ -198,3 +198,196 @@ def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new):
     gather_add_rows(dh_pn, ident, dh, col0=0)
     radial_bwd(x, row, col, node_cplx, saved["nrm"], drn, dx)
     return dh, dx, grads
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# second group: MC_Att_L reverse and the whole last-iteration reverse pass of the v1 stack.  The kernels under these wrappers are
+# compiled and bound; their GPU parity tests are gated (FB_EXPERIMENTAL=1) until they have run on a B200.  The orchestration
+# below is validated on the CPU against the pinned specification (tests/test_backward_orchestration.py swaps every wrapper for
+# its torch definition).
+# ------------------------------------------------------------------------------------------------------------------------
+def rowdot2(A, Bm):
+    _chk(A), _chk(Bm)
+    M, N = A.shape
+    out = torch.empty(M, dtype=torch.float32, device=A.device)
+    _lib.check(_lib.lib().fb_rowdot2(A.data_ptr(), N, Bm.data_ptr(), N, M, N, out.data_ptr(), _st(A)), "fb_rowdot2")
+    return out
+
+
+def scale_rows(A, u):
+    """A[m,:] *= u[m] (in place)"""
+    _chk(A), _chk(u)
+    _lib.check(_lib.lib().fb_rows_update(A.data_ptr(), A.shape[1], A.shape[0], A.shape[1], u.data_ptr(), None, 0, _st(A)), "fb_rows_update")
+    return A
+
+
+def rank1_add(A, u, v):
+    """A[m,n] += u[m] v[n] (in place)"""
+    _chk(A), _chk(u), _chk(v)
+    _lib.check(_lib.lib().fb_rows_update(A.data_ptr(), A.shape[1], A.shape[0], A.shape[1], u.data_ptr(), v.data_ptr(), 1, _st(A)),
+               "fb_rows_update")
+    return A
+
+
+def vec_mul(a, b):
+    _chk(a), _chk(b)
+    c = torch.empty_like(a)
+    _lib.check(_lib.lib().fb_vec_op(a.data_ptr(), b.data_ptr(), c.data_ptr(), a.numel(), 0, _st(a)), "fb_vec_op")
+    return c
+
+
+def vec_add_(c, a):
+    """c += a (in place; c and a contiguous, same numel)"""
+    _chk(a), _chk(c)
+    _lib.check(_lib.lib().fb_vec_op(c.data_ptr(), a.data_ptr(), c.data_ptr(), c.numel(), 1, _st(a)), "fb_vec_op")
+    return c
+
+
+def gather_rows(src, idx, col0=0, width=None):
+    """src[idx, col0:col0+width] as a new contiguous tensor"""
+    width = src.shape[1] - col0 if width is None else width
+    dst = torch.zeros(idx.numel(), width, dtype=torch.float32, device=src.device)
+    return gather_add_rows(src, idx, dst, col0=col0)
+
+
+def softmax_seg_bwd(alpha, dalpha, row, n_rows):
+    _chk(alpha), _chk(dalpha), _chk(row, torch.int32)
+    t = torch.zeros(n_rows, dtype=torch.float32, device=alpha.device)
+    out = torch.empty_like(alpha)
+    _lib.check(_lib.lib().fb_softmax_seg_bwd(alpha.data_ptr(), dalpha.data_ptr(), row.data_ptr(), alpha.numel(), t.data_ptr(),
+                                             out.data_ptr(), _st(alpha)), "fb_softmax_seg_bwd")
+    return out
+
+
+def pair_bias_gate_bwd(raw, dPB):
+    """raw [P, ld], dPB [P, nblk, 4] -> draw [P, ld]"""
+    _chk(raw), _chk(dPB)
+    draw = torch.empty_like(raw)
+    _lib.check(_lib.lib().fb_pair_bias_gate_bwd(raw.data_ptr(), raw.shape[1], raw.shape[0], dPB.shape[1], dPB.data_ptr(), draw.data_ptr(),
+                                                _st(raw)), "fb_pair_bias_gate_bwd")
+    return draw
+
+
+def pair_outer_bwd(douter, pc, geo):
+    """douter [P,H], pc [N,H] (both sides, internal order) -> dpc [N,H]"""
+    _chk(douter), _chk(pc)
+    N, H = pc.shape
+    dpc = torch.zeros_like(pc)
+    _lib.check(_lib.lib().fb_pair_outer_bwd(douter.data_ptr(), pc.data_ptr(), H, geo["c_off"].data_ptr(), geo["p_off"].data_ptr(),
+                                            geo["pair_base"].data_ptr(), geo["node_cplx"].data_ptr(), geo["Nc"], N - geo["Nc"],
+                                            dpc.data_ptr(), _st(pc)), "fb_pair_outer_bwd")
+    return dpc
+
+
+def row_attention_bwd(geo, q_is_prot, Q, G, K, V, PB, dO, dQ, dG, dK, dV):
+    """Q, G, K, V, dQ, dG, dK, dV: (tensor, first column) pairs -- column slices of the stacked projection buffers; compound-side
+    buffers have Nc rows, protein-side buffers N - Nc rows (internal node id minus Nc).  PB [P,4] -> returns dPB [P,4]."""
+    Nc = geo["Nc"]
+
+    def ptr(tc, prot_side):
+        t, c0 = tc
+        _chk(t)
+        return t.data_ptr() + 4 * c0 - (4 * Nc * t.shape[1] if prot_side else 0), t.shape[1]
+    qs, ks = bool(q_is_prot), not bool(q_is_prot)
+    (q, ldq), (g, ldg), (k, ldk), (v, ldv) = ptr(Q, qs), ptr(G, qs), ptr(K, ks), ptr(V, ks)
+    (dq, lddq), (dg, lddg), (dk, lddk), (dv, lddv) = ptr(dQ, qs), ptr(dG, qs), ptr(dK, ks), ptr(dV, ks)
+    _chk(PB), _chk(dO)
+    dPB = torch.zeros_like(PB)
+    do = dO.data_ptr() - (4 * Nc * dO.shape[1] if qs else 0)
+    _lib.check(_lib.lib().fb_row_attention_bwd(geo["c_off"].data_ptr(), geo["p_off"].data_ptr(), geo["pair_base"].data_ptr(), geo["B"],
+                                               int(qs), geo["max_c"] if qs else geo["max_p"], q, ldq, g, ldg, k, ldk, v, ldv,
+                                               PB.data_ptr(), do, dO.shape[1], dq, lddq, dg, lddg, dk, lddk, dv, lddv, dPB.data_ptr(),
+                                               _st(dO)), "fb_row_attention_bwd")
+    return dPB
+
+
+HD = 128
+
+
+def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0):
+    """Reverse pass of one MC_Att_L sub-layer (v1 layout; forward: csrc/forward.cu::run_att; reference egnn.py:186-333,
+    cross_att.py:24-54).  Specification: tests/emulate_backward.py::att_bwd.
+
+    w: packed-arena tensors of the layer + `<name>_t` transposes of the matrices.  geo: int32 device tensors c_off, p_off, pair_base,
+    node_cplx and ints Nc, B, max_c, max_p.  row, col: int32 interface edges (destination, source).
+    sv (training-mode forward): h_in [N,H], x [N,3], CAc [Nc,4*128], CAp [Np,2*128], CAp2 [Np,2*128], PB_p, PB_c [P,4], Op, Oc, hp1, hc1,
+      Ttp, Ttc (transition hidden, post-ReLU), h2, QK [N,4H+128], pc32 [N,32], pair [E] int32, u_pair / u_pi / u_ci [U] int32 (pair row,
+      protein node, compound node of the lig->prot edges), zcat [U,H+64], Zp [U,H], rn [E], nrm [B], alpha, se [E], zc [E,H], step [N,3].
+    dP0 [P,H] is accumulated in place.  Returns (dh, dx, grads, dPB_p, dPB_c)."""
+    Nc, N = geo["Nc"], sv["h2"].shape[0]
+    H = sv["h2"].shape[1]
+    dev = dh3.device
+    x, rn, alpha, se, QK = sv["x"], sv["rn"], sv["alpha"], sv["se"], sv["QK"]
+    grads = {}
+    dQK = torch.zeros_like(QK)
+    # interfacial coordinate update
+    dx, dw = coord_step_bwd(x, row, col, vec_mul(alpha, se), sv["step"], None, cmax, dx_new)
+    dalpha, dse = vec_mul(dw, se), vec_mul(dw, alpha)
+    grads["ac2_w"] = colsum(act_fwd(sv["zc"], ACT_SILU), dse)
+    dzc = outer_act_bwd(sv["zc"], dse, w["ac2_w"], ACT_SILU)
+    grads["ac1_b"] = colsum(dzc)
+    grads["ac_u"] = colsum(dzc, rn)
+    drn = rowdot(dzc, w["ac_u"])
+    scatter_add_rows(dzc, col, dQK, col0=3 * H + 128)
+    # interfacial aggregation h3 = h2 + sum_e alpha_e (V[col] + rn v_r)
+    dh2 = dh3.clone()
+    dve = gather_rows(dh3, row)
+    ve = rank1_add(gather_rows(QK, col, 2 * H + 128, H), rn, w["v_r"])
+    vec_add_(dalpha, rowdot2(dve, ve))
+    scale_rows(dve, alpha)
+    scatter_add_rows(dve, col, dQK, col0=2 * H + 128)
+    grads["v_r"] = colsum(dve, rn)
+    vec_add_(drn, rowdot(dve, w["v_r"]))
+    # segment softmax over the destination row, then the logits q . (k + rn k_r) + pair bias
+    dlogit = softmax_seg_bwd(alpha, dalpha, row, N)
+    dq = rank1_add(gather_rows(QK, col, H, H), rn, w["k_r"])          # kk
+    scale_rows(dq, dlogit)
+    scatter_add_rows(dq, row, dQK, col0=0)
+    dkk = scale_rows(gather_rows(QK, row, 0, H), dlogit)
+    scatter_add_rows(dkk, col, dQK, col0=H)
+    grads["k_r"] = colsum(dkk, rn)
+    vec_add_(drn, rowdot(dkk, w["k_r"]))
+    # pair bias on the unique interface pairs
+    P = dP0.shape[0]
+    dpb_dense = torch.zeros(P, 1, dtype=torch.float32, device=dev)
+    scatter_add_rows(dlogit.view(-1, 1), sv["pair"], dpb_dense)
+    dpbu = gather_rows(dpb_dense, sv["u_pair"])                      # [U,1]
+    grads["pt_c"] = colsum(dpbu)
+    dpbu = dpbu.view(-1)
+    grads["pt2v"] = colsum(act_fwd(sv["Zp"], ACT_RELU), dpbu)
+    dZp = outer_act_bwd(sv["Zp"], dpbu, w["pt2v"], ACT_RELU)
+    dz = _linear_bwd(grads, "pt1_w", "pt1_b", w["pt1_w_t"], sv["zcat"], dZp)
+    scatter_add_rows(dz, sv["u_pair"], dP0, col0=0, width=H)
+    U = dz.shape[0]
+    ident_u = torch.arange(U, dtype=torch.int32, device=dev)
+    dt = gather_rows(dz, ident_u, H, 32)
+    a32, b32 = gather_rows(sv["pc32"], sv["u_pi"]), gather_rows(sv["pc32"], sv["u_ci"])
+    dpc32 = torch.zeros(N, 32, dtype=torch.float32, device=dev)
+    scatter_add_rows(vec_mul(dt, b32), sv["u_pi"], dpc32)
+    scatter_add_rows(vec_mul(dt, a32), sv["u_ci"], dpc32)
+    scatter_add_rows(dpc32[Nc:], torch.arange(Nc, N, dtype=torch.int32, device=dev), dQK, col0=2 * H)
+    scatter_add_rows(dpc32[:Nc], torch.arange(0, Nc, dtype=torch.int32, device=dev), dQK, col0=2 * H + 32)
+    radial_bwd(x, row, col, geo["node_cplx"], sv["nrm"], drn, dx)
+    vec_add_(dh2, _linear_bwd(grads, "qk_w", "qk_b", w["qk_w_t"], sv["h2"], dQK))
+    dhc, dhp = dh2[:Nc], dh2[Nc:]                                    # contiguous row slices, updated in place below
+    # transitions h + linear_2(relu(linear_1(h)))
+    dTc = _linear_bwd(grads, "tc2_w", "tc2_b", w["tc2_w_t"], sv["Ttc"], dhc)
+    vec_add_(dhc, _linear_bwd(grads, "tc1_w", "tc1_b", w["tc1_w_t"], sv["hc1"], act_bwd(sv["Ttc"], dTc, ACT_RELU)))
+    dTp = _linear_bwd(grads, "tp2_w", "tp2_b", w["tp2_w_t"], sv["Ttp"], dhp)
+    vec_add_(dhp, _linear_bwd(grads, "tp1_w", "tp1_b", w["tp1_w_t"], sv["hp1"], act_bwd(sv["Ttp"], dTp, ACT_RELU)))
+    # compound-side row attention (keys / values from the updated protein side)
+    dOc = _linear_bwd(grads, "o_c_w", "o_c_b", w["o_c_w_t"], sv["Oc"], dhc)
+    dCAc = torch.zeros_like(sv["CAc"])
+    dCAp2 = torch.zeros_like(sv["CAp2"])
+    dPB_c = row_attention_bwd(geo, 0, (sv["CAc"], 2 * HD), (sv["CAc"], 3 * HD), (sv["CAp2"], 0), (sv["CAp2"], HD), sv["PB_c"], dOc,
+                              (dCAc, 2 * HD), (dCAc, 3 * HD), (dCAp2, 0), (dCAp2, HD))
+    vec_add_(dhp, _linear_bwd(grads, "ca_p2_w", None, w["ca_p2_w_t"], sv["hp1"], dCAp2))
+    # protein-side row attention
+    dOp = _linear_bwd(grads, "o_p_w", "o_p_b", w["o_p_w_t"], sv["Op"], dhp)
+    dCAp = torch.zeros_like(sv["CAp"])
+    dPB_p = row_attention_bwd(geo, 1, (sv["CAp"], 0), (sv["CAp"], HD), (sv["CAc"], 0), (sv["CAc"], HD), sv["PB_p"], dOp,
+                              (dCAp, 0), (dCAp, HD), (dCAc, 0), (dCAc, HD))
+    h_in = sv["h_in"]
+    vec_add_(dhc, _linear_bwd(grads, "ca_c_w", "ca_c_b", w["ca_c_w_t"], h_in[:Nc], dCAc))
+    vec_add_(dhp, _linear_bwd(grads, "ca_p_w", "ca_p_b", w["ca_p_w_t"], h_in[Nc:], dCAp))
+    return dh2, dx, grads, dPB_p, dPB_c

@@ -226,6 +226,208 @@ __global__ void las_bwd_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
+// ---- second group (MC_Att_L reverse; compiled, orchestration validated on the CPU against autograd with stand-ins, GPU parity
+// tests gated behind FB_EXPERIMENTAL until they have run on a B200) -----------------------------------------------------------
+
+// out[m] = sum_n A[m,n] B[m,n]
+__global__ void rowdot2_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb, int M, int N,
+                               float* __restrict__ out) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* a = A + (size_t)warp * lda;
+  const float* b = Bm + (size_t)warp * ldb;
+  float s = 0.f;
+  for (int f = lane; f < N; f += 32) s = fmaf(a[f], b[f], s);
+  s = warp_sum(s);
+  if (lane == 0) out[warp] = s;
+}
+
+// A[m,n] = A[m,n] * u[m]   (mode 0)      A[m,n] += u[m] * v[n]   (mode 1)
+__global__ void rows_update_kernel(float* __restrict__ A, int lda, int M, int N, const float* __restrict__ u,
+                                   const float* __restrict__ v, int mode) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  float* a = A + (size_t)warp * lda;
+  const float um = u[warp];
+  if (mode == 0) { for (int f = lane; f < N; f += 32) a[f] *= um; }
+  else { for (int f = lane; f < N; f += 32) a[f] = fmaf(um, v[f], a[f]); }
+}
+
+// c = a * b (op 0), c = a + b (op 1), c += a * b (op 2)
+__global__ void vec_op_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ c, long long n, int op) {
+  pdl_entry();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (op == 0) c[i] = a[i] * b[i];
+    else if (op == 1) c[i] = a[i] + b[i];
+    else c[i] = fmaf(a[i], b[i], c[i]);
+  }
+}
+
+// segment softmax reverse (scatter_softmax over the destination row, egnn.py:221): dlogit_e = alpha_e (dalpha_e - sum_{e' in row} alpha dalpha)
+__global__ void softmax_seg_bwd_sum_kernel(const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                                           const int* __restrict__ row, int E, float* __restrict__ t) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) atomicAdd(&t[row[e]], alpha[e] * dalpha[e]);
+}
+__global__ void softmax_seg_bwd_apply_kernel(const float* __restrict__ alpha, const float* __restrict__ dalpha,
+                                             const int* __restrict__ row, int E, const float* __restrict__ t,
+                                             float* __restrict__ dlogit) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) dlogit[e] = alpha[e] * (dalpha[e] - t[row[e]]);
+}
+
+// gated pair bias reverse (model_utils.py:96-133 `linear(pair) * sigmoid(linear_g(pair))`): raw [P, ld] holds per block
+// (8 columns each) 4 values then 4 gates; dPB [P, nblk, 4] -> draw [P, ld] (columns >= 8 nblk zeroed)
+__global__ void pair_bias_gate_bwd_kernel(const float* __restrict__ raw, int ld, long long P, int nblk, const float* __restrict__ dPB,
+                                          float* __restrict__ draw) {
+  pdl_entry();
+  const long long total = P * ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / ld;
+    const int c = (int)(i - p * ld);
+    float o = 0.f;
+    if (c < 8 * nblk) {
+      const int blk = c >> 3, h = c & 3, is_gate = (c >> 2) & 1;
+      const float* rp = raw + p * ld + blk * 8;
+      const float sg = 1.0f / (1.0f + expf(-rp[4 + h]));
+      const float d = dPB[(p * nblk + blk) * 4 + h];
+      o = is_gate ? d * rp[h] * sg * (1.0f - sg) : d * sg;
+    }
+    draw[i] = o;
+  }
+}
+
+// reverse of the per-complex outer product pair0 operand  outer[b, i, j, :] = pp[i, :] * cc[j, :]  (model_utils.py:216-220):
+// one CTA per protein-side row i: dpp[i,:] = sum_j dO[i,j,:] cc[j,:]  (written),  dcc[j,:] += dO[i,j,:] pp[i,:]  (atomics)
+__global__ void pair_outer_bwd_kernel(const float* __restrict__ dO, const float* __restrict__ pc, int H, const int* __restrict__ c_off,
+                                      const int* __restrict__ p_off, const int* __restrict__ pair_base,
+                                      const int* __restrict__ node_cplx, int p_begin, float* __restrict__ dpc) {
+  pdl_entry();
+  const int i = p_begin + blockIdx.x;            // internal row of a protein-side node
+  const int b = node_cplx[i];
+  const int nc1 = c_off[b + 1] - c_off[b];
+  const size_t base = (size_t)pair_base[b] + (size_t)(i - p_off[b]) * nc1;
+  for (int f = threadIdx.x; f < H; f += blockDim.x) {
+    const float pv = pc[(size_t)i * H + f];
+    float acc = 0.f;
+    for (int j = 0; j < nc1; ++j) {
+      const float d = dO[(base + j) * H + f];
+      acc = fmaf(d, pc[(size_t)(c_off[b] + j) * H + f], acc);
+      atomicAdd(&dpc[(size_t)(c_off[b] + j) * H + f], d * pv);
+    }
+    dpc[(size_t)i * H + f] = acc;
+  }
+}
+
+// RowAttentionBlock core reverse (forward: layers.cu::row_attention_kernel; cross_att.py:118-134, model_utils.py:21-38):
+//   O[q, h*32+d] = sigmoid(G) * sum_j a_j v_j[d],  a = softmax_j(q.k_j / sqrt(32) + bias_j)
+// One CTA per (complex, head): the keys / values of the head and their gradient accumulators live in shared memory
+// (n_k <= RB_MAXK), every warp walks queries, probabilities are recomputed.  Writes dQ, dG, dPB (one owner each) and, once per
+// CTA, dK and dV.
+constexpr int RB_MAXK = 256;
+constexpr int RB_WARPS = 8;
+constexpr int RB_SMEM_FLOATS = 4 * RB_MAXK * 33 + RB_WARPS * (2 * RB_MAXK + 64);
+__global__ void __launch_bounds__(RB_WARPS * 32) row_attention_bwd_kernel(
+    const int* __restrict__ c_off, const int* __restrict__ p_off, const int* __restrict__ pair_base, int q_is_prot,
+    const float* __restrict__ Q, int ldq, const float* __restrict__ G, int ldg, const float* __restrict__ Kb, int ldk,
+    const float* __restrict__ Vb, int ldv, const float* __restrict__ PB, const float* __restrict__ dO, int ldo,
+    float* __restrict__ dQ, int lddq, float* __restrict__ dG, int lddg, float* __restrict__ dK, int lddk,
+    float* __restrict__ dV, int lddv, float* __restrict__ dPB) {
+  pdl_entry();
+  extern __shared__ float rb_smem[];
+  const int b = blockIdx.x, head = blockIdx.y;
+  const int c_lo = c_off[b], nc1 = c_off[b + 1] - c_lo, p_lo = p_off[b], np1 = p_off[b + 1] - p_lo;
+  const int n_q = q_is_prot ? np1 : nc1, n_k = q_is_prot ? nc1 : np1;
+  const int q_lo = q_is_prot ? p_lo : c_lo, k_lo = q_is_prot ? c_lo : p_lo;
+  float* sK = rb_smem;                   // [n_k][33]
+  float* sV = sK + RB_MAXK * 33;
+  float* sdK = sV + RB_MAXK * 33;
+  float* sdV = sdK + RB_MAXK * 33;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pa = sdV + RB_MAXK * 33 + warp * (2 * RB_MAXK + 64);   // probabilities of the warp's current query
+  float* pd = pa + RB_MAXK;                                      // da, then dlogit
+  float* wq = pd + RB_MAXK;                                      // scaled query, 32 channels
+  float* wdo = wq + 32;                                          // gradient w.r.t. the un-gated output, 32 channels
+  const float scale = 0.17677669529663687f;                      // 1/sqrt(32)
+  for (int i = threadIdx.x; i < n_k * 32; i += blockDim.x) {
+    const int j = i >> 5, d = i & 31;
+    sK[j * 33 + d] = Kb[(size_t)(k_lo + j) * ldk + head * 32 + d];
+    sV[j * 33 + d] = Vb[(size_t)(k_lo + j) * ldv + head * 32 + d];
+    sdK[j * 33 + d] = 0.f;
+    sdV[j * 33 + d] = 0.f;
+  }
+  __syncthreads();
+  for (int ql = warp; ql < n_q; ql += RB_WARPS) {
+    const int qn = q_lo + ql;
+    const float qd = Q[(size_t)qn * ldq + head * 32 + lane] * scale;      // lane = channel
+    const float gd = G[(size_t)qn * ldg + head * 32 + lane];
+    const float sg = 1.0f / (1.0f + expf(-gd));
+    const float dod = dO[(size_t)qn * ldo + head * 32 + lane];
+    const float do_d = dod * sg;
+    wq[lane] = qd;
+    wdo[lane] = do_d;
+    __syncwarp();
+    const size_t pb0 = (size_t)pair_base[b];
+    // scores and softmax: lanes over keys
+    float mx = -INFINITY;
+    for (int j = lane; j < n_k; j += 32) {
+      float sc = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) sc = fmaf(wq[d], sK[j * 33 + d], sc);
+      const size_t pair = pb0 + (q_is_prot ? ((size_t)ql * nc1 + j) : ((size_t)j * nc1 + ql));
+      sc += PB[pair * 4 + head];
+      pa[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n_k; j += 32) { const float e = expf(pa[j] - mx); pa[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    // da_j = <do, v_j>,  sum_j a_j da_j
+    float dsum = 0.f;
+    for (int j = lane; j < n_k; j += 32) {
+      const float a = pa[j] * inv;
+      float da = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) da = fmaf(wdo[d], sV[j * 33 + d], da);
+      pa[j] = a;
+      pd[j] = da;
+      dsum = fmaf(a, da, dsum);
+    }
+    dsum = warp_sum(dsum);
+    for (int j = lane; j < n_k; j += 32) {
+      const float dl = pa[j] * (pd[j] - dsum);
+      pd[j] = dl;
+      const size_t pair = pb0 + (q_is_prot ? ((size_t)ql * nc1 + j) : ((size_t)j * nc1 + ql));
+      dPB[pair * 4 + head] = dl;
+    }
+    __syncwarp();
+    // lane = channel: o (for the gate gradient), dq, and the accumulation into dk / dv
+    float od = 0.f, dq_d = 0.f;
+    for (int j = 0; j < n_k; ++j) {
+      const float a = pa[j], dl = pd[j];
+      od = fmaf(a, sV[j * 33 + lane], od);
+      dq_d = fmaf(dl, sK[j * 33 + lane], dq_d);
+      atomicAdd(&sdV[j * 33 + lane], a * do_d);
+      atomicAdd(&sdK[j * 33 + lane], dl * qd);
+    }
+    dG[(size_t)qn * lddg + head * 32 + lane] = dod * od * sg * (1.0f - sg);
+    dQ[(size_t)qn * lddq + head * 32 + lane] = dq_d * scale;
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_k * 32; i += blockDim.x) {
+    const int j = i >> 5, d = i & 31;
+    dK[(size_t)(k_lo + j) * lddk + head * 32 + d] = sdK[j * 33 + d];
+    dV[(size_t)(k_lo + j) * lddv + head * 32 + d] = sdV[j * 33 + d];
+  }
+}
+
 static inline int grid_1d(long long n, int block, int cap = 148 * 16) {
   long long g = (n + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -343,6 +545,82 @@ int32_t fb_las_bwd(const float* x, const float* xref, const int32_t* a_idx, cons
   if (E <= 0) return FB_OK;
   fb_launch(las_bwd_kernel, dim3((E + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x, xref, a_idx, b_idx, (int)E, acc, step_size,
             lcl, dx_new, dx);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_rowdot2(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t M, int32_t N, float* out, void* stream) {
+  if (M <= 0) return FB_OK;
+  fb_launch(rowdot2_kernel, dim3((int)(((long long)M * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, A, (int)lda, B, (int)ldb,
+            (int)M, (int)N, out);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_rows_update(float* A, int32_t lda, int32_t M, int32_t N, const float* u, const float* v, int32_t mode, void* stream) {
+  if (M <= 0 || N <= 0) return FB_OK;
+  if (mode != 0 && mode != 1) return FB_ERR_BAD_ARG;
+  fb_launch(rows_update_kernel, dim3((int)(((long long)M * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, A, (int)lda, (int)M,
+            (int)N, u, v, (int)mode);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_vec_op(const float* a, const float* b, float* c, int64_t n, int32_t op, void* stream) {
+  if (n <= 0) return FB_OK;
+  if (op < 0 || op > 2) return FB_ERR_BAD_ARG;
+  fb_launch(vec_op_kernel, dim3(grid_1d(n, 256)), dim3(256), 0, (cudaStream_t)stream, a, b, c, (long long)n, (int)op);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_softmax_seg_bwd(const float* alpha, const float* dalpha, const int32_t* row, int32_t E, float* t_zeroed, float* dlogit,
+                           void* stream) {
+  if (E <= 0) return FB_OK;
+  fb_launch(softmax_seg_bwd_sum_kernel, dim3((E + 255) / 256), dim3(256), 0, (cudaStream_t)stream, alpha, dalpha, row, (int)E, t_zeroed);
+  fb_launch(softmax_seg_bwd_apply_kernel, dim3((E + 255) / 256), dim3(256), 0, (cudaStream_t)stream, alpha, dalpha, row, (int)E,
+            (const float*)t_zeroed, dlogit);
+  count_launch(2);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_pair_bias_gate_bwd(const float* raw, int32_t ld, int64_t P, int32_t nblk, const float* dPB, float* draw, void* stream) {
+  if (P <= 0) return FB_OK;
+  if (8 * nblk > ld) return FB_ERR_BAD_ARG;
+  fb_launch(pair_bias_gate_bwd_kernel, dim3(grid_1d(P * ld, 256)), dim3(256), 0, (cudaStream_t)stream, raw, (int)ld, (long long)P,
+            (int)nblk, dPB, draw);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_pair_outer_bwd(const float* dO, const float* pc, int32_t H, const int32_t* c_off, const int32_t* p_off,
+                          const int32_t* pair_base, const int32_t* node_cplx, int32_t p_begin, int32_t n_p_rows, float* dpc,
+                          void* stream) {
+  if (n_p_rows <= 0) return FB_OK;
+  fb_launch(pair_outer_bwd_kernel, dim3(n_p_rows), dim3(128), 0, (cudaStream_t)stream, dO, pc, (int)H, c_off, p_off, pair_base, node_cplx,
+            (int)p_begin, dpc);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_row_attention_bwd(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t q_is_prot,
+                             int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K, int32_t ldk,
+                             const float* V, int32_t ldv, const float* PB, const float* dO, int32_t ldo, float* dQ, int32_t lddq,
+                             float* dG, int32_t lddg, float* dK, int32_t lddk, float* dV, int32_t lddv, float* dPB, void* stream) {
+  if (B <= 0) return FB_OK;
+  if (max_k > RB_MAXK) return FB_ERR_UNSUPPORTED;
+  static unsigned long long done = 0;
+  if (!ensure_smem_optin(row_attention_bwd_kernel, RB_SMEM_FLOATS * 4, done)) return FB_ERR_CUDA;
+  fb_launch(row_attention_bwd_kernel, dim3(B, 4), dim3(RB_WARPS * 32), RB_SMEM_FLOATS * 4, (cudaStream_t)stream, c_off, p_off, pair_base,
+            (int)q_is_prot, Q, (int)ldq, G, (int)ldg, K, (int)ldk, V, (int)ldv, PB, dO, (int)ldo, dQ, (int)lddq, dG, (int)lddg, dK,
+            (int)lddk, dV, (int)lddv, dPB);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

@@ -283,6 +283,29 @@ int32_t fb_radial_bwd(const float* x, const int32_t* row, const int32_t* col, in
 /* reverse of the LAS constrained step (egnn.py:433-449): acc = the unclamped forward step, dx holds dx_new on entry */
 int32_t fb_las_bwd(const float* x, const float* xref, const int32_t* a_idx, const int32_t* b_idx, int32_t E, const float* acc,
                    float step_size, float lcl, const float* dx_new, float* dx, void* stream);
+/* -- second group: MC_Att_L reverse (row attention, interfacial attention, pair path).  Compiled and bound; their GPU parity
+ *    tests are gated behind FB_EXPERIMENTAL=1 until they have run on a B200 (the orchestration over them is validated on the
+ *    CPU against autograd with stand-ins, tests/test_backward_orchestration.py). -- */
+/* out[m] = sum_n A[m,n] B[m,n] */
+int32_t fb_rowdot2(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t M, int32_t N, float* out, void* stream);
+/* mode 0: A[m,:] *= u[m];  mode 1: A[m,n] += u[m] v[n]  (the rank-1 radial terms of linear_kv, egnn.py:203-205) */
+int32_t fb_rows_update(float* A, int32_t lda, int32_t M, int32_t N, const float* u, const float* v, int32_t mode, void* stream);
+/* op 0: c = a*b, 1: c = a+b, 2: c += a*b */
+int32_t fb_vec_op(const float* a, const float* b, float* c, int64_t n, int32_t op, void* stream);
+/* reverse of scatter_softmax over the destination row (egnn.py:221): dlogit = alpha (dalpha - segsum(alpha dalpha)); t_zeroed[N] scratch */
+int32_t fb_softmax_seg_bwd(const float* alpha, const float* dalpha, const int32_t* row, int32_t E, float* t_zeroed, float* dlogit,
+                           void* stream);
+/* reverse of the gated pair bias linear(pair)*sigmoid(linear_g(pair)) (model_utils.py:96-133): raw [P,ld] = per block 4 values + 4 gates */
+int32_t fb_pair_bias_gate_bwd(const float* raw, int32_t ld, int64_t P, int32_t nblk, const float* dPB, float* draw, void* stream);
+/* reverse of the InteractionModule outer product p_i * c_j per complex (model_utils.py:216-220): dpc rows of both sides */
+int32_t fb_pair_outer_bwd(const float* dO, const float* pc, int32_t H, const int32_t* c_off, const int32_t* p_off,
+                          const int32_t* pair_base, const int32_t* node_cplx, int32_t p_begin, int32_t n_p_rows, float* dpc,
+                          void* stream);
+/* reverse of the RowAttentionBlock core (cross_att.py:118-134, model_utils.py:21-38), probabilities recomputed; PB / dPB = [P,4] */
+int32_t fb_row_attention_bwd(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t q_is_prot,
+                             int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K, int32_t ldk,
+                             const float* V, int32_t ldv, const float* PB, const float* dO, int32_t ldo, float* dQ, int32_t lddq,
+                             float* dG, int32_t lddg, float* dK, int32_t lddk, float* dV, int32_t lddv, float* dPB, void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,7 +91,7 @@ def gcl_fwd(W, pre, h, x, ctx, cplx, B, cmax):
     Z4 = F.linear(cat, W.m(pre + "n1_w"), W.m(pre + "n1_b"))
     t1 = F.silu(Z4)
     h_new = h + F.linear(t1, W.m(pre + "n2_w"), W.m(pre + "n2_b"))
-    return h_new, x_new, dict(h=h, rn=rn, rs=rs, Z1=Z1, A1=A1, Z2=Z2, M=M, Z3=Z3, T3=T3, s=s, deg=deg, d=d, step=step,
+    return h_new, x_new, dict(h=h, x=x, rn=rn, rs=rs, Z1=Z1, A1=A1, Z2=Z2, M=M, Z3=Z3, T3=T3, s=s, deg=deg, d=d, step=step,
                               cat=cat, Z4=Z4, t1=t1)
 
 
@@ -134,7 +134,7 @@ def las_fwd(x, xl, las, step_size, lcl):
     d = x[a] - x[b]
     diff = (d * d).sum(1) - ((xl[a] - xl[b]) ** 2).sum(1)
     acc = torch.zeros_like(x).index_add_(0, b, 4 * diff[:, None] * d) * step_size
-    return x + acc.clamp(-lcl, lcl), dict(d=d, diff=diff, acc=acc)
+    return x + acc.clamp(-lcl, lcl), dict(x=x, d=d, diff=diff, acc=acc)
 
 
 def las_bwd(sv, las, step_size, lcl, dx_new):
@@ -234,7 +234,7 @@ def att_fwd(W, pre, l, h, x, geo, P0, PB, inter, cmax):
     step = torch.zeros(N, 3).index_add_(0, int_r, d * (alpha * se)[:, None])
     x_new = x + step.clamp(-cmax, cmax)
     sv = dict(hc0=hc0, hp0=hp0, blocks=blocks, svp=svp, svc=svc, Op=Op, Oc=Oc, hp1=hp1, hc1=hc1, Tp=Tp, Tc=Tc, h2=h2, QK=QK,
-              pc32=pc32, pi=pi, ci=ci, pair=pair, u=u, zcat=zcat, Zp=Zp, Rp=Rp, rn=rn, rs=rs, q=q, kk=kk, alpha=alpha, ve=ve,
+              CAc=CAc, CAp=CAp, CAp2=CAp2, x=x, h_in=h, pc32=pc32, pi=pi, ci=ci, pair=pair, u=u, zcat=zcat, Zp=Zp, Rp=Rp, rn=rn, rs=rs, q=q, kk=kk, alpha=alpha, ve=ve,
               zc=zc, sc=sc, se=se, d=d, step=step)
     return h3, x_new, sv
 
@@ -320,9 +320,10 @@ def att_bwd(G, W, pre, l, sv, geo, inter, cmax, dh3, dx_new, dP0, dPB):
 
 
 # ------------------------------------------------------------------------------------------------- whole step
-def forward_backward_v1(sd, cfg, batch, gX, gH, arena=None):
+def forward_backward_v1(sd, cfg, batch, gX, gH, arena=None, export=None):
     """Forward (all iterations) + explicit backward of the last one for loss = <X_out, gX> + <H_out, gH>.
-    Returns (X_out, H_out, grad of the flat arena, grad of batch.H)."""
+    Returns (X_out, H_out, grad of the flat arena, grad of batch.H).  export: optional dict that receives the internals of the
+    last iteration (weights, geometry, edge lists, per-layer saved tensors) for tests of GPU-side orchestration."""
     from types import SimpleNamespace
     H = batch.H.shape[1]
     L = cfg.n_layers
@@ -382,6 +383,9 @@ def forward_backward_v1(sd, cfg, batch, gX, gH, arena=None):
         H_out = torch.empty_like(batch.H)
         H_out[permt] = h_final
 
+        if export is not None:
+            export.update(W=W, geo=geo, ctx=ctx, inter=inter, las=las, tape=tape, s_out=s_out, P0=P0, PB=PB, cmax=cmax, lcl=lcl,
+                          xl=xl, N=N, B=B, Nc=Nc)
         # ---- reverse pass
         G = Grads()
         dx = gX[permt, 0] * moves[:, None]
