@@ -391,3 +391,47 @@ def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0):
     vec_add_(dhc, _linear_bwd(grads, "ca_c_w", "ca_c_b", w["ca_c_w_t"], h_in[:Nc], dCAc))
     vec_add_(dhp, _linear_bwd(grads, "ca_p_w", "ca_p_b", w["ca_p_w_t"], h_in[Nc:], dCAp))
     return dh2, dx, grads, dPB_p, dPB_c
+
+
+def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
+    """Reverse pass of the LAST refinement iteration of the v1 stack (att_model.py:227-245: earlier iterations run under no_grad):
+    linear_out <- out layer <- [LAS <- MC_Att_L <- MC_E_GCL] x L <- linear_in, plus pair_embed0 and the gated pair biases of every
+    row-attention block.  Specification: tests/emulate_backward.py::forward_backward_v1.
+
+    weights: {prefix: dict of packed-arena tensors (+ `_t` transposes)} for "" (top level), "gclI.", "attI.", "out.".
+    tape: per layer (saved_gcl, saved_att, saved_las); top: Hin, pc, outer, P0, raw_full, h_last, out_saved (internal node order).
+    edges: ctx_row/ctx_col, int_row/int_col, las_a/las_b (int32).  consts: cmax, lcl, las_step, xl (LAS reference coordinates).
+    dH_out [N,H], dX_out [N,3]: gradients of the outputs in internal order (dX_out already masked to the moving nodes).
+    Returns (grads keyed by full slot name, dHin)."""
+    L = len(tape)
+    Nc = geo["Nc"]
+    grads = {}
+
+    def take(pre, g):
+        for k, v in g.items():
+            grads[pre + k] = v
+    g0 = {}
+    dh = _linear_bwd(g0, "out_w", "out_b", weights[""]["out_w_t"], top["h_last"], dH_out)
+    dh, dx, g = gcl_backward(weights["out."], top["out_saved"], edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dX_out)
+    take("out.", g)
+    P0 = top["P0"]
+    dP0 = torch.zeros_like(P0)
+    dPB = torch.zeros(P0.shape[0], 2 * L, 4, dtype=torch.float32, device=P0.device)
+    for l in reversed(range(L)):
+        s_gcl, s_att, s_las = tape[l]
+        dx = las_bwd(s_las["x"], consts["xl"], edges["las_a"], edges["las_b"], s_las["acc"], consts["las_step"], consts["lcl"], dx)
+        dh, dx, g, dPB_p, dPB_c = att_backward(weights[f"att{l}."], s_att, geo, edges["int_row"], edges["int_col"], consts["cmax"], dh, dx, dP0)
+        take(f"att{l}.", g)
+        dPB[:, 2 * l].copy_(dPB_p)
+        dPB[:, 2 * l + 1].copy_(dPB_c)
+        dh, dx, g = gcl_backward(weights[f"gcl{l}."], s_gcl, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dx)
+        take(f"gcl{l}.", g)
+    dHin = _linear_bwd(g0, "in_w", "in_b", weights[""]["in_w_t"], top["Hin"], dh)
+    draw = pair_bias_gate_bwd(top["raw_full"], dPB)
+    vec_add_(dP0, _linear_bwd(g0, "pb_w", "pb_b", weights[""]["pb_w_t"], P0, draw))
+    douter = _linear_bwd(g0, "il_o_w", "il_o_b", weights[""]["il_o_w_t"], top["outer"], dP0)
+    dpc = pair_outer_bwd(douter, top["pc"], geo)
+    vec_add_(dHin[:Nc], _linear_bwd(g0, "il_c_w", "il_c_b", weights[""]["il_c_w_t"], top["Hin"][:Nc], dpc[:Nc]))
+    vec_add_(dHin[Nc:], _linear_bwd(g0, "il_p_w", "il_p_b", weights[""]["il_p_w_t"], top["Hin"][Nc:], dpc[Nc:]))
+    take("", g0)
+    return grads, dHin

@@ -125,15 +125,10 @@ def _weights(W, pre, names):
 def test_orchestration_matches_specification(monkeypatch):
     from fabind_b200 import backward as bw
     _install_standins(monkeypatch, bw)
-    g, r, b, sd, cfg = load_golden(sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))[0])
-    gen = torch.Generator().manual_seed(4)
-    ex = {}
-    spec.forward_backward_v1(sd, cfg, b, torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen), export=ex)
+    ex, cfg, H, dh_up, dx_up = spec_case()
     W, geo, tape, N, B, Nc, cmax = ex["W"], ex["geo"], ex["tape"], ex["N"], ex["B"], ex["Nc"], ex["cmax"]
-    H = b.H.shape[1]
     i32 = lambda t: t.to(torch.int32)
     s1, s2, s3 = tape[0]
-    dh_up, dx_up = torch.randn(N, H, generator=gen), torch.randn(N, 3, generator=gen)
 
     # ---- LAS step
     a, bb = ex["las"]
@@ -155,6 +150,39 @@ def test_orchestration_matches_specification(monkeypatch):
         assert rel_err(v.reshape(-1), G["gcl0." + k].reshape(-1)) < 1e-5, k
 
     # ---- MC_Att_L
+    case = att_case(ex, dh_up, dx_up)
+    dP0 = torch.zeros_like(ex["P0"])
+    dh, dx, grads, dPB_p, dPB_c = bw.att_backward(case["w"], case["sv"], case["geo"], case["row"], case["col"], cmax, dh_up.clone(),
+                                                  dx_up.clone(), dP0)
+    check_att(case, dh, dx, grads, dPB_p, dPB_c, dP0, 1e-5)
+
+
+def spec_case(seed=4):
+    """saved tensors of the last iteration of a real forward (gradient golden batch) + upstream gradients"""
+    g, r, b, sd, cfg = load_golden(sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))[0])
+    gen = torch.Generator().manual_seed(seed)
+    ex = {}
+    spec.forward_backward_v1(sd, cfg, b, torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen), export=ex)
+    H = b.H.shape[1]
+    return ex, cfg, H, torch.randn(ex["N"], H, generator=gen), torch.randn(ex["N"], 3, generator=gen)
+
+
+def check_att(case, dh, dx, grads, dPB_p, dPB_c, dP0, tol):
+    G = case["G"]
+    assert rel_err(dh, case["dh"]) < tol, rel_err(dh, case["dh"])
+    assert rel_err(dx, case["dx"]) < tol, rel_err(dx, case["dx"])
+    assert rel_err(dP0, case["dP0"]) < tol
+    assert rel_err(dPB_p, case["dPB"][:, 0, 0]) < tol and rel_err(dPB_c, case["dPB"][:, 0, 1]) < tol
+    assert set("att0." + k for k in grads) == set(G), set("att0." + k for k in grads) ^ set(G)
+    for k, v in grads.items():
+        assert rel_err(v.reshape(-1), G["att0." + k].reshape(-1)) < tol, k
+
+
+def att_case(ex, dh_up, dx_up):
+    """inputs of bw.att_backward for layer 0 of the exported forward + the specification's results"""
+    W, geo, tape, N, B, Nc, cmax = ex["W"], ex["geo"], ex["tape"], ex["N"], ex["B"], ex["Nc"], ex["cmax"]
+    i32 = lambda t: t.to(torch.int32)
+    s2 = tape[0][1]
     G = spec.Grads()
     P0, PB = ex["P0"], ex["PB"]
     rdP0, rdPB = torch.zeros_like(P0), torch.zeros_like(PB)
@@ -169,13 +197,121 @@ def test_orchestration_matches_specification(monkeypatch):
               Op=s2["Op"], Oc=s2["Oc"], hp1=s2["hp1"], hc1=s2["hc1"], Ttp=s2["Tp"], Ttc=s2["Tc"], h2=s2["h2"], QK=s2["QK"], pc32=s2["pc32"],
               pair=i32(s2["pair"]), u_pair=i32(s2["pair"][u]), u_pi=i32(s2["pi"][u]), u_ci=i32(s2["ci"][u]), zcat=s2["zcat"], Zp=s2["Zp"],
               rn=s2["rn"], nrm=s2["rs"][2], alpha=s2["alpha"], se=s2["se"], zc=s2["zc"], step=s2["step"])
-    dP0 = torch.zeros_like(P0)
-    dh, dx, grads, dPB_p, dPB_c = bw.att_backward(_weights(W, "att0.", names), sv, geo_dev, i32(ex["inter"][0]), i32(ex["inter"][1]), cmax,
-                                                  dh_up.clone(), dx_up.clone(), dP0)
-    assert rel_err(dh, rdh) < 1e-5, rel_err(dh, rdh)
-    assert rel_err(dx, rdx) < 1e-5, rel_err(dx, rdx)
-    assert rel_err(dP0, rdP0) < 1e-5
-    assert rel_err(dPB_p, rdPB[:, 0, 0]) < 1e-5 and rel_err(dPB_c, rdPB[:, 0, 1]) < 1e-5
-    assert set("att0." + k for k in grads) == set(G), set("att0." + k for k in grads) ^ set(G)
-    for k, v in grads.items():
-        assert rel_err(v.reshape(-1), G["att0." + k].reshape(-1)) < 1e-5, k
+    return dict(w=_weights(W, "att0.", names), sv=sv, geo=geo_dev, row=i32(ex["inter"][0]), col=i32(ex["inter"][1]), G=G, dh=rdh, dx=rdx,
+                dP0=rdP0, dPB=rdPB)
+
+
+def _gcl_saved(s1, H):
+    return dict(h=s1["h"], x=s1["x"], rn=s1["rn"], nrm=s1["rs"][2], Z1=s1["Z1"], Z2=s1["Z2"], Z3=s1["Z3"], s=s1["s"], deg=s1["deg"],
+                step=s1["step"], agg=s1["cat"][:, H:].contiguous(), Z4=s1["Z4"])
+
+
+def _att_saved(s2, PB, l):
+    i32 = lambda t: t.to(torch.int32)
+    u = s2["u"]
+    return dict(h_in=s2["h_in"], x=s2["x"], CAc=s2["CAc"], CAp=s2["CAp"], CAp2=s2["CAp2"], PB_p=PB[:, l, 0].contiguous(),
+                PB_c=PB[:, l, 1].contiguous(), Op=s2["Op"], Oc=s2["Oc"], hp1=s2["hp1"], hc1=s2["hc1"], Ttp=s2["Tp"], Ttc=s2["Tc"], h2=s2["h2"],
+                QK=s2["QK"], pc32=s2["pc32"], pair=i32(s2["pair"]), u_pair=i32(s2["pair"][u]), u_pi=i32(s2["pi"][u]), u_ci=i32(s2["ci"][u]),
+                zcat=s2["zcat"], Zp=s2["Zp"], rn=s2["rn"], nrm=s2["rs"][2], alpha=s2["alpha"], se=s2["se"], zc=s2["zc"], step=s2["step"])
+
+
+GCL_W = ["e1_rc", "e1_rad", "e2_w", "c1_w", "c2_w", "n1_w", "n2_w"]
+ATT_W = ["ac2_w", "ac_u", "ac1_b", "v_r", "k_r", "pt2v", "pt_c", "pt1_w", "qk_w", "tc1_w", "tc2_w", "tp1_w", "tp2_w", "o_c_w", "o_p_w", "ca_p2_w",
+         "ca_c_w", "ca_p_w"]
+TOP_W = ["out_w", "in_w", "pb_w", "il_o_w", "il_c_w", "il_p_w"]
+
+
+def two_layer_problem():
+    from fabind_b200 import EfficientMCAttModel
+    from fabind_b200.config import published_args
+    from fabind_b200.synthetic import make_batch
+    from oracle import fabind_oracle as orc
+    from oracle.det_weights import det_state_dict
+    H, L = 32, 2
+    m = EfficientMCAttModel(published_args(), H, H, 1, n_layers=L, n_iter=2,
+                            normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 23)
+    return make_batch(n_complexes=3, seed=11, embed=H, n_c_range=(4, 9), n_p_range=(10, 20)), sd, orc.make_cfg(n_layers=L, n_iter=2)
+
+
+def stack_case(path=None, seed=7, problem=None):
+    """everything fabind_b200.backward.stack_backward_v1 consumes, from the specification's forward on a golden batch (or on a
+    (batch, state_dict, cfg) problem), and the specification's arena gradient"""
+    if problem is None:
+        g, r, b, sd, cfg = load_golden(path)
+    else:
+        b, sd, cfg = problem
+    gen = torch.Generator().manual_seed(seed)
+    gX, gH = torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen)
+    ex = {}
+    _, _, garena, gHin = spec.forward_backward_v1(sd, cfg, b, gX, gH, export=ex)
+    W, geo, N, B, Nc, H, L = ex["W"], ex["geo"], ex["N"], ex["B"], ex["Nc"], b.H.shape[1], cfg.n_layers
+    i32 = lambda t: t.to(torch.int32)
+    geo_dev = dict(Nc=Nc, B=B, c_off=i32(torch.from_numpy(geo["c_off"].astype(np.int64))), p_off=i32(torch.from_numpy(geo["p_off"].astype(np.int64))),
+                   pair_base=i32(torch.from_numpy(geo["pair_base"].astype(np.int64))), node_cplx=i32(geo["cplx"]),
+                   max_c=int(np.diff(geo["c_off"]).max()), max_p=int(np.diff(geo["p_off"]).max()))
+    weights = {"": _weights(W, "", TOP_W), "out.": _weights(W, "out.", GCL_W)}
+    tape = []
+    for l in range(L):
+        weights[f"gcl{l}."] = _weights(W, f"gcl{l}.", GCL_W)
+        weights[f"att{l}."] = _weights(W, f"att{l}.", ATT_W)
+        s1, s2, s3 = ex["tape"][l]
+        tape.append((_gcl_saved(s1, H), _att_saved(s2, ex["PB"], l), dict(x=s3["x"], acc=s3["acc"])))
+    top = dict(Hin=ex["Hin"], pc=ex["pc"], outer=ex["outer"], P0=ex["P0"], raw_full=ex["raw_full"], h_last=ex["h_last"],
+               out_saved=_gcl_saved(ex["s_out"], H))
+    edges = dict(ctx_row=i32(ex["ctx"][0]), ctx_col=i32(ex["ctx"][1]), int_row=i32(ex["inter"][0]), int_col=i32(ex["inter"][1]),
+                 las_a=i32(ex["las"][0]), las_b=i32(ex["las"][1]))
+    consts = dict(cmax=ex["cmax"], lcl=ex["lcl"], las_step=cfg.geometry_reg_step_size, xl=ex["xl"])
+    permt = ex["permt"]
+    dH_out, dX_out = gH[permt].contiguous(), (gX[permt, 0] * ex["moves"][:, None]).contiguous()
+    return dict(weights=weights, tape=tape, top=top, geo=geo_dev, edges=edges, consts=consts, dH_out=dH_out, dX_out=dX_out, W=W,
+                garena=garena, gHin=gHin[permt])
+
+
+def check_stack(case, grads, dHin, tol):
+    W, ref = case["W"], case["garena"]
+    gmax = float(ref.abs().max())
+    seen = 0
+    for name, (r, c, off) in W.s.items():
+        if r * c == 0:
+            continue
+        t = ref[off:off + r * c]
+        if name not in grads:
+            assert float(t.abs().max()) == 0.0, f"{name}: gradient missing"
+            continue
+        err = float((grads[name].reshape(-1) - t).abs().max())
+        assert err < tol * float(t.abs().max()) + 1e-2 * tol * gmax, (name, err, float(t.abs().max()))
+        seen += 1
+    assert seen >= 40
+    assert rel_err(dHin, case["gHin"]) < tol
+
+
+def test_stack_reverse_pass_matches_specification(monkeypatch):
+    """the whole last-iteration reverse pass as fabind_b200.backward orchestrates it == the specification's arena gradient"""
+    from fabind_b200 import backward as bw
+    _install_standins(monkeypatch, bw)
+
+    def gate(raw, dPB):
+        P, nblk = dPB.shape[0], dPB.shape[1]
+        r5 = raw[:, :8 * nblk].reshape(P, nblk, 2, 4)
+        sg = torch.sigmoid(r5[:, :, 1])
+        out = torch.zeros_like(raw)
+        out[:, :8 * nblk] = torch.stack([dPB * sg, dPB * r5[:, :, 0] * sg * (1 - sg)], 2).reshape(P, -1)
+        return out
+
+    def outer_bwd(douter, pc, geo):
+        dpc = torch.zeros_like(pc)
+        for b in range(geo["B"]):
+            c0, c1, p0, p1 = int(geo["c_off"][b]), int(geo["c_off"][b + 1]), int(geo["p_off"][b]), int(geo["p_off"][b + 1])
+            t = douter[int(geo["pair_base"][b]):int(geo["pair_base"][b + 1])].view(p1 - p0, c1 - c0, -1)
+            dpc[p0:p1] += (t * pc[None, c0:c1]).sum(1)
+            dpc[c0:c1] += (t * pc[p0:p1, None]).sum(0)
+        return dpc
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", gate)
+    monkeypatch.setattr(bw, "pair_outer_bwd", outer_bwd)
+    cases = [stack_case(path) for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))]
+    cases.append(stack_case(problem=two_layer_problem()))      # two layers: pair-bias blocks and pair_embed0 gradients accumulate
+    for case in cases:
+        grads, dHin = bw.stack_backward_v1(case["weights"], case["tape"], case["top"], case["geo"], case["edges"], case["consts"],
+                                           case["dH_out"], case["dX_out"])
+        check_stack(case, grads, dHin, 1e-4)
