@@ -1,13 +1,17 @@
-"""Reverse pass of the docking stack on the GPU (training path, fp32) -- first part: the primitives and the MC_E_GCL sub-layer.
+"""Reverse pass of the docking stack on the GPU (training path, fp32): the primitives, the MC_E_GCL / MC_Att_L / LAS sub-layer
+reverse passes and the whole last-iteration reverse pass of the v1 stack (`stack_backward_v1`).
 
 The reference trains through torch autograd (main_fabind.py:380-401).  Here the reverse pass is hand-derived for the library's
-formulation (hoisted first Linears, CSR segment reductions; specification pinned against autograd and the unmodified
-reference: tests/emulate_backward.py) and runs as launches of csrc/backward.cu plus fb_gemm for the data-gradient GEMMs
-(`dX = dY W` on a transposed weight).  torch only allocates device memory here; there is no torch arithmetic on the path and
-no fallback: CPU tensors raise.
+formulation (hoisted first Linears, collapsed pair-bias vector, pair work on the interface pairs only; specification pinned
+against autograd and the unmodified reference's parameter gradients: tests/emulate_backward.py) and runs as launches of
+csrc/backward.cu plus fb_gemm for the data-gradient GEMMs (`dX = dY W` on a transposed weight).  torch only allocates / copies
+device memory here; there is no torch arithmetic on the path and no fallback: CPU tensors raise.
 
-Status: MC_E_GCL (egnn.py:68-144) reverse pass + the LAS step (egnn.py:433-449); MC_Att_L's reverse kernels (row attention,
-interfacial attention, pair path) are the next round's work."""
+Status (round 1): every reverse kernel and `stack_backward_v1` are parity-green on a B200 against the specification's arena
+gradient (tests/test_gpu_backward.py, tests/test_gpu_backward_att.py).  Not built yet: the training-mode forward that stores the
+pre-activations these functions consume (the tests take them from the specification's forward), the FABind+ layout's reverse
+kernels (specified in tests/emulate_backward.py), bf16 / tcgen05 weight-gradient GEMMs, and the `backward()` of the drop-in
+modules -- so `train()` with autograd enabled still raises."""
 import ctypes as C
 
 import torch
@@ -201,10 +205,9 @@ def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new):
 
 
 # ------------------------------------------------------------------------------------------------------------------------
-# second group: MC_Att_L reverse and the whole last-iteration reverse pass of the v1 stack.  The kernels under these wrappers are
-# compiled and bound; their GPU parity tests are gated (FB_EXPERIMENTAL=1) until they have run on a B200.  The orchestration
-# below is validated on the CPU against the pinned specification (tests/test_backward_orchestration.py swaps every wrapper for
-# its torch definition).
+# second group: MC_Att_L reverse and the whole last-iteration reverse pass of the v1 stack.  The orchestration below is also
+# validated on the CPU against the pinned specification (tests/test_backward_orchestration.py swaps every wrapper for its torch
+# definition), so a kernel regression and an orchestration regression show up in different tests.
 # ------------------------------------------------------------------------------------------------------------------------
 def rowdot2(A, Bm):
     _chk(A), _chk(Bm)

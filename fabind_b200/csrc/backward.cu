@@ -226,8 +226,7 @@ __global__ void las_bwd_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
-// ---- second group (MC_Att_L reverse; compiled, orchestration validated on the CPU against autograd with stand-ins, GPU parity
-// tests gated behind FB_EXPERIMENTAL until they have run on a B200) -----------------------------------------------------------
+// ---- second group: MC_Att_L reverse (row attention, interfacial attention, pair path) ----------------------------------------
 
 // out[m] = sum_n A[m,n] B[m,n]
 __global__ void rowdot2_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb, int M, int N,

@@ -174,8 +174,12 @@ def check_att(case, dh, dx, grads, dPB_p, dPB_c, dP0, tol):
     assert rel_err(dP0, case["dP0"]) < tol
     assert rel_err(dPB_p, case["dPB"][:, 0, 0]) < tol and rel_err(dPB_c, case["dPB"][:, 0, 1]) < tol
     assert set("att0." + k for k in grads) == set(G), set("att0." + k for k in grads) ^ set(G)
+    gmax = max(float(t.abs().max()) for t in G.values())
     for k, v in grads.items():
-        assert rel_err(v.reshape(-1), G["att0." + k].reshape(-1)) < tol, k
+        ref = G["att0." + k].reshape(-1)
+        # absolute floor: the gradient of the softmax-shift constant pt_c is exactly zero in real arithmetic (sum of dlogit over a row)
+        err = float((v.reshape(-1) - ref).abs().max())
+        assert err < tol * float(ref.abs().max()) + 1e-2 * tol * gmax, (k, err, float(ref.abs().max()))
 
 
 def att_case(ex, dh_up, dx_up):
