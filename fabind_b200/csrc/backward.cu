@@ -6,6 +6,7 @@
 #include "../../include/fabind_b200.h"
 
 #include "common.cuh"
+#include "layers.h"
 
 namespace fb {
 
@@ -427,6 +428,107 @@ __global__ void __launch_bounds__(RB_WARPS * 32) row_attention_bwd_kernel(
   }
 }
 
+// ---- training-mode forward pieces: the sub-steps whose intermediates the reverse pass needs and the fused inference kernels do
+// not keep (unclamped coordinate steps, per-complex radial norms, attention probabilities).  GPU parity tests gated behind
+// FB_EXPERIMENTAL until they have run on a B200; the forward orchestration over them is validated on the CPU. ------------------
+
+// d[e] = x[row] - x[col], d2[e] = |d|^2
+__global__ void edge_diff_kernel(const float* __restrict__ x, const int* __restrict__ row, const int* __restrict__ col, int E,
+                                 float* __restrict__ d, float* __restrict__ d2) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int i = row[e], j = col[e];
+  const float a = x[3 * i] - x[3 * j], b = x[3 * i + 1] - x[3 * j + 1], c = x[3 * i + 2] - x[3 * j + 2];
+  d[3 * e] = a; d[3 * e + 1] = b; d[3 * e + 2] = c;
+  d2[e] = a * a + b * b + c * c;
+}
+// coord2radial, norm_type per_sample (egnn.py:775-779): S[b] = sum_e d2^2 ; rn = d2 / sqrt(S[b]) ; nrm[b] = sqrt(S[b])
+__global__ void radial_sum_kernel(const float* __restrict__ d2, const int* __restrict__ row, const int* __restrict__ cplx, int E,
+                                  float* __restrict__ S) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) atomicAdd(&S[cplx[row[e]]], d2[e] * d2[e]);
+}
+__global__ void radial_norm_kernel(const float* __restrict__ d2, const int* __restrict__ row, const int* __restrict__ cplx, int E,
+                                   const float* __restrict__ S, int B, float* __restrict__ rn, float* __restrict__ nrm) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < B) nrm[e] = sqrtf(S[e]);
+  if (e < E) rn[e] = d2[e] / sqrtf(S[cplx[row[e]]]);
+}
+// step = sum / max(cnt, 1) (cnt == null: sum) ; x_new = x + clamp(step, +-cmax)   (egnn.py:85-98, :228-233)
+__global__ void coord_apply_kernel(const float* __restrict__ x, const float* __restrict__ sum, const float* __restrict__ cnt, int N,
+                                   float cmax, float* __restrict__ step, float* __restrict__ x_new) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * N) return;
+  const float s = cnt ? sum[i] / fmaxf(cnt[i / 3], 1.0f) : sum[i];
+  step[i] = s;
+  x_new[i] = x[i] + fminf(fmaxf(s, -cmax), cmax);
+}
+// scatter_softmax over destination rows stored CSR (edges of a row contiguous): one warp per row
+__global__ void softmax_seg_fwd_kernel(const float* __restrict__ logit, const int* __restrict__ rowptr, int n_rows,
+                                       float* __restrict__ alpha) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_rows) return;
+  const int lo = rowptr[warp], hi = rowptr[warp + 1];
+  float mx = -INFINITY;
+  for (int e = lo + lane; e < hi; e += 32) mx = fmaxf(mx, logit[e]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int e = lo + lane; e < hi; e += 32) sum += expf(logit[e] - mx);
+  sum = warp_sum(sum);
+  for (int e = lo + lane; e < hi; e += 32) alpha[e] = expf(logit[e] - mx) / sum;
+}
+// LAS step, unclamped part (egnn.py:433-449): acc[j] += step * 4 (|x_i-x_j|^2 - |ref_i-ref_j|^2) (x_i - x_j)
+__global__ void las_acc_kernel(const float* __restrict__ x, const float* __restrict__ xref, const int* __restrict__ a_idx,
+                               const int* __restrict__ b_idx, int E, float step_size, float* __restrict__ acc) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int i = a_idx[e], j = b_idx[e];
+  float d[3], cur = 0.f, ref = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    d[a] = x[3 * i + a] - x[3 * j + a];
+    const float r = xref[3 * i + a] - xref[3 * j + a];
+    cur = fmaf(d[a], d[a], cur);
+    ref = fmaf(r, r, ref);
+  }
+  const float f = 4.0f * (cur - ref) * step_size;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) atomicAdd(&acc[3 * j + a], f * d[a]);
+}
+// InteractionModule outer product operand (model_utils.py:216-220): outer[pair(i,j), :] = pc[i, :] * pc[j, :]; one CTA per protein row
+__global__ void pair_outer_fwd_kernel(const float* __restrict__ pc, int H, const int* __restrict__ c_off, const int* __restrict__ p_off,
+                                      const int* __restrict__ pair_base, const int* __restrict__ node_cplx, int p_begin,
+                                      float* __restrict__ outer) {
+  pdl_entry();
+  const int i = p_begin + blockIdx.x;
+  const int b = node_cplx[i];
+  const int nc1 = c_off[b + 1] - c_off[b];
+  const size_t base = (size_t)pair_base[b] + (size_t)(i - p_off[b]) * nc1;
+  for (int f = threadIdx.x; f < H; f += blockDim.x) {
+    const float pv = pc[(size_t)i * H + f];
+    for (int j = 0; j < nc1; ++j) outer[(base + j) * H + f] = pv * pc[(size_t)(c_off[b] + j) * H + f];
+  }
+}
+// gated pair bias (model_utils.py:96-133): PB[p, blk, h] = raw[p, 8 blk + h] * sigmoid(raw[p, 8 blk + 4 + h])
+__global__ void pair_bias_gate_fwd_kernel(const float* __restrict__ raw, int ld, long long P, int nblk, float* __restrict__ PB) {
+  pdl_entry();
+  const long long total = P * nblk * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(i & 3);
+    const long long pb = i >> 2;
+    const int blk = (int)(pb % nblk);
+    const long long p = pb / nblk;
+    const float* rp = raw + p * ld + blk * 8;
+    PB[i] = rp[h] / (1.0f + expf(-rp[4 + h]));
+  }
+}
+
 static inline int grid_1d(long long n, int block, int cap = 148 * 16) {
   long long g = (n + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -623,6 +725,73 @@ int32_t fb_row_attention_bwd(const int32_t* c_off, const int32_t* p_off, const i
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
+}
+
+int32_t fb_radial_fwd(const float* x, const int32_t* row, const int32_t* col, int32_t E, const int32_t* node_cplx, int32_t B,
+                      float* S_zeroed, float* d, float* d2, float* rn, float* nrm, void* stream) {
+  if (E <= 0) return FB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = ((E > B ? E : B) + 255) / 256;
+  fb_launch(edge_diff_kernel, dim3((E + 255) / 256), dim3(256), 0, st, x, row, col, (int)E, d, d2);
+  fb_launch(radial_sum_kernel, dim3((E + 255) / 256), dim3(256), 0, st, (const float*)d2, row, node_cplx, (int)E, S_zeroed);
+  fb_launch(radial_norm_kernel, dim3(g), dim3(256), 0, st, (const float*)d2, row, node_cplx, (int)E, (const float*)S_zeroed, (int)B, rn, nrm);
+  count_launch(3);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_coord_apply(const float* x, const float* sum, const float* cnt, int32_t N, float cmax, float* step, float* x_new, void* stream) {
+  if (N <= 0) return FB_OK;
+  fb_launch(coord_apply_kernel, dim3((3 * N + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x, sum, cnt, (int)N, cmax, step, x_new);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_softmax_seg_fwd(const float* logit, const int32_t* rowptr, int32_t n_rows, float* alpha, void* stream) {
+  if (n_rows <= 0) return FB_OK;
+  fb_launch(softmax_seg_fwd_kernel, dim3((int)(((long long)n_rows * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, logit, rowptr,
+            (int)n_rows, alpha);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_las_acc(const float* x, const float* xref, const int32_t* a_idx, const int32_t* b_idx, int32_t E, float step_size,
+                   float* acc_zeroed, void* stream) {
+  if (E <= 0) return FB_OK;
+  fb_launch(las_acc_kernel, dim3((E + 255) / 256), dim3(256), 0, (cudaStream_t)stream, x, xref, a_idx, b_idx, (int)E, step_size, acc_zeroed);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_pair_outer_fwd(const float* pc, int32_t H, const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base,
+                          const int32_t* node_cplx, int32_t p_begin, int32_t n_p_rows, float* outer, void* stream) {
+  if (n_p_rows <= 0) return FB_OK;
+  fb_launch(pair_outer_fwd_kernel, dim3(n_p_rows), dim3(128), 0, (cudaStream_t)stream, pc, (int)H, c_off, p_off, pair_base, node_cplx,
+            (int)p_begin, outer);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_pair_bias_gate_fwd(const float* raw, int32_t ld, int64_t P, int32_t nblk, float* PB, void* stream) {
+  if (P <= 0) return FB_OK;
+  if (8 * nblk > ld) return FB_ERR_BAD_ARG;
+  fb_launch(pair_bias_gate_fwd_kernel, dim3(grid_1d(P * nblk * 4, 256)), dim3(256), 0, (cudaStream_t)stream, raw, (int)ld, (long long)P,
+            (int)nblk, PB);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_row_attention_fwd(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t q_is_prot,
+                             int32_t max_q, int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K,
+                             int32_t ldk, const float* V, int32_t ldv, const float* PB, float* O, int32_t ldo, void* stream) {
+  GraphDev g;
+  g.B = B; g.c_off = c_off; g.p_off = p_off; g.pair_base = pair_base;
+  return row_attention(g, q_is_prot, max_q, max_k, Q, ldq, G, ldg, K, ldk, V, ldv, PB, O, ldo, false, (cudaStream_t)stream);
 }
 
 }  // extern "C"

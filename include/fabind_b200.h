@@ -305,6 +305,27 @@ int32_t fb_row_attention_bwd(const int32_t* c_off, const int32_t* p_off, const i
                              int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K, int32_t ldk,
                              const float* V, int32_t ldv, const float* PB, const float* dO, int32_t ldo, float* dQ, int32_t lddq,
                              float* dG, int32_t lddg, float* dK, int32_t lddk, float* dV, int32_t lddv, float* dPB, void* stream);
+/* -- training-mode forward pieces: the sub-steps whose intermediates the reverse pass consumes (the fused inference kernels do not
+ *    keep them).  fabind_b200/backward.py::stack_forward_train_v1 runs the last refinement iteration over these + fb_gemm. -- */
+/* coord2radial with norm_type per_sample (egnn.py:767-787): d [E,3], d2 [E], rn [E] = d2 / nrm[complex], nrm [B]; S_zeroed [B] scratch */
+int32_t fb_radial_fwd(const float* x, const int32_t* row, const int32_t* col, int32_t E, const int32_t* node_cplx, int32_t B,
+                      float* S_zeroed, float* d, float* d2, float* rn, float* nrm, void* stream);
+/* step = sum / max(cnt,1) (cnt == NULL: sum); x_new = x + clamp(step, +-cmax) (egnn.py:85-98, 228-233; LAS step :446-449) */
+int32_t fb_coord_apply(const float* x, const float* sum, const float* cnt, int32_t N, float cmax, float* step, float* x_new, void* stream);
+/* scatter_softmax over destination rows in CSR order (egnn.py:221) */
+int32_t fb_softmax_seg_fwd(const float* logit, const int32_t* rowptr, int32_t n_rows, float* alpha, void* stream);
+/* unclamped LAS step (egnn.py:433-445): acc[j] += step * 4 (|x_i-x_j|^2 - |ref_i-ref_j|^2)(x_i-x_j); acc_zeroed [N,3] */
+int32_t fb_las_acc(const float* x, const float* xref, const int32_t* a_idx, const int32_t* b_idx, int32_t E, float step_size,
+                   float* acc_zeroed, void* stream);
+/* InteractionModule outer-product operand p_i * c_j per complex (model_utils.py:216-220), fp32 rows in pair order */
+int32_t fb_pair_outer_fwd(const float* pc, int32_t H, const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base,
+                          const int32_t* node_cplx, int32_t p_begin, int32_t n_p_rows, float* outer, void* stream);
+/* gated pair bias linear(pair)*sigmoid(linear_g(pair)) (model_utils.py:96-133): raw [P,ld] -> PB [P,nblk,4] */
+int32_t fb_pair_bias_gate_fwd(const float* raw, int32_t ld, int64_t P, int32_t nblk, float* PB, void* stream);
+/* the inference row-attention kernel (layers.cu::row_attention_kernel, fp32 output) on caller-supplied projections; PB = [P,4] */
+int32_t fb_row_attention_fwd(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t q_is_prot,
+                             int32_t max_q, int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K,
+                             int32_t ldk, const float* V, int32_t ldv, const float* PB, float* O, int32_t ldo, void* stream);
 
 #ifdef __cplusplus
 }
