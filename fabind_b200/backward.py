@@ -438,3 +438,236 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
     vec_add_(dHin[Nc:], _linear_bwd(g0, "il_p_w", "il_p_b", weights[""]["il_p_w_t"], top["Hin"][Nc:], dpc[Nc:]))
     take("", g0)
     return grads, dHin
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Training-mode forward of the last refinement iteration (v1 layout): the same arithmetic as the inference launch sequence
+# (csrc/forward.cu), un-fused where the reverse pass needs an intermediate, every saved tensor in the form gcl_backward /
+# att_backward / las_bwd consume.  fp32; GEMMs through fb_gemm (SIMT parity kernel), row attention through the inference kernel.
+# The kernels under the wrappers of this section have NOT run on a GPU yet (their parity tests are gated, FB_EXPERIMENTAL=1);
+# the orchestration is validated on the CPU against the specification's forward (tests/test_backward_orchestration.py).
+# ------------------------------------------------------------------------------------------------------------------------
+def linear(A, W, bias=None, act=ACT_NONE, res=None):
+    """act(A W^T + bias) + res  (fp32, fb_gemm)"""
+    _chk(A), _chk(W)
+    M, K = A.shape
+    N = W.shape[0]
+    g = _lib.GemmParams()
+    g.A, g.lda, g.K1 = A.data_ptr(), K, K
+    g.W, g.bias, g.act = W.data_ptr(), (_chk(bias).data_ptr() if bias is not None else None), act
+    g.M, g.N, g.bf16_mode, g.force_simt = M, N, 0, 0
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    g.C, g.ldc = out.data_ptr(), N
+    if res is not None:
+        g.res, g.ldres = _chk(res).data_ptr(), res.shape[1]
+    _lib.check(_lib.lib().fb_gemm(C.byref(g), _st(A)), "fb_gemm")
+    return out
+
+
+def radial_fwd(x, row, col, node_cplx, B):
+    """-> d [E,3], d2 [E], rn [E], nrm [B]"""
+    _chk(x), _chk(row, torch.int32), _chk(col, torch.int32), _chk(node_cplx, torch.int32)
+    E, dev = row.numel(), x.device
+    S = torch.zeros(B, dtype=torch.float32, device=dev)
+    d, d2, rn, nrm = (torch.empty(E, 3, dtype=torch.float32, device=dev), torch.empty(E, dtype=torch.float32, device=dev),
+                      torch.empty(E, dtype=torch.float32, device=dev), torch.empty(B, dtype=torch.float32, device=dev))
+    _lib.check(_lib.lib().fb_radial_fwd(x.data_ptr(), row.data_ptr(), col.data_ptr(), E, node_cplx.data_ptr(), B, S.data_ptr(), d.data_ptr(),
+                                        d2.data_ptr(), rn.data_ptr(), nrm.data_ptr(), _st(x)), "fb_radial_fwd")
+    return d, d2, rn, nrm
+
+
+def coord_apply(x, ssum, cnt, cmax):
+    """-> (unclamped step, x + clamp(step))"""
+    _chk(x), _chk(ssum)
+    step, x_new = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.lib().fb_coord_apply(x.data_ptr(), ssum.data_ptr(), _chk(cnt).data_ptr() if cnt is not None else None, x.shape[0],
+                                         float(cmax), step.data_ptr(), x_new.data_ptr(), _st(x)), "fb_coord_apply")
+    return step, x_new
+
+
+def softmax_seg_fwd(logit, rowptr, n_rows):
+    _chk(logit), _chk(rowptr, torch.int32)
+    alpha = torch.empty_like(logit)
+    _lib.check(_lib.lib().fb_softmax_seg_fwd(logit.data_ptr(), rowptr.data_ptr(), n_rows, alpha.data_ptr(), _st(logit)), "fb_softmax_seg_fwd")
+    return alpha
+
+
+def las_acc(x, xref, a_idx, b_idx, step_size):
+    _chk(x), _chk(xref), _chk(a_idx, torch.int32), _chk(b_idx, torch.int32)
+    acc = torch.zeros_like(x)
+    _lib.check(_lib.lib().fb_las_acc(x.data_ptr(), xref.data_ptr(), a_idx.data_ptr(), b_idx.data_ptr(), a_idx.numel(), float(step_size),
+                                     acc.data_ptr(), _st(x)), "fb_las_acc")
+    return acc
+
+
+def pair_outer_fwd(pc, geo, n_pairs):
+    _chk(pc)
+    N, H = pc.shape
+    outer = torch.empty(n_pairs, H, dtype=torch.float32, device=pc.device)
+    _lib.check(_lib.lib().fb_pair_outer_fwd(pc.data_ptr(), H, geo["c_off"].data_ptr(), geo["p_off"].data_ptr(), geo["pair_base"].data_ptr(),
+                                            geo["node_cplx"].data_ptr(), geo["Nc"], N - geo["Nc"], outer.data_ptr(), _st(pc)),
+               "fb_pair_outer_fwd")
+    return outer
+
+
+def pair_bias_gate_fwd(raw, nblk):
+    _chk(raw)
+    PB = torch.empty(raw.shape[0], nblk, 4, dtype=torch.float32, device=raw.device)
+    _lib.check(_lib.lib().fb_pair_bias_gate_fwd(raw.data_ptr(), raw.shape[1], raw.shape[0], nblk, PB.data_ptr(), _st(raw)),
+               "fb_pair_bias_gate_fwd")
+    return PB
+
+
+def row_attention_fwd(geo, q_is_prot, Q, G, K, V, PB, n_q_rows):
+    """(tensor, first column) operands as in row_attention_bwd -> O [n_q_rows, 128]"""
+    Nc = geo["Nc"]
+
+    def ptr(tc, prot_side):
+        t, c0 = tc
+        _chk(t)
+        return t.data_ptr() + 4 * c0 - (4 * Nc * t.shape[1] if prot_side else 0), t.shape[1]
+    qs = bool(q_is_prot)
+    (q, ldq), (g, ldg), (k, ldk), (v, ldv) = ptr(Q, qs), ptr(G, qs), ptr(K, not qs), ptr(V, not qs)
+    _chk(PB)
+    O = torch.empty(n_q_rows, HD, dtype=torch.float32, device=PB.device)
+    o = O.data_ptr() - (4 * Nc * HD if qs else 0)
+    max_q, max_k = (geo["max_p"], geo["max_c"]) if qs else (geo["max_c"], geo["max_p"])
+    _lib.check(_lib.lib().fb_row_attention_fwd(geo["c_off"].data_ptr(), geo["p_off"].data_ptr(), geo["pair_base"].data_ptr(), geo["B"],
+                                               int(qs), max_q, max_k, q, ldq, g, ldg, k, ldk, v, ldv, PB.data_ptr(), o, HD, _st(PB)),
+               "fb_row_attention_fwd")
+    return O
+
+
+def _ones(n, dev):
+    return torch.ones(n, dtype=torch.float32, device=dev)
+
+
+def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax):
+    """MC_E_GCL forward (egnn.py:68-144; inference twin: forward.cu::run_gcl) keeping what gcl_backward consumes"""
+    N, H = h.shape
+    E, dev = row.numel(), h.device
+    d, d2, rn, nrm = radial_fwd(x, row, col, node_cplx, B)
+    Pn = linear(h, w["e1_rc"])
+    Z1 = gather_rows(Pn, row, 0, H)
+    gather_add_rows(Pn, col, Z1, col0=H)
+    rank1_add(Z1, rn, w["e1_rad"])
+    rank1_add(Z1, _ones(E, dev), w["e1_b"])
+    Z2 = linear(act_fwd(Z1, ACT_SILU), w["e2_w"], w["e2_b"])
+    M = act_fwd(Z2, ACT_SILU)
+    Z3 = linear(M, w["c1_w"], w["c1_b"])
+    s = rowdot(act_fwd(Z3, ACT_SILU), w["c2_w"])
+    ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+    scatter_add_rows(scale_rows(d.clone(), s), row, ssum)
+    deg = torch.zeros(N, 1, dtype=torch.float32, device=dev)
+    scatter_add_rows(_ones(E, dev).view(E, 1), row, deg)
+    deg = deg.view(N)
+    step, x_new = coord_apply(x, ssum, deg, cmax)
+    agg = torch.zeros(N, H, dtype=torch.float32, device=dev)
+    scatter_add_rows(M, row, agg)
+    cat = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
+    cat[:, :H].copy_(h)
+    cat[:, H:].copy_(agg)
+    Z4 = linear(cat, w["n1_w"], w["n1_b"])
+    h_new = linear(act_fwd(Z4, ACT_SILU), w["n2_w"], w["n2_b"], res=h)
+    return h_new, x_new, dict(h=h, x=x, rn=rn, nrm=nrm, Z1=Z1, Z2=Z2, Z3=Z3, s=s, deg=deg, step=step, agg=agg, Z4=Z4)
+
+
+def interface_indices(row, col, geo):
+    """pair row of every interface edge and the lig->prot subset (index bookkeeping with integer tensor ops; no float arithmetic)"""
+    Nc = geo["Nc"]
+    r, c = row.long(), col.long()
+    cplx = geo["node_cplx"].long()
+    eb = cplx[r]
+    is_c = r < Nc
+    ci, pi = torch.where(is_c, r, c), torch.where(is_c, c, r)
+    c_off, p_off, pair_base = geo["c_off"].long(), geo["p_off"].long(), geo["pair_base"].long()
+    nc1 = c_off[1:] - c_off[:-1]
+    pair = pair_base[eb] + (pi - p_off[eb]) * nc1[eb] + (ci - c_off[eb])
+    u = is_c.nonzero().squeeze(1)
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    n_rows = cplx.numel()
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=row.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(r, minlength=n_rows), 0)
+    return dict(pair=i32(pair), u_pair=i32(pair[u]), u_pi=i32(pi[u]), u_ci=i32(ci[u]), rowptr=i32(rowptr))
+
+
+def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax):
+    """MC_Att_L forward (egnn.py:186-333, cross_att.py:24-54; inference twin: forward.cu::run_att) keeping what att_backward consumes.
+    row / col must be sorted by row (the library's interface graph is); idx = interface_indices(row, col, geo)."""
+    N, H = h.shape
+    Nc, dev, E = geo["Nc"], h.device, row.numel()
+    hc0, hp0 = h[:Nc], h[Nc:]
+    CAc = linear(hc0, w["ca_c_w"], w["ca_c_b"])
+    CAp = linear(hp0, w["ca_p_w"], w["ca_p_b"])
+    Op = row_attention_fwd(geo, 1, (CAp, 0), (CAp, HD), (CAc, 0), (CAc, HD), PB_p, N - Nc)
+    hp1 = linear(Op, w["o_p_w"], w["o_p_b"], res=hp0)
+    CAp2 = linear(hp1, w["ca_p2_w"])
+    Oc = row_attention_fwd(geo, 0, (CAc, 2 * HD), (CAc, 3 * HD), (CAp2, 0), (CAp2, HD), PB_c, Nc)
+    hc1 = linear(Oc, w["o_c_w"], w["o_c_b"], res=hc0)
+    Ttp = linear(hp1, w["tp1_w"], w["tp1_b"], act=ACT_RELU)
+    Ttc = linear(hc1, w["tc1_w"], w["tc1_b"], act=ACT_RELU)
+    h2 = torch.empty(N, H, dtype=torch.float32, device=dev)
+    h2[:Nc].copy_(linear(Ttc, w["tc2_w"], w["tc2_b"], res=hc1))
+    h2[Nc:].copy_(linear(Ttp, w["tp2_w"], w["tp2_b"], res=hp1))
+    QK = linear(h2, w["qk_w"], w["qk_b"])
+    pc32 = torch.empty(N, 32, dtype=torch.float32, device=dev)
+    pc32[Nc:].copy_(gather_rows(QK, torch.arange(Nc, N, dtype=torch.int32, device=dev), 2 * H, 32))
+    pc32[:Nc].copy_(gather_rows(QK, torch.arange(0, Nc, dtype=torch.int32, device=dev), 2 * H + 32, 32))
+    U = idx["u_pair"].numel()
+    zcat = torch.zeros(U, H + 64, dtype=torch.float32, device=dev)
+    zcat[:, :H].copy_(gather_rows(P0, idx["u_pair"]))
+    zcat[:, H:H + 32].copy_(vec_mul(gather_rows(pc32, idx["u_pi"]), gather_rows(pc32, idx["u_ci"])))
+    Zp = linear(zcat, w["pt1_w"], w["pt1_b"])
+    pbu = rowdot(act_fwd(Zp, ACT_RELU), w["pt2v"]).view(U, 1)
+    rank1_add(pbu, _ones(U, dev), w["pt_c"])
+    pb_dense = torch.zeros(P0.shape[0], 1, dtype=torch.float32, device=dev)
+    scatter_add_rows(pbu, idx["u_pair"], pb_dense)                      # unique pair rows: the sum is an assignment
+    d, d2, rn, nrm = radial_fwd(x, row, col, geo["node_cplx"], geo["B"])
+    logit = rowdot2(gather_rows(QK, row, 0, H), rank1_add(gather_rows(QK, col, H, H), rn, w["k_r"]))
+    vec_add_(logit, gather_rows(pb_dense, idx["pair"]).view(E))
+    alpha = softmax_seg_fwd(logit, idx["rowptr"], N)
+    ve = scale_rows(rank1_add(gather_rows(QK, col, 2 * H + 128, H), rn, w["v_r"]), alpha)
+    h3 = h2.clone()
+    scatter_add_rows(ve, row, h3)
+    zc = rank1_add(gather_rows(QK, col, 3 * H + 128, H), rn, w["ac_u"])
+    rank1_add(zc, _ones(E, dev), w["ac1_b"])
+    se = rowdot(act_fwd(zc, ACT_SILU), w["ac2_w"])
+    ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+    scatter_add_rows(scale_rows(d.clone(), vec_mul(alpha, se)), row, ssum)
+    step, x_new = coord_apply(x, ssum, None, cmax)
+    sv = dict(h_in=h, x=x, CAc=CAc, CAp=CAp, CAp2=CAp2, PB_p=PB_p, PB_c=PB_c, Op=Op, Oc=Oc, hp1=hp1, hc1=hc1, Ttp=Ttp, Ttc=Ttc, h2=h2, QK=QK,
+              pc32=pc32, pair=idx["pair"], u_pair=idx["u_pair"], u_pi=idx["u_pi"], u_ci=idx["u_ci"], zcat=zcat, Zp=Zp, rn=rn, nrm=nrm,
+              alpha=alpha, se=se, zc=zc, step=step)
+    return h3, x_new, sv
+
+
+def stack_forward_train_v1(weights, Hin, x_state, moves, geo, edges, consts, n_layers):
+    """Last refinement iteration of the v1 stack in training mode (internal node order): returns (X_out [N,3], H_out [N,H], tape, top)
+    in the form stack_backward_v1 consumes.  x_state: coordinates after the earlier (no_grad) iterations; moves: bool [N]."""
+    N, H = Hin.shape
+    Nc, dev = geo["Nc"], Hin.device
+    wt = weights[""]
+    pc = torch.empty(N, H, dtype=torch.float32, device=dev)
+    pc[:Nc].copy_(linear(Hin[:Nc], wt["il_c_w"], wt["il_c_b"]))
+    pc[Nc:].copy_(linear(Hin[Nc:], wt["il_p_w"], wt["il_p_b"]))
+    outer = pair_outer_fwd(pc, geo, consts["n_pairs"])
+    P0 = linear(outer, wt["il_o_w"], wt["il_o_b"])
+    raw_full = linear(P0, wt["pb_w"], wt["pb_b"])
+    PB = pair_bias_gate_fwd(raw_full, 2 * n_layers)
+    h = linear(Hin, wt["in_w"], wt["in_b"])
+    x = x_state
+    idx = interface_indices(edges["int_row"], edges["int_col"], geo)
+    tape = []
+    for l in range(n_layers):
+        h, x, s_gcl = gcl_forward_train(weights[f"gcl{l}."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"])
+        h, x, s_att = att_forward_train(weights[f"att{l}."], h, x, geo, edges["int_row"], edges["int_col"], idx, P0,
+                                        PB[:, 2 * l].contiguous(), PB[:, 2 * l + 1].contiguous(), consts["cmax"])
+        acc = las_acc(x, consts["xl"], edges["las_a"], edges["las_b"], consts["las_step"])
+        x_in = x
+        _, x = coord_apply(x_in, acc, None, consts["lcl"])
+        tape.append((s_gcl, s_att, dict(x=x_in, acc=acc)))
+    h_last, x, s_out = gcl_forward_train(weights["out."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"])
+    H_out = linear(h_last, wt["out_w"], wt["out_b"])
+    X_out = torch.where(moves[:, None], x, x_state)
+    top = dict(Hin=Hin, pc=pc, outer=outer, P0=P0, raw_full=raw_full, h_last=h_last, out_saved=s_out)
+    return X_out, H_out, tape, top

@@ -386,7 +386,7 @@ def forward_backward_v1(sd, cfg, batch, gX, gH, arena=None, export=None):
         if export is not None:
             export.update(W=W, geo=geo, ctx=ctx, inter=inter, las=las, tape=tape, s_out=s_out, P0=P0, PB=PB, cmax=cmax, lcl=lcl,
                           xl=xl, N=N, B=B, Nc=Nc, Hin=Hin, pc=pc, outer=outer, raw_full=raw_full, h_last=h_last, permt=permt,
-                          moves=moves)
+                          moves=moves, x_state=x_state, x_out=x_out, h_final=h_final)
         # ---- reverse pass
         G = Grads()
         dx = gX[permt, 0] * moves[:, None]

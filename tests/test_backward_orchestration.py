@@ -112,7 +112,10 @@ def _install_standins(monkeypatch, bw):
         monkeypatch.setattr(bw, k, v)
 
 
-def _weights(W, pre, names):
+def _weights(W, pre, names=None):
+    """every arena slot of a prefix (names=None) or the named ones, + `_t` transposes of the matrices"""
+    if names is None:
+        names = [n[len(pre):] for n in W.s if n.startswith(pre) and "." not in n[len(pre):] and W.s[n][0] * W.s[n][1] > 0]
     w = {}
     for n in names:
         t = W.m(pre + n).clone()
@@ -254,11 +257,11 @@ def stack_case(path=None, seed=7, problem=None):
     geo_dev = dict(Nc=Nc, B=B, c_off=i32(torch.from_numpy(geo["c_off"].astype(np.int64))), p_off=i32(torch.from_numpy(geo["p_off"].astype(np.int64))),
                    pair_base=i32(torch.from_numpy(geo["pair_base"].astype(np.int64))), node_cplx=i32(geo["cplx"]),
                    max_c=int(np.diff(geo["c_off"]).max()), max_p=int(np.diff(geo["p_off"]).max()))
-    weights = {"": _weights(W, "", TOP_W), "out.": _weights(W, "out.", GCL_W)}
+    weights = {"": _weights(W, ""), "out.": _weights(W, "out.")}
     tape = []
     for l in range(L):
-        weights[f"gcl{l}."] = _weights(W, f"gcl{l}.", GCL_W)
-        weights[f"att{l}."] = _weights(W, f"att{l}.", ATT_W)
+        weights[f"gcl{l}."] = _weights(W, f"gcl{l}.")
+        weights[f"att{l}."] = _weights(W, f"att{l}.")
         s1, s2, s3 = ex["tape"][l]
         tape.append((_gcl_saved(s1, H), _att_saved(s2, ex["PB"], l), dict(x=s3["x"], acc=s3["acc"])))
     top = dict(Hin=ex["Hin"], pc=ex["pc"], outer=ex["outer"], P0=ex["P0"], raw_full=ex["raw_full"], h_last=ex["h_last"],
@@ -268,8 +271,9 @@ def stack_case(path=None, seed=7, problem=None):
     consts = dict(cmax=ex["cmax"], lcl=ex["lcl"], las_step=cfg.geometry_reg_step_size, xl=ex["xl"])
     permt = ex["permt"]
     dH_out, dX_out = gH[permt].contiguous(), (gX[permt, 0] * ex["moves"][:, None]).contiguous()
+    consts["n_pairs"] = int(ex["P0"].shape[0])
     return dict(weights=weights, tape=tape, top=top, geo=geo_dev, edges=edges, consts=consts, dH_out=dH_out, dX_out=dX_out, W=W,
-                garena=garena, gHin=gHin[permt])
+                garena=garena, gHin=gHin[permt], x_state=ex["x_state"], moves=ex["moves"], x_out=ex["x_out"], h_final=ex["h_final"], L=L)
 
 
 def check_stack(case, grads, dHin, tol):
@@ -290,32 +294,120 @@ def check_stack(case, grads, dHin, tol):
     assert rel_err(dHin, case["gHin"]) < tol
 
 
+def _gate_bwd_standin(raw, dPB):
+    P, nblk = dPB.shape[0], dPB.shape[1]
+    r5 = raw[:, :8 * nblk].reshape(P, nblk, 2, 4)
+    sg = torch.sigmoid(r5[:, :, 1])
+    out = torch.zeros_like(raw)
+    out[:, :8 * nblk] = torch.stack([dPB * sg, dPB * r5[:, :, 0] * sg * (1 - sg)], 2).reshape(P, -1)
+    return out
+
+
+def _outer_bwd_standin(douter, pc, geo):
+    dpc = torch.zeros_like(pc)
+    for b in range(geo["B"]):
+        c0, c1, p0, p1 = int(geo["c_off"][b]), int(geo["c_off"][b + 1]), int(geo["p_off"][b]), int(geo["p_off"][b + 1])
+        t = douter[int(geo["pair_base"][b]):int(geo["pair_base"][b + 1])].view(p1 - p0, c1 - c0, -1)
+        dpc[p0:p1] += (t * pc[None, c0:c1]).sum(1)
+        dpc[c0:c1] += (t * pc[p0:p1, None]).sum(0)
+    return dpc
+
+
 def test_stack_reverse_pass_matches_specification(monkeypatch):
     """the whole last-iteration reverse pass as fabind_b200.backward orchestrates it == the specification's arena gradient"""
     from fabind_b200 import backward as bw
     _install_standins(monkeypatch, bw)
 
-    def gate(raw, dPB):
-        P, nblk = dPB.shape[0], dPB.shape[1]
-        r5 = raw[:, :8 * nblk].reshape(P, nblk, 2, 4)
-        sg = torch.sigmoid(r5[:, :, 1])
-        out = torch.zeros_like(raw)
-        out[:, :8 * nblk] = torch.stack([dPB * sg, dPB * r5[:, :, 0] * sg * (1 - sg)], 2).reshape(P, -1)
-        return out
-
-    def outer_bwd(douter, pc, geo):
-        dpc = torch.zeros_like(pc)
-        for b in range(geo["B"]):
-            c0, c1, p0, p1 = int(geo["c_off"][b]), int(geo["c_off"][b + 1]), int(geo["p_off"][b]), int(geo["p_off"][b + 1])
-            t = douter[int(geo["pair_base"][b]):int(geo["pair_base"][b + 1])].view(p1 - p0, c1 - c0, -1)
-            dpc[p0:p1] += (t * pc[None, c0:c1]).sum(1)
-            dpc[c0:c1] += (t * pc[p0:p1, None]).sum(0)
-        return dpc
-    monkeypatch.setattr(bw, "pair_bias_gate_bwd", gate)
-    monkeypatch.setattr(bw, "pair_outer_bwd", outer_bwd)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
     cases = [stack_case(path) for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))]
     cases.append(stack_case(problem=two_layer_problem()))      # two layers: pair-bias blocks and pair_embed0 gradients accumulate
     for case in cases:
         grads, dHin = bw.stack_backward_v1(case["weights"], case["tape"], case["top"], case["geo"], case["edges"], case["consts"],
                                            case["dH_out"], case["dX_out"])
+        check_stack(case, grads, dHin, 1e-4)
+
+
+def _install_forward_standins(monkeypatch, bw):
+    L = lambda t: t.long()
+
+    def linear(A, W, bias=None, act=0, res=None):
+        y = _actf(F.linear(A, W, bias), act)
+        return y if res is None else y + res
+
+    def radial_fwd(x, row, col, cplx, B):
+        d = x[L(row)] - x[L(col)]
+        d2 = (d * d).sum(1)
+        nrm = torch.zeros(B).index_add_(0, L(cplx)[L(row)], d2 * d2).sqrt()
+        return d, d2, d2 / nrm[L(cplx)[L(row)]], nrm
+
+    def coord_apply(x, ssum, cnt, cmax):
+        step = ssum / cnt.clamp(min=1)[:, None] if cnt is not None else ssum.clone()
+        return step, x + step.clamp(-cmax, cmax)
+
+    def softmax_seg_fwd(logit, rowptr, n_rows):
+        alpha = torch.empty_like(logit)
+        for r in range(n_rows):
+            lo, hi = int(rowptr[r]), int(rowptr[r + 1])
+            if hi > lo:
+                alpha[lo:hi] = torch.softmax(logit[lo:hi], 0)
+        return alpha
+
+    def las_acc(x, xref, a, b, step_size):
+        d = x[L(a)] - x[L(b)]
+        diff = (d * d).sum(1) - ((xref[L(a)] - xref[L(b)]) ** 2).sum(1)
+        return torch.zeros_like(x).index_add_(0, L(b), 4 * diff[:, None] * d * step_size)
+
+    def pair_outer_fwd(pc, geo, n_pairs):
+        H = pc.shape[1]
+        return torch.cat([(pc[int(geo["p_off"][b]):int(geo["p_off"][b + 1]), None, :] * pc[None, int(geo["c_off"][b]):int(geo["c_off"][b + 1]), :]
+                           ).reshape(-1, H) for b in range(geo["B"])])
+
+    def gate_fwd(raw, nblk):
+        r5 = raw[:, :8 * nblk].reshape(raw.shape[0], nblk, 2, 4)
+        return (r5[:, :, 0] * torch.sigmoid(r5[:, :, 1])).contiguous()
+
+    def rowatt_fwd(geo, q_is_prot, Q, G, K, V, PB, n_q_rows):
+        Nc, O = geo["Nc"], torch.zeros(n_q_rows, 128)
+        sl = lambda tc: tc[0][:, tc[1]:tc[1] + 128]
+        for b in range(geo["B"]):
+            c0, c1, p0, p1 = int(geo["c_off"][b]), int(geo["c_off"][b + 1]), int(geo["p_off"][b]) - Nc, int(geo["p_off"][b + 1]) - Nc
+            bias = PB[int(geo["pair_base"][b]):int(geo["pair_base"][b + 1])].view(p1 - p0, c1 - c0, 4)
+            qs, ks = (slice(p0, p1), slice(c0, c1)) if q_is_prot else (slice(c0, c1), slice(p0, p1))
+            O[qs] = spec.rowatt_fwd(sl(Q)[qs], sl(G)[qs], sl(K)[ks], sl(V)[ks], bias if q_is_prot else bias.transpose(0, 1))[0]
+        return O
+    for k, v in dict(linear=linear, radial_fwd=radial_fwd, coord_apply=coord_apply, softmax_seg_fwd=softmax_seg_fwd, las_acc=las_acc,
+                     pair_outer_fwd=pair_outer_fwd, pair_bias_gate_fwd=gate_fwd, row_attention_fwd=rowatt_fwd).items():
+        monkeypatch.setattr(bw, k, v)
+
+
+def check_forward(case, X_out, H_out, tape, top, tol):
+    """the training-mode forward reproduces the specification's outputs and every tensor the reverse pass consumes"""
+    assert rel_err(X_out, case["x_out"]) < tol and rel_err(H_out, case["h_final"]) < tol
+    for k in ("pc", "outer", "P0", "raw_full", "h_last"):
+        assert rel_err(top[k], case["top"][k]) < tol, k
+    for mine, ref in zip(tape + [(top["out_saved"],)], case["tape"] + [(case["top"]["out_saved"],)]):
+        for sm, sr in zip(mine, ref):
+            assert set(sm) == set(sr), set(sm) ^ set(sr)
+            for k in sr:
+                if sr[k].dtype == torch.int32:
+                    assert torch.equal(sm[k].cpu(), sr[k]), k
+                else:
+                    assert rel_err(sm[k], sr[k]) < tol, (k, rel_err(sm[k], sr[k]))
+
+
+def test_training_forward_and_reverse_close_the_loop(monkeypatch):
+    """stack_forward_train_v1 -> stack_backward_v1 as orchestrated for the GPU, on torch stand-ins: outputs, every saved tensor and
+    the final arena gradient equal the specification's (which is pinned to the unmodified reference)"""
+    from fabind_b200 import backward as bw
+    _install_standins(monkeypatch, bw)
+    _install_forward_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
+    cases = [stack_case(path) for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))] + [stack_case(problem=two_layer_problem())]
+    for case in cases:
+        X_out, H_out, tape, top = bw.stack_forward_train_v1(case["weights"], case["top"]["Hin"], case["x_state"], case["moves"], case["geo"],
+                                                            case["edges"], case["consts"], case["L"])
+        check_forward(case, X_out, H_out, tape, top, 1e-5)
+        grads, dHin = bw.stack_backward_v1(case["weights"], tape, top, case["geo"], case["edges"], case["consts"], case["dH_out"], case["dX_out"])
         check_stack(case, grads, dHin, 1e-4)

@@ -1,0 +1,86 @@
+"""Training-mode forward of the last refinement iteration (fabind_b200/backward.py::stack_forward_train_v1) and the closed loop
+forward -> reverse on the REAL kernels, against the pinned specification.
+
+GATED (FB_EXPERIMENTAL=1): the forward-side kernels of csrc/backward.cu (radial with norms, coordinate apply, segment softmax,
+unclamped LAS step, pair outer product, gated pair bias, the row-attention forward entry) were written after this round's GPU
+budget was spent; they compile and their orchestration is validated on the CPU (tests/test_backward_orchestration.py), but they
+have not run on a B200 yet -- a faulting kernel would poison the CUDA context of the whole test process, so the gate stays until
+they are green.  (The reverse-pass kernels went through exactly this route and passed on their first GPU run.)"""
+import glob
+import os
+
+import pytest
+import torch
+
+from helpers import GOLDEN_DIR, rel_err
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("FB_EXPERIMENTAL") != "1", reason="forward-side training kernels not yet validated on a GPU (FB_EXPERIMENTAL=1)")]
+TOL = 1e-4
+
+
+def _cuda(o):
+    if torch.is_tensor(o):
+        return o.cuda().contiguous()
+    if isinstance(o, dict):
+        return {k: _cuda(v) for k, v in o.items()}
+    return o
+
+
+def _cpu(o):
+    if torch.is_tensor(o):
+        return o.cpu()
+    if isinstance(o, dict):
+        return {k: _cpu(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return type(o)(_cpu(v) for v in o)
+    return o
+
+
+def test_forward_pieces_match_torch():
+    from fabind_b200 import backward as bw
+    g = torch.Generator().manual_seed(5)
+    N, E, B = 200, 3000, 4
+    x = torch.randn(N, 3, generator=g)
+    cplx = torch.sort(torch.randint(0, B, (N,), generator=g)).values
+    row = torch.sort(torch.randint(0, N, (E,), generator=g)).values
+    col = torch.randint(0, N, (E,), generator=g)
+    d = x[row] - x[col]
+    d2 = (d * d).sum(1)
+    nrm = torch.zeros(B).index_add_(0, cplx[row], d2 * d2).sqrt()
+    gd, gd2, grn, gnrm = bw.radial_fwd(x.cuda(), row.int().cuda(), col.int().cuda(), cplx.int().cuda(), B)
+    assert rel_err(gd, d) < 1e-6 and rel_err(gd2, d2) < 1e-6 and rel_err(gnrm, nrm) < 1e-5 and rel_err(grn, d2 / nrm[cplx[row]]) < 1e-5
+    ssum, cnt = torch.randn(N, 3, generator=g) * 3, torch.randint(0, 5, (N,), generator=g).float()
+    st, xn = bw.coord_apply(x.cuda(), ssum.cuda(), cnt.cuda(), 1.0)
+    ref = ssum / cnt.clamp(min=1)[:, None]
+    assert rel_err(st, ref) < 1e-6 and rel_err(xn, x + ref.clamp(-1, 1)) < 1e-6
+    logit = torch.randn(E, generator=g) * 3
+    rowptr = torch.zeros(N + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(row, minlength=N), 0)
+    mx = torch.full((N,), float("-inf")).scatter_reduce(0, row, logit, reduce="amax")
+    e = (logit - mx[row]).exp()
+    assert rel_err(bw.softmax_seg_fwd(logit.cuda(), rowptr.int().cuda(), N), e / torch.zeros(N).index_add_(0, row, e)[row]) < 1e-5
+    xref = x + 0.3 * torch.randn(N, 3, generator=g)
+    a, b = torch.randint(0, N, (500,), generator=g), torch.randint(0, N, (500,), generator=g)
+    dd = x[a] - x[b]
+    diff = (dd * dd).sum(1) - ((xref[a] - xref[b]) ** 2).sum(1)
+    assert rel_err(bw.las_acc(x.cuda(), xref.cuda(), a.int().cuda(), b.int().cuda(), 0.02),
+                   torch.zeros_like(x).index_add_(0, b, 4 * diff[:, None] * dd * 0.02)) < 1e-5
+    raw = torch.randn(1000, 128, generator=g)
+    r5 = raw[:, :64].reshape(1000, 8, 2, 4)
+    assert rel_err(bw.pair_bias_gate_fwd(raw.cuda(), 8), r5[:, :, 0] * torch.sigmoid(r5[:, :, 1])) < 1e-5
+
+
+def test_training_forward_and_reverse_on_the_real_kernels():
+    from fabind_b200 import backward as bw
+    from test_backward_orchestration import stack_case, check_forward, check_stack, two_layer_problem
+    cases = [stack_case(p) for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))] + [stack_case(problem=two_layer_problem())]
+    for case in cases:
+        w, geo, edges, consts = _cuda(case["weights"]), _cuda(case["geo"]), _cuda(case["edges"]), _cuda(case["consts"])
+        X_out, H_out, tape, top = bw.stack_forward_train_v1(w, case["top"]["Hin"].cuda(), case["x_state"].cuda(), case["moves"].cuda(), geo,
+                                                            edges, consts, case["L"])
+        torch.cuda.synchronize()
+        check_forward(case, X_out.cpu(), H_out.cpu(), _cpu(tape), _cpu(top), TOL)
+        grads, dHin = bw.stack_backward_v1(w, tape, top, geo, edges, consts, case["dH_out"].cuda(), case["dX_out"].cuda())
+        torch.cuda.synchronize()
+        check_stack(case, _cpu(grads), dHin.cpu(), TOL)
