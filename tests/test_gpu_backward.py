@@ -67,8 +67,7 @@ def gcl_problem(H, seed, device):
 
 
 def test_gcl_reference_exercises_the_clamp():
-    """(runs anywhere a GPU test runs; the CPU twin of this check is in test_formulation_cpu.py) the test problem has clamped and
-    unclamped coordinate steps, so the reverse pass of the clamp is exercised"""
+    """the test problem has clamped and unclamped coordinate steps, so the reverse pass of the clamp is exercised"""
     p, h, x, row, col, cplx, B, gh, gx = gcl_problem(64, 5, "cpu")
     _, _, sv = gcl_reference(p, h, x, row, col, cplx, B, 0.5)
     frac = float((sv["step"].abs() > 0.5).float().mean())
