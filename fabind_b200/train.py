@@ -1,0 +1,135 @@
+"""Assembly of one training step through the v1 docking stack (BASELINE config 5: forward + backward + gradient all-reduce).
+
+Reference semantics (att_model.py:210-246, refine='refine_coord'): the first `n_iter - 1` refinement iterations run under no_grad
+and only move the ligand; the last one is differentiated.  So a step is
+  1. iterations 0 .. n_iter-2: the inference path (`EfficientMCAttModel.forward`, one fb_model_forward call);
+  2. edge lists of the last iteration from the graph builder (`ComplexGraph.construct_edges`, bit-exact), mapped to the internal
+     node order;
+  3. `backward.stack_forward_train_v1` (training-mode forward of the last iteration, keeps what the reverse pass needs);
+  4. the caller's loss on (X, H) -> gradients of the outputs (the losses of main_fabind.py:380-401 live outside the path);
+  5. `backward.stack_backward_v1` -> gradient of the weight arena -> `weights.arena_grads_to_state_dict` -> parameter `.grad`s;
+  6. `shard.allreduce_gradients` over the ranks (one flat NCCL collective).
+`n_iter` is used as configured (the reference draws randint(1, n_iter) per step when --random-n-iter is set, att_model.py:210-211);
+dropout is not applied (the reference's 0.1 dropout of the v1 stack is the caller's choice to disable for parity).
+
+Status: the assembly below is validated on the CPU against the unmodified reference's parameter gradients with the kernel
+wrappers and the two GPU providers (earlier iterations, graph builder) replaced by their specifications
+(tests/test_backward_orchestration.py::test_training_step_assembly).  It has not run on a GPU yet (gated test in
+tests/test_gpu_train_forward.py), so `EfficientMCAttModel.forward` in train() mode still raises instead of routing here.
+"""
+import numpy as np
+import torch
+
+from . import backward as bw
+from .layout import build_layout
+from .weights import slots, pack_state_dict, arena_grads_to_state_dict
+
+
+def slot_tensors(arena, hidden, n_layers, flavour=0):
+    """{prefix: {slot: tensor view (+ `_t` transposed copies of the matrices)}} over a flat arena on any device"""
+    out = {}
+    for name, r, c, off in slots(hidden, n_layers, flavour):
+        if r * c == 0:
+            continue
+        pre, _, base = name.rpartition(".")
+        pre = pre + "." if pre else ""
+        t = arena[off:off + r * c]
+        t = t.view(r, c) if r > 1 else t.view(c)
+        d = out.setdefault(pre, {})
+        d[base] = t.contiguous()
+        if r > 1:
+            d[base + "_t"] = t.t().contiguous()
+    return out
+
+
+def internal_graph(lay, ctx_edges, inter_edges, bonds, las, device):
+    """reference-order edge lists in caller node ids (construct_edges + the bond list the caller prepends, att_model.py:231) ->
+    int32 lists in internal ids; the interface edges sorted by destination row (segment softmax wants CSR order)"""
+    o = lay.offs
+    N, B = lay.N, lay.B
+    blob = lay.blob.to(device)
+    inv = blob[o["inv"]:o["inv"] + N].long()
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    ctx = torch.cat([bonds.to(device), ctx_edges.to(device)], dim=1)
+    ctx_row, ctx_col = inv[ctx[0]], inv[ctx[1]]
+    ir, ic = inv[inter_edges[0].to(device)], inv[inter_edges[1].to(device)]
+    order = torch.sort(ir, stable=True).indices
+    las_a, las_b = inv[las[0].to(device)], inv[las[1].to(device)]
+    edges = dict(ctx_row=i32(ctx_row), ctx_col=i32(ctx_col), int_row=i32(ir[order]), int_col=i32(ic[order]), las_a=i32(las_a), las_b=i32(las_b))
+    geo = dict(Nc=lay.Nc_tot, B=B, max_c=lay.max_c, max_p=lay.max_p,
+               node_cplx=blob[o["node_cplx"]:o["node_cplx"] + N].contiguous(), c_off=blob[o["c_off"]:o["c_off"] + B + 1].contiguous(),
+               p_off=blob[o["p_off"]:o["p_off"] + B + 1].contiguous(), pair_base=blob[o["pair_base"]:o["pair_base"] + B + 1].contiguous())
+    perm = blob[o["perm"]:o["perm"] + N].long()
+    moves = (lay.flags.to(device) & 4) != 0
+    return geo, edges, perm, moves
+
+
+def _gpu_prev_coords(model, fa):
+    """iterations 0 .. n_iter-2 through the inference path (in place on a copy of X)"""
+    n = model._cfg["n_iter"]
+    X = fa["X"].clone()
+    if n <= 1:
+        return X
+    was_training = model.training
+    model._cfg["n_iter"] = n - 1
+    try:
+        model.eval()
+        model(**{**fa, "X": X})
+    finally:
+        model._cfg["n_iter"] = n
+        model.train(was_training)
+    return X
+
+
+def _gpu_edges(model, X_prev, fa):
+    ctx, inter, _ = model.extract_edges.construct_edges(X_prev, fa["batch_id"], fa["segment_id"], fa["is_global"])
+    return ctx, inter
+
+
+def training_step_v1(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, state_dict=None):
+    """model: fabind_b200.EfficientMCAttModel (v1 layout).  fa: the forward arguments (X, H, batch_id, segment_id, mask, is_global,
+    compound_edge_index, LAS_edge_index, batched_complex_coord_LAS).  output_grads(X_out, H_out) -> (dL/dX_out, dL/dH_out), caller order.
+    Returns (X_out, H_out, {parameter name: gradient}, dL/dH_in).  prev_coords / edge_lists: the two GPU providers (replaceable by their
+    specifications in CPU tests)."""
+    cfg = model._cfg
+    H, L = cfg["hidden"], cfg["n_layers"]
+    dev = fa["H"].device
+    sd = state_dict if state_dict is not None else {k: v.detach() for k, v in model.state_dict().items()}
+    X_prev = prev_coords(model, fa)
+    ctx, inter = edge_lists(model, X_prev, fa)
+    lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
+    geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
+    arena = pack_state_dict(sd, H, L, 0).to(dev)
+    weights = slot_tensors(arena, H, L, 0)
+    consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,
+                  xl=fa["batched_complex_coord_LAS"].reshape(-1, 3)[perm].to(torch.float32).contiguous())
+    Hin = fa["H"][perm].to(torch.float32).contiguous()
+    x_state = X_prev[:, 0][perm].to(torch.float32).contiguous()
+    X_int, H_int, tape, top = bw.stack_forward_train_v1(weights, Hin, x_state, moves, geo, edges, consts, L)
+    X_out = torch.empty_like(fa["X"])
+    X_out[perm, 0] = X_int.to(X_out.dtype)
+    H_out = torch.empty(Hin.shape, dtype=fa["H"].dtype, device=dev)
+    H_out[perm] = H_int.to(H_out.dtype)
+    gX, gH = output_grads(X_out, H_out)
+    dX_int = (gX[:, 0][perm].to(torch.float32) * moves[:, None]).contiguous()
+    dH_int = gH[perm].to(torch.float32).contiguous()
+    grads, dHin = bw.stack_backward_v1(weights, tape, top, geo, edges, consts, dH_int, dX_int)
+    garena = torch.zeros_like(arena)
+    for name, r, c, off in slots(H, L, 0):
+        if name in grads:
+            garena[off:off + r * c] = grads[name].reshape(-1)
+    pgrads = arena_grads_to_state_dict(sd, garena, H, L, 0)
+    gH_in = torch.empty_like(Hin)
+    gH_in[perm] = dHin
+    return X_out, H_out, pgrads, gH_in
+
+
+def apply_gradients(model, pgrads, group=None, average=True):
+    """parameter gradients -> `.grad` of the drop-in module's parameters, then ONE flat all-reduce over the ranks
+    (`shard.allreduce_gradients`; unused parameters carry zeros, like DDP with find_unused_parameters)"""
+    from .shard import allreduce_gradients
+    params = dict(model.named_parameters())
+    for k, p in params.items():
+        g = pgrads.get(k)
+        p.grad = None if g is None else g.to(p.device, p.dtype).reshape(p.shape).clone()
+    allreduce_gradients(list(params.values()), group=group, average=average)

@@ -411,3 +411,54 @@ def test_training_forward_and_reverse_close_the_loop(monkeypatch):
         check_forward(case, X_out, H_out, tape, top, 1e-5)
         grads, dHin = bw.stack_backward_v1(case["weights"], tape, top, case["geo"], case["edges"], case["consts"], case["dH_out"], case["dX_out"])
         check_stack(case, grads, dHin, 1e-4)
+
+
+def test_training_step_assembly(monkeypatch):
+    """fabind_b200/train.py::training_step_v1 end to end on the CPU: kernel wrappers -> torch stand-ins, the two GPU providers
+    (earlier iterations, graph builder) -> the oracle; the parameter gradients it returns are those of the UNMODIFIED reference
+    (tests/golden/grad_v1_*.pt), and the outputs are the oracle's."""
+    from fabind_b200 import EfficientMCAttModel, backward as bw, train
+    from fabind_b200.config import published_args
+    from oracle import fabind_oracle as orc
+    _install_standins(monkeypatch, bw)
+    _install_forward_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
+    for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt"))):
+        g, r, b, sd, cfg = load_golden(path)
+        H = r["hidden"]
+        model = EfficientMCAttModel(published_args(), H, H, 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                                    normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+        model.load_state_dict(sd, strict=True)
+        fa = b.forward_args()
+        gen = torch.Generator().manual_seed(r["readout_seed"])
+        rx, rh = torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen)
+
+        def prev_coords(m, fa):
+            if cfg.n_iter <= 1:
+                return fa["X"].clone()
+            c = orc.make_cfg(n_layers=cfg.n_layers, n_iter=cfg.n_iter - 1)
+            with torch.no_grad():
+                return orc.model_forward(sd, c, fa["X"], fa["H"], fa["batch_id"], fa["segment_id"], fa["mask"], fa["is_global"],
+                                         fa["compound_edge_index"], fa["LAS_edge_index"], fa["batched_complex_coord_LAS"])[0]
+
+        def edge_lists(m, X_prev, fa):
+            ctx, inter, _ = orc.build_edges(X_prev, fa["batch_id"], fa["segment_id"], fa["is_global"], cfg.intra_cutoff / cfg.coordinate_scale,
+                                            cfg.inter_cutoff / cfg.coordinate_scale)
+            return ctx, inter
+        X_out, H_out, pgrads, gH_in = train.training_step_v1(model, fa, lambda X, Hh: (rx, rh), prev_coords=prev_coords, edge_lists=edge_lists)
+        with torch.no_grad():
+            Xo, Ho = orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global, b.compound_edge_index,
+                                       b.LAS_edge_index, b.X_LAS)
+        assert rel_err(X_out, Xo) < 1e-5 and rel_err(H_out, Ho) < 1e-4
+        loss = float((X_out * rx).sum() + (H_out * rh).sum())
+        assert abs(loss - g["loss"]) < 1e-4 * abs(g["loss"])
+        gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+        n = 0
+        for k, ref in g["grads"].items():
+            if ref is None:
+                continue
+            err = float((pgrads[k] - ref).abs().max())
+            assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
+            n += 1
+        assert n >= 80

@@ -84,3 +84,34 @@ def test_training_forward_and_reverse_on_the_real_kernels():
         grads, dHin = bw.stack_backward_v1(w, tape, top, geo, edges, consts, case["dH_out"].cuda(), case["dX_out"].cuda())
         torch.cuda.synchronize()
         check_stack(case, _cpu(grads), dHin.cpu(), TOL)
+
+
+def test_training_step_on_the_gpu():
+    """fabind_b200/train.py::training_step_v1 with the real providers (earlier iterations through fb_model_forward, edge lists from
+    the graph builder) and the real kernels: parameter gradients of the unmodified reference (tests/golden/grad_v1_*.pt)"""
+    from fabind_b200 import EfficientMCAttModel, train
+    from fabind_b200.config import published_args
+    from helpers import load_golden
+    for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt"))):
+        g, r, b, sd, cfg = load_golden(path)
+        H = r["hidden"]
+        model = EfficientMCAttModel(published_args(), H, H, 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                                    normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        gen = torch.Generator().manual_seed(r["readout_seed"])
+        rx, rh = torch.randn(b.X.shape, generator=gen).cuda(), torch.randn(b.H.shape, generator=gen).cuda()
+        fa = b.to("cuda").forward_args()
+        X_out, H_out, pgrads, gH_in = train.training_step_v1(model, fa, lambda X, Hh: (rx, rh))
+        torch.cuda.synchronize()
+        loss = float((X_out * rx).sum() + (H_out * rh).sum())
+        assert abs(loss - g["loss"]) < 1e-3 * abs(g["loss"]), (loss, g["loss"])
+        gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+        n = 0
+        for k, ref in g["grads"].items():
+            if ref is None:
+                continue
+            err = float((pgrads[k].cpu() - ref).abs().max())
+            assert err < 1e-3 * float(ref.abs().max()) + 1e-5 * gmax, (k, err, float(ref.abs().max()))
+            n += 1
+        assert n >= 80

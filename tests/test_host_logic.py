@@ -104,3 +104,19 @@ def test_host_entry_points_validate_arguments():
     assert l.fb_model_workspace_bytes(C.byref(p)) == -1                           # dropout is a FABind+ (sampling) feature
     assert l.fb_weight_slot_info_f(64, 2, 1, 10 ** 6, None, 0, None, None, None) == -1
     assert l.fb_gemm(None, None) == -1 and l.fb_gemm_dot_tiles(45000, 512, 512, 1, 0) == 4
+
+
+def test_apply_gradients_sets_param_grads_single_process():
+    """train.apply_gradients: reference-shaped gradients land on the drop-in module's parameters (missing ones stay None -> zeros in
+    the flat all-reduce buffer); world size 1: no collective"""
+    import torch
+    from fabind_b200 import EfficientMCAttModel, train
+    from fabind_b200.config import published_args
+    m = EfficientMCAttModel(published_args(), 32, 32, 1, n_layers=1, n_iter=1, normalize_coord=lambda x: x / 5.0,
+                            unnormalize_coord=lambda x: x * 5.0)
+    names = [k for k, _ in m.named_parameters()]
+    pg = {k: torch.full_like(p, 0.5) for k, p in list(m.named_parameters())[:-2]}
+    train.apply_gradients(m, pg)
+    params = dict(m.named_parameters())
+    assert all(float(params[k].grad.mean()) == 0.5 for k in names[:-2])
+    assert all(params[k].grad is not None and float(params[k].grad.abs().max()) == 0.0 for k in names[-2:])
