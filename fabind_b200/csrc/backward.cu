@@ -529,6 +529,99 @@ __global__ void pair_bias_gate_fwd_kernel(const float* __restrict__ raw, int ld,
   }
 }
 
+// ---- FABind+ layout: LayerNorm MLPs (P/models/model_utils.py:10-74) and the LayerNorm folded through the node-level hoisting
+// (DESIGN section 1).  Compiled and bound; orchestration CPU-validated; GPU parity tests gated (FB_EXPERIMENTAL). ---------------
+
+// LayerNorm reverse, statistics recomputed: xhat = (x - mean) rstd (written for the gamma gradient),
+// dx = rstd (g - mean(g) - xhat mean(g xhat)),  g = dy * gamma.  One warp per row.
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ dy, int M,
+                                     int D, float eps, float* __restrict__ dx, float* __restrict__ xhat) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* r = x + (size_t)warp * D;
+  const float* g = dy + (size_t)warp * D;
+  float s = 0.f;
+  for (int f = lane; f < D; f += 32) s += r[f];
+  const float mean = warp_sum(s) / (float)D;
+  float v = 0.f;
+  for (int f = lane; f < D; f += 32) { const float d = r[f] - mean; v = fmaf(d, d, v); }
+  const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)D + eps);
+  float a = 0.f, b = 0.f;
+  for (int f = lane; f < D; f += 32) {
+    const float xh = (r[f] - mean) * rstd, gg = g[f] * gamma[f];
+    a += gg; b = fmaf(gg, xh, b);
+  }
+  a = warp_sum(a) / (float)D; b = warp_sum(b) / (float)D;
+  for (int f = lane; f < D; f += 32) {
+    const float xh = (r[f] - mean) * rstd;
+    xhat[(size_t)warp * D + f] = xh;
+    dx[(size_t)warp * D + f] = rstd * (g[f] * gamma[f] - a - xh * b);
+  }
+}
+// per-row statistics of the folded LayerNorm: s1 = sum h, s2 = sum h^2, s3 = sum h w (w optional)
+__global__ void row_stats_kernel(const float* __restrict__ h, int ld, int M, int D, const float* __restrict__ w, float* __restrict__ s1,
+                                 float* __restrict__ s2, float* __restrict__ s3) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float* r = h + (size_t)warp * ld;
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int f = lane; f < D; f += 32) { const float t = r[f]; a += t; b = fmaf(t, t, b); if (w) c = fmaf(t, w[f], c); }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  if (lane == 0) { s1[warp] = a; s2[warp] = b; if (w) s3[warp] = c; }
+}
+// reverse: dh[m, :] += ds1[m] + 2 h[m, :] ds2[m] + w[:] ds3[m]
+__global__ void row_stats_bwd_kernel(const float* __restrict__ h, int ld, int M, int D, const float* __restrict__ w,
+                                     const float* __restrict__ ds1, const float* __restrict__ ds2, const float* __restrict__ ds3,
+                                     float* __restrict__ dh, int lddh) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float a = ds1[warp], b = 2.0f * ds2[warp], c = (w && ds3) ? ds3[warp] : 0.f;
+  for (int f = lane; f < D; f += 32)
+    dh[(size_t)warp * lddh + f] += a + b * h[(size_t)warp * ld + f] + (w ? c * w[f] : 0.f);
+}
+// folded LayerNorm statistics of an edge row z_e = [gathered node rows | rn_e * w]:
+//   mu = (A1 + rn a0) / D,  ex2 = (A2 + 2 rn A3 + rn^2 a1) / D,  var = ex2 - mu^2,  rstd = rsqrt(max(var, 0) + eps)
+// (context edges: A1 = s1[row]+s1[col], A2 = s2[row]+s2[col], A3 = 0, a0 = a1 = 1;  interfacial coordinate head: A_k = s_k[col],
+//  a0 = sum v_r, a1 = sum v_r^2)
+__global__ void folded_stats_fwd_kernel(const float* __restrict__ A1, const float* __restrict__ A2, const float* __restrict__ A3,
+                                        const float* __restrict__ rn, float a0, float a1, float D, float eps, int E,
+                                        float* __restrict__ mu, float* __restrict__ var_raw, float* __restrict__ rstd) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float r = rn[e];
+  const float m = (A1[e] + r * a0) / D;
+  const float ex2 = (A2[e] + 2.0f * r * (A3 ? A3[e] : 0.f) + r * r * a1) / D;
+  const float v = ex2 - m * m;
+  mu[e] = m; var_raw[e] = v; rstd[e] = rsqrtf(fmaxf(v, 0.f) + eps);
+}
+__global__ void folded_stats_bwd_kernel(const float* __restrict__ A3, const float* __restrict__ rn, float a0, float a1, float D, int E,
+                                        const float* __restrict__ mu, const float* __restrict__ var_raw, const float* __restrict__ rstd,
+                                        const float* __restrict__ drstd, const float* __restrict__ dmu_in, float* __restrict__ dA1,
+                                        float* __restrict__ dA2, float* __restrict__ dA3, float* __restrict__ drn,
+                                        float* __restrict__ da /* [2] accumulated, may be null */) {
+  pdl_entry();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  float p0 = 0.f, p1 = 0.f;
+  if (e < E) {
+    const float r = rn[e], rs = rstd[e];
+    const float dvar = var_raw[e] >= 0.f ? drstd[e] * (-0.5f) * rs * rs * rs : 0.f;
+    const float dmu = dmu_in[e] - 2.0f * mu[e] * dvar;
+    dA1[e] = dmu / D;
+    dA2[e] = dvar / D;
+    if (dA3) dA3[e] = 2.0f * r * dvar / D;
+    drn[e] += a0 * dmu / D + (2.0f * (A3 ? A3[e] : 0.f) + 2.0f * r * a1) * dvar / D;
+    p0 = r * dmu / D; p1 = r * r * dvar / D;
+  }
+  if (da) {
+    p0 = warp_sum(p0); p1 = warp_sum(p1);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&da[0], p0); atomicAdd(&da[1], p1); }
+  }
+}
+
 static inline int grid_1d(long long n, int block, int cap = 148 * 16) {
   long long g = (n + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -792,6 +885,56 @@ int32_t fb_row_attention_fwd(const int32_t* c_off, const int32_t* p_off, const i
   GraphDev g;
   g.B = B; g.c_off = c_off; g.p_off = p_off; g.pair_base = pair_base;
   return row_attention(g, q_is_prot, max_q, max_k, Q, ldq, G, ldg, K, ldk, V, ldv, PB, O, ldo, false, (cudaStream_t)stream);
+}
+
+int32_t fb_layernorm_bwd(const float* x, const float* gamma, const float* dy, int32_t M, int32_t D, float eps, float* dx, float* xhat,
+                         void* stream) {
+  if (M <= 0) return FB_OK;
+  fb_launch(layernorm_bwd_kernel, dim3((int)(((long long)M * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, gamma, dy, (int)M,
+            (int)D, eps, dx, xhat);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_row_stats(const float* h, int32_t ld, int32_t M, int32_t D, const float* w, float* s1, float* s2, float* s3, void* stream) {
+  if (M <= 0) return FB_OK;
+  fb_launch(row_stats_kernel, dim3((int)(((long long)M * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, h, (int)ld, (int)M, (int)D,
+            w, s1, s2, s3);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_row_stats_bwd(const float* h, int32_t ld, int32_t M, int32_t D, const float* w, const float* ds1, const float* ds2,
+                         const float* ds3, float* dh, int32_t lddh, void* stream) {
+  if (M <= 0) return FB_OK;
+  fb_launch(row_stats_bwd_kernel, dim3((int)(((long long)M * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, h, (int)ld, (int)M,
+            (int)D, w, ds1, ds2, ds3, dh, (int)lddh);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_folded_stats_fwd(const float* A1, const float* A2, const float* A3, const float* rn, float a0, float a1, float D, float eps,
+                            int32_t E, float* mu, float* var_raw, float* rstd, void* stream) {
+  if (E <= 0) return FB_OK;
+  fb_launch(folded_stats_fwd_kernel, dim3((E + 255) / 256), dim3(256), 0, (cudaStream_t)stream, A1, A2, A3, rn, a0, a1, D, eps, (int)E, mu,
+            var_raw, rstd);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_folded_stats_bwd(const float* A3, const float* rn, float a0, float a1, float D, int32_t E, const float* mu, const float* var_raw,
+                            const float* rstd, const float* drstd, const float* dmu_in, float* dA1, float* dA2, float* dA3, float* drn,
+                            float* da, void* stream) {
+  if (E <= 0) return FB_OK;
+  fb_launch(folded_stats_bwd_kernel, dim3((E + 255) / 256), dim3(256), 0, (cudaStream_t)stream, A3, rn, a0, a1, D, (int)E, mu, var_raw, rstd,
+            drstd, dmu_in, dA1, dA2, dA3, drn, da);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
 }
 
 }  // extern "C"

@@ -326,6 +326,24 @@ int32_t fb_pair_bias_gate_fwd(const float* raw, int32_t ld, int64_t P, int32_t n
 int32_t fb_row_attention_fwd(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t q_is_prot,
                              int32_t max_q, int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K,
                              int32_t ldk, const float* V, int32_t ldv, const float* PB, float* O, int32_t ldo, void* stream);
+/* -- FABind+ layout: LayerNorm MLPs (FABind_plus/fabind/models/model_utils.py:10-74) and the LayerNorm folded through the node-level
+ *    hoisting of the per-edge first Linear.  GPU parity tests gated (FB_EXPERIMENTAL) until run on a B200. -- */
+/* torch.nn.LayerNorm reverse with recomputed statistics: dx, and xhat for the gamma gradient (dgamma = colsum(dy*xhat), dbeta = colsum(dy)) */
+int32_t fb_layernorm_bwd(const float* x, const float* gamma, const float* dy, int32_t M, int32_t D, float eps, float* dx, float* xhat,
+                         void* stream);
+/* s1 = sum_f h, s2 = sum_f h^2, s3 = sum_f h w (w, s3 optional): the per-node statistics of the folded LayerNorm */
+int32_t fb_row_stats(const float* h, int32_t ld, int32_t M, int32_t D, const float* w, float* s1, float* s2, float* s3, void* stream);
+/* dh[m,:] += ds1[m] + 2 h[m,:] ds2[m] + w ds3[m] */
+int32_t fb_row_stats_bwd(const float* h, int32_t ld, int32_t M, int32_t D, const float* w, const float* ds1, const float* ds2,
+                         const float* ds3, float* dh, int32_t lddh, void* stream);
+/* per-edge folded LayerNorm statistics: mu = (A1 + rn a0)/D, ex2 = (A2 + 2 rn A3 + rn^2 a1)/D, var_raw = ex2 - mu^2,
+ * rstd = rsqrt(max(var_raw,0) + eps); A3 may be NULL */
+int32_t fb_folded_stats_fwd(const float* A1, const float* A2, const float* A3, const float* rn, float a0, float a1, float D, float eps,
+                            int32_t E, float* mu, float* var_raw, float* rstd, void* stream);
+/* its reverse: dA1, dA2, dA3 (NULL with A3), drn accumulated, da[2] (gradients of a0, a1; NULL when they are constants) accumulated */
+int32_t fb_folded_stats_bwd(const float* A3, const float* rn, float a0, float a1, float D, int32_t E, const float* mu, const float* var_raw,
+                            const float* rstd, const float* drstd, const float* dmu_in, float* dA1, float* dA2, float* dA3, float* drn,
+                            float* da, void* stream);
 
 #ifdef __cplusplus
 }
