@@ -671,3 +671,107 @@ def stack_forward_train_v1(weights, Hin, x_state, moves, geo, edges, consts, n_l
     X_out = torch.where(moves[:, None], x, x_state)
     top = dict(Hin=Hin, pc=pc, outer=outer, P0=P0, raw_full=raw_full, h_last=h_last, out_saved=s_out)
     return X_out, H_out, tape, top
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# FABind+ layout (LayerNorm MLPs, LayerNorm folded through the node-level hoisting, propagated pair embedding): reverse pass.
+# Specification: tests/emulate_backward.py::{gcl_plus_bwd, att_plus_bwd, forward_backward_plus}.  Orchestration validated on the
+# CPU; the kernels of this section have not run on a GPU yet (gated tests).
+# ------------------------------------------------------------------------------------------------------------------------
+LN_EPS = 1e-5
+
+
+def layernorm(x, gamma, beta):
+    _chk(x), _chk(gamma), _chk(beta)
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().fb_layernorm(x.data_ptr(), x.shape[0], x.shape[1], gamma.data_ptr(), beta.data_ptr(), LN_EPS, out.data_ptr(), _st(x)),
+               "fb_layernorm")
+    return out
+
+
+def layernorm_bwd(grads, gname, bname, x, gamma, dy):
+    """accumulates dgamma, dbeta; returns dx"""
+    _chk(x), _chk(gamma), _chk(dy)
+    dx, xhat = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.lib().fb_layernorm_bwd(x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), x.shape[0], x.shape[1], LN_EPS, dx.data_ptr(),
+                                           xhat.data_ptr(), _st(x)), "fb_layernorm_bwd")
+    grads[gname] = colsum(vec_mul(dy, xhat), None, grads.get(gname))
+    grads[bname] = colsum(dy, None, grads.get(bname))
+    return dx
+
+
+def row_stats_bwd(h, w, ds1, ds2, ds3, dh):
+    """dh[m,:] += ds1[m] + 2 h[m,:] ds2[m] + w ds3[m]"""
+    _chk(h), _chk(dh)
+    p = lambda t: _chk(t).data_ptr() if t is not None else None
+    _lib.check(_lib.lib().fb_row_stats_bwd(h.data_ptr(), h.shape[1], h.shape[0], h.shape[1], p(w), p(ds1), p(ds2), p(ds3), dh.data_ptr(),
+                                           dh.shape[1], _st(h)), "fb_row_stats_bwd")
+    return dh
+
+
+def folded_stats_bwd(A3, rn, a0, a1, D, mu, var_raw, rstd, drstd, dmu, drn, want_da):
+    """-> dA1, dA2, dA3 (None without A3), da [2] (None unless want_da); drn accumulated in place"""
+    E, dev = rn.numel(), rn.device
+    p = lambda t: _chk(t).data_ptr() if t is not None else None
+    dA1, dA2 = torch.empty_like(rn), torch.empty_like(rn)
+    dA3 = torch.empty_like(rn) if A3 is not None else None
+    da = torch.zeros(2, dtype=torch.float32, device=dev) if want_da else None
+    _lib.check(_lib.lib().fb_folded_stats_bwd(p(A3), rn.data_ptr(), float(a0), float(a1), float(D), E, mu.data_ptr(), var_raw.data_ptr(),
+                                              rstd.data_ptr(), drstd.data_ptr(), dmu.data_ptr(), dA1.data_ptr(), dA2.data_ptr(), p(dA3),
+                                              drn.data_ptr(), p(da), _st(rn)), "fb_folded_stats_bwd")
+    return dA1, dA2, dA3, da
+
+
+def _neg(v):
+    return vec_mul(v, torch.full_like(v, -1.0))
+
+
+def _scatter_vec(v, idx, n):
+    out = torch.zeros(n, 1, dtype=torch.float32, device=v.device)
+    scatter_add_rows(v.view(-1, 1), idx, out)
+    return out
+
+
+def gcl_plus_backward(w, sv, row, col, node_cplx, cmax, dh_new, dx_new):
+    """Reverse of one FABind+ MC_E_GCL (P/models/egnn.py:44-115).  sv: h, x, rn, nrm, mu, var_raw, rstd [E], U [E,Dp] (the un-normalised
+    folded first Linear), Z2, Z3 [E,H] and Z4, Z5 [N,H] (pre-activations; post-ReLU values serve equally), s, deg, step, agg."""
+    h, x, rn, mu, rstd = sv["h"], sv["x"], sv["rn"], sv["mu"], sv["rstd"]
+    N, H = h.shape
+    E, dev = row.numel(), h.device
+    Dp, D = sv["U"].shape[1], 2 * H + 1
+    grads = {}
+    dx, ds = coord_step_bwd(x, row, col, sv["s"], sv["step"], sv["deg"], cmax, dx_new)
+    grads["c2_w"] = colsum(act_fwd(sv["Z3"], ACT_RELU), ds)
+    dZ3 = outer_act_bwd(sv["Z3"], ds, w["c2_w"], ACT_RELU)
+    M = act_fwd(sv["Z2"], ACT_RELU)
+    dM2 = _linear_bwd(grads, "c1_w", "c1_b", w["c1_w_t"], layernorm(M, w["cl_g"], w["cl_b"]), dZ3)
+    dM = layernorm_bwd(grads, "cl_g", "cl_b", M, w["cl_g"], dM2)
+    dt1 = _linear_bwd(grads, "n2_w", "n2_b", w["n2_w_t"], act_fwd(sv["Z4"], ACT_RELU), act_bwd(sv["Z5"], dh_new, ACT_RELU))
+    cat = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
+    cat[:, :H].copy_(h)
+    cat[:, H:].copy_(sv["agg"])
+    dt0 = _linear_bwd(grads, "n1_w", "n1_b", w["n1_w_t"], layernorm(cat, w["nl_g"], w["nl_b"]), act_bwd(sv["Z4"], dt1, ACT_RELU))
+    dcat = layernorm_bwd(grads, "nl_g", "nl_b", cat, w["nl_g"], dt0)
+    dh = dh_new.clone()
+    gather_add_rows(dcat, torch.arange(N, dtype=torch.int32, device=dev), dh, col0=0)
+    gather_add_rows(dcat, row, dM, col0=H)
+    Z1 = rank1_add(scale_rows(sv["U"].clone(), rstd), _ones(E, dev), w["e1_c0"])
+    dA1 = _linear_bwd(grads, "e2_w", "e2_b", w["e2_w_t"], act_fwd(Z1, ACT_RELU), act_bwd(sv["Z2"], dM, ACT_RELU))
+    dZ1 = act_bwd(Z1, dA1, ACT_RELU)
+    grads["e1_c0"] = colsum(dZ1)
+    drstd = rowdot2(dZ1, sv["U"])
+    dU = scale_rows(dZ1, rstd)
+    grads["e1_rad"] = colsum(dU, rn)
+    grads["e1_g"] = colsum(dU, _neg(mu))
+    drn = rowdot(dU, w["e1_rad"])
+    dmu = _neg(rowdot(dU, w["e1_g"]))
+    dPn = torch.zeros(N, 2 * Dp, dtype=torch.float32, device=dev)
+    scatter_add_rows(dU, row, dPn, col0=0)
+    scatter_add_rows(dU, col, dPn, col0=Dp)
+    vec_add_(dh, _linear_bwd(grads, "e1_rc", None, w["e1_rc_t"], h, dPn))
+    dA1s, dA2s, _, _ = folded_stats_bwd(None, rn, 1.0, 1.0, D, mu, sv["var_raw"], rstd, drstd, dmu, drn, False)
+    ds1 = vec_add_(_scatter_vec(dA1s, row, N), _scatter_vec(dA1s, col, N)).view(N)
+    ds2 = vec_add_(_scatter_vec(dA2s, row, N), _scatter_vec(dA2s, col, N)).view(N)
+    row_stats_bwd(h, None, ds1, ds2, None, dh)
+    radial_bwd(x, row, col, node_cplx, sv["nrm"], drn, dx)
+    return dh, dx, grads

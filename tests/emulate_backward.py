@@ -479,7 +479,7 @@ def gcl_plus_fwd(W, pre, h, x, ctx, cplx, B, cmax):
     t0, ln_n = ln_fwd(W, torch.cat([h, agg], 1), pre + "nl_g", pre + "nl_b")
     t1 = F.relu(F.linear(t0, W.m(pre + "n1_w"), W.m(pre + "n1_b")))
     t2 = F.relu(F.linear(t1, W.m(pre + "n2_w"), W.m(pre + "n2_b")))
-    sv = dict(h=h, rn=rn, rs=rs, mu=mu, var_raw=var_raw, rstd=rstd, U=U, Z1=Z1, A1=A1, M=M, M2=M2, lc=lc, T3=T3, s=s, deg=deg,
+    sv = dict(h=h, x=x, agg=agg, rn=rn, rs=rs, mu=mu, var_raw=var_raw, rstd=rstd, U=U, Z1=Z1, A1=A1, M=M, M2=M2, lc=lc, T3=T3, s=s, deg=deg,
               d=d, step=step, t0=t0, ln_n=ln_n, t1=t1, t2=t2, Dp=Dp, D=D)
     return h + t2, x_new, sv
 
@@ -719,7 +719,7 @@ def att_plus_bwd(G, W, pre, sv, geo, inter, cmax, dh3, dx_new, dpair_out):
     return torch.cat([dhc0, dhp0]), dx, dpair_in
 
 
-def forward_backward_plus(sd, cfg, batch, gX, gH, gP, arena=None):
+def forward_backward_plus(sd, cfg, batch, gX, gH, gP, arena=None, export=None):
     """FABind+ layout, eval-mode masks (no dropout): loss = <X,gX> + <H,gH> + <pair (packed rows), gP>.
     Returns (X_out, H_out, pair_out, grad of the flat arena, grad of batch.H)."""
     from types import SimpleNamespace
@@ -775,6 +775,9 @@ def forward_backward_plus(sd, cfg, batch, gX, gH, gP, arena=None):
         H_out = torch.empty_like(batch.H)
         H_out[permt] = h_final
 
+        if export is not None:
+            export.update(W=W, geo=geo, ctx=ctx, inter=inter, las=las, tape=tape, s_out=s_out, P0=P0, cmax=cmax, lcl=lcl, xl=xl, N=N, B=B,
+                          Nc=Nc, Hin=Hin, pc=pc, outer=outer, h_last=h_last, permt=permt, moves=moves, x_state=x_state)
         G = Grads()
         dx = gX[permt, 0] * moves[:, None]
         dh = lin_bwd(G, W, "out_w", "out_b", h_last, gH[permt])
