@@ -775,3 +775,133 @@ def gcl_plus_backward(w, sv, row, col, node_cplx, cmax, dh_new, dx_new):
     row_stats_bwd(h, None, ds1, ds2, None, dh)
     radial_bwd(x, row, col, node_cplx, sv["nrm"], drn, dx)
     return dh, dx, grads
+
+
+def att_plus_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dpair_out):
+    """Reverse of one FABind+ MC_Att_L (P/models/egnn.py:129-300, P/models/cross_att.py:20-45): as att_backward, plus the LayerNorm
+    transitions, the LayerNorm-folded coordinate head and the pair transition on EVERY pair row (the embedding is propagated:
+    dpair_out comes from the next layer / the loss, dpair_in goes to the previous one).
+    sv (beyond att_backward's): raw_full [P,ld], pair_in, Zpre, Zh, Zo [P,H] (pre-LayerNorm sum; hidden and output, post-ReLU), t32, a32,
+    b32 [P,32], pi_all, ci_all [P] int32, Tc1/Tc2/Tp1/Tp2 (transition hidden / output, post-ReLU), s3 [N], mu, var_raw, rstd [E], Uc [E,H].
+    Returns (dh, dx, grads, dpair_in)."""
+    Nc, N = geo["Nc"], sv["h2"].shape[0]
+    H = sv["h2"].shape[1]
+    dev, E = dh3.device, row.numel()
+    x, rn, alpha, se, QK, mu, rstd = sv["x"], sv["rn"], sv["alpha"], sv["se"], sv["QK"], sv["mu"], sv["rstd"]
+    grads = {}
+    dQK = torch.zeros_like(QK)
+    ident = torch.arange(N, dtype=torch.int32, device=dev)
+    dx, dw = coord_step_bwd(x, row, col, vec_mul(alpha, se), sv["step"], None, cmax, dx_new)
+    dalpha, dse = vec_mul(dw, se), vec_mul(dw, alpha)
+    # LayerNorm-folded coordinate head
+    tco = rank1_add(scale_rows(sv["Uc"].clone(), rstd), _ones(E, dev), w["ac_c0"])
+    grads["ac2_w"] = colsum(act_fwd(tco, ACT_RELU), dse)
+    dt = outer_act_bwd(tco, dse, w["ac2_w"], ACT_RELU)
+    grads["ac_c0"] = colsum(dt)
+    drstd = rowdot2(dt, sv["Uc"])
+    dUc = scale_rows(dt, rstd)
+    scatter_add_rows(dUc, col, dQK, col0=3 * H + 128)
+    grads["ac_u"] = colsum(dUc, rn)
+    grads["ac_g"] = colsum(dUc, _neg(mu))
+    drn = rowdot(dUc, w["ac_u"])
+    dmu = _neg(rowdot(dUc, w["ac_g"]))
+    acr = sv["acr"]                                               # (sum v_r, sum v_r^2) as python floats
+    A3 = gather_rows(sv["s3"].view(N, 1), col).view(E)
+    dA1, dA2, dA3, da = folded_stats_bwd(A3, rn, acr[0], acr[1], H, mu, sv["var_raw"], rstd, drstd, dmu, drn, True)
+    grads["ac_r"] = da
+    ds1, ds2, ds3 = _scatter_vec(dA1, col, N).view(N), _scatter_vec(dA2, col, N).view(N), _scatter_vec(dA3, col, N).view(N)
+    V = gather_rows(QK, ident, 2 * H + 128, H)
+    dV = row_stats_bwd(V, w["v_r"], ds1, ds2, ds3, torch.zeros(N, H, dtype=torch.float32, device=dev))
+    grads["v_r"] = colsum(V, ds3)
+    # aggregation, segment softmax, logits (as in the v1 layout)
+    dh2 = dh3.clone()
+    dve = gather_rows(dh3, row)
+    ve = rank1_add(gather_rows(QK, col, 2 * H + 128, H), rn, w["v_r"])
+    vec_add_(dalpha, rowdot2(dve, ve))
+    scale_rows(dve, alpha)
+    scatter_add_rows(dve, col, dV)
+    scatter_add_rows(dV, ident, dQK, col0=2 * H + 128)
+    grads["v_r"] = colsum(dve, rn, grads["v_r"])
+    vec_add_(drn, rowdot(dve, w["v_r"]))
+    dlogit = softmax_seg_bwd(alpha, dalpha, row, N)
+    dq = scale_rows(rank1_add(gather_rows(QK, col, H, H), rn, w["k_r"]), dlogit)
+    scatter_add_rows(dq, row, dQK, col0=0)
+    dkk = scale_rows(gather_rows(QK, row, 0, H), dlogit)
+    scatter_add_rows(dkk, col, dQK, col0=H)
+    grads["k_r"] = colsum(dkk, rn)
+    vec_add_(drn, rowdot(dkk, w["k_r"]))
+    radial_bwd(x, row, col, geo["node_cplx"], sv["nrm"], drn, dx)
+    # pair transition on every pair row, attn_bias_proj as its row-dot
+    P = sv["pair_in"].shape[0]
+    dpb = torch.zeros(P, 1, dtype=torch.float32, device=dev)
+    scatter_add_rows(dlogit.view(-1, 1), sv["pair"], dpb)
+    grads["pt_c"] = colsum(dpb)
+    dpb = dpb.view(P)
+    grads["wb"] = colsum(sv["Zo"], dpb)
+    dpo = rank1_add(dpair_out.clone(), dpb, w["wb"])
+    dZh = _linear_bwd(grads, "pt2_w", "pt2_b", w["pt2_w_t"], sv["Zh"], act_bwd(sv["Zo"], dpo, ACT_RELU))
+    dZl = _linear_bwd(grads, "pt1_w", "pt1_b", w["pt1_w_t"], layernorm(sv["Zpre"], w["zl_g"], w["zl_b"]), act_bwd(sv["Zh"], dZh, ACT_RELU))
+    dZpre = layernorm_bwd(grads, "zl_g", "zl_b", sv["Zpre"], w["zl_g"], dZl)
+    dpair_in = dZpre.clone()
+    grads["zo_b"] = colsum(dZpre)
+    grads["zo_w"] = gemm_wgrad(sv["t32"], dZpre)
+    dt32 = gemm_dgrad(dZpre, w["zo_w"])
+    scatter_add_rows(vec_mul(dt32, sv["b32"]), sv["pi_all"], dQK, col0=2 * H)
+    scatter_add_rows(vec_mul(dt32, sv["a32"]), sv["ci_all"], dQK, col0=2 * H + 32)
+    vec_add_(dh2, _linear_bwd(grads, "qk_w", "qk_b", w["qk_w_t"], sv["h2"], dQK))
+    dhc, dhp = dh2[:Nc], dh2[Nc:]
+    # transitions hs + relu(linear2(relu(linear1(LN(hs)))))
+    for t, dhs, hs, T1, T2 in (("tc", dhc, sv["hc1"], sv["Tc1"], sv["Tc2"]), ("tp", dhp, sv["hp1"], sv["Tp1"], sv["Tp2"])):
+        dT1 = _linear_bwd(grads, t + "2_w", t + "2_b", w[t + "2_w_t"], T1, act_bwd(T2, dhs, ACT_RELU))
+        dt0 = _linear_bwd(grads, t + "1_w", t + "1_b", w[t + "1_w_t"], layernorm(hs, w[t + "l_g"], w[t + "l_b"]), act_bwd(T1, dT1, ACT_RELU))
+        vec_add_(dhs, layernorm_bwd(grads, t + "l_g", t + "l_b", hs, w[t + "l_g"], dt0))
+    dOc = _linear_bwd(grads, "o_c_w", "o_c_b", w["o_c_w_t"], sv["Oc"], dhc)
+    dCAc = torch.zeros_like(sv["CAc"])
+    dCAp2 = torch.zeros_like(sv["CAp2"])
+    dPB_c = row_attention_bwd(geo, 0, (sv["CAc"], 2 * HD), (sv["CAc"], 3 * HD), (sv["CAp2"], 0), (sv["CAp2"], HD), sv["PB_c"], dOc,
+                              (dCAc, 2 * HD), (dCAc, 3 * HD), (dCAp2, 0), (dCAp2, HD))
+    vec_add_(dhp, _linear_bwd(grads, "ca_p2_w", None, w["ca_p2_w_t"], sv["hp1"], dCAp2))
+    dOp = _linear_bwd(grads, "o_p_w", "o_p_b", w["o_p_w_t"], sv["Op"], dhp)
+    dCAp = torch.zeros_like(sv["CAp"])
+    dPB_p = row_attention_bwd(geo, 1, (sv["CAp"], 0), (sv["CAp"], HD), (sv["CAc"], 0), (sv["CAc"], HD), sv["PB_p"], dOp,
+                              (dCAp, 0), (dCAp, HD), (dCAc, 0), (dCAc, HD))
+    h_in = sv["h_in"]
+    vec_add_(dhc, _linear_bwd(grads, "ca_c_w", "ca_c_b", w["ca_c_w_t"], h_in[:Nc], dCAc))
+    vec_add_(dhp, _linear_bwd(grads, "ca_p_w", "ca_p_b", w["ca_p_w_t"], h_in[Nc:], dCAp))
+    # gated pair biases of the layer's two row-attention blocks read the INCOMING pair embedding
+    dPB = torch.empty(P, 2, 4, dtype=torch.float32, device=dev)
+    dPB[:, 0].copy_(dPB_p)
+    dPB[:, 1].copy_(dPB_c)
+    vec_add_(dpair_in, _linear_bwd(grads, "pb_w", "pb_b", w["pb_w_t"], sv["pair_in"], pair_bias_gate_bwd(sv["raw_full"], dPB)))
+    return dh2, dx, grads, dpair_in
+
+
+def stack_backward_plus(weights, tape, top, geo, edges, consts, dH_out, dX_out, dP_out):
+    """Reverse pass of the last refinement iteration of the FABind+ stack (P/models/att_model.py:166-223): as stack_backward_v1, with
+    the pair embedding propagated layer to layer (dP_out = gradient of the returned pair embedding, packed rows) down to pair_embed0.
+    Specification: tests/emulate_backward.py::forward_backward_plus.  Returns (grads keyed by full slot name, dHin)."""
+    L = len(tape)
+    Nc = geo["Nc"]
+    grads, g0 = {}, {}
+
+    def take(pre, g):
+        for k, v in g.items():
+            grads[pre + k] = v
+    dh = _linear_bwd(g0, "out_w", "out_b", weights[""]["out_w_t"], top["h_last"], dH_out)
+    dh, dx, g = gcl_plus_backward(weights["out."], top["out_saved"], edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dX_out)
+    take("out.", g)
+    dpair = dP_out.clone()
+    for l in reversed(range(L)):
+        s_gcl, s_att, s_las = tape[l]
+        dx = las_bwd(s_las["x"], consts["xl"], edges["las_a"], edges["las_b"], s_las["acc"], consts["las_step"], consts["lcl"], dx)
+        dh, dx, g, dpair = att_plus_backward(weights[f"att{l}."], s_att, geo, edges["int_row"], edges["int_col"], consts["cmax"], dh, dx, dpair)
+        take(f"att{l}.", g)
+        dh, dx, g = gcl_plus_backward(weights[f"gcl{l}."], s_gcl, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dx)
+        take(f"gcl{l}.", g)
+    dHin = _linear_bwd(g0, "in_w", "in_b", weights[""]["in_w_t"], top["Hin"], dh)
+    douter = _linear_bwd(g0, "il_o_w", "il_o_b", weights[""]["il_o_w_t"], top["outer"], dpair)
+    dpc = pair_outer_bwd(douter, top["pc"], geo)
+    vec_add_(dHin[:Nc], _linear_bwd(g0, "il_c_w", "il_c_b", weights[""]["il_c_w_t"], top["Hin"][:Nc], dpc[:Nc]))
+    vec_add_(dHin[Nc:], _linear_bwd(g0, "il_p_w", "il_p_b", weights[""]["il_p_w_t"], top["Hin"][Nc:], dpc[Nc:]))
+    take("", g0)
+    return grads, dHin

@@ -575,7 +575,8 @@ def att_plus_fwd(W, pre, pair_in, h, x, geo, inter, cmax):
     pi_all, ci_all = _pair_rows(geo)
     a32, b32 = QK[pi_all, 2 * H:2 * H + 32], QK[ci_all, 2 * H + 32:2 * H + 64]
     t32 = a32 * b32
-    Zl, lz = ln_fwd(W, pair_in + (t32 @ W.m(pre + "zo_w") + W.m(pre + "zo_b")), pre + "zl_g", pre + "zl_b")
+    Zpre = pair_in + (t32 @ W.m(pre + "zo_w") + W.m(pre + "zo_b"))
+    Zl, lz = ln_fwd(W, Zpre, pre + "zl_g", pre + "zl_b")
     Zh = F.relu(F.linear(Zl, W.m(pre + "pt1_w"), W.m(pre + "pt1_b")))
     pair_out = F.relu(F.linear(Zh, W.m(pre + "pt2_w"), W.m(pre + "pt2_b")))
     pb_dense = pair_out @ W.m(pre + "wb") + W.m(pre + "pt_c")
@@ -606,7 +607,8 @@ def att_plus_fwd(W, pre, pair_in, h, x, geo, inter, cmax):
     se = F.relu(tco) @ W.m(pre + "ac2_w")
     d = x[int_r] - x[int_c]
     step = torch.zeros(N, 3).index_add_(0, int_r, d * (alpha * se)[:, None])
-    sv = dict(pair_in=pair_in, raw_full=raw_full, raw=raw, sig=sig, hc0=hc0, hp0=hp0, blocks=blocks, svp=svp, svc=svc, Op=Op,
+    sv = dict(pair_in=pair_in, raw_full=raw_full, raw=raw, sig=sig, PBl=PBl, Zpre=Zpre, CAc=CAc, CAp=CAp, CAp2=CAp2, x=x, h_in=h, hc0=hc0,
+              hp0=hp0, blocks=blocks, svp=svp, svc=svc, Op=Op,
               Oc=Oc, hp1=hp1, hc1=hc1, tr=tr, h2=h2, QK=QK, pi_all=pi_all, ci_all=ci_all, a32=a32, b32=b32, t32=t32, lz=lz, Zl=Zl,
               Zh=Zh, pair_out=pair_out, pair=pair, rn=rn, rs=rs, q=q, kk=kk, alpha=alpha, ve=ve, V=V, s3=s3, mu=mu, var_raw=var_raw,
               rstd=rstd, Uc=Uc, tco=tco, se=se, d=d, step=step)

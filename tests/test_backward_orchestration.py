@@ -528,3 +528,90 @@ def test_gcl_plus_orchestration_matches_specification(monkeypatch):
             ref = G[pre + k].reshape(-1)
             err = float((v.reshape(-1) - ref).abs().max())
             assert err < 1e-5 * float(ref.abs().max()) + 1e-7 * gmax, (k, err)
+
+
+def _att_plus_saved(s2, W, pre):
+    i32 = lambda t: t.to(torch.int32)
+    acr = W.m(pre + "ac_r")
+    return dict(h_in=s2["h_in"], x=s2["x"], CAc=s2["CAc"], CAp=s2["CAp"], CAp2=s2["CAp2"], PB_p=s2["PBl"][:, 0].contiguous(),
+                PB_c=s2["PBl"][:, 1].contiguous(), raw_full=s2["raw_full"], pair_in=s2["pair_in"], Zpre=s2["Zpre"], Zh=s2["Zh"], Zo=s2["pair_out"],
+                t32=s2["t32"], a32=s2["a32"].contiguous(), b32=s2["b32"].contiguous(), pi_all=i32(s2["pi_all"]), ci_all=i32(s2["ci_all"]),
+                Tc1=s2["tr"]["tc"][2], Tc2=s2["tr"]["tc"][3], Tp1=s2["tr"]["tp"][2], Tp2=s2["tr"]["tp"][3], Op=s2["Op"], Oc=s2["Oc"],
+                hp1=s2["hp1"], hc1=s2["hc1"], h2=s2["h2"], QK=s2["QK"], pair=i32(s2["pair"]), rn=s2["rn"], nrm=s2["rs"][2], alpha=s2["alpha"],
+                se=s2["se"], s3=s2["s3"], mu=s2["mu"], var_raw=s2["var_raw"], rstd=s2["rstd"], Uc=s2["Uc"], step=s2["step"],
+                acr=(float(acr[0]), float(acr[1])))
+
+
+def test_att_plus_orchestration_matches_specification(monkeypatch):
+    from fabind_b200 import backward as bw
+    from fabind_b200.layout import build_layout
+    _install_standins(monkeypatch, bw)
+    _install_plus_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    g, r, b, sd, cfg = load_golden(sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_plus_*.pt")))[0])
+    gen = torch.Generator().manual_seed(4)
+    H = b.H.shape[1]
+    P = build_layout(b.batch_id, b.segment_id, b.is_global, b.mask, "cpu").P_total
+    ex = {}
+    spec.forward_backward_plus(sd, cfg, b, torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen),
+                               0.1 * torch.randn(P, H, generator=gen), export=ex)
+    W, geo, N, B, Nc, cmax = ex["W"], ex["geo"], ex["N"], ex["B"], ex["Nc"], ex["cmax"]
+    i32 = lambda t: t.to(torch.int32)
+    dh_up, dx_up, dp_up = torch.randn(N, H, generator=gen), torch.randn(N, 3, generator=gen), 0.1 * torch.randn(P, H, generator=gen)
+    s2 = ex["tape"][0][1]
+    G = spec.Grads()
+    rdh, rdx, rdp = spec.att_plus_bwd(G, W, "att0.", s2, geo, ex["inter"], cmax, dh_up, dx_up, dp_up)
+    geo_dev = dict(Nc=Nc, B=B, c_off=i32(torch.from_numpy(geo["c_off"].astype(np.int64))), p_off=i32(torch.from_numpy(geo["p_off"].astype(np.int64))),
+                   pair_base=i32(torch.from_numpy(geo["pair_base"].astype(np.int64))), node_cplx=i32(geo["cplx"]),
+                   max_c=int(np.diff(geo["c_off"]).max()), max_p=int(np.diff(geo["p_off"]).max()))
+    dh, dx, grads, dp = bw.att_plus_backward(_weights(W, "att0."), _att_plus_saved(s2, W, "att0."), geo_dev, i32(ex["inter"][0]),
+                                             i32(ex["inter"][1]), cmax, dh_up.clone(), dx_up.clone(), dp_up.clone())
+    assert rel_err(dh, rdh) < 1e-5 and rel_err(dx, rdx) < 1e-5 and rel_err(dp, rdp) < 1e-5, (rel_err(dh, rdh), rel_err(dx, rdx), rel_err(dp, rdp))
+    assert set("att0." + k for k in grads) == set(G), set("att0." + k for k in grads) ^ set(G)
+    gmax = max(float(t.abs().max()) for t in G.values())
+    for k, v in grads.items():
+        ref = G["att0." + k].reshape(-1)
+        err = float((v.reshape(-1) - ref).abs().max())
+        assert err < 1e-5 * float(ref.abs().max()) + 1e-7 * gmax, (k, err, float(ref.abs().max()))
+
+
+def plus_stack_case(seed=7):
+    """inputs of fabind_b200.backward.stack_backward_plus from the specification's forward on the FABind+ gradient golden"""
+    from fabind_b200.layout import build_layout
+    g, r, b, sd, cfg = load_golden(sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_plus_*.pt")))[0])
+    gen = torch.Generator().manual_seed(seed)
+    H, L = b.H.shape[1], cfg.n_layers
+    P = build_layout(b.batch_id, b.segment_id, b.is_global, b.mask, "cpu").P_total
+    gX, gH, gP = torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen), 0.1 * torch.randn(P, H, generator=gen)
+    ex = {}
+    _, _, _, garena, gHin = spec.forward_backward_plus(sd, cfg, b, gX, gH, gP, export=ex)
+    W, geo, N, B, Nc = ex["W"], ex["geo"], ex["N"], ex["B"], ex["Nc"]
+    i32 = lambda t: t.to(torch.int32)
+    geo_dev = dict(Nc=Nc, B=B, c_off=i32(torch.from_numpy(geo["c_off"].astype(np.int64))), p_off=i32(torch.from_numpy(geo["p_off"].astype(np.int64))),
+                   pair_base=i32(torch.from_numpy(geo["pair_base"].astype(np.int64))), node_cplx=i32(geo["cplx"]),
+                   max_c=int(np.diff(geo["c_off"]).max()), max_p=int(np.diff(geo["p_off"]).max()))
+    weights = {"": _weights(W, ""), "out.": _weights(W, "out.")}
+    tape = []
+    for l in range(L):
+        weights[f"gcl{l}."], weights[f"att{l}."] = _weights(W, f"gcl{l}."), _weights(W, f"att{l}.")
+        s1, s2, s3 = ex["tape"][l]
+        tape.append((_gcl_plus_saved(s1), _att_plus_saved(s2, W, f"att{l}."), dict(x=s3["x"], acc=s3["acc"])))
+    top = dict(Hin=ex["Hin"], pc=ex["pc"], outer=ex["outer"], h_last=ex["h_last"], out_saved=_gcl_plus_saved(ex["s_out"]))
+    edges = dict(ctx_row=i32(ex["ctx"][0]), ctx_col=i32(ex["ctx"][1]), int_row=i32(ex["inter"][0]), int_col=i32(ex["inter"][1]),
+                 las_a=i32(ex["las"][0]), las_b=i32(ex["las"][1]))
+    consts = dict(cmax=ex["cmax"], lcl=ex["lcl"], las_step=cfg.geometry_reg_step_size, xl=ex["xl"])
+    permt = ex["permt"]
+    return dict(weights=weights, tape=tape, top=top, geo=geo_dev, edges=edges, consts=consts, dH_out=gH[permt].contiguous(),
+                dX_out=(gX[permt, 0] * ex["moves"][:, None]).contiguous(), dP_out=gP, W=W, garena=garena, gHin=gHin[permt])
+
+
+def test_plus_stack_reverse_pass_matches_specification(monkeypatch):
+    from fabind_b200 import backward as bw
+    _install_standins(monkeypatch, bw)
+    _install_plus_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
+    case = plus_stack_case()
+    grads, dHin = bw.stack_backward_plus(case["weights"], case["tape"], case["top"], case["geo"], case["edges"], case["consts"],
+                                         case["dH_out"], case["dX_out"], case["dP_out"])
+    check_stack(case, grads, dHin, 1e-4)

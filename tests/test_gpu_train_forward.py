@@ -115,3 +115,50 @@ def test_training_step_on_the_gpu():
             assert err < 1e-3 * float(ref.abs().max()) + 1e-5 * gmax, (k, err, float(ref.abs().max()))
             n += 1
         assert n >= 80
+
+
+def test_plus_kernels_match_torch():
+    from fabind_b200 import backward as bw
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(6)
+    M, D = 900, 160
+    x = (torch.randn(M, D, generator=g) * 2 + 0.5).requires_grad_(True)
+    gamma, beta, dy = torch.randn(D, generator=g), torch.randn(D, generator=g), torch.randn(M, D, generator=g)
+    y = F.layer_norm(x, (D,), gamma.clone().requires_grad_(True), beta, 1e-5)
+    gl = gamma.clone().requires_grad_(True)
+    bl = beta.clone().requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    F.layer_norm(x2, (D,), gl, bl, 1e-5).backward(dy)
+    grads = {}
+    dx = bw.layernorm_bwd(grads, "g", "b", x.detach().cuda(), gamma.cuda(), dy.cuda())
+    assert rel_err(dx, x2.grad) < 1e-5 and rel_err(grads["g"], gl.grad) < 1e-5 and rel_err(grads["b"], bl.grad) < 1e-5
+    h, w = torch.randn(M, D, generator=g), torch.randn(D, generator=g)
+    ds1, ds2, ds3 = torch.randn(M, generator=g), torch.randn(M, generator=g), torch.randn(M, generator=g)
+    base = torch.randn(M, D, generator=g)
+    out = bw.row_stats_bwd(h.cuda(), w.cuda(), ds1.cuda(), ds2.cuda(), ds3.cuda(), base.clone().cuda())
+    assert rel_err(out, base + ds1[:, None] + 2 * h * ds2[:, None] + w[None, :] * ds3[:, None]) < 1e-6
+    E, Dn = 4000, 65.0
+    A1, A2, A3, rn = (torch.randn(E, generator=g).requires_grad_(True), (torch.rand(E, generator=g) * 50 + 5).requires_grad_(True),
+                      torch.randn(E, generator=g).requires_grad_(True), torch.rand(E, generator=g).requires_grad_(True))
+    a = torch.tensor([0.7, 1.9], requires_grad=True)
+    mu = (A1 + rn * a[0]) / Dn
+    var_raw = (A2 + 2 * rn * A3 + rn * rn * a[1]) / Dn - mu * mu
+    rstd = torch.rsqrt(var_raw.clamp(min=0) + 1e-5)
+    drstd, dmu = torch.randn(E, generator=g), torch.randn(E, generator=g)
+    ((rstd * drstd).sum() + (mu * dmu).sum()).backward()
+    drn = torch.zeros(E).cuda()
+    c = lambda t: t.detach().cuda()
+    dA1, dA2, dA3, da = bw.folded_stats_bwd(c(A3), c(rn), 0.7, 1.9, Dn, c(mu), c(var_raw), c(rstd), drstd.cuda(), dmu.cuda(), drn, True)
+    assert rel_err(dA1, A1.grad) < 1e-5 and rel_err(dA2, A2.grad) < 1e-5 and rel_err(dA3, A3.grad) < 1e-5
+    assert rel_err(drn, rn.grad) < 1e-5 and rel_err(da, a.grad) < 1e-4
+
+
+def test_plus_stack_backward_on_the_real_kernels():
+    from fabind_b200 import backward as bw
+    from test_backward_orchestration import plus_stack_case, check_stack
+    case = plus_stack_case()
+    tape = [tuple(_cuda(s) for s in layer) for layer in case["tape"]]
+    grads, dHin = bw.stack_backward_plus(_cuda(case["weights"]), tape, _cuda(case["top"]), _cuda(case["geo"]), _cuda(case["edges"]),
+                                         _cuda(case["consts"]), case["dH_out"].cuda(), case["dX_out"].cuda(), case["dP_out"].cuda())
+    torch.cuda.synchronize()
+    check_stack(case, _cpu(grads), dHin.cpu(), TOL)
