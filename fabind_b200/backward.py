@@ -905,3 +905,166 @@ def stack_backward_plus(weights, tape, top, geo, edges, consts, dH_out, dX_out, 
     vec_add_(dHin[Nc:], _linear_bwd(g0, "il_p_w", "il_p_b", weights[""]["il_p_w_t"], top["Hin"][Nc:], dpc[Nc:]))
     take("", g0)
     return grads, dHin
+
+
+# ---- FABind+ training-mode forward of the last iteration (kernels not yet run on a GPU; orchestration CPU-validated) ----------
+def row_stats(h, w=None):
+    """-> s1 = sum_f h, s2 = sum_f h^2, s3 = sum_f h w (None without w)"""
+    _chk(h)
+    M, dev = h.shape[0], h.device
+    s1, s2 = torch.empty(M, dtype=torch.float32, device=dev), torch.empty(M, dtype=torch.float32, device=dev)
+    s3 = torch.empty(M, dtype=torch.float32, device=dev) if w is not None else None
+    p = lambda t: _chk(t).data_ptr() if t is not None else None
+    _lib.check(_lib.lib().fb_row_stats(h.data_ptr(), h.shape[1], M, h.shape[1], p(w), s1.data_ptr(), s2.data_ptr(), p(s3), _st(h)), "fb_row_stats")
+    return s1, s2, s3
+
+
+def folded_stats_fwd(A1, A2, A3, rn, a0, a1, D):
+    """-> mu, var_raw, rstd of the folded LayerNorm (see csrc/backward.cu::folded_stats_fwd_kernel)"""
+    _chk(A1), _chk(A2), _chk(rn)
+    mu, var_raw, rstd = torch.empty_like(rn), torch.empty_like(rn), torch.empty_like(rn)
+    _lib.check(_lib.lib().fb_folded_stats_fwd(A1.data_ptr(), A2.data_ptr(), _chk(A3).data_ptr() if A3 is not None else None, rn.data_ptr(),
+                                              float(a0), float(a1), float(D), LN_EPS, rn.numel(), mu.data_ptr(), var_raw.data_ptr(),
+                                              rstd.data_ptr(), _st(rn)), "fb_folded_stats_fwd")
+    return mu, var_raw, rstd
+
+
+def _gather_vec(v, idx):
+    return gather_rows(v.view(-1, 1), idx).view(-1)
+
+
+def gcl_plus_forward_train(w, h, x, row, col, node_cplx, B, cmax):
+    """FABind+ MC_E_GCL forward (P/models/egnn.py:44-115; inference twin: plus.cu / forward.cu) keeping what gcl_plus_backward consumes"""
+    N, H = h.shape
+    E, dev = row.numel(), h.device
+    Dp, D = w["e1_rad"].numel(), 2 * H + 1
+    d, d2, rn, nrm = radial_fwd(x, row, col, node_cplx, B)
+    s1, s2, _ = row_stats(h)
+    Pn = linear(h, w["e1_rc"])
+    mu, var_raw, rstd = folded_stats_fwd(vec_add_(_gather_vec(s1, row), _gather_vec(s1, col)), vec_add_(_gather_vec(s2, row), _gather_vec(s2, col)),
+                                         None, rn, 1.0, 1.0, D)
+    U = gather_rows(Pn, row, 0, Dp)
+    gather_add_rows(Pn, col, U, col0=Dp)
+    rank1_add(U, rn, w["e1_rad"])
+    rank1_add(U, _neg(mu), w["e1_g"])
+    Z1 = rank1_add(scale_rows(U.clone(), rstd), _ones(E, dev), w["e1_c0"])
+    M = linear(act_fwd(Z1, ACT_RELU), w["e2_w"], w["e2_b"], act=ACT_RELU)
+    T3 = linear(layernorm(M, w["cl_g"], w["cl_b"]), w["c1_w"], w["c1_b"], act=ACT_RELU)
+    s = rowdot(T3, w["c2_w"])
+    ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+    scatter_add_rows(scale_rows(d.clone(), s), row, ssum)
+    deg = torch.zeros(N, 1, dtype=torch.float32, device=dev)
+    scatter_add_rows(_ones(E, dev).view(E, 1), row, deg)
+    deg = deg.view(N)
+    step, x_new = coord_apply(x, ssum, deg, cmax)
+    agg = torch.zeros(N, H, dtype=torch.float32, device=dev)
+    scatter_add_rows(M, row, agg)
+    cat = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
+    cat[:, :H].copy_(h)
+    cat[:, H:].copy_(agg)
+    t1 = linear(layernorm(cat, w["nl_g"], w["nl_b"]), w["n1_w"], w["n1_b"], act=ACT_RELU)
+    t2 = linear(t1, w["n2_w"], w["n2_b"], act=ACT_RELU)
+    h_new = vec_add_(h.clone(), t2)
+    return h_new, x_new, dict(h=h, x=x, rn=rn, nrm=nrm, mu=mu, var_raw=var_raw, rstd=rstd, U=U, Z2=M, Z3=T3, Z4=t1, Z5=t2, s=s, deg=deg,
+                              step=step, agg=agg)
+
+
+def pair_row_nodes(geo):
+    """protein-side / compound-side node of every pair row (index bookkeeping; small host loop over complexes)"""
+    c_off, p_off = geo["c_off"].tolist(), geo["p_off"].tolist()
+    pi, ci = [], []
+    for b in range(geo["B"]):
+        nc1, np1 = c_off[b + 1] - c_off[b], p_off[b + 1] - p_off[b]
+        pi.append(torch.arange(p_off[b], p_off[b + 1], dtype=torch.int32).repeat_interleave(nc1))
+        ci.append(torch.arange(c_off[b], c_off[b + 1], dtype=torch.int32).repeat(np1))
+    dev = geo["c_off"].device
+    return torch.cat(pi).to(dev).contiguous(), torch.cat(ci).to(dev).contiguous()
+
+
+def att_plus_forward_train(w, pair_in, h, x, geo, row, col, idx, pair_nodes, cmax):
+    """FABind+ MC_Att_L forward (P/models/egnn.py:129-300, P/models/cross_att.py:20-45) keeping what att_plus_backward consumes"""
+    N, H = h.shape
+    Nc, dev, E = geo["Nc"], h.device, row.numel()
+    P = pair_in.shape[0]
+    pi_all, ci_all = pair_nodes
+    raw_full = linear(pair_in, w["pb_w"], w["pb_b"])
+    PB = pair_bias_gate_fwd(raw_full, 2)
+    PB_p, PB_c = PB[:, 0].contiguous(), PB[:, 1].contiguous()
+    hc0, hp0 = h[:Nc], h[Nc:]
+    CAc = linear(hc0, w["ca_c_w"], w["ca_c_b"])
+    CAp = linear(hp0, w["ca_p_w"], w["ca_p_b"])
+    Op = row_attention_fwd(geo, 1, (CAp, 0), (CAp, HD), (CAc, 0), (CAc, HD), PB_p, N - Nc)
+    hp1 = linear(Op, w["o_p_w"], w["o_p_b"], res=hp0)
+    CAp2 = linear(hp1, w["ca_p2_w"])
+    Oc = row_attention_fwd(geo, 0, (CAc, 2 * HD), (CAc, 3 * HD), (CAp2, 0), (CAp2, HD), PB_c, Nc)
+    hc1 = linear(Oc, w["o_c_w"], w["o_c_b"], res=hc0)
+    tr = {}
+    h2 = torch.empty(N, H, dtype=torch.float32, device=dev)
+    for t, hs, dst in (("tc", hc1, h2[:Nc]), ("tp", hp1, h2[Nc:])):
+        T1 = linear(layernorm(hs, w[t + "l_g"], w[t + "l_b"]), w[t + "1_w"], w[t + "1_b"], act=ACT_RELU)
+        T2 = linear(T1, w[t + "2_w"], w[t + "2_b"], act=ACT_RELU)
+        dst.copy_(hs)
+        vec_add_(dst, T2)
+        tr[t] = (T1, T2)
+    QK = linear(h2, w["qk_w"], w["qk_b"])
+    a32, b32 = gather_rows(QK, pi_all, 2 * H, 32), gather_rows(QK, ci_all, 2 * H + 32, 32)
+    t32 = vec_mul(a32, b32)
+    Zpre = linear(t32, w["zo_w_t"], w["zo_b"], res=pair_in)
+    Zh = linear(layernorm(Zpre, w["zl_g"], w["zl_b"]), w["pt1_w"], w["pt1_b"], act=ACT_RELU)
+    Zo = linear(Zh, w["pt2_w"], w["pt2_b"], act=ACT_RELU)
+    pb_dense = rowdot(Zo, w["wb"]).view(P, 1)
+    rank1_add(pb_dense, _ones(P, dev), w["pt_c"])
+    d, d2, rn, nrm = radial_fwd(x, row, col, geo["node_cplx"], geo["B"])
+    logit = rowdot2(gather_rows(QK, row, 0, H), rank1_add(gather_rows(QK, col, H, H), rn, w["k_r"]))
+    vec_add_(logit, gather_rows(pb_dense, idx["pair"]).view(E))
+    alpha = softmax_seg_fwd(logit, idx["rowptr"], N)
+    ve = scale_rows(rank1_add(gather_rows(QK, col, 2 * H + 128, H), rn, w["v_r"]), alpha)
+    h3 = h2.clone()
+    scatter_add_rows(ve, row, h3)
+    V = gather_rows(QK, torch.arange(N, dtype=torch.int32, device=dev), 2 * H + 128, H)
+    s1, s2, s3 = row_stats(V, w["v_r"])
+    acr = tuple(float(v) for v in w["ac_r"].tolist())
+    mu, var_raw, rstd = folded_stats_fwd(_gather_vec(s1, col), _gather_vec(s2, col), _gather_vec(s3, col), rn, acr[0], acr[1], H)
+    Uc = rank1_add(gather_rows(QK, col, 3 * H + 128, H), rn, w["ac_u"])
+    rank1_add(Uc, _neg(mu), w["ac_g"])
+    tco = rank1_add(scale_rows(Uc.clone(), rstd), _ones(E, dev), w["ac_c0"])
+    se = rowdot(act_fwd(tco, ACT_RELU), w["ac2_w"])
+    ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+    scatter_add_rows(scale_rows(d.clone(), vec_mul(alpha, se)), row, ssum)
+    step, x_new = coord_apply(x, ssum, None, cmax)
+    sv = dict(h_in=h, x=x, CAc=CAc, CAp=CAp, CAp2=CAp2, PB_p=PB_p, PB_c=PB_c, raw_full=raw_full, pair_in=pair_in, Zpre=Zpre, Zh=Zh, Zo=Zo, t32=t32,
+              a32=a32, b32=b32, pi_all=pi_all, ci_all=ci_all, Tc1=tr["tc"][0], Tc2=tr["tc"][1], Tp1=tr["tp"][0], Tp2=tr["tp"][1], Op=Op, Oc=Oc,
+              hp1=hp1, hc1=hc1, h2=h2, QK=QK, pair=idx["pair"], rn=rn, nrm=nrm, alpha=alpha, se=se, s3=s3, mu=mu, var_raw=var_raw, rstd=rstd,
+              Uc=Uc, step=step, acr=acr)
+    return h3, x_new, Zo, sv
+
+
+def stack_forward_train_plus(weights, Hin, x_state, moves, geo, edges, consts, n_layers):
+    """Last refinement iteration of the FABind+ stack in training mode, eval-mode masks (no dropout): returns
+    (X_out, H_out, pair_out [P,H], tape, top) in the form stack_backward_plus consumes."""
+    N, H = Hin.shape
+    Nc, dev = geo["Nc"], Hin.device
+    wt = weights[""]
+    pc = torch.empty(N, H, dtype=torch.float32, device=dev)
+    pc[:Nc].copy_(linear(Hin[:Nc], wt["il_c_w"], wt["il_c_b"]))
+    pc[Nc:].copy_(linear(Hin[Nc:], wt["il_p_w"], wt["il_p_b"]))
+    outer = pair_outer_fwd(pc, geo, consts["n_pairs"])
+    pair = linear(outer, wt["il_o_w"], wt["il_o_b"])
+    h = linear(Hin, wt["in_w"], wt["in_b"])
+    x = x_state
+    idx = interface_indices(edges["int_row"], edges["int_col"], geo)
+    pair_nodes = pair_row_nodes(geo)
+    tape = []
+    for l in range(n_layers):
+        h, x, s_gcl = gcl_plus_forward_train(weights[f"gcl{l}."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"])
+        h, x, pair, s_att = att_plus_forward_train(weights[f"att{l}."], pair, h, x, geo, edges["int_row"], edges["int_col"], idx, pair_nodes,
+                                                   consts["cmax"])
+        acc = las_acc(x, consts["xl"], edges["las_a"], edges["las_b"], consts["las_step"])
+        x_in = x
+        _, x = coord_apply(x_in, acc, None, consts["lcl"])
+        tape.append((s_gcl, s_att, dict(x=x_in, acc=acc)))
+    h_last, x, s_out = gcl_plus_forward_train(weights["out."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"])
+    H_out = linear(h_last, wt["out_w"], wt["out_b"])
+    X_out = torch.where(moves[:, None], x, x_state)
+    top = dict(Hin=Hin, pc=pc, outer=outer, h_last=h_last, out_saved=s_out)
+    return X_out, H_out, pair, tape, top

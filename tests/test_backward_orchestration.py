@@ -602,7 +602,8 @@ def plus_stack_case(seed=7):
     consts = dict(cmax=ex["cmax"], lcl=ex["lcl"], las_step=cfg.geometry_reg_step_size, xl=ex["xl"])
     permt = ex["permt"]
     return dict(weights=weights, tape=tape, top=top, geo=geo_dev, edges=edges, consts=consts, dH_out=gH[permt].contiguous(),
-                dX_out=(gX[permt, 0] * ex["moves"][:, None]).contiguous(), dP_out=gP, W=W, garena=garena, gHin=gHin[permt])
+                dX_out=(gX[permt, 0] * ex["moves"][:, None]).contiguous(), dP_out=gP, W=W, garena=garena, gHin=gHin[permt],
+                moves=ex["moves"], x_state=ex["x_state"])
 
 
 def test_plus_stack_reverse_pass_matches_specification(monkeypatch):
@@ -614,4 +615,40 @@ def test_plus_stack_reverse_pass_matches_specification(monkeypatch):
     case = plus_stack_case()
     grads, dHin = bw.stack_backward_plus(case["weights"], case["tape"], case["top"], case["geo"], case["edges"], case["consts"],
                                          case["dH_out"], case["dX_out"], case["dP_out"])
+    check_stack(case, grads, dHin, 1e-4)
+
+
+def test_plus_training_forward_and_reverse_close_the_loop(monkeypatch):
+    """FABind+: stack_forward_train_plus -> stack_backward_plus on torch stand-ins == the specification (outputs, saved tensors, arena gradient)"""
+    from fabind_b200 import backward as bw
+    _install_standins(monkeypatch, bw)
+    _install_forward_standins(monkeypatch, bw)
+    _install_plus_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
+    monkeypatch.setattr(bw, "row_stats", lambda h, w=None: (h.sum(1), (h * h).sum(1), (h * w).sum(1) if w is not None else None))
+
+    def fstats(A1, A2, A3, rn, a0, a1, D):
+        mu = (A1 + rn * a0) / D
+        var_raw = (A2 + 2 * rn * (A3 if A3 is not None else 0) + rn * rn * a1) / D - mu * mu
+        return mu, var_raw, torch.rsqrt(var_raw.clamp(min=0) + 1e-5)
+    monkeypatch.setattr(bw, "folded_stats_fwd", fstats)
+    case = plus_stack_case()
+    case["consts"]["n_pairs"] = int(case["dP_out"].shape[0])
+    ex_moves, x_state = case["moves"], case["x_state"]
+    L = len(case["tape"])
+    X_out, H_out, pair, tape, top = bw.stack_forward_train_plus(case["weights"], case["top"]["Hin"], x_state, ex_moves, case["geo"], case["edges"],
+                                                                case["consts"], L)
+    for mine, ref in zip(tape + [(top["out_saved"],)], case["tape"] + [(case["top"]["out_saved"],)]):
+        for sm, sr in zip(mine, ref):
+            assert set(sm) == set(sr), set(sm) ^ set(sr)
+            for k in sr:
+                if k == "acr":
+                    assert max(abs(a - b) for a, b in zip(sm[k], sr[k])) < 1e-6
+                elif sr[k].dtype == torch.int32:
+                    assert torch.equal(sm[k], sr[k]), k
+                else:
+                    assert rel_err(sm[k], sr[k]) < 1e-5, (k, rel_err(sm[k], sr[k]))
+    grads, dHin = bw.stack_backward_plus(case["weights"], tape, top, case["geo"], case["edges"], case["consts"], case["dH_out"], case["dX_out"],
+                                         case["dP_out"])
     check_stack(case, grads, dHin, 1e-4)

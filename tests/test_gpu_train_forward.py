@@ -162,3 +162,26 @@ def test_plus_stack_backward_on_the_real_kernels():
                                          _cuda(case["consts"]), case["dH_out"].cuda(), case["dX_out"].cuda(), case["dP_out"].cuda())
     torch.cuda.synchronize()
     check_stack(case, _cpu(grads), dHin.cpu(), TOL)
+
+
+def test_plus_training_forward_and_reverse_on_the_real_kernels():
+    from fabind_b200 import backward as bw
+    from test_backward_orchestration import plus_stack_case, check_stack
+    case = plus_stack_case()
+    case["consts"]["n_pairs"] = int(case["dP_out"].shape[0])
+    w, geo, edges, consts = _cuda(case["weights"]), _cuda(case["geo"]), _cuda(case["edges"]), _cuda(case["consts"])
+    X_out, H_out, pair, tape, top = bw.stack_forward_train_plus(w, case["top"]["Hin"].cuda(), case["x_state"].cuda(), case["moves"].cuda(), geo,
+                                                                edges, consts, len(case["tape"]))
+    torch.cuda.synchronize()
+    for mine, ref in zip(_cpu(tape) + [(_cpu(top["out_saved"]),)], case["tape"] + [(case["top"]["out_saved"],)]):
+        for sm, sr in zip(mine, ref):
+            for k in sr:
+                if k == "acr":
+                    continue
+                if sr[k].dtype == torch.int32:
+                    assert torch.equal(sm[k], sr[k]), k
+                else:
+                    assert rel_err(sm[k], sr[k]) < TOL, (k, rel_err(sm[k], sr[k]))
+    grads, dHin = bw.stack_backward_plus(w, tape, top, geo, edges, consts, case["dH_out"].cuda(), case["dX_out"].cuda(), case["dP_out"].cuda())
+    torch.cuda.synchronize()
+    check_stack(case, _cpu(grads), dHin.cpu(), TOL)
