@@ -1,4 +1,4 @@
-"""Assembly of one training step through the v1 docking stack (BASELINE config 5: forward + backward + gradient all-reduce).
+"""Assembly of one training step through the docking stack (v1 and FABind+ layouts) (BASELINE config 5: forward + backward + gradient all-reduce).
 
 Reference semantics (att_model.py:210-246, refine='refine_coord'): the first `n_iter - 1` refinement iterations run under no_grad
 and only move the ligand; the last one is differentiated.  So a step is
@@ -86,42 +86,56 @@ def _gpu_edges(model, X_prev, fa):
     return ctx, inter
 
 
-def training_step_v1(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, state_dict=None):
-    """model: fabind_b200.EfficientMCAttModel (v1 layout).  fa: the forward arguments (X, H, batch_id, segment_id, mask, is_global,
-    compound_edge_index, LAS_edge_index, batched_complex_coord_LAS).  output_grads(X_out, H_out) -> (dL/dX_out, dL/dH_out), caller order.
-    Returns (X_out, H_out, {parameter name: gradient}, dL/dH_in).  prev_coords / edge_lists: the two GPU providers (replaceable by their
-    specifications in CPU tests)."""
+def training_step(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, state_dict=None):
+    """model: fabind_b200.EfficientMCAttModel (v1 layout) or fabind_b200.plus.EfficientMCAttModel (FABind+ layout, eval-mode masks).
+    fa: the forward arguments (X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index, batched_complex_coord_LAS).
+    output_grads: v1  (X_out, H_out) -> (dL/dX_out, dL/dH_out);  FABind+  (X_out, H_out, pair rows [P,H]) -> (dL/dX, dL/dH, dL/dpair rows)
+    (caller node order; pair rows packed per complex as [Np', Nc'] blocks).
+    Returns (X_out, H_out[, pair rows], {parameter name: gradient}, dL/dH_in).  prev_coords / edge_lists: the two GPU providers
+    (replaceable by their specifications in CPU tests)."""
     cfg = model._cfg
-    H, L = cfg["hidden"], cfg["n_layers"]
+    H, L, flavour = cfg["hidden"], cfg["n_layers"], int(cfg.get("flavour", 0))
     dev = fa["H"].device
     sd = state_dict if state_dict is not None else {k: v.detach() for k, v in model.state_dict().items()}
     X_prev = prev_coords(model, fa)
     ctx, inter = edge_lists(model, X_prev, fa)
     lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
     geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
-    arena = pack_state_dict(sd, H, L, 0).to(dev)
-    weights = slot_tensors(arena, H, L, 0)
+    arena = pack_state_dict(sd, H, L, flavour).to(dev)
+    weights = slot_tensors(arena, H, L, flavour)
     consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,
                   xl=fa["batched_complex_coord_LAS"].reshape(-1, 3)[perm].to(torch.float32).contiguous())
     Hin = fa["H"][perm].to(torch.float32).contiguous()
     x_state = X_prev[:, 0][perm].to(torch.float32).contiguous()
-    X_int, H_int, tape, top = bw.stack_forward_train_v1(weights, Hin, x_state, moves, geo, edges, consts, L)
+    pair = None
+    if flavour == 1:
+        X_int, H_int, pair, tape, top = bw.stack_forward_train_plus(weights, Hin, x_state, moves, geo, edges, consts, L)
+    else:
+        X_int, H_int, tape, top = bw.stack_forward_train_v1(weights, Hin, x_state, moves, geo, edges, consts, L)
     X_out = torch.empty_like(fa["X"])
     X_out[perm, 0] = X_int.to(X_out.dtype)
     H_out = torch.empty(Hin.shape, dtype=fa["H"].dtype, device=dev)
     H_out[perm] = H_int.to(H_out.dtype)
-    gX, gH = output_grads(X_out, H_out)
-    dX_int = (gX[:, 0][perm].to(torch.float32) * moves[:, None]).contiguous()
-    dH_int = gH[perm].to(torch.float32).contiguous()
-    grads, dHin = bw.stack_backward_v1(weights, tape, top, geo, edges, consts, dH_int, dX_int)
+    og = output_grads(X_out, H_out, pair) if flavour == 1 else output_grads(X_out, H_out)
+    dX_int = (og[0][:, 0][perm].to(torch.float32) * moves[:, None]).contiguous()
+    dH_int = og[1][perm].to(torch.float32).contiguous()
+    if flavour == 1:
+        grads, dHin = bw.stack_backward_plus(weights, tape, top, geo, edges, consts, dH_int, dX_int, og[2].to(torch.float32).contiguous())
+    else:
+        grads, dHin = bw.stack_backward_v1(weights, tape, top, geo, edges, consts, dH_int, dX_int)
     garena = torch.zeros_like(arena)
-    for name, r, c, off in slots(H, L, 0):
+    for name, r, c, off in slots(H, L, flavour):
         if name in grads:
             garena[off:off + r * c] = grads[name].reshape(-1)
-    pgrads = arena_grads_to_state_dict(sd, garena, H, L, 0)
+    pgrads = arena_grads_to_state_dict(sd, garena, H, L, flavour)
     gH_in = torch.empty_like(Hin)
     gH_in[perm] = dHin
+    if flavour == 1:
+        return X_out, H_out, pair, pgrads, gH_in
     return X_out, H_out, pgrads, gH_in
+
+
+training_step_v1 = training_step
 
 
 def apply_gradients(model, pgrads, group=None, average=True):

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from helpers import GOLDEN_DIR, load_golden, rel_err
 import emulate_backward as spec
+from emulate_packed import forward_emulated
 
 
 def _actf(z, a):
@@ -652,3 +653,63 @@ def test_plus_training_forward_and_reverse_close_the_loop(monkeypatch):
     grads, dHin = bw.stack_backward_plus(case["weights"], tape, top, case["geo"], case["edges"], case["consts"], case["dH_out"], case["dX_out"],
                                          case["dP_out"])
     check_stack(case, grads, dHin, 1e-4)
+
+
+def test_plus_training_step_assembly(monkeypatch):
+    """train.training_step on the FABind+ layout, CPU: stand-ins for the kernel wrappers, the FABind+ oracle as the two providers;
+    parameter gradients of the UNMODIFIED FABind+ reference (tests/golden/grad_plus_*.pt)"""
+    from fabind_b200 import backward as bw, train
+    from fabind_b200.config import published_args_plus
+    from fabind_b200.plus import EfficientMCAttModel as PlusModel
+    from oracle import fabind_oracle as orc, fabind_plus_oracle as porc
+    from test_formulation_cpu import _dense_pair
+    _install_standins(monkeypatch, bw)
+    _install_forward_standins(monkeypatch, bw)
+    _install_plus_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
+    monkeypatch.setattr(bw, "row_stats", lambda h, w=None: (h.sum(1), (h * h).sum(1), (h * w).sum(1) if w is not None else None))
+    monkeypatch.setattr(bw, "folded_stats_fwd", lambda A1, A2, A3, rn, a0, a1, D: (
+        (A1 + rn * a0) / D, (A2 + 2 * rn * (A3 if A3 is not None else 0) + rn * rn * a1) / D - ((A1 + rn * a0) / D) ** 2,
+        torch.rsqrt(((A2 + 2 * rn * (A3 if A3 is not None else 0) + rn * rn * a1) / D - ((A1 + rn * a0) / D) ** 2).clamp(min=0) + 1e-5)))
+    for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_plus_*.pt"))):
+        g, r, b, sd, cfg = load_golden(path)
+        H = r["hidden"]
+        model = PlusModel(published_args_plus(), H, H, 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                          normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+        model.load_state_dict(sd, strict=True)
+        fa = b.forward_args()
+        gen = torch.Generator().manual_seed(r["readout_seed"])
+        rx, rh = torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen)
+        dims = [(int(b.n_p[i]) + 1, int(b.n_c[i]) + 1) for i in range(len(b.n_c))]
+        rp_holder = {}
+
+        def prev_coords(m, fa):
+            if cfg.n_iter <= 1:
+                return fa["X"].clone()
+            from types import SimpleNamespace
+            c = SimpleNamespace(**{**vars(cfg), "n_iter": cfg.n_iter - 1})
+            with torch.no_grad():
+                return forward_emulated(sd, c, b, flavour=1)[0]
+
+        def edge_lists(m, X_prev, fa):
+            ctx, inter, _ = orc.build_edges(X_prev, fa["batch_id"], fa["segment_id"], fa["is_global"], cfg.intra_cutoff / cfg.coordinate_scale,
+                                            cfg.inter_cutoff / cfg.coordinate_scale)
+            return ctx, inter
+
+        def output_grads(X, Hh, pair):
+            dense = _dense_pair(pair, dims, H)
+            rp = torch.randn(dense.shape, generator=gen) * 0.1
+            rp_holder["loss"] = float((X * rx).sum() + (Hh * rh).sum() + (dense * rp).sum())
+            return rx, rh, torch.cat([rp[i, :n, :c].reshape(-1, H) for i, (n, c) in enumerate(dims)])
+        X_out, H_out, pair, pgrads, gH_in = train.training_step(model, fa, output_grads, prev_coords=prev_coords, edge_lists=edge_lists)
+        assert abs(rp_holder["loss"] - g["loss"]) < 1e-4 * abs(g["loss"]), (rp_holder["loss"], g["loss"])
+        gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+        n = 0
+        for k, ref in g["grads"].items():
+            if ref is None:
+                continue
+            err = float((pgrads[k] - ref).abs().max())
+            assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
+            n += 1
+        assert n >= 80

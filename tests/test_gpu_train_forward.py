@@ -185,3 +185,44 @@ def test_plus_training_forward_and_reverse_on_the_real_kernels():
     grads, dHin = bw.stack_backward_plus(w, tape, top, geo, edges, consts, case["dH_out"].cuda(), case["dX_out"].cuda(), case["dP_out"].cuda())
     torch.cuda.synchronize()
     check_stack(case, _cpu(grads), dHin.cpu(), TOL)
+
+
+def test_plus_training_step_on_the_gpu():
+    """train.training_step on the FABind+ layout with the real providers and kernels: parameter gradients of the unmodified FABind+
+    reference (tests/golden/grad_plus_*.pt)"""
+    from fabind_b200 import train
+    from fabind_b200.config import published_args_plus
+    from fabind_b200.plus import EfficientMCAttModel as PlusModel
+    from helpers import load_golden
+    from test_formulation_cpu import _dense_pair
+    for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_plus_*.pt"))):
+        g, r, b, sd, cfg = load_golden(path)
+        H = r["hidden"]
+        model = PlusModel(published_args_plus(), H, H, 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                          normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        model.return_pair = False
+        gen = torch.Generator().manual_seed(r["readout_seed"])
+        rx, rh = torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen)
+        dims = [(int(b.n_p[i]) + 1, int(b.n_c[i]) + 1) for i in range(len(b.n_c))]
+        seen = {}
+
+        def output_grads(X, Hh, pair):
+            dense = _dense_pair(pair.cpu(), dims, H)
+            rp = torch.randn(dense.shape, generator=gen) * 0.1
+            seen["loss"] = float((X.cpu() * rx).sum() + (Hh.cpu() * rh).sum() + (dense * rp).sum())
+            return rx.cuda(), rh.cuda(), torch.cat([rp[i, :n, :c].reshape(-1, H) for i, (n, c) in enumerate(dims)]).cuda()
+        out = train.training_step(model, b.to("cuda").forward_args(), output_grads)
+        torch.cuda.synchronize()
+        pgrads = out[3]
+        assert abs(seen["loss"] - g["loss"]) < 1e-3 * abs(g["loss"]), (seen["loss"], g["loss"])
+        gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+        n = 0
+        for k, ref in g["grads"].items():
+            if ref is None:
+                continue
+            err = float((pgrads[k].cpu() - ref).abs().max())
+            assert err < 1e-3 * float(ref.abs().max()) + 1e-5 * gmax, (k, err, float(ref.abs().max()))
+            n += 1
+        assert n >= 80
