@@ -86,13 +86,8 @@ def _gpu_edges(model, X_prev, fa):
     return ctx, inter
 
 
-def training_step(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, state_dict=None):
-    """model: fabind_b200.EfficientMCAttModel (v1 layout) or fabind_b200.plus.EfficientMCAttModel (FABind+ layout, eval-mode masks).
-    fa: the forward arguments (X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index, batched_complex_coord_LAS).
-    output_grads: v1  (X_out, H_out) -> (dL/dX_out, dL/dH_out);  FABind+  (X_out, H_out, pair rows [P,H]) -> (dL/dX, dL/dH, dL/dpair rows)
-    (caller node order; pair rows packed per complex as [Np', Nc'] blocks).
-    Returns (X_out, H_out[, pair rows], {parameter name: gradient}, dL/dH_in).  prev_coords / edge_lists: the two GPU providers
-    (replaceable by their specifications in CPU tests)."""
+def _forward_half(model, fa, prev_coords, edge_lists, state_dict=None):
+    """steps 1-3: everything up to the outputs; returns (X_out, H_out, pair rows or None, state for the reverse half)"""
     cfg = model._cfg
     H, L, flavour = cfg["hidden"], cfg["n_layers"], int(cfg.get("flavour", 0))
     dev = fa["H"].device
@@ -105,7 +100,7 @@ def training_step(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_li
     weights = slot_tensors(arena, H, L, flavour)
     consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,
                   xl=fa["batched_complex_coord_LAS"].reshape(-1, 3)[perm].to(torch.float32).contiguous())
-    Hin = fa["H"][perm].to(torch.float32).contiguous()
+    Hin = fa["H"].detach()[perm].to(torch.float32).contiguous()
     x_state = X_prev[:, 0][perm].to(torch.float32).contiguous()
     pair = None
     if flavour == 1:
@@ -116,23 +111,82 @@ def training_step(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_li
     X_out[perm, 0] = X_int.to(X_out.dtype)
     H_out = torch.empty(Hin.shape, dtype=fa["H"].dtype, device=dev)
     H_out[perm] = H_int.to(H_out.dtype)
-    og = output_grads(X_out, H_out, pair) if flavour == 1 else output_grads(X_out, H_out)
-    dX_int = (og[0][:, 0][perm].to(torch.float32) * moves[:, None]).contiguous()
-    dH_int = og[1][perm].to(torch.float32).contiguous()
+    state = dict(H=H, L=L, flavour=flavour, sd=sd, arena=arena, weights=weights, tape=tape, top=top, geo=geo, edges=edges, consts=consts,
+                 perm=perm, moves=moves, Hin_shape=Hin.shape)
+    return X_out, H_out, pair, state
+
+
+def _backward_half(st, gX, gH, gP=None):
+    """steps 5: output gradients (caller order) -> ({parameter name: gradient}, dL/dH_in)"""
+    perm, moves, flavour = st["perm"], st["moves"], st["flavour"]
+    dX_int = (gX[:, 0][perm].to(torch.float32) * moves[:, None]).contiguous()
+    dH_int = gH[perm].to(torch.float32).contiguous()
     if flavour == 1:
-        grads, dHin = bw.stack_backward_plus(weights, tape, top, geo, edges, consts, dH_int, dX_int, og[2].to(torch.float32).contiguous())
+        gP = torch.zeros(st["consts"]["n_pairs"], st["H"], dtype=torch.float32, device=dX_int.device) if gP is None else gP
+        grads, dHin = bw.stack_backward_plus(st["weights"], st["tape"], st["top"], st["geo"], st["edges"], st["consts"], dH_int, dX_int,
+                                             gP.to(torch.float32).contiguous())
     else:
-        grads, dHin = bw.stack_backward_v1(weights, tape, top, geo, edges, consts, dH_int, dX_int)
-    garena = torch.zeros_like(arena)
-    for name, r, c, off in slots(H, L, flavour):
+        grads, dHin = bw.stack_backward_v1(st["weights"], st["tape"], st["top"], st["geo"], st["edges"], st["consts"], dH_int, dX_int)
+    garena = torch.zeros_like(st["arena"])
+    for name, r, c, off in slots(st["H"], st["L"], flavour):
         if name in grads:
             garena[off:off + r * c] = grads[name].reshape(-1)
-    pgrads = arena_grads_to_state_dict(sd, garena, H, L, flavour)
-    gH_in = torch.empty_like(Hin)
+    pgrads = arena_grads_to_state_dict(st["sd"], garena, st["H"], st["L"], flavour)
+    gH_in = torch.empty(st["Hin_shape"], dtype=torch.float32, device=dX_int.device)
     gH_in[perm] = dHin
-    if flavour == 1:
+    return pgrads, gH_in
+
+
+def training_step(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, state_dict=None):
+    """model: fabind_b200.EfficientMCAttModel (v1 layout) or fabind_b200.plus.EfficientMCAttModel (FABind+ layout, eval-mode masks).
+    fa: the forward arguments (X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index, batched_complex_coord_LAS).
+    output_grads: v1  (X_out, H_out) -> (dL/dX_out, dL/dH_out);  FABind+  (X_out, H_out, pair rows [P,H]) -> (dL/dX, dL/dH, dL/dpair rows)
+    (caller node order; pair rows packed per complex as [Np', Nc'] blocks).
+    Returns (X_out, H_out[, pair rows], {parameter name: gradient}, dL/dH_in).  prev_coords / edge_lists: the two GPU providers
+    (replaceable by their specifications in CPU tests)."""
+    X_out, H_out, pair, st = _forward_half(model, fa, prev_coords, edge_lists, state_dict)
+    if st["flavour"] == 1:
+        gX, gH, gP = output_grads(X_out, H_out, pair)
+        pgrads, gH_in = _backward_half(st, gX, gH, gP)
         return X_out, H_out, pair, pgrads, gH_in
+    gX, gH = output_grads(X_out, H_out)
+    pgrads, gH_in = _backward_half(st, gX, gH)
     return X_out, H_out, pgrads, gH_in
+
+
+class _StackFunction(torch.autograd.Function):
+    """The differentiated last iteration as ONE autograd node: the reference's `loss.backward()` (main_fabind.py:380-401) reaches the
+    stack's parameters and the incoming node features through it; everything inside runs on the library's kernels."""
+
+    @staticmethod
+    def forward(ctx, model, fa, prev_coords, edge_lists, names, H_in, *params):
+        X_out, H_out, pair, st = _forward_half(model, fa, prev_coords, edge_lists, {n: p.detach() for n, p in zip(names, params)})
+        ctx.st, ctx.names, ctx.h_dtype = st, names, H_in.dtype
+        if pair is None:
+            return X_out, H_out
+        return X_out, H_out, pair
+
+    @staticmethod
+    def backward(ctx, gX, gH, gP=None):
+        # (autograd materialises undefined output gradients as zeros: gX / gH / gP are always tensors here)
+        pgrads, gH_in = _backward_half(ctx.st, gX, gH, gP)
+        out = [None, None, None, None, None, gH_in.to(ctx.h_dtype)]
+        for n, p_needs in zip(ctx.names, ctx.needs_input_grad[6:]):
+            out.append(pgrads[n] if p_needs else None)
+        return tuple(out)
+
+
+def forward_with_grad(model, fa, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges):
+    """`EfficientMCAttModel.forward` with autograd: returns (X, H[, pair rows]) attached to the graph, so an unchanged training loop
+    (`loss.backward()`, optimizer over `model.parameters()`) trains the drop-in module.  Buffers / non-float entries of the state_dict
+    are passed through untouched."""
+    named = [(n, p) for n, p in model.state_dict(keep_vars=True).items() if torch.is_floating_point(p)]
+    names = [n for n, _ in named]
+    out = _StackFunction.apply(model, fa, prev_coords, edge_lists, names, fa["H"], *[p for _, p in named])
+    X = fa["X"]
+    with torch.no_grad():
+        X.copy_(out[0].detach())                 # the reference updates the caller's X in place (att_model.py:236,245)
+    return out
 
 
 training_step_v1 = training_step

@@ -228,6 +228,7 @@ def arena_grads_to_state_dict(sd, arena_grad, hidden, n_layers, flavour=0):
     leaves = {k: v.detach().cpu().to(torch.float32).clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
     full = dict(sd)
     full.update(leaves)
-    arena = pack_state_dict(full, hidden, n_layers, flavour, differentiable=True)
-    arena.backward(arena_grad.detach().cpu().to(torch.float32).reshape(-1))
+    with torch.enable_grad():     # also callable from inside an autograd.Function's backward (grad mode is off there)
+        arena = pack_state_dict(full, hidden, n_layers, flavour, differentiable=True)
+        arena.backward(arena_grad.detach().cpu().to(torch.float32).reshape(-1))
     return {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}

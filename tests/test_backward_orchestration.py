@@ -713,3 +713,49 @@ def test_plus_training_step_assembly(monkeypatch):
             assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
             n += 1
         assert n >= 80
+
+
+def test_forward_with_grad_trains_the_drop_in_module(monkeypatch):
+    """train.forward_with_grad: an unchanged training loop (loss.backward() on the module's outputs) puts the UNMODIFIED reference's
+    gradients on the drop-in module's parameters and on the incoming node features (CPU: stand-ins + oracle providers)"""
+    from fabind_b200 import EfficientMCAttModel, backward as bw, train
+    from fabind_b200.config import published_args
+    from oracle import fabind_oracle as orc
+    _install_standins(monkeypatch, bw)
+    _install_forward_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
+    g, r, b, sd, cfg = load_golden(sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))[0])
+    H = r["hidden"]
+    model = EfficientMCAttModel(published_args(), H, H, 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                                normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    model.load_state_dict(sd, strict=True)
+    fa = b.forward_args()
+    fa["H"] = fa["H"].clone().requires_grad_(True)
+    gen = torch.Generator().manual_seed(r["readout_seed"])
+    rx, rh = torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen)
+
+    def prev_coords(m, fa):
+        c = orc.make_cfg(n_layers=cfg.n_layers, n_iter=cfg.n_iter - 1)
+        with torch.no_grad():
+            return orc.model_forward(sd, c, fa["X"], fa["H"].detach(), fa["batch_id"], fa["segment_id"], fa["mask"], fa["is_global"],
+                                     fa["compound_edge_index"], fa["LAS_edge_index"], fa["batched_complex_coord_LAS"])[0]
+
+    def edge_lists(m, X_prev, fa):
+        ctx, inter, _ = orc.build_edges(X_prev, fa["batch_id"], fa["segment_id"], fa["is_global"], cfg.intra_cutoff / cfg.coordinate_scale,
+                                        cfg.inter_cutoff / cfg.coordinate_scale)
+        return ctx, inter
+    X, Hh = train.forward_with_grad(model, fa, prev_coords=prev_coords, edge_lists=edge_lists)
+    loss = (X * rx).sum() + (Hh * rh).sum()
+    assert abs(float(loss) - g["loss"]) < 1e-4 * abs(g["loss"])
+    loss.backward()
+    params = dict(model.named_parameters())
+    gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+    n = 0
+    for k, ref in g["grads"].items():
+        if ref is None:
+            continue
+        err = float((params[k].grad - ref).abs().max())
+        assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
+        n += 1
+    assert n >= 80 and fa["H"].grad is not None and float(fa["H"].grad.abs().max()) > 0

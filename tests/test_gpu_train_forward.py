@@ -226,3 +226,31 @@ def test_plus_training_step_on_the_gpu():
             assert err < 1e-3 * float(ref.abs().max()) + 1e-5 * gmax, (k, err, float(ref.abs().max()))
             n += 1
         assert n >= 80
+
+
+def test_forward_with_grad_on_the_gpu():
+    """an unchanged training loop on the drop-in module: loss.backward() through train.forward_with_grad puts the unmodified
+    reference's gradients on the module's parameters (real providers, real kernels)"""
+    from fabind_b200 import EfficientMCAttModel, train
+    from fabind_b200.config import published_args
+    from helpers import load_golden
+    g, r, b, sd, cfg = load_golden(sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))[0])
+    H = r["hidden"]
+    model = EfficientMCAttModel(published_args(), H, H, 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                                normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    gen = torch.Generator().manual_seed(r["readout_seed"])
+    rx, rh = torch.randn(b.X.shape, generator=gen).cuda(), torch.randn(b.H.shape, generator=gen).cuda()
+    fa = b.to("cuda").forward_args()
+    X, Hh = train.forward_with_grad(model, fa)
+    loss = (X * rx).sum() + (Hh * rh).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - g["loss"]) < 1e-3 * abs(g["loss"])
+    params = dict(model.named_parameters())
+    gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+    for k, ref in g["grads"].items():
+        if ref is not None:
+            err = float((params[k].grad.cpu() - ref).abs().max())
+            assert err < 1e-3 * float(ref.abs().max()) + 1e-5 * gmax, (k, err)
