@@ -162,6 +162,7 @@ class _StackFunction(torch.autograd.Function):
     def forward(ctx, model, fa, prev_coords, edge_lists, names, H_in, *params):
         X_out, H_out, pair, st = _forward_half(model, fa, prev_coords, edge_lists, {n: p.detach() for n, p in zip(names, params)})
         ctx.st, ctx.names, ctx.h_dtype = st, names, H_in.dtype
+        ctx.pmeta = [(p.device, p.dtype) for p in params]
         if pair is None:
             return X_out, H_out
         return X_out, H_out, pair
@@ -171,8 +172,8 @@ class _StackFunction(torch.autograd.Function):
         # (autograd materialises undefined output gradients as zeros: gX / gH / gP are always tensors here)
         pgrads, gH_in = _backward_half(ctx.st, gX, gH, gP)
         out = [None, None, None, None, None, gH_in.to(ctx.h_dtype)]
-        for n, p_needs in zip(ctx.names, ctx.needs_input_grad[6:]):
-            out.append(pgrads[n] if p_needs else None)
+        for n, (dev, dt), p_needs in zip(ctx.names, ctx.pmeta, ctx.needs_input_grad[6:]):
+            out.append(pgrads[n].to(dev, dt) if p_needs else None)      # the packer's chain rule runs on the host
         return tuple(out)
 
 
