@@ -2,7 +2,7 @@
 
 Same constructor and forward signatures, same state_dict keys; the forward pass is one call into
 libfabind_b200 (hand-written sm_100a kernels).  Inference semantics (eval mode, refine='refine_coord',
-att_model.py:227-245); the training path (dropout, backward) is not built yet and raises.
+att_model.py:227-245); the training path lives in fabind_b200/train.py and is opt-in (see forward()).
 """
 import ctypes as C
 import os
@@ -104,8 +104,17 @@ class EfficientMCAttModel(nn.Module):
     def forward(self, X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index,
                 batched_complex_coord_LAS, LAS_mask=None):
         if self.training:
-            raise NotImplementedError("fabind_b200: the training path (dropout + backward kernels) is not built yet; "
-                                      "call .eval()")
+            # The training path (fabind_b200/train.py: reverse-pass kernels, training-mode forward, one autograd node) is validated
+            # on the CPU against the reference's parameter gradients and its reverse kernels on a B200; its forward-side kernels have
+            # not run on a GPU yet, so it is opt-in until the gated tests (tests/test_gpu_train_forward.py) are green.  No dropout.
+            if torch.is_grad_enabled() and os.environ.get("FABIND_B200_EXPERIMENTAL_TRAIN") == "1":
+                from . import train
+                return train.forward_with_grad(self, dict(X=X, H=H, batch_id=batch_id, segment_id=segment_id, mask=mask,
+                                                          is_global=is_global, compound_edge_index=compound_edge_index,
+                                                          LAS_edge_index=LAS_edge_index,
+                                                          batched_complex_coord_LAS=batched_complex_coord_LAS, LAS_mask=LAS_mask))
+            raise NotImplementedError("fabind_b200: train() mode is opt-in (FABIND_B200_EXPERIMENTAL_TRAIN=1, see "
+                                      "fabind_b200/train.py) until its forward-side kernels have run on a GPU; call .eval()")
         if self.precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         with torch.no_grad():

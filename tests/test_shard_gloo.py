@@ -131,3 +131,84 @@ def test_gradient_allreduce_world2():
         assert n == 35 + 11 + 9
         assert torch.equal(grads[0], torch.full((7, 5), 1.5)) and torch.equal(grads[1], torch.arange(11.0) * 1.5)
         assert torch.equal(grads[2], torch.full((3, 3), 0.5)) and grads[3] is None
+
+
+def _train_case(seed):
+    """one small batch + a v1 module with deterministic weights + fixed output gradients"""
+    from fabind_b200 import EfficientMCAttModel
+    from fabind_b200.config import published_args
+    b = make_batch(n_complexes=2, seed=seed, n_c_range=(5, 10), n_p_range=(14, 24), embed=HID)
+    m = EfficientMCAttModel(published_args(), HID, HID, 1, n_layers=L, n_iter=IT, normalize_coord=lambda x: x / 5.0,
+                            unnormalize_coord=lambda x: x * 5.0)
+    m.load_state_dict(_weights(), strict=True)
+    g = torch.Generator().manual_seed(seed + 100)
+    return b, m, torch.randn(b.X.shape, generator=g), torch.randn(b.H.shape, generator=g)
+
+
+def _rank_gradients(seed):
+    """parameter gradients of one rank's batch through train.training_step (kernel wrappers -> torch stand-ins, providers -> oracle)"""
+    from _pytest.monkeypatch import MonkeyPatch
+    from fabind_b200 import backward as bw, train
+    import test_backward_orchestration as T
+    mp_ = MonkeyPatch()
+    T._install_standins(mp_, bw)
+    T._install_forward_standins(mp_, bw)
+    mp_.setattr(bw, "pair_bias_gate_bwd", T._gate_bwd_standin)
+    mp_.setattr(bw, "pair_outer_bwd", T._outer_bwd_standin)
+    b, m, rx, rh = _train_case(seed)
+    sd = _weights()
+    cfg = orc.make_cfg(n_layers=L, n_iter=IT)
+
+    def prev_coords(model, fa):
+        with torch.no_grad():
+            return orc.model_forward(sd, orc.make_cfg(n_layers=L, n_iter=IT - 1), fa["X"], fa["H"], fa["batch_id"], fa["segment_id"], fa["mask"],
+                                     fa["is_global"], fa["compound_edge_index"], fa["LAS_edge_index"], fa["batched_complex_coord_LAS"])[0]
+
+    def edge_lists(model, X_prev, fa):
+        ctx, inter, _ = orc.build_edges(X_prev, fa["batch_id"], fa["segment_id"], fa["is_global"], cfg.intra_cutoff / cfg.coordinate_scale,
+                                        cfg.inter_cutoff / cfg.coordinate_scale)
+        return ctx, inter
+    try:
+        _, _, pg, _ = train.training_step(m, b.forward_args(), lambda X, H: (rx, rh), prev_coords=prev_coords, edge_lists=edge_lists)
+    finally:
+        mp_.undo()
+    return m, pg
+
+
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fabind_b200 import train
+        m, pg = _rank_gradients(20 + rank)
+        train.apply_gradients(m, pg, average=True)
+        q.put((rank, {k: p.grad.numpy().copy() for k, p in m.named_parameters()}))   # numpy: no shared-memory handles that die with the worker
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_data_parallel_training_step_world2():
+    """config 5's structure on CPU: every rank differentiates ITS complexes (train.training_step), one flat all-reduce averages the
+    gradients (train.apply_gradients); every rank ends with the mean of the per-rank gradients, unused parameters as zeros"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = [_rank_gradients(20 + r)[1] for r in range(2)]
+    gmax = max(float((0.5 * (ref[0][k] + ref[1][k])).abs().max()) for k in ref[0])
+    for rank, grads in res:
+        for k, g in grads.items():
+            want = 0.5 * (ref[0][k] + ref[1][k])
+            # (the workers run with 2 threads, the parent with all: summation order differs in the last bits)
+            assert float((torch.from_numpy(g) - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-6 * gmax, (rank, k)
+    assert any(float(abs(g).max()) == 0.0 for g in res[0][1].values())          # att_i.inter_layer.*: never used, zero gradient
