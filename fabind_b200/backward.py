@@ -22,6 +22,30 @@ from .runtime import current_stream_ptr
 
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 
+# GEMMs of the training path: "fp32" = the FFMA parity kernel (what the gradient-parity tests pin); "bf16" = the tcgen05 kernels of
+# the inference path (bf16 operands, fp32 accumulation and outputs) for the forward / data-gradient GEMMs, and for the weight
+# gradients dW = dY^T X as a GEMM over transposed bf16 copies (reduction over the rows, padded to a multiple of 64).  The casts and
+# transposed copies are torch copies (no arithmetic).  Not validated on a GPU yet: default "fp32".
+PRECISION = "fp32"
+WGRAD_TC_MIN_ROWS = 2048
+
+
+def _gemm_call(A, W, bias, act, res, M, N, K):
+    """C[M,N] = act(A W^T + bias) + res through fb_gemm in the current PRECISION; A [M,K], W [N,K] fp32 in, fp32 out"""
+    g = _lib.GemmParams()
+    bf16 = PRECISION == "bf16" and K % 8 == 0
+    if bf16:
+        A, W = A.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous()
+    g.A, g.lda, g.K1 = A.data_ptr(), K, K
+    g.W, g.bias, g.act = W.data_ptr(), (bias.data_ptr() if bias is not None else None), act
+    g.M, g.N, g.bf16_mode, g.force_simt = M, N, int(bf16), 0
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    g.C, g.ldc = out.data_ptr(), N
+    if res is not None:
+        g.res, g.ldres = res.data_ptr(), res.shape[1]
+    _lib.check(_lib.lib().fb_gemm(C.byref(g), _st(A)), "fb_gemm")
+    return out
+
 
 def _chk(t, dtype=torch.float32):
     if not t.is_cuda:
@@ -101,6 +125,20 @@ def gemm_wgrad(dY, X, out=None):
     _chk(dY), _chk(X)
     M, N = dY.shape
     K = X.shape[1]
+    if PRECISION == "bf16" and M >= WGRAD_TC_MIN_ROWS:
+        Mp = (M + 63) // 64 * 64
+        At = torch.zeros(N, Mp, dtype=torch.bfloat16, device=dY.device)
+        Wt = torch.zeros(K, Mp, dtype=torch.bfloat16, device=dY.device)
+        At[:, :M].copy_(dY.t())
+        Wt[:, :M].copy_(X.t())
+        g = _lib.GemmParams()
+        g.A, g.lda, g.K1 = At.data_ptr(), Mp, Mp
+        g.W, g.bias, g.act = Wt.data_ptr(), None, ACT_NONE
+        g.M, g.N, g.bf16_mode, g.force_simt = N, K, 1, 0
+        r = torch.empty(N, K, dtype=torch.float32, device=dY.device)
+        g.C, g.ldc = r.data_ptr(), K
+        _lib.check(_lib.lib().fb_gemm(C.byref(g), _st(dY)), "fb_gemm")
+        return r if out is None else vec_add_(out, r)
     if out is None:
         out = torch.zeros(N, K, dtype=torch.float32, device=dY.device)
     _lib.check(_lib.lib().fb_gemm_wgrad(dY.data_ptr(), N, X.data_ptr(), K, M, N, K, out.data_ptr(), K, _st(dY)), "fb_gemm_wgrad")
@@ -111,15 +149,7 @@ def gemm_dgrad(dY, Wt):
     """dX = dY W, with Wt = W^T stored [K_in, N_out] contiguous (the 'weight' of the data-gradient GEMM); fp32 SIMT path"""
     _chk(dY), _chk(Wt)
     M, N = dY.shape
-    K = Wt.shape[0]
-    g = _lib.GemmParams()
-    g.A, g.lda, g.K1 = dY.data_ptr(), N, N
-    g.W, g.bias, g.act = Wt.data_ptr(), None, ACT_NONE
-    g.M, g.N, g.bf16_mode, g.force_simt = M, K, 0, 0
-    out = torch.empty(M, K, dtype=torch.float32, device=dY.device)
-    g.C, g.ldc = out.data_ptr(), K
-    _lib.check(_lib.lib().fb_gemm(C.byref(g), _st(dY)), "fb_gemm")
-    return out
+    return _gemm_call(dY, Wt, None, ACT_NONE, None, M, Wt.shape[0], N)
 
 
 def coord_step_bwd(x, row, col, s, step, cnt, cmax, dx_new):
@@ -451,18 +481,11 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
 def linear(A, W, bias=None, act=ACT_NONE, res=None):
     """act(A W^T + bias) + res  (fp32, fb_gemm)"""
     _chk(A), _chk(W)
-    M, K = A.shape
-    N = W.shape[0]
-    g = _lib.GemmParams()
-    g.A, g.lda, g.K1 = A.data_ptr(), K, K
-    g.W, g.bias, g.act = W.data_ptr(), (_chk(bias).data_ptr() if bias is not None else None), act
-    g.M, g.N, g.bf16_mode, g.force_simt = M, N, 0, 0
-    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
-    g.C, g.ldc = out.data_ptr(), N
+    if bias is not None:
+        _chk(bias)
     if res is not None:
-        g.res, g.ldres = _chk(res).data_ptr(), res.shape[1]
-    _lib.check(_lib.lib().fb_gemm(C.byref(g), _st(A)), "fb_gemm")
-    return out
+        _chk(res)
+    return _gemm_call(A, W, bias, act, res, A.shape[0], W.shape[0], A.shape[1])
 
 
 def radial_fwd(x, row, col, node_cplx, B):

@@ -29,8 +29,10 @@ def main():
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="precision of the no_grad iterations")
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "bf16"], help="GEMMs of the differentiated iteration (backward.PRECISION)")
     a = ap.parse_args()
-    from fabind_b200 import EfficientMCAttModel, train
+    from fabind_b200 import EfficientMCAttModel, train, backward
+    backward.PRECISION = a.gemm
     from fabind_b200.config import published_args
     from fabind_b200.synthetic import make_batch, randomize_coord_heads
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -75,7 +77,7 @@ def main():
         print(json.dumps(dict(metric="training step (fwd + bwd + gradient all-reduce), v1 stack", n_gpus=world, global_batch=a.batch * world,
                               ms_step=round(ms, 2), ms_forward_backward=round(float(t[0]), 2), ms_grads_allreduce=round(float(t[1]), 2),
                               complexes_per_s=round(a.batch * world / (ms / 1e3), 1), hidden=a.hidden, layers=a.layers, iters=a.iters,
-                              no_grad_iterations=a.precision, reverse_pass="fp32 SIMT (first correct version)",
+                              no_grad_iterations=a.precision, reverse_pass="fp32 SIMT (first correct version)" if a.gemm == "fp32" else "tcgen05 GEMMs (bf16 operands), SIMT scatter kernels",
                               note="host-side packing / chain rule of the weight arena is inside ms_forward_backward")))
     if world > 1:
         dist.destroy_process_group()

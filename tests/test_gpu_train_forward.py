@@ -254,3 +254,32 @@ def test_forward_with_grad_on_the_gpu():
         if ref is not None:
             err = float((params[k].grad.cpu() - ref).abs().max())
             assert err < 1e-3 * float(ref.abs().max()) + 1e-5 * gmax, (k, err)
+
+
+def test_training_step_bf16_gemms_close_to_fp32():
+    """PRECISION = 'bf16': forward / data-gradient GEMMs on the tcgen05 kernels, weight gradients as a tcgen05 GEMM over transposed
+    bf16 copies; gradients stay within bf16 distance of the fp32 parity path (the reference has no bf16 mode: own bound, 5 % of scale)"""
+    from fabind_b200 import EfficientMCAttModel, backward as bw, train
+    from fabind_b200.config import published_args
+    from fabind_b200.synthetic import make_batch
+    H, L = 128, 2
+    torch.manual_seed(0)
+    model = EfficientMCAttModel(published_args(), H, H, 1, n_layers=L, n_iter=2, normalize_coord=lambda x: x / 5.0,
+                                unnormalize_coord=lambda x: x * 5.0).cuda().eval()
+    b = make_batch(n_complexes=4, seed=2, embed=H, n_c_range=(20, 40), n_p_range=(120, 200)).to("cuda")
+    g = torch.Generator().manual_seed(3)
+    rx, rh = torch.randn(b.X.shape, generator=g).cuda(), torch.randn(b.H.shape, generator=g).cuda()
+    res = {}
+    X0 = b.X.clone()
+    for prec in ("fp32", "bf16"):
+        bw.PRECISION = prec
+        try:
+            fa = b.forward_args()
+            fa["X"] = X0.clone()
+            res[prec] = train.training_step(model, fa, lambda X, Hh: (rx, rh))[2]
+        finally:
+            bw.PRECISION = "fp32"
+    gmax = max(float(v.abs().max()) for v in res["fp32"].values())
+    for k, ref in res["fp32"].items():
+        err = float((res["bf16"][k] - ref).abs().max())
+        assert err < 5e-2 * float(ref.abs().max()) + 5e-3 * gmax, (k, err, float(ref.abs().max()))
