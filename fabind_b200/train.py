@@ -96,7 +96,7 @@ def _forward_half(model, fa, prev_coords, edge_lists, state_dict=None):
     ctx, inter = edge_lists(model, X_prev, fa)
     lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
     geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
-    arena = pack_state_dict(sd, H, L, flavour).to(dev)
+    arena = pack_state_dict(sd, H, L, flavour, device=dev)
     weights = slot_tensors(arena, H, L, flavour)
     consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,
                   xl=fa["batched_complex_coord_LAS"].reshape(-1, 3)[perm].to(torch.float32).contiguous())
@@ -131,7 +131,7 @@ def _backward_half(st, gX, gH, gP=None):
     for name, r, c, off in slots(st["H"], st["L"], flavour):
         if name in grads:
             garena[off:off + r * c] = grads[name].reshape(-1)
-    pgrads = arena_grads_to_state_dict(st["sd"], garena, st["H"], st["L"], flavour)
+    pgrads = arena_grads_to_state_dict(st["sd"], garena, st["H"], st["L"], flavour, device=garena.device)
     gH_in = torch.empty(st["Hin_shape"], dtype=torch.float32, device=dX_int.device)
     gH_in[perm] = dHin
     return pgrads, gH_in

@@ -192,14 +192,20 @@ def _att_plus(sd, p, H):
     return d
 
 
-def pack_state_dict(sd, hidden, n_layers, flavour=0, differentiable=False):
+def pack_state_dict(sd, hidden, n_layers, flavour=0, differentiable=False, device="cpu"):
     """Returns the fp32 arena (CPU tensor) for a state_dict with the reference's key names
     (flavour 0: FABind v1 layout, 1: FABind+ layout).  differentiable=True keeps the autograd graph from the reference
     parameters to the arena (every derivation is a torch expression): gradients w.r.t. arena slots map back to reference
     parameters by the chain rule -- how a training path in this formulation returns `state_dict`-shaped gradients
     (tests/test_formulation_cpu.py::test_refactored_formulation_gradients)."""
-    sd = {k: (v.cpu() if differentiable else v.detach().cpu()) for k, v in sd.items()}
+    dev = torch.device(device)
+    sd = {k: (v.to(dev) if differentiable else v.detach().to(dev)) for k, v in sd.items()}
     l = _lib.lib()
+    with torch.device(dev):      # every factory call of the derivations below lands on `device` (training re-packs on the GPU every step)
+        return _pack_on_device(sd, l, hidden, n_layers, flavour)
+
+
+def _pack_on_device(sd, l, hidden, n_layers, flavour):
     arena = torch.zeros(l.fb_weight_arena_elems_f(hidden, n_layers, flavour), dtype=torch.float32)
     gcl, att = (_gcl_plus, _att_plus) if flavour == 1 else (_gcl, _att)
     groups = {"": _top(sd, hidden, 0 if flavour == 1 else n_layers)}
@@ -219,16 +225,18 @@ def pack_state_dict(sd, hidden, n_layers, flavour=0, differentiable=False):
     return arena
 
 
-def arena_grads_to_state_dict(sd, arena_grad, hidden, n_layers, flavour=0):
+def arena_grads_to_state_dict(sd, arena_grad, hidden, n_layers, flavour=0, device="cpu"):
     """Chain rule of the packer: gradient w.r.t. the flat weight arena (what backward kernels of this formulation produce:
     hoisted first Linears, folded LayerNorms, collapsed pair-bias vector, stacked projections) -> gradients keyed and shaped
     like the reference `state_dict` (what an optimizer over the drop-in modules' parameters consumes).  Parameters the
     formulation never reads (`att_i.inter_layer.*` of the v1 layout, unused in the reference too) come back as zeros, which is
-    what the flat gradient all-reduce (`shard.allreduce_gradients`) expects.  Host-side, a few ms; float32 like the arena."""
-    leaves = {k: v.detach().cpu().to(torch.float32).clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    what the flat gradient all-reduce (`shard.allreduce_gradients`) expects.  float32 like the arena.  On the CPU this costs seconds at
+    the published size (float64 derivations, 28 M arena elements); the training step runs it on the GPU (`device=`)."""
+    dev = torch.device(device)
+    leaves = {k: v.detach().to(dev, torch.float32).clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
     full = dict(sd)
     full.update(leaves)
     with torch.enable_grad():     # also callable from inside an autograd.Function's backward (grad mode is off there)
-        arena = pack_state_dict(full, hidden, n_layers, flavour, differentiable=True)
-        arena.backward(arena_grad.detach().cpu().to(torch.float32).reshape(-1))
+        arena = pack_state_dict(full, hidden, n_layers, flavour, differentiable=True, device=dev)
+        arena.backward(arena_grad.detach().to(dev, torch.float32).reshape(-1))
     return {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
