@@ -1,6 +1,6 @@
 """A/B of one environment knob of the library on the bench workload (development aid): runs the forward in two
 subprocesses (knob = 0 / 1), prints per-forward device times and the largest difference of the outputs.
-    python scripts/dev/ab_probe.py FB_TC3_WIDE [B]"""
+    python scripts/dev/ab_probe.py FB_PB_FOLD [B]        (any 0/1 environment knob of the library)"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "--child":
