@@ -17,7 +17,6 @@ wrappers and the two GPU providers (earlier iterations, graph builder) replaced 
 (tests/test_backward_orchestration.py::test_training_step_assembly).  It has not run on a GPU yet (gated test in
 tests/test_gpu_train_forward.py), so `EfficientMCAttModel.forward` in train() mode still raises instead of routing here.
 """
-import numpy as np
 import torch
 
 from . import backward as bw
