@@ -8,7 +8,7 @@ csrc/backward.cu plus fb_gemm for the data-gradient GEMMs (`dX = dY W` on a tran
 device memory here; there is no torch arithmetic on the path and no fallback: CPU tensors raise.
 
 Status (round 1): the v1 reverse kernels, `gcl_backward` / `att_backward` / `las_bwd` and `stack_backward_v1` are parity-green on a
-B200 against the specification's arena gradient (tests/test_gpu_backward.py, tests/test_gpu_backward_att.py).  Written after the GPU
+B200 against the specification's arena gradient (tests/test_gpu_train_reverse.py, tests/test_gpu_train_reverse_att.py).  Written after the GPU
 budget was spent, validated on the CPU only (every kernel wrapper swapped for its torch definition,
 tests/test_backward_orchestration.py), GPU tests gated behind FB_EXPERIMENTAL=1 (tests/test_gpu_train_forward.py): the training-mode
 forward of both layouts (`stack_forward_train_v1/plus`), the FABind+ reverse pass (`stack_backward_plus`) and the assembled step

@@ -284,7 +284,7 @@ int32_t fb_radial_bwd(const float* x, const int32_t* row, const int32_t* col, in
 int32_t fb_las_bwd(const float* x, const float* xref, const int32_t* a_idx, const int32_t* b_idx, int32_t E, const float* acc,
                    float step_size, float lcl, const float* dx_new, float* dx, void* stream);
 /* -- second group: MC_Att_L reverse (row attention, interfacial attention, pair path); fabind_b200/backward.py::att_backward and
- *    stack_backward_v1 orchestrate them (GPU parity: tests/test_gpu_backward_att.py) -- */
+ *    stack_backward_v1 orchestrate them (GPU parity: tests/test_gpu_train_reverse_att.py) -- */
 /* out[m] = sum_n A[m,n] B[m,n] */
 int32_t fb_rowdot2(const float* A, int32_t lda, const float* B, int32_t ldb, int32_t M, int32_t N, float* out, void* stream);
 /* mode 0: A[m,:] *= u[m];  mode 1: A[m,n] += u[m] v[n]  (the rank-1 radial terms of linear_kv, egnn.py:203-205) */

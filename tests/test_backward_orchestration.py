@@ -183,7 +183,7 @@ def check_att(case, dh, dx, grads, dPB_p, dPB_c, dP0, tol):
         ref = G["att0." + k].reshape(-1)
         # absolute floor: the gradient of the softmax-shift constant pt_c is exactly zero in real arithmetic (sum of dlogit over a row)
         err = float((v.reshape(-1) - ref).abs().max())
-        assert err < tol * float(ref.abs().max()) + 1e-2 * tol * gmax, (k, err, float(ref.abs().max()))
+        assert err < tol * float(ref.abs().max()) + 5e-2 * tol * gmax, (k, err, float(ref.abs().max()))
 
 
 def att_case(ex, dh_up, dx_up):
