@@ -759,3 +759,56 @@ def test_forward_with_grad_trains_the_drop_in_module(monkeypatch):
         assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
         n += 1
     assert n >= 80 and fa["H"].grad is not None and float(fa["H"].grad.abs().max()) > 0
+
+
+class _MarshalCheckLib:
+    """stands in for the loaded library: every call is checked against the REAL ctypes prototype (argument count, convertibility of
+    each argument) and returns 0 without touching memory -- catches marshalling mistakes of the Python wrappers without a GPU"""
+
+    def __init__(self, real):
+        self._real, self.calls = real, {}
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        argtypes = fn.argtypes
+
+        def call(*args):
+            assert len(args) == len(argtypes), f"{name}: {len(args)} arguments for {len(argtypes)} parameters"
+            for i, (a, t) in enumerate(zip(args, argtypes)):
+                try:
+                    t.from_param(a)
+                except Exception as e:          # noqa: BLE001
+                    raise AssertionError(f"{name}: argument {i} ({type(a).__name__}) does not convert to {t.__name__}: {e}")
+            self.calls[name] = self.calls.get(name, 0) + 1
+            return 0
+        return call
+
+
+def test_kernel_wrappers_marshal_their_arguments(monkeypatch):
+    """the REAL wrappers of fabind_b200/backward.py (no stand-ins) over a library double that validates every call against the ctypes
+    prototypes: the training-mode forward and the reverse pass of both layouts issue well-formed calls for every entry point they use"""
+    import ctypes
+    from fabind_b200 import _lib, backward as bw
+    v1 = stack_case(sorted(glob.glob(os.path.join(GOLDEN_DIR, "grad_v1_*.pt")))[0])      # (built with the real library: slot tables)
+    pl = plus_stack_case()
+    fake = _MarshalCheckLib(_lib.lib())
+    monkeypatch.setattr(_lib, "lib", lambda: fake)
+    monkeypatch.setattr(bw, "_chk", lambda t, dtype=torch.float32: (_ for _ in ()).throw(AssertionError(f"dtype {t.dtype} != {dtype}"))
+                        if t.dtype != dtype or not t.is_contiguous() else t)
+    monkeypatch.setattr(bw, "_st", lambda t: ctypes.c_void_p(0))
+    X, Hh, tape, top = bw.stack_forward_train_v1(v1["weights"], v1["top"]["Hin"], v1["x_state"], v1["moves"], v1["geo"], v1["edges"], v1["consts"],
+                                                 v1["L"])
+    bw.stack_backward_v1(v1["weights"], v1["tape"], v1["top"], v1["geo"], v1["edges"], v1["consts"], v1["dH_out"], v1["dX_out"])
+    pl["consts"]["n_pairs"] = int(pl["dP_out"].shape[0])
+    for layer in pl["tape"]:
+        layer[1]["acr"] = tuple(layer[1]["acr"])
+    # the forward double leaves outputs uninitialised; ac_r is read back on the host, keep it finite
+    bw.stack_forward_train_plus(pl["weights"], pl["top"]["Hin"], pl["x_state"], pl["moves"], pl["geo"], pl["edges"], pl["consts"], len(pl["tape"]))
+    bw.stack_backward_plus(pl["weights"], pl["tape"], pl["top"], pl["geo"], pl["edges"], pl["consts"], pl["dH_out"], pl["dX_out"], pl["dP_out"])
+    used = set(fake.calls)
+    expected = {"fb_gemm", "fb_act_fwd", "fb_act_bwd", "fb_outer_act_bwd", "fb_colsum", "fb_rowdot", "fb_rowdot2", "fb_rows_update", "fb_vec_op",
+                "fb_scatter_add_rows", "fb_gather_add_rows", "fb_gemm_wgrad", "fb_coord_step_bwd", "fb_radial_bwd", "fb_las_bwd",
+                "fb_softmax_seg_bwd", "fb_row_attention_bwd", "fb_pair_bias_gate_bwd", "fb_pair_outer_bwd", "fb_radial_fwd", "fb_coord_apply",
+                "fb_softmax_seg_fwd", "fb_las_acc", "fb_pair_outer_fwd", "fb_pair_bias_gate_fwd", "fb_row_attention_fwd", "fb_layernorm",
+                "fb_layernorm_bwd", "fb_row_stats", "fb_row_stats_bwd", "fb_folded_stats_fwd", "fb_folded_stats_bwd"}
+    assert expected <= used, expected - used
