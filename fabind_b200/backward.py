@@ -329,7 +329,8 @@ def row_attention_bwd(geo, q_is_prot, Q, G, K, V, PB, dO, dQ, dG, dK, dV):
     dPB = torch.zeros_like(PB)
     do = dO.data_ptr() - (4 * Nc * dO.shape[1] if qs else 0)
     _lib.check(_lib.lib().fb_row_attention_bwd(geo["c_off"].data_ptr(), geo["p_off"].data_ptr(), geo["pair_base"].data_ptr(), geo["B"],
-                                               int(qs), geo["max_c"] if qs else geo["max_p"], q, ldq, g, ldg, k, ldk, v, ldv,
+                                               int(qs), geo["max_p"] if qs else geo["max_c"], geo["max_c"] if qs else geo["max_p"], q, ldq,
+                                               g, ldg, k, ldk, v, ldv,
                                                PB.data_ptr(), do, dO.shape[1], dq, lddq, dg, lddg, dk, lddk, dv, lddv, dPB.data_ptr(),
                                                _st(dO)), "fb_row_attention_bwd")
     return dPB

@@ -428,6 +428,87 @@ __global__ void __launch_bounds__(RB_WARPS * 32) row_attention_bwd_kernel(
   }
 }
 
+// Same reverse for long key lists (n_k > RB_MAXK, e.g. whole proteins in the pocket stage): keys / values are read from global
+// memory (L2-resident: <= 1500 x 128 floats per side and complex), dK / dV accumulate with global atomics into buffers the caller
+// zeroed; one warp per query, grid = (complex, head, query tile).  n_k <= RBB_MAXK.
+constexpr int RBB_MAXK = 2048;
+__global__ void __launch_bounds__(RB_WARPS * 32) row_attention_bwd_big_kernel(
+    const int* __restrict__ c_off, const int* __restrict__ p_off, const int* __restrict__ pair_base, int q_is_prot,
+    const float* __restrict__ Q, int ldq, const float* __restrict__ G, int ldg, const float* __restrict__ Kb, int ldk,
+    const float* __restrict__ Vb, int ldv, const float* __restrict__ PB, const float* __restrict__ dO, int ldo,
+    float* __restrict__ dQ, int lddq, float* __restrict__ dG, int lddg, float* __restrict__ dK, int lddk,
+    float* __restrict__ dV, int lddv, float* __restrict__ dPB) {
+  pdl_entry();
+  extern __shared__ float rb_smem[];
+  const int b = blockIdx.x, head = blockIdx.y;
+  const int c_lo = c_off[b], nc1 = c_off[b + 1] - c_lo, p_lo = p_off[b], np1 = p_off[b + 1] - p_lo;
+  const int n_q = q_is_prot ? np1 : nc1, n_k = q_is_prot ? nc1 : np1;
+  const int q_lo = q_is_prot ? p_lo : c_lo, k_lo = q_is_prot ? c_lo : p_lo;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ql = blockIdx.z * RB_WARPS + warp;
+  if (ql >= n_q) return;                                         // warp-uniform; no block-level barrier below
+  float* pa = rb_smem + warp * (2 * RBB_MAXK + 64);
+  float* pd = pa + RBB_MAXK;
+  float* wq = pd + RBB_MAXK;
+  float* wdo = wq + 32;
+  const float scale = 0.17677669529663687f;
+  const int qn = q_lo + ql;
+  const float qd = Q[(size_t)qn * ldq + head * 32 + lane] * scale;
+  const float gd = G[(size_t)qn * ldg + head * 32 + lane];
+  const float sg = 1.0f / (1.0f + expf(-gd));
+  const float dod = dO[(size_t)qn * ldo + head * 32 + lane];
+  const float do_d = dod * sg;
+  wq[lane] = qd;
+  wdo[lane] = do_d;
+  __syncwarp();
+  const size_t pb0 = (size_t)pair_base[b];
+  float mx = -INFINITY;
+  for (int j = lane; j < n_k; j += 32) {
+    const float* kr = Kb + (size_t)(k_lo + j) * ldk + head * 32;
+    float sc = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) sc = fmaf(wq[d], kr[d], sc);
+    const size_t pair = pb0 + (q_is_prot ? ((size_t)ql * nc1 + j) : ((size_t)j * nc1 + ql));
+    sc += PB[pair * 4 + head];
+    pa[j] = sc;
+    mx = fmaxf(mx, sc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < n_k; j += 32) { const float e = expf(pa[j] - mx); pa[j] = e; sum += e; }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  float dsum = 0.f;
+  for (int j = lane; j < n_k; j += 32) {
+    const float* vr = Vb + (size_t)(k_lo + j) * ldv + head * 32;
+    const float a = pa[j] * inv;
+    float da = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) da = fmaf(wdo[d], vr[d], da);
+    pa[j] = a;
+    pd[j] = da;
+    dsum = fmaf(a, da, dsum);
+  }
+  dsum = warp_sum(dsum);
+  for (int j = lane; j < n_k; j += 32) {
+    const float dl = pa[j] * (pd[j] - dsum);
+    pd[j] = dl;
+    const size_t pair = pb0 + (q_is_prot ? ((size_t)ql * nc1 + j) : ((size_t)j * nc1 + ql));
+    dPB[pair * 4 + head] = dl;
+  }
+  __syncwarp();
+  float od = 0.f, dq_d = 0.f;
+  for (int j = 0; j < n_k; ++j) {
+    const float a = pa[j], dl = pd[j];
+    od = fmaf(a, Vb[(size_t)(k_lo + j) * ldv + head * 32 + lane], od);
+    dq_d = fmaf(dl, Kb[(size_t)(k_lo + j) * ldk + head * 32 + lane], dq_d);
+    atomicAdd(&dV[(size_t)(k_lo + j) * lddv + head * 32 + lane], a * do_d);
+    atomicAdd(&dK[(size_t)(k_lo + j) * lddk + head * 32 + lane], dl * qd);
+  }
+  dG[(size_t)qn * lddg + head * 32 + lane] = dod * od * sg * (1.0f - sg);
+  dQ[(size_t)qn * lddq + head * 32 + lane] = dq_d * scale;
+}
+
 // ---- training-mode forward pieces: the sub-steps whose intermediates the reverse pass needs and the fused inference kernels do
 // not keep (unclamped coordinate steps, per-complex radial norms, attention probabilities).  GPU parity tests gated behind
 // FB_EXPERIMENTAL until they have run on a B200; the forward orchestration over them is validated on the CPU. ------------------
@@ -805,11 +886,23 @@ int32_t fb_pair_outer_bwd(const float* dO, const float* pc, int32_t H, const int
 }
 
 int32_t fb_row_attention_bwd(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t q_is_prot,
-                             int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K, int32_t ldk,
+                             int32_t max_q, int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K, int32_t ldk,
                              const float* V, int32_t ldv, const float* PB, const float* dO, int32_t ldo, float* dQ, int32_t lddq,
                              float* dG, int32_t lddg, float* dK, int32_t lddk, float* dV, int32_t lddv, float* dPB, void* stream) {
   if (B <= 0) return FB_OK;
-  if (max_k > RB_MAXK) return FB_ERR_UNSUPPORTED;
+  if (max_k > RB_MAXK) {
+    // long key lists: global-memory variant (dK / dV must be zeroed by the caller: they are accumulated with atomics)
+    if (max_k > RBB_MAXK || max_q <= 0) return FB_ERR_UNSUPPORTED;
+    static unsigned long long done_big = 0;
+    const int smem = RB_WARPS * (2 * RBB_MAXK + 64) * 4;
+    if (!ensure_smem_optin(row_attention_bwd_big_kernel, smem, done_big)) return FB_ERR_CUDA;
+    fb_launch(row_attention_bwd_big_kernel, dim3(B, 4, (max_q + RB_WARPS - 1) / RB_WARPS), dim3(RB_WARPS * 32), smem, (cudaStream_t)stream,
+              c_off, p_off, pair_base, (int)q_is_prot, Q, (int)ldq, G, (int)ldg, K, (int)ldk, V, (int)ldv, PB, dO, (int)ldo, dQ, (int)lddq,
+              dG, (int)lddg, dK, (int)lddk, dV, (int)lddv, dPB);
+    count_launch(1);
+    FB_CHECK_LAUNCH();
+    return FB_OK;
+  }
   static unsigned long long done = 0;
   if (!ensure_smem_optin(row_attention_bwd_kernel, RB_SMEM_FLOATS * 4, done)) return FB_ERR_CUDA;
   fb_launch(row_attention_bwd_kernel, dim3(B, 4), dim3(RB_WARPS * 32), RB_SMEM_FLOATS * 4, (cudaStream_t)stream, c_off, p_off, pair_base,

@@ -283,3 +283,25 @@ def test_training_step_bf16_gemms_close_to_fp32():
     for k, ref in res["fp32"].items():
         err = float((res["bf16"][k] - ref).abs().max())
         assert err < 5e-2 * float(ref.abs().max()) + 5e-3 * gmax, (k, err, float(ref.abs().max()))
+
+
+def test_row_attention_reverse_long_key_lists():
+    """more than 256 keys (whole proteins of the pocket stage): the global-memory variant of the row-attention reverse"""
+    import emulate_backward as spec
+    from fabind_b200 import backward as bw
+    g = torch.Generator().manual_seed(8)
+    nc1, np1 = 21, 301
+    geo = dict(Nc=nc1, B=1, max_c=nc1, max_p=np1, c_off=torch.tensor([0, nc1], dtype=torch.int32), p_off=torch.tensor([nc1, nc1 + np1], dtype=torch.int32),
+               pair_base=torch.tensor([0, nc1 * np1], dtype=torch.int32), node_cplx=torch.zeros(nc1 + np1, dtype=torch.int32))
+    CAc, CAp2 = torch.randn(nc1, 512, generator=g), torch.randn(np1, 256, generator=g)
+    PB, dO = torch.randn(np1 * nc1, 4, generator=g), torch.randn(nc1, 128, generator=g)
+    _, sv = spec.rowatt_fwd(CAc[:, 256:384], CAc[:, 384:], CAp2[:, :128], CAp2[:, 128:], PB.view(np1, nc1, 4).transpose(0, 1))
+    dq, dg, dk, dv, db = spec.rowatt_bwd(sv, dO)
+    gd = _cuda(geo)
+    dCAc, dCAp2 = torch.zeros_like(CAc).cuda(), torch.zeros_like(CAp2).cuda()
+    dPB = bw.row_attention_bwd(gd, 0, (CAc.cuda(), 256), (CAc.cuda(), 384), (CAp2.cuda(), 0), (CAp2.cuda(), 128), PB.cuda(), dO.cuda(),
+                               (dCAc, 256), (dCAc, 384), (dCAp2, 0), (dCAp2, 128))
+    torch.cuda.synchronize()
+    assert rel_err(dCAc[:, 256:384], dq) < TOL and rel_err(dCAc[:, 384:], dg) < TOL
+    assert rel_err(dCAp2[:, :128], dk) < TOL and rel_err(dCAp2[:, 128:], dv) < TOL
+    assert rel_err(dPB, db.transpose(0, 1).reshape(-1, 4)) < TOL
