@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="precision of the no_grad iterations")
+    ap.add_argument("--flavour", default="v1", choices=["v1", "plus"], help="weight layout: FABind (4 layers) or FABind+ (5 layers, LayerNorm MLPs)")
     ap.add_argument("--gemm", default="fp32", choices=["fp32", "bf16"], help="GEMMs of the differentiated iteration (backward.PRECISION)")
     a = ap.parse_args()
     from fabind_b200 import EfficientMCAttModel, train, backward
@@ -42,9 +43,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    m = EfficientMCAttModel(published_args(), a.hidden, a.hidden, 1, n_layers=a.layers, n_iter=a.iters,
-                            normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
-    randomize_coord_heads(m, std=0.5)
+    if a.flavour == "plus":
+        from fabind_b200.config import published_args_plus
+        from fabind_b200.plus import EfficientMCAttModel as PlusModel
+        m = PlusModel(published_args_plus(), a.hidden, a.hidden, 1, n_layers=a.layers, n_iter=a.iters,
+                      normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+        m.return_pair = False
+    else:
+        m = EfficientMCAttModel(published_args(), a.hidden, a.hidden, 1, n_layers=a.layers, n_iter=a.iters,
+                                normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+        randomize_coord_heads(m, std=0.5)
     m = m.to(dev).eval()
     m.precision = a.precision
     b = make_batch(n_complexes=a.batch, n_c=30, n_p=200, embed=a.hidden, seed=100 + rank).to(dev)
@@ -58,7 +66,10 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         fa["X"] = X0.clone()
         ev[0].record()
-        X, H, pg, gH = train.training_step_v1(m, fa, lambda X_, H_: (rx, rh), state_dict=sd)
+        if a.flavour == "plus":
+            pg = train.training_step(m, fa, lambda X_, H_, P_: (rx, rh, torch.zeros_like(P_)), state_dict=sd)[3]
+        else:
+            pg = train.training_step(m, fa, lambda X_, H_: (rx, rh), state_dict=sd)[2]
         ev[1].record()
         train.apply_gradients(m, pg)
         ev[2].record()
@@ -74,7 +85,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         ms = float(t.sum())
-        print(json.dumps(dict(metric="training step (fwd + bwd + gradient all-reduce), v1 stack", n_gpus=world, global_batch=a.batch * world,
+        print(json.dumps(dict(metric=f"training step (fwd + bwd + gradient all-reduce), {a.flavour} stack", n_gpus=world, global_batch=a.batch * world,
                               ms_step=round(ms, 2), ms_forward_backward=round(float(t[0]), 2), ms_grads_allreduce=round(float(t[1]), 2),
                               complexes_per_s=round(a.batch * world / (ms / 1e3), 1), hidden=a.hidden, layers=a.layers, iters=a.iters,
                               no_grad_iterations=a.precision, reverse_pass="fp32 SIMT (first correct version)" if a.gemm == "fp32" else "tcgen05 GEMMs (bf16 operands), SIMT scatter kernels",
