@@ -176,13 +176,24 @@ class _StackFunction(torch.autograd.Function):
         return tuple(out)
 
 
-def forward_with_grad(model, fa, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges):
+def forward_with_grad(model, fa, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, n_iter=None):
     """`EfficientMCAttModel.forward` with autograd: returns (X, H[, pair rows]) attached to the graph, so an unchanged training loop
     (`loss.backward()`, optimizer over `model.parameters()`) trains the drop-in module.  Buffers / non-float entries of the state_dict
-    are passed through untouched."""
+    are passed through untouched.  n_iter: refinement iterations of this step; default = the reference's rule (att_model.py:210-211:
+    `random.randint(1, n_iter)` in train() mode when --random-n-iter is set, else the configured n_iter)."""
+    full = model._cfg["n_iter"]
+    if n_iter is None:
+        n_iter = full
+        if model.training and getattr(model, "random_n_iter", False):
+            import random
+            n_iter = random.randint(1, full)
     named = [(n, p) for n, p in model.state_dict(keep_vars=True).items() if torch.is_floating_point(p)]
     names = [n for n, _ in named]
-    out = _StackFunction.apply(model, fa, prev_coords, edge_lists, names, fa["H"], *[p for _, p in named])
+    model._cfg["n_iter"] = int(n_iter)
+    try:
+        out = _StackFunction.apply(model, fa, prev_coords, edge_lists, names, fa["H"], *[p for _, p in named])
+    finally:
+        model._cfg["n_iter"] = full
     X = fa["X"]
     with torch.no_grad():
         X.copy_(out[0].detach())                 # the reference updates the caller's X in place (att_model.py:236,245)
