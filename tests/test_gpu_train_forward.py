@@ -243,7 +243,7 @@ def test_forward_with_grad_on_the_gpu():
     gen = torch.Generator().manual_seed(r["readout_seed"])
     rx, rh = torch.randn(b.X.shape, generator=gen).cuda(), torch.randn(b.H.shape, generator=gen).cuda()
     fa = b.to("cuda").forward_args()
-    X, Hh = train.forward_with_grad(model, fa)
+    X, Hh = train.forward_with_grad(model, fa, n_iter=r["n_iter"])     # (train() mode would draw randint(1, n_iter): pin it for the golden)
     loss = (X * rx).sum() + (Hh * rh).sum()
     loss.backward()
     torch.cuda.synchronize()
