@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfabind_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "CUDA launch error", -4: "unsupported configuration"}
 
@@ -60,11 +60,19 @@ class GemmParams(C.Structure):
         ("bf16_mode", C.c_int32), ("force_simt", C.c_int32),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_site", C.c_uint32), ("drop_row0", C.c_int32),
         ("drop_colonly", C.c_int32),
+        ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_size_t), ("W_f32", C.c_void_p), ("n_split", C.c_int32),
     ]
 
 
+PREC_FP32, PREC_BF16, PREC_SPLIT3, PREC_SPLIT6 = 0, 1, 2, 3
+# precision names of the drop-in modules -> FB_PREC_*: "fp32_tc" = fp32 activations, GEMMs on tcgen05 as six bf16 products per
+# term (fp32-grade accuracy); "bf16x3" = three products (terms down to 2^-9)
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_SPLIT3, "fp32_tc": PREC_SPLIT6}
+
 EXPORTS = {
     "fb_abi_version": (C.c_int32, []),
+    "fb_source_hash": (C.c_int64, []),
+    "fb_split_rows": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "fb_launch_count": (C.c_int64, []),
     "fb_prof_enable": (C.c_int32, [C.c_int32]),
     "fb_prof_read": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
@@ -134,6 +142,8 @@ EXPORTS = {
     "fb_rowdot2": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "fb_rows_update": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "fb_vec_op": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "fb_dropout_apply": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint32, C.c_uint32,
+                                     C.c_int32, C.c_int32, C.c_void_p]),
     "fb_softmax_seg_bwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fb_pair_bias_gate_bwd": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fb_pair_outer_bwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -174,7 +184,12 @@ def lib():
         fn.restype = res
         fn.argtypes = args
     if l.fb_abi_version() != ABI_VERSION:
-        raise RuntimeError("libfabind_b200.so ABI version mismatch; rebuild")
+        raise RuntimeError("libfabind_b200.so ABI version mismatch; rebuild (python -m fabind_b200.build)")
+    from .build import source_hash
+    want = source_hash()
+    if want is not None and l.fb_source_hash() != want:
+        raise RuntimeError("libfabind_b200.so was built from different sources than the ones next to it (stale library): "
+                           "rebuild with `python -m fabind_b200.build`")
     _lib = l
     return l
 

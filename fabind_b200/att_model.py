@@ -1,8 +1,9 @@
 """Drop-in replacements for FABind/fabind/models/att_model.py: `ComplexGraph` and `EfficientMCAttModel`.
 
 Same constructor and forward signatures, same state_dict keys; the forward pass is one call into
-libfabind_b200 (hand-written sm_100a kernels).  Inference semantics (eval mode, refine='refine_coord',
-att_model.py:227-245); the training path lives in fabind_b200/train.py and is opt-in (see forward()).
+libfabind_b200 (hand-written sm_100a kernels).  eval(): inference semantics (refine='refine_coord', att_model.py:227-245);
+train() under no_grad: the same with every nn.Dropout active; train() with autograd: the training step of fabind_b200/train.py
+(earlier iterations without gradient, the last one differentiated by the reverse-pass kernels).
 """
 import ctypes as C
 import os
@@ -95,31 +96,53 @@ class EfficientMCAttModel(nn.Module):
                          coord_clamp=float(normalize_coord(10)), las_clamp=float(normalize_coord(15)),
                          las_step=float(args.geometry_reg_step_size))
         self._packed = PackedWeights()
-        # "fp32": FFMA GEMMs, parity mode (<= 1e-4 rel vs the reference);  "bf16": tcgen05 GEMMs with bf16
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._packed.invalidate())
+        # "fp32": FFMA GEMMs (parity mode);  "fp32_tc": fp32 activations, GEMMs on tcgen05 as six bf16 products per term (the
+        # tensor-core parity mode, <= 1e-4 rel vs the reference);  "bf16x3": three products;  "bf16": tcgen05 GEMMs with bf16
         # operands / fp32 accumulation (coordinates, softmax statistics and the residual stream stay fp32)
         self.precision = os.environ.get("FABIND_B200_PRECISION", "fp32")
+        # train() mode: every nn.Dropout of the reference's stack is active (egnn.py:82,106,236,398,461, cross_att.py:128), in all
+        # refinement iterations.  Masks are applied in-kernel, keyed by `dropout_seed` (None: drawn from torch's global generator per
+        # call, like nn.Dropout; see fabind_b200/dropout.py); `dropout_colonly` = column-only masks (tests: pins mask placement)
+        self.dropout_p = float(dropout)
+        self.dropout_seed = None
+        self.dropout_colonly = False
         self.last_stats = None
         self.debug_trace = False   # tests: record h/x after every sub-layer of the last iteration
 
+    def _apply(self, fn, *a, **k):
+        self._packed.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def invalidate_packed_weights(self):
+        """call after editing parameters through `.data` (EMA swaps, manual re-initialisation): such writes change neither
+        `_version` nor `data_ptr()`, which is what the packed-arena cache keys on"""
+        self._packed.invalidate()
+
     def forward(self, X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index,
                 batched_complex_coord_LAS, LAS_mask=None):
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        dropout, n_iter = None, None
         if self.training:
-            # The training path (fabind_b200/train.py: reverse-pass kernels, training-mode forward, one autograd node) is validated
-            # on the CPU against the reference's parameter gradients and its reverse kernels on a B200; its forward-side kernels have
-            # not run on a GPU yet, so it is opt-in until the gated tests (tests/test_gpu_train_forward.py) are green.  No dropout.
-            if torch.is_grad_enabled() and os.environ.get("FABIND_B200_EXPERIMENTAL_TRAIN") == "1":
+            if self.dropout_p > 0:
+                seed = self.dropout_seed if self.dropout_seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+                dropout = (self.dropout_p, seed, self.dropout_colonly)
+            if torch.is_grad_enabled():
+                # training step (att_model.py:210-245): iterations 0..n-2 under no_grad, the last one differentiated -- one autograd
+                # node whose backward runs the reverse-pass kernels (fabind_b200/train.py)
                 from . import train
                 return train.forward_with_grad(self, dict(X=X, H=H, batch_id=batch_id, segment_id=segment_id, mask=mask,
                                                           is_global=is_global, compound_edge_index=compound_edge_index,
                                                           LAS_edge_index=LAS_edge_index,
-                                                          batched_complex_coord_LAS=batched_complex_coord_LAS, LAS_mask=LAS_mask))
-            raise NotImplementedError("fabind_b200: train() mode is opt-in (FABIND_B200_EXPERIMENTAL_TRAIN=1, see "
-                                      "fabind_b200/train.py) until its forward-side kernels have run on a GPU; call .eval()")
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+                                                          batched_complex_coord_LAS=batched_complex_coord_LAS, LAS_mask=LAS_mask),
+                                               dropout=dropout)
+            if self.random_n_iter:        # att_model.py:210-211: iter_i = random.randint(1, n_iter) in training mode
+                import random
+                n_iter = random.randint(1, self.n_iter)
         with torch.no_grad():
             H_out, stats, e_ctx, tr = model_forward(self, self._packed, X, H, batch_id, segment_id, mask, is_global,
                                                     compound_edge_index, LAS_edge_index, batched_complex_coord_LAS,
-                                                    self._cfg, self.precision == "bf16", trace=self.debug_trace)
+                                                    self._cfg, self.precision, trace=self.debug_trace, dropout=dropout, n_iter=n_iter)
         self.last_stats = dict(inter_edges_per_iter=stats, ctx_edges=e_ctx, trace=tr)
         return X, H_out

@@ -7,12 +7,11 @@ against autograd and the unmodified reference's parameter gradients: tests/emula
 csrc/backward.cu plus fb_gemm for the data-gradient GEMMs (`dX = dY W` on a transposed weight).  torch only allocates / copies
 device memory here; there is no torch arithmetic on the path and no fallback: CPU tensors raise.
 
-Status (round 1): the v1 reverse kernels, `gcl_backward` / `att_backward` / `las_bwd` and `stack_backward_v1` are parity-green on a
-B200 against the specification's arena gradient (tests/test_gpu_train_reverse.py, tests/test_gpu_train_reverse_att.py).  Written after the GPU
-budget was spent, validated on the CPU only (every kernel wrapper swapped for its torch definition,
-tests/test_backward_orchestration.py), GPU tests gated behind FB_EXPERIMENTAL=1 (tests/test_gpu_train_forward.py): the training-mode
-forward of both layouts (`stack_forward_train_v1/plus`), the FABind+ reverse pass (`stack_backward_plus`) and the assembled step
-(fabind_b200/train.py).  `train()` with autograd enabled still raises in the drop-in modules."""
+Status: every kernel and orchestration function here is parity-green on a B200 against the specification's arena gradient and,
+assembled into the training step, against the unmodified reference's parameter gradients in both layouts
+(tests/test_gpu_train_reverse.py, tests/test_gpu_train_reverse_att.py, tests/test_gpu_train_forward.py); the orchestration is also
+validated on the CPU with every kernel wrapper swapped for its torch definition (tests/test_backward_orchestration.py).  The v1
+layout carries the reference's training-mode dropout (class Drop); the FABind+ reverse pass does not yet."""
 import ctypes as C
 
 import torch
@@ -30,9 +29,40 @@ PRECISION = "fp32"
 WGRAD_TC_MIN_ROWS = 2048
 
 
-def _gemm_call(A, W, bias, act, res, M, N, K):
-    """C[M,N] = act(A W^T + bias) + res through fb_gemm in the current PRECISION; A [M,K], W [N,K] fp32 in, fp32 out"""
+class Drop:
+    """nn.Dropout of the reference's training step (v1 stack: egnn.py:82,106,236,398,461; cross_att.py:128) for ONE refinement
+    iteration, with the library's counter-based masks (csrc/common.cuh, fabind_b200/dropout.py): the forward applies
+    keep(seed_it, site, row, col) / (1 - p), the reverse pass applies the same function to the incoming gradient -- no mask is stored."""
+
+    def __init__(self, p, seed, colonly, it):
+        from .dropout import iter_seed
+        self.p, self.seed, self.colonly = float(p), iter_seed(seed, it), int(bool(colonly))
+
+    def site(self, layer, name):
+        from .dropout import site_id
+        return site_id(layer, name)
+
+    def apply(self, X, layer, name, row0=0):
+        """drop(X) as a new tensor (X [M, N] fp32 contiguous, or a contiguous row slice)"""
+        _chk(X)
+        Y = torch.empty_like(X)
+        M, N = X.shape
+        _lib.check(_lib.lib().fb_dropout_apply(X.data_ptr(), Y.data_ptr(), N, M, N, self.p, self.seed, self.site(layer, name), int(row0),
+                                               self.colonly, _st(X)), "fb_dropout_apply")
+        return Y
+
+
+def _drop(drop, X, layer, name, row0=0):
+    return X if drop is None or drop.p <= 0 else drop.apply(X, layer, name, row0)
+
+
+def _gemm_call(A, W, bias, act, res, M, N, K, drop=None):
+    """C[M,N] = drop(act(A W^T + bias)) + res through fb_gemm in the current PRECISION; A [M,K], W [N,K] fp32 in, fp32 out.
+    drop = (Drop, layer, site name, row0) or None: dropout in the epilogue, after the activation and before the residual."""
     g = _lib.GemmParams()
+    if drop is not None and drop[0] is not None and drop[0].p > 0:
+        d, layer, name, row0 = drop
+        g.drop_p, g.drop_seed, g.drop_site, g.drop_row0, g.drop_colonly = d.p, d.seed, d.site(layer, name), int(row0), d.colonly
     bf16 = PRECISION == "bf16" and K % 8 == 0
     if bf16:
         A, W = A.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous()
@@ -187,7 +217,7 @@ def _linear_bwd(grads, wname, bname, Wt, X, dY, need_dx=True):
     return gemm_dgrad(dY, Wt) if need_dx else None
 
 
-def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new):
+def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new, drop=None, layer=0):
     """Reverse pass of one MC_E_GCL sub-layer (v1 layout; forward: csrc/forward.cu::run_gcl, reference egnn.py:68-144).
 
     w: dict of fp32 CUDA tensors in the packed-arena naming -- e1_rc [2H,H], e1_rad [H], e2_w, c1_w [H,H], c2_w [H], n1_w [H,2H],
@@ -203,19 +233,19 @@ def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new):
     T3 = act_fwd(saved["Z3"], ACT_SILU)
     grads["c2_w"] = colsum(T3, ds)
     dZ3 = outer_act_bwd(saved["Z3"], ds, w["c2_w"], ACT_SILU)        # dZ3[e,f] = ds[e] c2[f] silu'(Z3[e,f])
-    M = act_fwd(saved["Z2"], ACT_SILU)
+    M = _drop(drop, act_fwd(saved["Z2"], ACT_SILU), layer, "edge2")   # the edge message as the forward used it (egnn.py:82)
     dM = _linear_bwd(grads, "c1_w", "c1_b", w["c1_w_t"], M, dZ3)
-    # node branch: h_new = h + n2(silu(n1([h | agg])))
+    # node branch: h_new = h + drop(n2(silu(n1([h | agg]))))
     t1 = act_fwd(saved["Z4"], ACT_SILU)
-    dt1 = _linear_bwd(grads, "n2_w", "n2_b", w["n2_w_t"], t1, dh_new)
+    dt1 = _linear_bwd(grads, "n2_w", "n2_b", w["n2_w_t"], t1, _drop(drop, dh_new, layer, "node2"))
     dZ4 = act_bwd(saved["Z4"], dt1, ACT_SILU)
     cat = torch.empty(N, 2 * H, dtype=torch.float32, device=h.device)
     cat[:, :H].copy_(h)
     cat[:, H:].copy_(saved["agg"])
     dcat = _linear_bwd(grads, "n1_w", "n1_b", w["n1_w_t"], cat, dZ4)
     gather_add_rows(dcat, row, dM, col0=H)                    # dM[e] += dagg[row[e]]
-    # edge MLP
-    dZ2 = act_bwd(saved["Z2"], dM, ACT_SILU)
+    # edge MLP (dM is the gradient of the DROPPED message)
+    dZ2 = act_bwd(saved["Z2"], _drop(drop, dM, layer, "edge2"), ACT_SILU)
     A1 = act_fwd(saved["Z1"], ACT_SILU)
     dA1 = _linear_bwd(grads, "e2_w", "e2_b", w["e2_w_t"], A1, dZ2)
     dZ1 = act_bwd(saved["Z1"], dA1, ACT_SILU)
@@ -339,7 +369,7 @@ def row_attention_bwd(geo, q_is_prot, Q, G, K, V, PB, dO, dQ, dG, dK, dV):
 HD = 128
 
 
-def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0):
+def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0, drop=None, layer=0):
     """Reverse pass of one MC_Att_L sub-layer (v1 layout; forward: csrc/forward.cu::run_att; reference egnn.py:186-333,
     cross_att.py:24-54).  Specification: tests/emulate_backward.py::att_bwd.
 
@@ -366,7 +396,7 @@ def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0):
     scatter_add_rows(dzc, col, dQK, col0=3 * H + 128)
     # interfacial aggregation h3 = h2 + sum_e alpha_e (V[col] + rn v_r)
     dh2 = dh3.clone()
-    dve = gather_rows(dh3, row)
+    dve = gather_rows(_drop(drop, dh3, layer, "agg"), row)            # h3 = h2 + drop(agg) (egnn.py:236)
     ve = rank1_add(gather_rows(QK, col, 2 * H + 128, H), rn, w["v_r"])
     vec_add_(dalpha, rowdot2(dve, ve))
     scale_rows(dve, alpha)
@@ -411,14 +441,14 @@ def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0):
     dTp = _linear_bwd(grads, "tp2_w", "tp2_b", w["tp2_w_t"], sv["Ttp"], dhp)
     vec_add_(dhp, _linear_bwd(grads, "tp1_w", "tp1_b", w["tp1_w_t"], sv["hp1"], act_bwd(sv["Ttp"], dTp, ACT_RELU)))
     # compound-side row attention (keys / values from the updated protein side)
-    dOc = _linear_bwd(grads, "o_c_w", "o_c_b", w["o_c_w_t"], sv["Oc"], dhc)
+    dOc = _linear_bwd(grads, "o_c_w", "o_c_b", w["o_c_w_t"], sv["Oc"], _drop(drop, dhc, layer, "catt"))
     dCAc = torch.zeros_like(sv["CAc"])
     dCAp2 = torch.zeros_like(sv["CAp2"])
     dPB_c = row_attention_bwd(geo, 0, (sv["CAc"], 2 * HD), (sv["CAc"], 3 * HD), (sv["CAp2"], 0), (sv["CAp2"], HD), sv["PB_c"], dOc,
                               (dCAc, 2 * HD), (dCAc, 3 * HD), (dCAp2, 0), (dCAp2, HD))
     vec_add_(dhp, _linear_bwd(grads, "ca_p2_w", None, w["ca_p2_w_t"], sv["hp1"], dCAp2))
     # protein-side row attention
-    dOp = _linear_bwd(grads, "o_p_w", "o_p_b", w["o_p_w_t"], sv["Op"], dhp)
+    dOp = _linear_bwd(grads, "o_p_w", "o_p_b", w["o_p_w_t"], sv["Op"], _drop(drop, dhp, layer, "patt", Nc))
     dCAp = torch.zeros_like(sv["CAp"])
     dPB_p = row_attention_bwd(geo, 1, (sv["CAp"], 0), (sv["CAp"], HD), (sv["CAc"], 0), (sv["CAc"], HD), sv["PB_p"], dOp,
                               (dCAp, 0), (dCAp, HD), (dCAc, 0), (dCAc, HD))
@@ -441,13 +471,15 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
     L = len(tape)
     Nc = geo["Nc"]
     grads = {}
+    drop = consts.get("drop")
 
     def take(pre, g):
         for k, v in g.items():
             grads[pre + k] = v
     g0 = {}
-    dh = _linear_bwd(g0, "out_w", "out_b", weights[""]["out_w_t"], top["h_last"], dH_out)
-    dh, dx, g = gcl_backward(weights["out."], top["out_saved"], edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dX_out)
+    dh = _drop(drop, _linear_bwd(g0, "out_w", "out_b", weights[""]["out_w_t"], top.get("h_last_d", top["h_last"]), dH_out), -1, "stack_out")
+    dh, dx, g = gcl_backward(weights["out."], top["out_saved"], edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dX_out,
+                             drop, L)
     take("out.", g)
     P0 = top["P0"]
     dP0 = torch.zeros_like(P0)
@@ -455,13 +487,14 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
     for l in reversed(range(L)):
         s_gcl, s_att, s_las = tape[l]
         dx = las_bwd(s_las["x"], consts["xl"], edges["las_a"], edges["las_b"], s_las["acc"], consts["las_step"], consts["lcl"], dx)
-        dh, dx, g, dPB_p, dPB_c = att_backward(weights[f"att{l}."], s_att, geo, edges["int_row"], edges["int_col"], consts["cmax"], dh, dx, dP0)
+        dh, dx, g, dPB_p, dPB_c = att_backward(weights[f"att{l}."], s_att, geo, edges["int_row"], edges["int_col"], consts["cmax"], dh, dx, dP0,
+                                               drop, l)
         take(f"att{l}.", g)
         dPB[:, 2 * l].copy_(dPB_p)
         dPB[:, 2 * l + 1].copy_(dPB_c)
-        dh, dx, g = gcl_backward(weights[f"gcl{l}."], s_gcl, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dx)
+        dh, dx, g = gcl_backward(weights[f"gcl{l}."], s_gcl, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dx, drop, l)
         take(f"gcl{l}.", g)
-    dHin = _linear_bwd(g0, "in_w", "in_b", weights[""]["in_w_t"], top["Hin"], dh)
+    dHin = _linear_bwd(g0, "in_w", "in_b", weights[""]["in_w_t"], top["Hin"], _drop(drop, dh, -1, "stack_in"))
     draw = pair_bias_gate_bwd(top["raw_full"], dPB)
     vec_add_(dP0, _linear_bwd(g0, "pb_w", "pb_b", weights[""]["pb_w_t"], P0, draw))
     douter = _linear_bwd(g0, "il_o_w", "il_o_b", weights[""]["il_o_w_t"], top["outer"], dP0)
@@ -476,17 +509,17 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
 # Training-mode forward of the last refinement iteration (v1 layout): the same arithmetic as the inference launch sequence
 # (csrc/forward.cu), un-fused where the reverse pass needs an intermediate, every saved tensor in the form gcl_backward /
 # att_backward / las_bwd consume.  fp32; GEMMs through fb_gemm (SIMT parity kernel), row attention through the inference kernel.
-# The kernels under the wrappers of this section have NOT run on a GPU yet (their parity tests are gated, FB_EXPERIMENTAL=1);
-# the orchestration is validated on the CPU against the specification's forward (tests/test_backward_orchestration.py).
+# GPU parity: tests/test_gpu_train_forward.py; the orchestration is also validated on the CPU against the specification's forward
+# (tests/test_backward_orchestration.py).
 # ------------------------------------------------------------------------------------------------------------------------
-def linear(A, W, bias=None, act=ACT_NONE, res=None):
-    """act(A W^T + bias) + res  (fp32, fb_gemm)"""
+def linear(A, W, bias=None, act=ACT_NONE, res=None, drop=None):
+    """drop(act(A W^T + bias)) + res  (fp32, fb_gemm); drop = (Drop, layer, site name, row0) or None"""
     _chk(A), _chk(W)
     if bias is not None:
         _chk(bias)
     if res is not None:
         _chk(res)
-    return _gemm_call(A, W, bias, act, res, A.shape[0], W.shape[0], A.shape[1])
+    return _gemm_call(A, W, bias, act, res, A.shape[0], W.shape[0], A.shape[1], drop)
 
 
 def radial_fwd(x, row, col, node_cplx, B):
@@ -567,7 +600,7 @@ def _ones(n, dev):
     return torch.ones(n, dtype=torch.float32, device=dev)
 
 
-def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax):
+def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax, drop=None, layer=0):
     """MC_E_GCL forward (egnn.py:68-144; inference twin: forward.cu::run_gcl) keeping what gcl_backward consumes"""
     N, H = h.shape
     E, dev = row.numel(), h.device
@@ -578,7 +611,7 @@ def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax):
     rank1_add(Z1, rn, w["e1_rad"])
     rank1_add(Z1, _ones(E, dev), w["e1_b"])
     Z2 = linear(act_fwd(Z1, ACT_SILU), w["e2_w"], w["e2_b"])
-    M = act_fwd(Z2, ACT_SILU)
+    M = _drop(drop, act_fwd(Z2, ACT_SILU), layer, "edge2")            # egnn.py:82
     Z3 = linear(M, w["c1_w"], w["c1_b"])
     s = rowdot(act_fwd(Z3, ACT_SILU), w["c2_w"])
     ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)
@@ -593,7 +626,7 @@ def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax):
     cat[:, :H].copy_(h)
     cat[:, H:].copy_(agg)
     Z4 = linear(cat, w["n1_w"], w["n1_b"])
-    h_new = linear(act_fwd(Z4, ACT_SILU), w["n2_w"], w["n2_b"], res=h)
+    h_new = linear(act_fwd(Z4, ACT_SILU), w["n2_w"], w["n2_b"], res=h, drop=(drop, layer, "node2", 0))   # egnn.py:106
     return h_new, x_new, dict(h=h, x=x, rn=rn, nrm=nrm, Z1=Z1, Z2=Z2, Z3=Z3, s=s, deg=deg, step=step, agg=agg, Z4=Z4)
 
 
@@ -616,7 +649,7 @@ def interface_indices(row, col, geo):
     return dict(pair=i32(pair), u_pair=i32(pair[u]), u_pi=i32(pi[u]), u_ci=i32(ci[u]), rowptr=i32(rowptr))
 
 
-def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax):
+def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax, drop=None, layer=0):
     """MC_Att_L forward (egnn.py:186-333, cross_att.py:24-54; inference twin: forward.cu::run_att) keeping what att_backward consumes.
     row / col must be sorted by row (the library's interface graph is); idx = interface_indices(row, col, geo)."""
     N, H = h.shape
@@ -625,10 +658,10 @@ def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax):
     CAc = linear(hc0, w["ca_c_w"], w["ca_c_b"])
     CAp = linear(hp0, w["ca_p_w"], w["ca_p_b"])
     Op = row_attention_fwd(geo, 1, (CAp, 0), (CAp, HD), (CAc, 0), (CAc, HD), PB_p, N - Nc)
-    hp1 = linear(Op, w["o_p_w"], w["o_p_b"], res=hp0)
+    hp1 = linear(Op, w["o_p_w"], w["o_p_b"], res=hp0, drop=(drop, layer, "patt", Nc))       # cross_att.py:128
     CAp2 = linear(hp1, w["ca_p2_w"])
     Oc = row_attention_fwd(geo, 0, (CAc, 2 * HD), (CAc, 3 * HD), (CAp2, 0), (CAp2, HD), PB_c, Nc)
-    hc1 = linear(Oc, w["o_c_w"], w["o_c_b"], res=hc0)
+    hc1 = linear(Oc, w["o_c_w"], w["o_c_b"], res=hc0, drop=(drop, layer, "catt", 0))
     Ttp = linear(hp1, w["tp1_w"], w["tp1_b"], act=ACT_RELU)
     Ttc = linear(hc1, w["tc1_w"], w["tc1_b"], act=ACT_RELU)
     h2 = torch.empty(N, H, dtype=torch.float32, device=dev)
@@ -652,8 +685,13 @@ def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax):
     vec_add_(logit, gather_rows(pb_dense, idx["pair"]).view(E))
     alpha = softmax_seg_fwd(logit, idx["rowptr"], N)
     ve = scale_rows(rank1_add(gather_rows(QK, col, 2 * H + 128, H), rn, w["v_r"]), alpha)
-    h3 = h2.clone()
-    scatter_add_rows(ve, row, h3)
+    if drop is not None and drop.p > 0:                                  # h3 = h2 + drop(agg)  (egnn.py:235-237)
+        agg = torch.zeros_like(h2)
+        scatter_add_rows(ve, row, agg)
+        h3 = vec_add_(drop.apply(agg, layer, "agg"), h2)
+    else:
+        h3 = h2.clone()
+        scatter_add_rows(ve, row, h3)
     zc = rank1_add(gather_rows(QK, col, 3 * H + 128, H), rn, w["ac_u"])
     rank1_add(zc, _ones(E, dev), w["ac1_b"])
     se = rowdot(act_fwd(zc, ACT_SILU), w["ac2_w"])
@@ -679,22 +717,26 @@ def stack_forward_train_v1(weights, Hin, x_state, moves, geo, edges, consts, n_l
     P0 = linear(outer, wt["il_o_w"], wt["il_o_b"])
     raw_full = linear(P0, wt["pb_w"], wt["pb_b"])
     PB = pair_bias_gate_fwd(raw_full, 2 * n_layers)
-    h = linear(Hin, wt["in_w"], wt["in_b"])
+    drop = consts.get("drop")
+    h = linear(Hin, wt["in_w"], wt["in_b"], drop=(drop, -1, "stack_in", 0))         # egnn.py:398
     x = x_state
     idx = interface_indices(edges["int_row"], edges["int_col"], geo)
     tape = []
     for l in range(n_layers):
-        h, x, s_gcl = gcl_forward_train(weights[f"gcl{l}."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"])
+        h, x, s_gcl = gcl_forward_train(weights[f"gcl{l}."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"],
+                                        drop, l)
         h, x, s_att = att_forward_train(weights[f"att{l}."], h, x, geo, edges["int_row"], edges["int_col"], idx, P0,
-                                        PB[:, 2 * l].contiguous(), PB[:, 2 * l + 1].contiguous(), consts["cmax"])
+                                        PB[:, 2 * l].contiguous(), PB[:, 2 * l + 1].contiguous(), consts["cmax"], drop, l)
         acc = las_acc(x, consts["xl"], edges["las_a"], edges["las_b"], consts["las_step"])
         x_in = x
         _, x = coord_apply(x_in, acc, None, consts["lcl"])
         tape.append((s_gcl, s_att, dict(x=x_in, acc=acc)))
-    h_last, x, s_out = gcl_forward_train(weights["out."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"])
-    H_out = linear(h_last, wt["out_w"], wt["out_b"])
+    h_last, x, s_out = gcl_forward_train(weights["out."], h, x, edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], geo["B"], consts["cmax"],
+                                         drop, n_layers)
+    h_last_d = _drop(drop, h_last, -1, "stack_out")                                 # egnn.py:461
+    H_out = linear(h_last_d, wt["out_w"], wt["out_b"])
     X_out = torch.where(moves[:, None], x, x_state)
-    top = dict(Hin=Hin, pc=pc, outer=outer, P0=P0, raw_full=raw_full, h_last=h_last, out_saved=s_out)
+    top = dict(Hin=Hin, pc=pc, outer=outer, P0=P0, raw_full=raw_full, h_last=h_last, h_last_d=h_last_d, out_saved=s_out)
     return X_out, H_out, tape, top
 
 

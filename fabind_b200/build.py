@@ -11,16 +11,40 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+def _deps():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
+        os.path.join(os.path.dirname(HERE), "include", "fabind_b200.h")]
+
+
+def source_hash():
+    """63-bit digest of the header + csrc/ (None when the sources are not shipped next to the library)"""
+    import hashlib
+    h = hashlib.sha256()
+    try:
+        for d in _deps():
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    except OSError:
+        return None
+    return int.from_bytes(h.digest()[:8], "little") & 0x7FFFFFFFFFFFFFFF
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(os.path.dirname(HERE), "include", "fabind_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    if any(os.path.getmtime(d) > t for d in _deps()):
+        return True
+    stamp = LIB + ".hash"
+    try:
+        return int(open(stamp).read().strip()) != source_hash()
+    except (OSError, ValueError):
+        return True
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, diag=False):
+    """diag=True adds -DFB_DIAG: the diagnostic environment knobs (FB_PDL, FB_SKIP_CATS, FB_TC4, ...) exist only in such builds"""
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -30,7 +54,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + FLAGS + [f"-DFB_SOURCE_HASH={source_hash()}LL"] + (["-DFB_DIAG"] if diag else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -45,8 +69,10 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    with open(LIB + ".hash", "w") as f:
+        f.write(str(source_hash()))
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, diag="--diag" in sys.argv))

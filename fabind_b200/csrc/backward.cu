@@ -844,6 +844,33 @@ int32_t fb_rows_update(float* A, int32_t lda, int32_t M, int32_t N, const float*
   return FB_OK;
 }
 
+// dst[m, n] = keep(seed, site, row0 + m, n) ? src[m, n] / (1 - p) : 0  -- the library's counter-based dropout mask (common.cuh) as a
+// stand-alone op: the training-mode forward applies it where the inference path has it fused into an epilogue, and the reverse
+// pass applies the SAME mask to the incoming gradient (the mask is a pure function of its coordinates, nothing is stored).
+__global__ void dropout_apply_kernel(const float* __restrict__ src, float* __restrict__ dst, int ld, int M, int N, DropCfg dc) {
+  pdl_entry();
+  const long long total = (long long)M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+    dst[(size_t)m * ld + n] = drop_apply(src[(size_t)m * ld + n], dc, m, n);
+  }
+}
+
+int32_t fb_dropout_apply(const float* src, float* dst, int32_t ld, int32_t M, int32_t N, float p, uint32_t seed, uint32_t site,
+                         int32_t row0, int32_t colonly, void* stream) {
+  if (M <= 0 || N <= 0) return FB_OK;
+  if (!(p >= 0.f && p < 1.f)) return FB_ERR_BAD_ARG;
+  const DropCfg dc = make_drop(p, seed, site, row0, colonly);
+  if (p == 0.f) {
+    if (src != dst) cudaMemcpy2DAsync(dst, sizeof(float) * ld, src, sizeof(float) * ld, sizeof(float) * N, M, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    return FB_OK;
+  }
+  fb_launch(dropout_apply_kernel, dim3(grid_1d((long long)M * N, 256)), dim3(256), 0, (cudaStream_t)stream, src, dst, (int)ld, (int)M, (int)N, dc);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
 int32_t fb_vec_op(const float* a, const float* b, float* c, int64_t n, int32_t op, void* stream) {
   if (n <= 0) return FB_OK;
   if (op < 0 || op > 2) return FB_ERR_BAD_ARG;

@@ -20,17 +20,23 @@ extern long long* g_tc_dbg;
 // ------------------------------------------------------------------------------------------------
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
+// Diagnostic environment knobs exist only in -DFB_DIAG builds (python -m fabind_b200.build --diag); the release library reads no
+// environment variable.  FB_PDL=0 disables programmatic dependent launch; FB_SKIP_CATS=<bitmask> (scripts/dev/skip_probe.sh) drops
+// every launch of the masked categories so the in-situ cost of a category can be read off as a difference of step times (results
+// are garbage).
+#ifdef FB_DIAG
 bool pdl_enabled() {
   static bool on = [] { const char* e = getenv("FB_PDL"); return !(e && e[0] == '0'); }();
   return on;
 }
-
-// diagnostic only (scripts/skip_probe.sh): FB_SKIP_CATS=<bitmask> drops every launch of the masked categories so the
-// in-situ (PDL-overlapped) cost of a category can be read off as a difference of step times; results are garbage
 static int skip_mask() {
   static int m = [] { const char* e = getenv("FB_SKIP_CATS"); return e ? atoi(e) : 0; }();
   return m;
 }
+#else
+bool pdl_enabled() { return true; }
+static constexpr int skip_mask() { return 0; }
+#endif
 
 struct ProfSpan { cudaEvent_t a, b; int cat; };
 static bool g_prof_on = false;
@@ -263,15 +269,17 @@ struct Bufs {
   float *radc, *normc, *radi, *normi, *dotE, *lgt, *sde;
   // FABind+ only
   float *hstat, *vstat, *dotP; void *M2, *TH2, *Tn, *PairA, *PairB, *Zl, *Zh; void *A1, *M;
+  void* split_ws; size_t split_bytes;
 };
 
 static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   const size_t N = p.N, H = p.hidden, E = p.E_ctx > 0 ? p.E_ctx : 1, P = p.P_total, L = p.n_layers;
   const size_t capI = p.cap_int > 0 ? p.cap_int : 2, capU = capI / 2 + 1;
-  const size_t TS = p.bf16_mode ? 2 : 4;
+  const bool bf = p.bf16_mode == FB_PREC_BF16;
+  const int gmode = p.bf16_mode;
+  const size_t TS = bf ? 2 : 4;
   const size_t Nc = p.Nc_tot, Np = N - Nc;
-  const bool bf = p.bf16_mode;
-  const size_t tilesH = gemm_dot_tiles((int)E, (int)H, (int)H, bf), tiles2H = gemm_dot_tiles((int)(capI / 2), (int)(2 * H), (int)H, bf);
+  const size_t tilesH = gemm_dot_tiles((int)E, (int)H, (int)H, gmode), tiles2H = gemm_dot_tiles((int)(capI / 2), (int)(2 * H), (int)H, gmode);
   const bool plus = p.flavour == FB_FLAVOUR_PLUS;
   const size_t Dp = dp_of((int)H);
   b.ctx_row = a.get<int>(E); b.ctx_col = a.get<int>(E);
@@ -294,7 +302,7 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
     b.hstat = a.get<float>(3 * N); b.vstat = a.get<float>(3 * N);
     b.M2 = a.take(E * H * TS); b.TH2 = a.take(N * 2 * H * TS); b.Tn = a.take(N * H * TS);
     b.PairA = a.take(P * H * TS); b.PairB = a.take(P * H * TS); b.Zl = a.take(P * H * TS); b.Zh = a.take(P * H * TS);
-    b.dotP = a.get<float>((size_t)gemm_dot_tiles((int)P, (int)H, (int)H, bf) * P);
+    b.dotP = a.get<float>((size_t)gemm_dot_tiles((int)P, (int)H, (int)H, gmode) * P);
   }
   b.dotE = a.get<float>(tilesH * E);
   b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
@@ -309,6 +317,17 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   // pair0 construction temporaries (alive only before the iteration loop, but kept simple: own space)
   b.A0 = a.take(P * H * TS);
   b.PBraw = a.get<float>(P * (plus ? 128 : pb_cols((int)L)));
+  // split-precision modes: scratch for the three bf16 planes of the largest A operand (edge rows x Dp / H, pair rows x H,
+  // unique interface pairs x (H + 64), node rows x 2H)
+  b.split_ws = nullptr; b.split_bytes = 0;
+  if (gmode >= FB_PREC_SPLIT3) {
+    size_t el = E * (plus ? Dp : H);
+    if (P * H > el) el = P * H;
+    if (capU * (H + 64) > el) el = capU * (H + 64);
+    if (N * 2 * H > el) el = N * 2 * H;
+    b.split_bytes = el * 3 * sizeof(bf16);
+    b.split_ws = a.take(b.split_bytes);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -320,12 +339,16 @@ struct Run {
   GraphDev g;
   Bufs b;
   cudaStream_t st;
-  bool bf;
+  bool bf;           // bf16 activations (FB_PREC_BF16)
+  int gmode = 0;     // precision mode of the GEMMs (FB_PREC_*); the split modes keep fp32 activations
   int H, N, Nc, Np;
   size_t TS;
   int rc = FB_OK;
 
-  const void* W(int64_t off) const { return bf ? (const void*)((const bf16*)p.w16 + off) : (const void*)(p.w32 + off); }
+  const void* W(int64_t off) const {
+    if (gmode >= FB_PREC_SPLIT3) return (const void*)((const bf16*)p.w16 + 3 * off);
+    return bf ? (const void*)((const bf16*)p.w16 + off) : (const void*)(p.w32 + off);
+  }
   const float* F(int64_t off) const { return p.w32 + off; }
   void* at(void* base, size_t elem) const { return (char*)base + elem * TS; }
   const void* at(const void* base, size_t elem) const { return (const char*)base + elem * TS; }
@@ -357,6 +380,7 @@ struct Run {
     GemmArgs a;
     a.A = A; a.lda = lda; a.K1 = K; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
     a.W = W(w_off); a.bias = b_off >= 0 ? F(b_off) : nullptr; a.act = act;
+    a.W_f32 = p.w32 + w_off; a.split_ws = b.split_ws; a.split_ws_bytes = b.split_bytes;
     a.res = res; a.ldres = ldres; a.C = C; a.ldc = ldc;
     a.Cb = bf ? Cb : nullptr; a.ldcb = ldcb;
     if (!bf && Cb != nullptr && (void*)C != Cb) {  // fp32 mode: the typed output IS the fp32 output
@@ -370,7 +394,7 @@ struct Run {
   void gemm(const GemmArgs& a) {
     if (a.M <= 0 || (skip_mask() >> gemm_cat & 1)) return;
     prof_begin(gemm_cat, st);
-    chk(gemm_launch(a, bf, st));
+    chk(gemm_launch(a, gmode, st));
     prof_end(st);
   }
   template <typename... Ts> void gemm(const void* A, Ts... ts) { gemm(mk(A, ts...)); }
@@ -378,7 +402,7 @@ struct Run {
   void gemm_pair(const GemmArgs& c, const GemmArgs& pr) {
     if (c.M <= 0 || pr.M <= 0 || (skip_mask() >> gemm_cat & 1)) { gemm(c); gemm(pr); return; }
     prof_begin(gemm_cat, st);
-    chk(gemm_launch_pair(c, pr, bf, st));
+    chk(gemm_launch_pair(c, pr, gmode, st));
     prof_end(st);
   }
 
@@ -391,8 +415,9 @@ struct Run {
       return gcl_edge_pre(E, H, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st);
     });
     gemm_cat = CAT_GEMM_EDGE;
-    gemm(b.A1, H, H, gw.e2_w, H, gw.e2_b, FB_ACT_SILU, E, nullptr, 0, b.M, H);
-    const int tiles = gemm_dot_tiles(E, H, H, bf);
+    // training-mode dropout of the v1 stack (dropout_p > 0): edge_mlp output (egnn.py:82), node_mlp output (egnn.py:106)
+    gemm(wd(mk(b.A1, H, H, gw.e2_w, H, gw.e2_b, FB_ACT_SILU, E, nullptr, 0, b.M, H), dr(S_EDGE2)));
+    const int tiles = gemm_dot_tiles(E, H, H, gmode);
     gemm(b.M, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_SILU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st);
@@ -400,7 +425,7 @@ struct Run {
     gemm_cat = CAT_GEMM_NODE;
     if (need_h) {
       gemm(b.hT, H, H, gw.n1_w, H, gw.n1_b, FB_ACT_SILU, N, nullptr, 0, b.T1, H, nullptr, 0, b.agg, H, H);
-      gemm(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h, H, b.hT, H, b.h, H);
+      gemm(wd(mk(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h, H, b.hT, H, b.h, H), dr(S_NODE2)));
     }
   }
 
@@ -417,14 +442,15 @@ struct Run {
       return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
                            b.PB + (size_t)(layer * 2 + 0) * P * 4, b.O, HD, bf, st);
     });
-    gemm(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H);
+    // RowAttentionBlock dropout on the attention output (cross_att.py:128), row index = internal node id
+    gemm(wd(mk(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H), dr(S_PATT, Nc)));
     gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
     const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
     stage(CAT_ATTENTION, [&] {
       return row_attention(g, 0, p.max_c, p.max_p, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
                            b.PB + (size_t)(layer * 2 + 1) * P * 4, b.O, HD, bf, st);
     });
-    gemm(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H);
+    gemm(wd(mk(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H), dr(S_CATT)));
     // transitions (model_utils.py:171-175), residual
     void* THp = at(b.TH, (size_t)Nc * 2 * H);
     gemm_pair(mk(b.hT, H, H, aw.tc1_w, 2 * H, aw.tc1_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, 2 * H),
@@ -440,20 +466,24 @@ struct Run {
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
     stage(CAT_ATTENTION, [&] { return pair_gather(g, capU, H, b.P0, b.QK + 2 * H, ldqk, b.Zg, b.T64, bf, st); });
-    const int tiles2 = gemm_dot_tiles(capU, 2 * H, H, bf);
+    const int tiles2 = gemm_dot_tiles(capU, 2 * H, H, gmode);
     gemm_cat = CAT_GEMM_PAIR;
     gemm(b.Zg, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, b.T64, 64, 64,
          aw.pt2v, b.dotU, capU, u_dev);
     gemm_cat = CAT_GEMM_NODE;
     // FB_PB_FOLD=0 (A/B): separate pair_bias_finish launch + dense scatter instead of reading the row-dot partials in inter_logit
+#ifdef FB_DIAG
     static const bool pb_fold = [] { const char* e = getenv("FB_PB_FOLD"); return !(e && atoi(e) == 0); }();
+#else
+    const bool pb_fold = true;
+#endif
     if (!pb_fold) stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
     // --- interfacial attention (egnn.py:186-252)
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
     stage(CAT_ATTENTION, [&] {
       return inter_attention(g, p.cap_int, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
                              b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, b.lgt, b.sde, bf, st,
-                             nullptr, nullptr, nullptr, 1e-5f, DropCfg(), DropCfg(), pb_fold ? b.dotU : nullptr, tiles2, capU, F(aw.pt_c));
+                             nullptr, nullptr, nullptr, 1e-5f, DropCfg(), dr(S_AGG) /* egnn.py:236 */, pb_fold ? b.dotU : nullptr, tiles2, capU, F(aw.pt_c));
     });
   }
 
@@ -476,7 +506,7 @@ struct Run {
     gemm(wd(mk(b.A1, Dp, Dp, gw.e2_w, H, gw.e2_b, FB_ACT_RELU, E, nullptr, 0, b.M, H), dr(S_EDGE2)));
     // coord_mlp = MLPwoBias: LayerNorm on the edge message, Linear + ReLU, Linear(H,1) as the row-dot epilogue
     stage(CAT_EDGE_ELEMWISE, [&] { return ln_rows(b.M, true, H, H, nullptr, 0, 0, E, F(gw.cl_g), F(gw.cl_b), LN_EPS, b.M2, H, bf, st); });
-    const int tiles = gemm_dot_tiles(E, H, H, bf);
+    const int tiles = gemm_dot_tiles(E, H, H, gmode);
     gemm(wd(mk(b.M2, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_RELU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E),
             dr(S_GCOORD)));
     stage(CAT_EDGE_ELEMWISE, [&] {
@@ -535,7 +565,7 @@ struct Run {
     });
     gemm_cat = CAT_GEMM_PAIR;
     gemm(wd(mk(b.Zl, H, H, aw.pt1_w, H, aw.pt1_b, FB_ACT_RELU, (int)P, nullptr, 0, b.Zh, H), dr(S_PAIR1)));
-    const int tilesP = gemm_dot_tiles((int)P, H, H, bf);
+    const int tilesP = gemm_dot_tiles((int)P, H, H, gmode);
     gemm(wd(mk(b.Zh, H, H, aw.pt2_w, H, aw.pt2_b, FB_ACT_RELU, (int)P, nullptr, 0, pair_out, H, nullptr, 0, nullptr, 0, 0, aw.wb, b.dotP,
                (int)P), dr(S_PAIR2)));
     gemm_cat = CAT_GEMM_NODE;
@@ -692,12 +722,17 @@ using namespace fb;
 static bool params_ok(const fb_model_params* p) {
   return p && p->N > 0 && p->B > 0 && p->hidden > 0 && (p->hidden % 8) == 0 && p->hidden <= 512 && p->n_layers >= 0 &&
          p->n_iter >= 1 && p->Nc_tot > 0 && p->Nc_tot <= p->N && (p->flavour == FB_FLAVOUR_V1 || p->flavour == FB_FLAVOUR_PLUS) &&
-         p->dropout_p >= 0.f && p->dropout_p < 1.f && !(p->dropout_p > 0.f && p->flavour != FB_FLAVOUR_PLUS);
+         p->dropout_p >= 0.f && p->dropout_p < 1.f && p->bf16_mode >= FB_PREC_FP32 && p->bf16_mode <= FB_PREC_SPLIT6;
 }
 
 extern "C" {
 
 int32_t fb_abi_version(void) { return FB_ABI_VERSION; }
+
+#ifndef FB_SOURCE_HASH
+#define FB_SOURCE_HASH 0
+#endif
+int64_t fb_source_hash(void) { return (int64_t)FB_SOURCE_HASH; }
 
 int64_t fb_launch_count(void) { return (int64_t)g_launches.load(); }
 
@@ -792,7 +827,7 @@ const int32_t* fb_graph_ctx_count_ptr(const fb_model_params* p) {
 }
 
 int32_t fb_model_forward(const fb_model_params* p, void* stream) {
-  if (!params_ok(p) || p->E_ctx < 0) return FB_ERR_BAD_ARG;
+  if (!params_ok(p) || p->E_ctx < 0 || (p->bf16_mode != FB_PREC_FP32 && !p->w16)) return FB_ERR_BAD_ARG;
   const ModelW& w = weights_for(p->hidden, p->n_layers, p->flavour);
   Run r{*p, w};
   Arena ag(p->ws_graph, p->ws_graph_bytes, false);
@@ -803,7 +838,7 @@ int32_t fb_model_forward(const fb_model_params* p, void* stream) {
   r.g.ctx_row = r.b.ctx_row; r.g.ctx_col = r.b.ctx_col;
   r.g.int_row = r.b.int_row; r.g.int_col = r.b.int_col; r.g.int_pair = r.b.int_pair;
   r.st = (cudaStream_t)stream;
-  r.bf = p->bf16_mode != 0;
+  r.bf = p->bf16_mode == FB_PREC_BF16; r.gmode = p->bf16_mode;
   r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;
   r.TS = r.bf ? 2 : 4;
   r.forward();
@@ -816,6 +851,7 @@ int32_t fb_egnn_forward(const fb_model_params* p, const fb_egnn_extra* e, void* 
   if ((e->steps & FB_STEP_ATT) && (!e->pair0 || p->Nc_tot <= 0 || p->Nc_tot >= p->N)) return FB_ERR_BAD_ARG;
   if (e->E_int > p->cap_int) return FB_ERR_BAD_ARG;
   if (p->flavour != FB_FLAVOUR_V1 && p->flavour != FB_FLAVOUR_PLUS) return FB_ERR_BAD_ARG;
+  if (p->bf16_mode < FB_PREC_FP32 || p->bf16_mode > FB_PREC_SPLIT6 || (p->bf16_mode != FB_PREC_FP32 && !p->w16)) return FB_ERR_BAD_ARG;
   if (p->dropout_p != 0.f) return FB_ERR_UNSUPPORTED;           // sampling mode goes through fb_model_forward
   const ModelW& w = weights_for(p->hidden, p->n_layers, p->flavour);
   Run r{*p, w};
@@ -827,7 +863,7 @@ int32_t fb_egnn_forward(const fb_model_params* p, const fb_egnn_extra* e, void* 
   r.g.ctx_row = r.b.ctx_row; r.g.ctx_col = r.b.ctx_col;
   r.g.int_row = r.b.int_row; r.g.int_col = r.b.int_col; r.g.int_pair = r.b.int_pair;
   r.st = (cudaStream_t)stream;
-  r.bf = p->bf16_mode != 0;
+  r.bf = p->bf16_mode == FB_PREC_BF16; r.gmode = p->bf16_mode;
   r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;
   r.TS = r.bf ? 2 : 4;
   r.forward_egnn(*e);
@@ -863,21 +899,27 @@ static GemmArgs gemm_args_from(const fb_gemm_params* q) {
   a.A = q->A; a.lda = q->lda; a.K1 = q->K1; a.A2 = q->A2; a.lda2 = q->lda2; a.K2 = q->K2; a.W = q->W;
   a.bias = q->bias; a.act = q->act; a.res = q->res; a.ldres = q->ldres; a.C = q->C; a.ldc = q->ldc;
   a.Cb = q->Cb; a.ldcb = q->ldcb; a.dotv = q->dotv; a.dot_out = q->dot_out; a.dot_stride = q->dot_stride;
-  a.M = q->M; a.N = q->N; a.m_dev = q->m_dev;
+  a.M = q->M; a.N = q->N; a.m_dev = q->m_dev; a.n_split = q->n_split;
   a.drop = make_drop(q->drop_p, q->drop_seed, q->drop_site, q->drop_row0, q->drop_colonly);
+  a.split_ws = q->split_ws; a.split_ws_bytes = q->split_ws_bytes; a.W_f32 = q->W_f32;
   return a;
 }
+static bool prec_ok(int m) { return m >= FB_PREC_FP32 && m <= FB_PREC_SPLIT6; }
 
 int32_t fb_gemm(const fb_gemm_params* q, void* stream) {
   if (!q) return FB_ERR_BAD_ARG;
   const GemmArgs a = gemm_args_from(q);
-  if (q->force_simt) return gemm_simt_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
-  return gemm_launch(a, q->bf16_mode != 0, (cudaStream_t)stream);
+  if (!prec_ok(q->bf16_mode)) return FB_ERR_BAD_ARG;
+  if (q->force_simt) {
+    if (q->bf16_mode >= FB_PREC_SPLIT3) return FB_ERR_BAD_ARG;
+    return gemm_simt_launch(a, q->bf16_mode == FB_PREC_BF16, (cudaStream_t)stream);
+  }
+  return gemm_launch(a, q->bf16_mode, (cudaStream_t)stream);
 }
 
 int32_t fb_gemm_pair(const fb_gemm_params* q0, const fb_gemm_params* q1, void* stream) {
-  if (!q0 || !q1 || q0->bf16_mode != q1->bf16_mode) return FB_ERR_BAD_ARG;
-  return gemm_launch_pair(gemm_args_from(q0), gemm_args_from(q1), q0->bf16_mode != 0, (cudaStream_t)stream);
+  if (!q0 || !q1 || q0->bf16_mode != q1->bf16_mode || !prec_ok(q0->bf16_mode)) return FB_ERR_BAD_ARG;
+  return gemm_launch_pair(gemm_args_from(q0), gemm_args_from(q1), q0->bf16_mode, (cudaStream_t)stream);
 }
 
 int32_t fb_gemm_set_debug(int64_t* dbg) {
@@ -887,7 +929,11 @@ int32_t fb_gemm_set_debug(int64_t* dbg) {
 
 int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt) {
   if (force_simt) return gemm_simt_dot_tiles(N);
-  return gemm_dot_tiles(M, N, K, bf16_mode != 0);
+  return gemm_dot_tiles(M, N, K, bf16_mode);
+}
+
+int32_t fb_split_rows(const float* src, int32_t ld, int32_t M, int32_t K, void* dst, void* stream) {
+  return split_rows(src, ld, K, nullptr, 0, 0, M, dst, (cudaStream_t)stream);
 }
 
 }  // extern "C"

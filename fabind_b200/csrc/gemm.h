@@ -21,17 +21,32 @@ struct GemmArgs {
   int n_split = 0;                                       // >0: columns < n_split go to C only, the rest to Cb only (at column n - n_split)
   const int* m_dev = nullptr;                            // optional device-side row count (<= M)
   DropCfg drop;                                          // dropout after the activation, before residual / row-dot / stores
+  // split-precision modes (GEMM_SPLIT3 / GEMM_SPLIT6): A / A2 are fp32, W is the split weight [N, 3K] bf16 (three bf16 planes
+  // w0 | w1 | w2 with w0 + w1 + w2 == w, made by split_rows); split_ws = scratch for the split A operand, M x 3K bf16
+  void* split_ws = nullptr; size_t split_ws_bytes = 0;
+  const void* W_f32 = nullptr;                           // the same weight in fp32 [N, K]: shapes tcgen05 cannot take run on the FFMA kernel
+  int nprod = 0;                                         // set by the dispatcher: products per k-block (tc3 / tc4 kernels)
+  bool exact_act = false;                                // full-precision SiLU in the tcgen05 epilogues (split modes)
 };
 
+// precision modes of gemm_launch.  SPLITn: fp32 operands as sums of bf16 planes (x = x0 + x1 + x2, 8 mantissa bits each), the
+// product as n bf16 tensor-core products accumulated in fp32 (TMEM): n = 3 keeps the terms down to 2^-9 (x0 w0, x0 w1, x1 w0),
+// n = 6 the terms down to 2^-18 (+ x1 w1, x0 w2, x2 w0) -- fp32-grade accuracy on tcgen05.
+enum { GEMM_FP32 = 0, GEMM_BF16 = 1, GEMM_SPLIT3 = 2, GEMM_SPLIT6 = 3 };
+inline int gemm_mode_products(int mode) { return mode == GEMM_SPLIT3 ? 3 : mode == GEMM_SPLIT6 ? 6 : 0; }
+
 // number of N tiles (= number of row-dot partials per row) the kernel chosen for `bf16` will use
-int gemm_dot_tiles(int M, int N, int K, bool bf16_mode);
+int gemm_dot_tiles(int M, int N, int K, int mode);
 
 // returns FB_OK or an error code; never synchronises
-int gemm_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st);
+int gemm_launch(const GemmArgs& g, int mode, cudaStream_t st);
 
 // two independent problems over disjoint row ranges of one activation buffer (g1.A = g0.A + r * lda, same K):
 // one grouped launch when the tcgen05 path can take it, otherwise two launches
-int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, bool bf16_mode, cudaStream_t st);
+int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, int mode, cudaStream_t st);
+
+// fp32 rows -> three bf16 planes: dst[m, p * K + k] (p = 0..2), K = K1 + K2 ([A | A2] concatenated); K1, K2 multiples of 8
+int split_rows(const float* A, int lda, int K1, const float* A2, int lda2, int K2, int M, void* dst, cudaStream_t st);
 
 // implemented per backend
 int gemm_simt_launch(const GemmArgs& g, bool bf16_mode, cudaStream_t st);

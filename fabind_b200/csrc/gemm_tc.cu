@@ -275,7 +275,11 @@ static int launch_cfg(const GemmArgs& g, cudaStream_t st);
 long long* g_tc_dbg = nullptr;   // set through fb_gemm_set_debug (development probe)
 
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t st) {
+#ifdef FB_DIAG
   static int stages = [] { const char* e = getenv("FB_TC_STAGES"); return e ? atoi(e) : tc::STAGES_SEL; }();
+#else
+  const int stages = tc::STAGES_SEL;
+#endif
   if (stages == 4) return launch_cfg<tc::BN_SEL, 4>(g, st);
   if (stages == 6) return launch_cfg<tc::BN_SEL, 6>(g, st);
   return launch_cfg<tc::BN_SEL, 3>(g, st);

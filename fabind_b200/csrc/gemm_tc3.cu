@@ -46,11 +46,13 @@ struct Prob {
   int has_res, has_c, has_cb;
   const float* dotv; float* dot_out; int dot_stride;
   int n_split;
+  int exact_act;
   DropCfg drop;
 };
 struct Params {
   Prob q0, q1;
   int KB1, KB2;
+  int nprod;               // split-precision mode: products per k-block (0 = plain bf16); then KB1 = k-blocks of ONE plane
   const int* m_dev;
   long long* dbg;
 };
@@ -97,7 +99,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint32_t* tmem_slot = (uint32_t*)(resbar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = p.KB1 + p.KB2;
+  const int KB = p.nprod ? p.nprod * p.KB1 : p.KB1 + p.KB2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -162,6 +164,13 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + S::A_BYTES;
           mbar_expect_tx(&full[s], S::STAGE_BYTES);
+          if (p.nprod) {
+            // split precision: k-block kb = product j of plane pair (pa, pw), smallest terms first
+            const int j = kb / p.KB1, r = kb - j * p.KB1;
+            tma_load_2d(&map_a, &full[s], a_dst, (split_plane_a(j, p.nprod) * p.KB1 + r) * BK, m0);
+            tma_load_2d(&map_w, &full[s], b_dst, (split_plane_w(j, p.nprod) * p.KB1 + r) * BK, n0);
+            continue;
+          }
           if (kb < p.KB1) tma_load_2d(&map_a, &full[s], a_dst, kb * BK, m0);
           else tma_load_2d(&map_a2, &full[s], a_dst, (kb - p.KB1) * BK, m0);
           tma_load_2d((GROUPED && second) ? &map_w2 : &map_w, &full[s], b_dst, kb * BK, n0);
@@ -256,7 +265,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bv[ch], j);
-          if (pp.act == FB_ACT_SILU) x = silu_fast(x);
+          if (pp.act == FB_ACT_SILU) x = pp.exact_act ? silu(x) : silu_fast(x);
           else if (pp.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
@@ -342,6 +351,7 @@ static bool fill_prob(Prob& q, const GemmArgs& g, int m_begin, CUtensorMap* mc, 
   q.has_res = g.res != nullptr; q.has_c = g.C != nullptr; q.has_cb = g.Cb != nullptr;
   q.dotv = g.dotv; q.dot_out = g.dot_out; q.dot_stride = g.dot_stride;
   q.n_split = g.n_split;
+  q.exact_act = g.exact_act ? 1 : 0;
   q.drop = g.drop;
   const int nc = g.n_split > 0 ? g.n_split : g.N, ncb = g.n_split > 0 ? g.N - g.n_split : g.N;
   if (g.C && !tc_make_map_out(mc, g.C, true, (uint64_t)g.M, (uint64_t)nc, (uint64_t)g.ldc)) return false;
@@ -365,9 +375,10 @@ static int launch(const GemmArgs& g, const GemmArgs* g1, int m_begin1, cudaStrea
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   CUtensorMap ma, ma2, mw, mw2, mc, mcb, mres, mc1, mcb1, mres1;
-  const int K = g.K1 + g.K2;
+  // split precision: A and W hold three bf16 planes of K1 columns each
+  const int K = g.nprod ? 3 * g.K1 : g.K1 + g.K2;
   const int rows = g1 ? (m_begin1 + g1->M > g.M ? m_begin1 + g1->M : g.M) : g.M;
-  if (!tc_make_map(&ma, g.A, (uint64_t)rows, (uint64_t)g.K1, (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
+  if (!tc_make_map(&ma, g.A, (uint64_t)rows, (uint64_t)(g.nprod ? K : g.K1), (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
   if (g.K2 > 0) {
     if (!tc_make_map(&ma2, g.A2, (uint64_t)g.M, (uint64_t)g.K2, (uint64_t)g.lda2, BM)) return FB_ERR_CUDA;
   } else {
@@ -377,7 +388,7 @@ static int launch(const GemmArgs& g, const GemmArgs* g1, int m_begin1, cudaStrea
   mc = mcb = mres = ma;   // placeholders for absent operands (never dereferenced)
   Params p;
   if (!fill_prob(p.q0, g, 0, &mc, &mcb, &mres)) return FB_ERR_CUDA;
-  p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.m_dev = g.m_dev; p.dbg = g_tc_dbg;
+  p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.nprod = g.nprod; p.m_dev = g.m_dev; p.dbg = g_tc_dbg;
   int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   mc1 = mcb1 = mres1 = ma;
   if (g1) {
@@ -411,8 +422,12 @@ int gemm_tc2_bn(int M, int N);
 // 256-wide tiles of v3 lost to v2 on the long edge-level GEMMs (5.2 vs 3.4 ms/step); with two alternating boxes v3
 // is ahead there too (2.6 vs 3.0 ms/step), so the default is "no limit".
 static int tc3_max_m() {
+#ifdef FB_DIAG
   static int m = [] { const char* e = getenv("FB_TC3_MAXM"); return e ? atoi(e) : 1 << 30; }();
   return m;
+#else
+  return 1 << 30;
+#endif
 }
 
 int gemm_tc3_launch(const GemmArgs& g, cudaStream_t st) {
@@ -427,7 +442,7 @@ int gemm_tc3_launch(const GemmArgs& g, cudaStream_t st) {
 }
 
 int gemm_tc3_launch_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t st) {
-  if (g0.M <= 0 || g1.M <= 0) return FB_ERR_UNSUPPORTED;
+  if (g0.M <= 0 || g1.M <= 0 || g0.nprod || g1.nprod) return FB_ERR_UNSUPPORTED;
   if (g0.K2 || g1.K2 || g0.K1 != g1.K1 || g0.lda != g1.lda || g0.m_dev || g1.m_dev || g1.dotv) return FB_ERR_UNSUPPORTED;
   if ((g0.N % 128) || (g1.N % 128)) return FB_ERR_UNSUPPORTED;
   if ((g0.n_split % 64) || (g1.n_split % 64)) return FB_ERR_UNSUPPORTED;

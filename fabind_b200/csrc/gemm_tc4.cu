@@ -38,6 +38,7 @@ constexpr int STAGES = 5;
 
 struct Params {
   int M, N, KB1, KB2;
+  int nprod, exact_act;     // split-precision mode (see gemm.h): products per k-block, KB1 = k-blocks of ONE plane
   const float* bias; int act;
   int has_c, has_cb;
   const float* dotv; float* dot_out; int dot_stride;
@@ -123,7 +124,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int KB = p.KB1 + p.KB2;
+  const int KB = p.nprod ? p.nprod * p.KB1 : p.KB1 + p.KB2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -171,6 +172,12 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + S::A_BYTES;
           if (leader) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
+          if (p.nprod) {
+            const int j = kb / p.KB1, r = kb - j * p.KB1;
+            tma_load_2d_pair(&map_a, &full[s], a_dst, (split_plane_a(j, p.nprod) * p.KB1 + r) * BK, m0);
+            tma_load_2d_pair(&map_w, &full[s], b_dst, (split_plane_w(j, p.nprod) * p.KB1 + r) * BK, n0);
+            continue;
+          }
           if (kb < p.KB1) tma_load_2d_pair(&map_a, &full[s], a_dst, kb * BK, m0);
           else tma_load_2d_pair(&map_a2, &full[s], a_dst, (kb - p.KB1) * BK, m0);
           tma_load_2d_pair(&map_w, &full[s], b_dst, kb * BK, n0);
@@ -252,7 +259,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bv[ch], j);
-          if (p.act == FB_ACT_SILU) x = silu_fast(x);
+          if (p.act == FB_ACT_SILU) x = p.exact_act ? silu(x) : silu_fast(x);
           else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
@@ -325,8 +332,8 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   CUtensorMap ma, ma2, mw, mc, mcb;
-  const int K = g.K1 + g.K2;
-  if (!tc_make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)g.K1, (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
+  const int K = g.nprod ? 3 * g.K1 : g.K1 + g.K2;   // split precision: three bf16 planes of K1 columns each
+  if (!tc_make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)(g.nprod ? K : g.K1), (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
   if (g.K2 > 0) {
     if (!tc_make_map(&ma2, g.A2, (uint64_t)g.M, (uint64_t)g.K2, (uint64_t)g.lda2, BM)) return FB_ERR_CUDA;
   } else {
@@ -338,7 +345,7 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
   if (g.C && !tc_make_map_out(&mc, g.C, true, (uint64_t)g.M, (uint64_t)nc, (uint64_t)g.ldc)) return FB_ERR_CUDA;
   if (g.Cb && !tc_make_map_out(&mcb, g.Cb, false, (uint64_t)g.M, (uint64_t)ncb, (uint64_t)g.ldcb)) return FB_ERR_CUDA;
   Params p;
-  p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK;
+  p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.nprod = g.nprod; p.exact_act = g.exact_act ? 1 : 0;
   p.bias = g.bias; p.act = g.act; p.has_c = g.C != nullptr; p.has_cb = g.Cb != nullptr;
   p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride; p.n_split = g.n_split; p.m_dev = g.m_dev; p.drop = g.drop;
   const int tiles = ((g.M + PM - 1) / PM) * (g.N / BN);
@@ -353,9 +360,13 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
 
 int gemm_tc2_bn(int M, int N);
 
-// FB_ERR_UNSUPPORTED -> the caller goes on to the v3 kernel.  FB_TC4=0 disables the CTA-pair kernel (A/B comparisons).
+// FB_ERR_UNSUPPORTED -> the caller goes on to the v3 kernel.  FB_TC4=0 disables the CTA-pair kernel (A/B comparisons, -DFB_DIAG builds).
 int gemm_tc4_launch(const GemmArgs& g, cudaStream_t st) {
+#ifdef FB_DIAG
   static const bool on = [] { const char* e = getenv("FB_TC4"); return !(e && atoi(e) == 0); }();
+#else
+  const bool on = true;
+#endif
   if (!on || g.M <= 0) return FB_ERR_UNSUPPORTED;
   if (gemm_tc2_bn(g.M, g.N) != 256 || g.res || (g.C && g.Cb)) return FB_ERR_UNSUPPORTED;
   if (g.m_dev && (g.C || g.Cb)) return FB_ERR_UNSUPPORTED;

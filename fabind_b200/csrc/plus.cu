@@ -389,7 +389,11 @@ int pair_zin_plus(const GraphDev& g, int P_total, int H, const void* pair, const
                   const float* bo, const float* gamma, const float* beta, float eps, void* Zl, bool bf16_mode, cudaStream_t st) {
   if (P_total <= 0) return FB_OK;
   if ((H & 3) || H > 512) return FB_ERR_UNSUPPORTED;
+#ifdef FB_DIAG
   static const bool use_mma = [] { const char* e = getenv("FB_PZ_MMA"); return !(e && atoi(e) == 0); }();
+#else
+  const bool use_mma = true;
+#endif
   if (bf16_mode && (H & 31) == 0 && use_mma) {
     const int smem_m = (H >> 3) * 64 * 8 + 3 * H * 4;
     const int grid_m = std::max(1, std::min(148 * 4, (P_total + 127) / 128));

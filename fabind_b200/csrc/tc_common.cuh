@@ -41,6 +41,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// split-precision k-block walk: product j (0 .. nprod-1) multiplies plane split_plane_a of A with plane split_plane_w of W.
+// Six products, smallest terms first: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0); three products = the last three.
+__device__ __forceinline__ int split_plane_a(int j, int nprod) { return (0x001102 >> (4 * (j + 6 - nprod))) & 0xF; }
+__device__ __forceinline__ int split_plane_w(int j, int nprod) { return (0x010120 >> (4 * (j + 6 - nprod))) & 0xF; }
+
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

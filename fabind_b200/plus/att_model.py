@@ -43,6 +43,7 @@ class EfficientMCAttModel(nn.Module):
                          coord_clamp=float(normalize_coord(10)), las_clamp=float(normalize_coord(15)),
                          las_step=float(args.geometry_reg_step_size), flavour=_lib.FLAVOUR_PLUS)
         self._packed = PackedWeights()
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._packed.invalidate())
         self.precision = os.environ.get("FABIND_B200_PRECISION", "fp32")
         self.return_pair = True    # False: skip the dense [B, max_p, max_c, H] fp32 copy of the pair embedding (returns None)
         # train() mode = the reference's SAMPLING mode (P/test_sampling_fabind.py:118-124 runs the model in train() mode
@@ -54,24 +55,41 @@ class EfficientMCAttModel(nn.Module):
         self.last_stats = None
         self.debug_trace = False
 
+    def _apply(self, fn, *a, **k):
+        self._packed.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def invalidate_packed_weights(self):
+        """call after editing parameters through `.data` (see fabind_b200.runtime.PackedWeights)"""
+        self._packed.invalidate()
+
     def forward(self, X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index,
                 batched_complex_coord_LAS, LAS_mask=None):
         dropout, n_iter = None, None
         if self.training:
             if torch.is_grad_enabled():
-                raise NotImplementedError("fabind_b200: backward kernels are not built; train() mode is served as the "
-                                          "reference's dropout SAMPLING mode only - wrap the call in torch.no_grad()")
+                # FABind+ training step: the reverse pass of this layout (fabind_b200/train.py) differentiates the eval-mode
+                # arithmetic; its dropout masks are not threaded through the reverse kernels yet, so refuse rather than train a
+                # different objective silently
+                if self.dropout_p > 0:
+                    raise NotImplementedError("fabind_b200.plus: train() with autograd needs dropout_p = 0 (the FABind+ reverse pass "
+                                              "carries no dropout masks yet); sampling mode = train() under torch.no_grad()")
+                from .. import train
+                return train.forward_with_grad(self, dict(X=X, H=H, batch_id=batch_id, segment_id=segment_id, mask=mask,
+                                                          is_global=is_global, compound_edge_index=compound_edge_index,
+                                                          LAS_edge_index=LAS_edge_index,
+                                                          batched_complex_coord_LAS=batched_complex_coord_LAS, LAS_mask=LAS_mask))
             seed = self.dropout_seed if self.dropout_seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
             dropout = (self.dropout_p, seed, self.dropout_colonly)
             if self.random_n_iter:        # att_model.py:199-202: iter_i = random.randint(1, n_iter) in training mode
                 import random
                 n_iter = random.randint(1, self.n_iter)
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         with torch.no_grad():
             H_out, stats, e_ctx, tr, pair = model_forward(self, self._packed, X, H, batch_id, segment_id, mask, is_global,
                                                           compound_edge_index, LAS_edge_index, batched_complex_coord_LAS,
-                                                          self._cfg, self.precision == "bf16", trace=self.debug_trace,
+                                                          self._cfg, self.precision, trace=self.debug_trace,
                                                           want_pair=self.return_pair, dropout=dropout, n_iter=n_iter)
         self.last_stats = dict(inter_edges_per_iter=stats, ctx_edges=e_ctx, trace=tr)
         return X, H_out, pair

@@ -23,31 +23,75 @@ def current_stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def precision_mode(precision):
+    """'fp32' | 'bf16' | 'bf16x3' | 'fp32_tc' (or a bool: bf16 yes / no) -> FB_PREC_*"""
+    if isinstance(precision, str):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        return _lib.PRECISIONS[precision]
+    return int(precision)
+
+
+def split_arena(w32, hidden, n_layers, flavour):
+    """The weight arena of the split-precision modes: every matrix slot (rows, cols, off) as three bf16 planes [rows, 3*cols] at
+    element 3*off (fb_split_rows: w = w0 + w1 + w2, 8 mantissa bits per plane); vector slots are read from the fp32 arena."""
+    from .weights import slots
+    l = _lib.lib()
+    out = torch.zeros(3 * w32.numel(), dtype=torch.bfloat16, device=w32.device)
+    st = current_stream_ptr(w32.device)
+    for name, r, c, off in slots(hidden, n_layers, flavour):
+        if r <= 1 or r * c == 0 or c % 8:
+            continue
+        _lib.check(l.fb_split_rows(w32.data_ptr() + 4 * off, c, r, c, out.data_ptr() + 2 * 3 * off, st), "fb_split_rows")
+    return out
+
+
 class PackedWeights:
-    """fp32 (and bf16) weight arenas on the device, re-packed when any parameter changes."""
+    """fp32 (and bf16 / split-bf16) weight arenas on the device, re-packed when any parameter changes.
+
+    What "changes" means: the key holds, per parameter, `_version` and `data_ptr()`.  Optimizer steps, `load_state_dict`, `.to()`,
+    `.half()` and in-place ops on the Parameter bump one of them; the owning modules additionally call `invalidate()` from
+    `_apply` and a load_state_dict post-hook, which also re-walks the module tree (parameters REPLACED by new Parameter objects).
+    Writes through `.data` (`p.data.copy_(ema)`) change neither: call `model.invalidate_packed_weights()` after such edits, or
+    set `strict=True`, which folds a content fingerprint (sum of squares of all parameters: a few fused launches) into the key."""
 
     def __init__(self):
         self.key = None
         self.w32 = None
-        self.w16 = None
+        self.w16 = {}
+        self.params = None
+        self.strict = False
+
+    def invalidate(self):
+        self.key = None
         self.params = None
 
-    def get(self, module, hidden, n_layers, device, want_bf16, flavour=0):
+    def get(self, module, hidden, n_layers, device, mode, flavour=0):
         # the Parameter OBJECTS of a module persist across load_state_dict / .to() / in-place optimizer updates (which bump
         # _version or change data_ptr), so the module tree is walked once; walking it on every call cost 0.3 ms of host time
         # during which the GPU sat idle at the start of each forward
+        mode = precision_mode(mode)
         if self.params is None:
             self.params = list(module.parameters())
         params = self.params
         key = (device, flavour, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        if self.strict:
+            key = key + (float(torch.stack(torch._foreach_norm([p.detach() for p in params])).double().square().sum()),)
         if key != self.key:
             arena = pack_state_dict(module.state_dict(), hidden, n_layers, flavour)
             self.w32 = arena.to(device)
-            self.w16 = None
+            self.w16 = {}
             self.key = key
-        if want_bf16 and self.w16 is None:
-            self.w16 = self.w32.to(torch.bfloat16)
-        return self.w32, self.w16
+        w16 = None
+        if mode == _lib.PREC_BF16:
+            w16 = self.w16.get("bf16")
+            if w16 is None:
+                w16 = self.w16["bf16"] = self.w32.to(torch.bfloat16)
+        elif mode in (_lib.PREC_SPLIT3, _lib.PREC_SPLIT6):
+            w16 = self.w16.get("split")
+            if w16 is None:
+                w16 = self.w16["split"] = split_arena(self.w32, hidden, n_layers, flavour)
+        return self.w32, w16
 
 
 def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, bonds, las, X_las, cfg, bf16, trace=False,
@@ -87,7 +131,8 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     lay = build_layout(batch_id, segment_id, is_global, mask, dev)
     _mark("build_layout")
     flavour = cfg.get("flavour", _lib.FLAVOUR_V1)
-    w32, w16 = packed.get(module, hidden, cfg["n_layers"], dev, bf16, flavour)
+    mode = precision_mode(bf16)
+    w32, w16 = packed.get(module, hidden, cfg["n_layers"], dev, mode, flavour)
     H_out = torch.empty((N, hidden), dtype=torch.float32, device=dev)
     stats = torch.zeros(cfg["n_iter"], dtype=torch.int32, device=dev)
 
@@ -95,7 +140,7 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.N, p.B, p.Nc_tot, p.P_total = lay.N, lay.B, lay.Nc_tot, lay.P_total
     p.hidden, p.n_layers, p.n_iter = hidden, cfg["n_layers"], cfg["n_iter"]
     p.n_bond, p.n_las = bonds.shape[1], las.shape[1]
-    p.E_ctx, p.cap_int, p.bf16_mode = 0, lay.cap_int, 1 if bf16 else 0
+    p.E_ctx, p.cap_int, p.bf16_mode = 0, lay.cap_int, mode
     p.fb_atom, p.fb_res = lay.fb_atom, lay.fb_res
     p.max_c, p.max_p = lay.max_c, lay.max_p
     p.intra_cutoff, p.inter_cutoff = cfg["intra_cutoff"], cfg["inter_cutoff"]

@@ -2,20 +2,22 @@
 
 Reference semantics (att_model.py:210-246, refine='refine_coord'): the first `n_iter - 1` refinement iterations run under no_grad
 and only move the ligand; the last one is differentiated.  So a step is
-  1. iterations 0 .. n_iter-2: the inference path (`EfficientMCAttModel.forward`, one fb_model_forward call);
+  1. iterations 0 .. n_iter-2: the inference path (one fb_model_forward call, training-mode dropout masks included);
   2. edge lists of the last iteration from the graph builder (`ComplexGraph.construct_edges`, bit-exact), mapped to the internal
      node order;
   3. `backward.stack_forward_train_v1` (training-mode forward of the last iteration, keeps what the reverse pass needs);
   4. the caller's loss on (X, H) -> gradients of the outputs (the losses of main_fabind.py:380-401 live outside the path);
   5. `backward.stack_backward_v1` -> gradient of the weight arena -> `weights.arena_grads_to_state_dict` -> parameter `.grad`s;
   6. `shard.allreduce_gradients` over the ranks (one flat NCCL collective).
-`n_iter` is used as configured (the reference draws randint(1, n_iter) per step when --random-n-iter is set, att_model.py:210-211);
-dropout is not applied (the reference's 0.1 dropout of the v1 stack is the caller's choice to disable for parity).
+`n_iter`: the reference draws randint(1, n_iter) per step when --random-n-iter is set (att_model.py:210-211); `forward_with_grad`
+does the same.  Dropout (v1 layout): the reference trains the stack with nn.Dropout(0.1) at egnn.py:82,106,236,398,461 and
+cross_att.py:128; the same sites carry the library's counter-based masks here, in the no_grad iterations (fused into the inference
+kernels' epilogues), in the training-mode forward and -- the identical mask function -- in the reverse pass.  The FABind+ layout's
+reverse pass carries no masks yet: `plus.EfficientMCAttModel` refuses train()+autograd with dropout_p > 0.
 
-Status: the assembly below is validated on the CPU against the unmodified reference's parameter gradients with the kernel
-wrappers and the two GPU providers (earlier iterations, graph builder) replaced by their specifications
-(tests/test_backward_orchestration.py::test_training_step_assembly).  It has not run on a GPU yet (gated test in
-tests/test_gpu_train_forward.py), so `EfficientMCAttModel.forward` in train() mode still raises instead of routing here.
+Status: parity-green on a B200 (tests/test_gpu_train_forward.py: training-mode forward, reverse pass and the assembled step against
+the unmodified reference's parameter gradients, both layouts) and on the CPU with the kernel wrappers replaced by their
+specifications (tests/test_backward_orchestration.py).  `EfficientMCAttModel.forward` routes here in train() mode with autograd.
 """
 import torch
 
@@ -63,20 +65,19 @@ def internal_graph(lay, ctx_edges, inter_edges, bonds, las, device):
     return geo, edges, perm, moves
 
 
-def _gpu_prev_coords(model, fa):
-    """iterations 0 .. n_iter-2 through the inference path (in place on a copy of X)"""
-    n = model._cfg["n_iter"]
-    X = fa["X"].clone()
+def _gpu_prev_coords(model, fa, n_iter=None, dropout=None):
+    """iterations 0 .. n_iter-2 through the inference path (in place on a copy of X; the module's mode flags and configuration are
+    not touched).  dropout = (p, seed, colonly) or None: training-mode masks of those iterations."""
+    from .runtime import model_forward
+    n = model._cfg["n_iter"] if n_iter is None else int(n_iter)
+    X = fa["X"].detach().clone()
     if n <= 1:
         return X
-    was_training = model.training
-    model._cfg["n_iter"] = n - 1
-    try:
-        model.eval()
-        model(**{**fa, "X": X})
-    finally:
-        model._cfg["n_iter"] = n
-        model.train(was_training)
+    plus = int(model._cfg.get("flavour", 0)) == 1
+    with torch.no_grad():
+        model_forward(model, model._packed, X, fa["H"].detach(), fa["batch_id"], fa["segment_id"], fa["mask"], fa["is_global"],
+                      fa["compound_edge_index"], fa["LAS_edge_index"], fa["batched_complex_coord_LAS"], model._cfg,
+                      getattr(model, "precision", "fp32"), want_pair=False if plus else None, dropout=dropout, n_iter=n - 1)
     return X
 
 
@@ -85,20 +86,27 @@ def _gpu_edges(model, X_prev, fa):
     return ctx, inter
 
 
-def _forward_half(model, fa, prev_coords, edge_lists, state_dict=None):
-    """steps 1-3: everything up to the outputs; returns (X_out, H_out, pair rows or None, state for the reverse half)"""
+def _forward_half(model, fa, prev_coords=None, edge_lists=None, state_dict=None, n_iter=None, dropout=None):
+    """steps 1-3: everything up to the outputs; returns (X_out, H_out, pair rows or None, state for the reverse half).
+    prev_coords(model, fa) / edge_lists(model, X_prev, fa): the two GPU providers (None = the library's); n_iter: refinement
+    iterations of this step (default: configured); dropout = (p, seed, colonly) or None (v1 layout only)."""
     cfg = model._cfg
     H, L, flavour = cfg["hidden"], cfg["n_layers"], int(cfg.get("flavour", 0))
+    n_iter = cfg["n_iter"] if n_iter is None else int(n_iter)
+    if dropout is not None and dropout[0] > 0 and flavour == 1:
+        raise NotImplementedError("fabind_b200.train: the FABind+ reverse pass carries no dropout masks")
     dev = fa["H"].device
     sd = state_dict if state_dict is not None else {k: v.detach() for k, v in model.state_dict().items()}
-    X_prev = prev_coords(model, fa)
-    ctx, inter = edge_lists(model, X_prev, fa)
+    X_prev = prev_coords(model, fa) if prev_coords is not None else _gpu_prev_coords(model, fa, n_iter, dropout)
+    ctx, inter = (edge_lists or _gpu_edges)(model, X_prev, fa)
     lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
     geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
     arena = pack_state_dict(sd, H, L, flavour, device=dev)
     weights = slot_tensors(arena, H, L, flavour)
     consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,
                   xl=fa["batched_complex_coord_LAS"].reshape(-1, 3)[perm].to(torch.float32).contiguous())
+    if dropout is not None and dropout[0] > 0:
+        consts["drop"] = bw.Drop(dropout[0], dropout[1], dropout[2], n_iter - 1)    # masks of the LAST (differentiated) iteration
     Hin = fa["H"].detach()[perm].to(torch.float32).contiguous()
     x_state = X_prev[:, 0][perm].to(torch.float32).contiguous()
     pair = None
@@ -136,14 +144,14 @@ def _backward_half(st, gX, gH, gP=None):
     return pgrads, gH_in
 
 
-def training_step(model, fa, output_grads, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, state_dict=None):
+def training_step(model, fa, output_grads, prev_coords=None, edge_lists=None, state_dict=None, n_iter=None, dropout=None):
     """model: fabind_b200.EfficientMCAttModel (v1 layout) or fabind_b200.plus.EfficientMCAttModel (FABind+ layout, eval-mode masks).
     fa: the forward arguments (X, H, batch_id, segment_id, mask, is_global, compound_edge_index, LAS_edge_index, batched_complex_coord_LAS).
     output_grads: v1  (X_out, H_out) -> (dL/dX_out, dL/dH_out);  FABind+  (X_out, H_out, pair rows [P,H]) -> (dL/dX, dL/dH, dL/dpair rows)
     (caller node order; pair rows packed per complex as [Np', Nc'] blocks).
     Returns (X_out, H_out[, pair rows], {parameter name: gradient}, dL/dH_in).  prev_coords / edge_lists: the two GPU providers
     (replaceable by their specifications in CPU tests)."""
-    X_out, H_out, pair, st = _forward_half(model, fa, prev_coords, edge_lists, state_dict)
+    X_out, H_out, pair, st = _forward_half(model, fa, prev_coords, edge_lists, state_dict, n_iter, dropout)
     if st["flavour"] == 1:
         gX, gH, gP = output_grads(X_out, H_out, pair)
         pgrads, gH_in = _backward_half(st, gX, gH, gP)
@@ -158,8 +166,9 @@ class _StackFunction(torch.autograd.Function):
     stack's parameters and the incoming node features through it; everything inside runs on the library's kernels."""
 
     @staticmethod
-    def forward(ctx, model, fa, prev_coords, edge_lists, names, H_in, *params):
-        X_out, H_out, pair, st = _forward_half(model, fa, prev_coords, edge_lists, {n: p.detach() for n, p in zip(names, params)})
+    def forward(ctx, model, fa, prev_coords, edge_lists, names, step, H_in, *params):
+        X_out, H_out, pair, st = _forward_half(model, fa, prev_coords, edge_lists, {n: p.detach() for n, p in zip(names, params)},
+                                               step["n_iter"], step["dropout"])
         ctx.st, ctx.names, ctx.h_dtype = st, names, H_in.dtype
         ctx.pmeta = [(p.device, p.dtype) for p in params]
         if pair is None:
@@ -170,17 +179,18 @@ class _StackFunction(torch.autograd.Function):
     def backward(ctx, gX, gH, gP=None):
         # (autograd materialises undefined output gradients as zeros: gX / gH / gP are always tensors here)
         pgrads, gH_in = _backward_half(ctx.st, gX, gH, gP)
-        out = [None, None, None, None, None, gH_in.to(ctx.h_dtype)]
-        for n, (dev, dt), p_needs in zip(ctx.names, ctx.pmeta, ctx.needs_input_grad[6:]):
+        out = [None, None, None, None, None, None, gH_in.to(ctx.h_dtype)]
+        for n, (dev, dt), p_needs in zip(ctx.names, ctx.pmeta, ctx.needs_input_grad[7:]):
             out.append(pgrads[n].to(dev, dt) if p_needs else None)      # the packer's chain rule runs on the host
         return tuple(out)
 
 
-def forward_with_grad(model, fa, prev_coords=_gpu_prev_coords, edge_lists=_gpu_edges, n_iter=None):
+def forward_with_grad(model, fa, prev_coords=None, edge_lists=None, n_iter=None, dropout=None):
     """`EfficientMCAttModel.forward` with autograd: returns (X, H[, pair rows]) attached to the graph, so an unchanged training loop
     (`loss.backward()`, optimizer over `model.parameters()`) trains the drop-in module.  Buffers / non-float entries of the state_dict
     are passed through untouched.  n_iter: refinement iterations of this step; default = the reference's rule (att_model.py:210-211:
-    `random.randint(1, n_iter)` in train() mode when --random-n-iter is set, else the configured n_iter)."""
+    `random.randint(1, n_iter)` in train() mode when --random-n-iter is set, else the configured n_iter).  dropout = (p, seed,
+    colonly) or None.  The module's configuration is not mutated (re-entrant across streams / threads)."""
     full = model._cfg["n_iter"]
     if n_iter is None:
         n_iter = full
@@ -189,11 +199,8 @@ def forward_with_grad(model, fa, prev_coords=_gpu_prev_coords, edge_lists=_gpu_e
             n_iter = random.randint(1, full)
     named = [(n, p) for n, p in model.state_dict(keep_vars=True).items() if torch.is_floating_point(p)]
     names = [n for n, _ in named]
-    model._cfg["n_iter"] = int(n_iter)
-    try:
-        out = _StackFunction.apply(model, fa, prev_coords, edge_lists, names, fa["H"], *[p for _, p in named])
-    finally:
-        model._cfg["n_iter"] = full
+    step = dict(n_iter=int(n_iter), dropout=dropout)
+    out = _StackFunction.apply(model, fa, prev_coords, edge_lists, names, step, fa["H"], *[p for _, p in named])
     X = fa["X"]
     with torch.no_grad():
         X.copy_(out[0].detach())                 # the reference updates the caller's X in place (att_model.py:236,245)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 3
+#define FB_ABI_VERSION 4
 
 /* One batch of complexes + model dimensions.  Node layout in caller order is the reference
  * dataloader's [glb_c | atoms | glb_p | residues] per complex (utils/utils.py:328-335). */
@@ -37,7 +37,9 @@ typedef struct fb_model_params {
   int32_t n_las;      /* columns of LAS_edge_index */
   int32_t E_ctx;      /* context edges (bonds + geometric); read back after fb_graph_static */
   int32_t cap_int;    /* capacity of the interface edge list: 2 * sum n_c*n_p (worst case) */
-  int32_t bf16_mode;  /* 0: fp32 parity mode (FFMA GEMMs); 1: bf16 operands, fp32 accumulate (tcgen05) */
+  int32_t bf16_mode;  /* precision mode, FB_PREC_*: 0 fp32 (FFMA GEMMs); 1 bf16 operands, fp32 accumulate (tcgen05);
+                       * 2 / 3 (ABI 4) fp32 activations with the GEMMs on tcgen05 as 3 / 6 bf16 products per term
+                       * (x = x0 + x1 + x2 in bf16 planes, fp32 accumulation in TMEM): 3 = fp32-grade accuracy ("fp32_tc") */
   int32_t max_c, max_p;    /* largest compound-side / protein-side node count of any complex (launch bounds) */
   int32_t fb_atom, fb_res; /* internal ids of the first ligand atom / first residue of complex 0 (att_model.py:85-86) */
   /* ---- geometry constants, already divided by coordinate_scale ---- */
@@ -60,7 +62,8 @@ typedef struct fb_model_params {
   const int32_t* pair_base; /* [B+1] */
   /* ---- weights: flat arenas laid out by fb_weight_slot_* ---- */
   const float* w32;
-  const void* w16;          /* bf16 copy of the same arena (bf16_mode only) */
+  const void* w16;          /* FB_PREC_BF16: bf16 copy of the same arena; FB_PREC_SPLIT3/6: the split arena, 3 x the elements:
+                             * slot (rows, cols, off) holds [rows, 3*cols] bf16 at element 3*off = fb_split_rows of the fp32 slot */
   /* ---- scratch ---- */
   void* ws_graph; size_t ws_graph_bytes;   /* >= fb_graph_workspace_bytes */
   void* ws_main;  size_t ws_main_bytes;    /* >= fb_model_workspace_bytes */
@@ -82,12 +85,21 @@ typedef struct fb_model_params {
    * values scaled by 1/(1-p).  dropout_colonly = 1 drops whole feature columns (row ignored): test mode that pins the
    * placement of every mask against the unmodified reference.  FB_FLAVOUR_PLUS only. */
   float dropout_p; uint32_t dropout_seed; int32_t dropout_colonly;
+  /* ABI 4: dropout is also served for FB_FLAVOUR_V1 -- the training-mode forward of the reference (models/egnn.py:82,106,236,
+   * 398,461; models/cross_att.py:128), same sites / hash as the FABind+ stack where the layouts share them. */
 } fb_model_params;
 #define FB_FLAVOUR_V1 0
 #define FB_FLAVOUR_PLUS 1
+#define FB_PREC_FP32 0
+#define FB_PREC_BF16 1
+#define FB_PREC_SPLIT3 2
+#define FB_PREC_SPLIT6 3
 
-/* [host] library identification */
+/* [host] library identification.  fb_source_hash: 63-bit digest of include/fabind_b200.h + every file under csrc/ at build
+ * time (fabind_b200/build.py passes it as -DFB_SOURCE_HASH); the binding recomputes it from the sources next to it and refuses
+ * a library built from different ones -- a stale .so with shifted arguments must not load. */
 int32_t fb_abi_version(void);
+int64_t fb_source_hash(void);
 
 /* Instrumentation for bench.py.  fb_launch_count: kernels launched by this library since load.
  * fb_prof_enable(1): every stage of fb_model_forward is bracketed by CUDA events on its stream, tagged
@@ -173,7 +185,14 @@ typedef struct fb_gemm_params {
   int32_t force_simt;   /* 1: never take the tcgen05 path */
   /* ABI 3: dropout after the activation, before residual / row-dot / stores (0 = off); row index = row + drop_row0 */
   float drop_p; uint32_t drop_seed; uint32_t drop_site; int32_t drop_row0; int32_t drop_colonly;
+  /* ABI 4: split-precision modes (bf16_mode = FB_PREC_SPLIT3 / 6): A, A2 fp32; W = fb_split_rows of the fp32 weight ([N, 3K] bf16);
+   * split_ws = scratch of at least M * 3K * 2 bytes for the split A operand; W_f32 = the fp32 weight, used when the shape does not
+   * tile on tcgen05 (optional: without it such shapes return FB_ERR_UNSUPPORTED).  All outputs are fp32 (Cb too, under n_split). */
+  void* split_ws; size_t split_ws_bytes; const float* W_f32;
+  int32_t n_split;      /* >0: columns < n_split go to C, the rest to Cb at column n - n_split (multiple of 128) */
 } fb_gemm_params;
+/* fp32 rows -> three bf16 planes, dst[m, p*K + k] (p = 0..2) with src = p0 + p1 + p2 to 2^-27: the operand format of the split modes */
+int32_t fb_split_rows(const float* src, int32_t ld, int32_t M, int32_t K, void* dst, void* stream);
 int32_t fb_gemm(const fb_gemm_params* g, void* stream);
 /* two layers over disjoint row ranges of ONE activation buffer (g1->A = g0->A + r*lda rows, r >= g0->M, same K):
  * one grouped tcgen05 launch when both qualify, otherwise the two launches in order.  This is how the stack runs
@@ -291,6 +310,11 @@ int32_t fb_rowdot2(const float* A, int32_t lda, const float* B, int32_t ldb, int
 int32_t fb_rows_update(float* A, int32_t lda, int32_t M, int32_t N, const float* u, const float* v, int32_t mode, void* stream);
 /* op 0: c = a*b, 1: c = a+b, 2: c += a*b */
 int32_t fb_vec_op(const float* a, const float* b, float* c, int64_t n, int32_t op, void* stream);
+/* nn.Dropout of the training step (egnn.py:82,106,236,398,461; cross_att.py:128) as a stand-alone op, forward and reverse alike:
+ * dst[m,n] = keep(seed, site, row0 + m, n) ? src[m,n] / (1-p) : 0 with the library's counter-based mask (fb_model_params.dropout_*);
+ * dst may alias src */
+int32_t fb_dropout_apply(const float* src, float* dst, int32_t ld, int32_t M, int32_t N, float p, uint32_t seed, uint32_t site,
+                         int32_t row0, int32_t colonly, void* stream);
 /* reverse of scatter_softmax over the destination row (egnn.py:221): dlogit = alpha (dalpha - segsum(alpha dalpha)); t_zeroed[N] scratch */
 int32_t fb_softmax_seg_bwd(const float* alpha, const float* dalpha, const int32_t* row, int32_t E, float* t_zeroed, float* dlogit,
                            void* stream);

@@ -149,14 +149,31 @@ def radial_per_sample(edges, x, batch_id):
 # ------------------------------------------------------------------------------------------------
 # MC_E_GCL  (models/egnn.py:20-144)
 # ------------------------------------------------------------------------------------------------
-def gcl_forward(sd, pre, h, edges, x, batch_id, clamp):
+def _nodrop(x, layer, name):
+    return x
+
+
+def make_drop(dropout, it):
+    """Training-mode dropout of the v1 stack (models/egnn.py:82,106,236,398,461, models/cross_att.py:128) with the deterministic
+    COLUMN-ONLY masks of fabind_b200/dropout.py (the form the goldens of scripts/make_golden.py::main_grad_dropout pin against the
+    unmodified reference): dropout = (p, seed, colonly=True) or None; `it` = refinement iteration."""
+    if dropout is None or dropout[0] <= 0:
+        return _nodrop
+    p, seed, colonly = dropout
+    if not colonly:
+        raise NotImplementedError("the oracle restates column-only masks (row x column masks depend on the library's internal row order)")
+    from fabind_b200.dropout import keep_mask, site_id, iter_seed
+    return lambda x, layer, name: x * keep_mask(iter_seed(seed, it), site_id(layer, name), 1, x.shape[-1], p, colonly=True)[0]
+
+
+def gcl_forward(sd, pre, h, edges, x, batch_id, clamp, drop=_nodrop, layer=0):
     row, col = edges
     n = h.shape[0]
     radial, diff = radial_per_sample(edges, x, batch_id)
     # edge_model (egnn.py:68-87): cat[h_row, h_col, radial] -> Linear -> SiLU -> Linear -> SiLU
     m = torch.cat([h[row], h[col], radial.reshape(radial.shape[0], -1)], dim=1)
     m = F.silu(_lin(sd, pre + "edge_mlp.0", m))
-    m = F.silu(_lin(sd, pre + "edge_mlp.2", m))
+    m = drop(F.silu(_lin(sd, pre + "edge_mlp.2", m)), layer, "edge2")      # egnn.py:82
     # coord_model (egnn.py:111-128): mean-aggregated, clamped update
     s = F.linear(F.silu(_lin(sd, pre + "coord_mlp.0", m)), sd[pre + "coord_mlp.2.weight"])
     trans = diff * s.unsqueeze(-1)
@@ -164,7 +181,7 @@ def gcl_forward(sd, pre, h, edges, x, batch_id, clamp):
     # node_model (egnn.py:89-109): sum-aggregate, cat[h, agg] -> Linear -> SiLU -> Linear, residual
     agg = segment_sum(m, row, n)
     out = _lin(sd, pre + "node_mlp.2", F.silu(_lin(sd, pre + "node_mlp.0", torch.cat([h, agg], 1))))
-    return h + out, x
+    return h + drop(out, layer, "node2"), x                                # egnn.py:106
 
 
 # ------------------------------------------------------------------------------------------------
@@ -177,7 +194,7 @@ def interaction(sd, pre, p, c):
     return _lin(sd, pre + "linear_out", pp[:, None, :] * cc[None, :, :])
 
 
-def row_attention(sd, pre, xi, xj, pair, heads=4, dh=32):
+def row_attention(sd, pre, xi, xj, pair, heads=4, dh=32, drop=_nodrop, layer=0, site="patt"):
     """RowAttentionBlock (models/cross_att.py:118-134) + gated multi-head Attention
     (models/model_utils.py:96-159, _attention :21-38) for ONE complex (no padding, so the 1e9
     mask bias of cross_att.py:124 never applies to a real entry).
@@ -191,7 +208,7 @@ def row_attention(sd, pre, xi, xj, pair, heads=4, dh=32):
     o = torch.einsum("hij,jhd->ihd", a, v)
     g = torch.sigmoid(_lin(sd, pre + "mha.linear_g", xi)).view(-1, heads, dh)
     o = (o * g).reshape(-1, heads * dh)
-    return xi + _lin(sd, pre + "mha.linear_o", o)
+    return xi + drop(_lin(sd, pre + "mha.linear_o", o), layer, site)      # cross_att.py:128
 
 
 def transition(sd, pre, x):
@@ -199,10 +216,10 @@ def transition(sd, pre, x):
     return _lin(sd, pre + "linear_2", _lin(sd, pre + "linear_1", x).relu())
 
 
-def cross_attention(sd, pre, p, c, pair):
+def cross_attention(sd, pre, p, c, pair, drop=_nodrop, layer=0):
     """CrossAttentionModule.forward (models/cross_att.py:24-54), one complex."""
-    p = row_attention(sd, pre + "p_attention_block.", p, c, pair)
-    c = row_attention(sd, pre + "c_attention_block.", c, p, pair.transpose(0, 1))   # uses the NEW p
+    p = row_attention(sd, pre + "p_attention_block.", p, c, pair, drop=drop, layer=layer, site="patt")
+    c = row_attention(sd, pre + "c_attention_block.", c, p, pair.transpose(0, 1), drop=drop, layer=layer, site="catt")   # uses the NEW p
     p = p + transition(sd, pre + "p_transition.", p)
     c = c + transition(sd, pre + "c_transition.", c)
     pair = pair + interaction(sd, pre + "inter_layer.", p, c)
@@ -213,7 +230,7 @@ def cross_attention(sd, pre, p, c, pair):
 # ------------------------------------------------------------------------------------------------
 # MC_Att_L  (models/egnn.py:147-333)
 # ------------------------------------------------------------------------------------------------
-def att_forward(sd, pre, h, inter, x, batch_id, segment_id, pair0, clamp, layout):
+def att_forward(sd, pre, h, inter, x, batch_id, segment_id, pair0, clamp, layout, drop=_nodrop, layer=0):
     B, offs, counts, ncp = layout
     row, col = inter
     n = h.shape[0]
@@ -224,7 +241,7 @@ def att_forward(sd, pre, h, inter, x, batch_id, segment_id, pair0, clamp, layout
         o, nc1, nn = offs[b], ncp[b], counts[b]
         c = h[o:o + nc1]
         p = h[o + nc1:o + nn]
-        p, c, pr = cross_attention(sd, pre + "cross_attn_module.", p, c, pair0[b])
+        p, c, pr = cross_attention(sd, pre + "cross_attn_module.", p, c, pair0[b], drop, layer)
         new_h[o:o + nc1] = c
         new_h[o + nc1:o + nn] = p
         pair_new.append(pr)
@@ -251,7 +268,7 @@ def att_forward(sd, pre, h, inter, x, batch_id, segment_id, pair0, clamp, layout
     alpha = (q * k).sum(1) + _lin(sd, pre + "attn_bias_proj", pair_off).squeeze(-1)
     alpha = segment_softmax(alpha, row, n)
     aw = alpha.unsqueeze(-1)
-    h = h + segment_sum(aw * v, row, n)
+    h = h + drop(segment_sum(aw * v, row, n), layer, "agg")                # egnn.py:235-237
     cv = aw * F.linear(F.silu(_lin(sd, pre + "coord_mlp.0", v)), sd[pre + "coord_mlp.2.weight"])
     x = x + segment_sum(diff * cv.unsqueeze(-1), row, n).clamp(-clamp, clamp)
     return h, x, alpha, pair_new
@@ -274,25 +291,25 @@ def las_step(x, x_ref, las, step, clamp):
 # MCAttEGNN.forward  (models/egnn.py:392-466)
 # ------------------------------------------------------------------------------------------------
 def egnn_forward(sd, pre, cfg, h, x, ctx, inter, las, x_ref, batch_id, segment_id, pair0, layout,
-                 trace=None):
+                 trace=None, drop=_nodrop):
     clamp = 10.0 / cfg.coordinate_scale                       # normalize_coord(10), egnn.py:378
-    h = _lin(sd, pre + "linear_in", h)
+    h = drop(_lin(sd, pre + "linear_in", h), -1, "stack_in")  # egnn.py:397-398
     x = x.clone()
     atts = []
     for i in range(cfg.n_layers):
-        h, x = gcl_forward(sd, f"{pre}gcl_{i}.", h, ctx, x, batch_id, clamp)
+        h, x = gcl_forward(sd, f"{pre}gcl_{i}.", h, ctx, x, batch_id, clamp, drop, i)
         if trace is not None:
             trace.append((f"gcl_{i}", h.clone(), x.clone()))
         h, x, att, _ = att_forward(sd, f"{pre}att_{i}.", h, inter, x, batch_id, segment_id, pair0,
-                                   clamp, layout)
+                                   clamp, layout, drop, i)
         atts.append(att)
         if trace is not None:
             trace.append((f"att_{i}", h.clone(), x.clone()))
         x = las_step(x, x_ref, las, cfg.geometry_reg_step_size, 15.0 / cfg.coordinate_scale)
         if trace is not None:
             trace.append((f"las_{i}", h.clone(), x.clone()))
-    h, x = gcl_forward(sd, pre + "out_layer.", h, ctx, x, batch_id, clamp)
-    h = _lin(sd, pre + "linear_out", h)
+    h, x = gcl_forward(sd, pre + "out_layer.", h, ctx, x, batch_id, clamp, drop, cfg.n_layers)
+    h = _lin(sd, pre + "linear_out", drop(h, -1, "stack_out"))   # egnn.py:461-462
     return h, x, atts
 
 
@@ -317,11 +334,12 @@ def initial_pair(sd, H, layout):
 
 
 def model_forward(sd, cfg, X, H, batch_id, segment_id, mask, is_global, compound_edge_index,
-                  LAS_edge_index, X_LAS, trace=None, return_edges=False, grad_last_iter_only=False):
+                  LAS_edge_index, X_LAS, trace=None, return_edges=False, grad_last_iter_only=False, dropout=None):
     """Returns (X, H) like the reference; X is updated on a copy (the reference mutates its
     argument in place, att_model.py:236,245 -- callers that want that effect copy back).
     grad_last_iter_only: autograd semantics of refine='refine_coord' (att_model.py:227-245): every iteration but the last runs
-    under no_grad (graph construction always does); used by the gradient goldens that pin this oracle for the training path."""
+    under no_grad (graph construction always does); used by the gradient goldens that pin this oracle for the training path.
+    dropout = (p, seed, True): train() mode of the reference with column-only masks (see make_drop)."""
     X = X.clone()
     layout = complex_layout(batch_id, segment_id)
     pair0 = initial_pair(sd, H, layout)
@@ -338,7 +356,7 @@ def model_forward(sd, cfg, X, H, batch_id, segment_id, mask, is_global, compound
         tr = [] if trace is not None else None
         with torch.set_grad_enabled(torch.is_grad_enabled() and (not grad_last_iter_only or r == cfg.n_iter - 1)):
             h_new, Z, atts = egnn_forward(sd, "gnn.", cfg, H, X, ctx, inter, LAS_edge_index, X_LAS,
-                                          batch_id, segment_id, pair0, layout, trace=tr)
+                                          batch_id, segment_id, pair0, layout, trace=tr, drop=make_drop(dropout, r))
         if trace is not None:
             trace.append((r, tr, atts))
         X[mask] = Z[mask]

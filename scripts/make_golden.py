@@ -408,6 +408,97 @@ def main_grad():
         print("grad", flavour, "loss", float(loss), "params with grad", sum(v is not None for v in grads.values()), "/", len(grads))
 
 
+def patch_reference_dropout_v1(model, L, seed, p):
+    """The v1 twin of patch_reference_dropout: every nn.Dropout of the unmodified FABind stack (models/egnn.py:38,158,362;
+    models/cross_att.py:114) becomes a deterministic COLUMN-ONLY mask from the library's mask function.  MC_E_GCL uses ONE Dropout
+    module twice per call (edge_mlp output egnn.py:82 -> site edge2, node_mlp output egnn.py:106 -> site node2); MCAttEGNN uses its
+    own twice per call (after linear_in :398, before linear_out :461)."""
+    import re
+    import torch.nn as nn
+    from fabind_b200.dropout import keep_mask, site_id, iter_seed
+    state = dict(it=-1)
+
+    class ColDrop(nn.Module):
+        def __init__(self, sites):
+            super().__init__()
+            self.sites, self.calls = sites, 0
+
+        def forward(self, x):
+            site = self.sites[self.calls % len(self.sites)]
+            self.calls += 1
+            if not self.training:
+                return x
+            m = keep_mask(iter_seed(seed, state["it"]), site, 1, x.shape[-1], p, colonly=True)[0]
+            return x * m
+
+    def pre_hook(mod, inp):
+        state["it"] += 1
+    model.gnn.register_forward_pre_hook(pre_hook)
+    n = 0
+    for name, mod in list(model.named_modules()):
+        if not isinstance(mod, nn.Dropout):
+            continue
+        parent = model
+        parts = name.split(".")
+        for q in parts[:-1]:
+            parent = getattr(parent, q)
+        if name == "gnn.dropout":
+            new = ColDrop([site_id(-1, "stack_in"), site_id(-1, "stack_out")])
+        else:
+            m = re.match(r"gnn\.(gcl_(\d+)|att_(\d+)|out_layer)\.(.*)", name)
+            assert m, name
+            layer = L if m.group(1) == "out_layer" else int(m.group(2) or m.group(3))
+            rest = m.group(4)
+            if not m.group(1).startswith("att"):
+                assert rest == "dropout", name
+                new = ColDrop([site_id(layer, "edge2"), site_id(layer, "node2")])
+            elif rest == "dropout":
+                new = ColDrop([site_id(layer, "agg")])
+            elif rest == "cross_attn_module.p_attention_block.dropout":
+                new = ColDrop([site_id(layer, "patt")])
+            elif rest == "cross_attn_module.c_attention_block.dropout":
+                new = ColDrop([site_id(layer, "catt")])
+            else:
+                # dropout modules the published configuration constructs but never calls (e.g. inter_layer / pair blocks)
+                new = ColDrop([0xFFFF])
+        setattr(parent, parts[-1], new)
+        n += 1
+    return n
+
+
+def main_grad_dropout():
+    """Training-mode twin of main_grad for the v1 stack: the UNMODIFIED reference in train() mode (dropout 0.1 active in every
+    refinement iteration, att_model.py:210-245), its nn.Dropout modules patched to the library's column-only masks; outputs, loss
+    and parameter gradients for a fixed linear read-out.  Pins placement / scaling of every mask in the no_grad iterations, the
+    training-mode forward AND the reverse pass of the training step (fabind_b200/train.py)."""
+    mods = ref_shims.load_reference("v1")
+    args = ref_shims.published_args()
+    args.random_n_iter = False
+    pdrop, dseed = 0.1, 4242
+    for tag, hidden, L, IT, bkw, wseed in (("h32_l1_it2", 32, 1, 2, dict(n_complexes=2, seed=6, n_c_range=(5, 9), n_p_range=(14, 22)), 91),
+                                           ("h64_l2_it3", 64, 2, 3, dict(n_complexes=3, seed=8, n_c_range=(6, 14), n_p_range=(20, 40)), 92)):
+        scale = args.coordinate_scale
+        m = mods.att_model.EfficientMCAttModel(args, hidden, hidden, 1, n_edge_feats=0, n_layers=L, dropout=pdrop, n_iter=IT,
+                                               inter_cutoff=args.inter_cutoff, intra_cutoff=args.intra_cutoff,
+                                               normalize_coord=lambda x: x / scale, unnormalize_coord=lambda x: x * scale)
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(det_state_dict(shapes, wseed), strict=True)
+        n = patch_reference_dropout_v1(m, L, dseed, pdrop)
+        m.train()
+        b = batch_from_recipe(hidden, bkw, OUT)
+        g = torch.Generator().manual_seed(17)
+        out = m(**b.clone().forward_args())
+        rx, rh = torch.randn(out[0].shape, generator=g), torch.randn(out[1].shape, generator=g)
+        loss = (out[0] * rx).sum() + (out[1] * rh).sum()
+        loss.backward()
+        grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in m.named_parameters()}
+        torch.save({"recipe": dict(hidden=hidden, n_layers=L, n_iter=IT, batch=bkw, weight_seed=wseed, far_ligand=False, flavour="v1",
+                                   readout_seed=17, dropout_p=pdrop, dropout_seed=dseed, dropout_colonly=True),
+                    "shapes": shapes, "X": out[0].detach().clone(), "H": out[1].detach().clone(), "loss": float(loss), "grads": grads,
+                    "torch": torch.__version__}, os.path.join(OUT, f"graddrop_v1_{tag}.pt"))
+        print("graddrop v1", tag, "patched", n, "loss", float(loss), "params with grad", sum(v is not None for v in grads.values()), "/", len(grads))
+
+
 def main_l2_plus():
     """goldens for the FABind+ L2 wrapper (FABind_plus/fabind/models/model.py::FABindPlus): forward(stage=2) in eval mode
     (13-tuple + the in-place shift of data.coords) and inference()"""
@@ -447,7 +538,7 @@ def main_l2_plus():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample", "postopt", "l2plustrainfwd", "grad"]
+    which = sys.argv[1:] or ["v1", "l2", "plus", "l2plus", "plusdrop", "l2plussample", "postopt", "l2plustrainfwd", "grad", "graddrop"]
     if "l2plus" in which:
         main_l2_plus()
     if "plusdrop" in which:
@@ -458,6 +549,8 @@ if __name__ == "__main__":
         main_post_optim()
     if "grad" in which:
         main_grad()
+    if "graddrop" in which:
+        main_grad_dropout()
     if "l2plustrainfwd" in which:
         main_l2_plus_train_forward()
     if "v1" in which:

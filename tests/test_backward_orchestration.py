@@ -332,8 +332,15 @@ def test_stack_reverse_pass_matches_specification(monkeypatch):
 def _install_forward_standins(monkeypatch, bw):
     L = lambda t: t.long()
 
-    def linear(A, W, bias=None, act=0, res=None):
+    def drop_apply(self, X, layer, name, row0=0):
+        from fabind_b200.dropout import keep_mask
+        return X * keep_mask(self.seed, self.site(layer, name), X.shape[0], X.shape[1], self.p, colonly=bool(self.colonly), row0=row0)
+    monkeypatch.setattr(bw.Drop, "apply", drop_apply)
+
+    def linear(A, W, bias=None, act=0, res=None, drop=None):
         y = _actf(F.linear(A, W, bias), act)
+        if drop is not None and drop[0] is not None and drop[0].p > 0:
+            y = drop[0].apply(y, drop[1], drop[2], drop[3])
         return y if res is None else y + res
 
     def radial_fwd(x, row, col, cplx, B):
@@ -452,6 +459,57 @@ def test_training_step_assembly(monkeypatch):
             Xo, Ho = orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global, b.compound_edge_index,
                                        b.LAS_edge_index, b.X_LAS)
         assert rel_err(X_out, Xo) < 1e-5 and rel_err(H_out, Ho) < 1e-4
+        loss = float((X_out * rx).sum() + (H_out * rh).sum())
+        assert abs(loss - g["loss"]) < 1e-4 * abs(g["loss"])
+        gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)
+        n = 0
+        for k, ref in g["grads"].items():
+            if ref is None:
+                continue
+            err = float((pgrads[k] - ref).abs().max())
+            assert err < 5e-4 * float(ref.abs().max()) + 5e-7 * gmax, (k, err, float(ref.abs().max()))
+            n += 1
+        assert n >= 80
+
+
+def test_training_step_with_dropout(monkeypatch):
+    """the training step in the reference's train() mode (dropout 0.1 at egnn.py:82,106,236,398,461 / cross_att.py:128): kernel
+    wrappers -> torch stand-ins, earlier iterations / graph builder -> the oracle with the same column-only masks; outputs, loss
+    and parameter gradients are those of the UNMODIFIED reference in train() mode with its nn.Dropout modules patched to the
+    library's mask function (tests/golden/graddrop_v1_*.pt, scripts/make_golden.py::main_grad_dropout)."""
+    from fabind_b200 import EfficientMCAttModel, backward as bw, train
+    from fabind_b200.config import published_args
+    from oracle import fabind_oracle as orc
+    _install_standins(monkeypatch, bw)
+    _install_forward_standins(monkeypatch, bw)
+    monkeypatch.setattr(bw, "pair_bias_gate_bwd", _gate_bwd_standin)
+    monkeypatch.setattr(bw, "pair_outer_bwd", _outer_bwd_standin)
+    paths = sorted(glob.glob(os.path.join(GOLDEN_DIR, "graddrop_v1_*.pt")))
+    assert paths
+    for path in paths:
+        g, r, b, sd, cfg = load_golden(path)
+        H = r["hidden"]
+        dropout = (r["dropout_p"], r["dropout_seed"], True)
+        model = EfficientMCAttModel(published_args(), H, H, 1, n_layers=r["n_layers"], n_iter=r["n_iter"],
+                                    normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+        model.load_state_dict(sd, strict=True)
+        fa = b.forward_args()
+        gen = torch.Generator().manual_seed(r["readout_seed"])
+        rx, rh = torch.randn(b.X.shape, generator=gen), torch.randn(b.H.shape, generator=gen)
+
+        def prev_coords(m, fa):
+            c = orc.make_cfg(n_layers=cfg.n_layers, n_iter=cfg.n_iter - 1)
+            with torch.no_grad():
+                return orc.model_forward(sd, c, fa["X"], fa["H"], fa["batch_id"], fa["segment_id"], fa["mask"], fa["is_global"],
+                                         fa["compound_edge_index"], fa["LAS_edge_index"], fa["batched_complex_coord_LAS"], dropout=dropout)[0]
+
+        def edge_lists(m, X_prev, fa):
+            ctx, inter, _ = orc.build_edges(X_prev, fa["batch_id"], fa["segment_id"], fa["is_global"], cfg.intra_cutoff / cfg.coordinate_scale,
+                                            cfg.inter_cutoff / cfg.coordinate_scale)
+            return ctx, inter
+        X_out, H_out, pgrads, gH_in = train.training_step(model, fa, lambda X, Hh: (rx, rh), prev_coords=prev_coords, edge_lists=edge_lists,
+                                                          dropout=dropout)
+        assert rel_err(X_out, g["X"]) < 1e-5 and rel_err(H_out, g["H"]) < 1e-4
         loss = float((X_out * rx).sum() + (H_out * rh).sum())
         assert abs(loss - g["loss"]) < 1e-4 * abs(g["loss"])
         gmax = max(float(v.abs().max()) for v in g["grads"].values() if v is not None)

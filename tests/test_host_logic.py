@@ -101,7 +101,15 @@ def test_host_entry_points_validate_arguments():
     p.hidden = 1024
     assert l.fb_model_workspace_bytes(C.byref(p)) == -1                           # hidden > 512 is not built
     p.hidden, p.flavour, p.dropout_p = 64, _lib.FLAVOUR_V1, 0.1
-    assert l.fb_model_workspace_bytes(C.byref(p)) == -1                           # dropout is a FABind+ (sampling) feature
+    assert l.fb_model_workspace_bytes(C.byref(p)) > 0                             # ABI 4: the v1 stack carries its training-mode dropout
+    p.dropout_p = 1.0
+    assert l.fb_model_workspace_bytes(C.byref(p)) == -1
+    p.dropout_p, p.bf16_mode = 0.0, 7
+    assert l.fb_model_workspace_bytes(C.byref(p)) == -1                           # unknown precision mode
+    p.bf16_mode = _lib.PREC_SPLIT6
+    fp32_tc = l.fb_model_workspace_bytes(C.byref(p))
+    p.bf16_mode = _lib.PREC_FP32
+    assert fp32_tc > l.fb_model_workspace_bytes(C.byref(p))                       # split modes add the operand scratch
     assert l.fb_weight_slot_info_f(64, 2, 1, 10 ** 6, None, 0, None, None, None) == -1
     assert l.fb_gemm(None, None) == -1 and l.fb_gemm_dot_tiles(45000, 512, 512, 1, 0) == 4
 
