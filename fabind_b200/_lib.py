@@ -76,6 +76,7 @@ EXPORTS = {
     "fb_launch_count": (C.c_int64, []),
     "fb_prof_enable": (C.c_int32, [C.c_int32]),
     "fb_prof_read": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "fb_prof_flops": (C.c_int32, [C.POINTER(C.c_double), C.c_int32]),
     "fb_weight_slot_count": (C.c_int32, [C.c_int32, C.c_int32]),
     "fb_weight_slot_info": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32,
                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

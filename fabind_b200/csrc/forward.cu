@@ -44,6 +44,11 @@ static std::vector<ProfSpan> g_spans;       // recorded spans of the current pro
 static std::vector<ProfSpan> g_pool;        // reusable events
 static int g_open_cat = -1;
 static cudaEvent_t g_open_a, g_open_b;
+static double g_flops[CAT_COUNT] = {0};     // 2 M N K of the GEMMs enqueued per category while profiling (M = row CAPACITY for
+                                            // problems with a device-side row count)
+static void prof_flops(int cat, const GemmArgs& a) {
+  if (g_prof_on && cat >= 0 && cat < CAT_COUNT) g_flops[cat] += 2.0 * a.M * a.N * (a.K1 + a.K2);
+}
 
 void prof_begin(int cat, cudaStream_t st) {
   if (!g_prof_on) return;
@@ -394,6 +399,7 @@ struct Run {
   void gemm(const GemmArgs& a) {
     if (a.M <= 0 || (skip_mask() >> gemm_cat & 1)) return;
     prof_begin(gemm_cat, st);
+    prof_flops(gemm_cat, a);
     chk(gemm_launch(a, gmode, st));
     prof_end(st);
   }
@@ -402,6 +408,7 @@ struct Run {
   void gemm_pair(const GemmArgs& c, const GemmArgs& pr) {
     if (c.M <= 0 || pr.M <= 0 || (skip_mask() >> gemm_cat & 1)) { gemm(c); gemm(pr); return; }
     prof_begin(gemm_cat, st);
+    prof_flops(gemm_cat, c); prof_flops(gemm_cat, pr);
     chk(gemm_launch_pair(c, pr, gmode, st));
     prof_end(st);
   }
@@ -751,6 +758,12 @@ int32_t fb_prof_read(double* ms, int64_t* spans, int32_t n_cat) {
     g_pool.push_back(s);
   }
   g_spans.clear();
+  return FB_OK;
+}
+
+int32_t fb_prof_flops(double* flops, int32_t n_cat) {
+  for (int i = 0; i < n_cat; ++i) flops[i] = i < CAT_COUNT ? g_flops[i] : 0.0;
+  for (int i = 0; i < CAT_COUNT; ++i) g_flops[i] = 0.0;
   return FB_OK;
 }
 

@@ -109,6 +109,9 @@ int64_t fb_source_hash(void);
 int64_t fb_launch_count(void);
 int32_t fb_prof_enable(int32_t on);
 int32_t fb_prof_read(double* ms, int64_t* spans, int32_t n_cat);
+/* FLOPs (2 M N K, as launched) of the GEMMs enqueued per category since the last call while profiling was on; M = the row
+ * capacity for problems whose row count lives on the device (the pair-path GEMM) */
+int32_t fb_prof_flops(double* flops, int32_t n_cat);
 
 /* [host] weight arena layout for (hidden, n_layers): slot i has a name ("gcl0.e2_w", "att1.qk_w", ...),
  * a [rows, cols] shape and an element offset into the arena.  fabind_b200/weights.py maps every slot to

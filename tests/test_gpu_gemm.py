@@ -214,3 +214,82 @@ def test_gemm_cta_pair_kernel(M, N, K, act, use_dot, out):
         assert float((Cb1.double() - ref).abs().mean() / ref.abs().mean()) < 3e-3
     if use_dot:
         assert float((d1.double() - dref).abs().max() / dref.abs().max()) < 5e-5
+
+
+
+# ---- split-precision modes (FB_PREC_SPLIT3 / SPLIT6): fp32 operands on the tcgen05 kernels as sums of bf16 planes -------------
+def run_gemm_split(A, W, mode, bias=None, act=0, res=None, A2=None, dotv=None, n_split=0):
+    l = _lib.lib()
+    dev = A.device
+    M, K1 = A.shape
+    K2 = A2.shape[1] if A2 is not None else 0
+    K, N = K1 + K2, W.shape[0]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Wf = W.contiguous()
+    Ws = torch.empty(N, 3 * K, dtype=torch.bfloat16, device=dev)
+    _lib.check(l.fb_split_rows(Wf.data_ptr(), K, N, K, Ws.data_ptr(), st), "fb_split_rows")
+    planes = Ws.float().view(N, 3, K)
+    assert float((planes.sum(1) - Wf).abs().max()) <= 2.0 ** -24 * float(Wf.abs().max())      # w0 + w1 + w2 == w to fp32 rounding
+    ws = torch.empty(M * 3 * K, dtype=torch.bfloat16, device=dev)
+    g = _lib.GemmParams()
+    Ad = A.contiguous()
+    A2d = A2.contiguous() if A2 is not None else None
+    g.A, g.lda, g.K1 = Ad.data_ptr(), K1, K1
+    g.A2, g.lda2, g.K2 = (A2d.data_ptr() if A2d is not None else None), K2, K2
+    g.W, g.W_f32 = Ws.data_ptr(), Wf.data_ptr()
+    g.split_ws, g.split_ws_bytes = ws.data_ptr(), ws.numel() * 2
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.act = act
+    g.res, g.ldres = (res.data_ptr() if res is not None else None), N
+    n_lo = n_split if n_split else N
+    Cout = torch.full((M, n_lo), float("nan"), device=dev)
+    g.C, g.ldc = Cout.data_ptr(), n_lo
+    Chi = torch.full((M, N - n_split), float("nan"), device=dev) if n_split else None
+    if n_split:
+        g.Cb, g.ldcb, g.n_split = Chi.data_ptr(), N - n_split, n_split
+    tiles = l.fb_gemm_dot_tiles(M, N, K, mode, 0)
+    dot = torch.zeros((tiles, M), device=dev) if dotv is not None else None
+    g.dotv = dotv.data_ptr() if dotv is not None else None
+    g.dot_out = dot.data_ptr() if dot is not None else None
+    g.dot_stride, g.M, g.N, g.bf16_mode = M, M, N, mode
+    _lib.check(l.fb_gemm(C.byref(g), st), "fb_gemm")
+    torch.cuda.synchronize()
+    out = torch.cat([Cout, Chi], 1) if n_split else Cout
+    return out, (dot.sum(0) if dot is not None else None)
+
+
+SPLIT_CASES = [
+    # M, N, K1, K2, act, bias, res, dot, n_split
+    (232, 512, 512, 0, 1, True, False, False, 0),        # node-level, SiLU (exact in the split modes)
+    (500, 1024, 512, 0, 2, True, False, True, 0),
+    (300, 512, 512, 512, 1, True, False, False, 0),      # [h | agg] concatenation
+    (777, 512, 128, 0, 0, True, True, False, 0),         # residual
+    (20000, 512, 512, 0, 1, True, False, True, 0),       # CTA-pair kernel (M >= 16384, N % 256 == 0), row-dot epilogue
+    (3000, 1024 + 128 + 1024, 512, 0, 0, True, False, False, 1024 + 128),   # column-routed outputs (q | k | inter32 || v | vc)
+    (900, 1024, 512, 64, 2, True, False, True, 0),       # K2 = 64 (pair transition on [z | t64])
+    (37, 64, 32, 0, 0, True, False, False, 0),           # does not tile: FFMA kernel on the fp32 weight
+]
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("case", SPLIT_CASES)
+def test_gemm_split_precision(case, mode):
+    """bf16x3 (mode 2) keeps terms down to 2^-9 per operand: ~1e-5 of the row scale; six products (mode 3, 'fp32_tc') are fp32-grade:
+    <= 2e-6, the bound the FFMA kernel is held to above"""
+    M, N, K1, K2, act, has_b, has_r, has_d, n_split = case
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N + mode)
+    dev = "cuda"
+    A = torch.randn(M, K1, generator=g).to(dev)
+    A2 = torch.randn(M, K2, generator=g).to(dev) if K2 else None
+    W = (torch.randn(N, K1 + K2, generator=g) / (K1 + K2) ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g).to(dev) if has_b else None
+    res = torch.randn(M, N, generator=g).to(dev) if has_r else None
+    dotv = torch.randn(N, generator=g).to(dev) if has_d else None
+    out, dot = run_gemm_split(A, W, mode, bias, act, res, A2, dotv, n_split)
+    ref, dref = ref_gemm(A, W, bias, act, res, A2, dotv, False)
+    tol = 3e-5 if mode == 2 else 2e-6
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err < tol, (case, mode, err)
+    if has_d:
+        derr = float((dot.double() - dref).abs().max() / dref.abs().max())
+        assert derr < 10 * tol, (case, mode, derr)

@@ -86,6 +86,56 @@ def test_oracle_fp32(hidden, L, IT, bkw):
     assert rec["x_err"] < 1e-4 and rec["h_err"] < 1e-4, rec
 
 
+def _edge_drift(m, e_ref):
+    """interface-edge counts per refinement iteration against the oracle's (coordinate drift moves atoms across the cutoff)"""
+    e = m.last_stats["inter_edges_per_iter"].cpu().tolist()
+    return e, [abs(a - b) for a, b in zip(e, e_ref)]
+
+
+def test_tensor_core_parity_at_the_benched_shape():
+    """The BENCHED configuration (BASELINE configs[1]: B = 16, n_c = 30, n_p = 200, hidden 512, 4 layers x 8 iterations) against the
+    CPU oracle, in every precision mode:
+      fp32_tc (tcgen05, six bf16 products per term)  <= 1e-4 on X and H  -- the tensor-core kernel IS a parity kernel;
+      fp32    (FFMA)                                 <= 1e-4;
+      bf16x3 / bf16: reported (own, looser bounds), with the interface-edge drift per iteration."""
+    hidden, L, IT = 512, 4, 8
+    b = make_batch(embed=hidden, n_complexes=16, seed=100, n_c=30, n_p=200)
+    m0 = EfficientMCAttModel(ref_shims.published_args(), hidden, hidden, 1, n_layers=L, n_iter=IT,
+                             normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m0.state_dict().items()}, 31)
+    cfg = orc.make_cfg(n_layers=L, n_iter=IT)
+    with torch.no_grad():
+        Xo, Ho, edges = orc.model_forward(sd, cfg, b.X, b.H, b.batch_id, b.segment_id, b.mask, b.is_global,
+                                          b.compound_edge_index, b.LAS_edge_index, b.X_LAS, return_edges=True)
+    e_ref = [int(e[1].shape[1]) for e in edges]
+    recs = {}
+    for prec in ("fp32_tc", "fp32", "bf16x3", "bf16"):
+        m = _model(hidden, L, IT, sd, precision=prec)
+        X, H = _run(m, b)
+        e, drift = _edge_drift(m, e_ref)
+        recs[prec] = dict(precision=prec, x_err=rel_err(X, Xo), h_err=rel_err(H, Ho), x_abs=float((X - Xo).abs().max()), e_int=e, e_int_ref=e_ref,
+                          edge_drift=drift)
+        _log("benched_shape", recs[prec])
+    for prec in ("fp32_tc", "fp32"):
+        assert recs[prec]["x_err"] < 1e-4 and recs[prec]["h_err"] < 1e-4, recs[prec]
+        assert recs[prec]["e_int"] == e_ref, recs[prec]
+    assert recs["bf16x3"]["x_err"] < 2e-3 and recs["bf16x3"]["h_err"] < 2e-3, recs["bf16x3"]
+    assert recs["bf16"]["x_abs"] < 0.15 and recs["bf16"]["h_err"] < 0.02, recs["bf16"]
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-3])
+def test_golden_fp32_tc(path):
+    """the tensor-core parity mode against the goldens of the unmodified reference (shapes that do not tile fall to the FFMA kernel)"""
+    g, r, b, sd, cfg = load_golden(path)
+    m = _model(r["hidden"], r["n_layers"], r["n_iter"], sd, precision="fp32_tc")
+    X, H = _run(m, b)
+    e_int = m.last_stats["inter_edges_per_iter"].cpu().tolist()
+    rec = dict(case=os.path.basename(path), x_err=rel_err(X, g["X"]), h_err=rel_err(H, g["H"]))
+    _log("golden_fp32_tc", rec)
+    assert e_int == [int(e[1].shape[1]) for e in g["edges"]]
+    assert rec["x_err"] < 1e-4 and rec["h_err"] < 1e-4, rec
+
+
 def test_bf16_mode_deviation():
     """bf16 production mode: same path with bf16 GEMM operands.  The reference has no bf16 mode; this bound
     is the build's own: coordinates within 0.15 normalised units (0.75 A) of the fp32 oracle after 8 iterations x 4
