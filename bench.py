@@ -364,7 +364,7 @@ def setup_train(dev, rank):
             loss = (X * rx).sum() + (H * rh).sum()
             loss.backward()
             ev[1].record()
-            buf[0] = shard.allreduce_gradients(params, buffer=buf[0])
+            buf[0] = shard.allreduce_gradients(params, buffer=buf[0], model=model)
             ev[2].record()
             if host_inputs:
                 loss_host.copy_(loss.detach().reshape(1), non_blocking=True)

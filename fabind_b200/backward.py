@@ -29,6 +29,35 @@ PRECISION = "fp32"
 WGRAD_TC_MIN_ROWS = 2048
 
 
+# bf16 twins of the weight operands (PRECISION = "bf16"): train.slot_tensors converts the whole arena ONCE per step and registers,
+# per fp32 weight view, the bf16 view of the same slot -- no per-GEMM conversion kernels; anything unregistered is converted on the spot
+_W16 = {}
+
+
+def register_bf16(w32, w16):
+    _W16[(w32.data_ptr(), tuple(w32.shape))] = w16
+
+
+def clear_bf16():
+    _W16.clear()
+
+
+def bf16_twin(W):
+    if W.dtype == torch.bfloat16:
+        return W if W.is_contiguous() else W.contiguous()
+    t = _W16.get((W.data_ptr(), tuple(W.shape)))
+    return t if t is not None else W.to(torch.bfloat16).contiguous()
+
+
+def transpose_bf16(X, Mp):
+    """X [M, N] fp32 -> bf16 [N, Mp] (Mp >= M, a multiple of 64; the pad columns are zero): the K-major operand of a weight-gradient GEMM"""
+    _chk(X)
+    M, N = X.shape
+    out = torch.empty(N, Mp, dtype=torch.bfloat16, device=X.device)
+    _lib.check(_lib.lib().fb_transpose_bf16(X.data_ptr(), N, M, N, out.data_ptr(), Mp, _st(X)), "fb_transpose_bf16")
+    return out
+
+
 class Drop:
     """nn.Dropout of the reference's training step (v1 stack: egnn.py:82,106,236,398,461; cross_att.py:128) for ONE refinement
     iteration, with the library's counter-based masks (csrc/common.cuh, fabind_b200/dropout.py): the forward applies
@@ -65,7 +94,10 @@ def _gemm_call(A, W, bias, act, res, M, N, K, drop=None):
         g.drop_p, g.drop_seed, g.drop_site, g.drop_row0, g.drop_colonly = d.p, d.seed, d.site(layer, name), int(row0), d.colonly
     bf16 = PRECISION == "bf16" and K % 8 == 0
     if bf16:
-        A, W = A.to(torch.bfloat16).contiguous(), W.to(torch.bfloat16).contiguous()
+        A = A.to(torch.bfloat16).contiguous()
+        W = bf16_twin(W)
+    elif W.dtype != torch.float32:
+        raise RuntimeError("fabind_b200.backward: bf16 weight operand outside PRECISION = 'bf16'")
     g.A, g.lda, g.K1 = A.data_ptr(), K, K
     g.W, g.bias, g.act = W.data_ptr(), (bias.data_ptr() if bias is not None else None), act
     g.M, g.N, g.bf16_mode, g.force_simt = M, N, int(bf16), 0
@@ -157,10 +189,7 @@ def gemm_wgrad(dY, X, out=None):
     K = X.shape[1]
     if PRECISION == "bf16" and M >= WGRAD_TC_MIN_ROWS:
         Mp = (M + 63) // 64 * 64
-        At = torch.zeros(N, Mp, dtype=torch.bfloat16, device=dY.device)
-        Wt = torch.zeros(K, Mp, dtype=torch.bfloat16, device=dY.device)
-        At[:, :M].copy_(dY.t())
-        Wt[:, :M].copy_(X.t())
+        At, Wt = transpose_bf16(dY, Mp), transpose_bf16(X, Mp)
         g = _lib.GemmParams()
         g.A, g.lda, g.K1 = At.data_ptr(), Mp, Mp
         g.W, g.bias, g.act = Wt.data_ptr(), None, ACT_NONE
@@ -176,8 +205,8 @@ def gemm_wgrad(dY, X, out=None):
 
 
 def gemm_dgrad(dY, Wt):
-    """dX = dY W, with Wt = W^T stored [K_in, N_out] contiguous (the 'weight' of the data-gradient GEMM); fp32 SIMT path"""
-    _chk(dY), _chk(Wt)
+    """dX = dY W, with Wt = W^T stored [K_in, N_out] contiguous (the 'weight' of the data-gradient GEMM; bf16 under PRECISION = 'bf16')"""
+    _chk(dY)
     M, N = dY.shape
     return _gemm_call(dY, Wt, None, ACT_NONE, None, M, Wt.shape[0], N)
 
@@ -421,7 +450,9 @@ def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0, drop=None, layer=
     dpbu = dpbu.view(-1)
     grads["pt2v"] = colsum(act_fwd(sv["Zp"], ACT_RELU), dpbu)
     dZp = outer_act_bwd(sv["Zp"], dpbu, w["pt2v"], ACT_RELU)
-    dz = _linear_bwd(grads, "pt1_w", "pt1_b", w["pt1_w_t"], sv["zcat"], dZp)
+    dz = _linear_bwd(grads, "pt1_w", "pt1_b", _pt1_padded(w, "pt1_w_t", H), sv["zcat"], dZp)
+    if grads["pt1_w"].shape[1] != H + 64:
+        grads["pt1_w"] = grads["pt1_w"][:, :H + 64].contiguous()
     scatter_add_rows(dz, sv["u_pair"], dP0, col0=0, width=H)
     U = dz.shape[0]
     ident_u = torch.arange(U, dtype=torch.int32, device=dev)
@@ -514,7 +545,7 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
 # ------------------------------------------------------------------------------------------------------------------------
 def linear(A, W, bias=None, act=ACT_NONE, res=None, drop=None):
     """drop(act(A W^T + bias)) + res  (fp32, fb_gemm); drop = (Drop, layer, site name, row0) or None"""
-    _chk(A), _chk(W)
+    _chk(A), _chk(W, W.dtype if W.dtype == torch.bfloat16 else torch.float32)
     if bias is not None:
         _chk(bias)
     if res is not None:
@@ -649,6 +680,25 @@ def interface_indices(row, col, geo):
     return dict(pair=i32(pair), u_pair=i32(pair[u]), u_pi=i32(pi[u]), u_ci=i32(ci[u]), rowptr=i32(rowptr))
 
 
+def _pt1_cols(H):
+    return H + 128 if PRECISION == "bf16" else H + 64
+
+
+def _pt1_padded(w, name, H):
+    """pt1_w [2H, H+64] (or its transpose [H+64, 2H]) zero-padded to H+128 input columns under PRECISION = 'bf16'"""
+    t = w[name]
+    Kp = _pt1_cols(H)
+    if Kp == H + 64:
+        return t
+    if name.endswith("_t"):
+        out = torch.zeros(Kp, t.shape[1], dtype=t.dtype, device=t.device)
+        out[:H + 64].copy_(t)
+    else:
+        out = torch.zeros(t.shape[0], Kp, dtype=t.dtype, device=t.device)
+        out[:, :H + 64].copy_(t)
+    return out
+
+
 def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax, drop=None, layer=0):
     """MC_Att_L forward (egnn.py:186-333, cross_att.py:24-54; inference twin: forward.cu::run_att) keeping what att_backward consumes.
     row / col must be sorted by row (the library's interface graph is); idx = interface_indices(row, col, geo)."""
@@ -672,10 +722,13 @@ def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax, drop=No
     pc32[Nc:].copy_(gather_rows(QK, torch.arange(Nc, N, dtype=torch.int32, device=dev), 2 * H, 32))
     pc32[:Nc].copy_(gather_rows(QK, torch.arange(0, Nc, dtype=torch.int32, device=dev), 2 * H + 32, 32))
     U = idx["u_pair"].numel()
-    zcat = torch.zeros(U, H + 64, dtype=torch.float32, device=dev)
+    # [pair0 | t32 | 0]: H + 64 columns; under PRECISION = "bf16" padded to H + 128 so that the weight-gradient and data-gradient
+    # GEMMs of pair_transition.linear_1 tile on tcgen05 (N = K_in must be a multiple of 128)
+    Kp = _pt1_cols(H)
+    zcat = torch.zeros(U, Kp, dtype=torch.float32, device=dev)
     zcat[:, :H].copy_(gather_rows(P0, idx["u_pair"]))
     zcat[:, H:H + 32].copy_(vec_mul(gather_rows(pc32, idx["u_pi"]), gather_rows(pc32, idx["u_ci"])))
-    Zp = linear(zcat, w["pt1_w"], w["pt1_b"])
+    Zp = linear(zcat, _pt1_padded(w, "pt1_w", H), w["pt1_b"])
     pbu = rowdot(act_fwd(Zp, ACT_RELU), w["pt2v"]).view(U, 1)
     rank1_add(pbu, _ones(U, dev), w["pt_c"])
     pb_dense = torch.zeros(P0.shape[0], 1, dtype=torch.float32, device=dev)

@@ -844,6 +844,41 @@ int32_t fb_rows_update(float* A, int32_t lda, int32_t M, int32_t N, const float*
   return FB_OK;
 }
 
+// dst[n, m] = bf16(src[m, n]) for m < M, 0 for M <= m < Mp: the K-major bf16 operand of a weight-gradient GEMM (reduction over the rows
+// of the activation), 32 x 32 tiles through shared memory so that both the fp32 reads and the bf16 writes are row-contiguous
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const float* __restrict__ src, int ld, int M, int N, bf16* __restrict__ dst, int Mp) {
+  pdl_entry();
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const int tiles_m = (Mp + 31) / 32, tiles_n = (N + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_m * tiles_n; t += gridDim.x) {
+    const int m0 = (t % tiles_m) * 32, n0 = (t / tiles_m) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty + 8 * i, n = n0 + tx;
+      tile[ty + 8 * i][tx] = (m < M && n < N) ? src[(size_t)m * ld + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i, m = m0 + tx;
+      if (n < N && m < Mp) dst[(size_t)n * Mp + m] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+    __syncthreads();
+  }
+}
+
+int32_t fb_transpose_bf16(const float* src, int32_t ld, int32_t M, int32_t N, void* dst, int32_t Mp, void* stream) {
+  if (M <= 0 || N <= 0) return FB_OK;
+  if (Mp < M) return FB_ERR_BAD_ARG;
+  const long long tiles = (long long)((Mp + 31) / 32) * ((N + 31) / 32);
+  fb_launch(transpose_bf16_kernel, dim3((int)(tiles < 148 * 16 ? tiles : 148 * 16)), dim3(256), 0, (cudaStream_t)stream, src, (int)ld, (int)M,
+            (int)N, (bf16*)dst, (int)Mp);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
 // dst[m, n] = keep(seed, site, row0 + m, n) ? src[m, n] / (1 - p) : 0  -- the library's counter-based dropout mask (common.cuh) as a
 // stand-alone op: the training-mode forward applies it where the inference path has it fused into an epilogue, and the reverse
 // pass applies the SAME mask to the incoming gradient (the mask is a pure function of its coordinates, nothing is stored).

@@ -79,7 +79,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // 16-byte piece j (0..7) of row r (0..31) inside a 128B-swizzled box
 __device__ __forceinline__ uint32_t sw_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-template <int BN, int STAGES, int NS, bool GROUPED>
+// SPLIT: split-precision instantiation (table-driven k-block walk in the producer, full-precision SiLU in the epilogue); a template
+// parameter so that the bf16 instantiation carries neither (a runtime select between the two SiLU forms inside the unrolled epilogue
+// cost 2.3x on the edge GEMM)
+template <int BN, int STAGES, int NS, bool GROUPED, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w2,
@@ -99,7 +102,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint32_t* tmem_slot = (uint32_t*)(resbar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = p.nprod ? p.nprod * p.KB1 : p.KB1 + p.KB2;
+  const int KB = SPLIT ? p.nprod * p.KB1 : p.KB1 + p.KB2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -164,7 +167,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + S::A_BYTES;
           mbar_expect_tx(&full[s], S::STAGE_BYTES);
-          if (p.nprod) {
+          if (SPLIT) {
             // split precision: k-block kb = product j of plane pair (pa, pw), smallest terms first
             const int j = kb / p.KB1, r = kb - j * p.KB1;
             tma_load_2d(&map_a, &full[s], a_dst, (split_plane_a(j, p.nprod) * p.KB1 + r) * BK, m0);
@@ -265,7 +268,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bv[ch], j);
-          if (pp.act == FB_ACT_SILU) x = pp.exact_act ? silu(x) : silu_fast(x);
+          if (pp.act == FB_ACT_SILU) x = SPLIT ? silu(x) : silu_fast(x);
           else if (pp.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
@@ -367,8 +370,12 @@ static int launch(const GemmArgs& g, const GemmArgs* g1, int m_begin1, cudaStrea
   static_assert(S::TOTAL <= 232448, "shared memory budget");
   static unsigned long long optin = 0, optin_g = 0;
   static int num_sms = 0;
-  auto kern = g1 ? gemm_tc3_kernel<BN, STAGES, NS, true> : gemm_tc3_kernel<BN, STAGES, NS, false>;
-  if (!ensure_smem_optin(kern, S::TOTAL, g1 ? optin_g : optin)) return FB_ERR_CUDA;
+  static unsigned long long optin_s = 0;
+  const bool split = g.nprod > 0;
+  auto kern = split ? gemm_tc3_kernel<BN, STAGES, NS, false, true>
+                    : (g1 ? gemm_tc3_kernel<BN, STAGES, NS, true, false> : gemm_tc3_kernel<BN, STAGES, NS, false, false>);
+  if (split && g1) return FB_ERR_UNSUPPORTED;
+  if (!ensure_smem_optin(kern, S::TOTAL, split ? optin_s : (g1 ? optin_g : optin))) return FB_ERR_CUDA;
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -107,6 +107,7 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t sw_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
+template <bool SPLIT>   // split-precision instantiation: table-driven k-block walk + full-precision SiLU (see gemm_tc3.cu)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
@@ -124,7 +125,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int KB = p.nprod ? p.nprod * p.KB1 : p.KB1 + p.KB2;
+  const int KB = SPLIT ? p.nprod * p.KB1 : p.KB1 + p.KB2;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
@@ -172,7 +173,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           uint8_t* b_dst = a_dst + S::A_BYTES;
           if (leader) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
-          if (p.nprod) {
+          if (SPLIT) {
             const int j = kb / p.KB1, r = kb - j * p.KB1;
             tma_load_2d_pair(&map_a, &full[s], a_dst, (split_plane_a(j, p.nprod) * p.KB1 + r) * BK, m0);
             tma_load_2d_pair(&map_w, &full[s], b_dst, (split_plane_w(j, p.nprod) * p.KB1 + r) * BK, n0);
@@ -259,7 +260,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bv[ch], j);
-          if (p.act == FB_ACT_SILU) x = p.exact_act ? silu(x) : silu_fast(x);
+          if (p.act == FB_ACT_SILU) x = SPLIT ? silu(x) : silu_fast(x);
           else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
           o[j] = x;
         }
@@ -323,9 +324,11 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 static int launch(const GemmArgs& g, cudaStream_t st) {
   using S = Smem;
   static_assert(S::TOTAL <= 232448, "shared memory budget");
-  static unsigned long long optin = 0;
+  static unsigned long long optin = 0, optin_s = 0;
   static int num_sms = 0;
-  if (!ensure_smem_optin(gemm_tc4_kernel, S::TOTAL, optin)) return FB_ERR_CUDA;
+  const bool split = g.nprod > 0;
+  auto kern = split ? gemm_tc4_kernel<true> : gemm_tc4_kernel<false>;
+  if (!ensure_smem_optin(kern, S::TOTAL, split ? optin_s : optin)) return FB_ERR_CUDA;
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -350,7 +353,7 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
   p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride; p.n_split = g.n_split; p.m_dev = g.m_dev; p.drop = g.drop;
   const int tiles = ((g.M + PM - 1) / PM) * (g.N / BN);
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  fb_launch(gemm_tc4_kernel, dim3(2 * pairs), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, mc, mcb, p);
+  fb_launch(kern, dim3(2 * pairs), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, mc, mcb, p);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

@@ -113,7 +113,28 @@ def max_over_ranks(ms, device=None, group=None):
 
 
 # ---- training side of the data parallelism: ONE all-reduce of all gradients per step -------------------
-def allreduce_gradients(params, group=None, average=True, buffer=None):
+def _aliased_flat(params, model):
+    """the flat gradient buffer of the last training step (train._backward_half) if every parameter's .grad still is a view into it,
+    else None"""
+    hint = getattr(model, "_fb_flat_grad", None) if model is not None else None
+    if hint is None:
+        return None
+    flat, layout = hint
+    named = dict(model.named_parameters())
+    want = {id(p) for p in params}
+    seen = 0
+    for k, o, n, shape in layout:
+        p = named.get(k)
+        if p is None:
+            continue
+        if id(p) not in want or p.grad is None or p.grad.dtype != torch.float32 or not p.grad.is_contiguous() or \
+                p.grad.data_ptr() != flat.data_ptr() + 4 * o or p.grad.numel() != n:
+            return None
+        seen += 1
+    return flat if seen == len(want) else None
+
+
+def allreduce_gradients(params, group=None, average=True, buffer=None, model=None):
     """Sum (or average) the gradients of `params` over the ranks with a SINGLE collective on one flat fp32 buffer (the reference
     trains under DDP with `find_unused_parameters=True`, FABind/fabind/main_fabind.py:198-200: 36-45 M fp32 gradients, the unused
     `att_i.inter_layer.*` parameters contribute zeros).  Parameters whose `.grad` is None on this rank are treated as zero and
@@ -122,6 +143,15 @@ def allreduce_gradients(params, group=None, average=True, buffer=None):
     params = [p for p in params if p.requires_grad]
     if not params:
         return buffer
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    flat = _aliased_flat(params, model)
+    if flat is not None:
+        # the training step left all gradients in ONE flat buffer that the .grad tensors alias: reduce it in place, no copies
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat.div_(world)
+        return flat
     n = sum(p.numel() for p in params)
     dev = params[0].device
     if buffer is None or buffer.numel() != n or buffer.device != dev:
@@ -134,7 +164,6 @@ def allreduce_gradients(params, group=None, average=True, buffer=None):
         else:
             buffer[o:o + k].copy_(p.grad.reshape(-1))
         o += k
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > 1:
         dist.all_reduce(buffer, op=dist.ReduceOp.SUM, group=group)
         if average:

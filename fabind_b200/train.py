@@ -23,12 +23,35 @@ import torch
 
 from . import backward as bw
 from .layout import build_layout
-from .weights import slots, pack_state_dict, arena_grads_to_state_dict
+from .weights import slots, pack_state_dict, arena_grads_to_state_dict, GraphedPacker
+
+# pack / un-pack of the weight arena replayed from CUDA graphs (weights.GraphedPacker); False = the eager torch ops every step
+USE_GRAPHS = True
 
 
-def slot_tensors(arena, hidden, n_layers, flavour=0):
-    """{prefix: {slot: tensor view (+ `_t` transposed copies of the matrices)}} over a flat arena on any device"""
+def _packer(model, sd, H, L, flavour, dev):
+    """the module's GraphedPacker, re-captured when a parameter storage was re-allocated"""
+    key = GraphedPacker.make_key(sd, H, L, flavour, dev)
+    pk = getattr(model, "_fb_packer", None)
+    if pk is None or pk.key != key:
+        pk = GraphedPacker(sd, H, L, flavour, dev)
+        try:
+            object.__setattr__(model, "_fb_packer", pk)
+        except Exception:
+            pass
+    return pk
+
+
+def slot_tensors(arena, hidden, n_layers, flavour=0, bf16=None):
+    """{prefix: {slot: tensor view (+ `_t` transposed copies of the matrices)}} over a flat arena on any device.
+    bf16 (default: backward.PRECISION == "bf16"): the arena is converted to bf16 ONCE, every matrix view gets its bf16 twin registered
+    with backward.register_bf16 (the GEMM wrappers pick it up instead of converting per call) and the `_t` transposes are made in bf16
+    only (their one consumer is the data-gradient GEMM)."""
+    bf16 = (bw.PRECISION == "bf16") if bf16 is None else bf16
+    bf16 = bf16 and arena.is_cuda
     out = {}
+    bw.clear_bf16()
+    a16 = arena.to(torch.bfloat16) if bf16 else None
     for name, r, c, off in slots(hidden, n_layers, flavour):
         if r * c == 0:
             continue
@@ -39,7 +62,12 @@ def slot_tensors(arena, hidden, n_layers, flavour=0):
         d = out.setdefault(pre, {})
         d[base] = t.contiguous()
         if r > 1:
-            d[base + "_t"] = t.t().contiguous()
+            if bf16:
+                t16 = a16[off:off + r * c].view(r, c)
+                bw.register_bf16(d[base], t16)
+                d[base + "_t"] = t16.t().contiguous()
+            else:
+                d[base + "_t"] = t.t().contiguous()
     return out
 
 
@@ -101,7 +129,8 @@ def _forward_half(model, fa, prev_coords=None, edge_lists=None, state_dict=None,
     ctx, inter = (edge_lists or _gpu_edges)(model, X_prev, fa)
     lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
     geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
-    arena = pack_state_dict(sd, H, L, flavour, device=dev)
+    packer = _packer(model, sd, H, L, flavour, dev) if (USE_GRAPHS and dev.type == "cuda") else None
+    arena = packer.pack() if packer is not None else pack_state_dict(sd, H, L, flavour, device=dev)
     weights = slot_tensors(arena, H, L, flavour)
     consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,
                   xl=fa["batched_complex_coord_LAS"].reshape(-1, 3)[perm].to(torch.float32).contiguous())
@@ -119,7 +148,7 @@ def _forward_half(model, fa, prev_coords=None, edge_lists=None, state_dict=None,
     H_out = torch.empty(Hin.shape, dtype=fa["H"].dtype, device=dev)
     H_out[perm] = H_int.to(H_out.dtype)
     state = dict(H=H, L=L, flavour=flavour, sd=sd, arena=arena, weights=weights, tape=tape, top=top, geo=geo, edges=edges, consts=consts,
-                 perm=perm, moves=moves, Hin_shape=Hin.shape)
+                 perm=perm, moves=moves, Hin_shape=Hin.shape, packer=packer, model=model)
     return X_out, H_out, pair, state
 
 
@@ -138,7 +167,16 @@ def _backward_half(st, gX, gH, gP=None):
     for name, r, c, off in slots(st["H"], st["L"], flavour):
         if name in grads:
             garena[off:off + r * c] = grads[name].reshape(-1)
-    pgrads = arena_grads_to_state_dict(st["sd"], garena, st["H"], st["L"], flavour, device=garena.device)
+    if st.get("packer") is not None:
+        flat, pgrads = st["packer"].unpack(garena)
+        # one flat fp32 buffer holding every parameter gradient in state_dict order: shard.allreduce_gradients reduces it in place
+        # (no gather / scatter copies) when the parameters' .grad still alias it
+        try:
+            object.__setattr__(st["model"], "_fb_flat_grad", (flat, st["packer"].layout))
+        except Exception:
+            pass
+    else:
+        pgrads = arena_grads_to_state_dict(st["sd"], garena, st["H"], st["L"], flavour, device=garena.device)
     gH_in = torch.empty(st["Hin_shape"], dtype=torch.float32, device=dX_int.device)
     gH_in[perm] = dHin
     return pgrads, gH_in
@@ -179,9 +217,11 @@ class _StackFunction(torch.autograd.Function):
     def backward(ctx, gX, gH, gP=None):
         # (autograd materialises undefined output gradients as zeros: gX / gH / gP are always tensors here)
         pgrads, gH_in = _backward_half(ctx.st, gX, gH, gP)
+        ctx.st = None                                                   # the tape is consumed
         out = [None, None, None, None, None, None, gH_in.to(ctx.h_dtype)]
         for n, (dev, dt), p_needs in zip(ctx.names, ctx.pmeta, ctx.needs_input_grad[7:]):
-            out.append(pgrads[n].to(dev, dt) if p_needs else None)      # the packer's chain rule runs on the host
+            g = pgrads.pop(n)                                           # no second reference: autograd may adopt the view as .grad
+            out.append(g.to(dev, dt) if p_needs else None)
         return tuple(out)
 
 
@@ -217,5 +257,5 @@ def apply_gradients(model, pgrads, group=None, average=True):
     params = dict(model.named_parameters())
     for k, p in params.items():
         g = pgrads.get(k)
-        p.grad = None if g is None else g.to(p.device, p.dtype).reshape(p.shape).clone()
-    allreduce_gradients(list(params.values()), group=group, average=average)
+        p.grad = None if g is None else g.to(p.device, p.dtype).reshape(p.shape)
+    allreduce_gradients(list(params.values()), group=group, average=average, model=model)

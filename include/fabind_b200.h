@@ -313,6 +313,9 @@ int32_t fb_rowdot2(const float* A, int32_t lda, const float* B, int32_t ldb, int
 int32_t fb_rows_update(float* A, int32_t lda, int32_t M, int32_t N, const float* u, const float* v, int32_t mode, void* stream);
 /* op 0: c = a*b, 1: c = a+b, 2: c += a*b */
 int32_t fb_vec_op(const float* a, const float* b, float* c, int64_t n, int32_t op, void* stream);
+/* dst[n, m] = bf16(src[m, n]) (m < M; zero for M <= m < Mp), dst row stride Mp: the K-major operands of the weight-gradient GEMM
+ * dW = dY^T X on tcgen05 (reduction over the rows) */
+int32_t fb_transpose_bf16(const float* src, int32_t ld, int32_t M, int32_t N, void* dst, int32_t Mp, void* stream);
 /* nn.Dropout of the training step (egnn.py:82,106,236,398,461; cross_att.py:128) as a stand-alone op, forward and reverse alike:
  * dst[m,n] = keep(seed, site, row0 + m, n) ? src[m,n] / (1-p) : 0 with the library's counter-based mask (fb_model_params.dropout_*);
  * dst may alias src */
