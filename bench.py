@@ -469,7 +469,7 @@ def cpu_baseline_leg(model):
                       "probes, then 1 warm-up + 8 timed full forwards, median"}
 
 
-def roofline_objects(prof, peaks, clk, e_ctx, ms_per_step):
+def roofline_objects(prof, peaks, clk, e_ctx, ms_per_step, pair_rows_frac=1.0):
     """`roofline` = the stage that dominates the step, `roofline_kernels` = every GEMM stage; denominator: the burst peak unless the
     sampled SM clock sat well below max (a capped / sustained state), then the sustained peak -- stated in peak_source."""
     capped = bool(clk) and clk.get("sm_max_mhz") and clk["sm_mhz"] < 0.85 * clk["sm_max_mhz"]
@@ -485,6 +485,8 @@ def roofline_objects(prof, peaks, clk, e_ctx, ms_per_step):
              "gemm_pair": "pair-path GEMM on the unique interface pairs (M = E_int / 2, K = 576, N = 1024, row-dot epilogue)",
              "gemm_pair0": "pair_embed0 + pair-bias GEMMs (once per forward, M = pair rows)"}
     total = max(sum(v["ms_per_step"] for v in prof.values()), 1e-9)
+    # the pair-path GEMM is enqueued with its row CAPACITY (the row count lives on the device): scale to the rows it actually processes
+    prof["gemm_pair"]["gflop_per_step"] *= pair_rows_frac
     objs = {}
     for c in ("gemm_edge", "gemm_node", "gemm_pair", "gemm_pair0"):
         v = prof[c]
@@ -681,7 +683,9 @@ def main():
     out["config"] = cfg
     out["clocks"] = clk
     if prof is not None:
-        dominant, kernels, step = roofline_objects(prof, peaks, clk, cfg["ctx_edges"], out["ms_per_step"])
+        e_int = model.last_stats["inter_edges_per_iter"].float().mean().item()
+        cap_u = sum(c * p for c, p in zip(host.n_c, host.n_p))
+        dominant, kernels, step = roofline_objects(prof, peaks, clk, cfg["ctx_edges"], out["ms_per_step"], min(1.0, 0.5 * e_int / max(cap_u, 1)))
         out["roofline"] = dominant
         out["roofline_kernels"] = kernels
         out["roofline_step"] = step

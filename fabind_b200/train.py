@@ -23,18 +23,22 @@ import torch
 
 from . import backward as bw
 from .layout import build_layout
-from .weights import slots, pack_state_dict, arena_grads_to_state_dict, GraphedPacker
+from .weights import slots, pack_state_dict, arena_grads_to_state_dict, GraphedPacker, FastPackerV1
 
-# pack / un-pack of the weight arena replayed from CUDA graphs (weights.GraphedPacker); False = the eager torch ops every step
-USE_GRAPHS = True
+# per-step pack / un-pack of the weight arena: v1 layout = explicit selection + hand-written chain rule (weights.FastPackerV1), FABind+
+# layout = the generic functions replayed from CUDA graphs (weights.GraphedPacker); False = the generic eager torch ops every step
+USE_FAST_PACKER = True
 
 
 def _packer(model, sd, H, L, flavour, dev):
-    """the module's GraphedPacker, re-captured when a parameter storage was re-allocated"""
+    """the module's packer object, rebuilt when a parameter storage was re-allocated"""
     key = GraphedPacker.make_key(sd, H, L, flavour, dev)
     pk = getattr(model, "_fb_packer", None)
     if pk is None or pk.key != key:
-        pk = GraphedPacker(sd, H, L, flavour, dev)
+        if flavour == 0 and all(v.dtype == torch.float32 for v in sd.values() if v.is_floating_point()):
+            pk = FastPackerV1(sd, H, L, dev)
+        else:
+            pk = GraphedPacker(sd, H, L, flavour, dev)
         try:
             object.__setattr__(model, "_fb_packer", pk)
         except Exception:
@@ -129,7 +133,7 @@ def _forward_half(model, fa, prev_coords=None, edge_lists=None, state_dict=None,
     ctx, inter = (edge_lists or _gpu_edges)(model, X_prev, fa)
     lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
     geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
-    packer = _packer(model, sd, H, L, flavour, dev) if (USE_GRAPHS and dev.type == "cuda") else None
+    packer = _packer(model, sd, H, L, flavour, dev) if (USE_FAST_PACKER and (dev.type == "cuda" or flavour == 0)) else None
     arena = packer.pack() if packer is not None else pack_state_dict(sd, H, L, flavour, device=dev)
     weights = slot_tensors(arena, H, L, flavour)
     consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,

@@ -315,3 +315,137 @@ class GraphedPacker:
         else:
             flat = self._eager_unpack_flat(garena)
         return flat, {k: flat[o:o + n].view(shape) for k, o, n, shape in self.layout}
+
+
+class FastPackerV1:
+    """Explicit pack / chain rule for the v1 layout (training path): the packer is a SELECTION of parameter elements (with zero pads)
+    plus seven small bilinear derivations per MC_Att_L.  The selection is found once by running the derivations above on a
+    state_dict whose entries hold their own flat index (float64 ids), so it stays tied to `_top/_gcl/_att`; per step
+        pack:    arena[dst] = theta[src]  (one gather)          + the derived blocks (a few fp64 matmuls per layer)
+        unpack:  g_theta.index_add_(src, g_arena[dst])          + their hand-written chain rule
+    instead of several thousand small autograd kernels (`arena_grads_to_state_dict`: 14-18 ms of GPU time at the published size even
+    when replayed from a CUDA graph).  Checked against the generic functions in tests/test_host_logic.py."""
+
+    def __init__(self, sd, hidden, n_layers, device):
+        H, L = hidden, n_layers
+        self.H, self.L, self.device = H, L, torch.device(device)
+        self.sd = dict(sd)
+        self.ok, self.error = True, None
+        self.names = [k for k, v in sd.items() if v.is_floating_point()]
+        self.key = GraphedPacker.make_key(sd, H, L, 0, device)
+        self.layout, o = [], 0
+        ids = {}
+        for k in self.names:
+            n = sd[k].numel()
+            self.layout.append((k, o, n, tuple(sd[k].shape)))
+            ids[k] = (torch.arange(n, dtype=torch.float64) + (o + 1)).view(sd[k].shape)
+            o += n
+        self.total = o
+        self.off = {k: (o_, n_, s_) for k, o_, n_, s_ in self.layout}
+        groups = {"": _top(ids, H, L)}
+        for i in range(L):
+            groups[f"gcl{i}."] = _gcl(ids, f"gnn.gcl_{i}.", H)
+            groups[f"att{i}."] = _att(ids, f"gnn.att_{i}.", H)
+        groups["out."] = _gcl(ids, "gnn.out_layer.", H)
+        self.n_arena = _lib.lib().fb_weight_arena_elems_f(H, L, 0)
+        src = torch.zeros(self.n_arena, dtype=torch.int64)
+        self.slot = {}
+        for name, rows, cols, off in slots(H, L, 0):
+            if rows * cols == 0:
+                continue
+            pre, _, base = name.rpartition(".")
+            pre = pre + "." if pre else ""
+            self.slot[name] = (off, rows, cols)
+            blk = groups[pre][base].reshape(-1).double().round().long()
+            if pre.startswith("att"):
+                v = blk.view(rows, cols)
+                if base == "pt1_w":
+                    v[:, H:] = 0
+                elif base in ("pt1_b", "pt2v", "pt_c", "ac_u"):
+                    v[:] = 0
+                elif base == "qk_w":
+                    v[3 * H + QKX:] = 0
+                elif base == "qk_b":
+                    v[:, 3 * H + QKX:] = 0
+            src[off:off + rows * cols] = blk.clamp(min=0, max=self.total)
+        dst = src.nonzero().squeeze(1)
+        self.dst = dst.to(self.device)
+        self.src = (src[dst] - 1).to(self.device)
+
+    # ---- the seven derived blocks of one MC_Att_L (weights.py::_att) and their chain rule -------------------------------------
+    def _att_keys(self, l):
+        p = f"gnn.att_{l}."
+        ca = p + "cross_attn_module."
+        return dict(W1p=ca + "pair_transition.linear_1.weight", b1=ca + "pair_transition.linear_1.bias",
+                    W2=ca + "pair_transition.linear_2.weight", b2=ca + "pair_transition.linear_2.bias",
+                    Wo=ca + "inter_layer.linear_out.weight", bo=ca + "inter_layer.linear_out.bias",
+                    wb=p + "attn_bias_proj.weight", bb=p + "attn_bias_proj.bias", ac1=p + "coord_mlp.0.weight",
+                    Wkv=p + "linear_kv.weight", bkv=p + "linear_kv.bias")
+
+    def _view(self, flat, key):
+        o, n, shape = self.off[key]
+        return flat[o:o + n].view(shape)
+
+    def _slot(self, arena, name):
+        off, r, c = self.slot[name]
+        return arena[off:off + r * c].view(r, c)
+
+    def pack(self, sd=None):
+        """fp32 arena on self.device from the live state_dict tensors (same values as pack_state_dict)"""
+        H = self.H
+        sd = self.sd if sd is None else sd
+        theta = torch.cat([sd[k].detach().reshape(-1).to(self.device, torch.float32) for k in self.names])
+        arena = torch.zeros(self.n_arena, dtype=torch.float32, device=self.device)
+        arena[self.dst] = theta[self.src]
+        for l in range(self.L):
+            k = self._att_keys(l)
+            t = {n: self._view(theta, key).double() for n, key in k.items()}
+            pre = f"att{l}."
+            Wkv, bkv, ac1 = t["Wkv"], t["bkv"], t["ac1"]
+            wb = t["wb"][0]
+            self._slot(arena, pre + "pt1_w")[:, H:H + 32] = (t["W1p"] @ t["Wo"]).float()
+            self._slot(arena, pre + "pt1_b")[0] = (t["b1"] + t["W1p"] @ t["bo"]).float()
+            self._slot(arena, pre + "pt2v")[0] = (t["W2"].t() @ wb).float()
+            self._slot(arena, pre + "pt_c")[0, 0] = (wb @ t["b2"] + t["bb"][0]).float()
+            self._slot(arena, pre + "qk_w")[3 * H + QKX:] = (ac1 @ Wkv[1::2, 1:]).float()
+            self._slot(arena, pre + "qk_b")[0, 3 * H + QKX:] = (ac1 @ bkv[1::2]).float()
+            self._slot(arena, pre + "ac_u")[0] = (ac1 @ Wkv[1::2, 0]).float()
+        return arena
+
+    def unpack(self, garena, sd=None):
+        """arena gradient -> (flat fp32 gradient in state_dict order, {name: view})"""
+        H = self.H
+        sd = self.sd if sd is None else sd
+        garena = garena.reshape(-1).to(self.device, torch.float32)
+        g = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        g.index_add_(0, self.src, garena[self.dst])
+        for l in range(self.L):
+            k = self._att_keys(l)
+            P = {n: sd[key].detach().to(self.device, torch.float32) for n, key in k.items()}
+            G = {n: self._view(g, key) for n, key in k.items()}
+            pre = f"att{l}."
+            wb = P["wb"][0]
+            g_pt1 = self._slot(garena, pre + "pt1_w")[:, H:H + 32]           # d(W1p Wo)
+            G["W1p"] += g_pt1 @ P["Wo"].t()
+            G["Wo"] += P["W1p"].t() @ g_pt1
+            g_b = self._slot(garena, pre + "pt1_b")[0]                        # d(b1 + W1p bo)
+            G["b1"] += g_b
+            G["W1p"] += torch.outer(g_b, P["bo"])
+            G["bo"] += P["W1p"].t() @ g_b
+            g_v = self._slot(garena, pre + "pt2v")[0]                         # d(W2^T wb)
+            G["W2"] += torch.outer(wb, g_v)
+            G["wb"][0] += P["W2"] @ g_v
+            g_c = self._slot(garena, pre + "pt_c")[0, 0]                      # d(wb . b2 + bb)
+            G["wb"][0] += g_c * P["b2"]
+            G["b2"] += g_c * wb
+            G["bb"][0] += g_c
+            g_vc = self._slot(garena, pre + "qk_w")[3 * H + QKX:]             # d(ac1 Wkv_v)
+            G["ac1"] += g_vc @ P["Wkv"][1::2, 1:].t()
+            G["Wkv"][1::2, 1:] += P["ac1"].t() @ g_vc
+            g_vb = self._slot(garena, pre + "qk_b")[0, 3 * H + QKX:]          # d(ac1 bkv_v)
+            G["ac1"] += torch.outer(g_vb, P["bkv"][1::2])
+            G["bkv"][1::2] += P["ac1"].t() @ g_vb
+            g_u = self._slot(garena, pre + "ac_u")[0]                         # d(ac1 v_r)
+            G["ac1"] += torch.outer(g_u, P["Wkv"][1::2, 0])
+            G["Wkv"][1::2, 0] += P["ac1"].t() @ g_u
+        return g, {k_: g[o:o + n].view(shape) for k_, o, n, shape in self.layout}

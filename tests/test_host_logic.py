@@ -128,3 +128,29 @@ def test_apply_gradients_sets_param_grads_single_process():
     params = dict(m.named_parameters())
     assert all(float(params[k].grad.mean()) == 0.5 for k in names[:-2])
     assert all(params[k].grad is not None and float(params[k].grad.abs().max()) == 0.0 for k in names[-2:])
+
+
+def test_fast_packer_matches_the_generic_packer():
+    """weights.FastPackerV1 (what the training step uses every step: one gather + seven bilinear blocks per MC_Att_L, hand-written
+    chain rule) against pack_state_dict / arena_grads_to_state_dict (the differentiable derivations): identical arena, same
+    parameter gradients"""
+    import torch
+    from fabind_b200 import EfficientMCAttModel
+    from fabind_b200.config import published_args
+    from fabind_b200.weights import FastPackerV1, pack_state_dict, arena_grads_to_state_dict
+    for H, L in [(64, 2), (128, 1)]:
+        torch.manual_seed(H)
+        m = EfficientMCAttModel(published_args(), H, H, 1, n_layers=L, n_iter=2, normalize_coord=lambda x: x / 5.0,
+                                unnormalize_coord=lambda x: x * 5.0)
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        for v in sd.values():
+            v.copy_(torch.randn_like(v))
+        fp = FastPackerV1(sd, H, L, "cpu")
+        a0, a1 = pack_state_dict(sd, H, L, 0), fp.pack()
+        assert torch.equal(a0, a1)
+        ga = torch.randn_like(a0)
+        g0 = arena_grads_to_state_dict(sd, ga, H, L, 0)
+        flat, g1 = fp.unpack(ga)
+        assert set(g0) == set(g1) and flat.numel() == sum(v.numel() for v in g0.values())
+        for k in g0:
+            assert float((g0[k] - g1[k]).abs().max()) <= 2e-6 * float(g0[k].abs().max()) + 1e-7, k
