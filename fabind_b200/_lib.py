@@ -96,6 +96,9 @@ EXPORTS = {
     "fb_edges_ref_fill": (C.c_int32, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                       C.c_float, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
+    "fb_row_attention_tc": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "fb_gemm": (C.c_int32, [C.POINTER(GemmParams), C.c_void_p]),
     "fb_gemm_pair": (C.c_int32, [C.POINTER(GemmParams), C.POINTER(GemmParams), C.c_void_p]),
     "fb_gemm_dot_tiles": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

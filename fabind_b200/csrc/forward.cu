@@ -268,6 +268,7 @@ struct Bufs {
   // node features
   float *Hin32, *h, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
   void *HinT, *hT, *agg, *T1, *O, *TH, *VT, *Pn, *VCT;
+  void *CAcT, *CApT, *CAp2T;   // bf16 projections of the cross-attention block (tcgen05 attention core)
   // pair
   void *P0, *A0, *Zg, *T64; float *PBraw, *PB, *pb_dense, *dotU;
   // edge
@@ -312,6 +313,8 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.dotE = a.get<float>(tilesH * E);
   b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
   b.CAc = a.get<float>((Nc + 1) * 4 * HD); b.CAp = a.get<float>((Np + 1) * 2 * HD); b.CAp2 = a.get<float>((Np + 1) * 2 * HD);
+  b.CAcT = b.CApT = b.CAp2T = nullptr;
+  if (bf) { b.CAcT = a.take((Nc + 1) * 4 * HD * 2); b.CApT = a.take((Np + 1) * 2 * HD * 2); b.CAp2T = a.take((Np + 1) * 2 * HD * 2); }
   b.O = a.take(N * HD * TS); b.TH = a.take(N * 2 * H * TS);
   b.Zg = a.take(capU * H * TS); b.T64 = a.take(capU * 64 * TS);
   b.dotU = a.get<float>(tiles2H * capU);
@@ -413,6 +416,30 @@ struct Run {
     prof_end(st);
   }
 
+  // the attention core of both RowAttentionBlocks runs on tcgen05 (xatt_tc.cu) in bf16 mode when the per-complex blocks fit its
+  // tiles (keys <= 256 per complex); otherwise (and in the fp32 / split-precision parity modes) on the SIMT kernel
+  bool xa_on() const {
+    return bf && row_attention_tc_supported(p.max_p, p.max_c) && row_attention_tc_supported(p.max_c, p.max_p);
+  }
+  int att_p(const float* PBs) {
+    if (xa_on())
+      return row_attention_tc(g, 1, p.max_p, p.max_c, b.CApT, 2 * HD, 0, HD, Np, b.CAcT, 4 * HD, 0, HD, Nc, PBs, b.O, HD, st);
+    const float* CApv = b.CAp - (size_t)Nc * 2 * HD;  // virtual base indexed by internal node id
+    return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD, PBs, b.O, HD, bf, st);
+  }
+  int att_c(const float* PBs) {
+    if (xa_on())
+      return row_attention_tc(g, 0, p.max_c, p.max_p, b.CAcT, 4 * HD, 2 * HD, 3 * HD, Nc, b.CAp2T, 2 * HD, 0, HD, Np, PBs, b.O, HD, st);
+    const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
+    return row_attention(g, 0, p.max_c, p.max_p, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD, PBs, b.O, HD,
+                         bf, st);
+  }
+  // projections of the block: fp32 outputs for the SIMT attention kernel, bf16 outputs (TMA-loadable operands) for the tcgen05 one
+  GemmArgs proj(const void* A, int64_t w_off, int Nout, int64_t b_off, int M, float* C32, void* C16) {
+    return xa_on() ? mk(A, H, H, w_off, Nout, b_off, FB_ACT_NONE, M, nullptr, 0, C16, Nout)
+                   : mk(A, H, H, w_off, Nout, b_off, FB_ACT_NONE, M, C32, Nout, nullptr, 0);
+  }
+
   void run_gcl(const GclW& gw, const float* x_in, float* x_out, bool need_h) {
     const int E = p.E_ctx;
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
@@ -442,21 +469,12 @@ struct Run {
     void* hTp = at(b.hT, (size_t)Nc * H);
     gemm_cat = CAT_GEMM_NODE;
     // --- cross attention (cross_att.py:24-54) on the per-complex blocks
-    gemm_pair(mk(b.hT, H, H, aw.ca_c_w, 4 * HD, aw.ca_c_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0),
-              mk(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0));
-    const float* CApv = b.CAp - (size_t)Nc * 2 * HD;  // virtual base indexed by internal node id
-    stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD,
-                           b.PB + (size_t)(layer * 2 + 0) * P * 4, b.O, HD, bf, st);
-    });
+    gemm_pair(proj(b.hT, aw.ca_c_w, 4 * HD, aw.ca_c_b, Nc, b.CAc, b.CAcT), proj(hTp, aw.ca_p_w, 2 * HD, aw.ca_p_b, Np, b.CAp, b.CApT));
+    stage(CAT_ATTENTION, [&] { return att_p(b.PB + (size_t)(layer * 2 + 0) * P * 4); });
     // RowAttentionBlock dropout on the attention output (cross_att.py:128), row index = internal node id
     gemm(wd(mk(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H), dr(S_PATT, Nc)));
-    gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
-    const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
-    stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 0, p.max_c, p.max_p, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
-                           b.PB + (size_t)(layer * 2 + 1) * P * 4, b.O, HD, bf, st);
-    });
+    gemm(proj(hTp, aw.ca_p2_w, 2 * HD, -1, Np, b.CAp2, b.CAp2T));
+    stage(CAT_ATTENTION, [&] { return att_c(b.PB + (size_t)(layer * 2 + 1) * P * 4); });
     gemm(wd(mk(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H), dr(S_CATT)));
     // transitions (model_utils.py:171-175), residual
     void* THp = at(b.TH, (size_t)Nc * 2 * H);
@@ -539,19 +557,11 @@ struct Run {
     gemm(pair_in, H, H, aw.pb_w, 128, aw.pb_b, FB_ACT_NONE, (int)P, b.PBraw, 128, nullptr, 0);
     stage(CAT_EDGE_ELEMWISE, [&] { return pair_bias_gate((int)P, 1, b.PBraw, 128, b.PB, st); });
     gemm_cat = CAT_GEMM_NODE;
-    gemm_pair(mk(b.hT, H, H, aw.ca_c_w, 4 * HD, aw.ca_c_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0),
-              mk(hTp, H, H, aw.ca_p_w, 2 * HD, aw.ca_p_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0));
-    const float* CApv = b.CAp - (size_t)Nc * 2 * HD;
-    stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 1, p.max_p, p.max_c, CApv, 2 * HD, CApv + HD, 2 * HD, b.CAc, 4 * HD, b.CAc + HD, 4 * HD, b.PB, b.O, HD, bf, st);
-    });
+    gemm_pair(proj(b.hT, aw.ca_c_w, 4 * HD, aw.ca_c_b, Nc, b.CAc, b.CAcT), proj(hTp, aw.ca_p_w, 2 * HD, aw.ca_p_b, Np, b.CAp, b.CApT));
+    stage(CAT_ATTENTION, [&] { return att_p(b.PB); });
     gemm(wd(mk(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H), dr(S_PATT, Nc)));
-    gemm(hTp, H, H, aw.ca_p2_w, 2 * HD, -1, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0);
-    const float* CAp2v = b.CAp2 - (size_t)Nc * 2 * HD;
-    stage(CAT_ATTENTION, [&] {
-      return row_attention(g, 0, p.max_c, p.max_p, b.CAc + 2 * HD, 4 * HD, b.CAc + 3 * HD, 4 * HD, CAp2v, 2 * HD, CAp2v + HD, 2 * HD,
-                           b.PB + P * 4, b.O, HD, bf, st);
-    });
+    gemm(proj(hTp, aw.ca_p2_w, 2 * HD, -1, Np, b.CAp2, b.CAp2T));
+    stage(CAT_ATTENTION, [&] { return att_c(b.PB + P * 4); });
     gemm(wd(mk(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, b.h, H, b.hT, H, b.h, H), dr(S_CATT)));
     // transitions = MLPwithLastAct (LN, Linear+ReLU, Linear+ReLU), residual
     void* Tnp = at(b.Tn, (size_t)Nc * H);
@@ -943,6 +953,17 @@ int32_t fb_gemm_set_debug(int64_t* dbg) {
 int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt) {
   if (force_simt) return gemm_simt_dot_tiles(N);
   return gemm_dot_tiles(M, N, K, bf16_mode);
+}
+
+int32_t fb_row_attention_tc(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t Nc_tot,
+                            int32_t q_is_prot, int32_t max_q, int32_t max_k, const void* QG, int32_t ldqg, int32_t qcol, int32_t gcol,
+                            int32_t q_rows, const void* KV, int32_t ldkv, int32_t kcol, int32_t vcol, int32_t k_rows, const float* PB,
+                            void* O, int32_t ldo, void* stream) {
+  if (!c_off || !p_off || !pair_base || B <= 0 || !QG || !KV || !PB || !O) return FB_ERR_BAD_ARG;
+  GraphDev g{};
+  g.B = B; g.Nc_tot = Nc_tot; g.c_off = c_off; g.p_off = p_off; g.pair_base = pair_base;
+  return row_attention_tc(g, q_is_prot, max_q, max_k, QG, ldqg, qcol, gcol, q_rows, KV, ldkv, kcol, vcol, k_rows, PB, O, ldo,
+                          (cudaStream_t)stream);
 }
 
 int32_t fb_split_rows(const float* src, int32_t ld, int32_t M, int32_t K, void* dst, void* stream) {

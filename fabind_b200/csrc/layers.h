@@ -47,5 +47,9 @@ int pair_zin_plus(const GraphDev& g, int P_total, int H, const void* pair, const
 int pair_bias_all(int P_total, const float* dot, int tiles, int stride, const float* cst, float* pb_dense, cudaStream_t st);
 int pair_unpack(const GraphDev& g, int P_total, int H, int max_p, int max_c, const void* pair, float* out, bool bf16_mode, cudaStream_t st);
 int las_step(const GraphDev& g, const float* x, const float* xref, float step, float cl, float* x_out, cudaStream_t st);
+// ---- cross-attention core on tcgen05 (xatt_tc.cu): bf16 projections in, gated attention output out ----
+bool row_attention_tc_supported(int max_q, int max_k);
+int row_attention_tc(const GraphDev& g, int q_is_prot, int max_q, int max_k, const void* QG, int ldqg, int qcol, int gcol, int q_rows,
+                     const void* KV, int ldkv, int kcol, int vcol, int k_rows, const float* PB, void* O, int ldo, cudaStream_t st);
 
 }  // namespace fb

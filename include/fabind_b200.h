@@ -171,6 +171,17 @@ int32_t fb_edges_ref_fill(int32_t N, const int32_t* cplx, const int32_t* off, co
                           const float* x, float intra, float inter, int32_t* ws, const int32_t* counts_host,
                           int64_t* ctx_out /*[2,E_ctx]*/, int64_t* inter_out /*[2,E_int]*/, void* stream);
 
+/* Attention core of a RowAttentionBlock (cross_att.py:118-134; model_utils.py:21-38,96-133) on tcgen05, the kernel the stack uses in
+ * bf16 mode: O[q, h*32+d] = sigmoid(G) softmax_j(q_h . k_jh / sqrt(32) + PB[pair(q, j), h]) v_jh per complex, 4 heads x 32 channels.
+ * QG / KV: bf16 outputs of the stacked projections of the query side / key side (q_rows / k_rows rows, side-local row index =
+ * internal node id minus Nc_tot on the protein side); qcol / gcol / kcol / vcol: first column of Q, the gate, K, V (multiples of 64);
+ * PB [pair rows, 4] gated pair bias (pair row = pair_base[b] + prot_local * nc1 + comp_local); O [N, ldo] bf16, rows = internal node id.
+ * Keys per complex <= 256 (returns FB_ERR_UNSUPPORTED otherwise: the stack then runs its SIMT attention kernel). */
+int32_t fb_row_attention_tc(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t Nc_tot,
+                            int32_t q_is_prot, int32_t max_q, int32_t max_k, const void* QG, int32_t ldqg, int32_t qcol, int32_t gcol,
+                            int32_t q_rows, const void* KV, int32_t ldkv, int32_t kcol, int32_t vcol, int32_t k_rows, const float* PB,
+                            void* O, int32_t ldo, void* stream);
+
 /* Generic fused linear layer used by the stack (unit-test surface):
  * C = act([A|A2] W^T + bias) (+res).  bf16_mode selects operand type of A/A2/W/Cb. */
 typedef struct fb_gemm_params {
