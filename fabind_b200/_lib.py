@@ -30,7 +30,7 @@ class ModelParams(C.Structure):
         ("X_out", C.c_void_p), ("H_out", C.c_void_p), ("stats", C.c_void_p),
         ("trace_h", C.c_void_p), ("trace_x", C.c_void_p),
         ("flavour", C.c_int32), ("pair_out", C.c_void_p),
-        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint32), ("dropout_colonly", C.c_int32),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint32), ("dropout_colonly", C.c_int32), ("attn_tc", C.c_int32),
     ]
 
 

@@ -101,6 +101,9 @@ class EfficientMCAttModel(nn.Module):
         # tensor-core parity mode, <= 1e-4 rel vs the reference);  "bf16x3": three products;  "bf16": tcgen05 GEMMs with bf16
         # operands / fp32 accumulation (coordinates, softmax statistics and the residual stream stay fp32)
         self.precision = os.environ.get("FABIND_B200_PRECISION", "fp32")
+        # attention core of the RowAttentionBlocks in bf16 mode: "simt" (default, the faster kernel at PDBbind block sizes) or "tcgen05"
+        # (csrc/xatt_tc.cu: TMA-fed tiles, scores and outputs in TMEM)
+        self.attention = "simt"
         # train() mode: every nn.Dropout of the reference's stack is active (egnn.py:82,106,236,398,461, cross_att.py:128), in all
         # refinement iterations.  Masks are applied in-kernel, keyed by `dropout_seed` (None: drawn from torch's global generator per
         # call, like nn.Dropout; see fabind_b200/dropout.py); `dropout_colonly` = column-only masks (tests: pins mask placement)

@@ -416,10 +416,11 @@ struct Run {
     prof_end(st);
   }
 
-  // the attention core of both RowAttentionBlocks runs on tcgen05 (xatt_tc.cu) in bf16 mode when the per-complex blocks fit its
-  // tiles (keys <= 256 per complex); otherwise (and in the fp32 / split-precision parity modes) on the SIMT kernel
+  // the attention core of both RowAttentionBlocks runs on tcgen05 (xatt_tc.cu) in bf16 mode when asked for (fb_model_params.attn_tc)
+  // and the per-complex blocks fit its tiles (keys <= 256 per complex); otherwise (and in the fp32 / split-precision parity modes)
+  // on the SIMT kernel, which is the faster of the two at these block sizes (measured: DESIGN.md section 5)
   bool xa_on() const {
-    return bf && row_attention_tc_supported(p.max_p, p.max_c) && row_attention_tc_supported(p.max_c, p.max_p);
+    return bf && p.attn_tc && row_attention_tc_supported(p.max_p, p.max_c) && row_attention_tc_supported(p.max_c, p.max_p);
   }
   int att_p(const float* PBs) {
     if (xa_on())

@@ -156,6 +156,7 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.flavour = flavour
     if n_iter is not None:                       # training-mode `random_n_iter` draw (att_model.py:210-211)
         p.n_iter = int(n_iter)
+    p.attn_tc = 1 if getattr(module, "attention", "simt") == "tcgen05" else 0
     if dropout is not None and dropout[0] > 0:   # (p, seed, colonly): FABind+ sampling mode
         p.dropout_p, p.dropout_seed, p.dropout_colonly = float(dropout[0]), int(dropout[1]) & 0xFFFFFFFF, int(bool(dropout[2]))
     pair = None

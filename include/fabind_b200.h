@@ -85,6 +85,10 @@ typedef struct fb_model_params {
    * values scaled by 1/(1-p).  dropout_colonly = 1 drops whole feature columns (row ignored): test mode that pins the
    * placement of every mask against the unmodified reference.  FB_FLAVOUR_PLUS only. */
   float dropout_p; uint32_t dropout_seed; int32_t dropout_colonly;
+  /* ABI 4: attention core of the RowAttentionBlocks in bf16 mode: 0 = SIMT kernel (layers.cu::row_attention_kernel, the faster one at
+   * PDBbind block sizes: 22 / 20 us per launch at B = 16), 1 = tcgen05 kernel (xatt_tc.cu: TMA-fed Q / K tiles, S and O in TMEM; 37 / 62 us,
+   * profiles/r2e_xatt_*) whenever the per-complex key lists fit its tiles (<= 256 keys) */
+  int32_t attn_tc;
   /* ABI 4: dropout is also served for FB_FLAVOUR_V1 -- the training-mode forward of the reference (models/egnn.py:82,106,236,
    * 398,461; models/cross_att.py:128), same sites / hash as the FABind+ stack where the layouts share them. */
 } fb_model_params;

@@ -136,6 +136,24 @@ def test_golden_fp32_tc(path):
     assert rec["x_err"] < 1e-4 and rec["h_err"] < 1e-4, rec
 
 
+def test_tcgen05_attention_in_the_stack():
+    """bf16 mode with the tcgen05 attention core (module.attention = "tcgen05") against bf16 mode with the SIMT core: same inputs to
+    the attention (bf16 projections vs fp32 projections of bf16 operands), so the two forwards agree to bf16 rounding of Q / K / V / P"""
+    hidden, L, IT = 512, 2, 2
+    b = make_batch(embed=hidden, n_complexes=4, seed=9, n_c_range=(10, 50), n_p_range=(80, 200))
+    m0 = EfficientMCAttModel(ref_shims.published_args(), hidden, hidden, 1, n_layers=L, n_iter=IT,
+                             normalize_coord=lambda x: x / 5.0, unnormalize_coord=lambda x: x * 5.0)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in m0.state_dict().items()}, 31)
+    m = _model(hidden, L, IT, sd, precision="bf16")
+    Xs, Hs = _run(m, b)
+    m.attention = "tcgen05"
+    Xt, Ht = _run(m, b)
+    rec = dict(x_err=rel_err(Xt, Xs), h_err=rel_err(Ht, Hs))
+    _log("tcgen05_attention", rec)
+    assert rec["x_err"] < 2e-2 and rec["h_err"] < 2e-2, rec
+    assert rec["h_err"] > 0.0          # the other kernel did run
+
+
 def test_bf16_mode_deviation():
     """bf16 production mode: same path with bf16 GEMM operands.  The reference has no bf16 mode; this bound
     is the build's own: coordinates within 0.15 normalised units (0.75 A) of the fp32 oracle after 8 iterations x 4
