@@ -34,7 +34,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;   // 320
 constexpr int SLOT = 4096;                      // one staging box: 32 rows x 128 bytes
 constexpr int NS = 2;
-constexpr int STAGES = 5;
+constexpr int STAGES = 4;
+constexpr int VEC = BN / 2;                     // columns per epilogue warp: its bias / row-dot vectors live in shared memory
 
 struct Params {
   int M, N, KB1, KB2;
@@ -51,7 +52,8 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                       // 32 KB
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = STAGING_OFF + EPI_WARPS * NS * SLOT;         // full[S] empty[S] tfull[2] tempty[2] slot
+  static constexpr int VEC_OFF = STAGING_OFF + EPI_WARPS * NS * SLOT;         // per epilogue warp: bias[VEC] | dotv[VEC] (fp32)
+  static constexpr int BAR_OFF = VEC_OFF + EPI_WARPS * 2 * VEC * 4;           // full[S] empty[S] tfull[2] tempty[2] slot
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;    // + alignment slack
 };
 
@@ -106,8 +108,17 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t sw_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+// four consecutive floats of a read-only vector (16-byte load when the address allows it)
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  if (((uintptr_t)p & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+  return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
 
-template <bool SPLIT>   // split-precision instantiation: table-driven k-block walk + full-precision SiLU (see gemm_tc3.cu)
+// SPLIT: split-precision instantiation (table-driven k-block walk + full-precision SiLU, see gemm_tc3.cu); ACT: activation of the
+// epilogue as a template parameter, so that one instantiation carries one straight-line epilogue (the runtime select between three
+// unrolled variants tripled the code the eight epilogue warps walk through: 18 % of their stall samples were instruction fetches,
+// profiles/r2f_tc4_epilogue_before.txt)
+template <bool SPLIT, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
@@ -213,13 +224,21 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __syncwarp();
   } else {
     // ===== epilogue (both CTAs, own 128 TMEM lanes) =====
+    // thread = accumulator row, 32 columns per tcgen05.ld.  The per-column vectors (bias, row-dot weights) of this warp's 128 columns
+    // sit in its own slice of shared memory and are read as warp-uniform 16-byte loads (one LDS.128 per four columns) -- the
+    // lane-owns-a-column + shuffle form cost one SHFL per element and vector, a third of the epilogue's instructions.
+    // bf16 SiLU: x silu = h + h tanh(h), h = (acc + b) / 2 = fma(acc, 0.5, b / 2): the stored vector is b / 2.
     const int e = warp - 2;                 // 0..7
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = e >> 2;                // column half of the tile
     constexpr int COLS = BN / 2;            // columns per warp
     constexpr int NCH = COLS / 32;          // 32-column pieces per warp and tile
     uint8_t* const slots = smem + S::STAGING_OFF + e * NS * SLOT;
-    int lt = 0;
+    float* const vb = reinterpret_cast<float*>(smem + S::VEC_OFF) + e * 2 * VEC;
+    float* const vd = vb + VEC;
+    const bool use_dot = p.dotv != nullptr;
+    constexpr bool HALF_BIAS = ACT == FB_ACT_SILU && !SPLIT;
+    int lt = 0, vec_n0 = -1;
     for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
       const int a = lt & 1;
       const int m0 = (tile / n_tiles_n) * PM + (int)rank * BM;
@@ -227,18 +246,20 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int lrow0 = m0 + q * 32;
       const bool rows_live = lrow0 < M;
       const int colbase = n0 + half * COLS;
-      const bool use_dot = p.dotv != nullptr;
-      float bv[NCH], dv[NCH];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        bv[ch] = p.bias ? __ldg(p.bias + colbase + ch * 32 + lane) : 0.f;
-        dv[ch] = use_dot ? __ldg(p.dotv + colbase + ch * 32 + lane) : 0.f;
+      if (n0 != vec_n0) {                   // (warp-uniform) the vectors of this column range
+        vec_n0 = n0;
+        __syncwarp();
+        float4 b4 = p.bias ? ldg4(p.bias + colbase + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (HALF_BIAS) { b4.x *= 0.5f; b4.y *= 0.5f; b4.z *= 0.5f; b4.w *= 0.5f; }
+        reinterpret_cast<float4*>(vb)[lane] = b4;
+        if (use_dot) reinterpret_cast<float4*>(vd)[lane] = ldg4(p.dotv + colbase + 4 * lane);
+        __syncwarp();
       }
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
       mbar_wait(&tfull[a], (lt >> 1) & 1);
       tcgen05_fence_after();
-      float dsum = 0.f;
+      float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
       // TMEM loads are software-pipelined: the load of chunk ch+1 is in flight while chunk ch is processed
       uint32_t vv[2][32];
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + half * COLS);
@@ -257,20 +278,40 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         if (!rows_live) continue;
         float o[32];
+        const float4* const b4p = reinterpret_cast<const float4*>(vb + ch * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bv[ch], j);
-          if (p.act == FB_ACT_SILU) x = SPLIT ? silu(x) : silu_fast(x);
-          else if (p.act == FB_ACT_RELU) x = fmaxf(x, 0.0f);
-          o[j] = x;
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = b4p[j];
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float acc = __uint_as_float(v[4 * j + t]);
+            float x;
+            if (HALF_BIAS) {
+              const float h = fmaf(acc, 0.5f, bb[t]);
+              float th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+              x = fmaf(h, th, h);
+            } else {
+              x = acc + bb[t];
+              if (ACT == FB_ACT_SILU) x = silu(x);
+              else if (ACT == FB_ACT_RELU) x = fmaxf(x, 0.0f);
+            }
+            o[4 * j + t] = x;
+          }
         }
         if (p.drop.p > 0.f) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = drop_apply(o[j], p.drop, lrow0 + lane, n0 + c + j);
         }
         if (use_dot) {
+          const float4* const d4p = reinterpret_cast<const float4*>(vd + ch * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dsum = fmaf(__shfl_sync(0xffffffffu, dv[ch], j), o[j], dsum);
+          for (int j = 0; j < 8; ++j) {
+            const float4 d4 = d4p[j];
+            ds0 = fmaf(d4.x, o[4 * j], ds0); ds1 = fmaf(d4.y, o[4 * j + 1], ds1);
+            ds2 = fmaf(d4.z, o[4 * j + 2], ds2); ds3 = fmaf(d4.w, o[4 * j + 3], ds3);
+          }
         }
         const int ncol0 = n0 + c;
         const bool want_c = p.has_c && !(p.n_split > 0 && ncol0 >= p.n_split);
@@ -307,7 +348,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       if (use_dot && lrow0 + lane < M) {
         // two warps (column halves) share a row: partial index = 2 * n_tile + half
-        p.dot_out[(size_t)((tile % n_tiles_n) * 2 + half) * p.dot_stride + lrow0 + lane] = dsum;
+        p.dot_out[(size_t)((tile % n_tiles_n) * 2 + half) * p.dot_stride + lrow0 + lane] = (ds0 + ds1) + (ds2 + ds3);
       }
     }
     if (lane == 0) bulk_wait_read0();
@@ -324,11 +365,16 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 static int launch(const GemmArgs& g, cudaStream_t st) {
   using S = Smem;
   static_assert(S::TOTAL <= 232448, "shared memory budget");
-  static unsigned long long optin = 0, optin_s = 0;
   static int num_sms = 0;
   const bool split = g.nprod > 0;
-  auto kern = split ? gemm_tc4_kernel<true> : gemm_tc4_kernel<false>;
-  if (!ensure_smem_optin(kern, S::TOTAL, split ? optin_s : optin)) return FB_ERR_CUDA;
+  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Params);
+  static const Kern table[2][3] = {
+      {gemm_tc4_kernel<false, FB_ACT_NONE>, gemm_tc4_kernel<false, FB_ACT_SILU>, gemm_tc4_kernel<false, FB_ACT_RELU>},
+      {gemm_tc4_kernel<true, FB_ACT_NONE>, gemm_tc4_kernel<true, FB_ACT_SILU>, gemm_tc4_kernel<true, FB_ACT_RELU>}};
+  static unsigned long long optins[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  if (g.act < 0 || g.act > 2) return FB_ERR_BAD_ARG;
+  Kern kern = table[split ? 1 : 0][g.act];
+  if (!ensure_smem_optin(kern, S::TOTAL, optins[split ? 1 : 0][g.act])) return FB_ERR_CUDA;
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
