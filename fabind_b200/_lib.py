@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfabind_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "CUDA launch error", -4: "unsupported configuration"}
 
@@ -101,6 +101,8 @@ EXPORTS = {
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "fb_gemm": (C.c_int32, [C.POINTER(GemmParams), C.c_void_p]),
     "fb_gemm_pair": (C.c_int32, [C.POINTER(GemmParams), C.POINTER(GemmParams), C.c_void_p]),
+    "fb_derive_weights": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "fb_gemm_multi": (C.c_int32, [C.POINTER(GemmParams), C.c_int32, C.c_int32, C.c_void_p]),
     "fb_gemm_dot_tiles": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "fb_gemm_set_debug": (C.c_int32, [C.c_void_p]),
     "fb_assemble_rows": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

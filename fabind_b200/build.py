@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfabind_b200.so")
-SOURCES = ["gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "gemm_tc4.cu", "graph.cu", "layers.cu", "plus.cu", "forward.cu", "l2ops.cu", "postopt.cu", "backward.cu", "xatt_tc.cu"]
+SOURCES = ["gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_tc3.cu", "gemm_tc4.cu", "gemm_tc5.cu", "graph.cu", "layers.cu", "plus.cu", "forward.cu", "l2ops.cu", "postopt.cu", "backward.cu", "xatt_tc.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -83,6 +83,8 @@ struct AttW {
   int64_t tp1_w, tp1_b, tp2_w, tp2_b, tc1_w, tc1_b, tc2_w, tc2_b;
   int64_t pt1_w, pt1_b, pt2v, pt_c;
   int64_t qk_w, qk_b, k_r, v_r, ac1_b, ac2_w, ac_u;
+  // derived ("folded") slots, filled by fb_derive_weights from the slots above (names start with f_: the packers skip them)
+  int64_t f_cac_w, f_cac_b, f_cap_w, f_cap_b, f_l3_w, f_l3_b, f_l5_w, f_l5_b, f_qkc_w, f_qkc_b;
 };
 // FABind+ layout (LayerNorm -> Linear -> ReLU -> Linear [-> ReLU] MLPs, P/models/model_utils.py:10-74)
 static inline int dp_of(int H) { return (2 * H + 1 + 63) / 64 * 64; }   // 2H+1 edge-MLP features padded to a multiple of 64
@@ -153,9 +155,49 @@ static void build_weights(int H, int L, ModelW& w) {
     a.v_r = add(p + "v_r", 1, H);
     a.ac1_b = add(p + "ac1_b", 1, H);
     a.ac2_w = add(p + "ac2_w", 1, H); a.ac_u = add(p + "ac_u", 1, H);
+    // folded projections (see Run::run_att_folded): consecutive Linear maps of the cross-attention block collapsed into
+    // pre-multiplied weights over K-concatenated operands, so that dependent launches become independent problems of one launch
+    //   f_cac / f_cap : [W_ca | W_ca W_n2]            the block's first projections from [h | T1] of the preceding MC_E_GCL
+    //   f_l3          : [W_p2 | W_p2 W_op] (2 HD rows), [W_tp1 | W_tp1 W_op] (2H rows)     k/v of the new p, p transition hidden from [h_p | O_p]
+    //   f_l5          : [W_tc1 | W_tc1 W_oc]          c transition hidden from [h_c | O_c]
+    //   f_qkc         : [W_qk | W_qk W_tc2]           stacked q|k|v|vc of the compound rows from [h_c | TH_c]
+    a.f_cac_w = add(p + "f_cac_w", 4 * HD, 2 * H); a.f_cac_b = add(p + "f_cac_b", 1, 4 * HD);
+    a.f_cap_w = add(p + "f_cap_w", 2 * HD, 2 * H); a.f_cap_b = add(p + "f_cap_b", 1, 2 * HD);
+    a.f_l3_w = add(p + "f_l3_w", 2 * HD + 2 * H, H + HD); a.f_l3_b = add(p + "f_l3_b", 1, 2 * HD + 2 * H);
+    a.f_l5_w = add(p + "f_l5_w", 2 * H, H + HD); a.f_l5_b = add(p + "f_l5_b", 1, 2 * H);
+    a.f_qkc_w = add(p + "f_qkc_w", 4 * H + QKX, 3 * H); a.f_qkc_b = add(p + "f_qkc_b", 1, 4 * H + QKX);
     w.att.push_back(a);
   }
   w.total = off;
+}
+
+// out[r, 0:K) = Wa[r, :],  out[r, K + j) = sum_k Wa[r, k] Wb[k, j],  ob[r] = ba[r] + sum_k Wa[r, k] bb[k]   (fp64 accumulation,
+// rounded once: the same arithmetic as the packer's float64 derivations).  Runs when the weights change, not per forward.
+__global__ void __launch_bounds__(256) fold_weights_kernel(const float* __restrict__ Wa, const float* __restrict__ ba, int R, int K,
+                                                           const float* __restrict__ Wb, const float* __restrict__ bb, int J,
+                                                           float* __restrict__ out, float* __restrict__ ob) {
+  const int j = blockIdx.x * 32 + threadIdx.x;          // 0 .. K + J (copy columns first), one extra column for the bias
+  const int r = blockIdx.y * 8 + threadIdx.y;
+  if (r >= R) return;
+  const int ldo = K + J;
+  if (j < K) { out[(size_t)r * ldo + j] = Wa[(size_t)r * K + j]; return; }
+  const int jj = j - K;
+  if (jj > J) return;
+  double acc = 0.0;
+  if (jj < J) {
+    for (int k = 0; k < K; ++k) acc += (double)Wa[(size_t)r * K + k] * (double)Wb[(size_t)k * J + jj];
+    out[(size_t)r * ldo + j] = (float)acc;
+  } else {
+    for (int k = 0; k < K; ++k) acc += (double)Wa[(size_t)r * K + k] * (double)bb[k];
+    ob[r] = (float)(acc + (ba ? (double)ba[r] : 0.0));
+  }
+}
+
+static int fold_weights(float* w, int64_t wa, int64_t ba, int R, int K, int64_t wb, int64_t bb, int J, int64_t out, int64_t ob,
+                        cudaStream_t st) {
+  const dim3 grid((K + J + 1 + 31) / 32, (R + 7) / 8), block(32, 8);
+  fold_weights_kernel<<<grid, block, 0, st>>>(w + wa, ba >= 0 ? w + ba : nullptr, R, K, w + wb, w + bb, J, w + out, w + ob);
+  return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_CUDA;
 }
 
 static void build_weights_plus(int H, int L, ModelW& w) {
@@ -266,8 +308,8 @@ struct Bufs {
   // coordinates
   float *x_state, *xa, *xb, *xl;
   // node features
-  float *Hin32, *h, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
-  void *HinT, *hT, *agg, *T1, *O, *TH, *VT, *Pn, *VCT;
+  float *Hin32, *h, *h2, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
+  void *HinT, *hT, *hT2, *agg, *T1, *O, *TH, *VT, *Pn, *VCT;
   void *CAcT, *CApT, *CAp2T;   // bf16 projections of the cross-attention block (tcgen05 attention core)
   // pair
   void *P0, *A0, *Zg, *T64; float *PBraw, *PB, *pb_dense, *dotU;
@@ -282,11 +324,11 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   const size_t N = p.N, H = p.hidden, E = p.E_ctx > 0 ? p.E_ctx : 1, P = p.P_total, L = p.n_layers;
   const size_t capI = p.cap_int > 0 ? p.cap_int : 2, capU = capI / 2 + 1;
   const bool bf = p.bf16_mode == FB_PREC_BF16;
+  const bool plus = p.flavour == FB_FLAVOUR_PLUS;
   const int gmode = p.bf16_mode;
   const size_t TS = bf ? 2 : 4;
   const size_t Nc = p.Nc_tot, Np = N - Nc;
   const size_t tilesH = gemm_dot_tiles((int)E, (int)H, (int)H, gmode), tiles2H = gemm_dot_tiles((int)(capI / 2), (int)(2 * H), (int)H, gmode);
-  const bool plus = p.flavour == FB_FLAVOUR_PLUS;
   const size_t Dp = dp_of((int)H);
   b.ctx_row = a.get<int>(E); b.ctx_col = a.get<int>(E);
   b.int_row = a.get<int>(capI); b.int_col = a.get<int>(capI); b.int_pair = a.get<int>(capI);
@@ -295,6 +337,10 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   b.HinT = bf ? a.take(N * H * TS) : (void*)b.Hin32;
   b.h = a.get<float>(N * H);
   b.hT = bf ? a.take(N * H * TS) : (void*)b.h;
+  // second residual stream: the folded sequences write the new h next to the old one, which other problems of the same launch
+  // still read as their A operand (Run::run_att_folded)
+  b.h2 = b.h; b.hT2 = b.hT;
+  if (!plus) { b.h2 = a.get<float>(N * H); b.hT2 = bf ? a.take(N * H * TS) : (void*)b.h2; }
   b.Hfin = a.get<float>(N * H);
   b.pc = a.get<float>(N * H);
   b.P0 = a.take(P * H * TS);
@@ -416,6 +462,28 @@ struct Run {
     prof_end(st);
   }
 
+  // independent problems of one stage (folded sequences): one multi-problem tcgen05 launch in bf16 mode, else one after the other
+  void gemm_multi(const GemmArgs* g, int n) {
+    if (skip_mask() >> gemm_cat & 1) return;
+    prof_begin(gemm_cat, st);
+    for (int i = 0; i < n; ++i) prof_flops(gemm_cat, g[i]);
+    chk(gemm_launch_multi(g, n, gmode, /*prefetch_w=*/true, st));
+    prof_end(st);
+  }
+
+  // Folded sequences (v1 layout, no dropout, SIMT attention core): node_mlp.2 -> first projections of the cross-attention block,
+  // linear_o -> k/v of the other side -> transition.linear_1, transition.linear_2 -> q|k|v of the interfacial attention are exact
+  // compositions of Linear maps; with the pre-multiplied weights of fb_derive_weights the ten dependent node-level GEMM launches of
+  // a layer become six (run_gcl + run_att_folded).  Off: the launch sequence of round 1 (every Linear its own launch).
+  bool fold_on() const {
+#ifdef FB_DIAG
+    static const bool on = [] { const char* e = getenv("FB_FOLD"); return !(e && atoi(e) == 0); }();
+    if (!on) return false;
+#endif
+    return w.flavour == 0 && p.dropout_p <= 0.f && !xa_on() && p.n_layers > 0;
+  }
+  bool ca_ready = false;   // the block's first projections (CAc, CAp) were produced by the preceding run_gcl
+
   // the attention core of both RowAttentionBlocks runs on tcgen05 (xatt_tc.cu) in bf16 mode when asked for (fb_model_params.attn_tc)
   // and the per-complex blocks fit its tiles (keys <= 256 per complex); otherwise (and in the fp32 / split-precision parity modes)
   // on the SIMT kernel, which is the faster of the two at these block sizes (measured: DESIGN.md section 5)
@@ -441,7 +509,7 @@ struct Run {
                    : mk(A, H, H, w_off, Nout, b_off, FB_ACT_NONE, M, C32, Nout, nullptr, 0);
   }
 
-  void run_gcl(const GclW& gw, const float* x_in, float* x_out, bool need_h) {
+  void run_gcl(const GclW& gw, const float* x_in, float* x_out, bool need_h, const AttW* fold_att = nullptr) {
     const int E = p.E_ctx;
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
     gemm_cat = CAT_GEMM_NODE;
@@ -460,7 +528,67 @@ struct Run {
     gemm_cat = CAT_GEMM_NODE;
     if (need_h) {
       gemm(b.hT, H, H, gw.n1_w, H, gw.n1_b, FB_ACT_SILU, N, nullptr, 0, b.T1, H, nullptr, 0, b.agg, H, H);
-      gemm(wd(mk(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h, H, b.hT, H, b.h, H), dr(S_NODE2)));
+      if (fold_att && fold_on()) {
+        // node_mlp.2 + residual into the SECOND residual stream, and the cross-attention block's first projections of the new h
+        // from [h | T1] in the same launch:  h' W^T = h W^T + T1 (W W_n2)^T + W b_n2
+        const AttW& aw = *fold_att;
+        const size_t op = (size_t)Nc * H;
+        const GemmArgs g[3] = {
+            mk(b.hT, H, H, aw.f_cac_w, 4 * HD, aw.f_cac_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0, nullptr, 0, b.T1, H, H),
+            mk(at(b.hT, op), H, H, aw.f_cap_w, 2 * HD, aw.f_cap_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0, nullptr, 0, at(b.T1, op), H, H),
+            mk(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h2, H, b.hT2, H, b.h, H)};
+        gemm_multi(g, 3);
+        std::swap(b.h, b.h2); std::swap(b.hT, b.hT2);
+        ca_ready = true;
+      } else {
+        gemm(wd(mk(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h, H, b.hT, H, b.h, H), dr(S_NODE2)));
+      }
+    }
+  }
+
+  // cross-attention block + stacked q|k|v projections of run_att as THREE multi-problem launches (see fold_on).  Two residual
+  // streams: "o" = (b.h, b.hT), current on entry and on exit, "a" = (b.h2, b.hT2); a problem never writes rows of a stream that another
+  // problem of the same launch reads as its A operand:
+  //   L3 (after attention(p)):  TH_p  = relu([h_p|O_p] f_l3[2HD:]^T)        CAp2 = [h_p|O_p] f_l3[:2HD]^T        h_p: o -> a (linear_o + residual)
+  //   L5 (after attention(c)):  h_p: a -> o (p transition linear_2 + residual)     TH_c = relu([h_c|O_c] f_l5^T)     h_c: o -> a
+  //   L6:                       q|k|v(c) = [h_c(a)|TH_c] f_qkc^T        h_c: a -> o (c transition linear_2 + residual)        q|k|v(p) = h_p(o) qk^T
+  void run_att_folded(const AttW& aw, int layer) {
+    const size_t P = p.P_total;
+    const size_t op = (size_t)Nc * H;
+    float *h_o = b.h, *h_a = b.h2;
+    void *hT_o = b.hT, *hT_a = b.hT2;
+    void* Op = at(b.O, (size_t)Nc * HD);
+    void* THp = at(b.TH, (size_t)Nc * 2 * H);
+    gemm_cat = CAT_GEMM_NODE;
+    if (!ca_ready)
+      gemm_pair(proj(hT_o, aw.ca_c_w, 4 * HD, aw.ca_c_b, Nc, b.CAc, b.CAcT), proj(at(hT_o, op), aw.ca_p_w, 2 * HD, aw.ca_p_b, Np, b.CAp, b.CApT));
+    ca_ready = false;
+    stage(CAT_ATTENTION, [&] { return att_p(b.PB + (size_t)(layer * 2 + 0) * P * 4); });
+    {
+      const GemmArgs g[3] = {
+          mk(at(hT_o, op), H, H, aw.f_l3_w + (int64_t)2 * HD * (H + HD), 2 * H, aw.f_l3_b + 2 * HD, FB_ACT_RELU, Np, nullptr, 0, THp, 2 * H,
+             nullptr, 0, Op, HD, HD),
+          mk(at(hT_o, op), H, H, aw.f_l3_w, 2 * HD, aw.f_l3_b, FB_ACT_NONE, Np, b.CAp2, 2 * HD, nullptr, 0, nullptr, 0, Op, HD, HD),
+          mk(Op, HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, h_a + op, H, at(hT_a, op), H, h_o + op, H)};
+      gemm_multi(g, 3);
+    }
+    stage(CAT_ATTENTION, [&] { return att_c(b.PB + (size_t)(layer * 2 + 1) * P * 4); });
+    {
+      const GemmArgs g[3] = {
+          mk(THp, 2 * H, 2 * H, aw.tp2_w, H, aw.tp2_b, FB_ACT_NONE, Np, h_o + op, H, at(hT_o, op), H, h_a + op, H),
+          mk(hT_o, H, H, aw.f_l5_w, 2 * H, aw.f_l5_b, FB_ACT_RELU, Nc, nullptr, 0, b.TH, 2 * H, nullptr, 0, b.O, HD, HD),
+          mk(b.O, HD, HD, aw.o_c_w, H, aw.o_c_b, FB_ACT_NONE, Nc, h_a, H, hT_a, H, h_o, H)};
+      gemm_multi(g, 3);
+    }
+    {
+      const int ldqk = 2 * H + QKX;
+      const GemmArgs g[3] = {
+          mk(hT_a, H, H, aw.f_qkc_w, ldqk + 2 * H, aw.f_qkc_b, FB_ACT_NONE, Nc, b.QK, ldqk, b.VT, 2 * H, nullptr, 0, b.TH, 2 * H, 2 * H, -1,
+             nullptr, 0, nullptr, ldqk),
+          mk(b.TH, 2 * H, 2 * H, aw.tc2_w, H, aw.tc2_b, FB_ACT_NONE, Nc, h_o, H, hT_o, H, h_a, H),
+          mk(at(hT_o, op), H, H, aw.qk_w, ldqk + 2 * H, aw.qk_b, FB_ACT_NONE, Np, b.QK + (size_t)Nc * ldqk, ldqk, at(b.VT, (size_t)Nc * 2 * H),
+             2 * H, nullptr, 0, nullptr, 0, 0, -1, nullptr, 0, nullptr, ldqk)};
+      gemm_multi(g, 3);
     }
   }
 
@@ -469,8 +597,14 @@ struct Run {
     float* hp = b.h + (size_t)Nc * H;              // protein-side rows
     void* hTp = at(b.hT, (size_t)Nc * H);
     gemm_cat = CAT_GEMM_NODE;
+    const int ldqk = 2 * H + QKX;
+    if (fold_on()) {
+      run_att_folded(aw, layer);
+    } else {
     // --- cross attention (cross_att.py:24-54) on the per-complex blocks
-    gemm_pair(proj(b.hT, aw.ca_c_w, 4 * HD, aw.ca_c_b, Nc, b.CAc, b.CAcT), proj(hTp, aw.ca_p_w, 2 * HD, aw.ca_p_b, Np, b.CAp, b.CApT));
+    if (!ca_ready)
+      gemm_pair(proj(b.hT, aw.ca_c_w, 4 * HD, aw.ca_c_b, Nc, b.CAc, b.CAcT), proj(hTp, aw.ca_p_w, 2 * HD, aw.ca_p_b, Np, b.CAp, b.CApT));
+    ca_ready = false;
     stage(CAT_ATTENTION, [&] { return att_p(b.PB + (size_t)(layer * 2 + 0) * P * 4); });
     // RowAttentionBlock dropout on the attention output (cross_att.py:128), row index = internal node id
     gemm(wd(mk(at(b.O, (size_t)Nc * HD), HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H), dr(S_PATT, Nc)));
@@ -485,9 +619,9 @@ struct Run {
               mk(THp, 2 * H, 2 * H, aw.tp2_w, H, aw.tp2_b, FB_ACT_NONE, Np, hp, H, hTp, H, hp, H));
     // q | k of the interfacial attention stacked with the 32-channel interaction projections
     // (cross_att.py:22,51: linear_p on protein rows, linear_c on compound rows) in ONE node GEMM
-    const int ldqk = 2 * H + QKX;
     gemm(b.hT, H, H, aw.qk_w, ldqk + 2 * H, aw.qk_b, FB_ACT_NONE, N, b.QK, ldqk, b.VT, 2 * H, nullptr, 0, nullptr, 0, 0, -1,
          nullptr, 0, nullptr, ldqk);
+    }
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
@@ -634,7 +768,8 @@ struct Run {
     for (int l = 0; l < p.n_layers; ++l) {
       cur_layer = l;
       if (e.steps & FB_STEP_GCL) {
-        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true); else run_gcl(w.gcl[l], xc, bufs[k], true);
+        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true);
+        else run_gcl(w.gcl[l], xc, bufs[k], true, (e.steps & FB_STEP_ATT) ? &w.att[l] : nullptr);
         xc = bufs[k]; k ^= 1;
       }
       if (e.steps & FB_STEP_ATT) {
@@ -699,7 +834,7 @@ struct Run {
       const void* pair_cur = b.P0;   // FABind+: every iteration restarts from pair_embed0 (P/models/att_model.py:209-218)
       for (int l = 0; l < p.n_layers; ++l) {
         cur_layer = l;
-        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true); else run_gcl(w.gcl[l], xc, bufs[k], true);
+        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true); else run_gcl(w.gcl[l], xc, bufs[k], true, &w.att[l]);
         xc = bufs[k]; k ^= 1;
         if (last) tap(2 * l, xc);
         if (plus) {
@@ -811,6 +946,26 @@ int32_t fb_weight_slot_info_f(int32_t hidden, int32_t n_layers, int32_t flavour,
 }
 
 int64_t fb_weight_arena_elems_f(int32_t hidden, int32_t n_layers, int32_t flavour) { return weights_for(hidden, n_layers, flavour).total; }
+
+int32_t fb_derive_weights(float* w32, int32_t hidden, int32_t n_layers, int32_t flavour, void* stream) {
+  if (!w32 || hidden <= 0 || n_layers < 0 || (flavour != FB_FLAVOUR_V1 && flavour != FB_FLAVOUR_PLUS)) return FB_ERR_BAD_ARG;
+  if (flavour != FB_FLAVOUR_V1) return FB_OK;           // the FABind+ sequences are not folded
+  const ModelW& w = weights_for(hidden, n_layers, flavour);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = hidden;
+  for (int l = 0; l < n_layers; ++l) {
+    const AttW& a = w.att[l];
+    const GclW& g = w.gcl[l];
+    int r = fold_weights(w32, a.ca_c_w, a.ca_c_b, 4 * HD, H, g.n2_w, g.n2_b, H, a.f_cac_w, a.f_cac_b, st);
+    if (r == FB_OK) r = fold_weights(w32, a.ca_p_w, a.ca_p_b, 2 * HD, H, g.n2_w, g.n2_b, H, a.f_cap_w, a.f_cap_b, st);
+    if (r == FB_OK) r = fold_weights(w32, a.ca_p2_w, -1, 2 * HD, H, a.o_p_w, a.o_p_b, HD, a.f_l3_w, a.f_l3_b, st);
+    if (r == FB_OK) r = fold_weights(w32, a.tp1_w, a.tp1_b, 2 * H, H, a.o_p_w, a.o_p_b, HD, a.f_l3_w + (int64_t)2 * HD * (H + HD), a.f_l3_b + 2 * HD, st);
+    if (r == FB_OK) r = fold_weights(w32, a.tc1_w, a.tc1_b, 2 * H, H, a.o_c_w, a.o_c_b, HD, a.f_l5_w, a.f_l5_b, st);
+    if (r == FB_OK) r = fold_weights(w32, a.qk_w, a.qk_b, 4 * H + QKX, H, a.tc2_w, a.tc2_b, 2 * H, a.f_qkc_w, a.f_qkc_b, st);
+    if (r != FB_OK) return r;
+  }
+  return FB_OK;
+}
 
 int64_t fb_graph_workspace_bytes(const fb_model_params* p) {
   if (!params_ok(p)) return FB_ERR_BAD_ARG;
@@ -944,6 +1099,16 @@ int32_t fb_gemm(const fb_gemm_params* q, void* stream) {
 int32_t fb_gemm_pair(const fb_gemm_params* q0, const fb_gemm_params* q1, void* stream) {
   if (!q0 || !q1 || q0->bf16_mode != q1->bf16_mode || !prec_ok(q0->bf16_mode)) return FB_ERR_BAD_ARG;
   return gemm_launch_pair(gemm_args_from(q0), gemm_args_from(q1), q0->bf16_mode, (cudaStream_t)stream);
+}
+
+int32_t fb_gemm_multi(const fb_gemm_params* q, int32_t n, int32_t prefetch_w, void* stream) {
+  if (!q || n < 1 || n > 4) return FB_ERR_BAD_ARG;
+  GemmArgs a[4];
+  for (int i = 0; i < n; ++i) {
+    if (q[i].bf16_mode != q[0].bf16_mode || !prec_ok(q[i].bf16_mode) || q[i].force_simt) return FB_ERR_BAD_ARG;
+    a[i] = gemm_args_from(&q[i]);
+  }
+  return gemm_launch_multi(a, n, q[0].bf16_mode, prefetch_w != 0, (cudaStream_t)stream);
 }
 
 int32_t fb_gemm_set_debug(int64_t* dbg) {

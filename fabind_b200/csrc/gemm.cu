@@ -16,6 +16,7 @@ int gemm_tc2_launch_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t st
 int gemm_tc3_launch(const GemmArgs& g, cudaStream_t st);
 int gemm_tc4_launch(const GemmArgs& g, cudaStream_t st);
 int gemm_tc3_launch_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t st);
+int gemm_tc5_launch(const GemmArgs* g, int np, bool prefetch_w, cudaStream_t st);
 
 static int tc_version() {
 #ifdef FB_DIAG
@@ -148,6 +149,36 @@ int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, int mode, cudaStrea
   }
   const int r = gemm_launch(g0, mode, st);
   return r != FB_OK ? r : gemm_launch(g1, mode, st);
+}
+
+int gemm_launch_multi(const GemmArgs* g, int np, int mode, bool prefetch_w, cudaStream_t st) {
+  if (np <= 0) return FB_OK;
+#ifdef FB_DIAG
+  static const bool multi = [] { const char* e = getenv("FB_NO_MULTI"); return !(e && atoi(e)); }();
+#else
+  const bool multi = true;
+#endif
+  if (multi && mode == GEMM_BF16) {
+    // problems without rows drop out of the group
+    GemmArgs live[4];
+    int n = 0;
+    bool fits = true;
+    for (int i = 0; i < np; ++i) {
+      if (g[i].M <= 0) continue;
+      if (n == 4) { fits = false; break; }
+      live[n++] = g[i];
+    }
+    if (fits && n > 0) {
+      const int r = gemm_tc5_launch(live, n, prefetch_w, st);
+      if (r != FB_ERR_UNSUPPORTED) return r;
+    }
+    if (fits && n == 0) return FB_OK;
+  }
+  for (int i = 0; i < np; ++i) {
+    const int r = gemm_launch(g[i], mode, st);
+    if (r != FB_OK) return r;
+  }
+  return FB_OK;
 }
 
 }  // namespace fb

@@ -45,6 +45,11 @@ int gemm_launch(const GemmArgs& g, int mode, cudaStream_t st);
 // one grouped launch when the tcgen05 path can take it, otherwise two launches
 int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, int mode, cudaStream_t st);
 
+// up to four INDEPENDENT problems (no problem reads what another one writes) as one multi-problem tcgen05 launch (gemm_tc5.cu) when
+// the mode is bf16 and every problem qualifies, otherwise one after the other in the given order.  prefetch_w: the weights were NOT
+// written by the kernels immediately before this launch in the stream (their first slabs are requested before griddepcontrol.wait)
+int gemm_launch_multi(const GemmArgs* g, int np, int mode, bool prefetch_w, cudaStream_t st);
+
 // fp32 rows -> three bf16 planes: dst[m, p * K + k] (p = 0..2), K = K1 + K2 ([A | A2] concatenated); K1, K2 multiples of 8
 int split_rows(const float* A, int lda, int K1, const float* A2, int lda2, int K2, int M, void* dst, cudaStream_t st);
 

@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 
 #include "gemm.h"
 #include "tc_common.cuh"
@@ -219,17 +220,49 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded descriptors are cached: the operand / output buffers of a forward are the same every layer and iteration, and the driver
+// call costs ~1 us of host time per descriptor (up to 24 per multi-problem launch).  Key = everything the descriptor depends on.
+struct MapKey {
+  const void* ptr; uint64_t rows, cols, ld; uint32_t kind;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && kind == o.kind; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full; h ^= h >> 29;
+    h ^= (k.cols * 0x165667B19E3779F9ull) ^ (k.ld << 17) ^ ((uint64_t)k.kind << 51);
+    return (size_t)(h ^ (h >> 32));
+  }
+};
+template <typename F>
+static bool cached_map(CUtensorMap* m, const MapKey& key, F encode) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *m = it->second; return true; }
+  }
+  if (!encode(m)) return false;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *m);
+  return true;
+}
+
 // 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = box_rows x 64 columns, 128B swizzle
 static bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
-  const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {ld * 2};
-  const cuuint32_t box[2] = {BK, box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return cached_map(m, MapKey{ptr, rows, cols, ld, box_rows}, [&](CUtensorMap* out) {
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint32_t box[2] = {BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  });
 }
 
 constexpr int BN_SEL = 128, STAGES_SEL = 3;
@@ -244,13 +277,15 @@ bool tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
 bool tc_make_map_out(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t rows, uint64_t cols, uint64_t ld) {
   tc::EncodeTiledFn fn = tc::encode_fn();
   if (!fn) return false;
-  const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {ld * (is_f32 ? 4u : 2u)};
-  const cuuint32_t box[2] = {is_f32 ? 32u : 64u, 32u};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
-            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return tc::cached_map(m, tc::MapKey{ptr, rows, cols, ld, is_f32 ? 0x80000001u : 0x80000002u}, [&](CUtensorMap* out) {
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * (is_f32 ? 4u : 2u)};
+    const cuuint32_t box[2] = {is_f32 ? 32u : 64u, 32u};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  });
 }
 
 bool gemm_tc_shape_ok(int N, int K) { return N >= tc::BN_SEL && (N % tc::BN_SEL) == 0 && K >= 64 && (K % 64) == 0; }

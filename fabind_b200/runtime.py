@@ -5,7 +5,7 @@ import torch
 
 from . import _lib
 from .layout import build_layout
-from .weights import pack_state_dict
+from .weights import pack_state_dict, derive_on_device
 
 _scratch = {}
 
@@ -39,7 +39,7 @@ def split_arena(w32, hidden, n_layers, flavour):
     l = _lib.lib()
     out = torch.zeros(3 * w32.numel(), dtype=torch.bfloat16, device=w32.device)
     st = current_stream_ptr(w32.device)
-    for name, r, c, off in slots(hidden, n_layers, flavour):
+    for name, r, c, off in slots(hidden, n_layers, flavour, derived=True):
         if r <= 1 or r * c == 0 or c % 8:
             continue
         _lib.check(l.fb_split_rows(w32.data_ptr() + 4 * off, c, r, c, out.data_ptr() + 2 * 3 * off, st), "fb_split_rows")
@@ -79,7 +79,7 @@ class PackedWeights:
             key = key + (float(torch.stack(torch._foreach_norm([p.detach() for p in params])).double().square().sum()),)
         if key != self.key:
             arena = pack_state_dict(module.state_dict(), hidden, n_layers, flavour)
-            self.w32 = arena.to(device)
+            self.w32 = derive_on_device(arena.to(device), hidden, n_layers, flavour)
             self.w16 = {}
             self.key = key
         w16 = None

@@ -9,7 +9,7 @@ import torch
 from . import _lib
 from .layout import build_layout
 from .runtime import _scratch_buf, current_stream_ptr
-from .weights import pack_state_dict
+from .weights import pack_state_dict, derive_on_device
 
 _templates = {}
 
@@ -40,7 +40,7 @@ def packed_arena(module, args, hidden, n_layers, prefix, device, flavour=0):
             for k in sd:
                 if k.endswith("layernorm.weight") and not k.startswith(prefix):
                     sd[k] = torch.ones_like(sd[k])
-        w32 = pack_state_dict(sd, hidden, n_layers, flavour).to(device)
+        w32 = derive_on_device(pack_state_dict(sd, hidden, n_layers, flavour).to(device), hidden, n_layers, flavour)
         cache = (key, w32, None)
         module._fb_arena = cache
     return cache

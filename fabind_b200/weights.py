@@ -22,7 +22,10 @@ HD = 128
 QKX = 128   # extra columns of the stacked q|k GEMM (csrc/forward.cu)
 
 
-def slots(hidden, n_layers, flavour=0):
+def slots(hidden, n_layers, flavour=0, derived=False):
+    """(name, rows, cols, offset) of the arena slots.  derived=False leaves out the library's own "f_*" slots (pre-multiplied
+    projections filled on the device by fb_derive_weights, see `derive_on_device`): packers, their chain rules and the training path
+    neither write nor read them."""
     l = _lib.lib()
     out = []
     name = C.create_string_buffer(64)
@@ -30,8 +33,21 @@ def slots(hidden, n_layers, flavour=0):
     for i in range(l.fb_weight_slot_count_f(hidden, n_layers, flavour)):
         _lib.check(l.fb_weight_slot_info_f(hidden, n_layers, flavour, i, name, 64, C.byref(r), C.byref(c), C.byref(o)),
                    "fb_weight_slot_info_f")
-        out.append((name.value.decode(), r.value, c.value, o.value))
+        nm = name.value.decode()
+        if not derived and nm.rpartition(".")[2].startswith("f_"):
+            continue
+        out.append((nm, r.value, c.value, o.value))
     return out
+
+
+def derive_on_device(w32, hidden, n_layers, flavour=0):
+    """fill the derived ("f_*") slots of a device-resident fp32 arena in place (fb_derive_weights, on the current stream)"""
+    if w32.device.type != "cuda" or w32.dtype != torch.float32 or not w32.is_contiguous():
+        raise ValueError("derive_on_device: a contiguous float32 CUDA arena is required")
+    st = C.c_void_p(torch.cuda.current_stream(w32.device).cuda_stream)
+    with torch.cuda.device(w32.device):
+        _lib.check(_lib.lib().fb_derive_weights(w32.data_ptr(), hidden, n_layers, flavour, st), "fb_derive_weights")
+    return w32
 
 
 def _gcl(sd, p, H):

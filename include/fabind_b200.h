@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 4
+#define FB_ABI_VERSION 5
 
 /* One batch of complexes + model dimensions.  Node layout in caller order is the reference
  * dataloader's [glb_c | atoms | glb_p | residues] per complex (utils/utils.py:328-335). */
@@ -129,6 +129,14 @@ int32_t fb_weight_slot_count_f(int32_t hidden, int32_t n_layers, int32_t flavour
 int32_t fb_weight_slot_info_f(int32_t hidden, int32_t n_layers, int32_t flavour, int32_t i, char* name, int32_t name_cap,
                               int64_t* rows, int64_t* cols, int64_t* offset);
 int64_t fb_weight_arena_elems_f(int32_t hidden, int32_t n_layers, int32_t flavour);
+/* ABI 5: DERIVED slots (names "att<l>.f_*").  Consecutive Linear maps of the cross-attention block (models/cross_att.py:24-54:
+ * linear_o -> linear_k/linear_v of the other side -> transition.linear_1; node_mlp.2 of the preceding MC_E_GCL -> the block's first
+ * projections; transition.linear_2 -> linear_q / linear_kv) are exact compositions W_b(W_a x + b_a) + b_b = (W_b W_a) x + (W_b b_a +
+ * b_b); the library keeps the pre-multiplied matrices in the arena so that those dependent launches become independent problems of
+ * one launch (fb_gemm_multi).  fb_derive_weights fills them from the base slots of the fp32 arena `w32` (device memory, on `stream`,
+ * fp64 accumulation); call it after every (re)pack and BEFORE converting the arena to its bf16 / split copies.  A packer leaves
+ * these slots untouched (fabind_b200/weights.py lists them only on request).  FB_FLAVOUR_PLUS has none (no-op). */
+int32_t fb_derive_weights(float* w32, int32_t hidden, int32_t n_layers, int32_t flavour, void* stream);
 
 /* [host] scratch sizes */
 int64_t fb_graph_workspace_bytes(const fb_model_params* p);
@@ -216,6 +224,12 @@ int32_t fb_gemm(const fb_gemm_params* g, void* stream);
  * one grouped tcgen05 launch when both qualify, otherwise the two launches in order.  This is how the stack runs
  * the compound-side / protein-side linears of a stage (cross_att.py:24-54, model_utils.py:171-175). */
 int32_t fb_gemm_pair(const fb_gemm_params* g0, const fb_gemm_params* g1, void* stream);
+/* ABI 5: n (1..4) INDEPENDENT layers (no problem reads what another one writes; same precision mode) -- one multi-problem tcgen05
+ * launch when the mode is bf16 and every problem tiles (N % 128 == 0, no row-dot / dropout / device-side row count), otherwise the n
+ * launches in order.  prefetch_w != 0: the caller guarantees that the weights were not written by the kernels immediately before
+ * this launch in the stream (their first slabs are requested before the dependency wait).  This is how the stack runs the folded
+ * per-side projection groups of a layer (cross_att.py:24-54 with o_p -> k/v -> transition collapsed into pre-multiplied weights). */
+int32_t fb_gemm_multi(const fb_gemm_params* g, int32_t n, int32_t prefetch_w, void* stream);
 int32_t fb_gemm_dot_tiles(int32_t M, int32_t N, int32_t K, int32_t bf16_mode, int32_t force_simt);
 /* development probe: when non-null, sampled CTAs of the tcgen05 GEMMs write globaltimer stamps; the buffer must hold at least
  * 8192 int64 (slots up to 2048 + 19 * 16 + 15 are written) */

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_gemm.py -x -q 2>&1 | tail -15 | tee gpurun_out/r2i_gemm_tests.txt
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 | tee gpurun_out/r2i_gpu_tests.txt
+timeout 600 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2i_bench.json 2> gpurun_out/r2i_bench.err; head -c 700 gpurun_out/r2i_bench.json; echo; tail -c 700 gpurun_out/r2i_bench.json; tail -3 gpurun_out/r2i_bench.err

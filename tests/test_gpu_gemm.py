@@ -293,3 +293,76 @@ def test_gemm_split_precision(case, mode):
     if has_d:
         derr = float((dot.double() - dref).abs().max() / dref.abs().max())
         assert derr < 10 * tol, (case, mode, derr)
+
+
+def _multi_problem(spec, bf16, dev):
+    """spec = (M, N, K1, K2, act, res, out) with out in {"c", "cb", "both", "split"} -> (params, tensors, reference fn)"""
+    M, N, K1, K2, act, use_res, out = spec
+    dt = torch.bfloat16 if bf16 else torch.float32
+    A = torch.randn(M, K1, device=dev).to(dt).contiguous()
+    A2 = torch.randn(M, K2, device=dev).to(dt).contiguous() if K2 else None
+    W = (torch.randn(N, K1 + K2, device=dev) / (K1 + K2) ** 0.5).to(dt).contiguous()
+    b = torch.randn(N, device=dev)
+    n_split = (N // 2 + 127) // 128 * 128 if out == "split" else 0        # column routing wants a multiple of 128 (q|k: 1152 of 2176)
+    nc = n_split if n_split else N
+    res = torch.randn(M, nc, device=dev) if use_res else None
+    Cf = res.clone() if use_res else torch.full((M, nc), float("nan"), device=dev)     # in-place residual, like the stack
+    Cb = torch.zeros(M, N - n_split, dtype=dt, device=dev)
+    g = _lib.GemmParams()
+    g.A, g.lda, g.K1 = A.data_ptr(), K1, K1
+    if K2:
+        g.A2, g.lda2, g.K2 = A2.data_ptr(), K2, K2
+    g.W, g.bias, g.act = W.data_ptr(), b.data_ptr(), act
+    if use_res:
+        g.res, g.ldres = Cf.data_ptr(), nc
+    if out in ("c", "both", "split"):
+        g.C, g.ldc = Cf.data_ptr(), nc
+    if out in ("cb", "both", "split"):
+        g.Cb, g.ldcb = Cb.data_ptr(), N - n_split
+    g.M, g.N, g.n_split = M, N, n_split
+    g.bf16_mode = int(bf16)
+    ref, _ = ref_gemm(A.float(), W.float(), b, act, None, A2.float() if K2 else None, None, bf16)
+    if use_res:
+        ref = ref + res.double()
+    keep = (A, A2, W, b, res, Cf, Cb)
+    return g, keep, ref, out, n_split
+
+
+MULTI_GROUPS = [
+    # the folded groups of one layer at the benched shape (forward.cu): rows p = 3216, rows c = 496
+    [(3216, 512, 128, 0, 0, True, "both"), (3216, 256, 512, 128, 0, False, "c"), (3216, 1024, 512, 128, 2, False, "cb")],
+    [(496, 512, 128, 0, 0, True, "both"), (496, 1024, 512, 128, 2, False, "cb"), (3216, 512, 1024, 0, 0, True, "both")],
+    [(496, 512, 1024, 0, 0, True, "both"), (3216, 2176, 512, 0, 0, False, "split"), (496, 2176, 512, 1024, 0, False, "split")],
+    [(3712, 512, 512, 0, 0, True, "both"), (496, 512, 512, 512, 0, False, "c"), (3216, 256, 512, 512, 0, False, "c")],
+    # ragged: one row, a row count that is not a multiple of the tile, four problems, a single problem
+    [(1, 128, 64, 0, 1, False, "cb"), (129, 384, 64, 64, 0, True, "c"), (77, 128, 192, 0, 2, False, "both"), (300, 256, 128, 0, 1, False, "c")],
+    [(232, 512, 512, 0, 1, False, "cb")],
+]
+
+
+@pytest.mark.parametrize("prefetch", [0, 1])
+@pytest.mark.parametrize("bf16", [True, False])
+@pytest.mark.parametrize("group", range(len(MULTI_GROUPS)))
+def test_gemm_multi_matches_torch(group, bf16, prefetch):
+    """fb_gemm_multi: independent problems with their own operands, K, epilogues and outputs == the layers one by one; in bf16 mode
+    the group must take ONE launch (gemm_tc5.cu)"""
+    dev = "cuda"
+    torch.manual_seed(100 + group)
+    probs = [_multi_problem(s, bf16, dev) for s in MULTI_GROUPS[group]]
+    arr = (_lib.GemmParams * len(probs))(*[p[0] for p in probs])
+    l = _lib.lib()
+    n0 = l.fb_launch_count()
+    _lib.check(l.fb_gemm_multi(arr, len(probs), prefetch, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fb_gemm_multi")
+    torch.cuda.synchronize()
+    if bf16:
+        assert l.fb_launch_count() - n0 == 1, "the group was expected to take the multi-problem tcgen05 launch"
+    for g, keep, ref, out, n_split in probs:
+        Cf, Cb = keep[5], keep[6]
+        scale = ref.abs().max()
+        if out in ("c", "both"):
+            assert float((Cf.double() - ref).abs().max() / scale) < 2e-5
+        if out in ("cb", "both"):
+            assert float((Cb.double() - ref).abs().max() / scale) < (1e-2 if bf16 else 2e-5)
+        if out == "split":
+            assert float((Cf.double() - ref[:, :n_split]).abs().max() / scale) < 2e-5
+            assert float((Cb.double() - ref[:, n_split:]).abs().max() / scale) < (1e-2 if bf16 else 2e-5)
