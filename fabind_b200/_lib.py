@@ -31,6 +31,7 @@ class ModelParams(C.Structure):
         ("trace_h", C.c_void_p), ("trace_x", C.c_void_p),
         ("flavour", C.c_int32), ("pair_out", C.c_void_p),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint32), ("dropout_colonly", C.c_int32), ("attn_tc", C.c_int32),
+        ("n_mv", C.c_int32), ("E_ctx_mv", C.c_int32),
     ]
 
 
@@ -101,6 +102,7 @@ EXPORTS = {
                                         C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "fb_gemm": (C.c_int32, [C.POINTER(GemmParams), C.c_void_p]),
     "fb_gemm_pair": (C.c_int32, [C.POINTER(GemmParams), C.POINTER(GemmParams), C.c_void_p]),
+    "fb_graph_counts_ptr": (C.c_void_p, [C.POINTER(ModelParams)]),
     "fb_derive_weights": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "fb_gemm_multi": (C.c_int32, [C.POINTER(GemmParams), C.c_int32, C.c_int32, C.c_void_p]),
     "fb_gemm_dot_tiles": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

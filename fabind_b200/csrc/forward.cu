@@ -300,16 +300,19 @@ static void plan_graph(const fb_model_params& p, Arena& a, GraphDev& g) {
   g.int_deg = a.get<int>(p.N); g.int_rowptr = a.get<int>(p.N + 1);
   g.int_fallback = a.get<int>(1);
   g.xtmp = a.get<float>(3 * (size_t)p.N);
+  g.n_mv = p.n_mv > 0 && p.n_mv <= p.N ? p.n_mv : 0;
+  g.mv_rows = a.get<int>((size_t)g.n_mv + 1); g.mv_rowptr = a.get<int>((size_t)g.n_mv + 1);
+  g.counts = a.get<int>(2);
 }
 
 struct Bufs {
   // edges
-  int *ctx_row, *ctx_col, *int_row, *int_col, *int_pair;
+  int *ctx_row, *ctx_col, *int_row, *int_col, *int_pair, *mv_erow, *mv_ecol, *mv_emap;
   // coordinates
   float *x_state, *xa, *xb, *xl;
   // node features
-  float *Hin32, *h, *h2, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
-  void *HinT, *hT, *hT2, *agg, *T1, *O, *TH, *VT, *Pn, *VCT;
+  float *Hin32, *h, *h2, *h0, *pc, *CAc, *CAp, *CAp2, *QK, *Hfin;
+  void *HinT, *hT, *hT2, *h0T, *Pn0, *agg, *T1, *O, *TH, *VT, *Pn, *VCT;
   void *CAcT, *CApT, *CAp2T;   // bf16 projections of the cross-attention block (tcgen05 attention core)
   // pair
   void *P0, *A0, *Zg, *T64; float *PBraw, *PB, *pb_dense, *dotU;
@@ -332,6 +335,10 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   const size_t Dp = dp_of((int)H);
   b.ctx_row = a.get<int>(E); b.ctx_col = a.get<int>(E);
   b.int_row = a.get<int>(capI); b.int_col = a.get<int>(capI); b.int_pair = a.get<int>(capI);
+  {
+    const size_t Emv = p.E_ctx_mv > 0 ? p.E_ctx_mv : 1;
+    b.mv_erow = a.get<int>(Emv); b.mv_ecol = a.get<int>(Emv); b.mv_emap = a.get<int>(Emv);
+  }
   b.x_state = a.get<float>(3 * N); b.xa = a.get<float>(3 * N); b.xb = a.get<float>(3 * N); b.xl = a.get<float>(3 * N);
   b.Hin32 = a.get<float>(N * H);
   b.HinT = bf ? a.take(N * H * TS) : (void*)b.Hin32;
@@ -340,7 +347,13 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
   // second residual stream: the folded sequences write the new h next to the old one, which other problems of the same launch
   // still read as their A operand (Run::run_att_folded)
   b.h2 = b.h; b.hT2 = b.hT;
-  if (!plus) { b.h2 = a.get<float>(N * H); b.hT2 = bf ? a.take(N * H * TS) : (void*)b.h2; }
+  b.h0 = nullptr; b.h0T = nullptr; b.Pn0 = nullptr;
+  if (!plus) {
+    b.h2 = a.get<float>(N * H); b.hT2 = bf ? a.take(N * H * TS) : (void*)b.h2;
+    // iteration-invariant head of the stack: linear_in(H) and the first layer's per-node edge-MLP projections of it
+    b.h0 = a.get<float>(N * H); b.h0T = bf ? a.take(N * H * TS) : (void*)b.h0;
+    b.Pn0 = a.take(N * 2 * H * TS);
+  }
   b.Hfin = a.get<float>(N * H);
   b.pc = a.get<float>(N * H);
   b.P0 = a.take(P * H * TS);
@@ -356,7 +369,10 @@ static void plan_main(const fb_model_params& p, Arena& a, Bufs& b) {
     b.PairA = a.take(P * H * TS); b.PairB = a.take(P * H * TS); b.Zl = a.take(P * H * TS); b.Zh = a.take(P * H * TS);
     b.dotP = a.get<float>((size_t)gemm_dot_tiles((int)P, (int)H, (int)H, gmode) * P);
   }
-  b.dotE = a.get<float>(tilesH * E);
+  {
+    const size_t tiles_small = gemm_dot_tiles(1, (int)H, (int)H, gmode);   // short edge lists (compound rows only) take the narrow tiles
+    b.dotE = a.get<float>((tilesH > tiles_small ? tilesH : tiles_small) * E);
+  }
   b.agg = a.take(N * H * TS); b.T1 = a.take(N * H * TS);
   b.CAc = a.get<float>((Nc + 1) * 4 * HD); b.CAp = a.get<float>((Np + 1) * 2 * HD); b.CAp2 = a.get<float>((Np + 1) * 2 * HD);
   b.CAcT = b.CApT = b.CAp2T = nullptr;
@@ -482,6 +498,7 @@ struct Run {
 #endif
     return w.flavour == 0 && p.dropout_p <= 0.f && !xa_on() && p.n_layers > 0;
   }
+  bool mv_ready = false;   // compact edge lists of the moving rows are filled (forward(): after graph_fill_ctx)
   bool ca_ready = false;   // the block's first projections (CAc, CAp) were produced by the preceding run_gcl
 
   // the attention core of both RowAttentionBlocks runs on tcgen05 (xatt_tc.cu) in bf16 mode when asked for (fb_model_params.attn_tc)
@@ -509,13 +526,27 @@ struct Run {
                    : mk(A, H, H, w_off, Nout, b_off, FB_ACT_NONE, M, C32, Nout, nullptr, 0);
   }
 
-  void run_gcl(const GclW& gw, const float* x_in, float* x_out, bool need_h, const AttW* fold_att = nullptr) {
-    const int E = p.E_ctx;
+  // hin32 / hin16 / Pn_pre (folded path only): the layer's input h lives in another buffer (the iteration-invariant linear_in(H)) and
+  // its per-node edge-MLP projections are already there; b.h / b.hT are then only written (through the second residual stream)
+  void run_gcl(const GclW& gw, const float* x_in, float* x_out, bool need_h, const AttW* fold_att = nullptr, const float* hin32 = nullptr,
+               const void* hin16 = nullptr, const void* Pn_pre = nullptr) {
+    const float* h_in = hin32 ? hin32 : b.h;
+    const void* hT_in = hin16 ? hin16 : b.hT;
+    const void* Pn = Pn_pre ? Pn_pre : b.Pn;
+    // coordinates only (out_layer of a non-final iteration: H is discarded and only the masked nodes keep their update,
+    // att_model.py:232-236): the edge MLP runs on the compact list of context edges INTO the moving rows (graph_mv_*: ligand atoms
+    // and the two global nodes, ~1/8 of the edges) and the coordinate step on those rows
+    const bool mv_only = !need_h && mv_ready && p.dropout_p <= 0.f;
+    const int E = mv_only ? p.E_ctx_mv : p.E_ctx;
+    const int n_rows = mv_only ? g.n_mv : N;
+    const int* erow = mv_only ? g.mv_erow : g.ctx_row;
+    const int* ecol = mv_only ? g.mv_ecol : g.ctx_col;
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
     gemm_cat = CAT_GEMM_NODE;
-    gemm(b.hT, H, H, gw.e1_rc, 2 * H, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * H);
+    if (!Pn_pre) gemm(hT_in, H, H, gw.e1_rc, 2 * H, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * H);
     stage(CAT_EDGE_ELEMWISE, [&] {
-      return gcl_edge_pre(E, H, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st);
+      return gcl_edge_pre(E, H, erow, ecol, g.node_cplx, Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st,
+                          mv_only ? g.mv_emap : nullptr);
     });
     gemm_cat = CAT_GEMM_EDGE;
     // training-mode dropout of the v1 stack (dropout_p > 0): edge_mlp output (egnn.py:82), node_mlp output (egnn.py:106)
@@ -523,20 +554,21 @@ struct Run {
     const int tiles = gemm_dot_tiles(E, H, H, gmode);
     gemm(b.M, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_SILU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
     stage(CAT_EDGE_ELEMWISE, [&] {
-      return gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st);
+      return gcl_node(n_rows, H, mv_only ? g.mv_rowptr : g.ctx_rowptr, ecol, b.M, b.dotE, tiles, E, x_in, p.coord_clamp,
+                      need_h ? b.agg : nullptr, x_out, bf, st, mv_only ? g.mv_rows : nullptr);
     });
     gemm_cat = CAT_GEMM_NODE;
     if (need_h) {
-      gemm(b.hT, H, H, gw.n1_w, H, gw.n1_b, FB_ACT_SILU, N, nullptr, 0, b.T1, H, nullptr, 0, b.agg, H, H);
+      gemm(hT_in, H, H, gw.n1_w, H, gw.n1_b, FB_ACT_SILU, N, nullptr, 0, b.T1, H, nullptr, 0, b.agg, H, H);
       if (fold_att && fold_on()) {
         // node_mlp.2 + residual into the SECOND residual stream, and the cross-attention block's first projections of the new h
         // from [h | T1] in the same launch:  h' W^T = h W^T + T1 (W W_n2)^T + W b_n2
         const AttW& aw = *fold_att;
         const size_t op = (size_t)Nc * H;
         const GemmArgs g[3] = {
-            mk(b.hT, H, H, aw.f_cac_w, 4 * HD, aw.f_cac_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0, nullptr, 0, b.T1, H, H),
-            mk(at(b.hT, op), H, H, aw.f_cap_w, 2 * HD, aw.f_cap_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0, nullptr, 0, at(b.T1, op), H, H),
-            mk(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h2, H, b.hT2, H, b.h, H)};
+            mk(hT_in, H, H, aw.f_cac_w, 4 * HD, aw.f_cac_b, FB_ACT_NONE, Nc, b.CAc, 4 * HD, nullptr, 0, nullptr, 0, b.T1, H, H),
+            mk(at(hT_in, op), H, H, aw.f_cap_w, 2 * HD, aw.f_cap_b, FB_ACT_NONE, Np, b.CAp, 2 * HD, nullptr, 0, nullptr, 0, at(b.T1, op), H, H),
+            mk(b.T1, H, H, gw.n2_w, H, gw.n2_b, FB_ACT_NONE, N, b.h2, H, b.hT2, H, h_in, H)};
         gemm_multi(g, 3);
         std::swap(b.h, b.h2); std::swap(b.hT, b.hT2);
         ca_ready = true;
@@ -821,20 +853,34 @@ struct Run {
     gemm_cat = CAT_GEMM_NODE;
     // context graph: protein coordinates are reset every iteration, so it is built once
     stage(CAT_GRAPH_MISC, [&] { return graph_fill_ctx(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
+    if (!plus && g.n_mv > 0 && p.E_ctx_mv > 0 && p.E_ctx_mv < p.E_ctx && p.n_iter > 1) {
+      stage(CAT_GRAPH_MISC, [&] { return graph_mv_fill(g, st); });
+      mv_ready = true;
+    }
+    // iteration-invariant head (folded path): every iteration restarts from linear_in(H) (att_model.py:227-231 feeds the same H
+    // each time), so it and the first layer's per-node projections of it are computed once per forward
+    const bool hoist = fold_on() && p.n_iter > 1 && b.h0 != nullptr;
+    if (hoist) {
+      gemm_cat = CAT_GEMM_NODE;
+      gemm(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h0, H, b.h0T, H);
+      gemm(b.h0T, H, H, w.gcl[0].e1_rc, 2 * H, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn0, 2 * H);
+    }
     for (int it = 0; it < p.n_iter; ++it) {
       const bool last = it == p.n_iter - 1;
       stage(CAT_GRAPH_MISC, [&] { return graph_build_inter(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
       if (p.stats) cudaMemcpyAsync(p.stats + it, g.int_rowptr + N, sizeof(int), cudaMemcpyDeviceToDevice, st);
       gemm_cat = CAT_GEMM_NODE;
       cur_it = it; cur_layer = -1;
-      gemm(wd(mk(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H), dr(S_IN)));
+      if (!hoist) gemm(wd(mk(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H), dr(S_IN)));
       const float* xc = b.x_state;
       float* bufs[2] = {b.xa, b.xb};
       int k = 0;
       const void* pair_cur = b.P0;   // FABind+: every iteration restarts from pair_embed0 (P/models/att_model.py:209-218)
       for (int l = 0; l < p.n_layers; ++l) {
         cur_layer = l;
-        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true); else run_gcl(w.gcl[l], xc, bufs[k], true, &w.att[l]);
+        if (plus) run_gcl_plus(w.gclp[l], xc, bufs[k], true);
+        else if (hoist && l == 0) run_gcl(w.gcl[l], xc, bufs[k], true, &w.att[l], b.h0, b.h0T, b.Pn0);
+        else run_gcl(w.gcl[l], xc, bufs[k], true, &w.att[l]);
         xc = bufs[k]; k ^= 1;
         if (last) tap(2 * l, xc);
         if (plus) {
@@ -995,7 +1041,16 @@ int32_t fb_graph_static(const fb_model_params* p, void* stream) {
   // the count pass needs coordinates in the internal order
   r = permute_x(g, p->X_in, g.xtmp, st);
   if (r != FB_OK) return r;
-  return graph_count_ctx(g, g.xtmp, p->intra_cutoff, p->inter_cutoff, st);
+  r = graph_count_ctx(g, g.xtmp, p->intra_cutoff, p->inter_cutoff, st);
+  if (r != FB_OK) return r;
+  return graph_mv_index(g, st);
+}
+
+const int32_t* fb_graph_counts_ptr(const fb_model_params* p) {
+  Arena a(p->ws_graph, p->ws_graph_bytes, false);
+  GraphDev g;
+  plan_graph(*p, a, g);
+  return g.counts;
 }
 
 const int32_t* fb_graph_ctx_count_ptr(const fb_model_params* p) {
@@ -1016,6 +1071,7 @@ int32_t fb_model_forward(const fb_model_params* p, void* stream) {
   if (!ag.ok || !am.ok) return FB_ERR_WORKSPACE;
   r.g.ctx_row = r.b.ctx_row; r.g.ctx_col = r.b.ctx_col;
   r.g.int_row = r.b.int_row; r.g.int_col = r.b.int_col; r.g.int_pair = r.b.int_pair;
+  r.g.mv_erow = r.b.mv_erow; r.g.mv_ecol = r.b.mv_ecol; r.g.mv_emap = r.b.mv_emap;
   r.st = (cudaStream_t)stream;
   r.bf = p->bf16_mode == FB_PREC_BF16; r.gmode = p->bf16_mode;
   r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;
@@ -1041,6 +1097,7 @@ int32_t fb_egnn_forward(const fb_model_params* p, const fb_egnn_extra* e, void* 
   if (!ag.ok || !am.ok) return FB_ERR_WORKSPACE;
   r.g.ctx_row = r.b.ctx_row; r.g.ctx_col = r.b.ctx_col;
   r.g.int_row = r.b.int_row; r.g.int_col = r.b.int_col; r.g.int_pair = r.b.int_pair;
+  r.g.mv_erow = r.b.mv_erow; r.g.mv_ecol = r.b.mv_ecol; r.g.mv_emap = r.b.mv_emap;
   r.st = (cudaStream_t)stream;
   r.bf = p->bf16_mode == FB_PREC_BF16; r.gmode = p->bf16_mode;
   r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;

@@ -202,6 +202,79 @@ __global__ void __launch_bounds__(256) las_rows_kernel(GraphDev g) {
 
 static inline int warp_grid(int n_rows) { return (n_rows * 32 + 255) / 256; }
 
+// moving rows (flag bit2) in ascending order + exclusive scan of their context degrees; single block.  Also publishes the two edge
+// counts the host reads back (counts[0] = E_ctx, counts[1] = E_mv).
+__global__ void __launch_bounds__(1024) mv_index_kernel(GraphDev g) {
+  pdl_entry();
+  __shared__ int tot_c[32], tot_d[32];
+  __shared__ int carry_c, carry_d;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { carry_c = 0; carry_d = 0; }
+  __syncthreads();
+  for (int i0 = 0; i0 < g.N; i0 += 1024) {
+    const int i = i0 + tid;
+    const int f = (i < g.N && (g.node_flags[i] & 4)) ? 1 : 0;
+    const int d = f ? g.ctx_rowptr[i + 1] - g.ctx_rowptr[i] : 0;
+    int ic = f, id = d;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tc = __shfl_up_sync(0xffffffffu, ic, o), td = __shfl_up_sync(0xffffffffu, id, o);
+      if (lane >= o) { ic += tc; id += td; }
+    }
+    if (lane == 31) { tot_c[wid] = ic; tot_d[wid] = id; }
+    __syncthreads();
+    if (wid == 0) {
+      int wc = tot_c[lane], wd = tot_d[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tc = __shfl_up_sync(0xffffffffu, wc, o), td = __shfl_up_sync(0xffffffffu, wd, o);
+        if (lane >= o) { wc += tc; wd += td; }
+      }
+      tot_c[lane] = wc; tot_d[lane] = wd;
+    }
+    __syncthreads();
+    const int pos = carry_c + (wid ? tot_c[wid - 1] : 0) + ic - f;
+    const int off = carry_d + (wid ? tot_d[wid - 1] : 0) + id - d;
+    if (f && pos < g.n_mv) { g.mv_rows[pos] = i; g.mv_rowptr[pos] = off; }
+    __syncthreads();
+    if (tid == 1023) { carry_c += tot_c[31]; carry_d += tot_d[31]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    g.mv_rowptr[g.n_mv] = carry_d;
+    g.counts[0] = g.ctx_rowptr[g.N];
+    g.counts[1] = carry_c == g.n_mv ? carry_d : 0;    // a host / device disagreement on the number of moving rows switches the subset off
+  }
+}
+
+// compact edge lists of the moving rows: one warp per row
+__global__ void __launch_bounds__(256) mv_fill_kernel(GraphDev g) {
+  pdl_entry();
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= g.n_mv) return;
+  const int r = g.mv_rows[j], lo = g.ctx_rowptr[r], n = g.ctx_rowptr[r + 1] - lo, dst = g.mv_rowptr[j];
+  for (int k = lane; k < n; k += 32) {
+    g.mv_erow[dst + k] = r;
+    g.mv_ecol[dst + k] = g.ctx_col[lo + k];
+    g.mv_emap[dst + k] = lo + k;
+  }
+}
+
+int graph_mv_index(const GraphDev& g, cudaStream_t st) {
+  fb_launch(mv_index_kernel, dim3(1), dim3(1024), 0, st, g);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int graph_mv_fill(const GraphDev& g, cudaStream_t st) {
+  if (g.n_mv <= 0) return FB_OK;
+  fb_launch(mv_fill_kernel, dim3(warp_grid(g.n_mv)), dim3(256), 0, st, g);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
 int graph_prepare_static(const GraphDev& g, const long long* bonds, const long long* las,
                          cudaStream_t st) {
   if (g.n_bond > 0) fb_launch(convert_edges_kernel, dim3((g.n_bond + 255) / 256), dim3(256), 0, st, bonds, g.n_bond, g.inv, g.bond_row, g.bond_col);

@@ -32,11 +32,22 @@ struct GraphDev {
   int* int_row = nullptr; int* int_col = nullptr; int* int_pair = nullptr;  // [cap_int]
   int* int_fallback = nullptr;                        // [1]
   float* xtmp = nullptr;                              // [3N] coordinates in internal order (count pass)
+  // moving rows (node_flags bit2) and the context edges INTO them, compacted: the out_layer of a non-final iteration only has to
+  // produce the coordinates of these rows (att_model.py:232-236)
+  int n_mv = 0;                                       // number of moving rows (host-known)
+  int* mv_rows = nullptr;                             // [n_mv] internal ids, ascending
+  int* mv_rowptr = nullptr;                           // [n_mv + 1] CSR over the compact edge list
+  int* mv_erow = nullptr; int* mv_ecol = nullptr;     // [E_mv] endpoints
+  int* mv_emap = nullptr;                             // [E_mv] index of the edge in the full context list
+  int* counts = nullptr;                              // [2] E_ctx, E_mv (read by the host after fb_graph_static)
 };
 
 int graph_prepare_static(const GraphDev& g, const long long* bonds, const long long* las, cudaStream_t st);
 int graph_count_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st);
 int graph_fill_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st);
+// moving rows: index + compact row pointers (after graph_count_ctx), compact edge lists (after graph_fill_ctx)
+int graph_mv_index(const GraphDev& g, cudaStream_t st);
+int graph_mv_fill(const GraphDev& g, cudaStream_t st);
 int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st);
 
 int graph_ref_count(int N, const int* cplx, const int* off, const uint8_t* flags, const float* x,

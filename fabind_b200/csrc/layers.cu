@@ -192,13 +192,14 @@ template <typename T>
 __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, const int* __restrict__ ecol,
                                     const int* __restrict__ node_cplx, const T* __restrict__ P,
                                     const float* __restrict__ rad, const float* __restrict__ norm,
-                                    const float* __restrict__ w_rad, const float* __restrict__ b1, T* __restrict__ A1) {
+                                    const float* __restrict__ w_rad, const float* __restrict__ b1, T* __restrict__ A1,
+                                    const int* __restrict__ emap) {
   pdl_entry();
   constexpr bool FAST = !std::is_same<T, float>::value;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
   const int e = warp, r = erow[e], c = ecol[e];
-  const float rn = rad[e] / radial_norm(norm, node_cplx[r]);
+  const float rn = rad[emap ? emap[e] : e] / radial_norm(norm, node_cplx[r]);
   const T* pr = P + (size_t)r * 2 * H;
   const T* pc = P + (size_t)c * 2 * H + H;
   for (int f = lane * 8; f < H; f += 256) {
@@ -215,11 +216,11 @@ __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, 
 
 int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node_cplx, const void* P,
                  const float* rad, const float* norm, const float* w_rad, const float* b1, void* A1, bool bf16_mode,
-                 cudaStream_t st) {
+                 cudaStream_t st, const int* emap) {
   if (E <= 0) return FB_OK;
   if (H & 7) return FB_ERR_UNSUPPORTED;
-  if (bf16_mode) fb_launch(gcl_edge_pre_kernel<bf16>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const bf16*)P, rad, norm, w_rad, b1, (bf16*)A1);
-  else fb_launch(gcl_edge_pre_kernel<float>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const float*)P, rad, norm, w_rad, b1, (float*)A1);
+  if (bf16_mode) fb_launch(gcl_edge_pre_kernel<bf16>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const bf16*)P, rad, norm, w_rad, b1, (bf16*)A1, emap);
+  else fb_launch(gcl_edge_pre_kernel<float>, dim3(warp_grid(E)), dim3(256), 0, st, E, H, erow, ecol, node_cplx, (const float*)P, rad, norm, w_rad, b1, (float*)A1, emap);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
                                                         const int* __restrict__ ecol, const T* __restrict__ M,
                                                         const float* __restrict__ dot, int dot_tiles, int dot_stride,
                                                         const float* __restrict__ x, float cmax, T* __restrict__ agg,
-                                                        float* __restrict__ x_out) {
+                                                        float* __restrict__ x_out, const int* __restrict__ rmap) {
   pdl_entry();
   extern __shared__ float part[];  // [G][H]
   const int G = blockDim.x >> 6;   // node groups (64 feature lanes each) per CTA
@@ -298,7 +299,8 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
   if (r < N) { lo = s_rp[grp]; hi = s_rp[grp + 1]; }
   // coordinate part: first warp of each group, lanes over edges
   if (r < N && t < 32) {
-    const float xr0 = x[3 * r], xr1 = x[3 * r + 1], xr2 = x[3 * r + 2];
+    const int rn = rmap ? rmap[r] : r;      // node id of this row
+    const float xr0 = x[3 * rn], xr1 = x[3 * rn + 1], xr2 = x[3 * rn + 2];
     float ax = 0.f, ay = 0.f, az = 0.f;
     for (int e = lo + lane; e < hi; e += 32) {
       float s = 0.f;
@@ -311,9 +313,9 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
     ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
     if (lane == 0) {
       const float cnt = fmaxf((float)(hi - lo), 1.0f);
-      x_out[3 * r] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
-      x_out[3 * r + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
-      x_out[3 * r + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
+      x_out[3 * rn] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
+      x_out[3 * rn + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
+      x_out[3 * rn + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
     }
   }
   if (agg == nullptr) return;
@@ -348,13 +350,14 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
 }
 
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
-             int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st) {
+             int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st, const int* rmap) {
   if (H & 7) return FB_ERR_UNSUPPORTED;
+  if (rmap && agg) return FB_ERR_BAD_ARG;
   const int G = 16;
   const int smem = G * H * 4;
   const int grid = (N + G - 1) / G;
-  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out);
-  else fb_launch(gcl_node_kernel<float>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out);
+  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out, rmap);
+  else fb_launch(gcl_node_kernel<float>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out, rmap);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

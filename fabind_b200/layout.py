@@ -27,6 +27,7 @@ class Layout:
     orig_off: np.ndarray    # [B+1] node offsets in caller order
     n_c: np.ndarray
     n_p: np.ndarray
+    n_mv: int = 0                   # number of masked (moving) nodes
 
     def ptr(self, name):
         return self.blob.data_ptr() + 4 * self.offs[name]
@@ -88,4 +89,5 @@ def build_layout(batch_id, segment_id, is_global, mask, device, allow_single_sid
     blob = torch.from_numpy(np.concatenate(chunks)).to(device, non_blocking=True)
     flags_t = torch.from_numpy(flags).to(device, non_blocking=True)
     return Layout(N=N, B=B, Nc_tot=Nc_tot, P_total=int(pair_base[-1]), cap_int=cap_int, fb_atom=int(fb_atom),
-                  fb_res=int(fb_res), max_c=int(nc1.max()), max_p=int(np1.max()) if len(np1) else 0, blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p)
+                  fb_res=int(fb_res), max_c=int(nc1.max()), max_p=int(np1.max()) if len(np1) else 0, blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p,
+                  n_mv=int(msk.sum()))

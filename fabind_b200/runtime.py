@@ -141,6 +141,7 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.hidden, p.n_layers, p.n_iter = hidden, cfg["n_layers"], cfg["n_iter"]
     p.n_bond, p.n_las = bonds.shape[1], las.shape[1]
     p.E_ctx, p.cap_int, p.bf16_mode = 0, lay.cap_int, mode
+    p.n_mv = lay.n_mv
     p.fb_atom, p.fb_res = lay.fb_atom, lay.fb_res
     p.max_c, p.max_p = lay.max_c, lay.max_p
     p.intra_cutoff, p.inter_cutoff = cfg["intra_cutoff"], cfg["inter_cutoff"]
@@ -178,11 +179,12 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     wsg = _scratch_buf(dev, "graph", gbytes)
     p.ws_graph, p.ws_graph_bytes = wsg.data_ptr(), wsg.numel()
     _lib.check(l.fb_graph_static(C.byref(p), st), "fb_graph_static")
-    # one host read per forward: the number of context edges sizes the edge-level scratch
-    cnt_ptr = l.fb_graph_ctx_count_ptr(C.byref(p))
-    off = (cnt_ptr - wsg.data_ptr())
-    e_ctx = int(wsg[off:off + 4].view(torch.int32).item())
-    p.E_ctx = e_ctx
+    # one host read per forward: the number of context edges sizes the edge-level scratch (the same read fetches the number of
+    # context edges into the moving rows, fb_model_params.E_ctx_mv)
+    cnt_ptr = l.fb_graph_counts_ptr(C.byref(p))
+    off = (cnt_ptr - wsg.data_ptr()) // 4
+    e_ctx, e_ctx_mv = wsg[: (off + 2) * 4].view(torch.int32)[off:off + 2].tolist()
+    p.E_ctx, p.E_ctx_mv = e_ctx, e_ctx_mv
     _mark("graph_static + E_ctx read")
     mbytes = l.fb_model_workspace_bytes(C.byref(p))
     if mbytes < 0:

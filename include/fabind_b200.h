@@ -91,6 +91,12 @@ typedef struct fb_model_params {
   int32_t attn_tc;
   /* ABI 4: dropout is also served for FB_FLAVOUR_V1 -- the training-mode forward of the reference (models/egnn.py:82,106,236,
    * 398,461; models/cross_att.py:128), same sites / hash as the FABind+ stack where the layouts share them. */
+  /* ABI 5: moving rows.  Non-final iterations discard H and keep only the coordinates of the masked nodes (node_flags bit2;
+   * att_model.py:232-236, model.py:261-262: ligand atoms + both global nodes), so their out_layer MC_E_GCL is evaluated on the
+   * context edges INTO those rows only.  n_mv = number of masked nodes (host-known; 0 switches the subset off); fb_graph_static
+   * compacts their rows, and E_ctx_mv = the number of such edges, read back next to E_ctx (fb_graph_counts_ptr), sizes the list. */
+  int32_t n_mv;
+  int32_t E_ctx_mv;
 } fb_model_params;
 #define FB_FLAVOUR_V1 0
 #define FB_FLAVOUR_PLUS 1
@@ -139,6 +145,8 @@ int64_t fb_weight_arena_elems_f(int32_t hidden, int32_t n_layers, int32_t flavou
 int32_t fb_derive_weights(float* w32, int32_t hidden, int32_t n_layers, int32_t flavour, void* stream);
 
 /* [host] scratch sizes */
+/* ABI 5: device pointer to int32[2] = {E_ctx, E_ctx_mv}, valid after fb_graph_static and a stream sync (one read for both) */
+const int32_t* fb_graph_counts_ptr(const fb_model_params* p);
 int64_t fb_graph_workspace_bytes(const fb_model_params* p);
 int64_t fb_model_workspace_bytes(const fb_model_params* p);
 
