@@ -122,7 +122,11 @@ int gemm_launch(const GemmArgs& g, int mode, cudaStream_t st) {
   const bool bf16_mode = mode == GEMM_BF16;
   if (bf16_mode && gemm_tc_supported(g)) {
     if (tc_version() == 3) {
-      // long (edge-level / pair-level) problems: CTA pairs (tcgen05 cta_group::2), a third less operand traffic per MMA
+      // long (edge-level / pair-level) problems: CTA pairs (tcgen05 cta_group::2), a third less operand traffic per MMA.
+      // (A weight-STATIONARY variant -- the pair's 256-column weight tile resident in shared memory, only A streaming, rows stored
+      // straight from registers -- was built and measured in round 2: 26.9 / 22.4 / 50.2 us against 25.3 / 22.3 / 52.8 us for
+      // SiLU+store / row-dot / 99.7k pair rows, profiles/r2m_gemm_time_tc6_weight_stationary_rejected.txt: operand traffic is not
+      // what bounds this kernel any more, so it was dropped.)
       const int r4 = gemm_tc4_launch(g, st);
       if (r4 != FB_ERR_UNSUPPORTED) return r4;
       const int r = gemm_tc3_launch(g, st);
