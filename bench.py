@@ -445,17 +445,22 @@ def stage_profile(lib, dev_step, steps, timer, dev):
     return {c: dict(ms_per_step=ms[i] / steps, launches_per_step=spans[i] / steps, gflop_per_step=fl[i] / steps / 1e9) for i, c in enumerate(CATS)}
 
 
-def cpu_baseline_leg(model):
+def cpu_baseline_leg(model, dev=None):
+    """the oracle port (checker) timed on the host cores on ONE complex of the benched shape; the same complex then goes through the
+    product path (this repo's CUDA kernels) in the benched precision and in the tensor-core parity mode, and the relative differences
+    to the oracle's outputs are reported next to the timing (`parity`)"""
     from oracle import fabind_oracle as orc
     from fabind_b200.synthetic import make_batch
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     cfg = orc.make_cfg(n_layers=LAYERS, n_iter=ITERS)
     sb = make_batch(n_complexes=1, n_c=N_C, n_p=N_P, embed=HIDDEN, seed=0)
+    ref = {}
 
     def cstep():
         with torch.no_grad():
-            orc.model_forward(sd, cfg, sb.X, sb.H, sb.batch_id, sb.segment_id, sb.mask, sb.is_global,
-                              sb.compound_edge_index, sb.LAS_edge_index, sb.X_LAS)
+            out = orc.model_forward(sd, cfg, sb.X.clone(), sb.H, sb.batch_id, sb.segment_id, sb.mask, sb.is_global,
+                                    sb.compound_edge_index, sb.LAS_edge_index, sb.X_LAS)
+        ref["out"] = out
     threads = pick_threads()
     torch.set_num_threads(threads)
     cstep()
@@ -464,9 +469,29 @@ def cpu_baseline_leg(model):
         t0 = time.perf_counter()
         cstep()
         ts.append(time.perf_counter() - t0)
-    return {"value": 1.0 / statistics.median(ts), "unit": "complexes/s", "cores": os.cpu_count(), "threads": threads, "kind": "port",
-            "sample": f"1 complex (n_c={N_C}, n_p={N_P}); thread count picked from {{16,32,all}} by subprocess "
-                      "probes, then 1 warm-up + 8 timed full forwards, median"}
+    res = {"value": 1.0 / statistics.median(ts), "unit": "complexes/s", "cores": os.cpu_count(), "threads": threads, "kind": "port",
+           "sample": f"1 complex (n_c={N_C}, n_p={N_P}); thread count picked from {{16,32,all}} by subprocess "
+                     "probes, then 1 warm-up + 8 timed full forwards, median"}
+    if dev is not None:
+        try:
+            Xr, Hr = ref["out"][0].reshape(-1, 3).double(), ref["out"][1].double()
+            par = {}
+            keep = model.precision
+            for prec in ("bf16", "fp32_tc"):
+                model.precision = prec
+                db = sb.to(dev)
+                with torch.no_grad():
+                    out = model(**db.forward_args())
+                Xg, Hg = out[0].reshape(-1, 3).double().cpu(), out[1].double().cpu()
+                par[prec] = {"x_rel": float((Xg - Xr).abs().max() / Xr.abs().max()), "h_rel": float((Hg - Hr).abs().max() / Hr.abs().max()),
+                             "x_abs_normalised_units": float((Xg - Xr).abs().max())}
+            model.precision = keep
+            par["what"] = ("max |ours - oracle| / max |oracle| over X and H of the same complex and weights: bf16 = the benched arithmetic, "
+                           "fp32_tc = tensor-core parity mode (tolerance of the parity tests: 1e-4)")
+            res["parity"] = par
+        except Exception as e:                    # the parity read-out must never take the graded line down
+            res["parity"] = {"error": repr(e)[:200]}
+    return res
 
 
 def roofline_objects(prof, peaks, clk, e_ctx, ms_per_step, pair_rows_frac=1.0):
@@ -481,7 +506,7 @@ def roofline_objects(prof, peaks, clk, e_ctx, ms_per_step, pair_rows_frac=1.0):
     if os.path.exists(tp):
         traffic_tab = json.load(open(tp))
     names = {"gemm_edge": "edge-MLP GEMMs (tc4::gemm_tc4_kernel, tcgen05 cta_group::2, 256x256 tiles; M = E_ctx, N = K = 512)",
-             "gemm_node": "node-level GEMMs (tc3::gemm_tc3_kernel persistent 128x128 tiles + fused node kernels; M <= N nodes)",
+             "gemm_node": "node-level GEMMs (tc5::gemm_tc5_kernel multi-problem launches of the folded projection groups + tc3::gemm_tc3_kernel, persistent 128x128 tiles; M <= N nodes)",
              "gemm_pair": "pair-path GEMM on the unique interface pairs (M = E_int / 2, K = 576, N = 1024, row-dot epilogue)",
              "gemm_pair0": "pair_embed0 + pair-bias GEMMs (once per forward, M = pair rows)"}
     total = max(sum(v["ms_per_step"] for v in prof.values()), 1e-9)
@@ -693,7 +718,7 @@ def main():
         out["stage_launches_per_step"] = {k: v["launches_per_step"] for k, v in prof.items()}
     else:
         out["roofline"] = None
-    out["cpu_baseline"] = cpu_baseline_leg(model) if (world == 1 and not args.no_cpu_baseline and args.config == 2) else None
+    out["cpu_baseline"] = cpu_baseline_leg(model, dev) if (world == 1 and not args.no_cpu_baseline and args.config == 2) else None
     if extras:
         out["extras"] = extras
     print(json.dumps(out))
