@@ -451,6 +451,7 @@ struct Run {
     a.A = A; a.lda = lda; a.K1 = K; a.A2 = A2; a.lda2 = lda2; a.K2 = K2;
     a.W = W(w_off); a.bias = b_off >= 0 ? F(b_off) : nullptr; a.act = act;
     a.W_f32 = p.w32 + w_off; a.split_ws = b.split_ws; a.split_ws_bytes = b.split_bytes;
+    a.w_static = true;       // the arena is written before the forward starts, never by its kernels
     a.res = res; a.ldres = ldres; a.C = C; a.ldc = ldc;
     a.Cb = bf ? Cb : nullptr; a.ldcb = ldcb;
     if (!bf && Cb != nullptr && (void*)C != Cb) {  // fp32 mode: the typed output IS the fp32 output

@@ -122,13 +122,14 @@ int gemm_launch(const GemmArgs& g, int mode, cudaStream_t st) {
   const bool bf16_mode = mode == GEMM_BF16;
   if (bf16_mode && gemm_tc_supported(g)) {
     if (tc_version() == 3) {
-      // long (edge-level / pair-level) problems: CTA pairs (tcgen05 cta_group::2), a third less operand traffic per MMA.
-      // (A weight-STATIONARY variant -- the pair's 256-column weight tile resident in shared memory, only A streaming, rows stored
-      // straight from registers -- was built and measured in round 2: 26.9 / 22.4 / 50.2 us against 25.3 / 22.3 / 52.8 us for
-      // SiLU+store / row-dot / 99.7k pair rows, profiles/r2m_gemm_time_tc6_weight_stationary_rejected.txt: operand traffic is not
-      // what bounds this kernel any more, so it was dropped.)
+      // long (edge-level / pair-level) problems: CTA pairs (tcgen05 cta_group::2) -- weight tile stationary in shared memory when
+      // K <= 512, both operands streaming otherwise (gemm_tc4.cu)
       const int r4 = gemm_tc4_launch(g, st);
       if (r4 != FB_ERR_UNSUPPORTED) return r4;
+      // node-level problems: the multi-producer kernel (three TMA-issuing warps) as a one-problem launch; what it declines (row-dot,
+      // dropout, device-side row counts) stays on v3
+      const int r5 = gemm_tc5_launch(&g, 1, g.w_static, st);
+      if (r5 != FB_ERR_UNSUPPORTED) return r5;
       const int r = gemm_tc3_launch(g, st);
       if (r != FB_ERR_UNSUPPORTED) return r;
     }
@@ -147,7 +148,12 @@ int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, int mode, cudaStrea
   const bool group = true;
 #endif
   if (group && mode == GEMM_BF16 && tc_version() >= 2 && gemm_tc_supported(g0) && gemm_tc_supported(g1)) {
-    int r = tc_version() == 3 ? gemm_tc3_launch_pair(g0, g1, st) : FB_ERR_UNSUPPORTED;
+    int r = FB_ERR_UNSUPPORTED;
+    if (tc_version() == 3 && g0.M > 0 && g1.M > 0) {
+      const GemmArgs two[2] = {g0, g1};
+      r = gemm_tc5_launch(two, 2, g0.w_static && g1.w_static, st);
+    }
+    if (r == FB_ERR_UNSUPPORTED && tc_version() == 3) r = gemm_tc3_launch_pair(g0, g1, st);
     if (r == FB_ERR_UNSUPPORTED && g0.drop.p <= 0.f && g1.drop.p <= 0.f) r = gemm_tc2_launch_pair(g0, g1, st);
     if (r != FB_ERR_UNSUPPORTED) return r;
   }

@@ -27,6 +27,8 @@ struct GemmArgs {
   const void* W_f32 = nullptr;                           // the same weight in fp32 [N, K]: shapes tcgen05 cannot take run on the FFMA kernel
   int nprod = 0;                                         // set by the dispatcher: products per k-block (tc3 / tc4 kernels)
   bool exact_act = false;                                // full-precision SiLU in the tcgen05 epilogues (split modes)
+  bool w_static = false;                                 // W was not written by the kernels immediately before this launch in the stream:
+                                                         // the multi-producer kernel (gemm_tc5.cu) may request it before griddepcontrol.wait
 };
 
 // precision modes of gemm_launch.  SPLITn: fp32 operands as sums of bf16 planes (x = x0 + x1 + x2, 8 mantissa bits each), the

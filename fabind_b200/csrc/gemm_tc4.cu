@@ -6,13 +6,19 @@
 // ONE 256x256 tile with tcgen05.mma.cta_group::2 each stage their own 128 rows of A and only HALF of the B (weight) slab:
 // 32 KB per CTA and k-slab for the same MMA time, a third less operand traffic.
 //
-// Structure (per CTA, same warp roles as v3): warp 0 = TMA producer (its 128 A rows + its 128 of the 256 W rows per k-slab, with
-// the completion bytes of BOTH CTAs signalled on the LEADER's "full" barrier), warp 1 = MMA issuer (leader CTA only; one
+// Structure (per CTA): warps 0-2 = TMA producers (a CTA's 128 A rows + its 128 of the 256 W rows per k-slab, with the completion
+// bytes of BOTH CTAs signalled on the LEADER's "full" barrier), warp 3 = MMA issuer (leader CTA only; one
 // tcgen05.mma.cta_group::2 per 16-wide k-step, M = 256, N = 256; tcgen05.commit multicast releases the smem stage / publishes the
-// accumulator in both CTAs), warps 2-9 = epilogue exactly as v3 (each CTA drains its own 128 TMEM lanes; TMA-store staging
-// boxes).  The leader's "accumulator drained" barrier counts the epilogue warps of both CTAs (remote mbarrier arrive).
+// accumulator in both CTAs), warps 4-11 = epilogue (each CTA drains its own 128 TMEM lanes; rows stored straight from registers).  The
+// leader's "accumulator drained" barrier counts the epilogue warps of both CTAs (remote mbarrier arrive).
+// THREE producer warps on three SM sub-partitions, k-slab i issued by producer i % 3 into ring slot i % 4: the bulk-tensor loads of
+// ONE issuing thread are served at ~32 B/clk per SM however deep the ring (profiles/r2n_tma_issue_microbench_*: 23 B/clk with one
+// box per barrier, 32 with two, 65 from two warps, 106 from four), and SIX ring stages: with four, the MMA warp spent 38-47 % of
+// the kernel waiting for operands while the producer waited as long for free slots (profiles/r2p_tc4_role_stalls_4_stage_ring.txt:
+// the slot round trip -- load, queue, MMA, commit, re-issue -- is ~3500 clk, four slots in flight sustain one k-slab per ~950 clk
+// against ~750 clk of MMA time).  The 64 KB the two extra stages need were the TMA-store staging boxes of the epilogue.
 // Persistent over 256x256 tiles; two TMEM accumulator stages (2 x 256 columns).  No residual, one stored output (the shapes this
-// kernel is picked for never need more).
+// kernel is picked for never need more); outputs need 32-byte aligned rows (256-bit stores).
 #include <cstdlib>
 
 #include "gemm.h"
@@ -22,7 +28,6 @@ namespace fb {
 
 extern long long* g_tc_dbg;
 bool tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
-bool tc_make_map_out(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t rows, uint64_t cols, uint64_t ld);
 
 namespace tc4 {
 using namespace tc;
@@ -31,30 +36,41 @@ constexpr int BN = 256;                         // tile columns (the pair's MMA 
 constexpr int BNH = BN / 2;                     // W rows staged per CTA
 constexpr int PM = 2 * BM;                      // tile rows of the pair
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + EPI_WARPS * 32;   // 320
-constexpr int SLOT = 4096;                      // one staging box: 32 rows x 128 bytes
-constexpr int NS = 2;
-constexpr int STAGES = 4;
+constexpr int PRODUCERS = 3;                    // TMA-issuing warps on three SM sub-partitions (the fourth hosts the MMA warp); 12 warps keep 168 registers per thread
+constexpr int MMA_WARP = PRODUCERS;             // warp 3
+constexpr int EPI_WARP0 = PRODUCERS + 1;        // warps 4..11
+constexpr int THREADS = (PRODUCERS + 1 + EPI_WARPS) * 32;   // 384
+constexpr int STAGES = 6;                       // 192 KB of operands in flight per CTA (see the header: the ring depth is what fed the MMAs too slowly)
 constexpr int VEC = BN / 2;                     // columns per epilogue warp: its bias / row-dot vectors live in shared memory
 
 struct Params {
   int M, N, KB1, KB2;
   int nprod, exact_act;     // split-precision mode (see gemm.h): products per k-block, KB1 = k-blocks of ONE plane
   const float* bias; int act;
-  int has_c, has_cb;
+  float* C; int ldc;
+  bf16* Cb; int ldcb;
   const float* dotv; float* dot_out; int dot_stride;
   int n_split;
   const int* m_dev;
   DropCfg drop;
+  int w_static;             // the weights were not written by the kernels just before this launch (weight-stationary form: prefetch)
+  long long* dbg;
 };
 
+constexpr int KB_MAX = 8;                       // weight-stationary form: up to 8 resident k-slabs (K <= 512)
+
+// WSTAT = weight-stationary form: the CTA's half of ONE 256-column weight tile (128 rows x K <= 512 = up to 128 KB) stays in shared
+// memory for the life of the CTA and only A streams through the ring (16 KB slabs)
+template <bool WSTAT>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNH * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;                       // 32 KB
-  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
-  static constexpr int VEC_OFF = STAGING_OFF + EPI_WARPS * NS * SLOT;         // per epilogue warp: bias[VEC] | dotv[VEC] (fp32)
-  static constexpr int BAR_OFF = VEC_OFF + EPI_WARPS * 2 * VEC * 4;           // full[S] empty[S] tfull[2] tempty[2] slot
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;    // + alignment slack
+  static constexpr int NSTAGE = WSTAT ? 5 : STAGES;
+  static constexpr int STAGE_BYTES = WSTAT ? A_BYTES : A_BYTES + B_BYTES;     // 16 / 32 KB
+  static constexpr int W_OFF = 0;                                             // WSTAT: resident weight slabs
+  static constexpr int RING_OFF = WSTAT ? KB_MAX * B_BYTES : 0;
+  static constexpr int VEC_OFF = RING_OFF + NSTAGE * STAGE_BYTES;             // per epilogue warp: bias[VEC] | dotv[VEC] (fp32)
+  static constexpr int BAR_OFF = VEC_OFF + EPI_WARPS * 2 * VEC * 4;           // full[S] empty[S] tfull[2] tempty[2] wfull slot
+  static constexpr int TOTAL = BAR_OFF + (2 * NSTAGE + 5) * 8 + 16 + 1024;    // + alignment slack
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -99,15 +115,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+// 32 bytes = one full sector per lane
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint32_t sw_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 // four consecutive floats of a read-only vector (16-byte load when the address allows it)
 __device__ __forceinline__ float4 ldg4(const float* p) {
   if (((uintptr_t)p & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
@@ -118,20 +130,37 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
 // epilogue as a template parameter, so that one instantiation carries one straight-line epilogue (the runtime select between three
 // unrolled variants tripled the code the eight epilogue warps walk through: 18 % of their stall samples were instruction fetches,
 // profiles/r2f_tc4_epilogue_before.txt)
-template <bool SPLIT, int ACT>
+#ifdef FB_DIAG
+// per-role stall accounting (clock64 deltas summed per CTA): g_tc_dbg[cta * 8 + k], k = 0 MMA waits for data (full), 1 MMA waits for a
+// drained accumulator (tempty), 2 producer 0 waits for a free slot (empty), 3 epilogue warp 0 waits for an accumulator (tfull),
+// 4 epilogue warp 0 busy, 5 kernel total (thread 0)
+#define FB_T0() const long long t0__ = clock64()
+#define FB_ACC(var) var += clock64() - t0__
+#else
+#define FB_T0() do { } while (0)
+#define FB_ACC(var) do { } while (0)
+#endif
+
+template <bool SPLIT, int ACT, bool WSTAT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
-                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
-                const __grid_constant__ CUtensorMap map_cb, const Params p) {
-  using S = Smem;
+                const __grid_constant__ CUtensorMap map_w, const Params p) {
+  using S = Smem<WSTAT>;
+  constexpr int NST = S::NSTAGE;
+  static_assert(!(SPLIT && WSTAT), "the weight-stationary form is a bf16-mode kernel");
   pdl_trigger();
+#ifdef FB_DIAG
+  const long long t_start = clock64();
+  long long w_full = 0, w_tempty = 0, w_empty = 0, w_tfull = 0, e_busy = 0;
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -143,15 +172,12 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w) : "memory");
     if (p.KB2) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a2) : "memory");
   }
-  if (warp == 2 && lane == 0) {
-    if (p.has_c) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_c) : "memory");
-    if (p.has_cb) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_cb) : "memory");
-  }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       // tempty of the leader collects the epilogue warps of BOTH CTAs
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
+      mbar_init(wfull, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -163,57 +189,88 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   cluster_sync_all();               // the peer's barriers are initialised before anything is signalled on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles_n = p.N / BN;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // tile schedule.  Streaming form: tile = pair, pair + n_pairs, ... over (row block, column tile) with the column tile fastest.
+  // Weight-stationary form: the pair keeps column tile pair % n_tiles_n and walks the row blocks pair / n_tiles_n, + n_pairs /
+  // n_tiles_n, ... (the launch sizes the grid to a multiple of n_tiles_n pairs).
+  const int ppn = WSTAT ? n_pairs / n_tiles_n : 1;
+  const int nt_fixed = WSTAT ? pair % n_tiles_n : 0;
+  if (WSTAT && warp == 0 && lane == 0) {
+    // resident weight tile: this CTA's 128 of the 256 rows, all k-slabs, completion on the leader's wfull.  Requested before the wait
+    // on the previous grid when the caller vouches for the weights (w_static): they then arrive while that grid drains.
+    if (p.w_static) {
+      if (leader) mbar_expect_tx(wfull, 2 * KB * S::B_BYTES);
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d_pair(&map_w, wfull, smem + S::W_OFF + kb * S::B_BYTES, kb * BK, nt_fixed * BN + (int)rank * BNH);
+    }
+  }
   pdl_wait();
+  if (WSTAT && warp == 0 && lane == 0 && !p.w_static) {
+    if (leader) mbar_expect_tx(wfull, 2 * KB * S::B_BYTES);
+    for (int kb = 0; kb < KB; ++kb)
+      tma_load_2d_pair(&map_w, wfull, smem + S::W_OFF + kb * S::B_BYTES, kb * BK, nt_fixed * BN + (int)rank * BNH);
+  }
   int M = p.M;
   if (p.m_dev) M = min(M, *p.m_dev);
-  const int n_tiles_n = p.N / BN;
-  const int n_tiles = ((M + PM - 1) / PM) * n_tiles_n;
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_rb = (M + PM - 1) / PM;
+  const int n_tiles = n_rb * n_tiles_n;
+  int my_tiles = 0;
+  if (WSTAT) { const int rb0 = pair / n_tiles_n; my_tiles = rb0 < n_rb ? (n_rb - rb0 + ppn - 1) / ppn : 0; }
+  else { my_tiles = pair < n_tiles ? (n_tiles - pair + n_pairs - 1) / n_pairs : 0; }
+  // lt-th tile of this pair -> (row block, column tile)
+  auto sched = [&](int lt, int& rb, int& nt) {
+    if (WSTAT) { rb = pair / n_tiles_n + lt * ppn; nt = nt_fixed; }
+    else { const int tile = pair + lt * n_pairs; rb = tile / n_tiles_n; nt = tile % n_tiles_n; }
+  };
 
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs) =====
+  if (warp < PRODUCERS) {
+    // ===== TMA producers (both CTAs): producer `warp` issues the k-slabs it, it + PRODUCERS, ... of the CTA's tile sequence =====
     if (lane == 0) {
-      int it = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-        const int m0 = (tile / n_tiles_n) * PM + (int)rank * BM;
-        const int n0 = (tile % n_tiles_n) * BN + (int)rank * BNH;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + S::A_BYTES;
-          if (leader) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
-          if (SPLIT) {
-            const int j = kb / p.KB1, r = kb - j * p.KB1;
-            tma_load_2d_pair(&map_a, &full[s], a_dst, (split_plane_a(j, p.nprod) * p.KB1 + r) * BK, m0);
-            tma_load_2d_pair(&map_w, &full[s], b_dst, (split_plane_w(j, p.nprod) * p.KB1 + r) * BK, n0);
-            continue;
-          }
-          if (kb < p.KB1) tma_load_2d_pair(&map_a, &full[s], a_dst, kb * BK, m0);
-          else tma_load_2d_pair(&map_a2, &full[s], a_dst, (kb - p.KB1) * BK, m0);
-          tma_load_2d_pair(&map_w, &full[s], b_dst, kb * BK, n0);
+      const int total = my_tiles * KB;
+      for (int it = warp; it < total; it += PRODUCERS) {
+        const int lt = it / KB, kb = it - lt * KB;
+        int rb, nt;
+        sched(lt, rb, nt);
+        const int m0 = rb * PM + (int)rank * BM;
+        const int n0 = nt * BN + (int)rank * BNH;
+        const int s = it % NST;
+        const uint32_t ph = (it / NST) & 1;
+        { FB_T0(); mbar_wait(&empty[s], ph ^ 1); FB_ACC(w_empty); }
+        uint8_t* a_dst = smem + S::RING_OFF + s * S::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + S::A_BYTES;
+        if (leader) mbar_expect_tx(&full[s], 2 * S::STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
+        if (SPLIT) {
+          const int j = kb / p.KB1, r = kb - j * p.KB1;
+          tma_load_2d_pair(&map_a, &full[s], a_dst, (split_plane_a(j, p.nprod) * p.KB1 + r) * BK, m0);
+          tma_load_2d_pair(&map_w, &full[s], b_dst, (split_plane_w(j, p.nprod) * p.KB1 + r) * BK, n0);
+          continue;
         }
+        if (kb < p.KB1) tma_load_2d_pair(&map_a, &full[s], a_dst, kb * BK, m0);
+        else tma_load_2d_pair(&map_a2, &full[s], a_dst, (kb - p.KB1) * BK, m0);
+        if (!WSTAT) tma_load_2d_pair(&map_w, &full[s], b_dst, kb * BK, n0);
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ===== MMA issuer (leader CTA only) =====
     if (leader && lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
-      int it = 0, lt = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
+      int it = 0;
+      if (WSTAT) mbar_wait(wfull, 0);
+      for (int lt = 0; lt < my_tiles; ++lt) {
         const int a = lt & 1;
-        mbar_wait(&tempty[a], ((lt >> 1) & 1) ^ 1);   // both epilogues have drained this accumulator stage
+        { FB_T0(); mbar_wait(&tempty[a], ((lt >> 1) & 1) ^ 1); FB_ACC(w_tempty); }   // both epilogues have drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
+          const int s = it % NST;
+          const uint32_t ph = (it / NST) & 1;
+          { FB_T0(); mbar_wait(&full[s], ph); FB_ACC(w_full); }
           tcgen05_fence_after();
-          const uint8_t* a_src = smem + s * S::STAGE_BYTES;
-          const uint64_t adesc = make_smem_desc(a_src), bdesc = make_smem_desc(a_src + S::A_BYTES);
+          const uint8_t* a_src = smem + S::RING_OFF + s * S::STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(a_src);
+          const uint64_t bdesc = make_smem_desc(WSTAT ? smem + S::W_OFF + kb * S::B_BYTES : a_src + S::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_pair(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           umma_commit_pair(&empty[s]);
@@ -228,21 +285,22 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // sit in its own slice of shared memory and are read as warp-uniform 16-byte loads (one LDS.128 per four columns) -- the
     // lane-owns-a-column + shuffle form cost one SHFL per element and vector, a third of the epilogue's instructions.
     // bf16 SiLU: x silu = h + h tanh(h), h = (acc + b) / 2 = fma(acc, 0.5, b / 2): the stored vector is b / 2.
-    const int e = warp - 2;                 // 0..7
+    const int e = warp - EPI_WARP0;         // 0..7
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = e >> 2;                // column half of the tile
     constexpr int COLS = BN / 2;            // columns per warp
     constexpr int NCH = COLS / 32;          // 32-column pieces per warp and tile
-    uint8_t* const slots = smem + S::STAGING_OFF + e * NS * SLOT;
     float* const vb = reinterpret_cast<float*>(smem + S::VEC_OFF) + e * 2 * VEC;
     float* const vd = vb + VEC;
     const bool use_dot = p.dotv != nullptr;
     constexpr bool HALF_BIAS = ACT == FB_ACT_SILU && !SPLIT;
-    int lt = 0, vec_n0 = -1;
-    for (int tile = pair; tile < n_tiles; tile += n_pairs, ++lt) {
+    int vec_n0 = -1;
+    for (int lt = 0; lt < my_tiles; ++lt) {
       const int a = lt & 1;
-      const int m0 = (tile / n_tiles_n) * PM + (int)rank * BM;
-      const int n0 = (tile % n_tiles_n) * BN;
+      int rb, nt;
+      sched(lt, rb, nt);
+      const int m0 = rb * PM + (int)rank * BM;
+      const int n0 = nt * BN;
       const int lrow0 = m0 + q * 32;
       const bool rows_live = lrow0 < M;
       const int colbase = n0 + half * COLS;
@@ -255,9 +313,10 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (use_dot) reinterpret_cast<float4*>(vd)[lane] = ldg4(p.dotv + colbase + 4 * lane);
         __syncwarp();
       }
-      if (lane == 0) bulk_wait_read0();
-      __syncwarp();
-      mbar_wait(&tfull[a], (lt >> 1) & 1);
+      { FB_T0(); mbar_wait(&tfull[a], (lt >> 1) & 1); FB_ACC(w_tfull); }
+#ifdef FB_DIAG
+      const long long t_busy0 = clock64();
+#endif
       tcgen05_fence_after();
       float ds0 = 0.f, ds1 = 0.f, ds2 = 0.f, ds3 = 0.f;
       // TMEM loads are software-pipelined: the load of chunk ch+1 is in flight while chunk ch is processed
@@ -313,75 +372,95 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             ds2 = fmaf(d4.z, o[4 * j + 2], ds2); ds3 = fmaf(d4.w, o[4 * j + 3], ds3);
           }
         }
+        // rows go straight from registers to global memory: 32 consecutive columns of the thread's row = four (fp32) or two (bf16)
+        // full 32-byte sectors per 256-bit store; the staging boxes of the TMA-store epilogue gave their 64 KB to the operand ring
         const int ncol0 = n0 + c;
-        const bool want_c = p.has_c && !(p.n_split > 0 && ncol0 >= p.n_split);
-        const bool want_cb = p.has_cb && !(p.n_split > 0 && ncol0 < p.n_split);
-        uint8_t* const fs = slots + (ch & 1) * SLOT;
-        uint8_t* const bs = slots + ((ch >> 1) & 1) * SLOT;
-        if (want_c) {
-          if (lane == 0) bulk_wait_read1();
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(fs + sw_off(lane, j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) tma_store_2d(&map_c, fs, ncol0, lrow0);
-        }
-        if (want_cb) {
-          if ((ch & 1) == 0) { if (lane == 0) bulk_wait_read1(); __syncwarp(); }
+        const bool want_c = p.C != nullptr && !(p.n_split > 0 && ncol0 >= p.n_split);
+        const bool want_cb = p.Cb != nullptr && !(p.n_split > 0 && ncol0 < p.n_split);
+        const int row = lrow0 + lane;
+        if (want_c && row < M) {
+          float* dst = p.C + (size_t)row * p.ldc + ncol0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(o[8 * j], o[8 * j + 1]), t1 = __floats2bfloat162_rn(o[8 * j + 2], o[8 * j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(o[8 * j + 4], o[8 * j + 5]), t3 = __floats2bfloat162_rn(o[8 * j + 6], o[8 * j + 7]);
-            u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
-            u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(bs + sw_off(lane, (ch & 1) * 4 + j)) = u;
+            uint32_t w8[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) w8[t] = __float_as_uint(o[8 * j + t]);
+            st_global_256(dst + 8 * j, w8);
           }
-          if (ch & 1) {
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) tma_store_2d(&map_cb, bs, ncol0 - 32 - (p.n_split > 0 ? p.n_split : 0), lrow0);
+        }
+        if (want_cb && row < M) {
+          bf16* dst = p.Cb + (size_t)row * p.ldcb + (ncol0 - (p.n_split > 0 ? p.n_split : 0));
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t w8[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(o[16 * j + 2 * t], o[16 * j + 2 * t + 1]);
+              w8[t] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            st_global_256(dst + 16 * j, w8);
           }
         }
       }
       if (use_dot && lrow0 + lane < M) {
         // two warps (column halves) share a row: partial index = 2 * n_tile + half
-        p.dot_out[(size_t)((tile % n_tiles_n) * 2 + half) * p.dot_stride + lrow0 + lane] = (ds0 + ds1) + (ds2 + ds3);
+        p.dot_out[(size_t)(nt * 2 + half) * p.dot_stride + lrow0 + lane] = (ds0 + ds1) + (ds2 + ds3);
       }
+#ifdef FB_DIAG
+      e_busy += clock64() - t_busy0;
+#endif
     }
-    if (lane == 0) bulk_wait_read0();
   }
+#ifdef FB_DIAG
+  if (p.dbg && lane == 0) {
+    long long* d = p.dbg + (size_t)blockIdx.x * 8;
+    if (warp == MMA_WARP && leader) { d[0] = w_full; d[1] = w_tempty; }
+    if (warp == 0) d[2] = w_empty;
+    if (warp == EPI_WARP0) { d[3] = w_tfull; d[4] = e_busy; }
+  }
+#endif
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();               // no CTA of the pair leaves (or frees TMEM) while the other may still signal it
-  if (warp == 1) {
+#ifdef FB_DIAG
+  if (p.dbg && threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 8 + 5] = clock64() - t_start;
+#endif
+  if (warp == MMA_WARP) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
 static int launch(const GemmArgs& g, cudaStream_t st) {
-  using S = Smem;
-  static_assert(S::TOTAL <= 232448, "shared memory budget");
+  static_assert(Smem<false>::TOTAL <= 232448 && Smem<true>::TOTAL <= 232448, "shared memory budget");
   static int num_sms = 0;
   const bool split = g.nprod > 0;
-  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Params);
-  static const Kern table[2][3] = {
-      {gemm_tc4_kernel<false, FB_ACT_NONE>, gemm_tc4_kernel<false, FB_ACT_SILU>, gemm_tc4_kernel<false, FB_ACT_RELU>},
-      {gemm_tc4_kernel<true, FB_ACT_NONE>, gemm_tc4_kernel<true, FB_ACT_SILU>, gemm_tc4_kernel<true, FB_ACT_RELU>}};
-  static unsigned long long optins[2][3] = {{0, 0, 0}, {0, 0, 0}};
-  if (g.act < 0 || g.act > 2) return FB_ERR_BAD_ARG;
-  Kern kern = table[split ? 1 : 0][g.act];
-  if (!ensure_smem_optin(kern, S::TOTAL, optins[split ? 1 : 0][g.act])) return FB_ERR_CUDA;
   if (num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  CUtensorMap ma, ma2, mw, mc, mcb;
+  const int n_tiles_n = g.N / BN, n_rb = (g.M + PM - 1) / PM;
   const int K = g.nprod ? 3 * g.K1 : g.K1 + g.K2;   // split precision: three bf16 planes of K1 columns each
+  // weight-stationary form: bf16 mode, K <= 512, at least one pair per column tile
+#ifdef FB_DIAG
+  static const bool wstat_on = [] { const char* e = getenv("FB_WSTAT"); return !(e && atoi(e) == 0); }();
+#else
+  const bool wstat_on = true;
+#endif
+  const bool wstat = wstat_on && !split && K <= KB_MAX * BK && n_tiles_n <= num_sms / 2;
+  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, Params);
+  static const Kern table[3][3] = {
+      {gemm_tc4_kernel<false, FB_ACT_NONE, false>, gemm_tc4_kernel<false, FB_ACT_SILU, false>, gemm_tc4_kernel<false, FB_ACT_RELU, false>},
+      {gemm_tc4_kernel<true, FB_ACT_NONE, false>, gemm_tc4_kernel<true, FB_ACT_SILU, false>, gemm_tc4_kernel<true, FB_ACT_RELU, false>},
+      {gemm_tc4_kernel<false, FB_ACT_NONE, true>, gemm_tc4_kernel<false, FB_ACT_SILU, true>, gemm_tc4_kernel<false, FB_ACT_RELU, true>}};
+  static unsigned long long optins[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  if (g.act < 0 || g.act > 2) return FB_ERR_BAD_ARG;
+  const int v = wstat ? 2 : (split ? 1 : 0);
+  Kern kern = table[v][g.act];
+  const int smem_bytes = wstat ? Smem<true>::TOTAL : Smem<false>::TOTAL;
+  if (!ensure_smem_optin(kern, smem_bytes, optins[v][g.act])) return FB_ERR_CUDA;
+  CUtensorMap ma, ma2, mw;
   if (!tc_make_map(&ma, g.A, (uint64_t)g.M, (uint64_t)(g.nprod ? K : g.K1), (uint64_t)g.lda, BM)) return FB_ERR_CUDA;
   if (g.K2 > 0) {
     if (!tc_make_map(&ma2, g.A2, (uint64_t)g.M, (uint64_t)g.K2, (uint64_t)g.lda2, BM)) return FB_ERR_CUDA;
@@ -389,17 +468,21 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
     ma2 = ma;
   }
   if (!tc_make_map(&mw, g.W, (uint64_t)g.N, (uint64_t)K, (uint64_t)K, BNH)) return FB_ERR_CUDA;
-  mc = mcb = ma;   // placeholders for absent operands (never dereferenced)
-  const int nc = g.n_split > 0 ? g.n_split : g.N, ncb = g.n_split > 0 ? g.N - g.n_split : g.N;
-  if (g.C && !tc_make_map_out(&mc, g.C, true, (uint64_t)g.M, (uint64_t)nc, (uint64_t)g.ldc)) return FB_ERR_CUDA;
-  if (g.Cb && !tc_make_map_out(&mcb, g.Cb, false, (uint64_t)g.M, (uint64_t)ncb, (uint64_t)g.ldcb)) return FB_ERR_CUDA;
   Params p;
   p.M = g.M; p.N = g.N; p.KB1 = g.K1 / BK; p.KB2 = g.K2 / BK; p.nprod = g.nprod; p.exact_act = g.exact_act ? 1 : 0;
-  p.bias = g.bias; p.act = g.act; p.has_c = g.C != nullptr; p.has_cb = g.Cb != nullptr;
-  p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride; p.n_split = g.n_split; p.m_dev = g.m_dev; p.drop = g.drop;
-  const int tiles = ((g.M + PM - 1) / PM) * (g.N / BN);
-  const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  fb_launch(kern, dim3(2 * pairs), dim3(THREADS), S::TOTAL, st, ma, ma2, mw, mc, mcb, p);
+  p.bias = g.bias; p.act = g.act; p.C = g.C; p.ldc = g.ldc; p.Cb = (bf16*)g.Cb; p.ldcb = g.ldcb;
+  p.dotv = g.dotv; p.dot_out = g.dot_out; p.dot_stride = g.dot_stride; p.n_split = g.n_split; p.m_dev = g.m_dev; p.drop = g.drop; p.dbg = g_tc_dbg;
+  p.w_static = g.w_static ? 1 : 0;
+  int pairs;
+  if (wstat) {
+    int ppn = (num_sms / 2) / n_tiles_n;       // pairs per column tile
+    if (ppn > n_rb) ppn = n_rb;
+    pairs = ppn * n_tiles_n;
+  } else {
+    const int tiles = n_rb * n_tiles_n;
+    pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  }
+  fb_launch(kern, dim3(2 * pairs), dim3(THREADS), smem_bytes, st, ma, ma2, mw, p);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -420,6 +503,9 @@ int gemm_tc4_launch(const GemmArgs& g, cudaStream_t st) {
   if (gemm_tc2_bn(g.M, g.N) != 256 || g.res || (g.C && g.Cb)) return FB_ERR_UNSUPPORTED;
   if (g.m_dev && (g.C || g.Cb)) return FB_ERR_UNSUPPORTED;
   if (g.n_split > 0 && (g.n_split % 64)) return FB_ERR_UNSUPPORTED;
+  // 256-bit row stores: 32-byte aligned rows
+  if (g.C && ((g.ldc % 8) || ((uintptr_t)g.C & 31))) return FB_ERR_UNSUPPORTED;
+  if (g.Cb && ((g.nprod ? (g.ldcb % 8) : (g.ldcb % 16)) || ((uintptr_t)g.Cb & 31))) return FB_ERR_UNSUPPORTED;
   return tc4::launch(g, st);
 }
 

@@ -5,8 +5,9 @@
 // into pre-multiplied weights (forward.cu: "folded" sequences) turns dependent launches into independent problems over different
 // operands, row ranges, K and epilogues; this kernel runs such a group as ONE persistent grid over the union of their 128x128 tiles.
 //
-// Structure = v3 (gemm_tc3.cu): warp 0 TMA producer (smem ring across tiles), warp 1 MMA issuer (two TMEM accumulator stages),
-// warps 2-9 epilogue (thread = row, swizzled staging boxes, TMA stores, residual through TMA).  Differences:
+// Structure = v3 (gemm_tc3.cu) with the producer role spread over three warps: warps 0-2 TMA producers (k-slab i of the CTA's tile
+// sequence issued by producer i % 3 into ring slot i % 4), warp 3 MMA issuer (two TMEM accumulator stages), warps 4-11 epilogue
+// (thread = row, swizzled staging boxes, TMA stores, residual through TMA).  Differences to v3:
 //   * every problem brings its own operand / output descriptors, k-slab counts and epilogue (bias, activation, residual, fp32 / bf16 /
 //     column-routed outputs); a tile index decodes to (problem, m0, n0) through the problems' tile offsets;
 //   * the descriptors travel inside ONE __grid_constant__ parameter block (24 x 128 B);
@@ -32,7 +33,10 @@ constexpr int BN = 128;
 constexpr int STAGES = 4;
 constexpr int NS = 3;                           // staging boxes per epilogue warp: two fp32 (also the residual landing zone) + one bf16
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + EPI_WARPS * 32;   // 320
+constexpr int PRODUCERS = 3;                    // TMA-issuing warps (see gemm_tc4.cu: one issuing thread is served at ~32 B/clk per SM)
+constexpr int MMA_WARP = PRODUCERS;             // warp 3
+constexpr int EPI_WARP0 = PRODUCERS + 1;        // warps 4..11
+constexpr int THREADS = (PRODUCERS + 1 + EPI_WARPS) * 32;   // 384
 constexpr int SLOT = 4096;                      // one staging box: 32 rows x 128 bytes
 
 struct Prob {
@@ -99,14 +103,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
       if (p.q[i].KB2) prefetch_map(&p.a2[i]);
     }
   }
-  if (warp == 2 && lane == 0) {
+  if (warp == EPI_WARP0 && lane == 0) {
     for (int i = 0; i < p.np; ++i) {
       if (p.q[i].has_c) prefetch_map(&p.c[i]);
       if (p.q[i].has_cb) prefetch_map(&p.cb[i]);
       if (p.q[i].has_res) prefetch_map(&p.res[i]);
     }
   }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
@@ -122,23 +126,28 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // weight slabs of this CTA's first tile: requested before the wait on the previous grid (see the header)
-  int pre = 0;
-  if (warp == 0 && lane == 0 && p.prefetch_w && (int)blockIdx.x < n_tiles) {
-    int m0, n0;
-    const int pi = decode(blockIdx.x, m0, n0);
-    const int KB = p.q[pi].KB1 + p.q[pi].KB2;
-    pre = KB < STAGES ? KB : STAGES;
-    for (int kb = 0; kb < pre; ++kb) {
-      mbar_expect_tx(&full[kb], S::STAGE_BYTES);
-      tma_load_2d(&p.w[pi], &full[kb], smem + kb * S::STAGE_BYTES + S::A_BYTES, kb * BK, n0);
+  // weight slab of each producer's FIRST k-slab: requested before the wait on the previous grid (see the header)
+  int pre_it = -1;
+  if (warp < PRODUCERS && lane == 0 && p.prefetch_w) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles && pre_it < 0 && it < STAGES; tile += gridDim.x) {
+      int m0, n0;
+      const int pi = decode(tile, m0, n0);
+      const int KB = p.q[pi].KB1 + p.q[pi].KB2;
+      for (int kb = 0; kb < KB && it < STAGES; ++kb, ++it) {
+        if (it % PRODUCERS != warp) continue;
+        mbar_expect_tx(&full[it], S::STAGE_BYTES);                  // first pass over the ring: slot it is free
+        tma_load_2d(&p.w[pi], &full[it], smem + it * S::STAGE_BYTES + S::A_BYTES, kb * BK, n0);
+        pre_it = it;
+        break;
+      }
     }
   }
   // everything above touched only on-chip state and the weights; activations are produced by the previous kernel in the stream
   pdl_wait();
 
-  if (warp == 0) {
-    // ===== TMA producer =====
+  if (warp < PRODUCERS) {
+    // ===== TMA producers: producer `warp` issues the k-slabs it with it % PRODUCERS == warp of the CTA's tile sequence =====
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -146,10 +155,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
         const int pi = decode(tile, m0, n0);
         const int KB1 = p.q[pi].KB1, KB = KB1 + p.q[pi].KB2;
         for (int kb = 0; kb < KB; ++kb, ++it) {
+          if (it % PRODUCERS != warp) continue;
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-          const bool armed = it < pre;          // barrier armed and W slab already in flight
+          const bool armed = it == pre_it;          // barrier armed and W slab already in flight
           if (!armed) {
             mbar_wait(&empty[s], ph ^ 1);
             mbar_expect_tx(&full[s], S::STAGE_BYTES);
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
     }
   } else {
     // ===== epilogue =====
-    const int e = warp - 2;                 // 0..7
+    const int e = warp - EPI_WARP0;         // 0..7
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = e >> 2;                // column half of the tile
     constexpr int COLS = BN / 2;            // columns per warp
@@ -287,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
