@@ -115,9 +115,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
-// 32 bytes = one full sector per lane
+// 32 bytes = one full sector per lane.  L2::evict_last: a row's 128-byte line is completed by two stores a chunk apart (and consumed
+// from L2 by the next kernel); with the default policy the half-written lines were evicted early and written twice -- 75.5 MB of
+// DRAM writes for 46 MB of output in the cold ncu capture (profiles/r2r_tc4_ncu_summary.txt)
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+  asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 // four consecutive floats of a read-only vector (16-byte load when the address allows it)
