@@ -141,7 +141,8 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
     p.hidden, p.n_layers, p.n_iter = hidden, cfg["n_layers"], cfg["n_iter"]
     p.n_bond, p.n_las = bonds.shape[1], las.shape[1]
     p.E_ctx, p.cap_int, p.bf16_mode = 0, lay.cap_int, mode
-    p.n_mv = lay.n_mv
+    # moving-rows subset of the out_layer (fb_model_params.n_mv); `module.moving_rows = False` evaluates every out_layer on all edges
+    p.n_mv = lay.n_mv if getattr(module, "moving_rows", True) else 0
     p.fb_atom, p.fb_res = lay.fb_atom, lay.fb_res
     p.max_c, p.max_p = lay.max_c, lay.max_p
     p.intra_cutoff, p.inter_cutoff = cfg["intra_cutoff"], cfg["inter_cutoff"]

@@ -198,3 +198,55 @@ def test_sharded_forward_real_module_single_rank():
     Xs, Hs = m(**sub)
     Xf, Hf = shard.sharded_forward(m, fa)
     assert rel_err(Xs, Xf[idx]) < 1e-5 and rel_err(Hs, Hf[idx]) < 1e-5
+
+
+def test_derived_weight_slots_match_float64_products():
+    """fb_derive_weights: every folded slot [W_b | W_b W_a] / bias W_b b_a + b_b against float64 products of the base slots"""
+    from fabind_b200.weights import slots, derive_on_device
+    from fabind_b200 import _lib
+    H, L = 128, 2
+    l = _lib.lib()
+    n = l.fb_weight_arena_elems_f(H, L, 0)
+    g = torch.Generator().manual_seed(5)
+    arena = (torch.randn(n, generator=g) * 0.1).cuda()
+    tab = {name: (r, c, off) for name, r, c, off in slots(H, L, 0, derived=True)}
+    base = {name for name, *_ in slots(H, L, 0)}
+    assert any(k.rpartition(".")[2].startswith("f_") for k in tab) and not any(k.rpartition(".")[2].startswith("f_") for k in base)
+    before = arena.clone()
+    derive_on_device(arena, H, L, 0)
+    torch.cuda.synchronize()
+    for name in base:                                   # base slots are not touched
+        r, c, off = tab[name]
+        assert torch.equal(arena[off:off + r * c], before[off:off + r * c]), name
+    A = arena.double().cpu()
+    get = lambda name: A[tab[name][2]:tab[name][2] + tab[name][0] * tab[name][1]].view(tab[name][0], tab[name][1])
+    HD = 128
+    for i in range(L):
+        a, gcl = f"att{i}.", f"gcl{i}."
+        checks = [
+            (a + "f_cac_w", a + "f_cac_b", get(a + "ca_c_w"), get(a + "ca_c_b")[0], get(gcl + "n2_w"), get(gcl + "n2_b")[0], 0),
+            (a + "f_cap_w", a + "f_cap_b", get(a + "ca_p_w"), get(a + "ca_p_b")[0], get(gcl + "n2_w"), get(gcl + "n2_b")[0], 0),
+            (a + "f_l3_w", a + "f_l3_b", get(a + "ca_p2_w"), None, get(a + "o_p_w"), get(a + "o_p_b")[0], 0),
+            (a + "f_l3_w", a + "f_l3_b", get(a + "tp1_w"), get(a + "tp1_b")[0], get(a + "o_p_w"), get(a + "o_p_b")[0], 2 * HD),
+            (a + "f_l5_w", a + "f_l5_b", get(a + "tc1_w"), get(a + "tc1_b")[0], get(a + "o_c_w"), get(a + "o_c_b")[0], 0),
+            (a + "f_qkc_w", a + "f_qkc_b", get(a + "qk_w"), get(a + "qk_b")[0], get(a + "tc2_w"), get(a + "tc2_b")[0], 0),
+        ]
+        for wn, bn, Wb, bb, Wa, ba, row0 in checks:
+            R, K = Wb.shape
+            want_w = torch.cat([Wb, Wb @ Wa], 1)
+            want_b = Wb @ ba + (bb if bb is not None else 0)
+            got_w, got_b = get(wn)[row0:row0 + R], get(bn)[0][row0:row0 + R]
+            assert float((got_w - want_w).abs().max()) <= 1e-6 * float(want_w.abs().max()) + 1e-9, wn
+            assert float((got_b - want_b).abs().max()) <= 1e-6 * float(want_b.abs().max()) + 1e-9, bn
+
+
+@pytest.mark.parametrize("path", [p for p in golden_files() if "_it" in p and "_it1" not in p][:3], ids=lambda p: p.split("/")[-1][:-3])
+def test_moving_rows_subset_is_exact(path):
+    """out_layer of the non-final iterations on the context edges INTO the masked rows only (fb_model_params.n_mv) == on all edges:
+    identical X and H in fp32 mode (the FFMA kernel computes every row independently of the others)"""
+    g, r, b, sd, cfg = load_golden(path)
+    m = _model(r["hidden"], r["n_layers"], r["n_iter"], sd, precision="fp32")
+    X1, H1 = _run(m, b)
+    m.moving_rows = False
+    X0, H0 = _run(m, b)
+    assert torch.equal(X1, X0) and torch.equal(H1, H0)

@@ -154,3 +154,38 @@ def test_fast_packer_matches_the_generic_packer():
         assert set(g0) == set(g1) and flat.numel() == sum(v.numel() for v in g0.values())
         for k in g0:
             assert float((g0[k] - g1[k]).abs().max()) <= 2e-6 * float(g0[k].abs().max()) + 1e-7, k
+
+
+def test_layout_cache_and_moving_rows_count():
+    """build_layout is cached per batch object (same tensors, unchanged versions) and counts the masked rows (fb_model_params.n_mv)"""
+    from fabind_b200.synthetic import make_batch
+    from fabind_b200.layout import build_layout
+    b = make_batch(n_complexes=3, n_c=12, n_p=40, embed=32, seed=4)
+    l1 = build_layout(b.batch_id, b.segment_id, b.is_global, b.mask, "cpu")
+    assert build_layout(b.batch_id, b.segment_id, b.is_global, b.mask, "cpu") is l1
+    assert l1.n_mv == int(b.mask.sum()) == 3 * (12 + 2)          # ligand atoms + both global nodes (model.py:261-262)
+    b.mask[0] = ~b.mask[0]                                        # in-place edit: version bump -> rebuilt
+    l2 = build_layout(b.batch_id, b.segment_id, b.is_global, b.mask, "cpu")
+    assert l2 is not l1 and l2.n_mv == int(b.mask.sum())
+    l3 = build_layout(b.batch_id.clone(), b.segment_id, b.is_global, b.mask, "cpu")     # another tensor object: rebuilt
+    assert l3 is not l2 and l3.n_mv == l2.n_mv
+
+
+def test_derived_slots_are_hidden_from_the_packers():
+    """weights.slots() lists the library's derived (f_*) slots only on request; the packed arena leaves them zero (fb_derive_weights
+    fills them on the device) and all slots stay disjoint"""
+    import torch
+    from fabind_b200 import _lib
+    from fabind_b200.weights import slots
+    H, L = 64, 2
+    base, full = slots(H, L, 0), slots(H, L, 0, derived=True)
+    names = {n for n, *_ in base}
+    extra = [(n, r, c, o) for n, r, c, o in full if n not in names]
+    assert extra and all(n.rpartition(".")[2].startswith("f_") for n, *_ in extra)
+    assert not any(n.rpartition(".")[2].startswith("f_") for n in names)
+    end = 0
+    for n, r, c, o in full:
+        assert o >= end, n
+        end = o + r * c
+    assert end <= _lib.lib().fb_weight_arena_elems_f(H, L, 0)
+    assert slots(H, L, 1, derived=True) == slots(H, L, 1)        # FABind+ layout: no folded slots
