@@ -77,7 +77,7 @@ constexpr int QKX = 128; // extra columns of the stacked q|k GEMM: inter_layer l
 // ------------------------------------------------------------------------------------------------
 struct Slot { std::string name; int64_t rows, cols, off; };
 
-struct GclW { int64_t e1_rc, e1_rad, e1_b, e2_w, e2_b, c1_w, c1_b, c2_w, n1_w, n1_b, n2_w, n2_b; };
+struct GclW { int64_t e1_rc, e1_rad, e1_b, e2_w, e2_b, c1_w, c1_b, c2_w, n1_w, n1_b, n2_w, n2_b, f_e1b; };
 struct AttW {
   int64_t ca_c_w, ca_c_b, ca_p_w, ca_p_b, ca_p2_w, o_p_w, o_p_b, o_c_w, o_c_b;
   int64_t tp1_w, tp1_b, tp2_w, tp2_b, tc1_w, tc1_b, tc2_w, tc2_b;
@@ -134,6 +134,8 @@ static void build_weights(int H, int L, ModelW& w) {
     g.c1_w = add(p + "c1_w", H, H); g.c1_b = add(p + "c1_b", 1, H); g.c2_w = add(p + "c2_w", 1, H);
     g.n1_w = add(p + "n1_w", H, 2 * H); g.n1_b = add(p + "n1_b", 1, H);
     g.n2_w = add(p + "n2_w", H, H); g.n2_b = add(p + "n2_b", 1, H);
+    // derived: [e1_b | 0], the bias of the stacked per-node projection GEMM -- the edge kernel then adds nothing but the radial term
+    g.f_e1b = add(p + "f_e1b", 1, 2 * H);
     w.gcl.push_back(g);
   }
   for (int i = 0; i < L; ++i) {
@@ -544,9 +546,10 @@ struct Run {
     const int* ecol = mv_only ? g.mv_ecol : g.ctx_col;
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
     gemm_cat = CAT_GEMM_NODE;
-    if (!Pn_pre) gemm(hT_in, H, H, gw.e1_rc, 2 * H, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * H);
+    // the first edge-MLP Linear per node: P[:, 0:H] = h W_row^T + b1, P[:, H:2H] = h W_col^T (bias [b1 | 0] = derived slot f_e1b)
+    if (!Pn_pre) gemm(hT_in, H, H, gw.e1_rc, 2 * H, gw.f_e1b, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * H);
     stage(CAT_EDGE_ELEMWISE, [&] {
-      return gcl_edge_pre(E, H, erow, ecol, g.node_cplx, Pn, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_b), b.A1, bf, st,
+      return gcl_edge_pre(E, H, erow, ecol, g.node_cplx, Pn, b.radc, b.normc, F(gw.e1_rad), nullptr, b.A1, bf, st,
                           mv_only ? g.mv_emap : nullptr);
     });
     gemm_cat = CAT_GEMM_EDGE;
@@ -864,7 +867,7 @@ struct Run {
     if (hoist) {
       gemm_cat = CAT_GEMM_NODE;
       gemm(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h0, H, b.h0T, H);
-      gemm(b.h0T, H, H, w.gcl[0].e1_rc, 2 * H, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn0, 2 * H);
+      gemm(b.h0T, H, H, w.gcl[0].e1_rc, 2 * H, w.gcl[0].f_e1b, FB_ACT_NONE, N, nullptr, 0, b.Pn0, 2 * H);
     }
     for (int it = 0; it < p.n_iter; ++it) {
       const bool last = it == p.n_iter - 1;
@@ -1000,6 +1003,12 @@ int32_t fb_derive_weights(float* w32, int32_t hidden, int32_t n_layers, int32_t 
   const ModelW& w = weights_for(hidden, n_layers, flavour);
   cudaStream_t st = (cudaStream_t)stream;
   const int H = hidden;
+  for (int l = 0; l <= n_layers; ++l) {
+    const GclW& g = w.gcl[l];
+    if (cudaMemcpyAsync(w32 + g.f_e1b, w32 + g.e1_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemsetAsync(w32 + g.f_e1b + H, 0, sizeof(float) * H, st) != cudaSuccess)
+      return FB_ERR_CUDA;
+  }
   for (int l = 0; l < n_layers; ++l) {
     const AttW& a = w.att[l];
     const GclW& g = w.gcl[l];

@@ -97,6 +97,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
     return pi;
   };
 
+  // tile of this CTA in round r of the persistent loop: boustrophedon over the CTAs (even rounds ascending, odd rounds descending).
+  // The launch orders the problems by descending K, so round 0 hands the heavy tiles to the low CTAs and the partial last rounds top
+  // up the CTAs that carry the light ones (plain round-robin gave the heavy CTAs the extra tiles too: makespan 3 instead of 2 tile
+  // units for node_mlp.2 + first projections, 6 instead of 5 for the stacked q|k|v group).  -1 = no tile in this round.
+  const int G = gridDim.x, n_rounds = (n_tiles + G - 1) / G;
+  auto tile_at = [&](int r) -> int {
+    const int t = r * G + ((r & 1) ? G - 1 - (int)blockIdx.x : (int)blockIdx.x);
+    return t < n_tiles ? t : -1;
+  };
+
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.np; ++i) {
       prefetch_map(&p.a[i]); prefetch_map(&p.w[i]);
@@ -130,7 +140,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
   int pre_it = -1;
   if (warp < PRODUCERS && lane == 0 && p.prefetch_w) {
     int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles && pre_it < 0 && it < STAGES; tile += gridDim.x) {
+    for (int r = 0; r < n_rounds && pre_it < 0 && it < STAGES; ++r) {
+      const int tile = tile_at(r);
+      if (tile < 0) continue;
       int m0, n0;
       const int pi = decode(tile, m0, n0);
       const int KB = p.q[pi].KB1 + p.q[pi].KB2;
@@ -150,7 +162,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
     // ===== TMA producers: producer `warp` issues the k-slabs it with it % PRODUCERS == warp of the CTA's tile sequence =====
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int r = 0; r < n_rounds; ++r) {
+        const int tile = tile_at(r);
+        if (tile < 0) continue;
         int m0, n0;
         const int pi = decode(tile, m0, n0);
         const int KB1 = p.q[pi].KB1, KB = KB1 + p.q[pi].KB2;
@@ -175,7 +189,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      for (int r = 0; r < n_rounds; ++r) {
+        const int tile = tile_at(r);
+        if (tile < 0) continue;
         int m0, n0;
         const int pi = decode(tile, m0, n0);
         const int KB = p.q[pi].KB1 + p.q[pi].KB2;
@@ -195,6 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[a]);
+        ++lt;
       }
     }
   } else {
@@ -207,8 +224,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
     uint8_t* const slots = smem + S::STAGING_OFF + e * NS * SLOT;
     uint64_t* const rbar = &resbar[e];
     uint32_t rphase = 0;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+    int lt = -1;
+    for (int r = 0; r < n_rounds; ++r) {
+      const int tile = tile_at(r);
+      if (tile < 0) continue;
+      ++lt;
       const int a = lt & 1;
       int m0, n0;
       const int pi = decode(tile, m0, n0);

@@ -203,8 +203,9 @@ __global__ void gcl_edge_pre_kernel(int E, int H, const int* __restrict__ erow, 
   const T* pr = P + (size_t)r * 2 * H;
   const T* pc = P + (size_t)c * 2 * H + H;
   for (int f = lane * 8; f < H; f += 256) {
-    float a[8], b[8], w[8], bb[8], o[8];
-    ld8(pr + f, a); ld8(pc + f, b); ld8(w_rad + f, w); ld8(b1 + f, bb);
+    float a[8], b[8], w[8], bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o[8];
+    ld8(pr + f, a); ld8(pc + f, b); ld8(w_rad + f, w);
+    if (b1) ld8(b1 + f, bb);           // null: the bias is already inside P (added by the projection GEMM)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float t = a[i] + b[i] + fmaf(rn, w[i], bb[i]);

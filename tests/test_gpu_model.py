@@ -221,6 +221,9 @@ def test_derived_weight_slots_match_float64_products():
     A = arena.double().cpu()
     get = lambda name: A[tab[name][2]:tab[name][2] + tab[name][0] * tab[name][1]].view(tab[name][0], tab[name][1])
     HD = 128
+    for pre in [f"gcl{i}." for i in range(L)] + ["out."]:          # [e1_b | 0]: bias of the stacked per-node projection GEMM
+        got = get(pre + "f_e1b")[0]
+        assert torch.equal(got[:H], get(pre + "e1_b")[0]) and float(got[H:].abs().max()) == 0.0
     for i in range(L):
         a, gcl = f"att{i}.", f"gcl{i}."
         checks = [
