@@ -871,8 +871,7 @@ struct Run {
     }
     for (int it = 0; it < p.n_iter; ++it) {
       const bool last = it == p.n_iter - 1;
-      stage(CAT_GRAPH_MISC, [&] { return graph_build_inter(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
-      if (p.stats) cudaMemcpyAsync(p.stats + it, g.int_rowptr + N, sizeof(int), cudaMemcpyDeviceToDevice, st);
+      stage(CAT_GRAPH_MISC, [&] { return graph_build_inter(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st, p.stats ? p.stats + it : nullptr); });
       gemm_cat = CAT_GEMM_NODE;
       cur_it = it; cur_layer = -1;
       if (!hoist) gemm(wd(mk(b.HinT, H, H, w.in_w, H, w.in_b, FB_ACT_NONE, N, b.h, H, b.hT, H), dr(S_IN)));

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) graph_rows_kernel(GraphDev g, const float
 // exclusive scan of deg[0..n) into rowptr[0..n]; single block.  For the inter list it also applies
 // the zero-edge fallback (sets the flag and gives the two designated rows degree 1).
 __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ deg, int* __restrict__ rowptr,
-                                                    int n, int* fallback, int fa, int fr) {
+                                                    int n, int* fallback, int fa, int fr, int* total_out) {
   pdl_entry();
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ deg,
     __syncthreads();
     if (!fb_s) break;
   }
+  if (tid == 0 && total_out) *total_out = rowptr[n];   // (per-iteration edge statistics of the forward: saves a 4-byte copy node)
 }
 
 __global__ void convert_edges_kernel(const long long* __restrict__ e, int n_e, const int* __restrict__ inv,
@@ -280,7 +281,7 @@ int graph_prepare_static(const GraphDev& g, const long long* bonds, const long l
   if (g.n_bond > 0) fb_launch(convert_edges_kernel, dim3((g.n_bond + 255) / 256), dim3(256), 0, st, bonds, g.n_bond, g.inv, g.bond_row, g.bond_col);
   if (g.n_las > 0) fb_launch(convert_edges_kernel, dim3((g.n_las + 255) / 256), dim3(256), 0, st, las, g.n_las, g.inv, g.las_src, g.las_dst);
   fb_launch(las_rows_kernel<false>, dim3(warp_grid(g.N)), dim3(256), 0, st, g);
-  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.las_deg, g.las_rowptr, g.N, nullptr, -1, -1);
+  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.las_deg, g.las_rowptr, g.N, nullptr, -1, -1, nullptr);
   fb_launch(las_rows_kernel<true>, dim3(warp_grid(g.N)), dim3(256), 0, st, g);
   count_launch(3 + (g.n_bond > 0) + (g.n_las > 0));
   FB_CHECK_LAUNCH();
@@ -289,7 +290,7 @@ int graph_prepare_static(const GraphDev& g, const long long* bonds, const long l
 
 int graph_count_ctx(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st) {
   fb_launch(graph_rows_kernel<1, false>, dim3(warp_grid(g.N)), dim3(256), 0, st, g, x, intra, inter);
-  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.ctx_deg, g.ctx_rowptr, g.N, nullptr, -1, -1);
+  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.ctx_deg, g.ctx_rowptr, g.N, nullptr, -1, -1, nullptr);
   count_launch(2);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -302,9 +303,9 @@ int graph_fill_ctx(const GraphDev& g, const float* x, float intra, float inter, 
   return FB_OK;
 }
 
-int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st) {
+int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st, int* total_out) {
   fb_launch(graph_rows_kernel<2, false>, dim3(warp_grid(g.N)), dim3(256), 0, st, g, x, intra, inter);
-  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.int_deg, g.int_rowptr, g.N, g.int_fallback, g.fb_atom, g.fb_res);
+  fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, g.int_deg, g.int_rowptr, g.N, g.int_fallback, g.fb_atom, g.fb_res, total_out);
   fb_launch(graph_rows_kernel<2, true>, dim3(warp_grid(g.N)), dim3(256), 0, st, g, x, intra, inter);
   count_launch(3);
   FB_CHECK_LAUNCH();
@@ -378,7 +379,7 @@ int graph_ref_count(int N, const int* cplx, const int* off, const uint8_t* flags
                                                         nullptr, nullptr, 0, nullptr, 0);
   for (int k = 0; k < 4; ++k)
     fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, deg + (size_t)k * N, rowptr + (size_t)k * (N + 1), N,
-                                    k == 3 ? fallback : nullptr, -1, -1);
+                                    k == 3 ? fallback : nullptr, -1, -1, nullptr);
   count_launch(5);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -390,7 +391,7 @@ int graph_ref_fill(int N, const int* cplx, const int* off, const uint8_t* flags,
                    cudaStream_t st) {
   if (fallback_host) {
     fb_launch(ref_fallback_fix_kernel, dim3(1), dim3(1), 0, st, N, deg, off, flags);
-    fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, deg + (size_t)3 * N, rowptr + (size_t)3 * (N + 1), N, nullptr, -1, -1);
+    fb_launch(scan_kernel, dim3(1), dim3(1024), 0, st, deg + (size_t)3 * N, rowptr + (size_t)3 * (N + 1), N, nullptr, -1, -1, nullptr);
   }
   fb_launch(ref_rows_kernel<true>, dim3(warp_grid(N)), dim3(256), 0, st, N, cplx, off, flags, x, intra, inter, deg, rowptr, cat_base,
                                                        fallback, ctx_out, e_ctx, int_out, e_int);

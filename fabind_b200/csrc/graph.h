@@ -48,7 +48,8 @@ int graph_fill_ctx(const GraphDev& g, const float* x, float intra, float inter, 
 // moving rows: index + compact row pointers (after graph_count_ctx), compact edge lists (after graph_fill_ctx)
 int graph_mv_index(const GraphDev& g, cudaStream_t st);
 int graph_mv_fill(const GraphDev& g, cudaStream_t st);
-int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st);
+// total_out (optional, device): receives the number of interface edges of this build
+int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st, int* total_out = nullptr);
 
 int graph_ref_count(int N, const int* cplx, const int* off, const uint8_t* flags, const float* x,
                     float intra, float inter, int* deg, int* rowptr, int* fallback, cudaStream_t st);
