@@ -688,15 +688,21 @@ struct Run {
 
   // MC_E_GCL (P/models/egnn.py:44-115)
   void run_gcl_plus(const GclPW& gw, const float* x_in, float* x_out, bool need_h) {
-    const int E = p.E_ctx, Dp = dp_of(H);
+    const int Dp = dp_of(H);
+    // coordinates only (out_layer of a non-final iteration): the edges INTO the moving rows, as in run_gcl
+    const bool mv_only = !need_h && mv_ready && p.dropout_p <= 0.f;
+    const int E = mv_only ? p.E_ctx_mv : p.E_ctx;
+    const int n_rows = mv_only ? g.n_mv : N;
+    const int* erow = mv_only ? g.mv_erow : g.ctx_row;
+    const int* ecol = mv_only ? g.mv_ecol : g.ctx_col;
     stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
     // per-node sums of h and h^2: the LayerNorm statistics of [h_row | h_col | radial] are assembled per edge
     stage(CAT_EDGE_ELEMWISE, [&] { return row_stats(b.h, H, N, H, nullptr, b.hstat, false, st); });
     gemm_cat = CAT_GEMM_NODE;
     gemm(b.hT, H, H, gw.e1_rc, 2 * Dp, -1, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * Dp);
     stage(CAT_EDGE_ELEMWISE, [&] {
-      return gcl_edge_pre_plus(E, H, Dp, g.ctx_row, g.ctx_col, g.node_cplx, b.Pn, b.hstat, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_g),
-                               F(gw.e1_c0), LN_EPS, b.A1, bf, st, dr(S_EDGE1));
+      return gcl_edge_pre_plus(E, H, Dp, erow, ecol, g.node_cplx, b.Pn, b.hstat, b.radc, b.normc, F(gw.e1_rad), F(gw.e1_g),
+                               F(gw.e1_c0), LN_EPS, b.A1, bf, st, dr(S_EDGE1), mv_only ? g.mv_emap : nullptr);
     });
     gemm_cat = CAT_GEMM_EDGE;
     gemm(wd(mk(b.A1, Dp, Dp, gw.e2_w, H, gw.e2_b, FB_ACT_RELU, E, nullptr, 0, b.M, H), dr(S_EDGE2)));
@@ -706,7 +712,8 @@ struct Run {
     gemm(wd(mk(b.M2, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_RELU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E),
             dr(S_GCOORD)));
     stage(CAT_EDGE_ELEMWISE, [&] {
-      return gcl_node(N, H, g.ctx_rowptr, g.ctx_col, b.M, b.dotE, tiles, E, x_in, p.coord_clamp, need_h ? b.agg : nullptr, x_out, bf, st);
+      return gcl_node(n_rows, H, mv_only ? g.mv_rowptr : g.ctx_rowptr, ecol, b.M, b.dotE, tiles, E, x_in, p.coord_clamp,
+                      need_h ? b.agg : nullptr, x_out, bf, st, mv_only ? g.mv_rows : nullptr);
     });
     gemm_cat = CAT_GEMM_NODE;
     if (need_h) {
@@ -857,7 +864,7 @@ struct Run {
     gemm_cat = CAT_GEMM_NODE;
     // context graph: protein coordinates are reset every iteration, so it is built once
     stage(CAT_GRAPH_MISC, [&] { return graph_fill_ctx(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
-    if (!plus && g.n_mv > 0 && p.E_ctx_mv > 0 && p.E_ctx_mv < p.E_ctx && p.n_iter > 1) {
+    if (g.n_mv > 0 && p.E_ctx_mv > 0 && p.E_ctx_mv < p.E_ctx && p.n_iter > 1) {
       stage(CAT_GRAPH_MISC, [&] { return graph_mv_fill(g, st); });
       mv_ready = true;
     }

@@ -41,7 +41,8 @@ int ln_rows(const void* x1, bool x1_typed, int ld1, int H1, const void* x2, int 
             const float* beta, float eps, void* out, int ldo, bool bf16_mode, cudaStream_t st);
 int gcl_edge_pre_plus(int E, int H, int Dp, const int* erow, const int* ecol, const int* node_cplx, const void* P,
                       const float* hstat, const float* rad, const float* norm, const float* w_rad, const float* gsum,
-                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st, DropCfg drop = DropCfg());
+                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st, DropCfg drop = DropCfg(),
+                      const int* emap = nullptr /* rad is indexed by emap[e] (compact edge subsets) */);
 int dropout_rows(float* x, void* xT, int M, int H, bool bf16_mode, DropCfg drop, cudaStream_t st);
 int pair_zin_plus(const GraphDev& g, int P_total, int H, const void* pair, const float* pc32, int ld32, const float* Wo,
                   const float* bo, const float* gamma, const float* beta, float eps, void* Zl, bool bf16_mode, cudaStream_t st);

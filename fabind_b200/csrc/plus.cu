@@ -119,12 +119,12 @@ __global__ void gcl_edge_pre_plus_kernel(int E, int H, int Dp, const int* __rest
                                          const int* __restrict__ node_cplx, const T* __restrict__ P, const float* __restrict__ hstat,
                                          const float* __restrict__ rad, const float* __restrict__ norm,
                                          const float* __restrict__ w_rad, const float* __restrict__ gsum, const float* __restrict__ c0,
-                                         float eps, T* __restrict__ A1, DropCfg dc) {
+                                         float eps, T* __restrict__ A1, DropCfg dc, const int* __restrict__ emap) {
   pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= E) return;
   const int e = warp, r = erow[e], c = ecol[e];
-  const float rn = rad[e] / radial_norm(norm, node_cplx[r]);
+  const float rn = rad[emap ? emap[e] : e] / radial_norm(norm, node_cplx[r]);
   const float invD = 1.0f / (float)(2 * H + 1);
   const float mu = (hstat[3 * r] + hstat[3 * c] + rn) * invD;
   // E[(x-mu)^2] = E[x^2] - mu^2, accumulated in fp32 from the per-node sums
@@ -147,11 +147,11 @@ __global__ void gcl_edge_pre_plus_kernel(int E, int H, int Dp, const int* __rest
 
 int gcl_edge_pre_plus(int E, int H, int Dp, const int* erow, const int* ecol, const int* node_cplx, const void* P,
                       const float* hstat, const float* rad, const float* norm, const float* w_rad, const float* gsum,
-                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st, DropCfg drop) {
+                      const float* c0, float eps, void* A1, bool bf16_mode, cudaStream_t st, DropCfg drop, const int* emap) {
   if (E <= 0) return FB_OK;
   if (Dp & 7) return FB_ERR_UNSUPPORTED;
-  if (bf16_mode) fb_launch(gcl_edge_pre_plus_kernel<bf16>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const bf16*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (bf16*)A1, drop);
-  else fb_launch(gcl_edge_pre_plus_kernel<float>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const float*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (float*)A1, drop);
+  if (bf16_mode) fb_launch(gcl_edge_pre_plus_kernel<bf16>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const bf16*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (bf16*)A1, drop, emap);
+  else fb_launch(gcl_edge_pre_plus_kernel<float>, dim3(warp_grid_p(E)), dim3(256), 0, st, E, H, Dp, erow, ecol, node_cplx, (const float*)P, hstat, rad, norm, w_rad, gsum, c0, eps, (float*)A1, drop, emap);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

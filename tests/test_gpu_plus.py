@@ -129,3 +129,14 @@ def test_plus_training_with_autograd_raises():
     b = make_batch(embed=64, n_complexes=1, seed=0, n_c=5, n_p=10).to("cuda")
     with pytest.raises(NotImplementedError):
         m(**b.forward_args())
+
+
+def test_plus_moving_rows_subset_is_exact():
+    """FABind+ layout: out_layer of the non-final iterations on the context edges INTO the masked rows only == on all edges (fp32 mode:
+    identical X, H and pair embedding)"""
+    b = make_batch(embed=64, n_complexes=3, seed=21, n_c=14, n_p=60)
+    m, _ = _model(64, 2, 3)
+    X1, H1, P1 = _run(m, b)
+    m.moving_rows = False
+    X0, H0, P0 = _run(m, b)
+    assert torch.equal(X1, X0) and torch.equal(H1, H0) and torch.equal(P1, P0)
