@@ -37,6 +37,42 @@ Cb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
 q = _lib.GemmParams()
 q.A, q.lda, q.K1, q.W, q.Cb, q.ldcb, q.M, q.N, q.bf16_mode, q.act = A.data_ptr(), K, K, W.data_ptr(), Cb.data_ptr(), N, M, N, 1, 1
 _lib.check(_lib.lib().fb_gemm(C.byref(q), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fb_gemm")
+# round 2: the streaming form of the CTA-pair GEMM (K > 512), row-dot epilogue, fp32 output
+M, N, K = 16600, 256, 576
+A = torch.randn(M, K, device="cuda").to(torch.bfloat16); W = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+Cf = torch.empty(M, N, device="cuda"); dv = torch.randn(N, device="cuda")
+nt = _lib.lib().fb_gemm_dot_tiles(M, N, K, 1, 0)
+dout = torch.zeros(nt * M, device="cuda")
+q = _lib.GemmParams()
+q.A, q.lda, q.K1, q.W, q.C, q.ldc, q.M, q.N, q.bf16_mode, q.act = A.data_ptr(), K, K, W.data_ptr(), Cf.data_ptr(), N, M, N, 1, 2
+q.dotv, q.dot_out, q.dot_stride = dv.data_ptr(), dout.data_ptr(), M
+_lib.check(_lib.lib().fb_gemm(C.byref(q), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fb_gemm")
+# round 2: multi-problem launch (gemm_tc5.cu): K-concatenated operands, residual, column-routed outputs, ragged row counts
+def prob(M, N, K1, K2, act, res, split):
+    g = _lib.GemmParams()
+    A = torch.randn(M, K1, device="cuda").to(torch.bfloat16); A2 = torch.randn(M, max(K2, 8), device="cuda").to(torch.bfloat16)
+    W = torch.randn(N, K1 + K2, device="cuda").to(torch.bfloat16); b = torch.randn(N, device="cuda")
+    ns = 128 if split else 0
+    Cf = torch.randn(M, ns if ns else N, device="cuda"); Cb = torch.zeros(M, N - ns, device="cuda", dtype=torch.bfloat16)
+    g.A, g.lda, g.K1, g.W, g.bias, g.act = A.data_ptr(), K1, K1, W.data_ptr(), b.data_ptr(), act
+    if K2:
+        g.A2, g.lda2, g.K2 = A2.data_ptr(), K2, K2
+    g.C, g.ldc, g.Cb, g.ldcb = Cf.data_ptr(), Cf.shape[1], Cb.data_ptr(), Cb.shape[1]
+    if res:
+        g.res, g.ldres = Cf.data_ptr(), Cf.shape[1]
+    g.M, g.N, g.n_split, g.bf16_mode = M, N, ns, 1
+    return g, (A, A2, W, b, Cf, Cb)
+ps = [prob(300, 256, 128, 64, 2, False, True), prob(129, 128, 64, 0, 0, True, False), prob(1, 384, 192, 0, 1, False, False), prob(700, 128, 128, 128, 0, True, False)]
+arr = (_lib.GemmParams * 4)(*[p[0] for p in ps])
+for pre in (0, 1):
+    _lib.check(_lib.lib().fb_gemm_multi(arr, 4, pre, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fb_gemm_multi")
+# round 2: folded sequences + iteration-invariant head + moving-rows out layer (three iterations), tcgen05 attention core
+m = EfficientMCAttModel(published_args(), 128, 128, 1, n_layers=2, n_iter=3, **nc)
+randomize_coord_heads(m)
+m = m.cuda().eval()
+for prec, att in (("bf16", "simt"), ("fp32", "simt"), ("fp32_tc", "simt"), ("bf16", "tcgen05")):
+    m.precision, m.attention = prec, att
+    m(**b.to("cuda").forward_args())
 # post-optimisation
 ref = torch.randn(40, 3, device="cuda"); pred = ref + 0.3 * torch.randn(40, 3, device="cuda")
 batch = torch.cat([torch.zeros(15), torch.ones(25)]).long().cuda()
