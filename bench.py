@@ -505,8 +505,8 @@ def roofline_objects(prof, peaks, clk, e_ctx, ms_per_step, pair_rows_frac=1.0):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         traffic_tab = json.load(open(tp))
-    names = {"gemm_edge": "edge-MLP GEMMs (tc4::gemm_tc4_kernel, tcgen05 cta_group::2, 256x256 tiles; M = E_ctx, N = K = 512)",
-             "gemm_node": "node-level GEMMs (tc5::gemm_tc5_kernel multi-problem launches of the folded projection groups + tc3::gemm_tc3_kernel, persistent 128x128 tiles; M <= N nodes)",
+    names = {"gemm_edge": "edge-MLP GEMMs (tc4::gemm_tc4_kernel, tcgen05 cta_group::2, 256x256 tiles, weight tile stationary in shared memory; M = E_ctx, N = K = 512)",
+             "gemm_node": "node-level GEMMs (tc5::gemm_tc5_kernel: multi-problem launches of the folded projection groups, single node-level projections and the short edge lists of the moving-rows out layer, persistent 128x128 tiles; tc3::gemm_tc3_kernel for row-dot epilogues)",
              "gemm_pair": "pair-path GEMM on the unique interface pairs (M = E_int / 2, K = 576, N = 1024, row-dot epilogue)",
              "gemm_pair0": "pair_embed0 + pair-bias GEMMs (once per forward, M = pair rows)"}
     total = max(sum(v["ms_per_step"] for v in prof.values()), 1e-9)

@@ -552,7 +552,8 @@ struct Run {
       return gcl_edge_pre(E, H, erow, ecol, g.node_cplx, Pn, b.radc, b.normc, F(gw.e1_rad), nullptr, b.A1, bf, st,
                           mv_only ? g.mv_emap : nullptr);
     });
-    gemm_cat = CAT_GEMM_EDGE;
+    // (profiling category = kernel class: the short edge lists of the moving-rows form run on the node-level kernels)
+    gemm_cat = mv_only ? CAT_GEMM_NODE : CAT_GEMM_EDGE;
     // training-mode dropout of the v1 stack (dropout_p > 0): edge_mlp output (egnn.py:82), node_mlp output (egnn.py:106)
     gemm(wd(mk(b.A1, H, H, gw.e2_w, H, gw.e2_b, FB_ACT_SILU, E, nullptr, 0, b.M, H), dr(S_EDGE2)));
     const int tiles = gemm_dot_tiles(E, H, H, gmode);
