@@ -134,8 +134,7 @@ static void build_weights(int H, int L, ModelW& w) {
     g.c1_w = add(p + "c1_w", H, H); g.c1_b = add(p + "c1_b", 1, H); g.c2_w = add(p + "c2_w", 1, H);
     g.n1_w = add(p + "n1_w", H, 2 * H); g.n1_b = add(p + "n1_b", 1, H);
     g.n2_w = add(p + "n2_w", H, H); g.n2_b = add(p + "n2_b", 1, H);
-    // derived: [e1_b | 0], the bias of the stacked per-node projection GEMM -- the edge kernel then adds nothing but the radial term
-    g.f_e1b = add(p + "f_e1b", 1, 2 * H);
+    g.f_e1b = 0;
     w.gcl.push_back(g);
   }
   for (int i = 0; i < L; ++i) {
@@ -157,18 +156,28 @@ static void build_weights(int H, int L, ModelW& w) {
     a.v_r = add(p + "v_r", 1, H);
     a.ac1_b = add(p + "ac1_b", 1, H);
     a.ac2_w = add(p + "ac2_w", 1, H); a.ac_u = add(p + "ac_u", 1, H);
-    // folded projections (see Run::run_att_folded): consecutive Linear maps of the cross-attention block collapsed into
-    // pre-multiplied weights over K-concatenated operands, so that dependent launches become independent problems of one launch
-    //   f_cac / f_cap : [W_ca | W_ca W_n2]            the block's first projections from [h | T1] of the preceding MC_E_GCL
-    //   f_l3          : [W_p2 | W_p2 W_op] (2 HD rows), [W_tp1 | W_tp1 W_op] (2H rows)     k/v of the new p, p transition hidden from [h_p | O_p]
-    //   f_l5          : [W_tc1 | W_tc1 W_oc]          c transition hidden from [h_c | O_c]
-    //   f_qkc         : [W_qk | W_qk W_tc2]           stacked q|k|v|vc of the compound rows from [h_c | TH_c]
+    w.att.push_back(a);
+  }
+  // ---- DERIVED slots, all behind the last base slot (a packer / the training path works on the base prefix of the arena) ----
+  // [e1_b | 0]: the bias of the stacked per-node projection GEMM -- the edge kernel then adds nothing but the radial term
+  for (int i = 0; i <= L; ++i) {
+    const std::string p = i < L ? "gcl" + std::to_string(i) + "." : std::string("out.");
+    w.gcl[i].f_e1b = add(p + "f_e1b", 1, 2 * H);
+  }
+  // folded projections (see Run::run_att_folded): consecutive Linear maps of the cross-attention block collapsed into
+  // pre-multiplied weights over K-concatenated operands, so that dependent launches become independent problems of one launch
+  //   f_cac / f_cap : [W_ca | W_ca W_n2]            the block's first projections from [h | T1] of the preceding MC_E_GCL
+  //   f_l3          : [W_p2 | W_p2 W_op] (2 HD rows), [W_tp1 | W_tp1 W_op] (2H rows)     k/v of the new p, p transition hidden from [h_p | O_p]
+  //   f_l5          : [W_tc1 | W_tc1 W_oc]          c transition hidden from [h_c | O_c]
+  //   f_qkc         : [W_qk | W_qk W_tc2]           stacked q|k|v|vc of the compound rows from [h_c | TH_c]
+  for (int i = 0; i < L; ++i) {
+    const std::string p = "att" + std::to_string(i) + ".";
+    AttW& a = w.att[i];
     a.f_cac_w = add(p + "f_cac_w", 4 * HD, 2 * H); a.f_cac_b = add(p + "f_cac_b", 1, 4 * HD);
     a.f_cap_w = add(p + "f_cap_w", 2 * HD, 2 * H); a.f_cap_b = add(p + "f_cap_b", 1, 2 * HD);
     a.f_l3_w = add(p + "f_l3_w", 2 * HD + 2 * H, H + HD); a.f_l3_b = add(p + "f_l3_b", 1, 2 * HD + 2 * H);
     a.f_l5_w = add(p + "f_l5_w", 2 * H, H + HD); a.f_l5_b = add(p + "f_l5_b", 1, 2 * H);
     a.f_qkc_w = add(p + "f_qkc_w", 4 * H + QKX, 3 * H); a.f_qkc_b = add(p + "f_qkc_b", 1, 4 * H + QKX);
-    w.att.push_back(a);
   }
   w.total = off;
 }

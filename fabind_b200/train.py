@@ -23,7 +23,7 @@ import torch
 
 from . import backward as bw
 from .layout import build_layout
-from .weights import slots, pack_state_dict, arena_grads_to_state_dict, GraphedPacker, FastPackerV1
+from .weights import slots, base_elems, pack_state_dict, arena_grads_to_state_dict, GraphedPacker, FastPackerV1
 
 # per-step pack / un-pack of the weight arena: v1 layout = explicit selection + hand-written chain rule (weights.FastPackerV1), FABind+
 # layout = the generic functions replayed from CUDA graphs (weights.GraphedPacker); False = the generic eager torch ops every step
@@ -55,7 +55,8 @@ def slot_tensors(arena, hidden, n_layers, flavour=0, bf16=None):
     bf16 = bf16 and arena.is_cuda
     out = {}
     bw.clear_bf16()
-    a16 = arena.to(torch.bfloat16) if bf16 else None
+    # (only the base prefix: the derived slots behind it belong to the inference path, fb_derive_weights)
+    a16 = arena[:base_elems(hidden, n_layers, flavour)].to(torch.bfloat16) if bf16 else None
     for name, r, c, off in slots(hidden, n_layers, flavour):
         if r * c == 0:
             continue

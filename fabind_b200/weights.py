@@ -40,6 +40,11 @@ def slots(hidden, n_layers, flavour=0, derived=False):
     return out
 
 
+def base_elems(hidden, n_layers, flavour=0):
+    """length of the base prefix of the arena: the library lays every derived ("f_*") slot out behind the last base slot"""
+    return max(off + r * c for _, r, c, off in slots(hidden, n_layers, flavour))
+
+
 def derive_on_device(w32, hidden, n_layers, flavour=0):
     """fill the derived ("f_*") slots of a device-resident fp32 arena in place (fb_derive_weights, on the current stream)"""
     if w32.device.type != "cuda" or w32.dtype != torch.float32 or not w32.is_contiguous():

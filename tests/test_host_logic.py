@@ -188,4 +188,6 @@ def test_derived_slots_are_hidden_from_the_packers():
         assert o >= end, n
         end = o + r * c
     assert end <= _lib.lib().fb_weight_arena_elems_f(H, L, 0)
+    from fabind_b200.weights import base_elems
+    assert all(o >= base_elems(H, L, 0) for _, _, _, o in extra)  # derived slots sit behind the base prefix of the arena
     assert slots(H, L, 1, derived=True) == slots(H, L, 1)        # FABind+ layout: no folded slots
