@@ -2,7 +2,8 @@
 identical, att_model.py:29-126) and `EfficientMCAttModel` whose forward returns `(X, H, pair_embed_batched)`
 (att_model.py:166-223).  eval(): inference semantics (refine='refine_coord').  train() under torch.no_grad(): the reference's
 dropout SAMPLING mode (P/test_sampling_fabind.py:118-124) with in-kernel masks at every nn.Dropout site and the `random_n_iter`
-draw of att_model.py:199-202; train() with autograd enabled raises (no backward kernels)."""
+draw of att_model.py:199-202; train() with autograd enabled routes to the training step (`train.forward_with_grad`, FABind+ reverse
+pass; it carries no dropout masks and therefore refuses dropout_p > 0)."""
 import os
 
 import torch

@@ -451,7 +451,7 @@ class FABindPlus(nn.Module):
         """Sampling-based FABind+ (P/test_sampling_fabind.py:126-131, P/inference_sampling_fabind.py:168-185): `n_samples` passes of
         `inference` in train() mode (dropout masks keyed by seed + k), returning the list of (coords, batch[, confidence]).
         `data_fn()` must return a fresh batch per pass (inference mutates nothing, the forward path shifts data.coords)."""
-        was_training = self.training
+        flags = {m: m.training for m in self.modules()}   # per-module: sub-modules the caller keeps in eval() stay there
         self.train()
         for name, sub in self.named_modules():
             if name.startswith("confidence") or name.startswith("ranking"):
@@ -464,7 +464,8 @@ class FABindPlus(nn.Module):
                     outs.append(self.inference(data_fn()))
         finally:
             self.dropout_seed = None
-            self.train(was_training)
+            for m, f in flags.items():
+                m.training = f
         return outs
 
     def inference(self, data):

@@ -60,7 +60,7 @@ def sample_batched(model, data, n_samples, seed=0, max_instances=256):
     B = int(data['compound'].batch.max()) + 1
     n_atoms = data['compound'].batch.shape[0]
     per = max(1, min(n_samples, max_instances // max(B, 1)))
-    was_training = model.training
+    flags = {m: m.training for m in model.modules()}   # per-module: sub-modules the caller keeps in eval() stay there
     model.train()
     for name, sub in model.named_modules():
         if name.startswith("confidence") or name.startswith("ranking"):
@@ -79,5 +79,6 @@ def sample_batched(model, data, n_samples, seed=0, max_instances=256):
                 done += s
     finally:
         model.dropout_seed = None
-        model.train(was_training)
+        for m, f in flags.items():
+            m.training = f
     return torch.cat(coords, 0), data['compound'].batch, (torch.cat(conf, 0) if conf else None)
