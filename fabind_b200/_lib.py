@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfabind_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "CUDA launch error", -4: "unsupported configuration"}
 
@@ -31,7 +31,7 @@ class ModelParams(C.Structure):
         ("trace_h", C.c_void_p), ("trace_x", C.c_void_p),
         ("flavour", C.c_int32), ("pair_out", C.c_void_p),
         ("dropout_p", C.c_float), ("dropout_seed", C.c_uint32), ("dropout_colonly", C.c_int32), ("attn_tc", C.c_int32),
-        ("n_mv", C.c_int32), ("E_ctx_mv", C.c_int32),
+        ("n_mv", C.c_int32), ("E_ctx_mv", C.c_int32), ("layout_flag", C.c_void_p),
     ]
 
 

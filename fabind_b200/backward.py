@@ -489,7 +489,7 @@ def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0, drop=None, layer=
     return dh2, dx, grads, dPB_p, dPB_c
 
 
-def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
+def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out, on_group=None):
     """Reverse pass of the LAST refinement iteration of the v1 stack (att_model.py:227-245: earlier iterations run under no_grad):
     linear_out <- out layer <- [LAS <- MC_Att_L <- MC_E_GCL] x L <- linear_in, plus pair_embed0 and the gated pair biases of every
     row-attention block.  Specification: tests/emulate_backward.py::forward_backward_v1.
@@ -498,6 +498,8 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
     tape: per layer (saved_gcl, saved_att, saved_las); top: Hin, pc, outer, P0, raw_full, h_last, out_saved (internal node order).
     edges: ctx_row/ctx_col, int_row/int_col, las_a/las_b (int32).  consts: cmax, lcl, las_step, xl (LAS reference coordinates).
     dH_out [N,H], dX_out [N,3]: gradients of the outputs in internal order (dX_out already masked to the moving nodes).
+    on_group(prefix, {slot: gradient}): called as soon as a layer's weight gradients are complete (out layer first, the top-level
+    slots last) -- the hook the overlapped gradient all-reduce hangs on.
     Returns (grads keyed by full slot name, dHin)."""
     L = len(tape)
     Nc = geo["Nc"]
@@ -507,6 +509,8 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out):
     def take(pre, g):
         for k, v in g.items():
             grads[pre + k] = v
+        if on_group is not None:        # this group's weight gradients are final: train.py starts their all-reduce behind the reverse pass
+            on_group(pre, g)
     g0 = {}
     dh = _drop(drop, _linear_bwd(g0, "out_w", "out_b", weights[""]["out_w_t"], top.get("h_last_d", top["h_last"]), dH_out), -1, "stack_out")
     dh, dx, g = gcl_backward(weights["out."], top["out_saved"], edges["ctx_row"], edges["ctx_col"], geo["node_cplx"], consts["cmax"], dh, dX_out,

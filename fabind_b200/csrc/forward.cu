@@ -873,6 +873,18 @@ struct Run {
     }
     gemm_cat = CAT_GEMM_NODE;
     // context graph: protein coordinates are reset every iteration, so it is built once
+    if (p.layout_flag) {
+      // host-supplied counts (a dataloader-side layout): entries a wrong claim would leave unwritten must still be valid node ids
+      if (p.E_ctx > 0) {
+        chk(cudaMemsetAsync(g.ctx_row, 0, (size_t)p.E_ctx * sizeof(int), st) == cudaSuccess ? FB_OK : FB_ERR_CUDA);
+        chk(cudaMemsetAsync(g.ctx_col, 0, (size_t)p.E_ctx * sizeof(int), st) == cudaSuccess ? FB_OK : FB_ERR_CUDA);
+      }
+      if (p.E_ctx_mv > 0) {
+        chk(cudaMemsetAsync(g.mv_erow, 0, (size_t)p.E_ctx_mv * sizeof(int), st) == cudaSuccess ? FB_OK : FB_ERR_CUDA);
+        chk(cudaMemsetAsync(g.mv_ecol, 0, (size_t)p.E_ctx_mv * sizeof(int), st) == cudaSuccess ? FB_OK : FB_ERR_CUDA);
+        chk(cudaMemsetAsync(g.mv_emap, 0, (size_t)p.E_ctx_mv * sizeof(int), st) == cudaSuccess ? FB_OK : FB_ERR_CUDA);
+      }
+    }
     stage(CAT_GRAPH_MISC, [&] { return graph_fill_ctx(g, b.x_state, p.intra_cutoff, p.inter_cutoff, st); });
     if (g.n_mv > 0 && p.E_ctx_mv > 0 && p.E_ctx_mv < p.E_ctx && p.n_iter > 1) {
       stage(CAT_GRAPH_MISC, [&] { return graph_mv_fill(g, st); });
@@ -1069,7 +1081,10 @@ int32_t fb_graph_static(const fb_model_params* p, void* stream) {
   if (r != FB_OK) return r;
   r = graph_count_ctx(g, g.xtmp, p->intra_cutoff, p->inter_cutoff, st);
   if (r != FB_OK) return r;
-  return graph_mv_index(g, st);
+  r = graph_mv_index(g, st);
+  if (r != FB_OK || !p->layout_flag) return r;
+  // ABI 6: the host supplied E_ctx / E_ctx_mv (no read-back): check the claim on the device
+  return graph_verify_counts(g, p->E_ctx, p->E_ctx_mv, p->layout_flag, st);
 }
 
 const int32_t* fb_graph_counts_ptr(const fb_model_params* p) {
@@ -1098,6 +1113,7 @@ int32_t fb_model_forward(const fb_model_params* p, void* stream) {
   r.g.ctx_row = r.b.ctx_row; r.g.ctx_col = r.b.ctx_col;
   r.g.int_row = r.b.int_row; r.g.int_col = r.b.int_col; r.g.int_pair = r.b.int_pair;
   r.g.mv_erow = r.b.mv_erow; r.g.mv_ecol = r.b.mv_ecol; r.g.mv_emap = r.b.mv_emap;
+  r.g.ctx_cap = p->E_ctx; r.g.mv_cap = p->E_ctx_mv;     // the sizes plan_main gave the lists
   r.st = (cudaStream_t)stream;
   r.bf = p->bf16_mode == FB_PREC_BF16; r.gmode = p->bf16_mode;
   r.H = p->hidden; r.N = p->N; r.Nc = p->Nc_tot; r.Np = p->N - p->Nc_tot;

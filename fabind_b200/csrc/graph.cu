@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(256) graph_rows_kernel(GraphDev g, const float
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (FILL && hit) {
         const int pos = base_ctx + n_ctx + __popc(m & lt);
-        g.ctx_row[pos] = r;
-        g.ctx_col[pos] = g.bond_col[e];
+        if (pos < g.ctx_cap) { g.ctx_row[pos] = r; g.ctx_col[pos] = g.bond_col[e]; }
       }
       n_ctx += __popc(m);
     }
@@ -86,8 +85,7 @@ __global__ void __launch_bounds__(256) graph_rows_kernel(GraphDev g, const float
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (FILL && hit) {
         const int pos = base_ctx + n_ctx + __popc(m & lt);
-        g.ctx_row[pos] = r;
-        g.ctx_col[pos] = c;
+        if (pos < g.ctx_cap) { g.ctx_row[pos] = r; g.ctx_col[pos] = c; }
       }
       n_ctx += __popc(m);
     }
@@ -254,11 +252,30 @@ __global__ void __launch_bounds__(256) mv_fill_kernel(GraphDev g) {
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (j >= g.n_mv) return;
   const int r = g.mv_rows[j], lo = g.ctx_rowptr[r], n = g.ctx_rowptr[r + 1] - lo, dst = g.mv_rowptr[j];
-  for (int k = lane; k < n; k += 32) {
+  for (int k = lane; k < n && dst + k < g.mv_cap; k += 32) {
     g.mv_erow[dst + k] = r;
     g.mv_ecol[dst + k] = g.ctx_col[lo + k];
     g.mv_emap[dst + k] = lo + k;
   }
+}
+
+// Host-supplied edge counts (fb_model_params.layout_flag): the dataloader counted the context edges on the CPU, so the host sized
+// the edge-level scratch and the GEMM row counts without reading the device.  One block checks the claim against the device-side
+// counts; a wrong claim raises the flag and clamps both CSR row pointers into the claimed sizes, so that every later consumer stays
+// inside the buffers the host sized (results are then garbage by contract, and flagged).
+__global__ void __launch_bounds__(1024) verify_counts_kernel(GraphDev g, int e_ctx, int e_mv, int* __restrict__ flag) {
+  pdl_entry();
+  if (g.counts[0] == e_ctx && g.counts[1] == e_mv) return;
+  if (threadIdx.x == 0) *flag = 1;
+  for (int i = threadIdx.x; i <= g.N; i += blockDim.x) g.ctx_rowptr[i] = min(g.ctx_rowptr[i], e_ctx);
+  for (int i = threadIdx.x; i <= g.n_mv; i += blockDim.x) g.mv_rowptr[i] = min(g.mv_rowptr[i], e_mv);
+}
+
+int graph_verify_counts(const GraphDev& g, int e_ctx, int e_mv, int* flag, cudaStream_t st) {
+  fb_launch(verify_counts_kernel, dim3(1), dim3(1024), 0, st, g, e_ctx, e_mv, flag);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
 }
 
 int graph_mv_index(const GraphDev& g, cudaStream_t st) {

@@ -40,6 +40,9 @@ struct GraphDev {
   int* mv_erow = nullptr; int* mv_ecol = nullptr;     // [E_mv] endpoints
   int* mv_emap = nullptr;                             // [E_mv] index of the edge in the full context list
   int* counts = nullptr;                              // [2] E_ctx, E_mv (read by the host after fb_graph_static)
+  // capacities of ctx_row / ctx_col and of the compact moving-rows lists: every fill is bounded by them.  They only bind when the
+  // host SUPPLIED the counts (fb_model_params.layout_flag, a dataloader-side layout) and was wrong; see graph_verify_counts
+  int ctx_cap = 0x7fffffff, mv_cap = 0x7fffffff;
 };
 
 int graph_prepare_static(const GraphDev& g, const long long* bonds, const long long* las, cudaStream_t st);
@@ -48,6 +51,8 @@ int graph_fill_ctx(const GraphDev& g, const float* x, float intra, float inter, 
 // moving rows: index + compact row pointers (after graph_count_ctx), compact edge lists (after graph_fill_ctx)
 int graph_mv_index(const GraphDev& g, cudaStream_t st);
 int graph_mv_fill(const GraphDev& g, cudaStream_t st);
+// host-supplied counts (after graph_mv_index): device counts != (e_ctx, e_mv) -> *flag = 1 and ctx_rowptr / mv_rowptr clamped to them
+int graph_verify_counts(const GraphDev& g, int e_ctx, int e_mv, int* flag, cudaStream_t st);
 // total_out (optional, device): receives the number of interface edges of this build
 int graph_build_inter(const GraphDev& g, const float* x, float intra, float inter, cudaStream_t st, int* total_out = nullptr);
 

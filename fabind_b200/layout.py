@@ -28,6 +28,12 @@ class Layout:
     n_c: np.ndarray
     n_p: np.ndarray
     n_mv: int = 0                   # number of masked (moving) nodes
+    # dataloader-side edge counts (fabind_b200/dataloader.py): context edges incl. `hint_n_bond` bonds, and those INTO the moving
+    # rows; None = unknown (the runtime reads them back after fb_graph_static: one host sync per forward)
+    e_ctx: int = None
+    e_ctx_mv: int = None
+    hint_n_bond: int = None
+    hint_cutoff: float = None
 
     def ptr(self, name):
         return self.blob.data_ptr() + 4 * self.offs[name]
@@ -37,6 +43,13 @@ _CACHE = []          # [(weakrefs of the four index tensors, their versions, dev
 _CACHE_MAX = 8
 
 
+def _norm_device(device):
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 def build_layout(batch_id, segment_id, is_global, mask, device, allow_single_side=False):
     """Layout of a batch, cached per batch OBJECT: the sampling protocol (40 passes over the same `data`, P/test_sampling_fabind.py:
     118-131), evaluation loops and benches hand the same four index tensors to every forward, and rebuilding the layout costs a
@@ -44,7 +57,7 @@ def build_layout(batch_id, segment_id, is_global, mask, device, allow_single_sid
     still alive) with unchanged `_version`s on the same target device; in-place edits bump the version, new tensors miss.  (Writes
     through `.data` are invisible to this test, as they are to autograd.)"""
     import weakref
-    dev = torch.device(device)
+    dev = _norm_device(device)
     tensors = (batch_id, segment_id, is_global, mask)
     vers = tuple(t._version for t in tensors)
     for i in range(len(_CACHE) - 1, -1, -1):
@@ -61,6 +74,21 @@ def build_layout(batch_id, segment_id, is_global, mask, device, allow_single_sid
 
 
 def _build_layout(batch_id, segment_id, is_global, mask, device, allow_single_side=False):
+    return materialize(layout_arrays(batch_id, segment_id, is_global, mask, allow_single_side), device)
+
+
+def register(tensors, lay, device, allow_single_side=False):
+    """Enter a layout made elsewhere (fabind_b200.dataloader: in a collate function / loader worker, with the edge counts of the
+    context graph) for the four index tensor OBJECTS (batch_id, segment_id, is_global, mask) a later forward will be handed."""
+    import weakref
+    tensors = tuple(tensors)
+    _CACHE.append((tuple(weakref.ref(t) for t in tensors), tuple(t._version for t in tensors), _norm_device(device), allow_single_side, lay))
+    del _CACHE[:-_CACHE_MAX]
+    return lay
+
+
+def layout_arrays(batch_id, segment_id, is_global, mask, allow_single_side=False):
+    """The host half of the layout: numpy only (safe in a DataLoader worker, picklable result)."""
     if batch_id.device.type != "cpu" and all(t.device == batch_id.device for t in (segment_id, is_global, mask)):
         # device inputs: ONE device->host transfer (one sync) for the four index vectors instead of four
         packed = (batch_id.detach().to(torch.int64) * 8 + segment_id.detach().to(torch.int64) + is_global.detach().to(torch.int64) * 2
@@ -113,8 +141,16 @@ def _build_layout(batch_id, segment_id, is_global, mask, device, allow_single_si
         pad = (-len(v)) % 4
         chunks.append(np.concatenate([v, np.zeros(pad, np.int32)]))
         cur += len(v) + pad
-    blob = torch.from_numpy(np.concatenate(chunks)).to(device, non_blocking=True)
-    flags_t = torch.from_numpy(flags).to(device, non_blocking=True)
-    return Layout(N=N, B=B, Nc_tot=Nc_tot, P_total=int(pair_base[-1]), cap_int=cap_int, fb_atom=int(fb_atom),
-                  fb_res=int(fb_res), max_c=int(nc1.max()), max_p=int(np1.max()) if len(np1) else 0, blob=blob, flags=flags_t, offs=offs, orig_off=orig_off, n_c=n_c, n_p=n_p,
-                  n_mv=int(msk.sum()))
+    return dict(N=N, B=B, Nc_tot=Nc_tot, P_total=int(pair_base[-1]), cap_int=cap_int, fb_atom=int(fb_atom), fb_res=int(fb_res),
+                max_c=int(nc1.max()), max_p=int(np1.max()) if len(np1) else 0, blob=np.concatenate(chunks), flags=flags, offs=offs,
+                orig_off=orig_off, n_c=n_c, n_p=n_p, n_mv=int(msk.sum()))
+
+
+def materialize(arr, device, e_ctx=None, e_ctx_mv=None, hint_n_bond=None, hint_cutoff=None):
+    """numpy layout (layout_arrays) -> Layout with its two index blobs on `device` (asynchronous copies, no sync)"""
+    arr = dict(arr)
+    blob, flags = torch.from_numpy(arr.pop("blob")), torch.from_numpy(arr.pop("flags"))
+    if torch.device(device).type == "cuda":
+        blob, flags = blob.pin_memory(), flags.pin_memory()
+    return Layout(blob=blob.to(device, non_blocking=True), flags=flags.to(device, non_blocking=True), e_ctx=e_ctx, e_ctx_mv=e_ctx_mv,
+                  hint_n_bond=hint_n_bond, hint_cutoff=hint_cutoff, **arr)

@@ -60,6 +60,11 @@ class EfficientMCAttModel(nn.Module):
         self._packed.invalidate()
         return super()._apply(fn, *a, **k)
 
+    def layout_cutoff(self):
+        """the normalised intra cutoff a dataloader-side layout counts the residue-residue edges with
+        (fabind_b200.dataloader.layout_hint / prepare_batch)"""
+        return self._cfg["intra_cutoff"]
+
     def invalidate_packed_weights(self):
         """call after editing parameters through `.data` (see fabind_b200.runtime.PackedWeights)"""
         self._packed.invalidate()

@@ -19,6 +19,39 @@ def _scratch_buf(device, tag, nbytes):
     return t
 
 
+_flags = {}
+
+
+def layout_flag(device):
+    """int32[1] on `device`, set to 1 by fb_graph_static when a dataloader-side layout (fb_model_params.layout_flag) claimed edge
+    counts that differ from the device's.  Host-buffer forwards check it at their final synchronisation and raise; device-resident
+    forwards never synchronise, so a caller that feeds hand-made hints checks `check_layout_flag(device)` at its own sync point."""
+    from .layout import _norm_device
+    dev = _norm_device(device)
+    t = _flags.get(dev)
+    if t is None:
+        t = _flags[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return t
+
+
+def _flag_host(device):
+    from .layout import _norm_device
+    key = ("host", _norm_device(device))
+    t = _flags.get(key)
+    if t is None:
+        t = _flags[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return t
+
+
+def check_layout_flag(device):
+    """Synchronising read of `layout_flag(device)`; raises (and clears the flag) when a hinted forward since the last check ran on
+    a wrong hint."""
+    t = layout_flag(device)
+    if int(t.item()) != 0:
+        t.zero_()
+        raise RuntimeError("fabind_b200: a dataloader-side layout did not match its batch (context-edge counts differ)")
+
+
 def current_stream_ptr(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -179,13 +212,23 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
         _lib.check(int(gbytes), "fb_graph_workspace_bytes")
     wsg = _scratch_buf(dev, "graph", gbytes)
     p.ws_graph, p.ws_graph_bytes = wsg.data_ptr(), wsg.numel()
-    _lib.check(l.fb_graph_static(C.byref(p), st), "fb_graph_static")
-    # one host read per forward: the number of context edges sizes the edge-level scratch (the same read fetches the number of
-    # context edges into the moving rows, fb_model_params.E_ctx_mv)
-    cnt_ptr = l.fb_graph_counts_ptr(C.byref(p))
-    off = (cnt_ptr - wsg.data_ptr()) // 4
-    e_ctx, e_ctx_mv = wsg[: (off + 2) * 4].view(torch.int32)[off:off + 2].tolist()
-    p.E_ctx, p.E_ctx_mv = e_ctx, e_ctx_mv
+    # Edge counts of the context graph.  Supplied by a dataloader-side layout (fabind_b200/dataloader.py: counted on the CPU at
+    # collate time): the host sizes the edge-level scratch from them and the device only CHECKS the claim (fb_model_params.
+    # layout_flag) -- no device->host read between entry and outputs.  Otherwise: one host read per forward after fb_graph_static
+    # (the same read fetches the number of context edges into the moving rows, fb_model_params.E_ctx_mv).
+    hinted = (lay.e_ctx is not None and lay.hint_n_bond == p.n_bond and lay.hint_cutoff is not None
+              and abs(lay.hint_cutoff - cfg["intra_cutoff"]) <= 1e-6 * abs(cfg["intra_cutoff"]))
+    if hinted:
+        p.E_ctx, p.E_ctx_mv = lay.e_ctx, lay.e_ctx_mv
+        p.layout_flag = layout_flag(dev).data_ptr()
+        _lib.check(l.fb_graph_static(C.byref(p), st), "fb_graph_static")
+        e_ctx = lay.e_ctx
+    else:
+        _lib.check(l.fb_graph_static(C.byref(p), st), "fb_graph_static")
+        cnt_ptr = l.fb_graph_counts_ptr(C.byref(p))
+        off = (cnt_ptr - wsg.data_ptr()) // 4
+        e_ctx, e_ctx_mv = wsg[: (off + 2) * 4].view(torch.int32)[off:off + 2].tolist()
+        p.E_ctx, p.E_ctx_mv = e_ctx, e_ctx_mv
     _mark("graph_static + E_ctx read")
     mbytes = l.fb_model_workspace_bytes(C.byref(p))
     if mbytes < 0:
@@ -204,8 +247,16 @@ def model_forward(module, packed, X, H, batch_id, segment_id, mask, is_global, b
         X_host.view(N, 3).copy_(xv, non_blocking=True)
         H_host = torch.empty((N, hidden), dtype=torch.float32, pin_memory=True)
         H_host.copy_(H_out, non_blocking=True)
+        if hinted:
+            fl = _flag_host(dev)
+            fl.copy_(layout_flag(dev), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         H_out = H_host
+        if hinted and int(fl[0]) != 0:
+            layout_flag(dev).zero_()
+            raise RuntimeError("fabind_b200: the dataloader-side layout of this batch does not match its coordinates / bond list "
+                               "(context-edge counts differ from the device's): outputs are invalid; rebuild the hint "
+                               "(fabind_b200.dataloader.layout_hint) from the tensors that are passed to the forward")
     if tr is not None:
         perm = lay.blob[lay.offs["perm"]:lay.offs["perm"] + N].long()
         th = torch.empty_like(tr[0]); tx = torch.empty_like(tr[1])

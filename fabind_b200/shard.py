@@ -141,6 +141,11 @@ def allreduce_gradients(params, group=None, average=True, buffer=None, model=Non
     receive the reduced value if any rank had one.  Backend-agnostic (NCCL on the GPU box, gloo in the CPU tests).
     Returns the flat buffer (re-usable through `buffer=` to avoid re-allocation)."""
     params = [p for p in params if p.requires_grad]
+    # train.overlap_allreduce: the stack's gradients were already reduced inside the reverse pass of this step
+    reduced = getattr(model, "_fb_reduced", None) if model is not None else None
+    if reduced:
+        object.__setattr__(model, "_fb_reduced", None)
+        params = [p for p in params if id(p) not in reduced]
     if not params:
         return buffer
     world = dist.get_world_size(group) if dist.is_initialized() else 1

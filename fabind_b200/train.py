@@ -162,16 +162,41 @@ def _backward_half(st, gX, gH, gP=None):
     perm, moves, flavour = st["perm"], st["moves"], st["flavour"]
     dX_int = (gX[:, 0][perm].to(torch.float32) * moves[:, None]).contiguous()
     dH_int = gH[perm].to(torch.float32).contiguous()
+    garena = torch.zeros_like(st["arena"])
+    slot_of = {name: (r, c, off) for name, r, c, off in slots(st["H"], st["L"], flavour)}
+    pre_of = lambda name: name[:name.index(".") + 1] if "." in name else ""
+    span = {}                                    # prefix -> [first element, end) of its run of slots
+    for name, (r, c, off) in slot_of.items():
+        lo, hi = span.get(pre_of(name), (off, off + r * c))
+        span[pre_of(name)] = (min(lo, off), max(hi, off + r * c))
+    ov = _overlap_state(st["model"], garena, max(hi for _, hi in span.values()))
     if flavour == 1:
         gP = torch.zeros(st["consts"]["n_pairs"], st["H"], dtype=torch.float32, device=dX_int.device) if gP is None else gP
         grads, dHin = bw.stack_backward_plus(st["weights"], st["tape"], st["top"], st["geo"], st["edges"], st["consts"], dH_int, dX_int,
                                              gP.to(torch.float32).contiguous())
+        done = set()
     else:
-        grads, dHin = bw.stack_backward_v1(st["weights"], st["tape"], st["top"], st["geo"], st["edges"], st["consts"], dH_int, dX_int)
-    garena = torch.zeros_like(st["arena"])
-    for name, r, c, off in slots(st["H"], st["L"], flavour):
-        if name in grads:
+        done = set()
+
+        def on_group(pre, g):
+            # the group's slots are contiguous in the arena (fb_weight_slot_*: one prefix = one run of slots): fill its slice now and,
+            # with the overlapped all-reduce switched on, hand it to the collective while the reverse pass of the earlier layers runs
+            for k, v in g.items():
+                name = pre + k
+                if name not in slot_of:
+                    continue
+                r, c, off = slot_of[name]
+                garena[off:off + r * c] = v.reshape(-1)
+                done.add(name)
+            if ov is not None and pre in span:
+                ov.reduce(pre, *span[pre])
+        grads, dHin = bw.stack_backward_v1(st["weights"], st["tape"], st["top"], st["geo"], st["edges"], st["consts"], dH_int, dX_int,
+                                           on_group=on_group)
+    for name, (r, c, off) in slot_of.items():
+        if name in grads and name not in done:
             garena[off:off + r * c] = grads[name].reshape(-1)
+    if ov is not None:
+        ov.finish(flavour)
     if st.get("packer") is not None:
         flat, pgrads = st["packer"].unpack(garena)
         # one flat fp32 buffer holding every parameter gradient in state_dict order: shard.allreduce_gradients reduces it in place
@@ -182,9 +207,92 @@ def _backward_half(st, gX, gH, gP=None):
             pass
     else:
         pgrads = arena_grads_to_state_dict(st["sd"], garena, st["H"], st["L"], flavour, device=garena.device)
+    if ov is not None:
+        # every parameter gradient of this step is already averaged over the ranks: shard.allreduce_gradients skips these parameters
+        named = dict(st["model"].named_parameters())
+        object.__setattr__(st["model"], "_fb_reduced", {id(named[k]) for k in pgrads if k in named})
     gH_in = torch.empty(st["Hin_shape"], dtype=torch.float32, device=dX_int.device)
     gH_in[perm] = dHin
     return pgrads, gH_in
+
+
+class _Overlap:
+    """Gradient all-reduce OVERLAPPED with the reverse pass (the role DDP's bucket hooks play for the reference, FABind/fabind/
+    main_fabind.py:198-200).  The reverse pass finishes the weight gradients layer by layer, last layer first; each finished group is
+    a contiguous slice of the ARENA gradient and is summed over the ranks on a side stream while the earlier layers are still being
+    differentiated.  The arena -> state_dict chain rule (packer.unpack) is linear in the arena gradient and uses only the weights,
+    which are identical on all ranks, so reducing before it gives the gradients of reducing after it (up to fp32 rounding order).
+    Uncovered slots (none for the v1 layout) and the FABind+ layout are reduced in one tail collective."""
+
+    def __init__(self, garena, group, average, end):
+        import torch.distributed as dist
+        self.dist, self.garena, self.group, self.average, self.end = dist, garena, group, average, end
+        self.world = dist.get_world_size(group)
+        self.handles, self.covered = [], []
+        self.cuda = garena.device.type == "cuda"
+        if self.cuda:
+            self.main = torch.cuda.current_stream(garena.device)
+            self.side = _side_stream(garena.device)
+
+    def _issue(self, lo, hi):
+        part = self.garena[lo:hi]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ev)
+                self.handles.append(self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.handles.append(self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def reduce(self, pre, lo, hi):
+        self.covered.append((lo, hi))
+        self._issue(lo, hi)
+
+    def finish(self, flavour):
+        # whatever the hooks did not cover (gaps between the groups, the whole arena for the FABind+ layout) in one tail collective
+        cur, gaps = 0, []
+        for lo, hi in sorted(self.covered):
+            if lo > cur:
+                gaps.append((cur, lo))
+            cur = max(cur, hi)
+        if cur < self.end:                  # (the derived slots behind `end` carry no gradient)
+            gaps.append((cur, self.end))
+        for lo, hi in gaps:
+            self._issue(lo, hi)
+        for h in self.handles:
+            h.wait()                       # CUDA: the side stream waits for the collective
+        if self.cuda:
+            self.main.wait_stream(self.side)
+        if self.average:
+            self.garena[:self.end].div_(self.world)
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    s = _SIDE.get(device)
+    if s is None:
+        s = _SIDE[device] = torch.cuda.Stream(device=device)
+    return s
+
+
+def overlap_allreduce(model, group=None, average=True, enabled=True):
+    """Switch the overlapped gradient all-reduce of the training step on (or off) for `model` (an EfficientMCAttModel of this package
+    used through `loss.backward()` or `training_step`): the collective then runs INSIDE the reverse pass, and a later
+    `shard.allreduce_gradients(params, model=model)` only reduces parameters that do not belong to the stack."""
+    object.__setattr__(model, "_fb_overlap", dict(group=group, average=average) if enabled else None)
+
+
+def _overlap_state(model, garena, end):
+    cfg = getattr(model, "_fb_overlap", None) if model is not None else None
+    if cfg is None:
+        return None
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(cfg["group"]) == 1:
+        return None
+    return _Overlap(garena, cfg["group"], cfg["average"], end)
 
 
 def training_step(model, fa, output_grads, prev_coords=None, edge_lists=None, state_dict=None, n_iter=None, dropout=None):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 5
+#define FB_ABI_VERSION 6
 
 /* One batch of complexes + model dimensions.  Node layout in caller order is the reference
  * dataloader's [glb_c | atoms | glb_p | residues] per complex (utils/utils.py:328-335). */
@@ -97,6 +97,14 @@ typedef struct fb_model_params {
    * compacts their rows, and E_ctx_mv = the number of such edges, read back next to E_ctx (fb_graph_counts_ptr), sizes the list. */
   int32_t n_mv;
   int32_t E_ctx_mv;
+  /* ABI 6: edge counts supplied by the HOST (a dataloader-side layout, fabind_b200/dataloader.py: the context graph depends only on
+   * the bond list and the protein coordinates, which the collate step knows; reference utils/utils.py:202-442 + att_model.py:38-116).
+   * layout_flag != NULL switches the read-back of fb_graph_counts_ptr off: E_ctx / E_ctx_mv are then EXPECTATIONS set before
+   * fb_graph_static, which compares them with the device-side counts in a one-block kernel; on a mismatch it sets *layout_flag = 1
+   * (device int32, never cleared by the library) and clamps the row pointers to the expected sizes, fb_model_forward zero-fills the
+   * edge lists before writing them and bounds every write by the expected sizes -- a wrong hint gives flagged garbage, never an
+   * out-of-bounds access.  NULL = round-1 protocol (host reads the counts after fb_graph_static). */
+  int32_t* layout_flag;
 } fb_model_params;
 #define FB_FLAVOUR_V1 0
 #define FB_FLAVOUR_PLUS 1

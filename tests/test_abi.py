@@ -16,7 +16,7 @@ def test_exports_match_header():
     for name in declared:
         assert hasattr(l, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
-    assert l.fb_abi_version() == _lib.ABI_VERSION == 5
+    assert l.fb_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_weight_slots_are_disjoint_and_cover_arena():

@@ -145,7 +145,7 @@ def _train_case(seed):
     return b, m, torch.randn(b.X.shape, generator=g), torch.randn(b.H.shape, generator=g)
 
 
-def _rank_gradients(seed):
+def _rank_gradients(seed, overlap=False):
     """parameter gradients of one rank's batch through train.training_step (kernel wrappers -> torch stand-ins, providers -> oracle)"""
     from _pytest.monkeypatch import MonkeyPatch
     from fabind_b200 import backward as bw, train
@@ -156,6 +156,8 @@ def _rank_gradients(seed):
     mp_.setattr(bw, "pair_bias_gate_bwd", T._gate_bwd_standin)
     mp_.setattr(bw, "pair_outer_bwd", T._outer_bwd_standin)
     b, m, rx, rh = _train_case(seed)
+    if overlap:
+        train.overlap_allreduce(m, average=True)
     sd = _weights()
     cfg = orc.make_cfg(n_layers=L, n_iter=IT)
 
@@ -175,21 +177,38 @@ def _rank_gradients(seed):
     return m, pg
 
 
-def _train_worker(rank, world, port, q):
+def _train_worker(rank, world, port, q, overlap=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from fabind_b200 import train
-        m, pg = _rank_gradients(20 + rank)
-        train.apply_gradients(m, pg, average=True)
+        if overlap:
+            # the collective runs INSIDE the reverse pass, group by group (train.overlap_allreduce); apply_gradients' own all-reduce
+            # must then leave the stack's parameters alone (they are already averaged)
+            calls = []
+            real = dist.all_reduce
+            def counting(t, *a, **k):
+                calls.append(t.numel())
+                return real(t, *a, **k)
+            dist.all_reduce = counting
+            m, pg = _rank_gradients(20 + rank, overlap=True)
+            n_inside = len(calls)
+            assert n_inside >= 2 * L + 2, calls            # out layer, att_l / gcl_l per layer, top-level slots
+            train.apply_gradients(m, pg, average=True)
+            assert len(calls) == n_inside, "second reduction of already reduced gradients"
+            dist.all_reduce = real
+        else:
+            m, pg = _rank_gradients(20 + rank)
+            train.apply_gradients(m, pg, average=True)
         q.put((rank, {k: p.grad.numpy().copy() for k, p in m.named_parameters()}))   # numpy: no shared-memory handles that die with the worker
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_data_parallel_training_step_world2():
+@pytest.mark.parametrize("overlap", [False, True], ids=["tail_allreduce", "overlapped_allreduce"])
+def test_data_parallel_training_step_world2(overlap):
     """config 5's structure on CPU: every rank differentiates ITS complexes (train.training_step), one flat all-reduce averages the
     gradients (train.apply_gradients); every rank ends with the mean of the per-rank gradients, unused parameters as zeros"""
     import sys
@@ -197,7 +216,7 @@ def test_data_parallel_training_step_world2():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=240) for _ in procs], key=lambda r: r[0])
