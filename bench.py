@@ -328,12 +328,38 @@ def setup_forward(dev, rank, precision, layers=LAYERS, iters=ITERS, batch=BATCH)
     return dict(step=dev_step, host_step=host_step, model=model, host=host, units=batch)
 
 
-def setup_train(dev, rank):
+def allreduce_alone(dev, n_elems, world, reps=5):
+    """the gradient collective by itself: `reps` back-to-back all-reduces of n_elems fp32 after a barrier (so that rank skew is not
+    counted), CUDA events, max over ranks; returns (ms per collective, bus bandwidth GB/s) or (None, None) without a process group"""
+    import torch.distributed as dist
+    if world <= 1:
+        return None, None
+    buf = torch.zeros(n_elems, dtype=torch.float32, device=dev)
+    for _ in range(2):
+        dist.all_reduce(buf)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dist.all_reduce(buf)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms, = max_ranks([e0.elapsed_time(e1) / reps], dev, world)
+    return ms, 4 * n_elems * 2 * (world - 1) / world / (ms * 1e-3) / 1e9
+
+
+def setup_train(dev, rank, overlap=False):
     """config 5 through the PUBLIC API: model.train(); X, H = model(...); loss.backward(); shard.allreduce_gradients(parameters).
     step(host_inputs) records three events per call: start, after backward, after the all-reduce."""
     from fabind_b200 import backward, shard
     from fabind_b200.synthetic import make_batch
     model = build_model(dev, "bf16").train()
+    if overlap:
+        # the collective runs inside the reverse pass, group by group behind the layers whose gradients are final (DDP's bucket hooks
+        # in the reference, main_fabind.py:198-200); shard.allreduce_gradients below then has nothing left to reduce
+        from fabind_b200 import train
+        train.overlap_allreduce(model, average=True)
     host = pin_batch(make_batch(n_complexes=BATCH, n_c=N_C, n_p=N_P, embed=HIDDEN, seed=100 + rank))
     devb = host.to(dev)
     X0 = devb.X.clone()
@@ -543,6 +569,11 @@ def main():
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32", "fp32_tc", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="config 5: gradient all-reduce overlapped with the reverse pass "
+                    "(train.overlap_allreduce: one collective per finished layer group on a side stream) instead of ONE tail collective. "
+                    "Measured at 2 GPUs (profiles/r2ag_*): the collective alone is 0.28 ms (475 GB/s bus bandwidth) of a 43 ms step; "
+                    "overlapped 43.85 ms per step, tail 42.88 ms -- ten small collectives cost more than the 0.5 ms they hide, so the "
+                    "tail form is the default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", 0))
@@ -626,7 +657,7 @@ def main():
         if args.config == 4:
             cfg["complexes_per_s_at_40_samples"] = world * n_units / (ms / 1e3) / 40
     else:
-        S = setup_train(dev, rank)
+        S = setup_train(dev, rank, overlap=args.overlap)
         for _ in range(W):
             S["step"]()
         S["host_step"]()
@@ -645,10 +676,18 @@ def main():
         out.update(value=world * BATCH / (ms / 1e3), unit="complexes/s", ms_per_step=ms, dtype="bf16", gpu_launches=int(round(launches * args.steps)))
         out["e2e"] = {"value": world * BATCH / (e2e / 1e3), "unit": "complexes/s", "h2d_bytes_per_step": S["h2d"], "d2h_bytes_per_step": 4,
                       "ms_per_step": e2e}
-        out["train"] = {"ms_forward_backward": fb, "ms_allreduce": ar, "allreduce_bytes": 4 * ge,
-                        "allreduce_busbw_gbs": (4 * ge * 2 * (world - 1) / world / (ar * 1e-3) / 1e9) if world > 1 and ar > 0 else None,
+        ar_alone, busbw = allreduce_alone(dev, ge, world)
+        ov = world > 1 and args.overlap
+        out["train"] = {"ms_forward_backward": fb, "ms_allreduce_exposed": ar, "allreduce_bytes": 4 * ge,
+                        "allreduce_mode": ("overlapped with the reverse pass: one collective per finished layer group on a side stream "
+                                           "(train.overlap_allreduce); ms_allreduce_exposed = what is left after loss.backward()") if ov else
+                                          ("one flat collective after the reverse pass; ms_allreduce_exposed includes the wait for the slowest "
+                                           "rank's reverse pass" if world > 1 else "single process (no collective issued)"),
+                        "ms_allreduce_alone": ar_alone, "allreduce_alone_busbw_gbs": busbw,
+                        "allreduce_alone_what": "the same bytes as ONE collective by itself, ranks aligned by a barrier first (no skew)",
                         "backend": "nccl" if world > 1 else "single process (no collective issued)"}
-        cfg.update(n_layers=LAYERS, n_iter=ITERS, global_batch=world * BATCH, parallelism=f"dp{world}, one flat all-reduce of {ge} fp32 gradients")
+        cfg.update(n_layers=LAYERS, n_iter=ITERS, global_batch=world * BATCH,
+                   parallelism=f"dp{world}, all-reduce of {ge} fp32 gradients " + ("overlapped with the reverse pass" if ov else "as one tail collective"))
     clk = clocks.stop() if rank == 0 else None
 
     extras = {}
@@ -688,8 +727,11 @@ def main():
             ms5, l5 = timed_launches(lib, timer, S5["step"], n, 2)
             fb, ar = train_parts(S5["parts"][-n:])
             ms5, fb, ar = max_ranks([ms5, fb, ar], dev, world)
+            ar_alone, busbw = allreduce_alone(dev, S5["grad_elems"], world)
             extras["train_step"] = {"value": world * BATCH / (ms5 / 1e3), "unit": "complexes/s", "ms_per_step": ms5, "ms_forward_backward": fb,
-                                    "allreduce_ms": ar, "allreduce_bytes": 4 * S5["grad_elems"], "launches_per_step": l5,
+                                    "allreduce_ms_exposed": ar, "allreduce_bytes": 4 * S5["grad_elems"], "launches_per_step": l5,
+                                    "allreduce_mode": "one flat collective after the reverse pass" if world > 1 else "none (one process)",
+                                    "allreduce_alone_ms": ar_alone, "allreduce_alone_busbw_gbs": busbw,
                                     "backend": "nccl" if world > 1 else "single process (no collective issued)", "what": WORKLOADS[5]}
             del S5
         except Exception as e:
