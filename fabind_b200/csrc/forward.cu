@@ -33,9 +33,14 @@ static int skip_mask() {
   static int m = [] { const char* e = getenv("FB_SKIP_CATS"); return e ? atoi(e) : 0; }();
   return m;
 }
+static int dup_mask() {
+  static int m = [] { const char* e = getenv("FB_KDUP"); return e ? atoi(e) : 0; }();
+  return m;
+}
 #else
 bool pdl_enabled() { return true; }
 static constexpr int skip_mask() { return 0; }
+static constexpr int dup_mask() { return 0; }
 #endif
 
 struct ProfSpan { cudaEvent_t a, b; int cat; };
@@ -435,9 +440,15 @@ struct Run {
   const void* at(const void* base, size_t elem) const { return (const char*)base + elem * TS; }
   void chk(int r) { if (rc == FB_OK && r != FB_OK) rc = r; }
   // category-tagged launch of a non-GEMM stage
-  template <typename F> void stage(int cat, F f) {
+  // kid (diagnostic builds): kernel id for FB_KDUP=<bitmask> -- the masked kernels are launched TWICE (all of them are idempotent:
+  // outputs never alias inputs), so the in-situ cost of one instance can be read off as a difference of step times with the results
+  // intact.  0 gcl_edge_pre, 1 gcl_node, 2 row_attention, 3 pair_gather, 4 inter_logit + inter_aggregate is NOT idempotent (h += ...)
+  // and has no id, 5 radial, 6 las_step
+  template <typename F> void stage(int cat, F f, int kid = -1) {
     if (skip_mask() >> cat & 1) return;
-    prof_begin(cat, st); chk(f()); prof_end(st);
+    prof_begin(cat, st); chk(f());
+    if (kid >= 0 && (dup_mask() >> kid & 1)) chk(f());
+    prof_end(st);
   }
   int gemm_cat = CAT_GEMM_NODE;
 
@@ -553,14 +564,14 @@ struct Run {
     const int n_rows = mv_only ? g.n_mv : N;
     const int* erow = mv_only ? g.mv_erow : g.ctx_row;
     const int* ecol = mv_only ? g.mv_ecol : g.ctx_col;
-    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); });
+    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.ctx_rowptr, g.ctx_row, g.ctx_col, x_in, b.radc, b.normc, st); }, 5);
     gemm_cat = CAT_GEMM_NODE;
     // the first edge-MLP Linear per node: P[:, 0:H] = h W_row^T + b1, P[:, H:2H] = h W_col^T (bias [b1 | 0] = derived slot f_e1b)
     if (!Pn_pre) gemm(hT_in, H, H, gw.e1_rc, 2 * H, gw.f_e1b, FB_ACT_NONE, N, nullptr, 0, b.Pn, 2 * H);
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_edge_pre(E, H, erow, ecol, g.node_cplx, Pn, b.radc, b.normc, F(gw.e1_rad), nullptr, b.A1, bf, st,
                           mv_only ? g.mv_emap : nullptr);
-    });
+    }, 0);
     // (profiling category = kernel class: the short edge lists of the moving-rows form run on the node-level kernels)
     gemm_cat = mv_only ? CAT_GEMM_NODE : CAT_GEMM_EDGE;
     // training-mode dropout of the v1 stack (dropout_p > 0): edge_mlp output (egnn.py:82), node_mlp output (egnn.py:106)
@@ -569,8 +580,8 @@ struct Run {
     gemm(b.M, H, H, gw.c1_w, H, gw.c1_b, FB_ACT_SILU, E, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 0, gw.c2_w, b.dotE, E);
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_node(n_rows, H, mv_only ? g.mv_rowptr : g.ctx_rowptr, ecol, b.M, b.dotE, tiles, E, x_in, p.coord_clamp,
-                      need_h ? b.agg : nullptr, x_out, bf, st, mv_only ? g.mv_rows : nullptr);
-    });
+                      need_h ? b.agg : nullptr, x_out, bf, st, mv_only ? g.mv_rows : nullptr, mv_only ? nullptr : &g);
+    }, 1);
     gemm_cat = CAT_GEMM_NODE;
     if (need_h) {
       gemm(hT_in, H, H, gw.n1_w, H, gw.n1_b, FB_ACT_SILU, N, nullptr, 0, b.T1, H, nullptr, 0, b.agg, H, H);
@@ -609,7 +620,7 @@ struct Run {
     if (!ca_ready)
       gemm_pair(proj(hT_o, aw.ca_c_w, 4 * HD, aw.ca_c_b, Nc, b.CAc, b.CAcT), proj(at(hT_o, op), aw.ca_p_w, 2 * HD, aw.ca_p_b, Np, b.CAp, b.CApT));
     ca_ready = false;
-    stage(CAT_ATTENTION, [&] { return att_p(b.PB + (size_t)(layer * 2 + 0) * P * 4); });
+    stage(CAT_ATTENTION, [&] { return att_p(b.PB + (size_t)(layer * 2 + 0) * P * 4); }, 2);
     {
       const GemmArgs g[3] = {
           mk(at(hT_o, op), H, H, aw.f_l3_w + (int64_t)2 * HD * (H + HD), 2 * H, aw.f_l3_b + 2 * HD, FB_ACT_RELU, Np, nullptr, 0, THp, 2 * H,
@@ -618,7 +629,7 @@ struct Run {
           mk(Op, HD, HD, aw.o_p_w, H, aw.o_p_b, FB_ACT_NONE, Np, h_a + op, H, at(hT_a, op), H, h_o + op, H)};
       gemm_multi(g, 3);
     }
-    stage(CAT_ATTENTION, [&] { return att_c(b.PB + (size_t)(layer * 2 + 1) * P * 4); });
+    stage(CAT_ATTENTION, [&] { return att_c(b.PB + (size_t)(layer * 2 + 1) * P * 4); }, 2);
     {
       const GemmArgs g[3] = {
           mk(THp, 2 * H, 2 * H, aw.tp2_w, H, aw.tp2_b, FB_ACT_NONE, Np, h_o + op, H, at(hT_o, op), H, h_a + op, H),
@@ -671,7 +682,7 @@ struct Run {
     // --- pair path on the unique inter pairs only
     const int capU = p.cap_int / 2;
     const int* u_dev = g.int_rowptr + Nc;  // number of compound->protein edges
-    stage(CAT_ATTENTION, [&] { return pair_gather(g, capU, H, b.P0, b.QK + 2 * H, ldqk, b.Zg, b.T64, bf, st); });
+    stage(CAT_ATTENTION, [&] { return pair_gather(g, capU, H, b.P0, b.QK + 2 * H, ldqk, b.Zg, b.T64, bf, st); }, 3);
     const int tiles2 = gemm_dot_tiles(capU, 2 * H, H, gmode);
     gemm_cat = CAT_GEMM_PAIR;
     gemm(b.Zg, H, H, aw.pt1_w, 2 * H, aw.pt1_b, FB_ACT_RELU, capU, nullptr, 0, nullptr, 0, nullptr, 0, b.T64, 64, 64,
@@ -685,7 +696,7 @@ struct Run {
 #endif
     if (!pb_fold) stage(CAT_ATTENTION, [&] { return pair_bias_finish(g, capU, b.dotU, tiles2, capU, F(aw.pt_c), b.pb_dense, st); });
     // --- interfacial attention (egnn.py:186-252)
-    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); });
+    stage(CAT_GRAPH_MISC, [&] { return radial(g, g.int_rowptr, g.int_row, g.int_col, x_in, b.radi, b.normi, st); }, 5);
     stage(CAT_ATTENTION, [&] {
       return inter_attention(g, p.cap_int, H, b.QK, ldqk, b.QK + H, ldqk, b.VT, at(b.VT, (size_t)H), 2 * H, F(aw.k_r), F(aw.v_r), F(aw.ac_u), F(aw.ac1_b), F(aw.ac2_w), b.radi,
                              b.normi, b.pb_dense, x_in, p.coord_clamp, b.h, bf ? b.hT : nullptr, x_out, att, b.lgt, b.sde, bf, st,
@@ -723,7 +734,7 @@ struct Run {
             dr(S_GCOORD)));
     stage(CAT_EDGE_ELEMWISE, [&] {
       return gcl_node(n_rows, H, mv_only ? g.mv_rowptr : g.ctx_rowptr, ecol, b.M, b.dotE, tiles, E, x_in, p.coord_clamp,
-                      need_h ? b.agg : nullptr, x_out, bf, st, mv_only ? g.mv_rows : nullptr);
+                      need_h ? b.agg : nullptr, x_out, bf, st, mv_only ? g.mv_rows : nullptr, mv_only ? nullptr : &g);
     });
     gemm_cat = CAT_GEMM_NODE;
     if (need_h) {
@@ -924,7 +935,7 @@ struct Run {
         }
         xc = bufs[k]; k ^= 1;
         if (last) tap(2 * l + 1, xc);
-        stage(CAT_GRAPH_MISC, [&] { return las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st); });
+        stage(CAT_GRAPH_MISC, [&] { return las_step(g, xc, b.xl, p.las_step, p.las_clamp, bufs[k], st); }, 6);
         xc = bufs[k]; k ^= 1;
       }
       // the out-layer node update and linear_out only matter on the last iteration

@@ -235,6 +235,8 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
 // consecutive features (16-byte loads in bf16 mode), the four edge groups take edges lo+g, lo+g+4, ...
 // with two loads in flight each, and are combined through shared memory.
 constexpr int GN_BIG = 48;   // nodes with more edges than this are reduced by the whole CTA
+// head CTAs of gcl_node_kernel: n = 2 * complexes (0 = off), offsets / complex ids in the internal node order
+struct GnHeads { int n = 0; const int* c_off = nullptr; const int* p_off = nullptr; const int* node_cplx = nullptr; };
 
 template <typename T>
 __device__ __forceinline__ void gcl_sum_rows(const T* __restrict__ M, int H, int f0, int lo, int hi, int step, float (&acc)[8]) {
@@ -278,6 +280,30 @@ __device__ __forceinline__ void gcl_sum_rows(const bf16* __restrict__ M, int H, 
   for (; e < hi; e += step, p += st) acc_bf16x8(*reinterpret_cast<const uint4*>(p), acc);
 }
 
+// coordinate update of one row by one warp (egnn.py:119-128): x_out[rn] = x[rn] + clamp(mean_e (x[rn] - x[col_e]) * s_e, +-cmax),
+// s_e = sum of the row-dot partials of the coordinate head; lanes over edges, fixed order
+__device__ __forceinline__ void gcl_coord_row(int rn, int lo, int hi, int lane, const int* __restrict__ ecol, const float* __restrict__ dot,
+                                              int dot_tiles, int dot_stride, const float* __restrict__ x, float cmax,
+                                              float* __restrict__ x_out) {
+  const float xr0 = x[3 * rn], xr1 = x[3 * rn + 1], xr2 = x[3 * rn + 2];
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  for (int e = lo + lane; e < hi; e += 32) {
+    float s = 0.f;
+    for (int k = 0; k < dot_tiles; ++k) s += dot[(size_t)k * dot_stride + e];
+    const int c = ecol[e];
+    ax = fmaf(xr0 - x[3 * c], s, ax);
+    ay = fmaf(xr1 - x[3 * c + 1], s, ay);
+    az = fmaf(xr2 - x[3 * c + 2], s, az);
+  }
+  ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+  if (lane == 0) {
+    const float cnt = fmaxf((float)(hi - lo), 1.0f);
+    x_out[3 * rn] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
+    x_out[3 * rn + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
+    x_out[3 * rn + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
+  }
+}
+
 // CTA = 4 nodes x 64 feature lanes (8 features = one 16-byte load per lane and edge row).  The rows of a
 // node are contiguous in M (edges are in CSR order), so the common case is a short streaming reduction with
 // no shared memory; the few high-degree nodes (global nodes) are then reduced by all 256 threads.
@@ -286,40 +312,64 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
                                                         const int* __restrict__ ecol, const T* __restrict__ M,
                                                         const float* __restrict__ dot, int dot_tiles, int dot_stride,
                                                         const float* __restrict__ x, float cmax, T* __restrict__ agg,
-                                                        float* __restrict__ x_out, const int* __restrict__ rmap) {
+                                                        float* __restrict__ x_out, const int* __restrict__ rmap, int diag_mode,
+                                                        GnHeads hd) {
   pdl_entry();
   extern __shared__ float part[];  // [G][H]
   const int G = blockDim.x >> 6;   // node groups (64 feature lanes each) per CTA
   const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * G + grp;
+  // ---- head CTAs (the first hd.n blocks of the grid): one per (complex, side), for that side's FIRST node when it is a high-degree
+  // row -- the global nodes, 31 / 201 context edges at PDBbind sizes.  Inside a 16-node CTA such a row doubled the CTA's critical path
+  // (its cooperative pass runs after the CTA's own rows: measured 6.6 of the kernel's 15.5 us in the step); here the whole CTA works on
+  // it from the start, coordinates included, while the other CTAs skip it.
+  if ((int)blockIdx.x < hd.n) {
+    const int b = blockIdx.x >> 1;
+    const int rk = (blockIdx.x & 1) ? hd.p_off[b] : hd.c_off[b];
+    if (rk >= N || hd.node_cplx[rk] != b) return;     // this complex has no node on that side
+    const int lk = rowptr[rk], hk = rowptr[rk + 1];
+    if (hk - lk <= GN_BIG) return;            // an ordinary row: its own CTA takes it
+    // coordinates: ONE warp, the very arithmetic of the ordinary path (bit-identical results whichever CTA takes the row), while the
+    // other 31 warps already gather the feature rows
+    if (threadIdx.x < 32) gcl_coord_row(rk, lk, hk, lane, ecol, dot, dot_tiles, dot_stride, x, cmax, x_out);
+    if (agg == nullptr) return;
+    for (int f0 = t * 8; f0 < H; f0 += 512) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      gcl_sum_rows(M, H, f0, lk + grp, hk, G, acc);
+      st8(&part[grp * H + f0], acc);
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < H; f += blockDim.x) {      // fixed summation order over the groups: deterministic
+      float o = 0.f;
+      for (int j = 0; j < G; ++j) o += part[j * H + f];
+      agg[(size_t)rk * H + f] = from_f<T>(o);
+    }
+    return;
+  }
+  const int cta = blockIdx.x - hd.n;
+  const int r = cta * G + grp;
   // row pointers of the CTA's G nodes, read once: the cooperative pass below walks them serially
   __shared__ int s_rp[33];
-  if (threadIdx.x <= G) s_rp[threadIdx.x] = rowptr[min(blockIdx.x * G + (int)threadIdx.x, N)];
+  __shared__ int s_head[32];       // 1: a head CTA owns this (high-degree, first-of-side) row
+  if (threadIdx.x <= G) s_rp[threadIdx.x] = rowptr[min(cta * G + (int)threadIdx.x, N)];
+  if (threadIdx.x < G) {
+    const int rr = cta * G + threadIdx.x;
+    int own = 0;
+    if (hd.n > 0 && rr < N) {
+      const int b = hd.node_cplx[rr];
+      own = (rr == hd.c_off[b] || rr == hd.p_off[b]) && (rowptr[rr + 1] - rowptr[rr] > GN_BIG);
+    }
+    s_head[threadIdx.x] = own;
+  }
   __syncthreads();
   int lo = 0, hi = 0;
   if (r < N) { lo = s_rp[grp]; hi = s_rp[grp + 1]; }
+  const bool head_owned = s_head[grp] != 0;
   // coordinate part: first warp of each group, lanes over edges
-  if (r < N && t < 32) {
-    const int rn = rmap ? rmap[r] : r;      // node id of this row
-    const float xr0 = x[3 * rn], xr1 = x[3 * rn + 1], xr2 = x[3 * rn + 2];
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    for (int e = lo + lane; e < hi; e += 32) {
-      float s = 0.f;
-      for (int k = 0; k < dot_tiles; ++k) s += dot[(size_t)k * dot_stride + e];
-      const int c = ecol[e];
-      ax = fmaf(xr0 - x[3 * c], s, ax);
-      ay = fmaf(xr1 - x[3 * c + 1], s, ay);
-      az = fmaf(xr2 - x[3 * c + 2], s, az);
-    }
-    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-    if (lane == 0) {
-      const float cnt = fmaxf((float)(hi - lo), 1.0f);
-      x_out[3 * rn] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
-      x_out[3 * rn + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
-      x_out[3 * rn + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
-    }
-  }
+  if (r < N && t < 32 && !head_owned) gcl_coord_row(rmap ? rmap[r] : r, lo, hi, lane, ecol, dot, dot_tiles, dot_stride, x, cmax, x_out);
   if (agg == nullptr) return;
+#ifdef FB_DIAG
+  if (diag_mode & 2) return;                 // timing probe: no feature part at all (results are garbage)
+#endif
   if (r < N && hi - lo <= GN_BIG) {
     for (int f0 = t * 8; f0 < H; f0 += 512) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -329,11 +379,14 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
   }
   // cooperative pass for the high-degree nodes (global nodes) of this CTA: all G groups stride over the edge
   // rows of the node, so its ~200 rows cost ~200/G/4 load round trips (block-uniform control flow)
+#ifdef FB_DIAG
+  if (diag_mode & 1) return;                 // timing probe: no cooperative pass for the high-degree rows
+#endif
   for (int k = 0; k < G; ++k) {
-    const int rk = blockIdx.x * G + k;
+    const int rk = cta * G + k;
     if (rk >= N) break;
     const int lk = s_rp[k], hk = s_rp[k + 1];
-    if (hk - lk <= GN_BIG) continue;
+    if (hk - lk <= GN_BIG || s_head[k]) continue;
     for (int f0 = t * 8; f0 < H; f0 += 512) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       gcl_sum_rows(M, H, f0, lk + grp, hk, G, acc);
@@ -351,14 +404,30 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
 }
 
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
-             int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st, const int* rmap) {
+             int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st, const int* rmap,
+             const GraphDev* heads) {
   if (H & 7) return FB_ERR_UNSUPPORTED;
   if (rmap && agg) return FB_ERR_BAD_ARG;
   const int G = 16;
   const int smem = G * H * 4;
-  const int grid = (N + G - 1) / G;
-  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out, rmap);
-  else fb_launch(gcl_node_kernel<float>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out, rmap);
+  GnHeads hd;
+  // head CTAs only for the full node list in the library's own order (rows = node ids, complexes with both sides)
+  if (heads && !rmap && heads->B > 0 && heads->c_off && heads->p_off && heads->node_cplx) {
+    hd.n = 2 * heads->B; hd.c_off = heads->c_off; hd.p_off = heads->p_off; hd.node_cplx = heads->node_cplx;
+  }
+#ifdef FB_DIAG
+  static const bool no_heads = [] { const char* e = getenv("FB_GN_HEADS"); return e && atoi(e) == 0; }();
+  if (no_heads) hd = GnHeads();
+#endif
+  const int grid = (N + G - 1) / G + hd.n;
+#ifdef FB_DIAG
+  static const int diag_mode = [] { const char* e = getenv("FB_GN_MODE"); return e ? atoi(e) : 0; }();
+  if (diag_mode & 4) return FB_OK;           // timing probe: kernel not launched
+#else
+  const int diag_mode = 0;
+#endif
+  if (bf16_mode) fb_launch(gcl_node_kernel<bf16>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const bf16*)M, dot, dot_tiles, dot_stride, x, cmax, (bf16*)agg, x_out, rmap, diag_mode, hd);
+  else fb_launch(gcl_node_kernel<float>, dim3(grid), dim3(64 * G), smem, st, N, H, rowptr, ecol, (const float*)M, dot, dot_tiles, dot_stride, x, cmax, (float*)agg, x_out, rmap, diag_mode, hd);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;
@@ -647,6 +716,7 @@ int pair_bias_finish(const GraphDev& g, int cap_u, const float* dot, int tiles, 
 // with mu_e / rstd_e from the per-node sums vstat[c] = {sum V, sum V^2, sum V*v_r} and ac_r = {sum v_r, sum v_r^2}.
 struct PbDot { const float* dot = nullptr; int tiles = 0, stride = 0, n_u = 0; const float* cst = nullptr; };
 
+
 template <typename T, int VEC, bool PLUS>
 __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, const float* __restrict__ QK, int ldqk,
                                                           const float* __restrict__ Kt, int ldk, const T* __restrict__ VC, int ldv,
@@ -680,6 +750,8 @@ __global__ void __launch_bounds__(256) inter_logit_kernel(GraphDev g, int H, con
       // row, whose columns are sorted) -- saves the pair_bias_finish launch and the dense scatter
       int u = e;
       if (e >= g.int_rowptr[g.Nc_tot]) {
+        // (a dense pair -> edge table written by the graph fill pass, one load instead of this search, was measured: no difference in
+        // the step -- the kernel is bound by the gathers' latency, not by this chain)
         int lo = g.int_rowptr[c], hi = g.int_rowptr[c + 1] - 1;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.int_col[mid] < r) lo = mid + 1; else hi = mid; }
         u = lo;
@@ -822,15 +894,32 @@ int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int 
   if (H > 512 || (H & 3)) return FB_ERR_UNSUPPORTED;
   PbDot pd;
   if (pb_dot) { pd.dot = pb_dot; pd.tiles = pb_tiles; pd.stride = pb_stride; pd.cst = pb_cst; pd.n_u = -1; }
-  const int grid1 = std::max(1, std::min(148 * 8, (cap_int + 7) / 8));
   const bool plus = vstat != nullptr;
+  // grid = exactly ONE wave of resident CTAs (occupancy query per instantiation, cached): a fixed 148 x 8 CTAs ran as 1.33 waves of the
+  // CTAs per SM the kernel fits -- the straggling third paid the kernel's latency chain a second time
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+#define FB_IL_K(K, T, SMEM)                                                                                                  \
+  do {                                                                                                                       \
+    static int per_sm = 0;                                                                                                   \
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, 256, SMEM) != cudaSuccess || per_sm < 1)) per_sm = 4; \
+    const int grid1 = std::max(1, std::min(sms * per_sm, (cap_int + 7) / 8));                                                \
+    fb_launch(K, dim3(grid1), dim3(256), SMEM, st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, ac_w2, ac_g, ac_r, vstat, \
+              eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord, pd);                                                   \
+  } while (0)
 #define FB_IL(T, VEC)                                                                                                        \
   do {                                                                                                                       \
-    if (plus) fb_launch(inter_logit_kernel<T, VEC, true>, dim3(grid1), dim3(256), 5 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
-                        ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord, pd);                \
-    else fb_launch(inter_logit_kernel<T, VEC, false>, dim3(grid1), dim3(256), 4 * H * sizeof(float), st, g, H, QK, ldqk, Kt, ldk, (const T*)VC, ldv, k_r, ac_u, ac_b, \
-                   ac_w2, ac_g, ac_r, vstat, eps, rad, norm, pb_dense, logit_ws, sdot_ws, drop_coord, pd);                     \
+    if (plus) FB_IL_K((inter_logit_kernel<T, VEC, true>), T, 5 * H * sizeof(float));                                          \
+    else FB_IL_K((inter_logit_kernel<T, VEC, false>), T, 4 * H * sizeof(float));                                              \
   } while (0)
+#ifdef FB_DIAG
+  static const bool dup_il = [] { const char* e = getenv("FB_KDUP"); return e && (atoi(e) >> 4 & 1); }();
+  if (dup_il && bf16_mode && H > 256) FB_IL(bf16, 4);       // timing probe (forward.cu: FB_KDUP): inter_logit twice, idempotent
+#endif
   if (bf16_mode) {
     if (H <= 128) FB_IL(bf16, 1); else if (H <= 256) FB_IL(bf16, 2); else FB_IL(bf16, 4);
     fb_launch(inter_aggregate_kernel<bf16>, dim3(g.N), dim3(128), 0, st, g, H, (const bf16*)V, ldv, v_r, rad, norm, logit_ws, sdot_ws, x,
@@ -841,6 +930,7 @@ int inter_attention(const GraphDev& g, int cap_int, int H, const float* QK, int 
               cmax, h, (float*)hT, x_out, att, drop_agg);
   }
 #undef FB_IL
+#undef FB_IL_K
   count_launch(2);
   FB_CHECK_LAUNCH();
   return FB_OK;

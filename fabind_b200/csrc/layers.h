@@ -17,7 +17,9 @@ int gcl_edge_pre(int E, int H, const int* erow, const int* ecol, const int* node
                  cudaStream_t st, const int* emap = nullptr /* rad is indexed by emap[e] (compact edge subsets) */);
 int gcl_node(int N, int H, const int* rowptr, const int* ecol, const void* M, const float* dot, int dot_tiles,
              int dot_stride, const float* x, float cmax, void* agg, float* x_out, bool bf16_mode, cudaStream_t st,
-             const int* rmap = nullptr /* row j of rowptr is node rmap[j] (compact row subsets; agg must be null) */);
+             const int* rmap = nullptr /* row j of rowptr is node rmap[j] (compact row subsets; agg must be null) */,
+             const GraphDev* heads = nullptr /* layout of the batch: the high-degree first-of-side rows (global nodes) get CTAs of
+                                               their own (rows must be node ids in the library's order) */);
 int pair_outer(const GraphDev& g, int P_total, int H, const float* pc, void* A0, bool bf16_mode, cudaStream_t st);
 int pair_bias_gate(int P_total, int L, const float* raw, int ld_raw, float* PB, cudaStream_t st);
 int row_attention(const GraphDev& g, int q_is_prot, int max_q, int max_k, const float* Q, int ldq, const float* G, int ldg,
