@@ -508,7 +508,7 @@ constexpr int RA_KC = 256;
 // chunks); the scaled queries sit in shared memory too (broadcast reads), so the register footprint stays small and
 // many warps are resident: the kernel is a chain of global -> smem -> compute latencies, not throughput.
 template <typename T, int NQ>
-__global__ void __launch_bounds__(512) row_attention_kernel(GraphDev g, int q_is_prot, int KC, const float* __restrict__ Q, int ldq,
+__global__ void __launch_bounds__(512, NQ == 4 ? 2 : 1) row_attention_kernel(GraphDev g, int q_is_prot, int KC, const float* __restrict__ Q, int ldq,
                                                             const float* __restrict__ G, int ldg,
                                                             const float* __restrict__ Kb, int ldk,
                                                             const float* __restrict__ Vb, int ldv,
@@ -622,16 +622,27 @@ int row_attention(const GraphDev& g, int q_is_prot, int max_q, int max_k, const 
   // few queries over long key lists (compound queries over a pocket): one query per warp, 8 warps, so that more CTAs
   // share the work; many queries over short key lists: 16 warps x 2 queries
   const bool one = max_q <= 64;
-  const int nw = one ? 8 : 16, nq = one ? 1 : 2;
+  int nw = one ? 8 : 16, nq = one ? 1 : 2;
+  // many queries: the 62-register kernel keeps two 512-thread CTAs per SM, and (tiles x complexes x heads) CTAs of 32 queries ran as
+  // 1.5 waves at B = 16 (448 CTAs on 296 slots); four queries per warp (64 per CTA) make it one wave -- the per-query work over a
+  // ligand's ~31 keys is small next to the CTA's staging latency, which the second wave paid again
+  if (!one && bf16_mode) {
+    const long long ctas2 = (long long)((max_q + 31) / 32) * g.B * 4, ctas4 = (long long)((max_q + 63) / 64) * g.B * 4;
+    if (ctas2 > 2 * 148 && ctas4 <= 2 * 148) nq = 4;
+  }
+#ifdef FB_DIAG
+  static const bool ra_nq4_off = [] { const char* e = getenv("FB_RA_NQ4"); return e && atoi(e) == 0; }();
+  if (ra_nq4_off && nq == 4) nq = 2;
+#endif
   const int smem = (KC * (33 + 32) + nw * nq * 32) * 4;
   dim3 grid((max_q + nw * nq - 1) / (nw * nq), g.B, 4);
-  static unsigned long long done[4] = {0, 0, 0, 0};
+  static unsigned long long done[5] = {0, 0, 0, 0, 0};
 #define FB_RA(T, NQ, slot)                                                                                              \
   do {                                                                                                                  \
-    if (!ensure_smem_optin(row_attention_kernel<T, NQ>, (RA_KC * 65 + 16 * 2 * 32) * 4, done[slot])) return FB_ERR_CUDA; \
+    if (!ensure_smem_optin(row_attention_kernel<T, NQ>, (RA_KC * 65 + 16 * NQ * 32) * 4, done[slot])) return FB_ERR_CUDA; \
     fb_launch(row_attention_kernel<T, NQ>, grid, dim3(nw * 32), smem, st, g, q_is_prot, KC, Q, ldq, G, ldg, K, ldk, V, ldv, PB, (T*)O, ldo); \
   } while (0)
-  if (bf16_mode) { if (one) FB_RA(bf16, 1, 0); else FB_RA(bf16, 2, 1); }
+  if (bf16_mode) { if (one) FB_RA(bf16, 1, 0); else if (nq == 4) FB_RA(bf16, 4, 4); else FB_RA(bf16, 2, 1); }
   else { if (one) FB_RA(float, 1, 2); else FB_RA(float, 2, 3); }
 #undef FB_RA
   count_launch(1);
