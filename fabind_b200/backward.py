@@ -259,13 +259,14 @@ def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new, drop=None,
     grads = {}
     # coordinate branch
     dx, ds = coord_step_bwd(x, row, col, saved["s"], saved["step"], saved["deg"], cmax, dx_new)
-    T3 = act_fwd(saved["Z3"], ACT_SILU)
+    T3 = saved["T3"] if "T3" in saved else act_fwd(saved["Z3"], ACT_SILU)
     grads["c2_w"] = colsum(T3, ds)
     dZ3 = outer_act_bwd(saved["Z3"], ds, w["c2_w"], ACT_SILU)        # dZ3[e,f] = ds[e] c2[f] silu'(Z3[e,f])
-    M = _drop(drop, act_fwd(saved["Z2"], ACT_SILU), layer, "edge2")   # the edge message as the forward used it (egnn.py:82)
+    # the edge message as the forward used it (egnn.py:82)
+    M = saved["M"] if "M" in saved else _drop(drop, act_fwd(saved["Z2"], ACT_SILU), layer, "edge2")
     dM = _linear_bwd(grads, "c1_w", "c1_b", w["c1_w_t"], M, dZ3)
     # node branch: h_new = h + drop(n2(silu(n1([h | agg]))))
-    t1 = act_fwd(saved["Z4"], ACT_SILU)
+    t1 = saved["t1"] if "t1" in saved else act_fwd(saved["Z4"], ACT_SILU)
     dt1 = _linear_bwd(grads, "n2_w", "n2_b", w["n2_w_t"], t1, _drop(drop, dh_new, layer, "node2"))
     dZ4 = act_bwd(saved["Z4"], dt1, ACT_SILU)
     cat = torch.empty(N, 2 * H, dtype=torch.float32, device=h.device)
@@ -275,7 +276,7 @@ def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new, drop=None,
     gather_add_rows(dcat, row, dM, col0=H)                    # dM[e] += dagg[row[e]]
     # edge MLP (dM is the gradient of the DROPPED message)
     dZ2 = act_bwd(saved["Z2"], _drop(drop, dM, layer, "edge2"), ACT_SILU)
-    A1 = act_fwd(saved["Z1"], ACT_SILU)
+    A1 = saved["A1"] if "A1" in saved else act_fwd(saved["Z1"], ACT_SILU)
     dA1 = _linear_bwd(grads, "e2_w", "e2_b", w["e2_w_t"], A1, dZ2)
     dZ1 = act_bwd(saved["Z1"], dA1, ACT_SILU)
     grads["e1_b"] = colsum(dZ1)
@@ -417,7 +418,7 @@ def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0, drop=None, layer=
     # interfacial coordinate update
     dx, dw = coord_step_bwd(x, row, col, vec_mul(alpha, se), sv["step"], None, cmax, dx_new)
     dalpha, dse = vec_mul(dw, se), vec_mul(dw, alpha)
-    grads["ac2_w"] = colsum(act_fwd(sv["zc"], ACT_SILU), dse)
+    grads["ac2_w"] = colsum(sv["Tzc"] if "Tzc" in sv else act_fwd(sv["zc"], ACT_SILU), dse)
     dzc = outer_act_bwd(sv["zc"], dse, w["ac2_w"], ACT_SILU)
     grads["ac1_b"] = colsum(dzc)
     grads["ac_u"] = colsum(dzc, rn)
@@ -448,7 +449,7 @@ def att_backward(w, sv, geo, row, col, cmax, dh3, dx_new, dP0, drop=None, layer=
     dpbu = gather_rows(dpb_dense, sv["u_pair"])                      # [U,1]
     grads["pt_c"] = colsum(dpbu)
     dpbu = dpbu.view(-1)
-    grads["pt2v"] = colsum(act_fwd(sv["Zp"], ACT_RELU), dpbu)
+    grads["pt2v"] = colsum(sv["Tzp"] if "Tzp" in sv else act_fwd(sv["Zp"], ACT_RELU), dpbu)
     dZp = outer_act_bwd(sv["Zp"], dpbu, w["pt2v"], ACT_RELU)
     dz = _linear_bwd(grads, "pt1_w", "pt1_b", _pt1_padded(w, "pt1_w_t", H), sv["zcat"], dZp)
     if grads["pt1_w"].shape[1] != H + 64:
@@ -645,10 +646,14 @@ def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax, drop=None, layer=0)
     gather_add_rows(Pn, col, Z1, col0=H)
     rank1_add(Z1, rn, w["e1_rad"])
     rank1_add(Z1, _ones(E, dev), w["e1_b"])
-    Z2 = linear(act_fwd(Z1, ACT_SILU), w["e2_w"], w["e2_b"])
+    # the activations the reverse pass multiplies with (A1, M, T3, t1) are kept next to their pre-activations: recomputing them cost four
+    # passes over [E, H] per sub-layer (35 us each at B = 16)
+    A1 = act_fwd(Z1, ACT_SILU)
+    Z2 = linear(A1, w["e2_w"], w["e2_b"])
     M = _drop(drop, act_fwd(Z2, ACT_SILU), layer, "edge2")            # egnn.py:82
     Z3 = linear(M, w["c1_w"], w["c1_b"])
-    s = rowdot(act_fwd(Z3, ACT_SILU), w["c2_w"])
+    T3 = act_fwd(Z3, ACT_SILU)
+    s = rowdot(T3, w["c2_w"])
     ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)
     scatter_add_rows(scale_rows(d.clone(), s), row, ssum)
     deg = torch.zeros(N, 1, dtype=torch.float32, device=dev)
@@ -661,8 +666,10 @@ def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax, drop=None, layer=0)
     cat[:, :H].copy_(h)
     cat[:, H:].copy_(agg)
     Z4 = linear(cat, w["n1_w"], w["n1_b"])
-    h_new = linear(act_fwd(Z4, ACT_SILU), w["n2_w"], w["n2_b"], res=h, drop=(drop, layer, "node2", 0))   # egnn.py:106
-    return h_new, x_new, dict(h=h, x=x, rn=rn, nrm=nrm, Z1=Z1, Z2=Z2, Z3=Z3, s=s, deg=deg, step=step, agg=agg, Z4=Z4)
+    t1 = act_fwd(Z4, ACT_SILU)
+    h_new = linear(t1, w["n2_w"], w["n2_b"], res=h, drop=(drop, layer, "node2", 0))   # egnn.py:106
+    return h_new, x_new, dict(h=h, x=x, rn=rn, nrm=nrm, Z1=Z1, Z2=Z2, Z3=Z3, s=s, deg=deg, step=step, agg=agg, Z4=Z4,
+                              A1=A1, M=M, T3=T3, t1=t1)
 
 
 def interface_indices(row, col, geo):
@@ -733,7 +740,8 @@ def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax, drop=No
     zcat[:, :H].copy_(gather_rows(P0, idx["u_pair"]))
     zcat[:, H:H + 32].copy_(vec_mul(gather_rows(pc32, idx["u_pi"]), gather_rows(pc32, idx["u_ci"])))
     Zp = linear(zcat, _pt1_padded(w, "pt1_w", H), w["pt1_b"])
-    pbu = rowdot(act_fwd(Zp, ACT_RELU), w["pt2v"]).view(U, 1)
+    Tzp = act_fwd(Zp, ACT_RELU)
+    pbu = rowdot(Tzp, w["pt2v"]).view(U, 1)
     rank1_add(pbu, _ones(U, dev), w["pt_c"])
     pb_dense = torch.zeros(P0.shape[0], 1, dtype=torch.float32, device=dev)
     scatter_add_rows(pbu, idx["u_pair"], pb_dense)                      # unique pair rows: the sum is an assignment
@@ -751,11 +759,12 @@ def att_forward_train(w, h, x, geo, row, col, idx, P0, PB_p, PB_c, cmax, drop=No
         scatter_add_rows(ve, row, h3)
     zc = rank1_add(gather_rows(QK, col, 3 * H + 128, H), rn, w["ac_u"])
     rank1_add(zc, _ones(E, dev), w["ac1_b"])
-    se = rowdot(act_fwd(zc, ACT_SILU), w["ac2_w"])
+    Tzc = act_fwd(zc, ACT_SILU)
+    se = rowdot(Tzc, w["ac2_w"])
     ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)
     scatter_add_rows(scale_rows(d.clone(), vec_mul(alpha, se)), row, ssum)
     step, x_new = coord_apply(x, ssum, None, cmax)
-    sv = dict(h_in=h, x=x, CAc=CAc, CAp=CAp, CAp2=CAp2, PB_p=PB_p, PB_c=PB_c, Op=Op, Oc=Oc, hp1=hp1, hc1=hc1, Ttp=Ttp, Ttc=Ttc, h2=h2, QK=QK,
+    sv = dict(Tzc=Tzc, Tzp=Tzp, h_in=h, x=x, CAc=CAc, CAp=CAp, CAp2=CAp2, PB_p=PB_p, PB_c=PB_c, Op=Op, Oc=Oc, hp1=hp1, hc1=hc1, Ttp=Ttp, Ttc=Ttc, h2=h2, QK=QK,
               pc32=pc32, pair=idx["pair"], u_pair=idx["u_pair"], u_pi=idx["u_pi"], u_ci=idx["u_ci"], zcat=zcat, Zp=Zp, rn=rn, nrm=nrm,
               alpha=alpha, se=se, zc=zc, step=step)
     return h3, x_new, sv

@@ -394,9 +394,13 @@ def check_forward(case, X_out, H_out, tape, top, tol):
     assert rel_err(X_out, case["x_out"]) < tol and rel_err(H_out, case["h_final"]) < tol
     for k in ("pc", "outer", "P0", "raw_full", "h_last"):
         assert rel_err(top[k], case["top"][k]) < tol, k
+    # activations the product's forward keeps NEXT TO their pre-activations so that the reverse pass does not recompute them (derived
+    # values: A1 = silu(Z1), M = drop(silu(Z2)), T3 = silu(Z3), t1 = silu(Z4), Tzc = silu(zc), Tzp = relu(Zp)); the specification keeps
+    # the pre-activations only
+    cached = {"A1", "M", "T3", "t1", "Tzc", "Tzp"}
     for mine, ref in zip(tape + [(top["out_saved"],)], case["tape"] + [(case["top"]["out_saved"],)]):
         for sm, sr in zip(mine, ref):
-            assert set(sm) == set(sr), set(sm) ^ set(sr)
+            assert set(sm) - cached == set(sr), (set(sm) - cached) ^ set(sr)
             for k in sr:
                 if sr[k].dtype == torch.int32:
                     assert torch.equal(sm[k].cpu(), sr[k]), k
