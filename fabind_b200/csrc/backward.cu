@@ -879,6 +879,49 @@ int32_t fb_transpose_bf16(const float* src, int32_t ld, int32_t M, int32_t N, vo
   return FB_OK;
 }
 
+// Batched form for the weight arena (training step: every matrix slot needs its transposed bf16 twin once per optimizer step, the
+// operand of the data-gradient GEMMs): desc[4 i .. 4 i + 3] = {source element offset, rows, cols, destination element offset}, slot i
+// = arena[off : off + rows * cols] as [rows, cols] fp32 -> dst[doff : doff + rows * cols] as [cols, rows] bf16; tile_begin[i] = first
+// 32 x 32 tile of slot i in the launch's tile list (tile_begin[n] = total).  One launch instead of one per slot.
+__global__ void __launch_bounds__(256) transpose_slots_kernel(const float* __restrict__ arena, const long long* __restrict__ desc,
+                                                              const int* __restrict__ tile_begin, int n, bf16* __restrict__ dst) {
+  pdl_entry();
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int total = tile_begin[n];
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int lo = 0, hi = n;                       // tile_begin[lo] <= t < tile_begin[hi]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tile_begin[mid] <= t) lo = mid; else hi = mid; }
+    const long long off = desc[4 * lo], doff = desc[4 * lo + 3];
+    const int R = (int)desc[4 * lo + 1], Cc = (int)desc[4 * lo + 2];
+    const int tiles_r = (R + 31) / 32, local = t - tile_begin[lo];
+    const int r0 = (local % tiles_r) * 32, c0 = (local / tiles_r) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + 8 * i, c = c0 + tx;
+      tile[ty + 8 * i][tx] = (r < R && c < Cc) ? arena[off + (long long)r * Cc + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i, r = r0 + tx;
+      if (c < Cc && r < R) dst[doff + (long long)c * R + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+    }
+    __syncthreads();
+  }
+}
+
+int32_t fb_transpose_slots_bf16(const float* arena, const int64_t* desc, const int32_t* tile_begin, int32_t n, int32_t n_tiles, void* dst,
+                                void* stream) {
+  if (n <= 0 || n_tiles <= 0) return FB_OK;
+  if (!arena || !desc || !tile_begin || !dst) return FB_ERR_BAD_ARG;
+  fb_launch(transpose_slots_kernel, dim3(n_tiles < 148 * 16 ? n_tiles : 148 * 16), dim3(256), 0, (cudaStream_t)stream, arena,
+            (const long long*)desc, (const int*)tile_begin, (int)n, (bf16*)dst);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
 // dst[m, n] = keep(seed, site, row0 + m, n) ? src[m, n] / (1 - p) : 0  -- the library's counter-based dropout mask (common.cuh) as a
 // stand-alone op: the training-mode forward applies it where the inference path has it fused into an epilogue, and the reverse
 // pass applies the SAME mask to the incoming gradient (the mask is a pure function of its coordinates, nothing is stored).

@@ -416,7 +416,12 @@ class FastPackerV1:
         H = self.H
         sd = self.sd if sd is None else sd
         theta = torch.cat([sd[k].detach().reshape(-1).to(self.device, torch.float32) for k in self.names])
-        arena = torch.zeros(self.n_arena, dtype=torch.float32, device=self.device)
+        # ONE arena buffer per packer, rewritten in place every step: every element that is not a zero pad is overwritten below, the
+        # pads are zeroed once.  (Two forwards before a backward see the same weights, hence the same values; train.slot_tensors keys
+        # its cached views on this buffer.)
+        arena = getattr(self, "_arena", None)
+        if arena is None:
+            arena = self._arena = torch.zeros(self.n_arena, dtype=torch.float32, device=self.device)
         arena[self.dst] = theta[self.src]
         for l in range(self.L):
             k = self._att_keys(l)

@@ -361,6 +361,12 @@ int32_t fb_vec_op(const float* a, const float* b, float* c, int64_t n, int32_t o
 /* dst[n, m] = bf16(src[m, n]) (m < M; zero for M <= m < Mp), dst row stride Mp: the K-major operands of the weight-gradient GEMM
  * dW = dY^T X on tcgen05 (reduction over the rows) */
 int32_t fb_transpose_bf16(const float* src, int32_t ld, int32_t M, int32_t N, void* dst, int32_t Mp, void* stream);
+/* ABI 6: the same for a whole weight arena in ONE launch (training step: the transposed bf16 twin of every matrix slot, once per optimizer
+ * step; reference: the `weight.t()` views autograd takes in `loss.backward()`, main_fabind.py:380-401).  desc[4 i .. 4 i + 3] = {source
+ * element offset, rows, cols, destination element offset} (device int64), tile_begin[0 .. n] (device int32) = running count of 32 x 32
+ * tiles, n_tiles = tile_begin[n]; slot i is written as [cols, rows] bf16 at dst + destination offset. */
+int32_t fb_transpose_slots_bf16(const float* arena, const int64_t* desc, const int32_t* tile_begin, int32_t n, int32_t n_tiles, void* dst,
+                                void* stream);
 /* nn.Dropout of the training step (egnn.py:82,106,236,398,461; cross_att.py:128) as a stand-alone op, forward and reverse alike:
  * dst[m,n] = keep(seed, site, row0 + m, n) ? src[m,n] / (1-p) : 0 with the library's counter-based mask (fb_model_params.dropout_*);
  * dst may alias src */
