@@ -411,11 +411,63 @@ class FastPackerV1:
         off, r, c = self.slot[name]
         return arena[off:off + r * c].view(r, c)
 
+    # ---- all L layers at once: the parameters of att_0 .. att_{L-1} sit at a constant stride in the flat state_dict order, and so do
+    # their arena slots, so [L, ...] views exist without a copy (checked once; otherwise the per-layer loops below run)
+    def _layers_stackable(self):
+        ok = getattr(self, "_stack_ok", None)
+        if ok is not None:
+            return ok
+        ok = self.L >= 1
+        self._pstride, self._sstride = 0, 0
+        if self.L > 1:
+            keys = [self._att_keys(l) for l in range(self.L)]
+            d = {self.off[keys[l + 1][n]][0] - self.off[keys[l][n]][0] for l in range(self.L - 1) for n in keys[0]}
+            ds = {self.slot[f"att{l + 1}.{b}"][0] - self.slot[f"att{l}.{b}"][0] for l in range(self.L - 1)
+                  for b in ("pt1_w", "pt1_b", "pt2v", "pt_c", "qk_w", "qk_b", "ac_u")}
+            ok = len(d) == 1 and len(ds) == 1
+            if ok:
+                self._pstride, self._sstride = d.pop(), ds.pop()
+        self._stack_ok = ok
+        return ok
+
+    @staticmethod
+    def _cstrides(shape):
+        st, acc = [], 1
+        for n in reversed(shape):
+            st.append(acc)
+            acc *= n
+        return tuple(reversed(st))
+
+    def _pstack(self, flat, n):
+        """[L, *shape] view of parameter `n` (short name of _att_keys) of all layers inside a flat state_dict-ordered vector"""
+        o, _, shape = self.off[self._att_keys(0)[n]]
+        return flat.as_strided((self.L,) + tuple(shape), (self._pstride,) + self._cstrides(shape), flat.storage_offset() + o)
+
+    def _sstack(self, arena, base):
+        """[L, rows, cols] view of slot att<l>.<base> of all layers inside a flat arena"""
+        off, r, c = self.slot["att0." + base]
+        return arena.as_strided((self.L, r, c), (self._sstride, c, 1), arena.storage_offset() + off)
+
+    def _theta_from(self, sd):
+        """flat fp32 copy of the floating parameters in state_dict order, in ONE persistent buffer (a few fused multi-tensor copies
+        instead of one conversion + one slice of a concatenation per parameter)"""
+        th = getattr(self, "_theta", None)
+        if th is None:
+            th = self._theta = torch.empty(self.total, dtype=torch.float32, device=self.device)
+            self._theta_views = [th[o:o + n].view(shape) for _, o, n, shape in self.layout]
+        src = [sd[k].detach() for k in self.names]
+        if all(t.device == self.device and t.dtype == torch.float32 for t in src):
+            torch._foreach_copy_(self._theta_views, src)
+        else:
+            for v, t in zip(self._theta_views, src):
+                v.copy_(t)
+        return th
+
     def pack(self, sd=None):
         """fp32 arena on self.device from the live state_dict tensors (same values as pack_state_dict)"""
         H = self.H
         sd = self.sd if sd is None else sd
-        theta = torch.cat([sd[k].detach().reshape(-1).to(self.device, torch.float32) for k in self.names])
+        theta = self._theta_from(sd)
         # ONE arena buffer per packer, rewritten in place every step: every element that is not a zero pad is overwritten below, the
         # pads are zeroed once.  (Two forwards before a backward see the same weights, hence the same values; train.slot_tensors keys
         # its cached views on this buffer.)
@@ -423,6 +475,19 @@ class FastPackerV1:
         if arena is None:
             arena = self._arena = torch.zeros(self.n_arena, dtype=torch.float32, device=self.device)
         arena[self.dst] = theta[self.src]
+        if self._layers_stackable():
+            t = {n: self._pstack(theta, n).double() for n in self._att_keys(0)}
+            Wkv, bkv, ac1 = t["Wkv"], t["bkv"], t["ac1"]
+            wb = t["wb"][:, 0]                                                        # [L, 2H]
+            S = lambda base: self._sstack(arena, base)
+            S("pt1_w")[:, :, H:H + 32] = (t["W1p"] @ t["Wo"]).float()
+            S("pt1_b")[:, 0] = (t["b1"] + (t["W1p"] @ t["bo"].unsqueeze(-1)).squeeze(-1)).float()
+            S("pt2v")[:, 0] = (t["W2"].transpose(1, 2) @ wb.unsqueeze(-1)).squeeze(-1).float()
+            S("pt_c")[:, 0, 0] = ((wb * t["b2"]).sum(-1) + t["bb"][:, 0]).float()
+            S("qk_w")[:, 3 * H + QKX:] = (ac1 @ Wkv[:, 1::2, 1:]).float()
+            S("qk_b")[:, 0, 3 * H + QKX:] = (ac1 @ bkv[:, 1::2].unsqueeze(-1)).squeeze(-1).float()
+            S("ac_u")[:, 0] = (ac1 @ Wkv[:, 1::2, 0].unsqueeze(-1)).squeeze(-1).float()
+            return arena
         for l in range(self.L):
             k = self._att_keys(l)
             t = {n: self._view(theta, key).double() for n, key in k.items()}
@@ -445,6 +510,38 @@ class FastPackerV1:
         garena = garena.reshape(-1).to(self.device, torch.float32)
         g = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         g.index_add_(0, self.src, garena[self.dst])
+        if self._layers_stackable() and garena.is_contiguous():
+            theta = self._theta_from(sd)
+            P = {n: self._pstack(theta, n) for n in self._att_keys(0)}
+            G = {n: self._pstack(g, n) for n in self._att_keys(0)}
+            S = lambda base: self._sstack(garena, base)
+            col = lambda v: v.unsqueeze(-1)                                           # [L, n] -> [L, n, 1]
+            outer = lambda a, b: a.unsqueeze(-1) * b.unsqueeze(-2)                     # batched torch.outer
+            wb = P["wb"][:, 0]
+            g_pt1 = S("pt1_w")[:, :, H:H + 32]                                         # d(W1p Wo)
+            G["W1p"] += g_pt1 @ P["Wo"].transpose(1, 2)
+            G["Wo"] += P["W1p"].transpose(1, 2) @ g_pt1
+            g_b = S("pt1_b")[:, 0]                                                     # d(b1 + W1p bo)
+            G["b1"] += g_b
+            G["W1p"] += outer(g_b, P["bo"])
+            G["bo"] += (P["W1p"].transpose(1, 2) @ col(g_b)).squeeze(-1)
+            g_v = S("pt2v")[:, 0]                                                      # d(W2^T wb)
+            G["W2"] += outer(wb, g_v)
+            G["wb"][:, 0] += (P["W2"] @ col(g_v)).squeeze(-1)
+            g_c = S("pt_c")[:, 0, 0]                                                   # d(wb . b2 + bb)
+            G["wb"][:, 0] += col(g_c) * P["b2"]
+            G["b2"] += col(g_c) * wb
+            G["bb"][:, 0] += g_c
+            g_vc = S("qk_w")[:, 3 * H + QKX:]                                          # d(ac1 Wkv_v)
+            G["ac1"] += g_vc @ P["Wkv"][:, 1::2, 1:].transpose(1, 2)
+            G["Wkv"][:, 1::2, 1:] += P["ac1"].transpose(1, 2) @ g_vc
+            g_vb = S("qk_b")[:, 0, 3 * H + QKX:]                                       # d(ac1 bkv_v)
+            G["ac1"] += outer(g_vb, P["bkv"][:, 1::2])
+            G["bkv"][:, 1::2] += (P["ac1"].transpose(1, 2) @ col(g_vb)).squeeze(-1)
+            g_u = S("ac_u")[:, 0]                                                      # d(ac1 v_r)
+            G["ac1"] += outer(g_u, P["Wkv"][:, 1::2, 0])
+            G["Wkv"][:, 1::2, 0] += (P["ac1"].transpose(1, 2) @ col(g_u)).squeeze(-1)
+            return g, {k_: g[o:o + n].view(shape) for k_, o, n, shape in self.layout}
         for l in range(self.L):
             k = self._att_keys(l)
             P = {n: sd[key].detach().to(self.device, torch.float32) for n, key in k.items()}

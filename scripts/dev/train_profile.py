@@ -30,6 +30,10 @@ def wrap(mod, name, tag=None):
 wrap(train, "_gpu_prev_coords"); wrap(train, "_gpu_edges"); wrap(train, "build_layout"); wrap(train, "pack_state_dict")
 wrap(train, "slot_tensors"); wrap(train, "internal_graph"); wrap(bw, "stack_forward_train_v1"); wrap(bw, "stack_backward_v1")
 wrap(train, "arena_grads_to_state_dict"); wrap(train, "_forward_half"); wrap(train, "_backward_half")
+wrap(weights.FastPackerV1, "pack", "packer.pack"); wrap(weights.FastPackerV1, "unpack", "packer.unpack")
+for _n in ("gcl_forward_train", "att_forward_train", "gcl_backward", "att_backward", "las_bwd", "pair_bias_gate_bwd", "pair_outer_bwd"):
+    if hasattr(bw, _n):
+        wrap(bw, _n)
 for _ in range(3):
     S["step"]()
 torch.cuda.synchronize()

@@ -154,6 +154,15 @@ def test_fast_packer_matches_the_generic_packer():
         assert set(g0) == set(g1) and flat.numel() == sum(v.numel() for v in g0.values())
         for k in g0:
             assert float((g0[k] - g1[k]).abs().max()) <= 2e-6 * float(g0[k].abs().max()) + 1e-7, k
+        # the packer rewrites ONE arena / parameter buffer in place: a second pack after an optimizer step sees the new weights
+        for v in sd.values():
+            v.mul_(0.5).add_(0.01)
+        a2 = fp.pack()
+        assert a2.data_ptr() == a1.data_ptr() and torch.equal(a2, pack_state_dict(sd, H, L, 0))
+        flat2, g2 = fp.unpack(ga)
+        g0b = arena_grads_to_state_dict(sd, ga, H, L, 0)
+        for k in g0b:
+            assert float((g0b[k] - g2[k]).abs().max()) <= 2e-6 * float(g0b[k].abs().max()) + 1e-7, k
 
 
 def test_layout_cache_and_moving_rows_count():
