@@ -173,12 +173,15 @@ def _forward_half(model, fa, prev_coords=None, edge_lists=None, state_dict=None,
     dev = fa["H"].device
     sd = state_dict if state_dict is not None else {k: v.detach() for k, v in model.state_dict().items()}
     X_prev = prev_coords(model, fa) if prev_coords is not None else _gpu_prev_coords(model, fa, n_iter, dropout)
-    ctx, inter = (edge_lists or _gpu_edges)(model, X_prev, fa)
-    lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
-    geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
+    # the weight arena of this step does not depend on the coordinates: packed and converted BEFORE the edge lists are read back, so
+    # that this host work (~1.3 ms) runs while the device is still busy with the earlier iterations (the edge lists have
+    # data-dependent sizes: building them is the step's one synchronisation)
     packer = _packer(model, sd, H, L, flavour, dev) if (USE_FAST_PACKER and (dev.type == "cuda" or flavour == 0)) else None
     arena = packer.pack() if packer is not None else pack_state_dict(sd, H, L, flavour, device=dev)
     weights = slot_tensors(arena, H, L, flavour)
+    lay = build_layout(fa["batch_id"], fa["segment_id"], fa["is_global"], fa["mask"], "cpu")
+    ctx, inter = (edge_lists or _gpu_edges)(model, X_prev, fa)
+    geo, edges, perm, moves = internal_graph(lay, ctx, inter, fa["compound_edge_index"], fa["LAS_edge_index"], dev)
     consts = dict(cmax=cfg["coord_clamp"], lcl=cfg["las_clamp"], las_step=cfg["las_step"], n_pairs=lay.P_total,
                   xl=fa["batched_complex_coord_LAS"].reshape(-1, 3)[perm].to(torch.float32).contiguous())
     if dropout is not None and dropout[0] > 0:
