@@ -85,7 +85,7 @@ def _drop(drop, X, layer, name, row0=0):
     return X if drop is None or drop.p <= 0 else drop.apply(X, layer, name, row0)
 
 
-def _gemm_call(A, W, bias, act, res, M, N, K, drop=None):
+def _gemm_call(A, W, bias, act, res, M, N, K, drop=None, A16=None):
     """C[M,N] = drop(act(A W^T + bias)) + res through fb_gemm in the current PRECISION; A [M,K], W [N,K] fp32 in, fp32 out.
     drop = (Drop, layer, site name, row0) or None: dropout in the epilogue, after the activation and before the residual."""
     g = _lib.GemmParams()
@@ -94,7 +94,8 @@ def _gemm_call(A, W, bias, act, res, M, N, K, drop=None):
         g.drop_p, g.drop_seed, g.drop_site, g.drop_row0, g.drop_colonly = d.p, d.seed, d.site(layer, name), int(row0), d.colonly
     bf16 = PRECISION == "bf16" and K % 8 == 0
     if bf16:
-        A = A.to(torch.bfloat16).contiguous()
+        # A16: the producer already wrote the bf16 twin of A (fused kernels of the training forward): no conversion pass
+        A = A16 if (A16 is not None and A16.dtype == torch.bfloat16 and A16.shape == A.shape) else A.to(torch.bfloat16).contiguous()
         W = bf16_twin(W)
     elif W.dtype != torch.float32:
         raise RuntimeError("fabind_b200.backward: bf16 weight operand outside PRECISION = 'bf16'")
@@ -548,14 +549,52 @@ def stack_backward_v1(weights, tape, top, geo, edges, consts, dH_out, dX_out, on
 # GPU parity: tests/test_gpu_train_forward.py; the orchestration is also validated on the CPU against the specification's forward
 # (tests/test_backward_orchestration.py).
 # ------------------------------------------------------------------------------------------------------------------------
-def linear(A, W, bias=None, act=ACT_NONE, res=None, drop=None):
-    """drop(act(A W^T + bias)) + res  (fp32, fb_gemm); drop = (Drop, layer, site name, row0) or None"""
+def linear(A, W, bias=None, act=ACT_NONE, res=None, drop=None, A16=None):
+    """drop(act(A W^T + bias)) + res  (fp32, fb_gemm); drop = (Drop, layer, site name, row0) or None; A16 = bf16 twin of A if its
+    producer wrote one"""
     _chk(A), _chk(W, W.dtype if W.dtype == torch.bfloat16 else torch.float32)
     if bias is not None:
         _chk(bias)
     if res is not None:
         _chk(res)
-    return _gemm_call(A, W, bias, act, res, A.shape[0], W.shape[0], A.shape[1], drop)
+    return _gemm_call(A, W, bias, act, res, A.shape[0], W.shape[0], A.shape[1], drop, A16)
+
+
+FUSED_FORWARD = True     # training forward: fused edge kernels (False / CPU stand-in tests: the composition of the primitive wrappers)
+
+
+def edge_pre_train(Pn, row, col, rn, w_rad, b1, act=ACT_SILU):
+    """Z1[e] = Pn[row[e], :H] + Pn[col[e], H:] + rn[e] w_rad + b1, A1 = act(Z1) -> (Z1, A1, bf16 twin of A1 or None)   (egnn.py:75-81)"""
+    E, H = row.numel(), Pn.shape[1] // 2
+    if not (FUSED_FORWARD and Pn.is_cuda and H % 4 == 0):
+        Z1 = gather_rows(Pn, row, 0, H)
+        gather_add_rows(Pn, col, Z1, col0=H)
+        rank1_add(Z1, rn, w_rad)
+        rank1_add(Z1, _ones(E, Pn.device), b1)
+        return Z1, act_fwd(Z1, act), None
+    _chk(Pn), _chk(rn), _chk(w_rad), _chk(b1), _chk(row, torch.int32), _chk(col, torch.int32)
+    Z1 = torch.empty(E, H, dtype=torch.float32, device=Pn.device)
+    A1 = torch.empty_like(Z1)
+    A16 = torch.empty(E, H, dtype=torch.bfloat16, device=Pn.device) if PRECISION == "bf16" else None
+    _lib.check(_lib.lib().fb_edge_pre_train(Pn.data_ptr(), row.data_ptr(), col.data_ptr(), E, H, rn.data_ptr(), w_rad.data_ptr(),
+                                            b1.data_ptr(), Z1.data_ptr(), A1.data_ptr(), A16.data_ptr() if A16 is not None else None,
+                                            act, _st(Pn)), "fb_edge_pre_train")
+    return Z1, A1, A16
+
+
+def act_drop(Z, act, drop, layer, name):
+    """drop(act(Z)) -> (fp32, bf16 twin or None): activation, the nn.Dropout behind it and the conversion for the next GEMM in one pass"""
+    if not (FUSED_FORWARD and Z.is_cuda and Z.shape[1] % 4 == 0):
+        return _drop(drop, act_fwd(Z, act), layer, name), None
+    _chk(Z)
+    M, N = Z.shape
+    Y = torch.empty_like(Z)
+    Y16 = torch.empty(M, N, dtype=torch.bfloat16, device=Z.device) if PRECISION == "bf16" else None
+    on = drop is not None and drop.p > 0
+    _lib.check(_lib.lib().fb_act_drop(Z.data_ptr(), M, N, act, drop.p if on else 0.0, drop.seed if on else 0, drop.site(layer, name) if on else 0,
+                                      0, drop.colonly if on else 0, Y.data_ptr(), Y16.data_ptr() if Y16 is not None else None, _st(Z)),
+               "fb_act_drop")
+    return Y, Y16
 
 
 def radial_fwd(x, row, col, node_cplx, B):
@@ -642,16 +681,12 @@ def gcl_forward_train(w, h, x, row, col, node_cplx, B, cmax, drop=None, layer=0)
     E, dev = row.numel(), h.device
     d, d2, rn, nrm = radial_fwd(x, row, col, node_cplx, B)
     Pn = linear(h, w["e1_rc"])
-    Z1 = gather_rows(Pn, row, 0, H)
-    gather_add_rows(Pn, col, Z1, col0=H)
-    rank1_add(Z1, rn, w["e1_rad"])
-    rank1_add(Z1, _ones(E, dev), w["e1_b"])
     # the activations the reverse pass multiplies with (A1, M, T3, t1) are kept next to their pre-activations: recomputing them cost four
     # passes over [E, H] per sub-layer (35 us each at B = 16)
-    A1 = act_fwd(Z1, ACT_SILU)
-    Z2 = linear(A1, w["e2_w"], w["e2_b"])
-    M = _drop(drop, act_fwd(Z2, ACT_SILU), layer, "edge2")            # egnn.py:82
-    Z3 = linear(M, w["c1_w"], w["c1_b"])
+    Z1, A1, A1h = edge_pre_train(Pn, row, col, rn, w["e1_rad"], w["e1_b"])
+    Z2 = linear(A1, w["e2_w"], w["e2_b"], A16=A1h)
+    M, Mh = act_drop(Z2, ACT_SILU, drop, layer, "edge2")              # egnn.py:82
+    Z3 = linear(M, w["c1_w"], w["c1_b"], A16=Mh)
     T3 = act_fwd(Z3, ACT_SILU)
     s = rowdot(T3, w["c2_w"])
     ssum = torch.zeros(N, 3, dtype=torch.float32, device=dev)

@@ -31,6 +31,53 @@ __global__ void act_fwd_kernel(const float* __restrict__ Z, float* __restrict__ 
     Y[i] = act_value(Z[i], kind);
 }
 
+// Training-mode twin of gcl_edge_pre (layers.cu): first edge-MLP Linear hoisted per node, pre-activation KEPT for the reverse pass.
+//   Z1[e, :] = Pn[row[e], 0:H] + Pn[col[e], H:2H] + rn[e] * w_rad + b1        A1 = act(Z1)  (fp32, and bf16 for the next GEMM)
+// One pass instead of a memset, two gather-adds, two rank-1 updates, the activation and the bf16 conversion (1.15 GB -> 0.23 GB of
+// traffic per sub-layer at B = 16).  One warp per edge, lane = 4 consecutive features.
+__global__ void __launch_bounds__(256) edge_pre_train_kernel(const float* __restrict__ Pn, const int* __restrict__ row,
+                                                             const int* __restrict__ col, int E, int H, const float* __restrict__ rn,
+                                                             const float* __restrict__ w_rad, const float* __restrict__ b1,
+                                                             float* __restrict__ Z1, float* __restrict__ A1, bf16* __restrict__ A16,
+                                                             int kind) {
+  pdl_entry();
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const float* pr = Pn + (size_t)row[e] * 2 * H;
+  const float* pc = Pn + (size_t)col[e] * 2 * H + H;
+  const float r = rn[e];
+  for (int f = lane * 4; f < H; f += 128) {
+    const float4 a = ld4(pr + f), b = ld4(pc + f), w = ld4(w_rad + f), bb = ld4(b1 + f);
+    float4 z;
+    z.x = fmaf(r, w.x, a.x + b.x) + bb.x; z.y = fmaf(r, w.y, a.y + b.y) + bb.y;
+    z.z = fmaf(r, w.z, a.z + b.z) + bb.z; z.w = fmaf(r, w.w, a.w + b.w) + bb.w;
+    const float4 y = make_float4(act_value(z.x, kind), act_value(z.y, kind), act_value(z.z, kind), act_value(z.w, kind));
+    st4(Z1 + (size_t)e * H + f, z);
+    st4(A1 + (size_t)e * H + f, y);
+    if (A16) st4(A16 + (size_t)e * H + f, y);
+  }
+}
+
+// Y = drop(act(Z)) in fp32 and, optionally, bf16 (the operand of the next GEMM): activation, the reference's nn.Dropout behind it
+// (egnn.py:82) and the conversion in one pass.  Row-major [M, N], N a multiple of 4.
+__global__ void __launch_bounds__(256) act_drop_kernel(const float* __restrict__ Z, int M, int N, int kind, DropCfg dc,
+                                                       float* __restrict__ Y, bf16* __restrict__ Y16) {
+  pdl_entry();
+  const long long total4 = (long long)M * N / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long o = i * 4;
+    const int m = (int)(o / N), n = (int)(o - (long long)m * N);
+    const float4 z = ld4(Z + o);
+    float4 y = make_float4(act_value(z.x, kind), act_value(z.y, kind), act_value(z.z, kind), act_value(z.w, kind));
+    if (dc.p > 0.f) {
+      y.x = drop_apply(y.x, dc, m, n); y.y = drop_apply(y.y, dc, m, n + 1);
+      y.z = drop_apply(y.z, dc, m, n + 2); y.w = drop_apply(y.w, dc, m, n + 3);
+    }
+    st4(Y + o, y);
+    if (Y16) st4(Y16 + o, y);
+  }
+}
+
 // dZ = dY * act'(Z)
 __global__ void act_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ dY, float* __restrict__ dZ, long long n,
                                int kind) {
@@ -717,6 +764,29 @@ extern "C" {
 int32_t fb_act_fwd(const float* Z, float* Y, int64_t n, int32_t act, void* stream) {
   if (n <= 0) return FB_OK;
   fb_launch(act_fwd_kernel, dim3(grid_1d(n, 256)), dim3(256), 0, (cudaStream_t)stream, Z, Y, (long long)n, (int)act);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_edge_pre_train(const float* Pn, const int32_t* row, const int32_t* col, int32_t E, int32_t H, const float* rn,
+                          const float* w_rad, const float* b1, float* Z1, float* A1, void* A16, int32_t act, void* stream) {
+  if (E <= 0) return FB_OK;
+  if (H <= 0 || (H & 3) || !Pn || !row || !col || !rn || !w_rad || !b1 || !Z1 || !A1) return FB_ERR_BAD_ARG;
+  fb_launch(edge_pre_train_kernel, dim3((int)(((long long)E * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, Pn, (const int*)row,
+            (const int*)col, (int)E, (int)H, rn, w_rad, b1, Z1, A1, (bf16*)A16, (int)act);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_act_drop(const float* Z, int32_t M, int32_t N, int32_t act, float p, uint32_t seed, uint32_t site, int32_t row0,
+                    int32_t colonly, float* Y, void* Y16, void* stream) {
+  if (M <= 0 || N <= 0) return FB_OK;
+  if ((N & 3) || !Z || !Y || !(p >= 0.f && p < 1.f)) return FB_ERR_BAD_ARG;
+  const DropCfg dc = p > 0.f ? make_drop(p, seed, site, row0, colonly) : DropCfg();
+  fb_launch(act_drop_kernel, dim3(grid_1d((long long)M * N / 4, 256)), dim3(256), 0, (cudaStream_t)stream, Z, (int)M, (int)N, (int)act, dc, Y,
+            (bf16*)Y16);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

@@ -322,6 +322,14 @@ int32_t fb_post_optimize(const float* ref_coords, const float* pred_coords, cons
  * 2 ReLU.  Scatter directions use fp32 atomics into caller-initialised buffers. ---- */
 /* Y = act(Z): re-materialise an activation from the saved pre-activation */
 int32_t fb_act_fwd(const float* Z, float* Y, int64_t n, int32_t act, void* stream);
+/* ABI 6: fused forms for the training-mode forward (same reference lines as fb_act_fwd / fb_gather_add_rows / fb_rows_update /
+ * fb_dropout_apply, models/egnn.py:75-82).  fb_edge_pre_train: Z1[e,:] = Pn[row[e], 0:H] + Pn[col[e], H:2H] + rn[e] w_rad + b1 (the first
+ * edge-MLP Linear hoisted per node, pre-activation kept for the reverse pass), A1 = act(Z1) in fp32 and optionally bf16 (A16 may be
+ * NULL).  fb_act_drop: Y = drop(act(Z)) in fp32 and optionally bf16, the library's counter-based mask (p = 0: no dropout). */
+int32_t fb_edge_pre_train(const float* Pn, const int32_t* row, const int32_t* col, int32_t E, int32_t H, const float* rn,
+                          const float* w_rad, const float* b1, float* Z1, float* A1, void* A16, int32_t act, void* stream);
+int32_t fb_act_drop(const float* Z, int32_t M, int32_t N, int32_t act, float p, uint32_t seed, uint32_t site, int32_t row0,
+                    int32_t colonly, float* Y, void* Y16, void* stream);
 /* dZ = dY * act'(Z)  (in place allowed: dZ == dY) */
 int32_t fb_act_bwd(const float* Z, const float* dY, float* dZ, int64_t n, int32_t act, void* stream);
 /* dZ[m,n] = u[m] v[n] act'(Z[m,n]): reverse of a Linear(H,1) head behind an activation (coord_mlp, egnn.py:54-60) */

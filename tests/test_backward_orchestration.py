@@ -337,7 +337,7 @@ def _install_forward_standins(monkeypatch, bw):
         return X * keep_mask(self.seed, self.site(layer, name), X.shape[0], X.shape[1], self.p, colonly=bool(self.colonly), row0=row0)
     monkeypatch.setattr(bw.Drop, "apply", drop_apply)
 
-    def linear(A, W, bias=None, act=0, res=None, drop=None):
+    def linear(A, W, bias=None, act=0, res=None, drop=None, A16=None):
         y = _actf(F.linear(A, W, bias), act)
         if drop is not None and drop[0] is not None and drop[0].p > 0:
             y = drop[0].apply(y, drop[1], drop[2], drop[3])
