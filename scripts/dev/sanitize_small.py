@@ -73,6 +73,33 @@ m = m.cuda().eval()
 for prec, att in (("bf16", "simt"), ("fp32", "simt"), ("fp32_tc", "simt"), ("bf16", "tcgen05")):
     m.precision, m.attention = prec, att
     m(**b.to("cuda").forward_args())
+# round 2 (late): dataloader-side layout -- a correct hint, then WRONG hints (too few / too many context edges: the device clamps its row
+# pointers into the claimed sizes and zero-fills the edge lists; flagged garbage, never an out-of-bounds access)
+from fabind_b200 import runtime
+from fabind_b200.dataloader import layout_hint, attach, prepare_batch
+m.precision, m.attention = "bf16", "simt"
+m(**prepare_batch(b.forward_args(), "cuda", m.layout_cutoff()))
+for de, dm in ((-41, 0), (+57, 0), (0, -7), (+9, +9)):
+    h = layout_hint(b.X, b.batch_id, b.segment_id, b.mask, b.is_global, b.compound_edge_index, m.layout_cutoff())
+    h.e_ctx += de; h.e_ctx_mv += dm
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in b.forward_args().items()}
+    attach(h, dev["batch_id"], dev["segment_id"], dev["is_global"], dev["mask"], "cuda")
+    m(**dev)
+    torch.cuda.synchronize()
+    runtime.layout_flag("cuda").zero_()
+# a batch at the benched per-complex sizes: head CTAs of gcl_node (global rows with 31 / 201 edges), four-query row attention
+b2 = make_batch(n_complexes=16, n_c=30, n_p=200, embed=128, seed=5)
+m(**b2.to("cuda").forward_args())
+# training step through the drop-in module (fused training-forward kernels, batched slot transposes, packer)
+from fabind_b200 import backward as bw
+mt = EfficientMCAttModel(published_args(), 128, 128, 1, n_layers=2, n_iter=2, **nc)
+randomize_coord_heads(mt)
+mt = mt.cuda().train(); mt.precision = "bf16"; mt.dropout_seed = 7
+bw.PRECISION = "bf16"
+for _ in range(2):
+    X, H = mt(**b.to("cuda").forward_args())
+    (X.sum() + H.sum()).backward()
+bw.PRECISION = "fp32"
 # post-optimisation
 ref = torch.randn(40, 3, device="cuda"); pred = ref + 0.3 * torch.randn(40, 3, device="cuda")
 batch = torch.cat([torch.zeros(15), torch.ones(25)]).long().cuda()
