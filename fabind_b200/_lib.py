@@ -137,6 +137,9 @@ EXPORTS = {
                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "fb_act_drop": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
+    "fb_act_bwd_drop": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fb_outer_act_bwd2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "fb_act_bwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "fb_outer_act_bwd": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "fb_colsum": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

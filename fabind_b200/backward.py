@@ -145,6 +145,34 @@ def outer_act_bwd(Z, u, v, act):
     return dZ
 
 
+def act_bwd_drop(Z, dY, act, drop, layer, name):
+    """dZ = drop(dY) * act'(Z) -> (fp32, bf16 twin or None): the gradient of a dropped activation in one pass"""
+    if not (FUSED_FORWARD and Z.is_cuda and Z.shape[1] % 4 == 0):
+        return act_bwd(Z, _drop(drop, dY, layer, name), act), None
+    _chk(Z), _chk(dY)
+    M, N = Z.shape
+    dZ = torch.empty_like(Z)
+    d16 = torch.empty(M, N, dtype=torch.bfloat16, device=Z.device) if PRECISION == "bf16" else None
+    on = drop is not None and drop.p > 0
+    _lib.check(_lib.lib().fb_act_bwd_drop(Z.data_ptr(), dY.data_ptr(), M, N, act, drop.p if on else 0.0, drop.seed if on else 0,
+                                          drop.site(layer, name) if on else 0, 0, drop.colonly if on else 0, dZ.data_ptr(),
+                                          d16.data_ptr() if d16 is not None else None, _st(Z)), "fb_act_bwd_drop")
+    return dZ, d16
+
+
+def outer_act_bwd16(Z, u, v, act):
+    """outer_act_bwd with the bf16 twin of the result -> (dZ, bf16 twin or None)"""
+    if not (FUSED_FORWARD and Z.is_cuda and Z.shape[1] % 4 == 0 and PRECISION == "bf16"):
+        return outer_act_bwd(Z, u, v, act), None
+    _chk(Z), _chk(u), _chk(v)
+    M, N = Z.shape
+    dZ = torch.empty_like(Z)
+    d16 = torch.empty(M, N, dtype=torch.bfloat16, device=Z.device)
+    _lib.check(_lib.lib().fb_outer_act_bwd2(Z.data_ptr(), u.data_ptr(), v.data_ptr(), dZ.data_ptr(), d16.data_ptr(), M, N, act, _st(Z)),
+               "fb_outer_act_bwd2")
+    return dZ, d16
+
+
 def colsum(A, w=None, out=None):
     """out[n] += sum_m w[m] A[m,n]"""
     _chk(A)
@@ -205,11 +233,12 @@ def gemm_wgrad(dY, X, out=None):
     return out
 
 
-def gemm_dgrad(dY, Wt):
-    """dX = dY W, with Wt = W^T stored [K_in, N_out] contiguous (the 'weight' of the data-gradient GEMM; bf16 under PRECISION = 'bf16')"""
+def gemm_dgrad(dY, Wt, dY16=None):
+    """dX = dY W, with Wt = W^T stored [K_in, N_out] contiguous (the 'weight' of the data-gradient GEMM; bf16 under PRECISION = 'bf16');
+    dY16 = bf16 twin of dY if its producer wrote one"""
     _chk(dY)
     M, N = dY.shape
-    return _gemm_call(dY, Wt, None, ACT_NONE, None, M, Wt.shape[0], N)
+    return _gemm_call(dY, Wt, None, ACT_NONE, None, M, Wt.shape[0], N, None, dY16)
 
 
 def coord_step_bwd(x, row, col, s, step, cnt, cmax, dx_new):
@@ -239,12 +268,14 @@ def las_bwd(x, xref, a_idx, b_idx, acc, step_size, lcl, dx_new):
     return dx
 
 
-def _linear_bwd(grads, wname, bname, Wt, X, dY, need_dx=True):
+def _linear_bwd(grads, wname, bname, Wt, X, dY, need_dx=True, dY16=None):
     """y = x W^T + b: accumulates dW, db into `grads`, returns dX = dY W"""
     grads[wname] = gemm_wgrad(dY, X, grads.get(wname))
     if bname is not None:
         grads[bname] = colsum(dY, None, grads.get(bname))
-    return gemm_dgrad(dY, Wt) if need_dx else None
+    if not need_dx:
+        return None
+    return gemm_dgrad(dY, Wt, dY16) if dY16 is not None else gemm_dgrad(dY, Wt)
 
 
 def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new, drop=None, layer=0):
@@ -262,10 +293,10 @@ def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new, drop=None,
     dx, ds = coord_step_bwd(x, row, col, saved["s"], saved["step"], saved["deg"], cmax, dx_new)
     T3 = saved["T3"] if "T3" in saved else act_fwd(saved["Z3"], ACT_SILU)
     grads["c2_w"] = colsum(T3, ds)
-    dZ3 = outer_act_bwd(saved["Z3"], ds, w["c2_w"], ACT_SILU)        # dZ3[e,f] = ds[e] c2[f] silu'(Z3[e,f])
+    dZ3, dZ3h = outer_act_bwd16(saved["Z3"], ds, w["c2_w"], ACT_SILU)        # dZ3[e,f] = ds[e] c2[f] silu'(Z3[e,f])
     # the edge message as the forward used it (egnn.py:82)
     M = saved["M"] if "M" in saved else _drop(drop, act_fwd(saved["Z2"], ACT_SILU), layer, "edge2")
-    dM = _linear_bwd(grads, "c1_w", "c1_b", w["c1_w_t"], M, dZ3)
+    dM = _linear_bwd(grads, "c1_w", "c1_b", w["c1_w_t"], M, dZ3, dY16=dZ3h)
     # node branch: h_new = h + drop(n2(silu(n1([h | agg]))))
     t1 = saved["t1"] if "t1" in saved else act_fwd(saved["Z4"], ACT_SILU)
     dt1 = _linear_bwd(grads, "n2_w", "n2_b", w["n2_w_t"], t1, _drop(drop, dh_new, layer, "node2"))
@@ -276,9 +307,9 @@ def gcl_backward(w, saved, row, col, node_cplx, cmax, dh_new, dx_new, drop=None,
     dcat = _linear_bwd(grads, "n1_w", "n1_b", w["n1_w_t"], cat, dZ4)
     gather_add_rows(dcat, row, dM, col0=H)                    # dM[e] += dagg[row[e]]
     # edge MLP (dM is the gradient of the DROPPED message)
-    dZ2 = act_bwd(saved["Z2"], _drop(drop, dM, layer, "edge2"), ACT_SILU)
+    dZ2, dZ2h = act_bwd_drop(saved["Z2"], dM, ACT_SILU, drop, layer, "edge2")
     A1 = saved["A1"] if "A1" in saved else act_fwd(saved["Z1"], ACT_SILU)
-    dA1 = _linear_bwd(grads, "e2_w", "e2_b", w["e2_w_t"], A1, dZ2)
+    dA1 = _linear_bwd(grads, "e2_w", "e2_b", w["e2_w_t"], A1, dZ2, dY16=dZ2h)
     dZ1 = act_bwd(saved["Z1"], dA1, ACT_SILU)
     grads["e1_b"] = colsum(dZ1)
     grads["e1_rad"] = colsum(dZ1, saved["rn"])

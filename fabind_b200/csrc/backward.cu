@@ -98,6 +98,45 @@ __global__ void outer_act_bwd_kernel(const float* __restrict__ Z, const float* _
   for (int f = lane; f < N; f += 32) d[f] = um * v[f] * act_grad(z[f], kind);
 }
 
+// Reverse-pass twins of the fused forward kernels: the gradient tensor goes out in fp32 AND bf16 (the operand of the data-gradient
+// GEMM), and the nn.Dropout in front of the activation's output is applied to the incoming gradient in the same pass.
+//   act_bwd_drop:    dZ = drop(dY) * act'(Z)                          (dY: gradient of the DROPPED activation, egnn.py:82)
+//   outer_act_bwd2:  dZ[m, n] = u[m] v[n] act'(Z[m, n])               (same as outer_act_bwd_kernel)
+__global__ void __launch_bounds__(256) act_bwd_drop_kernel(const float* __restrict__ Z, const float* __restrict__ dY, int M, int N, int kind,
+                                                           DropCfg dc, float* __restrict__ dZ, bf16* __restrict__ dZ16) {
+  pdl_entry();
+  const long long total4 = (long long)M * N / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long o = i * 4;
+    const int m = (int)(o / N), n = (int)(o - (long long)m * N);
+    const float4 z = ld4(Z + o);
+    float4 g = ld4(dY + o);
+    if (dc.p > 0.f) {
+      g.x = drop_apply(g.x, dc, m, n); g.y = drop_apply(g.y, dc, m, n + 1);
+      g.z = drop_apply(g.z, dc, m, n + 2); g.w = drop_apply(g.w, dc, m, n + 3);
+    }
+    const float4 d = make_float4(g.x * act_grad(z.x, kind), g.y * act_grad(z.y, kind), g.z * act_grad(z.z, kind), g.w * act_grad(z.w, kind));
+    st4(dZ + o, d);
+    if (dZ16) st4(dZ16 + o, d);
+  }
+}
+
+__global__ void __launch_bounds__(256) outer_act_bwd2_kernel(const float* __restrict__ Z, const float* __restrict__ u, const float* __restrict__ v,
+                                                             float* __restrict__ dZ, bf16* __restrict__ dZ16, int M, int N, int kind) {
+  pdl_entry();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const float um = u[warp];
+  const size_t base = (size_t)warp * N;
+  for (int f = lane * 4; f < N; f += 128) {
+    const float4 z = ld4(Z + base + f), vv = ld4(v + f);
+    const float4 d = make_float4(um * vv.x * act_grad(z.x, kind), um * vv.y * act_grad(z.y, kind), um * vv.z * act_grad(z.z, kind),
+                                 um * vv.w * act_grad(z.w, kind));
+    st4(dZ + base + f, d);
+    if (dZ16) st4(dZ16 + base + f, d);
+  }
+}
+
 // out[n] (+)= sum_m w[m] * A[m, n]   (bias gradients; w == null: plain column sums; w = radial: rank-1 column gradients)
 // grid.x tiles the columns (32 per CTA), grid.y splits the rows; partial sums are combined with atomics into a zeroed or
 // caller-accumulated buffer.
@@ -804,6 +843,29 @@ int32_t fb_outer_act_bwd(const float* Z, const float* u, const float* v, float* 
   if (M <= 0 || N <= 0) return FB_OK;
   fb_launch(outer_act_bwd_kernel, dim3((int)(((long long)M * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, Z, u, v, dZ, (int)M,
             (int)N, (int)act);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_act_bwd_drop(const float* Z, const float* dY, int32_t M, int32_t N, int32_t act, float p, uint32_t seed, uint32_t site,
+                        int32_t row0, int32_t colonly, float* dZ, void* dZ16, void* stream) {
+  if (M <= 0 || N <= 0) return FB_OK;
+  if ((N & 3) || !Z || !dY || !dZ || !(p >= 0.f && p < 1.f)) return FB_ERR_BAD_ARG;
+  const DropCfg dc = p > 0.f ? make_drop(p, seed, site, row0, colonly) : DropCfg();
+  fb_launch(act_bwd_drop_kernel, dim3(grid_1d((long long)M * N / 4, 256)), dim3(256), 0, (cudaStream_t)stream, Z, dY, (int)M, (int)N, (int)act,
+            dc, dZ, (bf16*)dZ16);
+  count_launch(1);
+  FB_CHECK_LAUNCH();
+  return FB_OK;
+}
+
+int32_t fb_outer_act_bwd2(const float* Z, const float* u, const float* v, float* dZ, void* dZ16, int32_t M, int32_t N, int32_t act,
+                          void* stream) {
+  if (M <= 0 || N <= 0) return FB_OK;
+  if ((N & 3) || !Z || !u || !v || !dZ) return FB_ERR_BAD_ARG;
+  fb_launch(outer_act_bwd2_kernel, dim3((int)(((long long)M * 32 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, Z, u, v, dZ, (bf16*)dZ16,
+            (int)M, (int)N, (int)act);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

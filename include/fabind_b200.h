@@ -330,6 +330,12 @@ int32_t fb_edge_pre_train(const float* Pn, const int32_t* row, const int32_t* co
                           const float* w_rad, const float* b1, float* Z1, float* A1, void* A16, int32_t act, void* stream);
 int32_t fb_act_drop(const float* Z, int32_t M, int32_t N, int32_t act, float p, uint32_t seed, uint32_t site, int32_t row0,
                     int32_t colonly, float* Y, void* Y16, void* stream);
+/* ABI 6: their reverse-pass twins (autograd's backward of the same reference lines): dZ = drop(dY) * act'(Z) and dZ[m,n] = u[m] v[n]
+ * act'(Z[m,n]), each also written as bf16 (dZ16 may be NULL) -- the operand of the data-gradient GEMM that follows. */
+int32_t fb_act_bwd_drop(const float* Z, const float* dY, int32_t M, int32_t N, int32_t act, float p, uint32_t seed, uint32_t site,
+                        int32_t row0, int32_t colonly, float* dZ, void* dZ16, void* stream);
+int32_t fb_outer_act_bwd2(const float* Z, const float* u, const float* v, float* dZ, void* dZ16, int32_t M, int32_t N, int32_t act,
+                          void* stream);
 /* dZ = dY * act'(Z)  (in place allowed: dZ == dY) */
 int32_t fb_act_bwd(const float* Z, const float* dY, float* dZ, int64_t n, int32_t act, void* stream);
 /* dZ[m,n] = u[m] v[n] act'(Z[m,n]): reverse of a Linear(H,1) head behind an activation (coord_mlp, egnn.py:54-60) */
