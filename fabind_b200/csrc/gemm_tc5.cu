@@ -25,8 +25,21 @@ namespace fb {
 bool tc_make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 bool tc_make_map_out(CUtensorMap* m, const void* ptr, bool is_f32, uint64_t rows, uint64_t cols, uint64_t ld);
 
+extern long long* g_tc_dbg;
+
 namespace tc5 {
 using namespace tc;
+
+// per-role wait accounting (diagnostic builds; scripts/dev/tc5_stalls.py): g_tc_dbg[cta * 8 + k], k = 0 MMA warp waits for operands
+// (full), 1 MMA warp waits for a drained accumulator stage (tempty), 2 producer 0 waits for a free ring slot (empty), 3 epilogue warp 0
+// waits for an accumulator (tfull), 4 epilogue warp 0 busy, 5 kernel total, 6 clocks spent in griddepcontrol.wait, 7 tiles of the CTA
+#ifdef FB_DIAG
+#define FB5_T0() const long long t0__ = clock64()
+#define FB5_ACC(var) var += clock64() - t0__
+#else
+#define FB5_T0() do { } while (0)
+#define FB5_ACC(var) do { } while (0)
+#endif
 
 constexpr int NPMAX = 4;
 constexpr int BN = 128;
@@ -51,6 +64,7 @@ struct Params {
   CUtensorMap a[NPMAX], a2[NPMAX], w[NPMAX], c[NPMAX], cb[NPMAX], res[NPMAX];
   Prob q[NPMAX];
   int np, n_tiles, prefetch_w;
+  long long* dbg;
 };
 
 struct Smem {
@@ -74,6 +88,11 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap* m) { asm volatil
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_constant__ Params p) {
   using S = Smem;
   pdl_trigger();
+#ifdef FB_DIAG
+  const long long t_start = clock64();
+  long long w_full = 0, w_tempty = 0, w_empty = 0, w_tfull = 0, e_busy = 0, w_pdl = 0;
+  int n_my = 0;
+#endif
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::BAR_OFF);
@@ -156,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
     }
   }
   // everything above touched only on-chip state and the weights; activations are produced by the previous kernel in the stream
-  pdl_wait();
+  { FB5_T0(); pdl_wait(); FB5_ACC(w_pdl); }
 
   if (warp < PRODUCERS) {
     // ===== TMA producers: producer `warp` issues the k-slabs it with it % PRODUCERS == warp of the CTA's tile sequence =====
@@ -175,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
           uint8_t* a_dst = smem + s * S::STAGE_BYTES;
           const bool armed = it == pre_it;          // barrier armed and W slab already in flight
           if (!armed) {
-            mbar_wait(&empty[s], ph ^ 1);
+            { FB5_T0(); mbar_wait(&empty[s], ph ^ 1); FB5_ACC(w_empty); }
             mbar_expect_tx(&full[s], S::STAGE_BYTES);
           }
           if (kb < KB1) tma_load_2d(&p.a[pi], &full[s], a_dst, kb * BK, m0);
@@ -196,13 +215,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
         const int pi = decode(tile, m0, n0);
         const int KB = p.q[pi].KB1 + p.q[pi].KB2;
         const int a = lt & 1;
-        mbar_wait(&tempty[a], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator stage
+        { FB5_T0(); mbar_wait(&tempty[a], ((lt >> 1) & 1) ^ 1); FB5_ACC(w_tempty); }   // epilogue has drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
+          { FB5_T0(); mbar_wait(&full[s], ph); FB5_ACC(w_full); }
           tcgen05_fence_after();
           const uint8_t* a_src = smem + s * S::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(a_src), bdesc = make_smem_desc(a_src + S::A_BYTES);
@@ -251,7 +270,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) tma_load_2d(mres, rbar, slots + ch * SLOT, colbase + ch * 32, lrow0);
       }
-      mbar_wait(&tfull[a], (lt >> 1) & 1);
+      { FB5_T0(); mbar_wait(&tfull[a], (lt >> 1) & 1); FB5_ACC(w_tfull); }
+#ifdef FB_DIAG
+      const long long t_busy0 = clock64();
+      ++n_my;
+#endif
       tcgen05_fence_after();
       if (has_res && rows_live) { mbar_wait(rbar, rphase); rphase ^= 1; }
 #pragma unroll
@@ -311,16 +334,30 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc5_kernel(const __grid_const
           }
         }
       }
+#ifdef FB_DIAG
+      e_busy += clock64() - t_busy0;
+#endif
     }
     // shared memory must stay valid until the last bulk stores have read it
     if (lane == 0) bulk_wait_read0();
   }
+#ifdef FB_DIAG
+  if (p.dbg && lane == 0) {
+    long long* d = p.dbg + (size_t)blockIdx.x * 8;
+    if (warp == MMA_WARP) { d[0] = w_full; d[1] = w_tempty; }
+    if (warp == 0) { d[2] = w_empty; d[6] = w_pdl; }
+    if (warp == EPI_WARP0) { d[3] = w_tfull; d[4] = e_busy; d[7] = n_my; }
+  }
+#endif
   tcgen05_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
+#ifdef FB_DIAG
+  if (p.dbg && threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 8 + 5] = clock64() - t_start;
+#endif
 }
 
 }  // namespace tc5
@@ -375,6 +412,7 @@ int gemm_tc5_launch(const GemmArgs* g, int np, bool prefetch_w, cudaStream_t st)
     tiles += ((a.M + BM - 1) / BM) * q.ntn;
   }
   p.np = np; p.n_tiles = tiles; p.prefetch_w = prefetch_w ? 1 : 0;
+  p.dbg = g_tc_dbg;
   const int grid = tiles < num_sms ? tiles : num_sms;
   fb_launch(gemm_tc5_kernel, dim3(grid), dim3(THREADS), Smem::TOTAL, st, p);
   count_launch(1);
