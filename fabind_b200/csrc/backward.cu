@@ -411,9 +411,10 @@ __global__ void pair_outer_bwd_kernel(const float* __restrict__ dO, const float*
 
 // RowAttentionBlock core reverse (forward: layers.cu::row_attention_kernel; cross_att.py:118-134, model_utils.py:21-38):
 //   O[q, h*32+d] = sigmoid(G) * sum_j a_j v_j[d],  a = softmax_j(q.k_j / sqrt(32) + bias_j)
-// One CTA per (complex, head): the keys / values of the head and their gradient accumulators live in shared memory
-// (n_k <= RB_MAXK), every warp walks queries, probabilities are recomputed.  Writes dQ, dG, dPB (one owner each) and, once per
-// CTA, dK and dV.
+// One CTA per (complex, head, tile of q_tile queries): the keys / values of the head and their gradient accumulators live in shared
+// memory (n_k <= KC <= RB_MAXK, sized to the launch), every warp walks queries of the tile, probabilities are recomputed.  Writes dQ, dG,
+// dPB (one owner each) and, once per CTA, ADDS its dK / dV to global memory (the caller zeroes them) -- with one CTA per (complex, head)
+// and 140 KB of shared memory the launch was 64 CTAs at one per SM (156 us at B = 16).
 constexpr int RB_MAXK = 256;
 constexpr int RB_WARPS = 8;
 constexpr int RB_SMEM_FLOATS = 4 * RB_MAXK * 33 + RB_WARPS * (2 * RB_MAXK + 64);
@@ -422,21 +423,23 @@ __global__ void __launch_bounds__(RB_WARPS * 32) row_attention_bwd_kernel(
     const float* __restrict__ Q, int ldq, const float* __restrict__ G, int ldg, const float* __restrict__ Kb, int ldk,
     const float* __restrict__ Vb, int ldv, const float* __restrict__ PB, const float* __restrict__ dO, int ldo,
     float* __restrict__ dQ, int lddq, float* __restrict__ dG, int lddg, float* __restrict__ dK, int lddk,
-    float* __restrict__ dV, int lddv, float* __restrict__ dPB) {
+    float* __restrict__ dV, int lddv, float* __restrict__ dPB, int KC, int q_tile) {
   pdl_entry();
   extern __shared__ float rb_smem[];
   const int b = blockIdx.x, head = blockIdx.y;
   const int c_lo = c_off[b], nc1 = c_off[b + 1] - c_lo, p_lo = p_off[b], np1 = p_off[b + 1] - p_lo;
   const int n_q = q_is_prot ? np1 : nc1, n_k = q_is_prot ? nc1 : np1;
   const int q_lo = q_is_prot ? p_lo : c_lo, k_lo = q_is_prot ? c_lo : p_lo;
+  const int q_begin = blockIdx.z * q_tile, q_end = min(n_q, q_begin + q_tile);
+  if (q_begin >= n_q) return;            // block-uniform
   float* sK = rb_smem;                   // [n_k][33]
-  float* sV = sK + RB_MAXK * 33;
-  float* sdK = sV + RB_MAXK * 33;
-  float* sdV = sdK + RB_MAXK * 33;
+  float* sV = sK + KC * 33;
+  float* sdK = sV + KC * 33;
+  float* sdV = sdK + KC * 33;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* pa = sdV + RB_MAXK * 33 + warp * (2 * RB_MAXK + 64);   // probabilities of the warp's current query
-  float* pd = pa + RB_MAXK;                                      // da, then dlogit
-  float* wq = pd + RB_MAXK;                                      // scaled query, 32 channels
+  float* pa = sdV + KC * 33 + warp * (2 * KC + 64);              // probabilities of the warp's current query
+  float* pd = pa + KC;                                           // da, then dlogit
+  float* wq = pd + KC;                                           // scaled query, 32 channels
   float* wdo = wq + 32;                                          // gradient w.r.t. the un-gated output, 32 channels
   const float scale = 0.17677669529663687f;                      // 1/sqrt(32)
   for (int i = threadIdx.x; i < n_k * 32; i += blockDim.x) {
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(RB_WARPS * 32) row_attention_bwd_kernel(
     sdV[j * 33 + d] = 0.f;
   }
   __syncthreads();
-  for (int ql = warp; ql < n_q; ql += RB_WARPS) {
+  for (int ql = q_begin + warp; ql < q_end; ql += RB_WARPS) {
     const int qn = q_lo + ql;
     const float qd = Q[(size_t)qn * ldq + head * 32 + lane] * scale;      // lane = channel
     const float gd = G[(size_t)qn * ldg + head * 32 + lane];
@@ -509,8 +512,8 @@ __global__ void __launch_bounds__(RB_WARPS * 32) row_attention_bwd_kernel(
   __syncthreads();
   for (int i = threadIdx.x; i < n_k * 32; i += blockDim.x) {
     const int j = i >> 5, d = i & 31;
-    dK[(size_t)(k_lo + j) * lddk + head * 32 + d] = sdK[j * 33 + d];
-    dV[(size_t)(k_lo + j) * lddv + head * 32 + d] = sdV[j * 33 + d];
+    atomicAdd(&dK[(size_t)(k_lo + j) * lddk + head * 32 + d], sdK[j * 33 + d]);
+    atomicAdd(&dV[(size_t)(k_lo + j) * lddv + head * 32 + d], sdV[j * 33 + d]);
   }
 }
 
@@ -1142,9 +1145,15 @@ int32_t fb_row_attention_bwd(const int32_t* c_off, const int32_t* p_off, const i
   }
   static unsigned long long done = 0;
   if (!ensure_smem_optin(row_attention_bwd_kernel, RB_SMEM_FLOATS * 4, done)) return FB_ERR_CUDA;
-  fb_launch(row_attention_bwd_kernel, dim3(B, 4), dim3(RB_WARPS * 32), RB_SMEM_FLOATS * 4, (cudaStream_t)stream, c_off, p_off, pair_base,
-            (int)q_is_prot, Q, (int)ldq, G, (int)ldg, K, (int)ldk, V, (int)ldv, PB, dO, (int)ldo, dQ, (int)lddq, dG, (int)lddg, dK,
-            (int)lddk, dV, (int)lddv, dPB);
+  if (max_q <= 0) return FB_OK;
+  // shared memory sized to the keys that exist; queries split over grid.z: two per warp (16 per CTA) for long query lists, one per
+  // warp for short ones.  dK / dV are ACCUMULATED (atomics): the caller zeroes them, as for the long-key variant above.
+  const int KC = (max_k + 31) & ~31;
+  const int q_tile = max_q > 64 ? 2 * RB_WARPS : RB_WARPS;
+  const int smem = (4 * KC * 33 + RB_WARPS * (2 * KC + 64)) * 4;
+  fb_launch(row_attention_bwd_kernel, dim3(B, 4, (max_q + q_tile - 1) / q_tile), dim3(RB_WARPS * 32), smem, (cudaStream_t)stream, c_off, p_off,
+            pair_base, (int)q_is_prot, Q, (int)ldq, G, (int)ldg, K, (int)ldk, V, (int)ldv, PB, dO, (int)ldo, dQ, (int)lddq, dG, (int)lddg, dK,
+            (int)lddk, dV, (int)lddv, dPB, KC, q_tile);
   count_launch(1);
   FB_CHECK_LAUNCH();
   return FB_OK;

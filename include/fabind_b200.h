@@ -396,7 +396,8 @@ int32_t fb_pair_outer_bwd(const float* dO, const float* pc, int32_t H, const int
                           const int32_t* pair_base, const int32_t* node_cplx, int32_t p_begin, int32_t n_p_rows, float* dpc,
                           void* stream);
 /* reverse of the RowAttentionBlock core (cross_att.py:118-134, model_utils.py:21-38), probabilities recomputed; PB / dPB = [P,4];
- * dK / dV zeroed by the caller (key lists longer than 256 are accumulated with atomics; up to 2048 keys) */
+ * dK / dV zeroed by the caller (they are accumulated with atomics: query tiles of one complex and head run in different CTAs; up to
+ * 2048 keys) */
 int32_t fb_row_attention_bwd(const int32_t* c_off, const int32_t* p_off, const int32_t* pair_base, int32_t B, int32_t q_is_prot,
                              int32_t max_q, int32_t max_k, const float* Q, int32_t ldq, const float* G, int32_t ldg, const float* K, int32_t ldk,
                              const float* V, int32_t ldv, const float* PB, const float* dO, int32_t ldo, float* dQ, int32_t lddq,
