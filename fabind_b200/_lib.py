@@ -61,7 +61,7 @@ class GemmParams(C.Structure):
         ("bf16_mode", C.c_int32), ("force_simt", C.c_int32),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_site", C.c_uint32), ("drop_row0", C.c_int32),
         ("drop_colonly", C.c_int32),
-        ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_size_t), ("W_f32", C.c_void_p), ("n_split", C.c_int32),
+        ("split_ws", C.c_void_p), ("split_ws_bytes", C.c_size_t), ("W_f32", C.c_void_p), ("n_split", C.c_int32), ("ldw", C.c_int32),
     ]
 
 

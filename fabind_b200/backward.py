@@ -27,6 +27,7 @@ ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 # transposed copies are torch copies (no arithmetic).  Not validated on a GPU yet: default "fp32".
 PRECISION = "fp32"
 WGRAD_TC_MIN_ROWS = 2048
+WGRAD_SPLIT = 4            # row splits of a tensor-core weight gradient = problems of one multi-problem launch (gemm_tc5.cu: up to 4)
 
 
 # bf16 twins of the weight operands (PRECISION = "bf16"): train.slot_tensors converts the whole arena ONCE per step and registers,
@@ -217,15 +218,28 @@ def gemm_wgrad(dY, X, out=None):
     M, N = dY.shape
     K = X.shape[1]
     if PRECISION == "bf16" and M >= WGRAD_TC_MIN_ROWS:
-        Mp = (M + 63) // 64 * 64
+        # dW = dY^T X as a GEMM over transposed bf16 operands: [N, K] output tiles (16 for a 512 x 512 weight) with the REDUCTION over
+        # the M rows.  As one problem it ran on 16 of 148 SMs for 220 us per edge-level weight (44.9k rows, 702 k-slabs per tile) and
+        # 480 us for the pair rows; split over the rows into WGRAD_SPLIT independent problems of ONE multi-problem launch
+        # (fb_gemm_multi, gemm_tc5.cu) with a partial output each, summed afterwards.
+        S = WGRAD_SPLIT if (K % 128 == 0 and M >= 2 * WGRAD_TC_MIN_ROWS) else 1
+        Mp = (M + 64 * S - 1) // (64 * S) * (64 * S)
         At, Wt = transpose_bf16(dY, Mp), transpose_bf16(X, Mp)
-        g = _lib.GemmParams()
-        g.A, g.lda, g.K1 = At.data_ptr(), Mp, Mp
-        g.W, g.bias, g.act = Wt.data_ptr(), None, ACT_NONE
-        g.M, g.N, g.bf16_mode, g.force_simt = N, K, 1, 0
-        r = torch.empty(N, K, dtype=torch.float32, device=dY.device)
-        g.C, g.ldc = r.data_ptr(), K
-        _lib.check(_lib.lib().fb_gemm(C.byref(g), _st(dY)), "fb_gemm")
+        chunk = Mp // S
+        r = torch.empty(S, N, K, dtype=torch.float32, device=dY.device)
+        arr = (_lib.GemmParams * S)()
+        for i in range(S):
+            g = arr[i]
+            g.A, g.lda, g.K1 = At.data_ptr() + 2 * i * chunk, Mp, chunk
+            g.W, g.bias, g.act, g.ldw = Wt.data_ptr() + 2 * i * chunk, None, ACT_NONE, (Mp if S > 1 else 0)
+            g.M, g.N, g.bf16_mode, g.force_simt = N, K, 1, 0
+            g.C, g.ldc = r.data_ptr() + 4 * i * N * K, K
+        if S == 1:
+            _lib.check(_lib.lib().fb_gemm(C.byref(arr[0]), _st(dY)), "fb_gemm")
+        else:
+            # prefetch_w = 0: the "weights" of these problems (X^T) were written by the transpose just before
+            _lib.check(_lib.lib().fb_gemm_multi(arr, S, 0, _st(dY)), "fb_gemm_multi")
+        r = r[0] if S == 1 else r.sum(0)
         return r if out is None else vec_add_(out, r)
     if out is None:
         out = torch.zeros(N, K, dtype=torch.float32, device=dY.device)

@@ -1188,7 +1188,7 @@ static GemmArgs gemm_args_from(const fb_gemm_params* q) {
   a.A = q->A; a.lda = q->lda; a.K1 = q->K1; a.A2 = q->A2; a.lda2 = q->lda2; a.K2 = q->K2; a.W = q->W;
   a.bias = q->bias; a.act = q->act; a.res = q->res; a.ldres = q->ldres; a.C = q->C; a.ldc = q->ldc;
   a.Cb = q->Cb; a.ldcb = q->ldcb; a.dotv = q->dotv; a.dot_out = q->dot_out; a.dot_stride = q->dot_stride;
-  a.M = q->M; a.N = q->N; a.m_dev = q->m_dev; a.n_split = q->n_split;
+  a.M = q->M; a.N = q->N; a.m_dev = q->m_dev; a.n_split = q->n_split; a.ldw = q->ldw;
   a.drop = make_drop(q->drop_p, q->drop_seed, q->drop_site, q->drop_row0, q->drop_colonly);
   a.split_ws = q->split_ws; a.split_ws_bytes = q->split_ws_bytes; a.W_f32 = q->W_f32;
   return a;

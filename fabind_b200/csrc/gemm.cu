@@ -107,6 +107,7 @@ static int gemm_split_launch(const GemmArgs& g, int mode, cudaStream_t st) {
 }
 
 int gemm_launch(const GemmArgs& g, int mode, cudaStream_t st) {
+  if (g.ldw != 0 && g.ldw != g.K1 + g.K2) return FB_ERR_UNSUPPORTED;   // a strided W is served by the multi-problem kernel only
   if (mode >= GEMM_SPLIT3) {
     // shapes the tcgen05 kernels cannot take (narrow N, K not a multiple of 64, device-side row counts with stored outputs) stay on
     // the FFMA kernel: same fp32 operands, W read from the fp32 arena by the caller's choice of pointer (see Run::mk)
@@ -147,7 +148,8 @@ int gemm_launch_pair(const GemmArgs& g0, const GemmArgs& g1, int mode, cudaStrea
 #else
   const bool group = true;
 #endif
-  if (group && mode == GEMM_BF16 && tc_version() >= 2 && gemm_tc_supported(g0) && gemm_tc_supported(g1)) {
+  const bool strided_w = (g0.ldw != 0 && g0.ldw != g0.K1 + g0.K2) || (g1.ldw != 0 && g1.ldw != g1.K1 + g1.K2);
+  if (group && !strided_w && mode == GEMM_BF16 && tc_version() >= 2 && gemm_tc_supported(g0) && gemm_tc_supported(g1)) {
     int r = FB_ERR_UNSUPPORTED;
     if (tc_version() == 3 && g0.M > 0 && g1.M > 0) {
       const GemmArgs two[2] = {g0, g1};

@@ -10,6 +10,7 @@ struct GemmArgs {
   const void* A = nullptr;  int lda = 0;  int K1 = 0;
   const void* A2 = nullptr; int lda2 = 0; int K2 = 0;   // optional second block, concatenated on K
   const void* W = nullptr;                               // [N, K1+K2], same element type as A
+  int ldw = 0;                                           // row stride of W (0 = K1 + K2); != K only on the multi-problem kernel (gemm_tc5.cu)
   const float* bias = nullptr;                           // [N] or null
   int act = FB_ACT_NONE;
   const float* res = nullptr; int ldres = 0;             // fp32 residual added after the activation

@@ -292,6 +292,7 @@ bool gemm_tc_shape_ok(int N, int K) { return N >= tc::BN_SEL && (N % tc::BN_SEL)
 
 bool gemm_tc_supported(const GemmArgs& g) {
   if (g.n_split > 0 && (g.n_split % 128)) return false;
+  if (g.ldw != 0 && (g.ldw % 8)) return false;            // (a strided W: only gemm_tc5.cu builds its tensor map with ldw)
   if (!gemm_tc_shape_ok(g.N, g.K1 + g.K2)) return false;
   if ((g.K1 % 64) || (g.K2 % 64) || g.K1 <= 0) return false;
   if ((g.lda % 8) || ((uintptr_t)g.A & 15) || ((uintptr_t)g.W & 15)) return false;

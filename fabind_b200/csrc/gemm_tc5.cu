@@ -372,6 +372,7 @@ int gemm_tc5_launch(const GemmArgs* g, int np, bool prefetch_w, cudaStream_t st)
     if (a.n_split > 0 && ((a.n_split % 64) || !a.C || !a.Cb)) return FB_ERR_UNSUPPORTED;
     if (a.res && !a.C && !a.Cb) return FB_ERR_UNSUPPORTED;
     if (a.res && a.n_split > 0) return FB_ERR_UNSUPPORTED;
+    if (a.ldw != 0 && (a.ldw < a.K1 + a.K2 || (a.ldw % 8))) return FB_ERR_UNSUPPORTED;
   }
   static_assert(Smem::TOTAL <= 232448, "shared memory budget");
   static_assert(sizeof(Params) <= 4096, "kernel parameter budget");
@@ -400,7 +401,7 @@ int gemm_tc5_launch(const GemmArgs* g, int np, bool prefetch_w, cudaStream_t st)
     } else {
       p.a2[i] = p.a[i];
     }
-    if (!tc_make_map(&p.w[i], a.W, (uint64_t)a.N, (uint64_t)K, (uint64_t)K, BN)) return FB_ERR_CUDA;
+    if (!tc_make_map(&p.w[i], a.W, (uint64_t)a.N, (uint64_t)K, (uint64_t)(a.ldw > 0 ? a.ldw : K), BN)) return FB_ERR_CUDA;
     p.c[i] = p.cb[i] = p.res[i] = p.a[i];   // placeholders for absent operands (never dereferenced)
     const int nc = a.n_split > 0 ? a.n_split : a.N, ncb = a.n_split > 0 ? a.N - a.n_split : a.N;
     if (a.C && !tc_make_map_out(&p.c[i], a.C, true, (uint64_t)a.M, (uint64_t)nc, (uint64_t)a.ldc)) return FB_ERR_CUDA;

@@ -232,6 +232,10 @@ typedef struct fb_gemm_params {
    * tile on tcgen05 (optional: without it such shapes return FB_ERR_UNSUPPORTED).  All outputs are fp32 (Cb too, under n_split). */
   void* split_ws; size_t split_ws_bytes; const float* W_f32;
   int32_t n_split;      /* >0: columns < n_split go to C, the rest to Cb at column n - n_split (multiple of 128) */
+  /* ABI 6: row stride of W in elements (0 = K1 + K2, a contiguous [N, K] weight).  A strided W -- a K-range of a wider matrix: the
+   * row-split weight gradients of the training step, dW = sum over row chunks of dY_c^T X_c -- is served by fb_gemm_multi's tcgen05
+   * kernel only (bf16 mode, multiple of 8); every other path returns FB_ERR_UNSUPPORTED rather than ignore it. */
+  int32_t ldw;
 } fb_gemm_params;
 /* fp32 rows -> three bf16 planes, dst[m, p*K + k] (p = 0..2) with src = p0 + p1 + p2 to 2^-27: the operand format of the split modes */
 int32_t fb_split_rows(const float* src, int32_t ld, int32_t M, int32_t K, void* dst, void* stream);

@@ -33,3 +33,24 @@ def test_transposed_twins_match_torch(hidden, layers, flavour):
         assert torch.equal(t, want), name
         seen += 1
     assert seen > 10 and base_elems(hidden, layers, flavour) <= n
+
+
+def test_row_split_weight_gradient_matches_torch():
+    """backward.gemm_wgrad on tcgen05: the reduction over the rows split into independent problems of one multi-problem launch
+    (strided W operand, fb_gemm_params.ldw) against dY^T X in fp32 on bf16-rounded operands"""
+    old = bw.PRECISION
+    bw.PRECISION = "bf16"
+    try:
+        g = torch.Generator().manual_seed(5)
+        for M, N, K in [(44904, 512, 512), (9000, 128, 512), (4100, 512, 640), (3000, 512, 512)]:
+            dY = torch.randn(M, N, generator=g).cuda()
+            X = torch.randn(M, K, generator=g).cuda()
+            got = bw.gemm_wgrad(dY, X)
+            want = dY.to(torch.bfloat16).float().t() @ X.to(torch.bfloat16).float()
+            torch.cuda.synchronize()
+            assert got.shape == (N, K)
+            assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max()), (M, N, K)
+            acc = bw.gemm_wgrad(dY, X, out=got.clone())
+            assert float((acc - 2 * want).abs().max()) <= 4e-3 * float(want.abs().max())
+    finally:
+        bw.PRECISION = old
