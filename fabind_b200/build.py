@@ -54,7 +54,8 @@ def build(force=False, verbose=False, diag=False):
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + FLAGS + [f"-DFB_SOURCE_HASH={source_hash()}LL"] + (["-DFB_DIAG"] if diag else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + FLAGS + [f"-DFB_SOURCE_HASH={source_hash()}LL"] + (["-DFB_DIAG"] if diag else []) + os.environ.get("FB_EXTRA_NVCC_FLAGS", "").split() + \
+              ["-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

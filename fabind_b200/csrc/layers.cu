@@ -304,6 +304,43 @@ __device__ __forceinline__ void gcl_coord_row(int rn, int lo, int hi, int lane, 
   }
 }
 
+// The same update for a HIGH-DEGREE row by a whole CTA: every thread fetches the terms of one edge (the dependent loads: row-dot
+// partials, column index, neighbour coordinates) into shared memory, then one warp folds them in gcl_coord_row's order -- the FMA chain
+// per lane and the shuffle tree are the same, so the result is bit-identical; what changes is that the 201 edges of a pocket's global
+// node cost one round of global-memory latency instead of seven.  Block-wide (contains barriers); stage holds 4 floats per edge.
+__device__ __forceinline__ void gcl_coord_row_staged(int rn, int lo, int hi, const int* __restrict__ ecol, const float* __restrict__ dot,
+                                                     int dot_tiles, int dot_stride, const float* __restrict__ x, float cmax,
+                                                     float* __restrict__ x_out, float* __restrict__ stage) {
+  const float xr0 = x[3 * rn], xr1 = x[3 * rn + 1], xr2 = x[3 * rn + 2];
+  for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < dot_tiles; ++k) s += dot[(size_t)k * dot_stride + e];
+    const int c = ecol[e];
+    float* q = stage + 4 * (e - lo);
+    q[0] = xr0 - x[3 * c]; q[1] = xr1 - x[3 * c + 1]; q[2] = xr2 - x[3 * c + 2]; q[3] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int e = lo + lane; e < hi; e += 32) {
+      const float* q = stage + 4 * (e - lo);
+      const float sv = q[3];
+      ax = fmaf(q[0], sv, ax);
+      ay = fmaf(q[1], sv, ay);
+      az = fmaf(q[2], sv, az);
+    }
+    ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+    if (lane == 0) {
+      const float cnt = fmaxf((float)(hi - lo), 1.0f);
+      x_out[3 * rn] = xr0 + fminf(fmaxf(ax / cnt, -cmax), cmax);
+      x_out[3 * rn + 1] = xr1 + fminf(fmaxf(ay / cnt, -cmax), cmax);
+      x_out[3 * rn + 2] = xr2 + fminf(fmaxf(az / cnt, -cmax), cmax);
+    }
+  }
+  __syncthreads();
+}
+
 // CTA = 4 nodes x 64 feature lanes (8 features = one 16-byte load per lane and edge row).  The rows of a
 // node are contiguous in M (edges are in CSR order), so the common case is a short streaming reduction with
 // no shared memory; the few high-degree nodes (global nodes) are then reduced by all 256 threads.
@@ -328,9 +365,9 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
     if (rk >= N || hd.node_cplx[rk] != b) return;     // this complex has no node on that side
     const int lk = rowptr[rk], hk = rowptr[rk + 1];
     if (hk - lk <= GN_BIG) return;            // an ordinary row: its own CTA takes it
-    // coordinates: ONE warp, the very arithmetic of the ordinary path (bit-identical results whichever CTA takes the row), while the
-    // other 31 warps already gather the feature rows
-    if (threadIdx.x < 32) gcl_coord_row(rk, lk, hk, lane, ecol, dot, dot_tiles, dot_stride, x, cmax, x_out);
+    // coordinates: the arithmetic of the ordinary path (bit-identical results whichever CTA takes the row), staged by the whole CTA
+    if (4 * (hk - lk) <= G * H) gcl_coord_row_staged(rk, lk, hk, ecol, dot, dot_tiles, dot_stride, x, cmax, x_out, part);
+    else if (threadIdx.x < 32) gcl_coord_row(rk, lk, hk, lane, ecol, dot, dot_tiles, dot_stride, x, cmax, x_out);
     if (agg == nullptr) return;
     for (int f0 = t * 8; f0 < H; f0 += 512) {
       float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -365,6 +402,8 @@ __global__ void __launch_bounds__(1024, 2) gcl_node_kernel(int N, int H, const i
   if (r < N) { lo = s_rp[grp]; hi = s_rp[grp + 1]; }
   const bool head_owned = s_head[grp] != 0;
   // coordinate part: first warp of each group, lanes over edges
+  // (the staged form for high-degree rows INSIDE an ordinary CTA -- the global rows of the compact moving-rows launches -- was measured
+  // slower: 9.86 against 9.60 ms per step on the same box; they stay on the one-warp routine)
   if (r < N && t < 32 && !head_owned) gcl_coord_row(rmap ? rmap[r] : r, lo, hi, lane, ecol, dot, dot_tiles, dot_stride, x, cmax, x_out);
   if (agg == nullptr) return;
 #ifdef FB_DIAG
