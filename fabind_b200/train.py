@@ -168,6 +168,8 @@ def _forward_half(model, fa, prev_coords=None, edge_lists=None, state_dict=None,
     cfg = model._cfg
     H, L, flavour = cfg["hidden"], cfg["n_layers"], int(cfg.get("flavour", 0))
     n_iter = cfg["n_iter"] if n_iter is None else int(n_iter)
+    if fa["X"].dim() != 3 or fa["X"].shape[1] != 1:
+        raise ValueError("fabind_b200.train: X must be [N, 1, 3] (n_channel == 1, the published configuration)")
     if dropout is not None and dropout[0] > 0 and flavour == 1:
         raise NotImplementedError("fabind_b200.train: the FABind+ reverse pass carries no dropout masks")
     dev = fa["H"].device
